@@ -1,0 +1,163 @@
+/*
+ * dynamicemb_b200.h — C ABI of the B200-native DynamicEmb hot path (librecsys_b200.so).
+ *
+ * Drop-in boundary: these entry points are what the reference's pybind module
+ * `dynamicemb_extensions` (corelib/dynamicemb/src/module_bind.cu:22-43) provides to the Python
+ * package, re-cut as plain C: raw DEVICE pointers + sizes, a `cudaStream_t` passed as `void*`,
+ * no torch types, no allocation inside (callers pass workspaces sized by the *_workspace_bytes
+ * queries), no exceptions.  Every function returns 0 on success, a negative DEMB_ERR_* code, or
+ * -(cudaError_t) for a CUDA failure.  All work is enqueued on `stream`; nothing synchronises.
+ * Paths below are relative to /root/reference/corelib/dynamicemb/.
+ *
+ * Table image (byte-compatible with the reference, src/table_operation/types.cuh:242-284 and
+ * dynamicemb/scored_hashtable.py:378-425): `storage` holds num_buckets buckets of
+ * C=bucket_capacity slots (C % 16 == 0); bucket = keys[C] u64 | digests[C] u8 | scores[C][num_scores] u64.
+ * `table_bucket_offsets[T+1]` (device, int64) gives each logical table's first global bucket.
+ * Slot indices returned/accepted are table-local: (bucket - table_first_bucket) * C + position
+ * (src/table_operation/kernels.cuh:149).
+ */
+#ifndef DYNAMICEMB_B200_H_
+#define DYNAMICEMB_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEMB_ERR_ARG (-1000)
+#define DEMB_ERR_WORKSPACE (-1001)
+
+/* ScorePolicyType, src/table_operation/score.cuh:30-42 */
+#define DEMB_POLICY_CONST 0
+#define DEMB_POLICY_ASSIGN 1
+#define DEMB_POLICY_ACCUMULATE 2
+#define DEMB_POLICY_GLOBAL_TIMER 3
+#define DEMB_POLICY_LRU_LFU 4
+/* InsertResult, src/table_operation/types.cuh:52-61 (success <=> value <= EVICT) */
+#define DEMB_INSERT 0
+#define DEMB_RECLAIM 1
+#define DEMB_ASSIGN 2
+#define DEMB_EVICT 3
+#define DEMB_DUPLICATED 4
+#define DEMB_BUSY 5
+#define DEMB_ILLEGAL 6
+#define DEMB_INIT 7
+/* output dtypes */
+#define DEMB_F32 0
+#define DEMB_F16 1
+#define DEMB_BF16 2
+/* initializer modes, dynamicemb/types.py DynamicEmbInitializerMode / src/initializer.cuh:24-170 */
+#define DEMB_INIT_NORMAL 0
+#define DEMB_INIT_TRUNCATED_NORMAL 1
+#define DEMB_INIT_UNIFORM 2
+#define DEMB_INIT_DEBUG 3
+#define DEMB_INIT_CONSTANT 4
+/* optimizers, src/optimizer_kernel.cuh:41-404 */
+#define DEMB_OPT_NONE 0
+#define DEMB_OPT_SGD 1
+#define DEMB_OPT_ADAM 2
+#define DEMB_OPT_ADAGRAD 3
+#define DEMB_OPT_ROWWISE_ADAGRAD 4
+
+/* ---- hash table (replaces src/table_operation/{lookup,insert,insert_and_evict,erase,export_batch,bucketize}.cu) ---- */
+
+/* scored_hashtable.py:476-496 _init_table: keys=~0, digests=digest(~0), scores=0 */
+int demb_table_init(void* storage, int64_t num_buckets, int64_t bucket_capacity, int num_scores, void* stream);
+
+/* table_lookup (src/table_operation/table.cuh:68, kernels.cuh:83-187).  keys[n] u64/i64, table_ids[n] (nullable => 0),
+ * score_in[n] (ASSIGN/ACCUMULATE/LRU_LFU), timestamp: GLOBAL_TIMER score (0 => read %globaltimer per key as the
+ * reference does).  Outputs founds[n] (u8, nullable), indices[n] (slot or -1), score_out[n] (nullable). */
+int demb_table_lookup(void* storage, const int64_t* table_bucket_offsets, int64_t bucket_capacity, int num_scores, int64_t n,
+                      const void* keys, const int64_t* table_ids, int policy, const uint64_t* score_in, uint64_t timestamp,
+                      uint8_t* founds, int64_t* indices, int64_t* score_out, void* stream);
+
+/* table_insert / table_insert_and_evict (table.cuh:81-130, kernels.cuh:189-567).  Keys must be unique per call.
+ * Always deterministic: equivalent to the reference under DEMB_DETERMINISM_MODE (scored_hashtable.py:1451-1640):
+ * keys ordered by (global bucket, key [signed if key_is_signed]) and inserted one per bucket at a time.
+ * results[n] u8 InsertResult (nullable), indices[n] slot or -1, score_out[n] (nullable).
+ * Evicted records (EVICT or BUSY, kernels.cuh:522-556) are appended at atomically claimed offsets of
+ * evicted_*[>=n] when evicted_count (device u64, caller zeroes it) is non-null. */
+int64_t demb_table_insert_workspace_bytes(int64_t n);
+int demb_table_insert(void* storage, const int64_t* table_bucket_offsets, int64_t bucket_capacity, int num_scores, int64_t num_buckets_total,
+                      int32_t* bucket_sizes, int64_t n, const void* keys, const int64_t* table_ids, int policy, const uint64_t* score_in,
+                      uint64_t timestamp, const int32_t* ref_counter, int key_is_signed, uint8_t* results, int64_t* indices,
+                      int64_t* score_out, uint64_t* evicted_count, void* evicted_keys, int64_t* evicted_scores, int64_t* evicted_indices,
+                      int64_t* evicted_table_ids, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* table_erase (table.cuh:132, kernels.cuh:587-652): slot -> ReclaimKey, digest -> empty, score word 0 -> 0 */
+int demb_table_erase(void* storage, const int64_t* table_bucket_offsets, int64_t bucket_capacity, int num_scores, int32_t* bucket_sizes,
+                     int64_t n, const void* keys, const int64_t* table_ids, int64_t* indices, void* stream);
+
+/* table_update_counter_with_layout (insert_and_evict.cu:27-60): ref_counter[bucket_off[tid]*C + slot] += delta; slot<0 skipped */
+int demb_counter_update(int32_t* ref_counter, const int64_t* slot_indices, const int64_t* table_ids, const int64_t* table_bucket_offsets,
+                        int64_t bucket_capacity, int64_t n, int delta, void* stream);
+
+/* table_export_batch (export_batch.cu, kernels.cuh:654-708): compact valid (key, score[score_word], table-local slot) of global
+ * slots [slot_begin, slot_end); d_counter (device u64) is the running output cursor. */
+int demb_table_export(void* storage, const int64_t* table_bucket_offsets, int64_t bucket_capacity, int num_scores, int64_t slot_begin,
+                      int64_t slot_end, int64_t table_slot_begin, uint64_t threshold, int use_threshold, int score_word,
+                      uint64_t* d_counter, void* keys_out, uint64_t* scores_out, int64_t* indices_out, void* stream);
+
+/* ---- dedup (replaces src/unique_op.cu, src/index_calculation.cu:237) ---- */
+/* get_table_range: table_range[t] = offsets[feature_offsets[t] * batch_size], t in [0, T] */
+int demb_get_table_range(const int64_t* offsets, const int64_t* feature_offsets, int num_tables, int64_t batch_size, int64_t* table_range,
+                         void* stream);
+/* segmented_unique_cuda (unique_op.cu:484): per-table dedup of keys[n] (grouped by table via table_range[T+1], nullable if T==1).
+ * unique_keys in first-occurrence order (deterministic; the reference's order is racy), reverse_indices[n] id->unique idx,
+ * table_offsets[T+1], freq_out (count or sum of freq_in per unique; nullable), unique_table_ids (nullable; = expand_table_ids),
+ * num_unique device scalar (nullable). */
+int64_t demb_segmented_unique_workspace_bytes(int64_t n, int num_tables);
+int demb_segmented_unique(int64_t n, const void* keys, const int64_t* table_range, int num_tables, const int64_t* freq_in, void* unique_keys,
+                          int64_t* reverse_indices, int64_t* table_offsets, int64_t* freq_out, int64_t* unique_table_ids,
+                          int64_t* num_unique, void* workspace, int64_t workspace_bytes, void* stream);
+/* expand_table_ids_cuda (unique_op.cu:471,719) */
+int demb_expand_table_ids(const int64_t* table_offsets, int num_tables, int64_t n, int64_t* table_ids, void* stream);
+
+/* ---- rows (replaces src/lookup_forward.cu, lookup_backward.cu, dynamic_emb_op.cu, optimizer.cu, initializer.cu) ---- */
+/* Value table: fp32 rows `values[row * value_dim + 0..]` = [embedding(emb_dim) | optimizer state] (key_value_table.py:346-356);
+ * global row of (table t, slot s) = row_base[t] + s.  emb_dim % 4 == 0, value_dim % 4 == 0, emb_dim <= 1024. */
+
+/* FUSED forward for ids already in the table (eval path, batched_dynamicemb_function.py:836 dynamicemb_eval_forward;
+ * fuses table_lookup + load_from_flat + gather_embedding[_pooled]).  combiner -1: sequence, out[n, D];
+ * 0 SUM / 1 MEAN: pooled over bags given by offsets[F*B+1] (feature-major), out[B, F*D].  Absent ids contribute
+ * `absent_value` (sequence) or nothing (pooled).  founds[n]/slots_out[n] optional. */
+int demb_lookup_forward(void* storage, const int64_t* table_bucket_offsets, int64_t bucket_capacity, int num_scores, const float* values,
+                        int64_t value_dim, int emb_dim, const int64_t* row_base, int64_t n, const void* keys, const int64_t* table_range,
+                        int num_tables, const int64_t* offsets, int64_t batch_size, int num_features, int combiner, void* out, int out_dtype,
+                        float absent_value, uint8_t* founds, int64_t* slots_out, void* stream);
+/* training forward after prefetch (DynamicEmbeddingFunction.forward, batched_dynamicemb_function.py:1044: load_from_flat +
+ * gather_embedding[_pooled] in one pass): row of id i = rows[inverse[i]] (inverse nullable => rows[i]); rows<0 => zeros */
+int demb_gather_forward(const float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* rows, const int64_t* inverse,
+                        const int64_t* offsets, int64_t batch_size, int num_features, int combiner, void* out, int out_dtype, void* stream);
+int demb_rows_from_slots(int64_t n, const int64_t* slots, const int64_t* table_ids, const int64_t* row_base, int64_t* rows, void* stream);
+/* initializer + store_to_flat fused (initializer.cu, dynamic_emb_op.cu:400-490): values[rows[i]] = [init(keys[i]) | state_init];
+ * params: UNIFORM(p0=lower,p1=upper) NORMAL(p0=mean,p1=std) TRUNCATED_NORMAL(+p2=lower,p3=upper) CONSTANT(p0) DEBUG(key%100000).
+ * only_if[n] (nullable) masks rows; emb_out[n,D] (nullable) also receives the embedding. */
+int demb_init_rows(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* rows, const void* keys, int mode, float p0, float p1,
+                   float p2, float p3, uint64_t seed, float state_init, const uint8_t* only_if, float* emb_out, void* stream);
+/* load_from_flat_table / store_to_flat_table (dynamic_emb_op.cu:295-490): copy `width` floats per row table<->dense */
+int demb_copy_rows(float* values, int64_t value_dim, int width, int64_t n, const int64_t* rows, float* dense, int64_t dense_stride, int to_table,
+                   void* stream);
+/* FUSED backward (DynamicEmbeddingFunction.backward, :1194: reduce_grads + fused_update_for_flat_table).  See demb_rows.cu. */
+int64_t demb_backward_workspace_bytes(int64_t n, int emb_dim);
+int demb_backward(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound, const int64_t* rows,
+                  const float* grads, int64_t grad_stride, const int64_t* offsets, int64_t batch_size, int num_features, int combiner,
+                  int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
+                  float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, void* stream);
+/* {sgd,adam,adagrad,rowwise_adagrad}_update_for_flat_table (optimizer.cu): dense grads[n, D] -> rows */
+int demb_update_rows(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* rows, const float* grads, int64_t grad_stride,
+                     int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
+                     float bias_correction2, void* stream);
+
+/* ---- row-wise sharding input dist (replaces src/sparse_block_bucketize_features.cu:372) ---- */
+int64_t demb_bucketize_workspace_bytes(int64_t num_slots, int world_size);
+/* dist_type_per_feature[F]: 0 continuous, 1 roundrobin, 2 hash_roundrobin; block_sizes[F].  new_lengths[W*S] rank-major. */
+int demb_block_bucketize_sparse_features(int64_t num_slots, int64_t batch_size, int world_size, const int64_t* offsets, const int64_t* ids,
+                                         const int64_t* block_sizes, const int32_t* dist_type_per_feature, const float* weights,
+                                         int64_t* new_lengths, int64_t* new_ids, int64_t* unbucketize_permute, float* new_weights,
+                                         void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,622 @@
+// DynamicEmb row path — sm_100a kernels + C-ABI: fused probe+gather(+pool) forward, row init,
+// gather-by-slot, and the fused backward (segmented gradient reduce + sparse optimizer row update).
+//
+// Replaces reference corelib/dynamicemb/src/{lookup_forward.cu,lookup_kernel.cuh,lookup_backward.cu,
+// dynamic_emb_op.cu (load/store flat table, gather_embedding[_pooled], reduce_grads),
+// optimizer.cu, optimizer_kernel.cuh, initializer.cu}.  The reference runs probe -> flagged_compact ->
+// load_from_flat -> gather as four passes with a staging copy of every unique row; here one warp
+// probes 32 ids at a time (32 independent 16-B digest loads in flight) and then streams each found
+// 512-B row straight from the value table into the output (or the bag accumulator) with 16-B
+// no-allocate loads / streaming stores, 8 rows in flight per warp.  Backward sorts (unique idx, grad
+// row) pairs once, then fixed 32-row tiles reduce and apply the optimizer in place in the same kernel.
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "../../include/dynamicemb_b200.h"
+#include "demb_common.cuh"
+
+using namespace demb;
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kBlock = kWarpsPerBlock * 32;
+constexpr int kMaxChunks = 8;   // D <= 1024 (reference limit, lookup_kernel.cuh copy_multi_to_one)
+
+inline int warp_grid(int64_t warps) {
+  int64_t blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  int64_t cap = 148 * 8 * 4;   // persistent-ish: multiple of 148 SMs x 8 resident CTAs
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+__device__ __forceinline__ int table_of(const int64_t* __restrict__ range, int T, int64_t i) {
+  int lo = 0, hi = T;
+  while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (range[mid] <= i) lo = mid; else hi = mid; }
+  return lo;
+}
+
+// ---- typed output store ---------------------------------------------------------------------------
+__device__ __forceinline__ void store_out4(void* out, int dtype, int64_t elem_off, float4 v) {
+  if (dtype == DEMB_F32) { st_cs_f4(reinterpret_cast<float*>(out) + elem_off, v); }
+  else if (dtype == DEMB_BF16) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 p; p.x = *reinterpret_cast<uint32_t*>(&a); p.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + elem_off) = p;
+  } else {
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 p; p.x = *reinterpret_cast<uint32_t*>(&a); p.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + elem_off) = p;
+  }
+}
+
+// Row source for the forward kernels: either probe the hash table per id (eval / inference path,
+// `rows`==nullptr) or read a precomputed global row index through `inverse` (training path after
+// prefetch: rows[unique idx], inverse[id] = unique idx).
+struct RowSrc {
+  Table t;
+  const uint64_t* keys;       // probe mode
+  const int64_t* table_range; // probe mode, ids grouped by table; nullable when T==1
+  int T;
+  const int64_t* row_base;    // [T] first value row of each table, nullable (0)
+  const int64_t* rows;        // indirect mode: global value row per unique (or per id when inverse==nullptr), -1 = absent
+  const int64_t* inverse;     // indirect mode, nullable
+  uint8_t* founds;            // optional outputs (probe mode)
+  int64_t* slots_out;
+};
+__device__ __forceinline__ int64_t resolve_row(const RowSrc& s, int64_t i) {
+  if (s.rows) { int64_t u = s.inverse ? s.inverse[i] : i; return s.rows[u]; }
+  const uint64_t key = s.keys[i];
+  const int tid = (s.T > 1 && s.table_range) ? table_of(s.table_range, s.T, i) : 0;
+  Locus L = locate(s.t, key, tid);
+  int64_t slot = -1;
+  if (L.cap > 0) {
+    int64_t it = probe_thread(s.t, s.t.bucket(L.bucket), key, L.h, nullptr);
+    if (it >= 0) slot = (L.bucket - L.bkt_begin) * s.t.C + it;
+  }
+  if (s.founds) s.founds[i] = slot >= 0;
+  if (s.slots_out) s.slots_out[i] = slot;
+  return slot < 0 ? -1 : (s.row_base ? s.row_base[tid] : 0) + slot;
+}
+
+// ---- forward, sequence mode: out[i,:] = values[row(i), :D] -------------------------------------------
+// A12 + A11(load) + A4 fused.  Absent rows produce `absent_value` (reference eval default: zeros).
+template <int U>
+__global__ void __launch_bounds__(kBlock) forward_seq_kernel(RowSrc s, const float* __restrict__ values, int64_t vdim, int D, int64_t n,
+                                                             void* __restrict__ out, int out_dtype, float absent_value) {
+  const int lane = threadIdx.x & 31;
+  const int D4 = D >> 2;
+  const int64_t tiles = (n + 31) >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); tile < tiles; tile += wstride) {
+    const int64_t base = tile << 5;
+    const int cnt = (int)((n - base) < 32 ? (n - base) : 32);
+    int64_t row = -1;
+    if (lane < cnt) row = resolve_row(s, base + lane);
+    for (int j = 0; j < cnt; j += U) {
+      int64_t r[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) r[u] = __shfl_sync(0xffffffffu, row, (j + u) & 31);
+      for (int c = lane; c < D4; c += 32) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (j + u < cnt && r[u] >= 0) v[u] = ld_nc_f4(values + r[u] * vdim + 4 * c);
+          else v[u] = make_float4(absent_value, absent_value, absent_value, absent_value);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (j + u < cnt) store_out4(out, out_dtype, (base + j + u) * (int64_t)D + 4 * c, v[u]);
+      }
+    }
+  }
+}
+
+// ---- forward, pooled mode: one warp per bag (feature f, sample b); ids feature-major (offsets index
+// f*B+b, lookup_forward.cu:53-59); out[b, f*D : (f+1)*D] = SUM or MEAN of the bag's rows, fp32
+// accumulation in id order (lookup_kernel.cuh:901-962).  A13 + A11 + A4 fused.
+template <int NCHUNK>
+__global__ void __launch_bounds__(kBlock) forward_pool_kernel(RowSrc s, const float* __restrict__ values, int64_t vdim, int D, int64_t B, int F,
+                                                              const int64_t* __restrict__ offsets, int combiner, void* __restrict__ out,
+                                                              int out_dtype, int64_t total_D) {
+  const int lane = threadIdx.x & 31;
+  const int D4 = D >> 2;
+  const int64_t bags = B * (int64_t)F;
+  const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); g < bags; g += wstride) {
+    const int64_t f = g / B, b = g - f * B;
+    const int64_t beg = offsets[g], end = offsets[g + 1];
+    float4 acc[NCHUNK];
+#pragma unroll
+    for (int k = 0; k < NCHUNK; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t base = beg; base < end; base += 32) {
+      const int cnt = (int)((end - base) < 32 ? (end - base) : 32);
+      int64_t row = -1;
+      if (lane < cnt) row = resolve_row(s, base + lane);
+      constexpr int U = 4;
+      for (int j = 0; j < cnt; j += U) {
+        int64_t r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u] = __shfl_sync(0xffffffffu, row, (j + u) & 31);
+#pragma unroll
+        for (int k = 0; k < NCHUNK; ++k) {
+          const int c = lane + 32 * k;
+          if (c < D4) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              v[u] = (j + u < cnt && r[u] >= 0) ? ld_nc_f4(values + r[u] * vdim + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {   // in id order => bit-reproducible
+              acc[k].x = __fadd_rn(acc[k].x, v[u].x); acc[k].y = __fadd_rn(acc[k].y, v[u].y);
+              acc[k].z = __fadd_rn(acc[k].z, v[u].z); acc[k].w = __fadd_rn(acc[k].w, v[u].w);
+            }
+          }
+        }
+      }
+    }
+    if (combiner == 1 && end > beg) {
+      const float L = (float)(end - beg);
+#pragma unroll
+      for (int k = 0; k < NCHUNK; ++k) { acc[k].x = __fdiv_rn(acc[k].x, L); acc[k].y = __fdiv_rn(acc[k].y, L); acc[k].z = __fdiv_rn(acc[k].z, L); acc[k].w = __fdiv_rn(acc[k].w, L); }
+    }
+#pragma unroll
+    for (int k = 0; k < NCHUNK; ++k) {
+      const int c = lane + 32 * k;
+      if (c < D4) store_out4(out, out_dtype, b * total_D + f * (int64_t)D + 4 * c, acc[k]);
+    }
+  }
+}
+
+// ---- initializer + store (A10 + A11 store fused): values[row] = [init(key) | opt state] ---------------
+// Philox4x32-10 keyed by (seed, key): the value of a row depends only on (seed, key, column), not on
+// which thread or batch position initialises it (the reference draws from a pool of per-thread
+// curand states, initializer.cu:26-112, so its values depend on launch geometry).
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0,1)
+__device__ __forceinline__ void boxmuller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  float r = sqrtf(-2.0f * logf(u01(a))), th = 6.28318530717958647692f * u01(b);
+  z0 = r * cosf(th); z1 = r * sinf(th);
+}
+
+struct InitArgs { int mode; float p0, p1, p2, p3; uint64_t seed; };   // uniform(lower,upper) normal(mean,std) trunc(mean,std,lower,upper) const(value)
+
+__device__ __forceinline__ float4 init4(const InitArgs& a, uint64_t key, int c /*float4 chunk*/) {
+  if (a.mode == DEMB_INIT_CONSTANT) return make_float4(a.p0, a.p0, a.p0, a.p0);
+  if (a.mode == DEMB_INIT_DEBUG) { float v = (float)(key % 100000ull); return make_float4(v, v, v, v); }   // initializer.cuh:142-156
+  uint4 rnd = philox4x32(make_uint4((uint32_t)c, 0u, (uint32_t)key, (uint32_t)(key >> 32)), make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+  if (a.mode == DEMB_INIT_UNIFORM) {
+    float lo = a.p0, w = a.p1 - a.p0;
+    return make_float4(lo + w * u01(rnd.x), lo + w * u01(rnd.y), lo + w * u01(rnd.z), lo + w * u01(rnd.w));
+  }
+  float z[4];
+  boxmuller(rnd.x, rnd.y, z[0], z[1]); boxmuller(rnd.z, rnd.w, z[2], z[3]);
+  if (a.mode == DEMB_INIT_TRUNCATED_NORMAL) {
+    // resample from further Philox counters until inside [lower, upper] (initializer.cuh truncated normal rejects likewise)
+    uint32_t extra = 1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v = a.p0 + a.p1 * z[k];
+      while (v < a.p2 || v > a.p3) {
+        uint4 r2 = philox4x32(make_uint4((uint32_t)c, extra++ * 4u + (uint32_t)k, (uint32_t)key, (uint32_t)(key >> 32)), make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+        float y0, y1; boxmuller(r2.x, r2.y, y0, y1);
+        v = a.p0 + a.p1 * y0;
+        if (v < a.p2 || v > a.p3) v = a.p0 + a.p1 * y1;
+        if (extra > 64) { v = fminf(fmaxf(v, a.p2), a.p3); }
+      }
+      z[k] = (v - a.p0) / (a.p1 == 0.f ? 1.f : a.p1);
+    }
+  }
+  return make_float4(a.p0 + a.p1 * z[0], a.p0 + a.p1 * z[1], a.p0 + a.p1 * z[2], a.p0 + a.p1 * z[3]);
+}
+
+// warp per new row: rows[i] (global value row, <0 = skip), keys[i]; optional `emb_out[i,:D]` copy of the
+// initialised embedding (for non-admitted / eval-miss ids that are not stored).
+__global__ void __launch_bounds__(kBlock) init_rows_kernel(float* __restrict__ values, int64_t vdim, int D, int64_t n, const int64_t* __restrict__ rows,
+                                                           const uint64_t* __restrict__ keys, InitArgs a, float state_init,
+                                                           const uint8_t* __restrict__ only_if /*nullable: init only where !=0*/,
+                                                           float* __restrict__ emb_out) {
+  const int lane = threadIdx.x & 31;
+  const int D4 = D >> 2, V4 = (int)(vdim >> 2);
+  const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t i = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); i < n; i += wstride) {
+    if (only_if && !only_if[i]) continue;
+    const int64_t r = rows ? rows[i] : -1;
+    const uint64_t key = keys[i];
+    for (int c = lane; c < D4; c += 32) {
+      float4 v = init4(a, key, c);
+      if (r >= 0) st_f4(values + r * vdim + 4 * c, v);
+      if (emb_out) st_f4(emb_out + i * (int64_t)D + 4 * c, v);
+    }
+    if (r >= 0)
+      for (int c = D4 + lane; c < V4; c += 32) st_f4(values + r * vdim + 4 * c, make_float4(state_init, state_init, state_init, state_init));
+  }
+}
+
+// rows[i] = row_base[tid[i]] + slot[i]  (or -1)
+__global__ void rows_from_slots_kernel(int64_t n, const int64_t* __restrict__ slots, const int64_t* __restrict__ tids,
+                                       const int64_t* __restrict__ row_base, int64_t* __restrict__ rows) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t s = slots[i];
+    rows[i] = s < 0 ? -1 : ((row_base ? row_base[tids ? tids[i] : 0] : 0) + s);
+  }
+}
+
+// A11 standalone: copy [emb | state] rows between the value table and a dense [n, width] staging.
+__global__ void __launch_bounds__(kBlock) copy_rows_kernel(float* __restrict__ values, int64_t vdim, int width, int64_t n, const int64_t* __restrict__ rows,
+                                                           float* __restrict__ dense, int64_t dense_stride, int to_table) {
+  const int lane = threadIdx.x & 31;
+  const int W4 = width >> 2;
+  const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t i = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); i < n; i += wstride) {
+    const int64_t r = rows[i];
+    if (r < 0) {
+      if (!to_table) for (int c = lane; c < W4; c += 32) st_f4(dense + i * dense_stride + 4 * c, make_float4(0.f, 0.f, 0.f, 0.f));
+      continue;
+    }
+    for (int c = lane; c < W4; c += 32) {
+      if (to_table) st_f4(values + r * vdim + 4 * c, ld_f4(dense + i * dense_stride + 4 * c));
+      else st_f4(dense + i * dense_stride + 4 * c, ld_f4(values + r * vdim + 4 * c));
+    }
+  }
+}
+
+// ---- backward -----------------------------------------------------------------------------------------
+struct OptArgs { int type; float lr, eps, beta1, beta2, weight_decay, bc1, bc2; };
+
+// One row update, lane owns float4 chunk(s).  Formulas: optimizer_kernel.cuh:41-404 (IEEE fp32 here; the
+// reference compiles with --use_fast_math).  `g` holds the reduced gradient chunks of this lane.
+template <int NCHUNK>
+__device__ __forceinline__ void apply_row(const OptArgs& o, float* __restrict__ w, int D, const float4 (&g)[NCHUNK], int lane) {
+  const int D4 = D >> 2;
+  if (o.type == DEMB_OPT_SGD) {
+#pragma unroll
+    for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; if (c < D4) {
+      float4 x = ld_f4(w + 4 * c);
+      x.x -= o.lr * g[k].x; x.y -= o.lr * g[k].y; x.z -= o.lr * g[k].z; x.w -= o.lr * g[k].w;
+      st_f4(w + 4 * c, x); } }
+  } else if (o.type == DEMB_OPT_ADAGRAD) {
+#pragma unroll
+    for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; if (c < D4) {
+      float4 x = ld_f4(w + 4 * c), s = ld_f4(w + D + 4 * c);
+      s.x += g[k].x * g[k].x; s.y += g[k].y * g[k].y; s.z += g[k].z * g[k].z; s.w += g[k].w * g[k].w;
+      x.x -= o.lr * g[k].x / (sqrtf(s.x) + o.eps); x.y -= o.lr * g[k].y / (sqrtf(s.y) + o.eps);
+      x.z -= o.lr * g[k].z / (sqrtf(s.z) + o.eps); x.w -= o.lr * g[k].w / (sqrtf(s.w) + o.eps);
+      st_f4(w + D + 4 * c, s); st_f4(w + 4 * c, x); } }
+  } else if (o.type == DEMB_OPT_ADAM) {
+#pragma unroll
+    for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; if (c < D4) {
+      float4 x = ld_f4(w + 4 * c), m = ld_f4(w + D + 4 * c), v = ld_f4(w + 2 * D + 4 * c);
+      float* xp = &x.x; float* mp = &m.x; float* vp = &v.x; const float* gp = &g[k].x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        mp[e] = o.beta1 * mp[e] + (1.0f - o.beta1) * gp[e];
+        vp[e] = o.beta2 * vp[e] + (1.0f - o.beta2) * gp[e] * gp[e];
+        float mh = mp[e] / o.bc1, vh = vp[e] / o.bc2;
+        xp[e] -= o.lr * (mh / (sqrtf(vh) + o.eps) + o.weight_decay * xp[e]);
+      }
+      st_f4(w + D + 4 * c, m); st_f4(w + 2 * D + 4 * c, v); st_f4(w + 4 * c, x); } }
+  } else if (o.type == DEMB_OPT_ROWWISE_ADAGRAD) {
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; if (c < D4) ss += g[k].x * g[k].x + g[k].y * g[k].y + g[k].z * g[k].z + g[k].w * g[k].w; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+    float acc = w[D] + ss / (float)D;
+    __syncwarp();
+    if (lane == 0) w[D] = acc;
+    const float mult = o.lr / (sqrtf(acc) + o.eps);
+#pragma unroll
+    for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; if (c < D4) {
+      float4 x = ld_f4(w + 4 * c);
+      x.x -= mult * g[k].x; x.y -= mult * g[k].y; x.z -= mult * g[k].z; x.w -= mult * g[k].w;
+      st_f4(w + 4 * c, x); } }
+  }
+}
+
+struct BwdArgs {
+  const float* grads; int64_t grad_stride;   // row r of the gradient matrix is grads + r*grad_stride
+  int D; int pooled; int combiner; int64_t B; int F; const int64_t* offsets;   // pooled: row id = b*F+f, MEAN scale 1/len(bag f*B+b)
+  const int32_t* skey; const int32_t* sval; int64_t n;   // sorted (unique idx, gradient row id)
+  const int64_t* rows;      // unique idx -> global value row (<0: skip), nullable => emit only
+  float* values; int64_t vdim;
+  float* unique_grads;      // optional [n_unique, D] output of the reduced gradients (reduce_grads op), nullable
+  float* part_cont; float* part_start;   // [tiles, D] each
+  OptArgs opt;
+};
+
+template <int NCHUNK>
+__device__ __forceinline__ void finish_segment(const BwdArgs& a, int32_t u, const float4 (&acc)[NCHUNK], int lane) {
+  const int D4 = a.D >> 2;
+  if (a.unique_grads) {
+#pragma unroll
+    for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; if (c < D4) st_f4(a.unique_grads + (int64_t)u * a.D + 4 * c, acc[k]); }
+  }
+  if (a.rows && a.opt.type != DEMB_OPT_NONE) {
+    const int64_t r = a.rows[u];
+    if (r >= 0) apply_row<NCHUNK>(a.opt, a.values + r * a.vdim, a.D, acc, lane);
+  }
+}
+
+// Stage 1: warp per 32-row tile of the sorted pair list.  Segments (runs of equal unique idx) that lie
+// inside the tile are finished here (reduced gradient -> optimizer update in place).  A segment that
+// enters from the previous tile leaves its partial in part_cont[tile]; one that starts here and runs
+// past the tile end leaves it in part_start[tile].  Summation order is fixed: ascending sorted position
+// inside a tile, tiles in ascending order in stage 2 => bit-reproducible (oracle: oracle/dynamicemb.py).
+template <int NCHUNK>
+__global__ void __launch_bounds__(kBlock) backward_tiles_kernel(BwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int D4 = a.D >> 2;
+  const int64_t tiles = (a.n + 31) >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); tile < tiles; tile += wstride) {
+    const int64_t base = tile << 5;
+    const int cnt = (int)((a.n - base) < 32 ? (a.n - base) : 32);
+    int32_t myu = -1, myr = 0; float mys = 1.f;
+    if (lane < cnt) {
+      myu = a.skey[base + lane]; myr = a.sval[base + lane];
+      if (a.pooled && a.combiner == 1) {
+        int64_t b = myr / a.F, f = myr - b * a.F;
+        int64_t len = a.offsets[f * a.B + b + 1] - a.offsets[f * a.B + b];
+        mys = 1.0f / (float)len;                                   // lookup_backward.cu:209-241
+      }
+    }
+    const int32_t prev_u = base > 0 ? a.skey[base - 1] : -1;
+    const int32_t next_u = base + 32 < a.n ? a.skey[base + 32] : -2;
+    float4 acc[NCHUNK];
+#pragma unroll
+    for (int k = 0; k < NCHUNK; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool incoming = (__shfl_sync(0xffffffffu, myu, 0) == prev_u);
+    constexpr int U = 4;
+    for (int j = 0; j < cnt; j += U) {
+      int32_t uu[U + 1]; int32_t rr[U]; float sc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { uu[u] = __shfl_sync(0xffffffffu, myu, (j + u) & 31); rr[u] = __shfl_sync(0xffffffffu, myr, (j + u) & 31); sc[u] = __shfl_sync(0xffffffffu, mys, (j + u) & 31); }
+      uu[U] = __shfl_sync(0xffffffffu, myu, (j + U) & 31);
+      float4 v[U][NCHUNK];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int k = 0; k < NCHUNK; ++k) {
+          const int c = lane + 32 * k;
+          v[u][k] = (j + u < cnt && c < D4) ? ld_nc_f4(a.grads + (int64_t)rr[u] * a.grad_stride + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (j + u >= cnt) break;
+#pragma unroll
+        for (int k = 0; k < NCHUNK; ++k) {
+          acc[k].x = __fadd_rn(acc[k].x, __fmul_rn(v[u][k].x, sc[u])); acc[k].y = __fadd_rn(acc[k].y, __fmul_rn(v[u][k].y, sc[u]));
+          acc[k].z = __fadd_rn(acc[k].z, __fmul_rn(v[u][k].z, sc[u])); acc[k].w = __fadd_rn(acc[k].w, __fmul_rn(v[u][k].w, sc[u]));
+        }
+        const bool last_in_tile = (j + u == cnt - 1);
+        const int32_t nxt = last_in_tile ? next_u : ((u + 1 < U) ? uu[u + 1] : uu[U]);
+        if (nxt != uu[u]) {                       // segment ends at this row (really ends: next row differs)
+          if (incoming) {
+#pragma unroll
+            for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; if (c < D4) st_f4(a.part_cont + tile * a.D + 4 * c, acc[k]); }
+          } else {
+            finish_segment<NCHUNK>(a, uu[u], acc, lane);
+          }
+#pragma unroll
+          for (int k = 0; k < NCHUNK; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          incoming = false;
+        } else if (last_in_tile) {                // runs past the tile end
+          float* dst = incoming ? a.part_cont : a.part_start;
+#pragma unroll
+          for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; if (c < D4) st_f4(dst + tile * a.D + 4 * c, acc[k]); }
+        }
+      }
+    }
+  }
+}
+
+// Stage 2: warp per tile that owns a START partial: total = start[tile] + cont[tile+1] + ... while the
+// following tiles begin with the same unique idx; then finish the segment.
+template <int NCHUNK>
+__global__ void __launch_bounds__(kBlock) backward_spans_kernel(BwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int D4 = a.D >> 2;
+  const int64_t tiles = (a.n + 31) >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); tile + 1 < tiles; tile += wstride) {
+    const int64_t base = tile << 5;
+    const int32_t u = a.skey[base + 31];
+    if (a.skey[base + 32] != u) continue;                       // last segment does not spill
+    if (a.skey[base] == u && base > 0 && a.skey[base - 1] == u) continue;   // whole tile is a continuation
+    float4 acc[NCHUNK];
+#pragma unroll
+    for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; acc[k] = c < D4 ? ld_f4(a.part_start + tile * a.D + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f); }
+    for (int64_t t2 = tile + 1; t2 < tiles && a.skey[t2 << 5] == u; ++t2) {
+#pragma unroll
+      for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; if (c < D4) {
+        float4 p = ld_f4(a.part_cont + t2 * a.D + 4 * c);
+        acc[k].x = __fadd_rn(acc[k].x, p.x); acc[k].y = __fadd_rn(acc[k].y, p.y); acc[k].z = __fadd_rn(acc[k].z, p.z); acc[k].w = __fadd_rn(acc[k].w, p.w); } }
+    }
+    finish_segment<NCHUNK>(a, u, acc, lane);
+  }
+}
+
+// sort keys / payload for backward: key = inverse[i] (unique idx); payload = gradient row id
+// (sequence: i; pooled: b*F+f of the bag holding id i — generate_gather_ids_pooled_kernel, lookup_backward.cu).
+__global__ void backward_pairs_kernel(int64_t n, const int64_t* __restrict__ inverse, int pooled, int64_t B, int F, const int64_t* __restrict__ offsets,
+                                      int32_t* __restrict__ key, int32_t* __restrict__ val) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    key[i] = (int32_t)inverse[i];
+    if (!pooled) { val[i] = (int32_t)i; continue; }
+    int64_t lo = 0, hi = B * F;   // bag g with offsets[g] <= i < offsets[g+1]
+    while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (offsets[mid] <= i) lo = mid; else hi = mid; }
+    int64_t f = lo / B, b = lo - f * B;
+    val[i] = (int32_t)(b * F + f);
+  }
+}
+
+// A15 standalone: warp per unique row with a dense [n, D] gradient.
+template <int NCHUNK>
+__global__ void __launch_bounds__(kBlock) update_rows_kernel(float* __restrict__ values, int64_t vdim, int D, int64_t n, const int64_t* __restrict__ rows,
+                                                             const float* __restrict__ grads, int64_t grad_stride, OptArgs o) {
+  const int lane = threadIdx.x & 31;
+  const int D4 = D >> 2;
+  const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t i = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); i < n; i += wstride) {
+    const int64_t r = rows[i];
+    if (r < 0) continue;
+    float4 g[NCHUNK];
+#pragma unroll
+    for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; g[k] = c < D4 ? ld_nc_f4(grads + i * grad_stride + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f); }
+    apply_row<NCHUNK>(o, values + r * vdim, D, g, lane);
+  }
+}
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+inline int nchunk_of(int D) { return (D / 4 + 31) / 32; }
+
+}  // namespace
+
+#define DISPATCH_NCHUNK(D, ...)                                          \
+  switch (nchunk_of(D)) {                                                \
+    case 1: { constexpr int NC = 1; __VA_ARGS__; break; }                \
+    case 2: { constexpr int NC = 2; __VA_ARGS__; break; }                \
+    case 3: case 4: { constexpr int NC = 4; __VA_ARGS__; break; }        \
+    default: { constexpr int NC = 8; __VA_ARGS__; break; }               \
+  }
+
+extern "C" {
+
+static int check_dims(int D, int64_t vdim) { return (D <= 0 || (D & 3) || D > 128 * kMaxChunks || (vdim & 3) || vdim < D) ? DEMB_ERR_ARG : 0; }
+
+int demb_lookup_forward(void* storage, const int64_t* table_bucket_offsets, int64_t bucket_capacity, int num_scores, const float* values,
+                        int64_t value_dim, int emb_dim, const int64_t* row_base, int64_t n, const void* keys, const int64_t* table_range,
+                        int num_tables, const int64_t* offsets, int64_t batch_size, int num_features, int combiner, void* out, int out_dtype,
+                        float absent_value, uint8_t* founds, int64_t* slots_out, void* stream) {
+  if (check_dims(emb_dim, value_dim)) return DEMB_ERR_ARG;
+  RowSrc s{Table{(uint8_t*)storage, table_bucket_offsets, bucket_capacity, num_scores}, (const uint64_t*)keys, table_range, num_tables, row_base,
+           nullptr, nullptr, founds, slots_out};
+  if (combiner < 0) {
+    if (n <= 0) return 0;
+    forward_seq_kernel<8><<<warp_grid((n + 31) / 32), kBlock, 0, (cudaStream_t)stream>>>(s, values, value_dim, emb_dim, n, out, out_dtype, absent_value);
+  } else {
+    if (batch_size <= 0 || num_features <= 0) return 0;
+    if (emb_dim > 512) return DEMB_ERR_ARG;
+    int64_t bags = batch_size * num_features;
+    DISPATCH_NCHUNK(emb_dim, forward_pool_kernel<NC><<<warp_grid(bags), kBlock, 0, (cudaStream_t)stream>>>(
+                                 s, values, value_dim, emb_dim, batch_size, num_features, offsets, combiner, out, out_dtype,
+                                 (int64_t)num_features * emb_dim));
+  }
+  DEMB_CHECK_LAST();
+  return 0;
+}
+
+int demb_gather_forward(const float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* rows, const int64_t* inverse,
+                        const int64_t* offsets, int64_t batch_size, int num_features, int combiner, void* out, int out_dtype, void* stream) {
+  if (check_dims(emb_dim, value_dim)) return DEMB_ERR_ARG;
+  RowSrc s{Table{nullptr, nullptr, 0, 1}, nullptr, nullptr, 1, nullptr, rows, inverse, nullptr, nullptr};
+  if (combiner < 0) {
+    if (n <= 0) return 0;
+    forward_seq_kernel<8><<<warp_grid((n + 31) / 32), kBlock, 0, (cudaStream_t)stream>>>(s, values, value_dim, emb_dim, n, out, out_dtype, 0.f);
+  } else {
+    if (batch_size <= 0 || num_features <= 0) return 0;
+    if (emb_dim > 512) return DEMB_ERR_ARG;
+    int64_t bags = batch_size * num_features;
+    DISPATCH_NCHUNK(emb_dim, forward_pool_kernel<NC><<<warp_grid(bags), kBlock, 0, (cudaStream_t)stream>>>(
+                                 s, values, value_dim, emb_dim, batch_size, num_features, offsets, combiner, out, out_dtype,
+                                 (int64_t)num_features * emb_dim));
+  }
+  DEMB_CHECK_LAST();
+  return 0;
+}
+
+int demb_rows_from_slots(int64_t n, const int64_t* slots, const int64_t* table_ids, const int64_t* row_base, int64_t* rows, void* stream) {
+  if (n <= 0) return 0;
+  int grid = (int)((n + 255) / 256);
+  rows_from_slots_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, slots, table_ids, row_base, rows);
+  DEMB_CHECK_LAST();
+  return 0;
+}
+
+int demb_init_rows(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* rows, const void* keys, int mode, float p0, float p1,
+                   float p2, float p3, uint64_t seed, float state_init, const uint8_t* only_if, float* emb_out, void* stream) {
+  if (check_dims(emb_dim, value_dim)) return DEMB_ERR_ARG;
+  if (n <= 0) return 0;
+  InitArgs a{mode, p0, p1, p2, p3, seed};
+  init_rows_kernel<<<warp_grid(n), kBlock, 0, (cudaStream_t)stream>>>(values, value_dim, emb_dim, n, rows, (const uint64_t*)keys, a, state_init, only_if, emb_out);
+  DEMB_CHECK_LAST();
+  return 0;
+}
+
+int demb_copy_rows(float* values, int64_t value_dim, int width, int64_t n, const int64_t* rows, float* dense, int64_t dense_stride, int to_table,
+                   void* stream) {
+  if (width <= 0 || (width & 3) || width > value_dim || (dense_stride & 3)) return DEMB_ERR_ARG;
+  if (n <= 0) return 0;
+  copy_rows_kernel<<<warp_grid(n), kBlock, 0, (cudaStream_t)stream>>>(values, value_dim, width, n, rows, dense, dense_stride, to_table);
+  DEMB_CHECK_LAST();
+  return 0;
+}
+
+int64_t demb_backward_workspace_bytes(int64_t n, int emb_dim) {
+  if (n <= 0) return 256;
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const int32_t*)nullptr, (int32_t*)nullptr, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n);
+  size_t tiles = ((size_t)n + 31) / 32;
+  return (int64_t)(4 * align256(4 * (size_t)n) + 2 * align256(tiles * (size_t)emb_dim * 4) + align256(tmp) + 256);
+}
+
+// Fused backward: reduce gradients per unique id and apply the sparse optimizer to the value rows.
+//  grads: sequence mode [n, D] (row i = gradient of id i); pooled mode [B, F*D] viewed as [B*F, D].
+//  inverse[n]: id -> unique idx in [0, num_unique_bound).  rows[u]: global value row of unique u (<0 skip).
+//  unique_grads (nullable): also emit the reduced gradients [num_unique, D] (reference op reduce_grads).
+int demb_backward(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound, const int64_t* rows,
+                  const float* grads, int64_t grad_stride, const int64_t* offsets, int64_t batch_size, int num_features, int combiner,
+                  int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
+                  float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, void* stream_) {
+  if (check_dims(emb_dim, value_dim > 0 ? value_dim : emb_dim)) return DEMB_ERR_ARG;
+  if (n <= 0) return 0;
+  if (n >= (1ll << 31) || num_unique_bound >= (1ll << 31)) return DEMB_ERR_ARG;
+  if (workspace_bytes < demb_backward_workspace_bytes(n, emb_dim)) return DEMB_ERR_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int pooled = combiner >= 0;
+  size_t tiles = ((size_t)n + 31) / 32;
+  uint8_t* w = (uint8_t*)workspace;
+  int32_t* k0 = (int32_t*)w; w += align256(4 * (size_t)n);
+  int32_t* v0 = (int32_t*)w; w += align256(4 * (size_t)n);
+  int32_t* k1 = (int32_t*)w; w += align256(4 * (size_t)n);
+  int32_t* v1 = (int32_t*)w; w += align256(4 * (size_t)n);
+  float* pc = (float*)w; w += align256(tiles * (size_t)emb_dim * 4);
+  float* ps = (float*)w; w += align256(tiles * (size_t)emb_dim * 4);
+  size_t tmp_bytes = (size_t)((uint8_t*)workspace + workspace_bytes - w);
+  backward_pairs_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(n, inverse, pooled, batch_size, num_features, offsets, k0, v0);
+  int end_bit = 1; while (end_bit < 31 && (1ll << end_bit) < num_unique_bound) ++end_bit;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(w, tmp_bytes, k0, k1, v0, v1, (int)n, 0, end_bit, stream);
+  if (e != cudaSuccess) return -(int)e;
+  BwdArgs a{grads, grad_stride, emb_dim, pooled, combiner, batch_size, num_features, offsets, k1, v1, n, rows, values, value_dim, unique_grads, pc, ps,
+            OptArgs{opt_type, lr, eps, beta1, beta2, weight_decay, bias_correction1, bias_correction2}};
+  DISPATCH_NCHUNK(emb_dim, {
+    backward_tiles_kernel<NC><<<warp_grid((int64_t)tiles), kBlock, 0, stream>>>(a);
+    if (tiles > 1) backward_spans_kernel<NC><<<warp_grid((int64_t)tiles - 1), kBlock, 0, stream>>>(a);
+  });
+  DEMB_CHECK_LAST();
+  return 0;
+}
+
+int demb_update_rows(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* rows, const float* grads, int64_t grad_stride,
+                     int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
+                     float bias_correction2, void* stream) {
+  if (check_dims(emb_dim, value_dim)) return DEMB_ERR_ARG;
+  if (n <= 0) return 0;
+  OptArgs o{opt_type, lr, eps, beta1, beta2, weight_decay, bias_correction1, bias_correction2};
+  DISPATCH_NCHUNK(emb_dim, update_rows_kernel<NC><<<warp_grid(n), kBlock, 0, (cudaStream_t)stream>>>(values, value_dim, emb_dim, n, rows, grads, grad_stride, o));
+  DEMB_CHECK_LAST();
+  return 0;
+}
+
+}  // extern "C"

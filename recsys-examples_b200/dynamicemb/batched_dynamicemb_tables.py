@@ -1,0 +1,368 @@
+"""BatchedDynamicEmbeddingTablesV2 — the TBE-shaped module TorchRec's row-wise sharding wrapper calls.
+
+Drop-in for /root/reference/corelib/dynamicemb/dynamicemb/batched_dynamicemb_tables.py:452-1440
+(ctor :462-508, forward :999-1088, prefetch :1090) restricted to the HBM-direct storage tier
+(`DynamicEmbStorage`, key_value_table.py:1654; cache / host / external tiers are out of scope,
+"no CPU fallback").  Orchestration follows batched_dynamicemb_function.py
+(dynamicemb_prefetch :699, _prefetch_hbm_direct_path :559, DynamicEmbeddingFunction :1044/:1194)
+with the kernel sequence collapsed:
+
+  reference (15-20 launches, 3 host syncs)          here
+  ------------------------------------------------  -----------------------------------------------
+  get_table_range, segmented_unique(3), expand ids  get_table_range, segmented_unique (ids come out)
+  table_lookup, flagged_compact                      table_lookup (+1 host sync for #missing)
+  initializer, table_insert(+unlock), store_to_flat  table_insert (deterministic), init_rows (fused)
+  increment_counter x2                               counter_update
+  load_from_flat, gather_embedding[_pooled]          gather_forward (one pass, no staging copy)
+  reduce_grads (sort+2), optimizer, decrement        backward (sort + fused reduce/update), counter
+"""
+import warnings
+from collections import deque
+from dataclasses import dataclass
+from itertools import accumulate
+from typing import Deque, Dict, List, Optional
+
+import torch
+from torch import nn
+
+from . import dynamicemb_extensions as ext
+from .dynamicemb_extensions import InitializerMode, ScorePolicy
+from .optimizer import OptimizerArgs, SparseOptimizer
+from .scored_hashtable import LinearBucketTable, ScoreArg, ScoreSpec
+from .types import (BoundsCheckMode, DynamicEmbCheckMode, DynamicEmbEvictStrategy, DynamicEmbInitializerArgs, DynamicEmbInitializerMode,
+                    DynamicEmbPoolingMode, DynamicEmbScoreStrategy, DynamicEmbTableOptions, EmbOptimType)
+
+_INIT_MODE = {
+    DynamicEmbInitializerMode.NORMAL: InitializerMode.NORMAL,
+    DynamicEmbInitializerMode.TRUNCATED_NORMAL: InitializerMode.TRUNCATED_NORMAL,
+    DynamicEmbInitializerMode.UNIFORM: InitializerMode.UNIFORM,
+    DynamicEmbInitializerMode.CONSTANT: InitializerMode.CONSTANT,
+    DynamicEmbInitializerMode.DEBUG: InitializerMode.DEBUG,
+}
+
+
+def _init_params(a: DynamicEmbInitializerArgs, num_embeddings_hint: Optional[int] = None):
+    """(mode, p0..p3) for demb_init_rows; UNIFORM/TRUNCATED_NORMAL bounds default to +-1/sqrt(N) (dynamicemb_config.py:619-658)."""
+    mode = _INIT_MODE[a.mode]
+    lo, up = a.lower, a.upper
+    if lo is None or up is None:
+        bound = 1.0 / (float(num_embeddings_hint) ** 0.5) if num_embeddings_hint else 1.0
+        lo = -bound if lo is None else lo
+        up = bound if up is None else up
+    if a.mode == DynamicEmbInitializerMode.UNIFORM:
+        return mode, (lo, up, 0.0, 0.0)
+    if a.mode == DynamicEmbInitializerMode.NORMAL:
+        return mode, (a.mean, a.std_dev, 0.0, 0.0)
+    if a.mode == DynamicEmbInitializerMode.TRUNCATED_NORMAL:
+        return mode, (a.mean, a.std_dev, lo, up)
+    if a.mode == DynamicEmbInitializerMode.CONSTANT:
+        return mode, (a.value, 0.0, 0.0, 0.0)
+    return mode, (0.0, 0.0, 0.0, 0.0)
+
+
+@dataclass
+class PrefetchState:
+    """What forward/backward need from prefetch (batched_dynamicemb_function.py:166-181)."""
+    unique_keys: torch.Tensor
+    reverse_indices: torch.Tensor
+    unique_table_ids: torch.Tensor
+    slot_indices: torch.Tensor      # table-local slot per unique key, -1 = insert failed
+    rows: torch.Tensor              # global value row per unique key, -1 = absent
+    num_unique: int
+
+
+class _LookupFunction(torch.autograd.Function):
+    """DynamicEmbeddingFunction (batched_dynamicemb_function.py:1043-1300): the optimizer update happens
+    inside backward (fused); gradients returned to autograd are None."""
+
+    @staticmethod
+    def forward(ctx, module, state: PrefetchState, offsets, batch_size, dummy):
+        pooled = module.pooling_mode != DynamicEmbPoolingMode.NONE
+        combiner = int(module.pooling_mode) if pooled else -1
+        n = state.reverse_indices.numel()
+        out = ext.gather_forward(module._values, module.max_D, state.rows, state.reverse_indices, n, offsets=offsets if pooled else None,
+                                 batch_size=batch_size if pooled else 0, num_features=module.feature_num if pooled else 0,
+                                 combiner=combiner, out_dtype=module.output_dtype)
+        ctx.module, ctx.state, ctx.offsets, ctx.batch_size, ctx.combiner = module, state, offsets, batch_size, combiner
+        return out
+
+    @staticmethod
+    def backward(ctx, grads):
+        m, st = ctx.module, ctx.state
+        grads = grads.contiguous().to(torch.float32)
+        opt = m._optimizer
+        if opt.args.gradient_clipping:
+            grads = grads.clamp(-opt.args.max_gradient, opt.args.max_gradient)
+        opt.step()
+        pooled = ctx.combiner >= 0
+        ext.backward(m._values, m.max_D, st.reverse_indices, max(st.num_unique, 1), st.rows, grads, offsets=ctx.offsets if pooled else None,
+                     batch_size=ctx.batch_size if pooled else 0, num_features=m.feature_num if pooled else 0, combiner=ctx.combiner,
+                     **opt.kernel_kwargs())
+        m._table.decrement_counter(st.slot_indices, st.unique_table_ids)
+        return None, None, None, None, None
+
+
+class BatchedDynamicEmbeddingTablesV2(nn.Module):
+    def __init__(
+        self,
+        table_options: List[DynamicEmbTableOptions],
+        table_names: Optional[List[str]] = None,
+        feature_table_map: Optional[List[int]] = None,
+        use_index_dedup: bool = False,
+        prefetch_pipeline: bool = False,
+        pooling_mode: DynamicEmbPoolingMode = DynamicEmbPoolingMode.SUM,
+        output_dtype: torch.dtype = torch.float32,
+        device: torch.device = None,
+        enforce_hbm: bool = False,
+        bounds_check_mode: BoundsCheckMode = BoundsCheckMode.WARNING,
+        optimizer: EmbOptimType = EmbOptimType.SGD,
+        stochastic_rounding: bool = True,
+        gradient_clipping: bool = False,
+        max_gradient: float = 1.0,
+        max_norm: float = 0.0,
+        learning_rate: float = 0.01,
+        eps: float = 1.0e-8,
+        initial_accumulator_value: float = 0.0,
+        momentum: float = 0.9,
+        weight_decay: float = 0.0,
+        weight_decay_mode=None,
+        eta: float = 0.001,
+        beta1: float = 0.9,
+        beta2: float = 0.999,
+        counter_based_regularization=None,
+        cowclip_regularization=None,
+        *args,
+        **kwargs,
+    ) -> None:
+        super().__init__()
+        assert len(table_options) >= 1
+        opt0 = table_options[0]
+        for o in table_options:
+            assert o.get_grouped_key() == opt0.get_grouped_key(), "All tables must match in grouped keys."
+            if o.caching or o.external_storage is not None:
+                raise NotImplementedError("cache / external storage tiers are out of scope (HBM-direct only); see DESIGN.md")
+            if o.embedding_dtype != torch.float32:
+                raise NotImplementedError("value rows are fp32 in this build")
+        self._dynamicemb_options = table_options
+        self.index_type = opt0.index_type
+        self.embedding_dtype = opt0.embedding_dtype
+        self.output_dtype = output_dtype
+        self.pooling_mode = DynamicEmbPoolingMode(pooling_mode)
+        self.use_index_dedup = use_index_dedup
+        self._enable_prefetch = prefetch_pipeline
+        self._table_names = table_names if table_names is not None else [f"t{i}" for i in range(len(table_options))]
+        self.device_id = torch.device(device).index if device is not None and torch.device(device).index is not None else torch.cuda.current_device()
+        self._device = torch.device("cuda", self.device_id)
+        self.dims = [o.dim for o in table_options]
+        assert all(d == self.dims[0] for d in self.dims), "this build requires a uniform embedding dim per module (planner splits mixed dims)"
+        T_ = len(table_options)
+        self.feature_table_map = feature_table_map if feature_table_map is not None else list(range(T_))
+        assert sorted(set(self.feature_table_map)) == list(range(T_)), "Each table must have at least one feature!"
+        assert self.feature_table_map == sorted(self.feature_table_map), "features must be grouped by table"
+        self.feature_num = len(self.feature_table_map)
+        self.max_D = max(self.dims)
+        self.total_D = sum(self.dims[t] for t in self.feature_table_map)
+        offs, old = [], -1
+        for i, t in enumerate(self.feature_table_map):
+            if t != old:
+                offs.append(i)
+                old = t
+        offs.append(self.feature_num)
+        self.table_offsets_in_feature = offs
+        self.feature_offsets = torch.tensor(offs, device=self._device, dtype=torch.int64)
+        for o in table_options:
+            if o.init_capacity is None:
+                o.init_capacity = o.max_capacity
+        self._optimizer_type = optimizer if opt0.training else EmbOptimType.NONE
+        self._optimizer = SparseOptimizer(self._optimizer_type, OptimizerArgs(
+            learning_rate=learning_rate, eps=eps, initial_accumulator_value=initial_accumulator_value, beta1=beta1, beta2=beta2,
+            weight_decay=weight_decay, gradient_clipping=gradient_clipping, max_gradient=max_gradient))
+        self._create_score()
+        # --- storage: key index map + value rows [capacity, emb_dim + state_dim] in HBM (key_value_table.py:346-356)
+        policy = self._score_policy()
+        self._table = LinearBucketTable([o.max_capacity for o in table_options], [ScoreSpec(name="score", policy=policy)],
+                                        key_type=self.index_type, bucket_capacity=opt0.bucket_capacity, device=self._device)
+        self.value_dim = self.max_D + self._optimizer.get_state_dim(self.max_D)
+        self.value_dim = (self.value_dim + 3) // 4 * 4
+        self._values = torch.zeros(self._table.capacity_, self.value_dim, dtype=torch.float32, device=self._device)
+        self._seed = int(kwargs.get("seed", 0))
+        self._prefetch_states: Deque[PrefetchState] = deque()
+        self._empty_tensor = nn.Parameter(torch.empty(10, requires_grad=True, device=self._device, dtype=self.embedding_dtype))
+        self.bounds_check_mode_int = int(bounds_check_mode)
+
+    # ------------------------------------------------------------------ scores (batched_dynamicemb_tables.py:1210-1260)
+    def _create_score(self):
+        self._scores: Dict[str, int] = {}
+        for name, o in zip(self._table_names, self._dynamicemb_options):
+            s = o.score_strategy
+            if s == DynamicEmbScoreStrategy.TIMESTAMP:
+                o.evict_strategy = DynamicEmbEvictStrategy.LRU
+                self._scores[name] = 0
+            elif s == DynamicEmbScoreStrategy.STEP:
+                o.evict_strategy = DynamicEmbEvictStrategy.CUSTOMIZED
+                self._scores[name] = 1
+            elif s == DynamicEmbScoreStrategy.CUSTOMIZED:
+                o.evict_strategy = DynamicEmbEvictStrategy.CUSTOMIZED
+            elif s == DynamicEmbScoreStrategy.LFU:
+                o.evict_strategy = DynamicEmbEvictStrategy.LFU
+                self._scores[name] = 1
+            elif s == DynamicEmbScoreStrategy.NO_EVICTION:
+                o.evict_strategy = DynamicEmbEvictStrategy.CUSTOMIZED
+                self._scores[name] = 0
+            else:
+                raise NotImplementedError(f"score strategy {s}")
+
+    def _score_policy(self) -> ScorePolicy:
+        """key_value_table.py:136-177 strategy -> policy."""
+        s = self._dynamicemb_options[0].score_strategy
+        if s == DynamicEmbScoreStrategy.TIMESTAMP:
+            return ScorePolicy.GLOBAL_TIMER
+        if s == DynamicEmbScoreStrategy.LFU:
+            return ScorePolicy.ACCUMULATE
+        return ScorePolicy.ASSIGN
+
+    def _update_score(self):
+        for name, o in zip(self._table_names, self._dynamicemb_options):
+            if o.score_strategy == DynamicEmbScoreStrategy.STEP:
+                self._scores[name] = (self._scores[name] + 1) & 0xFFFFFFFFFFFFFFFF
+
+    def set_score(self, named_score: Dict[str, int]) -> None:
+        for name, score in named_score.items():
+            if not isinstance(score, int):
+                raise ValueError(f"Table's score is expect to int but got {type(score)}")
+            if score == 0:
+                raise ValueError("Can't set table's score to 0.")
+            idx = self._table_names.index(name)
+            assert self._dynamicemb_options[idx].score_strategy == DynamicEmbScoreStrategy.CUSTOMIZED, \
+                "Can only set score for table whose score_strategy is DynamicEmbScoreStrategy.CUSTOMIZED."
+            self._scores[name] = score
+
+    def get_score(self) -> Dict[str, int]:
+        out = {}
+        for name, o in zip(self._table_names, self._dynamicemb_options):
+            out[name] = ext.device_timestamp() if o.score_strategy == DynamicEmbScoreStrategy.TIMESTAMP else self._scores[name]
+        return out
+
+    def _score_arg(self, n: int, table_ids: torch.Tensor, freq: Optional[torch.Tensor], const: bool = False) -> ScoreArg:
+        if const:
+            return ScoreArg(name="score", policy=ScorePolicy.CONST)
+        policy = self._score_policy()
+        if policy == ScorePolicy.GLOBAL_TIMER:
+            return ScoreArg(name="score", policy=policy)
+        if policy == ScorePolicy.ACCUMULATE:
+            v = freq if freq is not None else torch.ones(n, dtype=torch.int64, device=self._device)
+            return ScoreArg(name="score", value=v.to(torch.int64), policy=policy)
+        for name in self._table_names:
+            if name not in self._scores:
+                raise RuntimeError(f"Must set score for table '{name}' whose score_strategy is customized.")
+        per_table = torch.tensor([self._scores[nm] & 0x7FFFFFFFFFFFFFFF for nm in self._table_names], dtype=torch.int64, device=self._device)
+        return ScoreArg(name="score", value=per_table[table_ids], policy=policy)
+
+    # ------------------------------------------------------------------ properties the callers use
+    @property
+    def optimizer(self) -> SparseOptimizer:
+        return self._optimizer
+
+    @property
+    def tables(self) -> LinearBucketTable:
+        return self._table
+
+    @property
+    def table_names(self) -> List[str]:
+        return self._table_names
+
+    def set_learning_rate(self, lr: float) -> None:
+        self._optimizer.set_learning_rate(lr)
+
+    def flush(self) -> None:
+        torch.cuda.current_stream(self._device).synchronize()
+
+    def reset_prefetch(self) -> None:
+        self._prefetch_states.clear()
+
+    # ------------------------------------------------------------------ prefetch / forward
+    def _split(self, indices: torch.Tensor, offsets: torch.Tensor):
+        if indices.dtype != self.index_type:
+            indices = indices.to(self.index_type)
+        fb = offsets.numel() - 1
+        assert fb > 0 and fb % self.feature_num == 0, "feature_batch_size must be divisible by feature_num"
+        return indices.contiguous(), offsets.to(torch.int64).contiguous(), fb // self.feature_num
+
+    def prefetch(self, indices, offsets, forward_stream=None, batch_size_per_feature_per_rank=None, frequency_counters=None) -> None:
+        """dynamicemb_prefetch + _prefetch_hbm_direct_path: dedup, find, insert+init the missing keys, pin rows."""
+        if not self.training:
+            return
+        indices, offsets, B = self._split(indices, offsets)
+        T = len(self._dynamicemb_options)
+        tb = self._table
+        trange = ext.get_table_range(offsets, self.feature_offsets, self.feature_num) if T > 1 else None
+        want_freq = self._score_policy() == ScorePolicy.ACCUMULATE
+        freq_in = (frequency_counters.to(torch.int64) if frequency_counters is not None
+                   else (torch.empty(0, dtype=torch.int64, device=self._device) if want_freq else None))
+        num_u, ukeys, reverse, toffs, freq, utids = ext.segmented_unique_cuda(indices, trange, T, freq_in, want_table_ids=True)
+        nu = int(num_u.item())                                   # host sync #1 (reference: batched_dynamicemb_function.py:141-142)
+        ukeys, utids = ukeys[:nu], utids[:nu]
+        freq = freq[:nu] if freq is not None else None
+        ts = ext.device_timestamp()
+        _, founds, slots = tb.lookup(ukeys, utids, self._score_arg(nu, utids, freq), timestamp=ts)
+        tb.increment_counter(slots, utids)                       # pin found rows before anything can evict them (:607)
+        miss = (~founds).nonzero(as_tuple=True)[0]               # host sync #2 (reference: flagged_compact)
+        if miss.numel() > 0:
+            mk, mt = ukeys[miss], utids[miss]
+            mf = freq[miss] if freq is not None else None
+            new_slots = tb.insert(mk, mt, self._score_arg(mk.numel(), mt, mf), timestamp=ts)
+            new_rows = ext.rows_from_slots(new_slots, mt, tb.row_base_)
+            mode, p = _init_params(self._dynamicemb_options[0].initializer_args, self._dynamicemb_options[0].max_capacity)
+            ext.init_rows(self._values, self.max_D, new_rows, mk, mode, *p, seed=self._seed, state_init=self._optimizer.initial_state_value)
+            tb.increment_counter(new_slots, mt)
+            slots[miss] = new_slots
+        rows = ext.rows_from_slots(slots, utids, tb.row_base_)
+        self._prefetch_states.append(PrefetchState(ukeys, reverse, utids, slots, rows, nu))
+        self._update_score()
+
+    def forward(self, indices, offsets, per_sample_weights=None, feature_requires_grad=None, batch_size_per_feature_per_rank=None,
+                total_unique_indices=None) -> torch.Tensor:
+        indices, offsets, B = self._split(indices, offsets)
+        if not self.training:
+            return self._eval_forward(indices, offsets, B)
+        if not self._prefetch_states:
+            self.prefetch(indices, offsets, frequency_counters=per_sample_weights)
+        state = self._prefetch_states.popleft()
+        if not torch.is_grad_enabled():
+            out = _LookupFunction.forward(_NoCtx(), self, state, offsets, B, None)
+            self._table.decrement_counter(state.slot_indices, state.unique_table_ids)
+            return out
+        return _LookupFunction.apply(self, state, offsets, B, self._empty_tensor)
+
+    def _eval_forward(self, indices, offsets, B) -> torch.Tensor:
+        """dynamicemb_eval_forward (batched_dynamicemb_function.py:836): read-only fused probe+gather; absent ids take the
+        eval initializer (constant, default 0)."""
+        tb = self._table
+        T = len(self._dynamicemb_options)
+        trange = ext.get_table_range(offsets, self.feature_offsets, self.feature_num) if T > 1 else None
+        pooled = self.pooling_mode != DynamicEmbPoolingMode.NONE
+        ea = self._dynamicemb_options[0].eval_initializer_args
+        absent = ea.value if ea.mode == DynamicEmbInitializerMode.CONSTANT else 0.0
+        return ext.lookup_forward(tb.table_storage_, tb.table_bucket_offsets_, tb.bucket_capacity_, self._values, self.max_D, indices,
+                                  row_base=tb.row_base_, table_range=trange, num_tables=T, offsets=offsets if pooled else None,
+                                  batch_size=B if pooled else 0, num_features=self.feature_num if pooled else 0,
+                                  combiner=int(self.pooling_mode) if pooled else -1, out_dtype=self.output_dtype, absent_value=absent,
+                                  num_scores=tb.num_scores_)
+
+    # ------------------------------------------------------------------ inspection helpers (tests, dump)
+    def export_keys_values(self, table_id: int = 0):
+        """All (key, embedding row, optimizer state) of one table — used by dump and by the tests."""
+        tb = self._table
+        ks, vs = [], []
+        base = int(tb.row_base_[table_id].item())
+        for keys, _scores, idx in tb.export(table_id):
+            ks.append(keys)
+            vs.append(self._values[base + idx])
+        if not ks:
+            return torch.empty(0, dtype=self.index_type, device=self._device), torch.empty(0, self.value_dim, device=self._device)
+        return torch.cat(ks), torch.cat(vs)
+
+
+class _NoCtx:
+    """Stand-in ctx so the no-grad path reuses _LookupFunction.forward."""
+    pass

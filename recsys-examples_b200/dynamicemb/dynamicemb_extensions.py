@@ -1,0 +1,374 @@
+"""Op layer: the names the reference's pybind module `dynamicemb_extensions` exports
+(/root/reference/corelib/dynamicemb/src/module_bind.cu:22-43, table_operation/table.cu:94-204),
+implemented over the C ABI of librecsys_b200.so.  Tensors in, current CUDA stream, Python
+exceptions on error — the same calling convention the reference Python package relies on.
+"""
+import enum
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+
+class ScorePolicy(enum.IntEnum):
+    """score.cuh:30-42"""
+    CONST = 0
+    ASSIGN = 1
+    ACCUMULATE = 2
+    GLOBAL_TIMER = 3
+    LRU_LFU = 4
+
+
+class InsertResult(enum.IntEnum):
+    """types.cuh:52-61"""
+    INSERT = 0
+    RECLAIM = 1
+    ASSIGN = 2
+    EVICT = 3
+    DUPLICATED = 4
+    BUSY = 5
+    ILLEGAL = 6
+    INIT = 7
+
+
+class EvictStrategy(enum.IntEnum):
+    KLru = 0
+    KLfu = 1
+    KEpochLru = 2
+    KEpochLfu = 3
+    KCustomized = 4
+
+
+class OptimizerType(enum.IntEnum):
+    NONE = 0
+    SGD = 1
+    ADAM = 2
+    ADAGRAD = 3
+    ROWWISE_ADAGRAD = 4
+
+
+class InitializerMode(enum.IntEnum):
+    NORMAL = 0
+    TRUNCATED_NORMAL = 1
+    UNIFORM = 2
+    DEBUG = 3
+    CONSTANT = 4
+
+
+_OUT_DTYPE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def _i64(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.int64:
+        t = t.to(torch.int64)
+    return t.contiguous()
+
+
+def _u64_view(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    return t.contiguous()
+
+
+def _num_buckets(storage: torch.Tensor, bucket_capacity: int, num_scores: int) -> int:
+    return storage.numel() * storage.element_size() // (bucket_capacity * (9 + 8 * num_scores))
+
+
+def device_timestamp() -> int:
+    import time
+    return time.time_ns()
+
+
+# ---------------------------------------------------------------------------------------------------
+# table ops
+# ---------------------------------------------------------------------------------------------------
+def table_partition(storage: torch.Tensor, dtypes: List[torch.dtype], bucket_capacity: int, num_buckets: int) -> List[torch.Tensor]:
+    """table.cu:22-65: per-field strided [num_buckets, bucket_capacity] views of the bucket-SoA storage."""
+    sizes = [torch.empty((), dtype=d).element_size() for d in dtypes]
+    bucket_bytes = sum(sizes) * bucket_capacity
+    if bucket_bytes * num_buckets != storage.numel() * storage.element_size():
+        raise RuntimeError("Storage size mismatched with bucket_bytes * num_buckets")
+    out, byte_off = [], 0
+    flat = storage.view(torch.uint8).reshape(-1)
+    for d, sz in zip(dtypes, sizes):
+        # bucket_bytes is a multiple of 16*17; every field offset is a multiple of its element size
+        v = flat[byte_off * bucket_capacity:].view(d) if (byte_off * bucket_capacity) % sz == 0 else None
+        assert v is not None
+        out.append(torch.as_strided(v, (num_buckets, bucket_capacity), (bucket_bytes // sz, 1)))
+        byte_off += sz
+    return out
+
+
+def table_init(table_storage: torch.Tensor, bucket_capacity: int, num_scores: int = 1) -> None:
+    nb = _num_buckets(table_storage, bucket_capacity, num_scores)
+    N.check(N.lib.demb_table_init(N.ptr(table_storage), nb, bucket_capacity, num_scores, N.stream()), "table_init")
+
+
+def table_lookup(table_storage, table_bucket_offsets, bucket_capacity, keys, table_ids, score_input, policy_type,
+                 num_scores: int = 1, timestamp: int = 0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """table.cuh:68 / lookup.cu.  Returns (score_out int64, founds bool, indices int64)."""
+    n = keys.numel()
+    dev = keys.device
+    score_out = torch.empty(n, dtype=torch.int64, device=dev)
+    founds = torch.empty(n, dtype=torch.bool, device=dev)
+    indices = torch.empty(n, dtype=torch.int64, device=dev)
+    if n == 0:
+        return score_out, founds, indices
+    keys = keys.contiguous()
+    table_ids = _i64(table_ids)
+    score_input = _u64_view(score_input)
+    N.check(N.lib.demb_table_lookup(N.ptr(table_storage), N.ptr(table_bucket_offsets), bucket_capacity, num_scores, n, N.ptr(keys),
+                                    N.ptr(table_ids), int(policy_type), N.ptr(score_input), int(timestamp), N.ptr(founds), N.ptr(indices),
+                                    N.ptr(score_out), N.stream()), "table_lookup")
+    return score_out, founds, indices
+
+
+def _insert_impl(table_storage, table_bucket_offsets, bucket_capacity, bucket_sizes, keys, table_ids, score_input, policy_type, counter,
+                 insert_results, score_output, num_scores, want_evicted, timestamp):
+    n = keys.numel()
+    dev = keys.device
+    indices = torch.empty(n, dtype=torch.int64, device=dev)
+    ev = None
+    if want_evicted:
+        ev = (torch.zeros(1, dtype=torch.int64, device=dev), torch.empty(n, dtype=keys.dtype, device=dev),
+              torch.empty(n, dtype=torch.int64, device=dev), torch.empty(n, dtype=torch.int64, device=dev),
+              torch.empty(n, dtype=torch.int64, device=dev))
+    if n == 0:
+        return indices, ev
+    keys = keys.contiguous()
+    table_ids = _i64(table_ids)
+    score_input = _u64_view(score_input)
+    ws_bytes = N.lib.demb_table_insert_workspace_bytes(n)
+    ws = N.workspace(ws_bytes, dev)
+    nb_total = bucket_sizes.numel()
+    N.check(N.lib.demb_table_insert(
+        N.ptr(table_storage), N.ptr(table_bucket_offsets), bucket_capacity, num_scores, nb_total, N.ptr(bucket_sizes), n, N.ptr(keys),
+        N.ptr(table_ids), int(policy_type), N.ptr(score_input), int(timestamp), N.ptr(counter), 1 if keys.dtype == torch.int64 else 0,
+        N.ptr(insert_results), N.ptr(indices), N.ptr(score_output),
+        N.ptr(ev[0]) if ev else None, N.ptr(ev[1]) if ev else None, N.ptr(ev[2]) if ev else None, N.ptr(ev[3]) if ev else None,
+        N.ptr(ev[4]) if ev else None, N.ptr(ws), ws.numel(), N.stream()), "table_insert")
+    return indices, ev
+
+
+def table_insert(table_storage, table_bucket_offsets, bucket_capacity, bucket_sizes, keys, table_ids, score_input, policy_type, counter,
+                 insert_results=None, score_output=None, num_scores: int = 1, timestamp: int = 0) -> torch.Tensor:
+    """table.cuh:81 / insert.cu.  Keys must be unique; always deterministic (see include/dynamicemb_b200.h)."""
+    indices, _ = _insert_impl(table_storage, table_bucket_offsets, bucket_capacity, bucket_sizes, keys, table_ids, score_input, policy_type,
+                              counter, insert_results, score_output, num_scores, False, timestamp)
+    return indices
+
+
+def table_insert_and_evict(table_storage, table_bucket_offsets, bucket_capacity, bucket_sizes, keys, table_ids, score_input, policy_type,
+                           counter, insert_results=None, score_output=None, num_scores: int = 1, timestamp: int = 0):
+    """table.cuh:100 / insert_and_evict.cu:330.  Returns (indices, num_evicted[1] device tensor, evicted_keys,
+    evicted_indices, evicted_scores, evicted_table_ids) — buffers sized n, first num_evicted valid."""
+    indices, ev = _insert_impl(table_storage, table_bucket_offsets, bucket_capacity, bucket_sizes, keys, table_ids, score_input, policy_type,
+                               counter, insert_results, score_output, num_scores, True, timestamp)
+    return indices, ev[0], ev[1], ev[3], ev[2], ev[4]
+
+
+def table_erase(table_storage, table_bucket_offsets, bucket_capacity, bucket_sizes, keys, table_ids, indices=None, num_scores: int = 1) -> None:
+    n = keys.numel()
+    if n == 0:
+        return
+    N.check(N.lib.demb_table_erase(N.ptr(table_storage), N.ptr(table_bucket_offsets), bucket_capacity, num_scores, N.ptr(bucket_sizes), n,
+                                   N.ptr(keys.contiguous()), N.ptr(_i64(table_ids)), N.ptr(indices), N.stream()), "table_erase")
+
+
+def table_update_counter_with_layout(counter, slot_indices, delta, table_bucket_offsets, bucket_capacity, total_capacity=None, num_tables=None,
+                                     table_ids=None, overflow_output_offsets=None, overflow_bucket_capacity=0) -> None:
+    n = slot_indices.numel()
+    if n == 0:
+        return
+    N.check(N.lib.demb_counter_update(N.ptr(counter), N.ptr(_i64(slot_indices)), N.ptr(_i64(table_ids)), N.ptr(table_bucket_offsets),
+                                      bucket_capacity, n, int(delta), N.stream()), "table_update_counter_with_layout")
+
+
+def table_export_batch(table_storage, bucket_capacity, batch, offset, key_dtype, threshold=None, table_begin=0, num_scores: int = 1,
+                       score_index: int = 0):
+    """export_batch.cu: returns (counter[1], keys[batch], scores[batch], indices[batch])."""
+    dev = table_storage.device
+    counter = torch.zeros(1, dtype=torch.int64, device=dev)
+    keys = torch.empty(batch, dtype=key_dtype, device=dev)
+    scores = torch.empty(batch, dtype=torch.int64, device=dev)
+    indices = torch.empty(batch, dtype=torch.int64, device=dev)
+    N.check(N.lib.demb_table_export(N.ptr(table_storage), None, bucket_capacity, num_scores, offset, offset + batch, table_begin,
+                                    int(threshold) if threshold is not None else 0, 0 if threshold is None else 1, score_index,
+                                    N.ptr(counter), N.ptr(keys), N.ptr(scores), N.ptr(indices), N.stream()), "table_export_batch")
+    return counter, keys, scores.view(torch.uint64), indices
+
+
+# ---------------------------------------------------------------------------------------------------
+# dedup
+# ---------------------------------------------------------------------------------------------------
+def get_table_range(offsets: torch.Tensor, feature_offsets: torch.Tensor, num_features: Optional[int] = None) -> torch.Tensor:
+    """index_calculation.cu:237: table_range[t] = offsets[feature_offsets[t] * B].  `num_features` avoids a device read."""
+    T = feature_offsets.numel() - 1
+    if num_features is None:
+        num_features = int(feature_offsets[-1].item())
+    B = (offsets.numel() - 1) // num_features if num_features > 0 else 0
+    out = torch.empty(T + 1, dtype=torch.int64, device=offsets.device)
+    N.check(N.lib.demb_get_table_range(N.ptr(_i64(offsets)), N.ptr(_i64(feature_offsets)), T, B, N.ptr(out), N.stream()), "get_table_range")
+    return out
+
+
+def segmented_unique_cuda(keys: torch.Tensor, segment_range: Optional[torch.Tensor], num_tables: int,
+                          input_frequencies: Optional[torch.Tensor] = None, want_table_ids: bool = False):
+    """unique_op.cu:484.  Returns (num_uniques[1] device, unique_keys[n], reverse_indices[n], table_offsets[T+1], freq[n] or None
+    [, unique_table_ids[n]]).  Unique order = first occurrence (deterministic)."""
+    n = keys.numel()
+    dev = keys.device
+    num_unique = torch.zeros(1, dtype=torch.int64, device=dev)
+    unique_keys = torch.empty(n, dtype=keys.dtype, device=dev)
+    reverse = torch.empty(n, dtype=torch.int64, device=dev)
+    table_offsets = torch.zeros(num_tables + 1, dtype=torch.int64, device=dev)
+    need_freq = input_frequencies is not None
+    freq_in = input_frequencies if (need_freq and input_frequencies.numel() == n and n > 0) else None
+    freq_out = torch.empty(n, dtype=torch.int64, device=dev) if need_freq else None
+    utids = torch.empty(n, dtype=torch.int64, device=dev) if want_table_ids else None
+    ws_bytes = N.lib.demb_segmented_unique_workspace_bytes(n, num_tables)
+    ws = N.workspace(ws_bytes, dev)
+    N.check(N.lib.demb_segmented_unique(n, N.ptr(keys.contiguous()), N.ptr(_i64(segment_range)) if num_tables > 1 else None, num_tables,
+                                        N.ptr(_i64(freq_in)), N.ptr(unique_keys), N.ptr(reverse), N.ptr(table_offsets), N.ptr(freq_out),
+                                        N.ptr(utids), N.ptr(num_unique), N.ptr(ws), ws.numel(), N.stream()), "segmented_unique")
+    if want_table_ids:
+        return num_unique, unique_keys, reverse, table_offsets, freq_out, utids
+    return num_unique, unique_keys, reverse, table_offsets, freq_out
+
+
+def expand_table_ids_cuda(table_offsets: torch.Tensor, num_unique: int) -> torch.Tensor:
+    out = torch.empty(num_unique, dtype=torch.int64, device=table_offsets.device)
+    N.check(N.lib.demb_expand_table_ids(N.ptr(table_offsets), table_offsets.numel() - 1, num_unique, N.ptr(out), N.stream()), "expand_table_ids")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# rows
+# ---------------------------------------------------------------------------------------------------
+def lookup_forward(table_storage, table_bucket_offsets, bucket_capacity, values, emb_dim, keys, *, row_base=None, table_range=None,
+                   num_tables=1, offsets=None, batch_size=0, num_features=0, combiner=-1, out_dtype=torch.float32, absent_value=0.0,
+                   want_founds=False, num_scores=1):
+    """Fused probe + gather (+pool): the eval-path forward."""
+    n = keys.numel()
+    dev = keys.device
+    D = emb_dim
+    if combiner < 0:
+        out = torch.empty(n, D, dtype=out_dtype, device=dev)
+    else:
+        out = torch.empty(batch_size, num_features * D, dtype=out_dtype, device=dev)
+    founds = torch.empty(n, dtype=torch.bool, device=dev) if want_founds else None
+    slots = torch.empty(n, dtype=torch.int64, device=dev) if want_founds else None
+    N.check(N.lib.demb_lookup_forward(N.ptr(table_storage), N.ptr(table_bucket_offsets), bucket_capacity, num_scores, N.ptr(values),
+                                      values.stride(0), D, N.ptr(row_base), n, N.ptr(keys.contiguous()), N.ptr(table_range), num_tables,
+                                      N.ptr(_i64(offsets)), batch_size, num_features, combiner, N.ptr(out), _OUT_DTYPE[out_dtype],
+                                      float(absent_value), N.ptr(founds), N.ptr(slots), N.stream()), "lookup_forward")
+    return (out, founds, slots) if want_founds else out
+
+
+def gather_forward(values, emb_dim, rows, inverse, n, *, offsets=None, batch_size=0, num_features=0, combiner=-1, out_dtype=torch.float32):
+    dev = values.device
+    if combiner < 0:
+        out = torch.empty(n, emb_dim, dtype=out_dtype, device=dev)
+    else:
+        out = torch.empty(batch_size, num_features * emb_dim, dtype=out_dtype, device=dev)
+    N.check(N.lib.demb_gather_forward(N.ptr(values), values.stride(0), emb_dim, n, N.ptr(rows), N.ptr(inverse), N.ptr(_i64(offsets)),
+                                      batch_size, num_features, combiner, N.ptr(out), _OUT_DTYPE[out_dtype], N.stream()), "gather_forward")
+    return out
+
+
+def rows_from_slots(slots, table_ids, row_base):
+    rows = torch.empty_like(slots)
+    N.check(N.lib.demb_rows_from_slots(slots.numel(), N.ptr(slots), N.ptr(_i64(table_ids)), N.ptr(row_base), N.ptr(rows), N.stream()),
+            "rows_from_slots")
+    return rows
+
+
+def init_rows(values, emb_dim, rows, keys, mode, p0=0.0, p1=1.0, p2=0.0, p3=0.0, seed=0, state_init=0.0, only_if=None, emb_out=None):
+    n = keys.numel()
+    N.check(N.lib.demb_init_rows(N.ptr(values), values.stride(0) if values is not None else emb_dim, emb_dim, n, N.ptr(rows),
+                                 N.ptr(keys.contiguous()), int(mode), float(p0), float(p1), float(p2), float(p3), int(seed),
+                                 float(state_init), N.ptr(only_if), N.ptr(emb_out), N.stream()), "init_rows")
+
+
+def copy_rows(values, width, rows, dense, to_table: bool):
+    N.check(N.lib.demb_copy_rows(N.ptr(values), values.stride(0), width, rows.numel(), N.ptr(rows), N.ptr(dense), dense.stride(0),
+                                 1 if to_table else 0, N.stream()), "copy_rows")
+
+
+def backward(values, emb_dim, inverse, num_unique_bound, rows, grads, *, offsets=None, batch_size=0, num_features=0, combiner=-1,
+             opt_type=0, lr=0.0, eps=1e-8, beta1=0.9, beta2=0.999, weight_decay=0.0, bc1=1.0, bc2=1.0, want_unique_grads=False):
+    """Fused reduce_grads + optimizer row update.  grads: [n, D] (sequence) or [B, F*D] (pooled)."""
+    n = inverse.numel()
+    dev = inverse.device
+    ug = torch.zeros(num_unique_bound, emb_dim, dtype=torch.float32, device=dev) if want_unique_grads else None
+    if n == 0:
+        return ug
+    grads = grads.contiguous()
+    ws_bytes = N.lib.demb_backward_workspace_bytes(n, emb_dim)
+    ws = N.workspace(ws_bytes, dev)
+    N.check(N.lib.demb_backward(N.ptr(values), values.stride(0) if values is not None else emb_dim, emb_dim, n, N.ptr(inverse),
+                                int(num_unique_bound), N.ptr(rows), N.ptr(grads), emb_dim, N.ptr(_i64(offsets)), batch_size, num_features,
+                                combiner, int(opt_type), lr, eps, beta1, beta2, weight_decay, bc1, bc2, N.ptr(ug), N.ptr(ws), ws.numel(),
+                                N.stream()), "backward")
+    return ug
+
+
+def update_rows(values, emb_dim, rows, grads, opt_type, lr, eps=1e-8, beta1=0.9, beta2=0.999, weight_decay=0.0, bc1=1.0, bc2=1.0):
+    grads = grads.contiguous()
+    N.check(N.lib.demb_update_rows(N.ptr(values), values.stride(0), emb_dim, rows.numel(), N.ptr(rows), N.ptr(grads), grads.stride(0),
+                                   int(opt_type), lr, eps, beta1, beta2, weight_decay, bc1, bc2, N.stream()), "update_rows")
+
+
+# reference-named thin aliases (dynamic_emb_op.cu:79,106,160) -----------------------------------------
+def gather_embedding(unique_embs: torch.Tensor, output_embs: torch.Tensor, reverse_indices: torch.Tensor) -> None:
+    n = reverse_indices.numel()
+    rows = torch.arange(unique_embs.shape[0], dtype=torch.int64, device=unique_embs.device)
+    N.check(N.lib.demb_gather_forward(N.ptr(unique_embs), unique_embs.stride(0), unique_embs.shape[1], n, N.ptr(rows), N.ptr(reverse_indices),
+                                      None, 0, 0, -1, N.ptr(output_embs), _OUT_DTYPE[output_embs.dtype], N.stream()), "gather_embedding")
+
+
+def gather_embedding_pooled(unique_embs, output_embs, reverse_indices, offsets, combiner, total_D, batch_size, D_offsets=None, max_D=0) -> None:
+    D = unique_embs.shape[1]
+    F = total_D // D
+    rows = torch.arange(unique_embs.shape[0], dtype=torch.int64, device=unique_embs.device)
+    N.check(N.lib.demb_gather_forward(N.ptr(unique_embs), unique_embs.stride(0), D, reverse_indices.numel(), N.ptr(rows), N.ptr(reverse_indices),
+                                      N.ptr(_i64(offsets)), batch_size, F, combiner, N.ptr(output_embs), _OUT_DTYPE[output_embs.dtype],
+                                      N.stream()), "gather_embedding_pooled")
+
+
+def reduce_grads(reverse_indices, grads, num_unique, batch_size, out_dim, offsets=None, D_offsets=None, combiner=-1, total_D=0) -> torch.Tensor:
+    F = (total_D // out_dim) if offsets is not None else 0
+    return backward(None, out_dim, reverse_indices, num_unique, None, grads, offsets=offsets, batch_size=batch_size if offsets is not None else 0,
+                    num_features=F, combiner=combiner if offsets is not None else -1, want_unique_grads=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# input dist
+# ---------------------------------------------------------------------------------------------------
+DIST_TYPE = {"continuous": 0, "roundrobin": 1, "hash_roundrobin": 2}
+
+
+def block_bucketize_sparse_features(lengths: torch.Tensor, indices: torch.Tensor, batch_size: int, world_size: int, block_sizes: torch.Tensor,
+                                    dist_type_per_feature: Optional[torch.Tensor] = None, weights: Optional[torch.Tensor] = None,
+                                    sequence: bool = True):
+    """sparse_block_bucketize_features.cu:372.  lengths[F*B] feature-major.  Returns (new_lengths[W*F*B], new_indices[n],
+    new_weights or None, unbucketize_permute[n] or None)."""
+    dev = indices.device
+    S = lengths.numel()
+    offsets = torch.zeros(S + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(lengths.to(torch.int64), 0, out=offsets[1:])
+    n = indices.numel()
+    new_lengths = torch.zeros(world_size * S, dtype=torch.int64, device=dev)
+    new_ids = torch.empty(n, dtype=torch.int64, device=dev)
+    perm = torch.empty(n, dtype=torch.int64, device=dev) if sequence else None
+    new_w = torch.empty(n, dtype=torch.float32, device=dev) if weights is not None else None
+    ws = N.workspace(N.lib.demb_bucketize_workspace_bytes(S, world_size), dev)
+    dt = dist_type_per_feature.to(torch.int32).contiguous() if dist_type_per_feature is not None else None
+    N.check(N.lib.demb_block_bucketize_sparse_features(S, batch_size, world_size, N.ptr(offsets), N.ptr(_i64(indices)),
+                                                       N.ptr(_i64(block_sizes)), N.ptr(dt), N.ptr(weights), N.ptr(new_lengths), N.ptr(new_ids),
+                                                       N.ptr(perm), N.ptr(new_w), N.ptr(ws), ws.numel(), N.stream()),
+            "block_bucketize_sparse_features")
+    return new_lengths, new_ids, new_w, perm

@@ -1,0 +1,142 @@
+"""Config enums / dataclasses of the DynamicEmb boundary.  Field names and defaults follow
+/root/reference/corelib/dynamicemb/dynamicemb/{types.py:33-110, dynamicemb_config.py:62-165,448-478}
+so user code written against the reference constructs the same objects."""
+import enum
+import math
+from dataclasses import dataclass, field
+from typing import Any, Optional, Tuple, Union
+
+import torch
+
+from .dynamicemb_extensions import EvictStrategy
+
+DEFAULT_INDEX_TYPE = torch.int64
+DEFAULT_BUCKET_CAPACITY = 128
+BUCKET_ALIGNMENT = 16
+DEBUG_EMB_INITIALIZER_MOD = 100_000
+BATCH_SIZE_PER_DUMP = 65536
+SUPPORTED_DIST_TYPES = ("continuous", "roundrobin", "hash_roundrobin")
+DTYPE_NUM_BYTES = {torch.float32: 4, torch.float16: 2, torch.bfloat16: 2}
+
+
+class EmbOptimType(enum.Enum):
+    """Subset of fbgemm_gpu.split_embedding_configs.EmbOptimType the reference dispatches on
+    (dynamicemb/optimizer.py:36-57); string values are fbgemm's."""
+    SGD = "sgd"
+    EXACT_SGD = "exact_sgd"
+    ADAM = "adam"
+    EXACT_ADAGRAD = "exact_adagrad"
+    EXACT_ROWWISE_ADAGRAD = "exact_row_wise_adagrad"
+    NONE = "none"
+
+
+class DynamicEmbInitializerMode(enum.Enum):
+    NORMAL = "normal"
+    TRUNCATED_NORMAL = "truncated_normal"
+    UNIFORM = "uniform"
+    CONSTANT = "constant"
+    DEBUG = "debug"
+
+
+@dataclass
+class DynamicEmbInitializerArgs:
+    mode: DynamicEmbInitializerMode = DynamicEmbInitializerMode.UNIFORM
+    mean: float = 0.0
+    std_dev: float = 1.0
+    lower: Optional[float] = None
+    upper: Optional[float] = None
+    value: float = 0.0
+
+
+@enum.unique
+class DynamicEmbCheckMode(enum.IntEnum):
+    ERROR = 0
+    WARNING = 1
+    IGNORE = 2
+
+
+class DynamicEmbPoolingMode(enum.IntEnum):
+    SUM = 0
+    MEAN = 1
+    NONE = 2
+
+
+@enum.unique
+class DynamicEmbEvictStrategy(enum.Enum):
+    LRU = EvictStrategy.KLru
+    LFU = EvictStrategy.KLfu
+    EPOCH_LRU = EvictStrategy.KEpochLru
+    EPOCH_LFU = EvictStrategy.KEpochLfu
+    CUSTOMIZED = EvictStrategy.KCustomized
+
+
+class DynamicEmbScoreStrategy(enum.IntEnum):
+    TIMESTAMP = 0
+    STEP = 1
+    CUSTOMIZED = 2
+    LFU = 3
+    NO_EVICTION = 4
+
+
+ScoreStrategy = Union[DynamicEmbScoreStrategy, Tuple[DynamicEmbScoreStrategy, ...]]
+
+
+class BoundsCheckMode(enum.IntEnum):
+    FATAL = 0
+    WARNING = 1
+    IGNORE = 2
+    NONE = 3
+
+
+@dataclass
+class DynamicEmbTableOptions:
+    """dynamicemb_config.py:307-520 (fields :448-478)."""
+    embedding_dtype: Optional[torch.dtype] = None
+    dim: Optional[int] = None
+    max_capacity: Optional[int] = None
+    evict_strategy: DynamicEmbEvictStrategy = DynamicEmbEvictStrategy.LRU
+    local_hbm_for_values: int = 0
+    device_id: Optional[int] = None
+    training: bool = True
+    initializer_args: DynamicEmbInitializerArgs = field(default_factory=DynamicEmbInitializerArgs)
+    eval_initializer_args: DynamicEmbInitializerArgs = field(
+        default_factory=lambda: DynamicEmbInitializerArgs(mode=DynamicEmbInitializerMode.CONSTANT, value=0.0))
+    caching: bool = False
+    init_capacity: Optional[int] = None
+    max_load_factor: float = 0.5
+    score_strategy: Optional[ScoreStrategy] = DynamicEmbScoreStrategy.TIMESTAMP
+    bucket_capacity: int = DEFAULT_BUCKET_CAPACITY
+    safe_check_mode: DynamicEmbCheckMode = DynamicEmbCheckMode.IGNORE
+    global_hbm_for_values: int = 0
+    external_storage: Any = None
+    index_type: Optional[torch.dtype] = None
+    dist_type: str = "roundrobin"
+    admit_strategy: Any = None
+    admission_counter: Any = None
+
+    def __post_init__(self):
+        if self.index_type is None:
+            self.index_type = DEFAULT_INDEX_TYPE
+        if self.embedding_dtype is None:
+            self.embedding_dtype = torch.float32
+        if self.dist_type not in SUPPORTED_DIST_TYPES:
+            raise ValueError(f"dist_type must be one of {SUPPORTED_DIST_TYPES}, got {self.dist_type}")
+        if isinstance(self.score_strategy, tuple) and len(self.score_strategy) == 1:
+            self.score_strategy = self.score_strategy[0]
+
+    def get_grouped_key(self):
+        return (self.embedding_dtype, self.training, self.caching, self.score_strategy, self.bucket_capacity, self.index_type)
+
+
+def align_to_table_size(n: int, alignment: int) -> int:
+    return ((int(n) + alignment - 1) // alignment) * alignment
+
+
+def get_sharded_table_capacity(num_embeddings: int, world_size: int, bucket_capacity: int = DEFAULT_BUCKET_CAPACITY) -> int:
+    """dynamicemb_config.py:696-765: shard_rows = ceil(N/W); capacity = round_up(shard_rows, bucket_capacity)."""
+    if world_size <= 0:
+        raise ValueError(f"world_size must be positive, got {world_size}")
+    if bucket_capacity <= 0 or bucket_capacity % BUCKET_ALIGNMENT != 0:
+        raise ValueError(f"bucket_capacity ({bucket_capacity}) must be a positive multiple of {BUCKET_ALIGNMENT}")
+    shard_rows = math.ceil(int(num_embeddings) / world_size)
+    return align_to_table_size(shard_rows, bucket_capacity)
