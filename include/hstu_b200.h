@@ -1,0 +1,46 @@
+/*
+ * hstu_b200.h — C ABI of the B200-native HSTU jagged attention (librecsys_b200.so).
+ *
+ * Drop-in boundary: what the reference's Python (`hstu.hstu_attn_varlen_func`,
+ * third_party/FBGEMM/fbgemm_gpu/experimental/hstu/hstu/cuda_hstu_attention.py:677-775 -> HstuAttnVarlenFunc :248-670)
+ * calls on sm_100: `hstu_varlen_fwd_100` / `hstu_varlen_bwd_100`
+ * (src/hstu_blackwell/hstu_ops_gpu.py:85-252, :257-512).  Re-cut as plain C: raw DEVICE pointers, element strides,
+ * a cudaStream_t passed as void*, no allocation inside, 0 / negative error code, nothing synchronises.
+ *
+ * Tensors: q, k, v are bf16 (T, H, D) with unit last stride and arbitrary token/head strides that are multiples of 8
+ * elements (views of the fused (T, 4*H*D) uvqk buffer are consumed in place, examples/hstu/ops/fused_hstu_op.py:494-501);
+ * out / dq / dk / dv are bf16 (T, H, D) contiguous.  cu_seqlens int32 (B+1) — cu_seqlens_q == cu_seqlens_k (self attention,
+ * the training case).  num_contexts / num_targets int32 (B), nullable.  window (-1,0) = causal, (-1,-1) = full, else local.
+ * Math: O_i = 1/scaling_seqlen * sum_{j in mask(i)} silu(alpha * q_i.k_j) v_j   (mask: src/hstu_blackwell/mask.py:61-127).
+ */
+#ifndef HSTU_B200_H_
+#define HSTU_B200_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSTU_ERR_ARG (-1100)
+#define HSTU_ERR_UNSUPPORTED (-1101)
+#define HSTU_ERR_WORKSPACE (-1102)
+
+/* strides[6] = {q_token, q_head, k_token, k_head, v_token, v_head} in elements */
+int hstu_fwd_sm100(const void* q, const void* k, const void* v, void* out, const int32_t* cu_seqlens, const int32_t* num_contexts,
+                   const int32_t* num_targets, int batch, int heads, int head_dim, int total_tokens, int max_seqlen, int scaling_seqlen,
+                   int target_group_size, int window_left, int window_right, float alpha, const int64_t* strides, void* stream);
+
+/* strides[8] = q,k,v as above + {do_token, do_head}.  dq/dk/dv contiguous (T,H,D) bf16.  No workspace: dK/dV come from a
+ * KV-stationary kernel and dQ from a Q-stationary kernel, so nothing is accumulated through global memory (the reference
+ * zero-fills and reduce-adds a dense fp32 [B,H,max_seqlen,D] dQ workspace every call, hstu_ops_gpu.py:373-382). */
+int hstu_bwd_sm100(const void* dout, const void* q, const void* k, const void* v, void* dq, void* dk, void* dv, const int32_t* cu_seqlens,
+                   const int32_t* num_contexts, const int32_t* num_targets, int batch, int heads, int head_dim, int total_tokens,
+                   int max_seqlen, int scaling_seqlen, int target_group_size, int window_left, int window_right, float alpha,
+                   const int64_t* strides, void* stream);
+
+/* development aid: one-CTA tcgen05 GEMM that pins the descriptor conventions (csrc/sm100_probe.cu) */
+int sm100_probe_gemm(const void* A, const void* B, float* C, int variant, const uint32_t* overrides, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -437,11 +437,33 @@ __global__ void __launch_bounds__(kBlock) backward_spans_kernel(BwdArgs a) {
     float4 acc[NCHUNK];
 #pragma unroll
     for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; acc[k] = c < D4 ? ld_f4(a.part_start + tile * a.D + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f); }
-    for (int64_t t2 = tile + 1; t2 < tiles && a.skey[t2 << 5] == u; ++t2) {
+    // Lanes look 32 tiles ahead at once (one 4-byte load each); partial rows are fetched 8 at a time so the adds
+    // (kept in ascending tile order) never wait on a dependent load chain — a Zipf-hot id spans thousands of tiles.
+    for (int64_t t2 = tile + 1; t2 < tiles; t2 += 32) {
+      const int64_t tt = t2 + lane;
+      const bool cont = tt < tiles && a.skey[tt << 5] == u;
+      const unsigned m = __ballot_sync(0xffffffffu, cont);
+      const int run = (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);      // contiguous continuation tiles in this window
+      for (int i0 = 0; i0 < run; i0 += 8) {
+        float4 pp[8][NCHUNK];
 #pragma unroll
-      for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; if (c < D4) {
-        float4 p = ld_f4(a.part_cont + t2 * a.D + 4 * c);
-        acc[k].x = __fadd_rn(acc[k].x, p.x); acc[k].y = __fadd_rn(acc[k].y, p.y); acc[k].z = __fadd_rn(acc[k].z, p.z); acc[k].w = __fadd_rn(acc[k].w, p.w); } }
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int k = 0; k < NCHUNK; ++k) {
+            const int c = lane + 32 * k;
+            pp[i][k] = (i0 + i < run && c < D4) ? ld_f4(a.part_cont + (t2 + i0 + i) * a.D + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i0 + i >= run) break;
+#pragma unroll
+          for (int k = 0; k < NCHUNK; ++k) {
+            acc[k].x = __fadd_rn(acc[k].x, pp[i][k].x); acc[k].y = __fadd_rn(acc[k].y, pp[i][k].y);
+            acc[k].z = __fadd_rn(acc[k].z, pp[i][k].z); acc[k].w = __fadd_rn(acc[k].w, pp[i][k].w);
+          }
+        }
+      }
+      if (run < 32) break;
     }
     finish_segment<NCHUNK>(a, u, acc, lane);
   }

@@ -36,27 +36,43 @@ struct Scratch { uint64_t* keys; int32_t* minpos; int32_t* cnt; };
 
 __global__ void unique_claim_kernel(int64_t n, const uint64_t* __restrict__ keys, const int64_t* __restrict__ range, int T, Scratch s,
                                     int32_t* __restrict__ pslot, const int64_t* __restrict__ freq_in, int need_freq) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint64_t key = keys[i];
-    const int t = T > 1 ? table_of(range, T, i) : 0;
-    const int64_t r0 = range ? range[t] : 0, r1 = range ? range[t + 1] : n;
-    // region of table t: [2*r0 + t, 2*r1 + t + 1): 2*(r1-r0) hashed slots + 1 slot reserved for key == ~0
-    const int64_t base = 2 * r0 + t, size = 2 * (r1 - r0);
-    int64_t p;
-    if (key == kEmptyKey) {
-      p = base + size;
-    } else {
-      int64_t q = (int64_t)(fmix64(key) % (uint64_t)size);
-      while (true) {
-        unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(s.keys + base + q), (unsigned long long)kEmptyKey, (unsigned long long)key);
-        if (old == kEmptyKey || old == key) break;
-        if (++q == size) q = 0;
+  const int lane = threadIdx.x & 31;
+  // grid-stride in whole warps so match.any sees a full warp; Zipf-hot ids mostly collide inside a warp, where one
+  // leader lane does the CAS / atomicMin for the whole group (the hot key would otherwise serialise ~7% of all atomics).
+  const int64_t n32 = (n + 31) & ~(int64_t)31;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool act = i < n;
+    const uint64_t key = act ? keys[i] : 0;
+    const int t = (act && T > 1) ? table_of(range, T, i) : 0;
+    // group = same (table, key); inactive lanes form singleton groups
+    const unsigned gk = __match_any_sync(0xffffffffu, act ? key : (0x8000000000000000ull | (uint64_t)lane));
+    const unsigned gt = __match_any_sync(0xffffffffu, act ? t : -1 - lane);
+    const unsigned grp = gk & gt;
+    const int leader = __ffs(grp) - 1;                       // lowest lane = lowest position of the group
+    int64_t p = -1;
+    if (act && lane == leader) {
+      const int64_t r0 = range ? range[t] : 0, r1 = range ? range[t + 1] : n;
+      // region of table t: [2*r0 + t, 2*r1 + t + 1): 2*(r1-r0) hashed slots + 1 slot reserved for key == ~0
+      const int64_t base = 2 * r0 + t, size = 2 * (r1 - r0);
+      if (key == kEmptyKey) {
+        p = base + size;
+      } else {
+        int64_t q = (int64_t)(fmix64(key) % (uint64_t)size);
+        while (true) {
+          unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(s.keys + base + q), (unsigned long long)kEmptyKey, (unsigned long long)key);
+          if (old == kEmptyKey || old == key) break;
+          if (++q == size) q = 0;
+        }
+        p = base + q;
       }
-      p = base + q;
+      atomicMin(s.minpos + p, (int32_t)i);
+      if (need_freq && !freq_in) atomicAdd(s.cnt + p, __popc(grp));
     }
-    atomicMin(s.minpos + p, (int32_t)i);
-    if (need_freq) atomicAdd(s.cnt + p, freq_in ? (int32_t)freq_in[i] : 1);
-    pslot[i] = (int32_t)p;
+    p = __shfl_sync(0xffffffffu, p, leader);
+    if (act) {
+      if (need_freq && freq_in) atomicAdd(s.cnt + p, (int32_t)freq_in[i]);
+      pslot[i] = (int32_t)p;
+    }
   }
 }
 
@@ -134,8 +150,8 @@ int demb_segmented_unique(int64_t n, const void* keys, const int64_t* table_rang
                           int64_t* reverse_indices, int64_t* table_offsets, int64_t* freq_out, int64_t* unique_table_ids,
                           int64_t* num_unique, void* workspace, int64_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (num_tables < 1 || num_tables > 1024) return DEMB_ERR_ARG;
-  if (n <= 0) { unique_empty_kernel<<<1, 1056, 0, stream>>>(table_offsets, num_tables, num_unique); DEMB_CHECK_LAST(); return 0; }
+  if (num_tables < 1 || num_tables > 256) return DEMB_ERR_ARG;
+  if (n <= 0) { unique_empty_kernel<<<1, 288, 0, stream>>>(table_offsets, num_tables, num_unique); DEMB_CHECK_LAST(); return 0; }
   if (n >= (1ll << 30)) return DEMB_ERR_ARG;
   if (num_tables > 1 && !table_range) return DEMB_ERR_ARG;
   if (workspace_bytes < demb_segmented_unique_workspace_bytes(n, num_tables)) return DEMB_ERR_WORKSPACE;

@@ -45,8 +45,10 @@ class DenseRef:
                 st[0] += g * g
                 w -= self.lr * g / (st[0].sqrt() + self.eps)
             elif self.opt == "adam":
-                st[0].mul_(self.b1).add_((1 - self.b1) * g)
-                st[1].mul_(self.b2).add_((1 - self.b2) * g * g)
+                f32 = lambda x: torch.tensor(x, dtype=torch.float32)
+                omb1, omb2 = f32(1.0) - f32(self.b1), f32(1.0) - f32(self.b2)     # fp32 (1 - beta), as optimizer_kernel.cuh:115-131
+                st[0].mul_(self.b1).add_(omb1 * g)
+                st[1].mul_(self.b2).add_(omb2 * g * g)
                 mh, vh = st[0] / (1 - self.b1 ** self.it), st[1] / (1 - self.b2 ** self.it)
                 w -= self.lr * (mh / (vh.sqrt() + self.eps) + self.wd * w)
             elif self.opt == "rowwise":

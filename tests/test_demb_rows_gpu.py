@@ -49,7 +49,9 @@ def _filled_table(cuda, rng, caps, D, state, n_keys, C=128):
     T = len(caps)
     keys = np.unique(rng.integers(0, 1 << 40, size=2 * n_keys, dtype=np.int64))[:n_keys]
     tids = rng.integers(0, T, size=keys.size).astype(np.int64)
-    idx = t.insert(torch.from_numpy(keys).to(cuda), torch.from_numpy(tids).to(cuda), ScoreArg("s", torch.ones(keys.size, dtype=torch.int64, device=cuda)))
+    kt, tt = torch.from_numpy(keys).to(cuda), torch.from_numpy(tids).to(cuda)
+    t.insert(kt, tt, ScoreArg("s", torch.ones(keys.size, dtype=torch.int64, device=cuda)))
+    _, _, idx = t.lookup(kt, tt, ScoreArg("s", None, ScorePolicy.CONST))     # final slots (a full bucket may have evicted early keys)
     return t, values, keys, tids, idx.cpu().numpy()
 
 

@@ -1,0 +1,106 @@
+"""CPU suite: the oracle against fixtures produced by the reference's own Python (tests/golden/gen_golden_cpu.py), host logic, and that
+the C-ABI library loads and exports every symbol include/*.h declares (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def test_hash_matches_reference_python():
+    from oracle import dynamicemb as orc
+    from dynamicemb.scored_hashtable import murmur3_hash_64bits
+    z = np.load(os.path.join(G, "hash_vectors.npz"))
+    for k, want in zip(z["keys"].view(np.uint64).tolist(), z["fmix64"].tolist()):
+        assert orc.fmix64(k) == want
+        assert orc.hash63(k) == want & 0x7FFFFFFFFFFFFFFF          # types.cuh:123-131
+        assert murmur3_hash_64bits(k) == want
+    assert orc.lib().orc_empty_digest() == (orc.fmix64(0xFFFFFFFFFFFFFFFF) & 0x7FFFFFFFFFFFFFFF) >> 32 & 0xFF
+
+
+def test_hstu_mask_matches_reference_construct_mask():
+    from oracle.hstu_attn import build_mask
+    z = np.load(os.path.join(G, "hstu_mask.npz"))
+    for c in range(int(z["ncases"])):
+        B, seqlen, seqlen_c, seqlen_t, Gs, w0, w1, N = z[f"c{c}_meta"].tolist()
+        hist, nc, nt = z[f"c{c}_hist"], z[f"c{c}_nc"], z[f"c{c}_nt"]
+        lens = (hist + nc + nt).tolist()
+        causal = (w0 < 0 and w1 == 0)
+        m = build_mask(lens, N, nc if (seqlen_c and causal) else None, nt if (seqlen_t and causal) else None, Gs, (w0, w1)).numpy()
+        ref = z[f"c{c}_mask"]
+        for b in range(B):
+            L = lens[b]
+            assert np.array_equal(m[b, :L, :L], ref[b, :L, :L]), f"case {c} batch {b}"
+            assert not m[b, L:, :].any() and not m[b, :, L:].any()
+
+
+def test_hstu_oracle_matches_reference_eager():
+    from oracle.hstu_attn import hstu_attention
+    z = np.load(os.path.join(G, "hstu_eager.npz"))
+    for c in range(int(z["ncases"])):
+        H, D, Gs, scaling = z[f"c{c}_meta"].tolist()
+        lens = z[f"c{c}_lens"].tolist()
+        nt = None if z[f"c{c}_nt"][0] < 0 else z[f"c{c}_nt"]
+        nc = None if z[f"c{c}_nc"][0] < 0 else z[f"c{c}_nc"]
+        cu = np.concatenate([[0], np.cumsum(lens)])
+        q, k, v = (torch.from_numpy(z[f"c{c}_{n}"]) for n in "qkv")
+        out = hstu_attention(q, k, v, cu, max(lens), 1.0 / D ** 0.5, scaling, nc, nt, Gs, (-1, 0))
+        torch.testing.assert_close(out, torch.from_numpy(z[f"c{c}_out"]), rtol=1e-5, atol=1e-6)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    lib = ctypes.CDLL(os.path.join(ROOT, "recsys-examples_b200", "lib", "librecsys_b200.so"))
+    names = set()
+    for h in ("dynamicemb_b200.h", "hstu_b200.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(?:int|int64_t)\s+((?:demb|hstu|sm100)_\w+)\s*\(", src))
+    assert len(names) >= 24
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in include/ but not exported"
+
+
+def test_no_cpu_fallback_in_product():
+    """The product must not import the oracle (tier rule); grep the package."""
+    pkg = os.path.join(ROOT, "recsys-examples_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(".py"):
+                s = open(os.path.join(dp, f)).read()
+                assert "oracle" not in s.replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+def test_oracle_table_invariants():
+    """test_table_operation.py:277-526 invariants on the oracle itself."""
+    from oracle.dynamicemb import OracleTable
+    rng = np.random.default_rng(0)
+    o = OracleTable([128 * 4], 128)
+    keys = np.unique(rng.integers(0, 1 << 60, size=400, dtype=np.int64))
+    idx, res, _, _ = o.insert(keys, None, policy=1, score_in=np.ones(keys.size, dtype=np.int64))
+    assert (res == 0).all() and len(set(idx.tolist())) == keys.size
+    idx2, res2, _, _ = o.insert(keys, None, policy=1, score_in=np.full(keys.size, 2, dtype=np.int64))
+    assert (res2 == 2).all() and np.array_equal(idx, idx2)
+    _, f, i = o.lookup(keys, None, policy=0)
+    assert f.all() and np.array_equal(i, idx)
+    o.erase(keys[:100])
+    _, f, _ = o.lookup(keys[:100], None, policy=0)
+    assert not f.any()
+    # fill to capacity then overflow => EVICT of the minimum-score slot; erased slots are reclaimed first only when no empty slot is left
+    more = np.unique(rng.integers(1 << 60, 1 << 61, size=700, dtype=np.int64))
+    _, res3, _, (ek, ei, es, _) = o.insert(more, None, policy=1, score_in=np.full(more.size, 5, dtype=np.int64))
+    assert set(res3.tolist()) <= {0, 1, 3}
+    assert (res3 == 1).sum() > 0 and (res3 == 3).sum() > 0
+    assert o.bucket_sizes.sum() <= 512
+
+
+def test_get_sharded_table_capacity():
+    from dynamicemb import get_sharded_table_capacity
+    assert get_sharded_table_capacity(1000, 8, 128) == 128
+    assert get_sharded_table_capacity(10_000_000_000, 8, 128) == 1_250_000_000 // 128 * 128 + (128 if 1_250_000_000 % 128 else 0)
+    with pytest.raises(ValueError):
+        get_sharded_table_capacity(10, 0, 128)
