@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for the two hot paths.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (torchrun launches N>1 ranks)
+  python bench.py --impl reference ...                      the reference's CPU path of the same workload (oracle port), rank 0 only
+
+Workload (BASELINE.json configs[1]): DynamicEmb hash-table embedding, key space 1e9, D=128 fp32, fused Adagrad in backward, ids from
+the reference's power-law generator (corelib/dynamicemb/benchmark/dataset_generator.py:4-22, alpha 1.05), 2^20 ids per step per GPU,
+sequence output.  Table: 32 Mi rows x 1 KiB ([emb | Adagrad state]) + 0.5 GiB key map per GPU, pre-filled to ~50 % load with ids
+of the same distribution, STEP scores with eviction.  A "step" = BatchedDynamicEmbeddingTablesV2.forward (dedup, probe, insert+init
+of new ids, gather) + backward (gradient reduce + Adagrad row update).  N>1: row-wise sharded (hash_roundrobin) with NCCL all_to_all
+of ids and rows, each rank feeds its own 2^20-id batch (weak scaling).  Second hot path (configs[2]): HSTU attention fwd+bwd,
+B=32 x S=4096 causal, H=8, D=128 bf16, reported under "hstu_attn".
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "recsys-examples_b200"))
+
+D = 128
+KEY_SPACE = 1_000_000_000
+ALPHA = 1.05
+METRIC = "128-d embedding lookups/sec (DynamicEmb lookup + fused Adagrad update, Zipf 1.05)"
+UNIT = "lookups/s"
+
+
+def power_law_ids(n, gen, device):
+    """PowerLaw(1, KEY_SPACE, alpha) — restates dataset_generator.py:4-22 (inverse-CDF on float64)."""
+    x = torch.rand(n, device=device, dtype=torch.float64, generator=gen)
+    g = 1.0 - ALPHA
+    y = torch.pow(x * (KEY_SPACE ** g - 1.0) + 1.0, 1.0 / g)
+    y = torch.clamp(y, max=KEY_SPACE - 1)
+    return y.to(torch.int64)
+
+
+def _lsr(x, n):
+    return (x >> n) & ((1 << (64 - n)) - 1)
+
+
+def fmix64_torch(x):
+    """murmur3 fmix64 on int64 tensors (two's-complement wraparound = uint64 arithmetic); returns the low 63 bits as a
+    non-negative int64 plus the top bit folded in the same way `uint64 % W` needs for W a power of two (W = 2, 4, 8)."""
+    k = x.clone()
+    k = k ^ _lsr(k, 33)
+    k = k * (-49064778989728563)          # 0xff51afd7ed558ccd as int64
+    k = k ^ _lsr(k, 33)
+    k = k * (-4265267296055464877)        # 0xc4ceb9fe1a85ec53 as int64
+    k = k ^ _lsr(k, 33)
+    return k & 0x7FFFFFFFFFFFFFFF         # for power-of-two W the low bits are all that matter
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return j["hbm_gbs"], j["bf16_tflops"], "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(int(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+
+
+# ---------------------------------------------------------------------------------------------------------------- CPU baseline
+def cpu_reference_step_factory(n_ids, seed):
+    """The reference's CPU path of this workload, as a port: TorchRec CPU EmbeddingCollection is an nn.Embedding-style dense
+    gather per table; dynamic keys need a key->row map first, done by the oracle's restatement of the reference hash
+    table (oracle/dynamicemb_oracle.c, sequential C).  Gather / per-key gradient reduce / Adagrad run in multi-threaded torch CPU ops."""
+    from oracle.dynamicemb import OracleTable
+    torch.set_num_threads(os.cpu_count())
+    cap = 1 << 22
+    tab = OracleTable([cap], 128)
+    values = torch.zeros(cap, 2 * D)
+    gen = torch.Generator().manual_seed(seed)
+
+    def step():
+        ids = power_law_ids(n_ids, gen, "cpu")
+        uk, inv = torch.unique(ids, return_inverse=True)
+        _, found, slots = tab.lookup(uk.numpy(), None, policy=1, score_in=np.ones(uk.numel(), dtype=np.int64))
+        miss = ~found
+        if miss.any():
+            new_slots, _, _, _ = tab.insert(uk.numpy()[miss], None, policy=1, score_in=np.ones(int(miss.sum()), dtype=np.int64))
+            slots[miss] = new_slots
+            ns = torch.from_numpy(new_slots[new_slots >= 0])
+            values[ns, :D] = torch.empty(ns.numel(), D).uniform_(-0.01, 0.01)
+            values[ns, D:] = 0
+        rows = torch.from_numpy(slots).clamp(min=0)
+        out = values[rows[inv], :D]                                   # forward gather
+        grad = torch.ones_like(out)
+        ug = torch.zeros(uk.numel(), D).index_add_(0, inv, grad)      # reduce per unique key
+        st = values[rows, D:] + ug * ug                               # Adagrad
+        values[rows, D:] = st
+        values[rows, :D] -= 0.01 * ug / (st.sqrt() + 1e-8)
+        return n_ids
+
+    return step
+
+
+def cpu_baseline(budget_s=12.0, n_ids=1 << 17):
+    step = cpu_reference_step_factory(n_ids, 7)
+    step()
+    t0, done = time.perf_counter(), 0
+    while time.perf_counter() - t0 < budget_s:
+        done += step()
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{done // n_ids} steps x {n_ids} ids of the same power-law stream, 4 Mi-row table, {dt:.1f} s wall"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    n_ids = 1 << 17
+    step = cpu_reference_step_factory(n_ids, 7)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = n_ids * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, n_ids),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"each step = {n_ids} ids (1/8 of the GPU arm's 2^20-id step) of the same power-law stream"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, n_ids):
+    return {"workload": "dynamicemb_keyspace1e9_d128_fp32_adagrad_zipf1.05_seq", "ids_per_step_per_gpu": n_ids, "table_rows_per_gpu": args.capacity,
+            "bucket_capacity": 128, "score_strategy": "STEP", "prefill_load": 0.5, "parallelism": f"row-wise x{args.gpus} (hash_roundrobin, all_to_all)" if args.gpus > 1 else "single GPU",
+            "l2": "tables (32 GiB) and per-step id/gradient streams exceed the 126 MB L2; a fresh id batch every step"}
+
+
+# ---------------------------------------------------------------------------------------------------------------- HSTU side bench
+def bench_hstu(dev, tflops_peak, iters=10):
+    try:
+        from hstu import hstu_ops_gpu as ops
+        B, S, H, Dh = 32, 4096, 8, 128
+        T = B * S
+        buf = torch.randn(T, 4 * H * Dh, device=dev, dtype=torch.bfloat16)
+        _, v, q, k = (t.view(T, H, Dh) for t in buf.split(H * Dh, dim=-1))
+        dout = torch.randn(T, H, Dh, device=dev, dtype=torch.bfloat16)
+        cu = torch.arange(0, T + 1, S, dtype=torch.int32, device=dev)
+        alpha = 1 / math.sqrt(Dh)
+        fwd = lambda: ops.hstu_varlen_fwd_100(q, k, v, cu, cu, S, S, None, None, 1, -1, 0, alpha)
+        bwd = lambda: ops.hstu_varlen_bwd_100(dout, q, k, v, cu, cu, S, S, None, None, None, None, None, 1, -1, 0, alpha)
+        res = {}
+        flops_fwd = 2.0 * H * Dh * S * S * B          # causal: 4*H*D*S^2/2 (examples/commons/utils/perf.py:729-739)
+        for name, f, fl in (("fwd", fwd, flops_fwd), ("bwd", bwd, 2.5 * flops_fwd)):
+            for _ in range(3):
+                f()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(iters):
+                e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+                e0.record(); f(); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = sorted(ts)[len(ts) // 10]            # P10 like hstu_attn_kernel_benchmark.py
+            res[name] = {"ms": ms, "tflops": fl / ms / 1e9, "frac_of_bf16_peak": fl / ms / 1e9 / tflops_peak}
+        res["samples_per_s_attn_only_8_layers"] = B / ((res["fwd"]["ms"] + res["bwd"]["ms"]) * 8 / 1e3)
+        res["config"] = "B=32 S=4096 causal H=8 D=128 bf16, q/k/v strided views of one (T, 4HD) buffer"
+        return res
+    except Exception as e:  # report, never kill the embedding line
+        return {"error": repr(e)[:300]}
+
+
+# ---------------------------------------------------------------------------------------------------------------- main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--ids", type=int, default=1 << 20)
+    ap.add_argument("--capacity", type=int, default=32 * 1024 * 1024)
+    ap.add_argument("--no-hstu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from dynamicemb import (BatchedDynamicEmbeddingTablesV2, DynamicEmbInitializerArgs, DynamicEmbInitializerMode, DynamicEmbPoolingMode,
+                            DynamicEmbScoreStrategy, DynamicEmbTableOptions, EmbOptimType)
+    from dynamicemb import _native as N
+    from dynamicemb import dynamicemb_extensions as ext
+    from dynamicemb.scored_hashtable import ScoreArg
+    from dynamicemb.dynamicemb_extensions import ScorePolicy
+
+    n_ids = args.ids
+    opt = DynamicEmbTableOptions(dim=D, max_capacity=args.capacity, local_hbm_for_values=1 << 50, score_strategy=DynamicEmbScoreStrategy.STEP,
+                                 initializer_args=DynamicEmbInitializerArgs(mode=DynamicEmbInitializerMode.UNIFORM, lower=-0.01, upper=0.01))
+    m = BatchedDynamicEmbeddingTablesV2([opt], table_names=["t0"], pooling_mode=DynamicEmbPoolingMode.NONE, optimizer=EmbOptimType.EXACT_ADAGRAD,
+                                        learning_rate=0.1, eps=1e-8, device=dev)
+    m.train()
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    # ---- prefill to ~50 % load with ids of the same distribution (keys owned by this rank only when sharded)
+    target = args.capacity // 2
+    filled = 0
+    while filled < target:
+        ids = torch.unique(power_law_ids(1 << 24, gen, dev))
+        if world > 1:   # keep only the keys this rank owns under hash_roundrobin (fmix64(id) % W)
+            ids = ids[(fmix64_torch(ids) % world) == rank]
+        ids = ids[: target - filled + (1 << 20)]
+        z = torch.zeros(ids.numel(), dtype=torch.int64, device=dev)
+        slots = m.tables.insert(ids, z, ScoreArg("score", torch.ones(ids.numel(), dtype=torch.int64, device=dev), ScorePolicy.ASSIGN))
+        ext.init_rows(m._values, D, slots, ids, ext.InitializerMode.UNIFORM, -0.01, 0.01, seed=1)
+        filled = m.tables.size()
+        if ids.numel() < (1 << 16):
+            break
+    if world > 1:
+        from dynamicemb.shard import RowWiseShardedDynamicEmbedding
+        model = RowWiseShardedDynamicEmbedding(m, None, dist_type="hash_roundrobin", use_index_dedup=True)
+        lengths = torch.ones(n_ids, dtype=torch.int64, device=dev)
+        call = lambda ids: model(ids, lengths)
+    else:
+        offsets = torch.arange(0, n_ids + 1, dtype=torch.int64, device=dev)
+        call = lambda ids: m(ids, offsets)
+    grad = torch.randn(n_ids, D, device=dev)
+    total = args.steps + args.warmup
+    batches = [power_law_ids(n_ids, gen, dev) for _ in range(total)]
+
+    def step(ids):
+        out = call(ids)
+        out.backward(grad)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(batches[i])
+    # ---- timed region: device-resident inputs
+    N.lib.demb_profile_enable(1)
+    N.PROFILE = {}
+    N.LAUNCHES[0] = 0
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    bwd_stage_ms = np.zeros(3)
+    for i in range(args.steps):
+        step(batches[args.warmup + i])
+        if i == args.steps - 1:
+            pass
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = N.LAUNCHES[0] // args.steps
+    prof = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in N.PROFILE.items()}
+    buf = (torch.zeros(3, dtype=torch.float32)).numpy()
+    import ctypes
+    N.lib.demb_profile_read(buf.ctypes.data_as(ctypes.c_void_p))
+    bwd_stage_ms = buf.copy()
+    N.PROFILE = None
+    N.lib.demb_profile_enable(0)
+    clk = clocks.stop()
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * n_ids * args.steps / (ms / 1e3)
+
+    # ---- e2e: pinned host ids -> H2D, step, D2H of the step result (sum of the looked-up rows)
+    host_batches = [b.cpu().pin_memory() for b in batches[args.warmup:]]
+    dev_ids = torch.empty(n_ids, dtype=torch.int64, device=dev)
+    host_res = torch.zeros(1, dtype=torch.float32).pin_memory()
+    barrier()
+    e0.record()
+    for hb in host_batches:
+        dev_ids.copy_(hb, non_blocking=True)
+        out = step(dev_ids)
+        host_res.copy_(out.sum().reshape(1), non_blocking=False)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_ids * args.steps / (float(t.item()) / 1e3)
+
+    if rank == 0:
+        hbm, tfl, which = peaks()
+        # ---- roofline of the dominant kernel.  Algorithmic bytes:
+        #   gather_forward : N_t*(8 inverse + 512 out) + N_u*(8 row id + 512 row)
+        #   backward tiles : N_t*(512 grad + 8 sorted pair) + N_u*(2*1024 row RW + 8)
+        with torch.no_grad():
+            nu = int(torch.unique(batches[-1]).numel())
+        cands = {"forward_seq_kernel (gather_forward)": (prof.get("gather_forward", 0.0), n_ids * (8 + 512) + nu * (8 + 512)),
+                 "backward_tiles_kernel": (float(bwd_stage_ms[1]), n_ids * (512 + 8) + nu * (2 * 1024 + 8))}
+        dom = max(cands.items(), key=lambda kv: kv[1][0])
+        kms, kbytes = dom[1]
+        roof = {"kernel": dom[0], "bound": "hbm", "achieved": kbytes / kms / 1e6 if kms > 0 else None, "peak": hbm, "unit": "GB/s",
+                "frac": (kbytes / kms / 1e6 / hbm) if kms > 0 else None, "traffic": None, "peak_source": which,
+                "algorithmic_bytes_per_launch": kbytes, "ms_per_launch": kms,
+                "other_kernels_ms": {**{k: round(v, 4) for k, v in prof.items()}, "backward.pairs+sort": float(bwd_stage_ms[0]),
+                                     "backward.tiles": float(bwd_stage_ms[1]), "backward.spans": float(bwd_stage_ms[2])}}
+        # the north_star's headline kernel: fused probe+gather forward (eval path) on the same ids
+        m.eval()
+        ev = []
+        for i in range(5):
+            a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+            a.record(); m(batches[-1 - i], offsets if world == 1 else torch.arange(0, n_ids + 1, dtype=torch.int64, device=dev)); b.record()
+            torch.cuda.synchronize()
+            ev.append(a.elapsed_time(b))
+        m.train()
+        fms = sorted(ev)[1]
+        fbytes = n_ids * (8 + 512) + nu * (24 + 512)
+        roof["fused_lookup_forward"] = {"ms": fms, "algorithmic_bytes": fbytes, "achieved_GBps": fbytes / fms / 1e6, "frac": fbytes / fms / 1e6 / hbm,
+                                        "lookups_per_s": n_ids / fms * 1e3}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(args, n_ids), "clocks": clk,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_ids * 8, "d2h_bytes_per_step": 4},
+                "gpu_launches": launches, "roofline": roof, "table_load": m.tables.size() / args.capacity}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline()
+        if world == 1 and not args.no_hstu:
+            del batches, host_batches
+            line["hstu_attn"] = bench_hstu(dev, tfl)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

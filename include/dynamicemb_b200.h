@@ -149,6 +149,10 @@ int demb_update_rows(float* values, int64_t value_dim, int emb_dim, int64_t n, c
                      int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
                      float bias_correction2, void* stream);
 
+/* measurement aid for bench.py: CUDA events around the stages of demb_backward; read returns ms of {pairs+sort, tiles, spans} */
+int demb_profile_enable(int on);
+int demb_profile_read(float* ms3);
+
 /* ---- row-wise sharding input dist (replaces src/sparse_block_bucketize_features.cu:372) ---- */
 int64_t demb_bucketize_workspace_bytes(int64_t num_slots, int world_size);
 /* dist_type_per_feature[F]: 0 continuous, 1 roundrobin, 2 hash_roundrobin; block_sizes[F].  new_lengths[W*S] rank-major. */

@@ -503,6 +503,10 @@ __global__ void __launch_bounds__(kBlock) update_rows_kernel(float* __restrict__
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 inline int nchunk_of(int D) { return (D / 4 + 31) / 32; }
 
+// bench.py's roofline needs per-kernel device time of the multi-kernel backward: optional CUDA events around its stages.
+bool g_prof_on = false;
+cudaEvent_t g_prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
 }  // namespace
 
 #define DISPATCH_NCHUNK(D, ...)                                          \
@@ -616,17 +620,34 @@ int demb_backward(float* values, int64_t value_dim, int emb_dim, int64_t n, cons
   float* pc = (float*)w; w += align256(tiles * (size_t)emb_dim * 4);
   float* ps = (float*)w; w += align256(tiles * (size_t)emb_dim * 4);
   size_t tmp_bytes = (size_t)((uint8_t*)workspace + workspace_bytes - w);
+  if (g_prof_on) cudaEventRecord(g_prof_ev[0], stream);
   backward_pairs_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(n, inverse, pooled, batch_size, num_features, offsets, k0, v0);
   int end_bit = 1; while (end_bit < 31 && (1ll << end_bit) < num_unique_bound) ++end_bit;
   cudaError_t e = cub::DeviceRadixSort::SortPairs(w, tmp_bytes, k0, k1, v0, v1, (int)n, 0, end_bit, stream);
   if (e != cudaSuccess) return -(int)e;
   BwdArgs a{grads, grad_stride, emb_dim, pooled, combiner, batch_size, num_features, offsets, k1, v1, n, rows, values, value_dim, unique_grads, pc, ps,
             OptArgs{opt_type, lr, eps, beta1, beta2, weight_decay, bias_correction1, bias_correction2}};
+  if (g_prof_on) cudaEventRecord(g_prof_ev[1], stream);
   DISPATCH_NCHUNK(emb_dim, {
     backward_tiles_kernel<NC><<<warp_grid((int64_t)tiles), kBlock, 0, stream>>>(a);
+    if (g_prof_on) cudaEventRecord(g_prof_ev[2], stream);
     if (tiles > 1) backward_spans_kernel<NC><<<warp_grid((int64_t)tiles - 1), kBlock, 0, stream>>>(a);
+    if (g_prof_on) cudaEventRecord(g_prof_ev[3], stream);
   });
   DEMB_CHECK_LAST();
+  return 0;
+}
+
+int demb_profile_enable(int on) {
+  if (on && !g_prof_ev[0]) for (int i = 0; i < 4; ++i) if (cudaEventCreate(&g_prof_ev[i]) != cudaSuccess) return DEMB_ERR_ARG;
+  g_prof_on = on != 0;
+  return 0;
+}
+// stage times (ms) of the most recent demb_backward: [pairs + sort, tiles kernel, spans kernel]; synchronises on the last event
+int demb_profile_read(float* ms3) {
+  if (!g_prof_ev[0]) return DEMB_ERR_ARG;
+  if (cudaEventSynchronize(g_prof_ev[3]) != cudaSuccess) return DEMB_ERR_ARG;
+  for (int i = 0; i < 3; ++i) if (cudaEventElapsedTime(&ms3[i], g_prof_ev[i], g_prof_ev[i + 1]) != cudaSuccess) return DEMB_ERR_ARG;
   return 0;
 }
 

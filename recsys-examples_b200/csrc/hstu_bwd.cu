@@ -36,7 +36,9 @@ struct Params {
   float scale0;          // dKV: 1/N (dV)        dQ: alpha/N
   float scale1;          // dKV: alpha/N (dK)
   int target_group, win_left, win_right;
+  volatile int* dbg;     // optional host-mapped progress buffer
 };
+#define HSTU_DBG(slot, val) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { p.dbg[(kIsDQ ? 64 : 32) + (slot)] = (val); __threadfence_system(); } } while (0)
 
 struct SeqMask {
   int L, seqlen_c, seqlen_h, G, wl, wr;
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
         const int st = j & 1, ph = (j >> 1) & 1;
         const int row = seq_start + y_tile_of(j) * 64;
         mbar_wait(&y_empty[st], ph ^ 1);
+        HSTU_DBG(1, j + 1);
         mbar_arrive_expect_tx(&y_full[st], 2 * SM::kY);
         uint8_t* y1 = smem + SM::oY + st * 2 * SM::kY;
 #pragma unroll
@@ -175,12 +178,17 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
         }
         umma_commit(&s_full[st]);
       };
+      HSTU_DBG(8, n_iter);
       mbar_wait(&x_full, 0);
+      HSTU_DBG(9, 1);
       issue_scores(0);
+      HSTU_DBG(10, 1);
       for (int j = 0; j < n_iter; ++j) {
         if (j + 1 < n_iter) issue_scores(j + 1);
         const int st = j & 1, ph = (j >> 1) & 1;
+        HSTU_DBG(11, j + 1);
         mbar_wait(&pd_full[st], ph);
+        HSTU_DBG(12, j + 1);
         tc_fence_after();
         const uint32_t aY1 = smem_u32(smem + SM::oY + st * 2 * SM::kY), aY2 = aY1 + SM::kY;
         const uint32_t aDS = smem_u32(smem + SM::oDS + st * SM::kPD);
@@ -197,6 +205,7 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
         umma_commit(&y_empty[st]);
       }
       umma_commit(&acc_full);
+      HSTU_DBG(13, 1);
     }
   } else if (warp >= 4) {
     const int wq = warp & 3;                        // TMEM lane quadrant
@@ -208,7 +217,9 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
       const int st = j & 1, ph = (j >> 1) & 1;
       const int y0 = y_tile_of(j) * 64;
       const bool full = kIsDQ ? mk.tile_full(x0, x1, y0, y0 + 63) : mk.tile_full(y0, y0 + 63, x0, x1);
+      if (threadIdx.x == 128) HSTU_DBG(16, j + 1);
       mbar_wait(&s_full[st], ph);
+      if (threadIdx.x == 128) HSTU_DBG(17, j + 1);
       tc_fence_after();
       uint32_t s[32], dp[32];
       tmem_ld32(tS[st] + lane_off + ch * 32, s);
@@ -250,9 +261,11 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pd_full[st]);
+      if (threadIdx.x == 128) HSTU_DBG(18, j + 1);
     }
     // epilogue: dKV: warps 4-7 store dV (acc0), warps 8-11 store dK (acc1); dQ: the two warpgroups split the D columns
     mbar_wait(&acc_full, 0);
+    if (threadIdx.x == 128) HSTU_DBG(19, 1);
     tc_fence_after();
     if (xi < L) {
       const uint32_t tacc = kIsDQ ? tA0 : (ch == 0 ? tA0 : tA1);
@@ -299,6 +312,7 @@ int launch(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMap& y1, 
 
 }  // namespace hstu_bwd
 
+extern "C" volatile int* hstu_get_debug_buffer();
 extern "C" int hstu_bwd_sm100(const void* dout, const void* q, const void* k, const void* v, void* dq, void* dk, void* dv, const int32_t* cu_seqlens,
                               const int32_t* num_contexts, const int32_t* num_targets, int batch, int heads, int head_dim, int total_tokens,
                               int max_seqlen, int scaling_seqlen, int target_group_size, int window_left, int window_right, float alpha,
@@ -320,6 +334,7 @@ extern "C" int hstu_bwd_sm100(const void* dout, const void* q, const void* k, co
   p.H = heads; p.half_alpha = 0.5f * alpha;
   p.target_group = target_group_size; p.win_left = window_left; p.win_right = window_right;
   const float invN = 1.0f / (float)scaling_seqlen;
+  p.dbg = hstu_get_debug_buffer();
   int rc;
   // dK, dV: X = (K, V), Y = (Q, dO)
   p.out0 = reinterpret_cast<__nv_bfloat16*>(dv); p.out1 = reinterpret_cast<__nv_bfloat16*>(dk); p.scale0 = invN; p.scale1 = alpha * invN;

@@ -33,7 +33,11 @@ struct FwdParams {
   float inv_scale;               // 1 / scaling_seqlen
   int target_group;
   int win_left, win_right;       // -1 = unbounded
+  volatile int* dbg;             // optional host-mapped progress buffer (hstu_set_debug_buffer), nullptr in production
 };
+
+// progress marks readable from the host even if the kernel never finishes (development aid)
+#define HSTU_DBG(slot, val) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { p.dbg[slot] = (val); __threadfence_system(); } } while (0)
 
 struct SeqMask {
   int L, seqlen_c, seqlen_h, G, wl, wr;
@@ -116,6 +120,7 @@ __global__ void __launch_bounds__(256, 1) hstu_fwd_kernel(const __grid_constant_
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      HSTU_DBG(0, 1);
       mbar_arrive_expect_tx(&q_full, SM::kTile);
 #pragma unroll
       for (int hf = 0; hf < NH; ++hf) tma_load_3d(smem + SM::kQ + hf * 16384, &map_q, &q_full, hf * 64, h, seq_start + r0);
@@ -123,10 +128,12 @@ __global__ void __launch_bounds__(256, 1) hstu_fwd_kernel(const __grid_constant_
         const int st = j & 1, ph = (j >> 1) & 1;
         const int row = seq_start + (nb0 + j) * 128;
         mbar_wait(&k_empty[st], ph ^ 1);
+        HSTU_DBG(1, j + 1);
         mbar_arrive_expect_tx(&k_full[st], SM::kTile);
 #pragma unroll
         for (int hf = 0; hf < NH; ++hf) tma_load_3d(smem + SM::kK + st * SM::kTile + hf * 16384, &map_k, &k_full[st], hf * 64, h, row);
         mbar_wait(&v_empty[st], ph ^ 1);
+        HSTU_DBG(2, j + 1);
         mbar_arrive_expect_tx(&v_full[st], SM::kTile);
 #pragma unroll
         for (int hf = 0; hf < NH; ++hf) tma_load_3d(smem + SM::kV + st * SM::kTile + hf * 16384, &map_v, &v_full[st], hf * 64, h, row);
@@ -152,13 +159,18 @@ __global__ void __launch_bounds__(256, 1) hstu_fwd_kernel(const __grid_constant_
         umma_commit(&s_full[st]);
         umma_commit(&k_empty[st]);
       };
+      HSTU_DBG(8, n_iter);
       mbar_wait(&q_full, 0);
+      HSTU_DBG(9, 1);
       issue_qk(0);
+      HSTU_DBG(10, 1);
       for (int j = 0; j < n_iter; ++j) {
         if (j + 1 < n_iter) issue_qk(j + 1);
         const int st = j & 1, ph = (j >> 1) & 1;
         mbar_wait(&v_full[st], ph);
+        HSTU_DBG(11, j + 1);
         mbar_wait(&p_full, j & 1);
+        HSTU_DBG(12, j + 1);
         tc_fence_after();
         const uint32_t aV = smem_u32(smem + SM::kV + st * SM::kTile);
 #pragma unroll
@@ -170,6 +182,7 @@ __global__ void __launch_bounds__(256, 1) hstu_fwd_kernel(const __grid_constant_
         umma_commit(&p_empty);
       }
       umma_commit(&o_full);
+      HSTU_DBG(13, 1);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ SiLU warpgroup + epilogue
@@ -182,7 +195,9 @@ __global__ void __launch_bounds__(256, 1) hstu_fwd_kernel(const __grid_constant_
       const int st = j & 1, ph = (j >> 1) & 1;
       const int c_base = (nb0 + j) * 128;
       const bool full = mk.tile_full(r0, r1, c_base, c_base + 127);
+      if (threadIdx.x == 128) HSTU_DBG(16, j + 1);
       mbar_wait(&s_full[st], ph);
+      if (threadIdx.x == 128) HSTU_DBG(17, j + 1);
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
@@ -217,9 +232,11 @@ __global__ void __launch_bounds__(256, 1) hstu_fwd_kernel(const __grid_constant_
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full);
+      if (threadIdx.x == 128) HSTU_DBG(18, j + 1);
     }
     // epilogue
     mbar_wait(&o_full, 0);
+    if (threadIdx.x == 128) HSTU_DBG(19, 1);
     tc_fence_after();
     __nv_bfloat16* orow = p.out + ((int64_t)(seq_start + row) * p.H + h) * D;
 #pragma unroll
@@ -262,6 +279,10 @@ int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mkk, const CUtensorMap&
 
 }  // namespace hstu
 
+static volatile int* g_hstu_dbg = nullptr;
+extern "C" int hstu_set_debug_buffer(int* host_mapped) { g_hstu_dbg = host_mapped; return 0; }
+extern "C" volatile int* hstu_get_debug_buffer() { return g_hstu_dbg; }
+
 extern "C" int hstu_fwd_sm100(const void* q, const void* k, const void* v, void* out, const int32_t* cu_seqlens, const int32_t* num_contexts,
                               const int32_t* num_targets, int batch, int heads, int head_dim, int total_tokens, int max_seqlen, int scaling_seqlen,
                               int target_group_size, int window_left, int window_right, float alpha, const int64_t* strides /*q_t,q_h,k_t,k_h,v_t,v_h (elements)*/,
@@ -281,6 +302,7 @@ extern "C" int hstu_fwd_sm100(const void* q, const void* k, const void* v, void*
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.H = heads; p.half_alpha = 0.5f * alpha; p.inv_scale = 1.0f / (float)scaling_seqlen;
   p.target_group = target_group_size; p.win_left = window_left; p.win_right = window_right;
+  p.dbg = g_hstu_dbg;
   if (head_dim == 128) return hstu::launch_fwd<128>(mq, mk, mv, p, batch, max_seqlen, (cudaStream_t)stream);
   return hstu::launch_fwd<64>(mq, mk, mv, p, batch, max_seqlen, (cudaStream_t)stream);
 }

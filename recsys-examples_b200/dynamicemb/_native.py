@@ -45,6 +45,8 @@ _SIGS = {
     "demb_backward_workspace_bytes": (I64, [I64, I32]),
     "demb_backward": (I32, [P, I64, I32, I64, P, I64, P, P, I64, P, I64, I32, I32, I32, F32, F32, F32, F32, F32, F32, F32, P, P, I64, P]),
     "demb_update_rows": (I32, [P, I64, I32, I64, P, P, I64, I32, F32, F32, F32, F32, F32, F32, F32, P]),
+    "demb_profile_enable": (I32, [I32]),
+    "demb_profile_read": (I32, [P]),
     "demb_bucketize_workspace_bytes": (I64, [I64, I32]),
     "demb_block_bucketize_sparse_features": (I32, [I64, I64, I32, P, P, P, P, P, P, P, P, P, P, I64, P]),
 }
@@ -76,6 +78,23 @@ def ptr(t):
 
 def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ---- measurement hook (bench.py): CUDA events around selected C-ABI calls + a count of this library's kernel launches
+PROFILE = None            # dict name -> list[(start_event, end_event)] when enabled
+LAUNCHES = [0]            # number of librecsys_b200 kernels launched (ours, excluding cub / memset nodes)
+
+
+def launch(name: str, kernels: int, fn, *args):
+    LAUNCHES[0] += kernels
+    if PROFILE is None:
+        return fn(*args)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    rc = fn(*args)
+    e.record()
+    PROFILE.setdefault(name, []).append((s, e))
+    return rc
 
 
 _ws_cache = {}

@@ -120,7 +120,7 @@ def table_lookup(table_storage, table_bucket_offsets, bucket_capacity, keys, tab
     keys = keys.contiguous()
     table_ids = _i64(table_ids)
     score_input = _u64_view(score_input)
-    N.check(N.lib.demb_table_lookup(N.ptr(table_storage), N.ptr(table_bucket_offsets), bucket_capacity, num_scores, n, N.ptr(keys),
+    N.check(N.launch("table_lookup", 1, N.lib.demb_table_lookup, N.ptr(table_storage), N.ptr(table_bucket_offsets), bucket_capacity, num_scores, n, N.ptr(keys),
                                     N.ptr(table_ids), int(policy_type), N.ptr(score_input), int(timestamp), N.ptr(founds), N.ptr(indices),
                                     N.ptr(score_out), N.stream()), "table_lookup")
     return score_out, founds, indices
@@ -144,7 +144,7 @@ def _insert_impl(table_storage, table_bucket_offsets, bucket_capacity, bucket_si
     ws_bytes = N.lib.demb_table_insert_workspace_bytes(n)
     ws = N.workspace(ws_bytes, dev)
     nb_total = bucket_sizes.numel()
-    N.check(N.lib.demb_table_insert(
+    N.check(N.launch("table_insert", 4, N.lib.demb_table_insert,
         N.ptr(table_storage), N.ptr(table_bucket_offsets), bucket_capacity, num_scores, nb_total, N.ptr(bucket_sizes), n, N.ptr(keys),
         N.ptr(table_ids), int(policy_type), N.ptr(score_input), int(timestamp), N.ptr(counter), 1 if keys.dtype == torch.int64 else 0,
         N.ptr(insert_results), N.ptr(indices), N.ptr(score_output),
@@ -183,7 +183,7 @@ def table_update_counter_with_layout(counter, slot_indices, delta, table_bucket_
     n = slot_indices.numel()
     if n == 0:
         return
-    N.check(N.lib.demb_counter_update(N.ptr(counter), N.ptr(_i64(slot_indices)), N.ptr(_i64(table_ids)), N.ptr(table_bucket_offsets),
+    N.check(N.launch("counter_update", 1, N.lib.demb_counter_update, N.ptr(counter), N.ptr(_i64(slot_indices)), N.ptr(_i64(table_ids)), N.ptr(table_bucket_offsets),
                                       bucket_capacity, n, int(delta), N.stream()), "table_update_counter_with_layout")
 
 
@@ -231,7 +231,7 @@ def segmented_unique_cuda(keys: torch.Tensor, segment_range: Optional[torch.Tens
     utids = torch.empty(n, dtype=torch.int64, device=dev) if want_table_ids else None
     ws_bytes = N.lib.demb_segmented_unique_workspace_bytes(n, num_tables)
     ws = N.workspace(ws_bytes, dev)
-    N.check(N.lib.demb_segmented_unique(n, N.ptr(keys.contiguous()), N.ptr(_i64(segment_range)) if num_tables > 1 else None, num_tables,
+    N.check(N.launch("segmented_unique", 4, N.lib.demb_segmented_unique, n, N.ptr(keys.contiguous()), N.ptr(_i64(segment_range)) if num_tables > 1 else None, num_tables,
                                         N.ptr(_i64(freq_in)), N.ptr(unique_keys), N.ptr(reverse), N.ptr(table_offsets), N.ptr(freq_out),
                                         N.ptr(utids), N.ptr(num_unique), N.ptr(ws), ws.numel(), N.stream()), "segmented_unique")
     if want_table_ids:
@@ -261,7 +261,7 @@ def lookup_forward(table_storage, table_bucket_offsets, bucket_capacity, values,
         out = torch.empty(batch_size, num_features * D, dtype=out_dtype, device=dev)
     founds = torch.empty(n, dtype=torch.bool, device=dev) if want_founds else None
     slots = torch.empty(n, dtype=torch.int64, device=dev) if want_founds else None
-    N.check(N.lib.demb_lookup_forward(N.ptr(table_storage), N.ptr(table_bucket_offsets), bucket_capacity, num_scores, N.ptr(values),
+    N.check(N.launch("lookup_forward", 1, N.lib.demb_lookup_forward, N.ptr(table_storage), N.ptr(table_bucket_offsets), bucket_capacity, num_scores, N.ptr(values),
                                       values.stride(0), D, N.ptr(row_base), n, N.ptr(keys.contiguous()), N.ptr(table_range), num_tables,
                                       N.ptr(_i64(offsets)), batch_size, num_features, combiner, N.ptr(out), _OUT_DTYPE[out_dtype],
                                       float(absent_value), N.ptr(founds), N.ptr(slots), N.stream()), "lookup_forward")
@@ -274,21 +274,21 @@ def gather_forward(values, emb_dim, rows, inverse, n, *, offsets=None, batch_siz
         out = torch.empty(n, emb_dim, dtype=out_dtype, device=dev)
     else:
         out = torch.empty(batch_size, num_features * emb_dim, dtype=out_dtype, device=dev)
-    N.check(N.lib.demb_gather_forward(N.ptr(values), values.stride(0), emb_dim, n, N.ptr(rows), N.ptr(inverse), N.ptr(_i64(offsets)),
+    N.check(N.launch("gather_forward", 1, N.lib.demb_gather_forward, N.ptr(values), values.stride(0), emb_dim, n, N.ptr(rows), N.ptr(inverse), N.ptr(_i64(offsets)),
                                       batch_size, num_features, combiner, N.ptr(out), _OUT_DTYPE[out_dtype], N.stream()), "gather_forward")
     return out
 
 
 def rows_from_slots(slots, table_ids, row_base):
     rows = torch.empty_like(slots)
-    N.check(N.lib.demb_rows_from_slots(slots.numel(), N.ptr(slots), N.ptr(_i64(table_ids)), N.ptr(row_base), N.ptr(rows), N.stream()),
+    N.check(N.launch("rows_from_slots", 1, N.lib.demb_rows_from_slots, slots.numel(), N.ptr(slots), N.ptr(_i64(table_ids)), N.ptr(row_base), N.ptr(rows), N.stream()),
             "rows_from_slots")
     return rows
 
 
 def init_rows(values, emb_dim, rows, keys, mode, p0=0.0, p1=1.0, p2=0.0, p3=0.0, seed=0, state_init=0.0, only_if=None, emb_out=None):
     n = keys.numel()
-    N.check(N.lib.demb_init_rows(N.ptr(values), values.stride(0) if values is not None else emb_dim, emb_dim, n, N.ptr(rows),
+    N.check(N.launch("init_rows", 1, N.lib.demb_init_rows, N.ptr(values), values.stride(0) if values is not None else emb_dim, emb_dim, n, N.ptr(rows),
                                  N.ptr(keys.contiguous()), int(mode), float(p0), float(p1), float(p2), float(p3), int(seed),
                                  float(state_init), N.ptr(only_if), N.ptr(emb_out), N.stream()), "init_rows")
 
@@ -309,7 +309,7 @@ def backward(values, emb_dim, inverse, num_unique_bound, rows, grads, *, offsets
     grads = grads.contiguous()
     ws_bytes = N.lib.demb_backward_workspace_bytes(n, emb_dim)
     ws = N.workspace(ws_bytes, dev)
-    N.check(N.lib.demb_backward(N.ptr(values), values.stride(0) if values is not None else emb_dim, emb_dim, n, N.ptr(inverse),
+    N.check(N.launch("backward", 3, N.lib.demb_backward, N.ptr(values), values.stride(0) if values is not None else emb_dim, emb_dim, n, N.ptr(inverse),
                                 int(num_unique_bound), N.ptr(rows), N.ptr(grads), emb_dim, N.ptr(_i64(offsets)), batch_size, num_features,
                                 combiner, int(opt_type), lr, eps, beta1, beta2, weight_decay, bc1, bc2, N.ptr(ug), N.ptr(ws), ws.numel(),
                                 N.stream()), "backward")
@@ -367,7 +367,7 @@ def block_bucketize_sparse_features(lengths: torch.Tensor, indices: torch.Tensor
     new_w = torch.empty(n, dtype=torch.float32, device=dev) if weights is not None else None
     ws = N.workspace(N.lib.demb_bucketize_workspace_bytes(S, world_size), dev)
     dt = dist_type_per_feature.to(torch.int32).contiguous() if dist_type_per_feature is not None else None
-    N.check(N.lib.demb_block_bucketize_sparse_features(S, batch_size, world_size, N.ptr(offsets), N.ptr(_i64(indices)),
+    N.check(N.launch("bucketize", 2, N.lib.demb_block_bucketize_sparse_features, S, batch_size, world_size, N.ptr(offsets), N.ptr(_i64(indices)),
                                                        N.ptr(_i64(block_sizes)), N.ptr(dt), N.ptr(weights), N.ptr(new_lengths), N.ptr(new_ids),
                                                        N.ptr(perm), N.ptr(new_w), N.ptr(ws), ws.numel(), N.stream()),
             "block_bucketize_sparse_features")

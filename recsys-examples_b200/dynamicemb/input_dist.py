@@ -1,0 +1,93 @@
+"""Row-wise sharded input/output dist: the only collectives on the embedding path.
+
+Restates, over plain torch.distributed (NCCL on GPUs over NVLink5/NVSwitch, gloo in the CPU tests), what the reference gets
+from TorchRec: `RwSparseFeaturesDist` = block_bucketize_sparse_features + KJTAllToAll (lengths, then ids)
+(/root/reference/corelib/dynamicemb/dynamicemb/input_dist.py:225-285) and `SequenceEmbeddingsAllToAll` (variable-split
+all_to_all of [n, D] fp32 rows, autograd-mirrored) (planner/rw_sharding.py:83).  The device work (bucketize, lookup) is injected
+as callables so this host logic is testable on CPU with world_size > 1.
+
+Layout conventions (TorchRec KJT): ids are feature-major, slot = f*B + b; after the exchange a rank holds, for every source rank r,
+that rank's ids for every (feature, sample) slot: received slot order = (feature, source rank, sample) once regrouped by feature.
+"""
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class DistContext:
+    """Everything output_dist needs to route rows back."""
+    send_splits: List[int]        # ids sent to each rank
+    recv_splits: List[int]        # ids received from each rank
+    unbucketize_permute: torch.Tensor   # position of original id i inside the bucketized (rank-major) send buffer
+    recv_order: torch.Tensor      # permutation applied to received ids to make them feature-major for the local lookup
+    num_ids: int
+
+
+def _all_to_all_single(out: torch.Tensor, inp: torch.Tensor, out_splits, in_splits, group) -> None:
+    dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
+
+
+class _RowsAllToAll(torch.autograd.Function):
+    """[n_in, D] -> [n_out, D] variable-split all_to_all; backward is the mirrored exchange (TorchRec SequenceEmbeddingsAllToAll)."""
+
+    @staticmethod
+    def forward(ctx, rows, out_splits, in_splits, group):
+        ctx.out_splits, ctx.in_splits, ctx.group = out_splits, in_splits, group
+        out = rows.new_empty(sum(out_splits), rows.shape[1])
+        _all_to_all_single(out, rows.contiguous(), out_splits, in_splits, group)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        g = grad.new_empty(sum(ctx.in_splits), grad.shape[1])
+        _all_to_all_single(g, grad.contiguous(), ctx.in_splits, ctx.out_splits, ctx.group)
+        return g, None, None, None
+
+
+def rw_input_dist(ids: torch.Tensor, lengths: torch.Tensor, batch_size: int, num_features: int, group,
+                  bucketize_fn: Callable) -> Tuple[torch.Tensor, torch.Tensor, DistContext]:
+    """ids[n] + lengths[F*B] (feature-major) of THIS rank's batch -> (ids_recv feature-major, lengths_recv[F*W*B], ctx).
+
+    bucketize_fn(lengths, ids) -> (new_lengths[W*F*B] rank-major, new_ids[n] rank-major, unbucketize_permute[n])."""
+    W = dist.get_world_size(group)
+    S = num_features * batch_size
+    new_lengths, new_ids, perm = bucketize_fn(lengths, ids)
+    # --- exchange lengths: every rank sends its [F*B] length vector for each destination
+    recv_lengths = torch.empty_like(new_lengths)
+    _all_to_all_single(recv_lengths, new_lengths, [S] * W, [S] * W, group)
+    send_splits = new_lengths.view(W, S).sum(dim=1).tolist()          # host sync (TorchRec KJTAllToAll does the same)
+    recv_splits = recv_lengths.view(W, S).sum(dim=1).tolist()
+    ids_recv = new_ids.new_empty(sum(recv_splits))
+    _all_to_all_single(ids_recv, new_ids, recv_splits, send_splits, group)
+    # --- received layout is (source rank, feature, sample); the lookup wants feature-major: (feature, source rank, sample)
+    rl = recv_lengths.view(W, num_features, batch_size)
+    lengths_fm = rl.permute(1, 0, 2).reshape(-1)                        # [F * W * B]
+    # permutation of ids: compute start offset of each (r, f, b) segment in received order, then gather in (f, r, b) order
+    seg_len = rl.reshape(-1)
+    seg_start = torch.cumsum(seg_len, 0) - seg_len
+    order_segments = torch.arange(W * S, device=ids.device).view(W, num_features, batch_size).permute(1, 0, 2).reshape(-1)
+    lens_o = seg_len[order_segments]
+    starts_o = seg_start[order_segments]
+    total = int(ids_recv.numel())
+    if total > 0:
+        out_start = torch.cumsum(lens_o, 0) - lens_o
+        seg_of = torch.repeat_interleave(torch.arange(W * S, device=ids.device), lens_o, output_size=total)
+        recv_order = starts_o[seg_of] + (torch.arange(total, device=ids.device) - out_start[seg_of])
+    else:
+        recv_order = torch.empty(0, dtype=torch.int64, device=ids.device)
+    ids_fm = ids_recv[recv_order]
+    ctx = DistContext(send_splits, recv_splits, perm, recv_order, int(ids.numel()))
+    return ids_fm, lengths_fm, ctx
+
+
+def rw_output_dist(rows_fm: torch.Tensor, ctx: DistContext, group) -> torch.Tensor:
+    """rows of the locally looked-up ids (feature-major order) -> rows for this rank's original ids, original order."""
+    # undo the feature-major regrouping, send every row back to the rank that asked, undo the bucketize permutation
+    inv = torch.empty_like(ctx.recv_order)
+    inv[ctx.recv_order] = torch.arange(ctx.recv_order.numel(), device=ctx.recv_order.device)
+    rows_recv_order = rows_fm[inv]
+    back = _RowsAllToAll.apply(rows_recv_order, ctx.send_splits, ctx.recv_splits, group)
+    return back[ctx.unbucketize_permute]
