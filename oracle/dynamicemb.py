@@ -161,11 +161,12 @@ def pool_rows(values, D, offsets, slots, combiner, B, F):
     return np.ascontiguousarray(tmp.reshape(F, B, D).transpose(1, 0, 2).reshape(B, F * D))
 
 
-def reduce_grads(inverse, grad_rows, scales, num_unique, D, tile=32):
-    """Per-unique gradient sums in the product's documented order (demb_rows.cu backward_tiles_kernel):
-    stable sort by unique idx; inside each 32-row tile of the SORTED list rows are added in order; a
-    segment spanning tiles is the ordered sum of its per-tile partials.  fp32, no FMA contraction.
-    grad_rows[i]: gradient row of id i (already gathered, [n, D]); scales[i]: MEAN scale or 1."""
+def reduce_grads(inverse, grad_rows, scales, num_unique, D, tile=32, window=32):
+    """Per-unique gradient sums in the product's documented order (demb_rows.cu backward_tiles / _windows / _spans kernels):
+    stable sort by unique idx.  Level 1: inside each 32-row TILE of the sorted list rows are added in order.  A segment that
+    spans tiles sums its per-tile partials in order up to the end of the 32-tile WINDOW (1024 rows) its first tile lies in;
+    every later window contributes the ordered sum of the segment's partials inside that window; the window sums are added in
+    order.  fp32, no FMA contraction.  grad_rows[i]: gradient row of id i ([n, D]); scales[i]: MEAN scale or 1."""
     inverse = np.asarray(inverse, dtype=np.int64)
     order = np.argsort(inverse, kind="stable")
     g = (np.asarray(grad_rows, dtype=np.float32) * np.asarray(scales, dtype=np.float32)[:, None]).astype(np.float32)
@@ -173,20 +174,36 @@ def reduce_grads(inverse, grad_rows, scales, num_unique, D, tile=32):
     n = inverse.size
     sk = inverse[order]
     q = 0
+    f32 = np.float32
     while q < n:
         u = sk[q]
         e = q
         while e < n and sk[e] == u:
             e += 1
-        total = None
+        # level-1 partials, keyed by tile index
+        parts = []
         p = q
         while p < e:
-            tile_end = min(e, (p // tile + 1) * tile)
-            part = np.zeros(D, dtype=np.float32)
+            t = p // tile
+            tile_end = min(e, (t + 1) * tile)
+            part = np.zeros(D, dtype=f32)
             for r in range(p, tile_end):
-                part = (part + g[order[r]]).astype(np.float32)
-            total = part if total is None else (total + part).astype(np.float32)
+                part = (part + g[order[r]]).astype(f32)
+            parts.append((t, part))
             p = tile_end
+        w0 = parts[0][0] // window
+        total = parts[0][1]
+        i = 1
+        while i < len(parts) and parts[i][0] // window == w0:
+            total = (total + parts[i][1]).astype(f32)
+            i += 1
+        while i < len(parts):
+            w = parts[i][0] // window
+            wsum = np.zeros(D, dtype=f32)
+            while i < len(parts) and parts[i][0] // window == w:
+                wsum = (wsum + parts[i][1]).astype(f32)
+                i += 1
+            total = (total + wsum).astype(f32)
         out[u] = total
         q = e
     return out

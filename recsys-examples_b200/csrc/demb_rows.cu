@@ -112,59 +112,80 @@ __global__ void __launch_bounds__(kBlock) forward_seq_kernel(RowSrc s, const flo
   }
 }
 
-// ---- forward, pooled mode: one warp per bag (feature f, sample b); ids feature-major (offsets index
-// f*B+b, lookup_forward.cu:53-59); out[b, f*D : (f+1)*D] = SUM or MEAN of the bag's rows, fp32
-// accumulation in id order (lookup_kernel.cuh:901-962).  A13 + A11 + A4 fused.
+// ---- forward, pooled mode: ids feature-major (offsets index f*B+b, lookup_forward.cu:53-59);
+// out[b, f*D : (f+1)*D] = SUM or MEAN of the bag's rows, fp32 accumulation in id order (lookup_kernel.cuh:901-962).
+// A13 + A11 + A4 fused.  A warp takes `bpw` consecutive bags per pass (bpw ~ 32 / average bag length, chosen by the host):
+// their ids are contiguous in the id stream, so ONE probe pass keeps all 32 lanes busy (the reference runs one warp per bag:
+// 10 active lanes at hotness 10) and the row loads of several bags are in flight together.  Rows are accumulated in id order and
+// flushed at every bag boundary, so results do not depend on bpw.
 template <int NCHUNK>
 __global__ void __launch_bounds__(kBlock) forward_pool_kernel(RowSrc s, const float* __restrict__ values, int64_t vdim, int D, int64_t B, int F,
                                                               const int64_t* __restrict__ offsets, int combiner, void* __restrict__ out,
-                                                              int out_dtype, int64_t total_D) {
+                                                              int out_dtype, int64_t total_D, int bpw) {
   const int lane = threadIdx.x & 31;
   const int D4 = D >> 2;
   const int64_t bags = B * (int64_t)F;
+  const int64_t groups = (bags + bpw - 1) / bpw;
   const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
-  for (int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); g < bags; g += wstride) {
-    const int64_t f = g / B, b = g - f * B;
-    const int64_t beg = offsets[g], end = offsets[g + 1];
+  for (int64_t grp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); grp < groups; grp += wstride) {
+    const int64_t g0 = grp * bpw;
+    const int nb = (int)((bags - g0) < bpw ? (bags - g0) : bpw);
+    // lane l < nb+1 holds offsets[g0 + l]
+    const int64_t my_off = lane <= nb ? offsets[g0 + lane] : 0;
+    const int64_t beg = __shfl_sync(0xffffffffu, my_off, 0), end = __shfl_sync(0xffffffffu, my_off, nb);
     float4 acc[NCHUNK];
 #pragma unroll
     for (int k = 0; k < NCHUNK; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cur = 0;                                             // bag (within the group) being accumulated
+    int64_t cur_end = __shfl_sync(0xffffffffu, my_off, 1);
+    auto flush = [&]() {
+      const int64_t g = g0 + cur;
+      const int64_t f = g / B, b = g - f * B;
+      const int64_t len = cur_end - __shfl_sync(0xffffffffu, my_off, cur);
+      if (combiner == 1 && len > 0) {
+        const float L = (float)len;
+#pragma unroll
+        for (int k = 0; k < NCHUNK; ++k) { acc[k].x = __fdiv_rn(acc[k].x, L); acc[k].y = __fdiv_rn(acc[k].y, L); acc[k].z = __fdiv_rn(acc[k].z, L); acc[k].w = __fdiv_rn(acc[k].w, L); }
+      }
+#pragma unroll
+      for (int k = 0; k < NCHUNK; ++k) {
+        const int c = lane + 32 * k;
+        if (c < D4) store_out4(out, out_dtype, b * total_D + f * (int64_t)D + 4 * c, acc[k]);
+        acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      ++cur;
+      cur_end = __shfl_sync(0xffffffffu, my_off, (cur + 1) & 31);
+    };
     for (int64_t base = beg; base < end; base += 32) {
       const int cnt = (int)((end - base) < 32 ? (end - base) : 32);
       int64_t row = -1;
       if (lane < cnt) row = resolve_row(s, base + lane);
-      constexpr int U = 4;
+      constexpr int U = 8;
       for (int j = 0; j < cnt; j += U) {
         int64_t r[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) r[u] = __shfl_sync(0xffffffffu, row, (j + u) & 31);
+        float4 v[U][NCHUNK];
 #pragma unroll
-        for (int k = 0; k < NCHUNK; ++k) {
-          const int c = lane + 32 * k;
-          if (c < D4) {
-            float4 v[U];
+        for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-              v[u] = (j + u < cnt && r[u] >= 0) ? ld_nc_f4(values + r[u] * vdim + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k = 0; k < NCHUNK; ++k) {
+            const int c = lane + 32 * k;
+            v[u][k] = (j + u < cnt && r[u] >= 0 && c < D4) ? ld_nc_f4(values + r[u] * vdim + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {   // in id order => bit-reproducible
-              acc[k].x = __fadd_rn(acc[k].x, v[u].x); acc[k].y = __fadd_rn(acc[k].y, v[u].y);
-              acc[k].z = __fadd_rn(acc[k].z, v[u].z); acc[k].w = __fadd_rn(acc[k].w, v[u].w);
-            }
+        for (int u = 0; u < U; ++u) {
+          if (j + u >= cnt) break;
+          while (base + j + u >= cur_end) flush();           // empty bags flush zeros
+#pragma unroll
+          for (int k = 0; k < NCHUNK; ++k) {                  // in id order => bit-reproducible
+            acc[k].x = __fadd_rn(acc[k].x, v[u][k].x); acc[k].y = __fadd_rn(acc[k].y, v[u][k].y);
+            acc[k].z = __fadd_rn(acc[k].z, v[u][k].z); acc[k].w = __fadd_rn(acc[k].w, v[u][k].w);
           }
         }
       }
     }
-    if (combiner == 1 && end > beg) {
-      const float L = (float)(end - beg);
-#pragma unroll
-      for (int k = 0; k < NCHUNK; ++k) { acc[k].x = __fdiv_rn(acc[k].x, L); acc[k].y = __fdiv_rn(acc[k].y, L); acc[k].z = __fdiv_rn(acc[k].z, L); acc[k].w = __fdiv_rn(acc[k].w, L); }
-    }
-#pragma unroll
-    for (int k = 0; k < NCHUNK; ++k) {
-      const int c = lane + 32 * k;
-      if (c < D4) store_out4(out, out_dtype, b * total_D + f * (int64_t)D + 4 * c, acc[k]);
-    }
+    while (cur < nb) flush();
   }
 }
 
@@ -421,13 +442,65 @@ __global__ void __launch_bounds__(kBlock) backward_tiles_kernel(BwdArgs a) {
   }
 }
 
-// Stage 2: warp per tile that owns a START partial: total = start[tile] + cont[tile+1] + ... while the
-// following tiles begin with the same unique idx; then finish the segment.
+// Ordered sum of `count` consecutive [D]-float partial rows starting at `src` into acc: loads 8 deep, adds in order.
 template <int NCHUNK>
-__global__ void __launch_bounds__(kBlock) backward_spans_kernel(BwdArgs a) {
+__device__ __forceinline__ void add_partials(float4 (&acc)[NCHUNK], const float* __restrict__ src, int count, int D, int lane) {
+  const int D4 = D >> 2;
+  for (int i0 = 0; i0 < count; i0 += 8) {
+    float4 pp[8][NCHUNK];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int k = 0; k < NCHUNK; ++k) {
+        const int c = lane + 32 * k;
+        pp[i][k] = (i0 + i < count && c < D4) ? ld_f4(src + (int64_t)(i0 + i) * D + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i0 + i >= count) break;
+#pragma unroll
+      for (int k = 0; k < NCHUNK; ++k) {
+        acc[k].x = __fadd_rn(acc[k].x, pp[i][k].x); acc[k].y = __fadd_rn(acc[k].y, pp[i][k].y);
+        acc[k].z = __fadd_rn(acc[k].z, pp[i][k].z); acc[k].w = __fadd_rn(acc[k].w, pp[i][k].w);
+      }
+    }
+  }
+}
+
+// Stage 2a: a Zipf-hot id spans thousands of tiles; walking its continuation partials with one warp is a serial chain.
+// So first every WINDOW of 32 tiles (1024 sorted rows) that begins inside a segment sums that segment's leading run of
+// continuation partials (part_cont) into win_cont[window] — one warp per window, all windows in parallel.
+template <int NCHUNK>
+__global__ void __launch_bounds__(kBlock) backward_windows_kernel(BwdArgs a, float* __restrict__ win_cont) {
   const int lane = threadIdx.x & 31;
   const int D4 = a.D >> 2;
   const int64_t tiles = (a.n + 31) >> 5;
+  const int64_t windows = (tiles + 31) >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t w = 1 + (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); w < windows; w += wstride) {
+    const int64_t t0 = w << 5;
+    const int32_t u = a.skey[t0 << 5];
+    if (a.skey[(t0 << 5) - 1] != u) continue;                   // window does not begin inside a segment
+    const int64_t tt = t0 + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, tt < tiles && a.skey[tt << 5] == u);
+    const int run = (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
+    float4 acc[NCHUNK];
+#pragma unroll
+    for (int k = 0; k < NCHUNK; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    add_partials<NCHUNK>(acc, a.part_cont + t0 * a.D, run, a.D, lane);
+#pragma unroll
+    for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; if (c < D4) st_f4(win_cont + w * a.D + 4 * c, acc[k]); }
+  }
+}
+
+// Stage 2b: warp per tile that owns a START partial: total = start[tile] + cont partials up to the end of its own window
+// + win_cont of every following window the segment reaches; then finish the segment.  Fixed order => bit-reproducible.
+template <int NCHUNK>
+__global__ void __launch_bounds__(kBlock) backward_spans_kernel(BwdArgs a, const float* __restrict__ win_cont) {
+  const int lane = threadIdx.x & 31;
+  const int D4 = a.D >> 2;
+  const int64_t tiles = (a.n + 31) >> 5;
+  const int64_t windows = (tiles + 31) >> 5;
   const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
   for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); tile + 1 < tiles; tile += wstride) {
     const int64_t base = tile << 5;
@@ -437,32 +510,21 @@ __global__ void __launch_bounds__(kBlock) backward_spans_kernel(BwdArgs a) {
     float4 acc[NCHUNK];
 #pragma unroll
     for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; acc[k] = c < D4 ? ld_f4(a.part_start + tile * a.D + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f); }
-    // Lanes look 32 tiles ahead at once (one 4-byte load each); partial rows are fetched 8 at a time so the adds
-    // (kept in ascending tile order) never wait on a dependent load chain — a Zipf-hot id spans thousands of tiles.
-    for (int64_t t2 = tile + 1; t2 < tiles; t2 += 32) {
-      const int64_t tt = t2 + lane;
-      const bool cont = tt < tiles && a.skey[tt << 5] == u;
-      const unsigned m = __ballot_sync(0xffffffffu, cont);
-      const int run = (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);      // contiguous continuation tiles in this window
-      for (int i0 = 0; i0 < run; i0 += 8) {
-        float4 pp[8][NCHUNK];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int k = 0; k < NCHUNK; ++k) {
-            const int c = lane + 32 * k;
-            pp[i][k] = (i0 + i < run && c < D4) ? ld_f4(a.part_cont + (t2 + i0 + i) * a.D + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (i0 + i >= run) break;
-#pragma unroll
-          for (int k = 0; k < NCHUNK; ++k) {
-            acc[k].x = __fadd_rn(acc[k].x, pp[i][k].x); acc[k].y = __fadd_rn(acc[k].y, pp[i][k].y);
-            acc[k].z = __fadd_rn(acc[k].z, pp[i][k].z); acc[k].w = __fadd_rn(acc[k].w, pp[i][k].w);
-          }
-        }
-      }
+    // continuation tiles inside this tile's own window
+    const int64_t w0 = tile >> 5;
+    const int64_t wend = ((w0 + 1) << 5) < tiles ? ((w0 + 1) << 5) : tiles;
+    {
+      const int64_t tt = tile + 1 + lane;
+      const unsigned m = __ballot_sync(0xffffffffu, tt < wend && a.skey[tt << 5] == u);
+      const int run = (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
+      add_partials<NCHUNK>(acc, a.part_cont + (tile + 1) * a.D, run, a.D, lane);
+    }
+    // following windows that begin inside this segment
+    for (int64_t w = w0 + 1; w < windows; w += 32) {
+      const int64_t ww = w + lane;
+      const unsigned m = __ballot_sync(0xffffffffu, ww < windows && a.skey[ww << 10] == u);
+      const int run = (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
+      add_partials<NCHUNK>(acc, win_cont + w * a.D, run, a.D, lane);
       if (run < 32) break;
     }
     finish_segment<NCHUNK>(a, u, acc, lane);
@@ -519,6 +581,13 @@ cudaEvent_t g_prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
 extern "C" {
 
+// bags a warp takes per pass: as many average-length bags as fit in one 32-lane probe pass (1..16)
+static int pool_bags_per_warp(int64_t n_ids, int64_t bags) {
+  if (bags <= 0 || n_ids <= 0) return 1;
+  int64_t avg = (n_ids + bags - 1) / bags;
+  int64_t bpw = 32 / (avg < 1 ? 1 : avg);
+  return (int)(bpw < 1 ? 1 : (bpw > 16 ? 16 : bpw));
+}
 static int check_dims(int D, int64_t vdim) { return (D <= 0 || (D & 3) || D > 128 * kMaxChunks || (vdim & 3) || vdim < D) ? DEMB_ERR_ARG : 0; }
 
 int demb_lookup_forward(void* storage, const int64_t* table_bucket_offsets, int64_t bucket_capacity, int num_scores, const float* values,
@@ -535,9 +604,10 @@ int demb_lookup_forward(void* storage, const int64_t* table_bucket_offsets, int6
     if (batch_size <= 0 || num_features <= 0) return 0;
     if (emb_dim > 512) return DEMB_ERR_ARG;
     int64_t bags = batch_size * num_features;
-    DISPATCH_NCHUNK(emb_dim, forward_pool_kernel<NC><<<warp_grid(bags), kBlock, 0, (cudaStream_t)stream>>>(
+    const int bpw = pool_bags_per_warp(n, bags);
+    DISPATCH_NCHUNK(emb_dim, forward_pool_kernel<NC><<<warp_grid((bags + bpw - 1) / bpw), kBlock, 0, (cudaStream_t)stream>>>(
                                  s, values, value_dim, emb_dim, batch_size, num_features, offsets, combiner, out, out_dtype,
-                                 (int64_t)num_features * emb_dim));
+                                 (int64_t)num_features * emb_dim, bpw));
   }
   DEMB_CHECK_LAST();
   return 0;
@@ -554,9 +624,10 @@ int demb_gather_forward(const float* values, int64_t value_dim, int emb_dim, int
     if (batch_size <= 0 || num_features <= 0) return 0;
     if (emb_dim > 512) return DEMB_ERR_ARG;
     int64_t bags = batch_size * num_features;
-    DISPATCH_NCHUNK(emb_dim, forward_pool_kernel<NC><<<warp_grid(bags), kBlock, 0, (cudaStream_t)stream>>>(
+    const int bpw = pool_bags_per_warp(n, bags);
+    DISPATCH_NCHUNK(emb_dim, forward_pool_kernel<NC><<<warp_grid((bags + bpw - 1) / bpw), kBlock, 0, (cudaStream_t)stream>>>(
                                  s, values, value_dim, emb_dim, batch_size, num_features, offsets, combiner, out, out_dtype,
-                                 (int64_t)num_features * emb_dim));
+                                 (int64_t)num_features * emb_dim, bpw));
   }
   DEMB_CHECK_LAST();
   return 0;
@@ -594,7 +665,7 @@ int64_t demb_backward_workspace_bytes(int64_t n, int emb_dim) {
   size_t tmp = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const int32_t*)nullptr, (int32_t*)nullptr, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n);
   size_t tiles = ((size_t)n + 31) / 32;
-  return (int64_t)(4 * align256(4 * (size_t)n) + 2 * align256(tiles * (size_t)emb_dim * 4) + align256(tmp) + 256);
+  return (int64_t)(4 * align256(4 * (size_t)n) + 2 * align256(tiles * (size_t)emb_dim * 4) + align256(((tiles + 31) / 32 + 1) * (size_t)emb_dim * 4) + align256(tmp) + 256);
 }
 
 // Fused backward: reduce gradients per unique id and apply the sparse optimizer to the value rows.
@@ -619,6 +690,7 @@ int demb_backward(float* values, int64_t value_dim, int emb_dim, int64_t n, cons
   int32_t* v1 = (int32_t*)w; w += align256(4 * (size_t)n);
   float* pc = (float*)w; w += align256(tiles * (size_t)emb_dim * 4);
   float* ps = (float*)w; w += align256(tiles * (size_t)emb_dim * 4);
+  float* wc = (float*)w; w += align256(((tiles + 31) / 32 + 1) * (size_t)emb_dim * 4);
   size_t tmp_bytes = (size_t)((uint8_t*)workspace + workspace_bytes - w);
   if (g_prof_on) cudaEventRecord(g_prof_ev[0], stream);
   backward_pairs_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(n, inverse, pooled, batch_size, num_features, offsets, k0, v0);
@@ -631,7 +703,8 @@ int demb_backward(float* values, int64_t value_dim, int emb_dim, int64_t n, cons
   DISPATCH_NCHUNK(emb_dim, {
     backward_tiles_kernel<NC><<<warp_grid((int64_t)tiles), kBlock, 0, stream>>>(a);
     if (g_prof_on) cudaEventRecord(g_prof_ev[2], stream);
-    if (tiles > 1) backward_spans_kernel<NC><<<warp_grid((int64_t)tiles - 1), kBlock, 0, stream>>>(a);
+    if (tiles > 32) backward_windows_kernel<NC><<<warp_grid((int64_t)(tiles + 31) / 32), kBlock, 0, stream>>>(a, wc);
+    if (tiles > 1) backward_spans_kernel<NC><<<warp_grid((int64_t)tiles - 1), kBlock, 0, stream>>>(a, wc);
     if (g_prof_on) cudaEventRecord(g_prof_ev[3], stream);
   });
   DEMB_CHECK_LAST();

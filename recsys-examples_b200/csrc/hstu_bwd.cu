@@ -267,7 +267,8 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
     mbar_wait(&acc_full, 0);
     if (threadIdx.x == 128) HSTU_DBG(19, 1);
     tc_fence_after();
-    if (xi < L) {
+    {
+      // tcgen05.ld is warp-collective (.sync.aligned): every lane must execute it; only the global stores are predicated.
       const uint32_t tacc = kIsDQ ? tA0 : (ch == 0 ? tA0 : tA1);
       __nv_bfloat16* dst = (kIsDQ || ch == 0) ? p.out0 : p.out1;
       const float sc = (kIsDQ || ch == 0) ? p.scale0 : p.scale1;
@@ -277,14 +278,16 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
         uint32_t o[32];
         tmem_ld32(tacc + lane_off + c, o);
         tmem_ld_wait();
+        if (xi < L) {
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(o[8 * q4 + 0]) * sc, __uint_as_float(o[8 * q4 + 1]) * sc);
-          v.y = pack_bf16x2(__uint_as_float(o[8 * q4 + 2]) * sc, __uint_as_float(o[8 * q4 + 3]) * sc);
-          v.z = pack_bf16x2(__uint_as_float(o[8 * q4 + 4]) * sc, __uint_as_float(o[8 * q4 + 5]) * sc);
-          v.w = pack_bf16x2(__uint_as_float(o[8 * q4 + 6]) * sc, __uint_as_float(o[8 * q4 + 7]) * sc);
-          *reinterpret_cast<uint4*>(orow + c + q4 * 8) = v;
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(o[8 * q4 + 0]) * sc, __uint_as_float(o[8 * q4 + 1]) * sc);
+            v.y = pack_bf16x2(__uint_as_float(o[8 * q4 + 2]) * sc, __uint_as_float(o[8 * q4 + 3]) * sc);
+            v.z = pack_bf16x2(__uint_as_float(o[8 * q4 + 4]) * sc, __uint_as_float(o[8 * q4 + 5]) * sc);
+            v.w = pack_bf16x2(__uint_as_float(o[8 * q4 + 6]) * sc, __uint_as_float(o[8 * q4 + 7]) * sc);
+            *reinterpret_cast<uint4*>(orow + c + q4 * 8) = v;
+          }
         }
       }
     }

@@ -184,7 +184,7 @@ def test_backward_reduce_and_update(cuda, opt, code, state_mult, mode):
                       opt_type=code, bc1=1 - 0.9 ** step, bc2=1 - 0.999 ** step, want_unique_grads=True, **kw)
     exp_ug = orc.reduce_grads(inverse, g_np[grow], scale, nu, D)
     assert np.array_equal(ug.cpu().numpy(), exp_ug), "reduced gradients must be bit-exact (fixed summation order)"
-    exp_vals = orc.optimizer_update(vals_before, D, rows, exp_ug, opt, step=step, **kw)
+    exp_vals = orc.optimizer_update(vals_before.copy(), D, rows, exp_ug, opt, step=step, **kw)
     np.testing.assert_allclose(values.cpu().numpy(), exp_vals, rtol=1e-6, atol=1e-6)
     # standalone op pair: reduce_grads + update_rows gives the same rows
     v2 = torch.from_numpy(vals_before).to(cuda)
