@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--capacity", type=int, default=32 * 1024 * 1024)
     ap.add_argument("--no-hstu", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="wrap 2 timed steps in cudaProfilerStart/Stop (ncu --profile-from-start off) and exit")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -247,18 +248,24 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     # ---- prefill to ~50 % load with ids of the same distribution (keys owned by this rank only when sharded)
     target = args.capacity // 2
-    filled = 0
-    while filled < target:
+    filled, stall = 0, 0
+    while filled < target and stall < 3:
         ids = torch.unique(power_law_ids(1 << 24, gen, dev))
         if world > 1:   # keep only the keys this rank owns under hash_roundrobin (fmix64(id) % W)
             ids = ids[(fmix64_torch(ids) % world) == rank]
-        ids = ids[: target - filled + (1 << 20)]
+        z = torch.zeros(ids.numel(), dtype=torch.int64, device=dev)
+        _, found, _ = m.tables.lookup(ids, z, ScoreArg("score", None, ScorePolicy.CONST))
+        ids = ids[~found]                                             # only keys not in the table yet
+        if ids.numel() > target - filled:
+            ids = ids[torch.randperm(ids.numel(), device=dev)[: target - filled]]
+        if ids.numel() == 0:
+            break
         z = torch.zeros(ids.numel(), dtype=torch.int64, device=dev)
         slots = m.tables.insert(ids, z, ScoreArg("score", torch.ones(ids.numel(), dtype=torch.int64, device=dev), ScorePolicy.ASSIGN))
         ext.init_rows(m._values, D, slots, ids, ext.InitializerMode.UNIFORM, -0.01, 0.01, seed=1)
-        filled = m.tables.size()
-        if ids.numel() < (1 << 16):
-            break
+        now = m.tables.size()
+        stall = stall + 1 if now <= filled else 0
+        filled = now
     if world > 1:
         from dynamicemb.shard import RowWiseShardedDynamicEmbedding
         model = RowWiseShardedDynamicEmbedding(m, None, dist_type="hash_roundrobin", use_index_dedup=True)
@@ -283,6 +290,16 @@ def main():
 
     for i in range(args.warmup):
         step(batches[i])
+    if args.ncu:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for i in range(2):
+            step(batches[args.warmup + i])
+        if world == 1:
+            m.eval(); m(batches[-1], offsets); m.train()       # the fused probe+gather forward (eval path)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     # ---- timed region: device-resident inputs
     N.lib.demb_profile_enable(1)
     N.PROFILE = {}
