@@ -13,6 +13,7 @@
 
 #include "../../include/dynamicemb_b200.h"
 #include "demb_common.cuh"
+#include "demb_insert.cuh"
 
 using namespace demb;
 
@@ -33,27 +34,6 @@ __global__ void table_init_kernel(uint8_t* storage, int64_t num_buckets, int64_t
     else if (off < 9 * C) v = make_uint4(ed, ed, ed, ed);
     else v = make_uint4(0, 0, 0, 0);
     reinterpret_cast<uint4*>(storage)[i] = v;
-  }
-}
-
-// ---- score policies (score.cuh:53-94), lock-free ------------------------------------------------
-__device__ __forceinline__ uint64_t policy_get(int pol, const uint64_t* in, int64_t i, uint64_t ts) {
-  if (pol == kConst) return 0;
-  if (pol == kGlobalTimer) return ts ? ts : globaltimer();
-  return in ? in[i] : 0;
-}
-// `atomic` = several threads may hit the same slot in this launch (lookup with duplicate keys).
-__device__ __forceinline__ uint64_t policy_update(int pol, uint64_t* s, uint64_t score, uint64_t ts, bool atomic) {
-  switch (pol) {
-    case kConst: return s[0];
-    case kAccumulate:
-      if (atomic) return atomicAdd(reinterpret_cast<unsigned long long*>(s), (unsigned long long)score) + score;
-      score += s[0]; s[0] = score; return score;
-    case kLruLfu:
-      s[0] = ts ? ts : globaltimer();
-      if (atomic) return atomicAdd(reinterpret_cast<unsigned long long*>(s + 1), (unsigned long long)score) + score;
-      score += s[1]; s[1] = score; return score;
-    default: s[0] = score; return score;
   }
 }
 
@@ -114,15 +94,11 @@ __global__ void __launch_bounds__(kBlock) table_insert_segments_kernel(Table t, 
   for (int64_t q0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q0 < n; q0 += warps_per_grid) {
     const int32_t b = bucket_sorted[q0];
     if (q0 > 0 && bucket_sorted[q0 - 1] == b) continue;   // not a segment start (warp-uniform)
-    uint8_t* bk = t.bucket(b);
-    volatile uint64_t* vkeys = t.keys(bk);
-    volatile uint8_t* vdig = t.digests(bk);
-    const uint32_t emp4 = (uint32_t)empty_digest() * 0x01010101u;
     for (int64_t q = q0; q < n && bucket_sorted[q] == b; ++q) {
       const int32_t i = order[q];
       const uint64_t key = a.keys[i];
       const int64_t tid = a.tids ? a.tids[i] : 0;
-      uint64_t score = policy_get(a.pol, a.score_in, i, a.ts);
+      const uint64_t score = policy_get(a.pol, a.score_in, i, a.ts);
       const int64_t bb = t.bkt_off[tid];
       const int64_t cap = (t.bkt_off[tid + 1] - bb) * t.C;
       if (!key_is_valid(key) || cap == 0) {               // kernels.cuh:338-348
@@ -133,81 +109,19 @@ __global__ void __launch_bounds__(kBlock) table_insert_segments_kernel(Table t, 
         }
         continue;
       }
-      const int64_t h = hash63(key);
-      const uint32_t want4 = (uint32_t)digest_of(h) * 0x01010101u;
-      const int64_t start = (h % t.C) & ~(int64_t)15;
-      // ---- probe (types.cuh:325-396 order), 128 slots per warp step, 4 per lane
-      int64_t hit = -1, empty = -1;
-      for (int64_t base = 0; base < t.C && hit < 0 && empty < 0; base += 128) {
-        int64_t s = base + lane * 4;
-        int kind = 0; int64_t pos = -1;                   // 1 = existed, 2 = empty
-        if (s < t.C) {
-          int64_t p0 = start + s; if (p0 >= t.C) p0 -= t.C;
-          uint32_t w = *reinterpret_cast<volatile const uint32_t*>(vdig + p0);
-          uint32_t m = __vcmpeq4(w, want4) & 0x01010101u;
-          while (m && !kind) { int o = (__ffs(m) - 1) >> 3; m &= m - 1; if (vkeys[p0 + o] == key) { kind = 1; pos = p0 + o; } }
-          m = kind ? 0 : (__vcmpeq4(w, emp4) & 0x01010101u);
-          while (m && !kind) { int o = (__ffs(m) - 1) >> 3; m &= m - 1; if (vkeys[p0 + o] == kEmptyKey) { kind = 2; pos = p0 + o; } }
-        }
-        unsigned any = __ballot_sync(0xffffffffu, kind != 0);
-        if (any) {
-          int src = __ffs(any) - 1;
-          int k = __shfl_sync(0xffffffffu, kind, src);
-          int64_t p = __shfl_sync(0xffffffffu, pos, src);
-          if (k == 1) hit = p; else empty = p;
-        }
-      }
-      int result = kInit; int64_t it = -1; uint64_t ev_key = 0, ev_score = 0;
-      const int64_t coff = ((int64_t)b - bb) * t.C;
-      if (hit >= 0) { result = kAssignHit; it = hit; }
-      else if (empty >= 0) { result = kInsert; it = empty; }
-      else {
-        // ---- evict: min reduction score over unlocked, non-empty, unpinned slots; first minimum
-        // in storage order wins (types.cuh:417-465, kernels.cuh:238-275).  The pin counter is indexed by
-        // GLOBAL slot (bucket*C+j) as update_counter_with_layout_kernel writes it (insert_and_evict.cu:27-60);
-        // the reference's reduce() reads it table-locally, which only agrees for table 0.
-        uint64_t best = 0xFFFFFFFFFFFFFFFFull; int64_t bi = -1; uint64_t bkey = 0;
-        for (int64_t j = lane; j < t.C; j += 32) {
-          uint64_t s = *reinterpret_cast<volatile const uint64_t*>(t.scores(bk, j) + (t.ns - 1));
-          if (s < best) {
-            uint64_t k = vkeys[j];
-            if (k != kLockedKey && k != kEmptyKey && !(a.counter && a.counter[(int64_t)b * t.C + j] > 0)) { best = s; bi = j; bkey = k; }
-          }
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-          uint64_t os = __shfl_xor_sync(0xffffffffu, best, d);
-          int64_t oi = __shfl_xor_sync(0xffffffffu, bi, d);
-          uint64_t ok = __shfl_xor_sync(0xffffffffu, bkey, d);
-          bool take = (oi >= 0) && (bi < 0 || os < best || (os == best && oi < bi));
-          if (take) { best = os; bi = oi; bkey = ok; }
-        }
-        if (bi >= 0) { it = bi; ev_key = bkey; ev_score = best; result = (bkey == kReclaimKey) ? kReclaim : kEvict; }
-        else { result = kBusy; ev_key = key; ev_score = score; }
-      }
+      const InsertOutcome o = warp_insert_one(t, b, key, score, a.pol, a.ts, a.bucket_sizes, a.counter, lane);
       if (lane == 0) {
-        int64_t index = -1;
-        if (result <= kEvict) {
-          uint64_t* sc = t.scores(bk, it);
-          if (result == kInsert || result == kReclaim || result == kEvict) vdig[it] = digest_of(h);
-          if (result == kInsert || result == kReclaim) a.bucket_sizes[b] += 1;
-          if (result == kEvict) for (int s = 0; s < t.ns; ++s) sc[s] = 0;
-          score = policy_update(a.pol, sc, score, a.ts, false);
-          vkeys[it] = key;
-          index = coff + it;
-        }
-        if (a.results) a.results[i] = (uint8_t)result;
+        const int64_t index = o.result <= kEvict ? ((int64_t)b - bb) * t.C + o.it : -1;
+        if (a.results) a.results[i] = (uint8_t)o.result;
         a.indices[i] = index;
-        if (a.score_out) a.score_out[i] = (int64_t)score;
-        if (a.ev_count && (result == kEvict || result == kBusy)) {
-          unsigned long long o = atomicAdd(a.ev_count, 1ull);
-          a.ev_keys[o] = ev_key; a.ev_scores[o] = (int64_t)ev_score;
-          a.ev_indices[o] = (result == kEvict) ? index : -((int64_t)i + 1);   // kernels.cuh:548-552
-          a.ev_tids[o] = tid;
+        if (a.score_out) a.score_out[i] = (int64_t)o.score;
+        if (a.ev_count && (o.result == kEvict || o.result == kBusy)) {
+          unsigned long long e = atomicAdd(a.ev_count, 1ull);
+          a.ev_keys[e] = o.ev_key; a.ev_scores[e] = (int64_t)o.ev_score;
+          a.ev_indices[e] = (o.result == kEvict) ? index : -((int64_t)i + 1);   // kernels.cuh:548-552
+          a.ev_tids[e] = tid;
         }
       }
-      __threadfence_block();
-      __syncwarp();
     }
   }
 }

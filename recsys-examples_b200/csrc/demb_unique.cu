@@ -59,13 +59,15 @@ __global__ void unique_claim_kernel(int64_t n, const uint64_t* __restrict__ keys
       } else {
         int64_t q = (int64_t)(fmix64(key) % (uint64_t)size);
         while (true) {
-          unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(s.keys + base + q), (unsigned long long)kEmptyKey, (unsigned long long)key);
+          // test before the atomic: a Zipf-hot key is claimed once and then only READ (same-address atomics serialise in L2)
+          unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(s.keys + base + q);
+          if (old == kEmptyKey) old = atomicCAS(reinterpret_cast<unsigned long long*>(s.keys + base + q), (unsigned long long)kEmptyKey, (unsigned long long)key);
           if (old == kEmptyKey || old == key) break;
           if (++q == size) q = 0;
         }
         p = base + q;
       }
-      atomicMin(s.minpos + p, (int32_t)i);
+      if (*reinterpret_cast<volatile int32_t*>(s.minpos + p) > (int32_t)i) atomicMin(s.minpos + p, (int32_t)i);
       if (need_freq && !freq_in) atomicAdd(s.cnt + p, __popc(grp));
     }
     p = __shfl_sync(0xffffffffu, p, leader);

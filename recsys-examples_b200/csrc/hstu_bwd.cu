@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 
 #include "../../include/hstu_b200.h"
+#include "hstu_mask.cuh"
 #include "sm100_ptx.cuh"
 #include "tma_host.cuh"
 
@@ -40,25 +41,8 @@ struct Params {
 };
 #define HSTU_DBG(slot, val) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { p.dbg[(kIsDQ ? 64 : 32) + (slot)] = (val); __threadfence_system(); } } while (0)
 
-struct SeqMask {
-  int L, seqlen_c, seqlen_h, G, wl, wr;
-  bool has_t, has_c;
-  __device__ __forceinline__ bool valid(int row, int col) const {
-    bool ok = col < L;
-    if (wr >= 0) ok = ok && (col <= row + wr);
-    if (wl >= 0) ok = ok && (col >= row - wl);
-    if (has_t && row >= seqlen_h && col >= seqlen_h && col < seqlen_h + ((row - seqlen_h) / G) * G) ok = false;
-    if (has_c && row < seqlen_c && col < seqlen_h) ok = true;
-    return ok && row < L;
-  }
-  __device__ __forceinline__ bool tile_full(int r0, int r1, int c0, int c1) const {
-    if (c1 >= L || r1 >= L) return false;
-    if (wr >= 0 && c1 > r0 + wr) return false;
-    if (wl >= 0 && c0 < r1 - wl) return false;
-    if (has_t && r1 >= seqlen_h && c1 >= seqlen_h) return false;
-    return true;
-  }
-};
+using hstu::SeqMask;
+using hstu::Intervals;
 
 template <int D, bool kIsDQ>
 struct Smem {
@@ -213,6 +197,7 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
     const int rit = wq * 32 + lane;                 // stationary row in tile
     const int xi = x0 + rit;                        // stationary index (dKV: key, dQ: query)
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    const Intervals iv = kIsDQ ? hstu::cols_of_row(mk, xi) : hstu::rows_of_col(mk, xi);
     for (int j = 0; j < n_iter; ++j) {
       const int st = j & 1, ph = (j >> 1) & 1;
       const int y0 = y_tile_of(j) * 64;
@@ -237,12 +222,13 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
           const float hh = __uint_as_float(s[i + e]) * p.half_alpha;
           const float t = tanh_approx(hh);
           float pe = fmaf(hh, t, hh);
-          // silu' = 0.5 (1 + t) (1 + h (1 - t))
-          float de = __uint_as_float(dp[i + e]) * (0.5f * (1.f + t)) * fmaf(hh, 1.f - t, 1.f);
+          // silu' = 0.5 (1 + t) (1 + h (1 - t)) = (1 - u/2)(1 + h u),  u = 1 - t
+          const float u = 1.f - t;
+          float de = __uint_as_float(dp[i + e]) * (fmaf(-0.5f, u, 1.f) * fmaf(hh, u, 1.f));
           if (!full) {
-            const int yi = y0 + ch * 32 + i + e;
-            const bool ok = kIsDQ ? mk.valid(xi, yi) : mk.valid(yi, xi);
-            if (!ok) { pe = 0.f; de = 0.f; }
+            const bool ok = iv.has(y0 + ch * 32 + i + e);
+            pe = ok ? pe : 0.f;
+            de = ok ? de : 0.f;
           }
           pv[e] = pe; dv[e] = de;
         }

@@ -16,6 +16,7 @@
 #include <cuda_bf16.h>
 
 #include "../../include/hstu_b200.h"
+#include "hstu_mask.cuh"
 #include "sm100_ptx.cuh"
 #include "tma_host.cuh"
 
@@ -38,27 +39,6 @@ struct FwdParams {
 
 // progress marks readable from the host even if the kernel never finishes (development aid)
 #define HSTU_DBG(slot, val) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { p.dbg[slot] = (val); __threadfence_system(); } } while (0)
-
-struct SeqMask {
-  int L, seqlen_c, seqlen_h, G, wl, wr;
-  bool has_t, has_c;
-  __device__ __forceinline__ bool valid(int row, int col) const {
-    bool ok = col < L;
-    if (wr >= 0) ok = ok && (col <= row + wr);
-    if (wl >= 0) ok = ok && (col >= row - wl);
-    if (has_t && row >= seqlen_h && col >= seqlen_h && col < seqlen_h + ((row - seqlen_h) / G) * G) ok = false;
-    if (has_c && row < seqlen_c && col < seqlen_h) ok = true;
-    return ok;
-  }
-  // every (row, col) of rows [r0, r1] x cols [c0, c1] valid?  (conservative: false => per-element mask is applied)
-  __device__ __forceinline__ bool tile_full(int r0, int r1, int c0, int c1) const {
-    if (c1 >= L) return false;
-    if (wr >= 0 && c1 > r0 + wr) return false;
-    if (wl >= 0 && c0 < r1 - wl) return false;
-    if (has_t && r1 >= seqlen_h && c1 >= seqlen_h) return false;
-    return true;
-  }
-};
 
 template <int D>
 struct FwdSmem {
@@ -191,6 +171,7 @@ __global__ void __launch_bounds__(256, 1) hstu_fwd_kernel(const __grid_constant_
     const int row = r0 + rit;
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     uint8_t* sP = smem + SM::kP;
+    const Intervals iv = cols_of_row(mk, row);
     for (int j = 0; j < n_iter; ++j) {
       const int st = j & 1, ph = (j >> 1) & 1;
       const int c_base = (nb0 + j) * 128;
@@ -216,8 +197,8 @@ __global__ void __launch_bounds__(256, 1) hstu_fwd_kernel(const __grid_constant_
           float p0 = fmaf(h0, tanh_approx(h0), h0), p1 = fmaf(h1, tanh_approx(h1), h1);
           if (!full) {
             const int col = c_base + cc * 32 + i;
-            if (!mk.valid(row, col)) p0 = 0.f;
-            if (!mk.valid(row, col + 1)) p1 = 0.f;
+            p0 = iv.has(col) ? p0 : 0.f;
+            p1 = iv.has(col + 1) ? p1 : 0.f;
           }
           pk[i >> 1] = pack_bf16x2(p0, p1);
         }
