@@ -149,6 +149,24 @@ int demb_update_rows(float* values, int64_t value_dim, int emb_dim, int64_t n, c
                      int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
                      float bias_correction2, void* stream);
 
+/* ---- fused training prefetch (replaces dynamicemb_prefetch / _prefetch_hbm_direct_path, batched_dynamicemb_function.py:559-830) ----
+ * dedup -> probe (+score update, +pin) -> insert + row init of the missing keys (+pin), no host synchronisation, no sort.
+ * bucket_heads[num_buckets] int32 must be -1 on entry and is left -1 (demb_fill_i32).  Outputs are sized n; only the first
+ * *num_unique entries are meaningful.  slots: table-local slot or -1 (insert failed); rows: global value row or -1.
+ * table_scores[T] (ASSIGN policies: one score per table); unique_freq[n] is filled for ACCUMULATE / LRU_LFU. */
+int demb_fill_i32(int32_t* p, int64_t n, int32_t v, void* stream);
+int64_t demb_train_prefetch_workspace_bytes(int64_t n, int num_tables);
+int demb_train_prefetch(void* storage, const int64_t* table_bucket_offsets, int64_t bucket_capacity, int num_scores, int32_t* bucket_sizes,
+                        int32_t* ref_counter, int32_t* bucket_heads, float* values, int64_t value_dim, int emb_dim, const int64_t* row_base,
+                        int64_t n, const void* keys, const int64_t* table_range, int num_tables, const int64_t* freq_in, int policy,
+                        const uint64_t* table_scores, uint64_t timestamp, int key_is_signed, int init_mode, float p0, float p1, float p2, float p3,
+                        uint64_t seed, float state_init, void* unique_keys, int64_t* reverse_indices, int64_t* unique_table_ids,
+                        int64_t* unique_freq, int64_t* slots, int64_t* rows, int64_t* num_unique, void* workspace, int64_t workspace_bytes,
+                        void* stream);
+/* demb_counter_update with the element count read from device memory (*n_device <= n_max) */
+int demb_counter_update_n(int32_t* ref_counter, const int64_t* slot_indices, const int64_t* table_ids, const int64_t* table_bucket_offsets,
+                          int64_t bucket_capacity, const int64_t* n_device, int64_t n_max, int delta, void* stream);
+
 /* measurement aid for bench.py: CUDA events around the stages of demb_backward; read returns ms of {pairs+sort, tiles, spans} */
 int demb_profile_enable(int on);
 int demb_profile_read(float* ms3);

@@ -72,7 +72,7 @@ __device__ __forceinline__ InsertOutcome warp_insert_one(const Table& t, int64_t
       uint64_t s = *reinterpret_cast<volatile const uint64_t*>(t.scores(bk, j) + (t.ns - 1));
       if (s < best) {
         uint64_t k = vkeys[j];
-        if (k != kLockedKey && k != kEmptyKey && !(counter && counter[b * t.C + j] > 0)) { best = s; bi = j; bkey = k; }
+        if (k != kLockedKey && k != kEmptyKey && !(counter && *reinterpret_cast<volatile const int32_t*>(counter + b * t.C + j) > 0)) { best = s; bi = j; bkey = k; }
       }
     }
 #pragma unroll

@@ -1,0 +1,209 @@
+// Fused training prefetch for the HBM-direct tier: dedup -> probe -> insert + init of the missing keys -> pin, with NO host
+// synchronisation and no sort.  Replaces the reference's dynamicemb_prefetch / _prefetch_hbm_direct_path
+// (corelib/dynamicemb/dynamicemb/batched_dynamicemb_function.py:559-830: segmented_unique (+host sync), table_lookup,
+// flagged_compact (+host sync), initializer, table_insert (+unlock), store_to_flat, increment_counter x2, expand_table_ids).
+//
+//   1. demb_segmented_unique                      unique keys in first-occurrence order, count stays on the device
+//   2. train_lookup_kernel (thread per unique)    probe; hit: score update + pin + slot/row out
+//                                                 miss: push the key on its bucket's list (atomicExch on heads[bucket]); the first
+//                                                 pusher records the bucket in `touched`
+//   3. train_insert_kernel (warp per touched bucket, persistent grid, device-side count)
+//                                                 pops the bucket's list, orders it by key (the reference's deterministic order:
+//                                                 (bucket, key), scored_hashtable.py:1451-1557), inserts sequentially with the shared
+//                                                 warp_insert_one, initialises the new row [emb | optimizer state] and pins it.
+// The resulting table image is identical to lookup + demb_table_insert + demb_init_rows run op by op (tests/test_demb_train_gpu.py).
+#include "../../include/dynamicemb_b200.h"
+#include "demb_common.cuh"
+#include "demb_insert.cuh"
+#include "demb_init.cuh"
+
+using namespace demb;
+
+namespace {
+constexpr int kBlock = 256;
+
+struct TrainArgs {
+  Table t;
+  int32_t* bucket_sizes; int32_t* counter; int32_t* heads;
+  float* values; int64_t vdim; int D; const int64_t* row_base;
+  const uint64_t* ukeys; const int64_t* utids; const int64_t* n_u;
+  int pol; const uint64_t* table_scores; const int64_t* freq; uint64_t ts; int key_is_signed;
+  InitArgs init; float state_init;
+  int64_t* slots; int64_t* rows; int32_t* next; int32_t* touched; unsigned long long* n_touched;
+};
+
+__device__ __forceinline__ uint64_t train_score(const TrainArgs& a, int64_t u, int64_t tid) {
+  if (a.pol == kConst) return 0;
+  if (a.pol == kGlobalTimer) return a.ts ? a.ts : globaltimer();
+  if (a.pol == kAccumulate || a.pol == kLruLfu) return a.freq ? (uint64_t)a.freq[u] : 1;
+  return a.table_scores ? a.table_scores[tid] : 0;
+}
+
+__global__ void train_lookup_kernel(TrainArgs a) {
+  const int64_t n = *a.n_u;
+  for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t key = a.ukeys[u];
+    const int64_t tid = a.utids ? a.utids[u] : 0;
+    Locus L = locate(a.t, key, tid);
+    int64_t slot = -1, row = -1;
+    if (L.cap > 0) {
+      uint8_t* bk = a.t.bucket(L.bucket);
+      const int64_t it = probe_thread(a.t, bk, key, L.h, nullptr);
+      if (it >= 0) {
+        if (a.pol != kConst) policy_update(a.pol, a.t.scores(bk, it), train_score(a, u, tid), a.ts, false);
+        slot = (L.bucket - L.bkt_begin) * a.t.C + it;
+        row = (a.row_base ? a.row_base[tid] : 0) + slot;
+        atomicAdd(a.counter + L.bucket * a.t.C + it, 1);                          // pin (increment_counter, :607)
+      } else {
+        const int old = atomicExch(a.heads + L.bucket, (int)u);
+        a.next[u] = old;
+        if (old == -1) a.touched[atomicAdd(a.n_touched, 1ull)] = (int32_t)L.bucket;
+      }
+    }
+    a.slots[u] = slot;
+    a.rows[u] = row;
+  }
+}
+
+__device__ __forceinline__ bool key_less(uint64_t x, uint64_t y, int is_signed) { return is_signed ? ((int64_t)x < (int64_t)y) : (x < y); }
+
+__device__ __forceinline__ void train_insert_key(const TrainArgs& a, int64_t b, int32_t u, uint64_t key, int lane) {
+  const int64_t tid = a.utids ? a.utids[u] : 0;
+  const int64_t bb = a.t.bkt_off[tid];
+  const InsertOutcome o = warp_insert_one(a.t, b, key, train_score(a, u, tid), a.pol, a.ts, a.bucket_sizes, a.counter, lane);
+  if (o.result <= kEvict) {
+    const int64_t slot = (b - bb) * a.t.C + o.it;
+    const int64_t row = (a.row_base ? a.row_base[tid] : 0) + slot;
+    const int D4 = a.D >> 2, V4 = (int)(a.vdim >> 2);
+    if (o.result != kAssignHit) {                                                   // new row: initializer + optimizer state (fused A10 + A11)
+      for (int c = lane; c < D4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, init4(a.init, key, c));
+      for (int c = D4 + lane; c < V4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, make_float4(a.state_init, a.state_init, a.state_init, a.state_init));
+    }
+    if (lane == 0) { a.slots[u] = slot; a.rows[u] = row; atomicAdd(a.counter + b * a.t.C + o.it, 1); }
+  }
+  __threadfence_block();
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kBlock) train_insert_kernel(TrainArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nt = (int64_t)*a.n_touched;
+  const int64_t wstride = (int64_t)gridDim.x * (kBlock / 32);
+  for (int64_t w = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); w < nt; w += wstride) {
+    const int64_t b = a.touched[w];
+    const int head = *reinterpret_cast<volatile int*>(a.heads + b);
+    // pop the list: lane l keeps the l-th element (lists are 1-3 long in practice; > 32 takes the selection path below)
+    int cnt = 0, mine = -1;
+    for (int cur = head; cur != -1; cur = a.next[cur]) { if (cnt == lane) mine = cur; ++cnt; }
+    if (cnt <= 32) {
+      const uint64_t mykey = mine >= 0 ? a.ukeys[mine] : 0;
+      int rank = 0;
+      for (int l = 0; l < cnt; ++l) {
+        const uint64_t ok = __shfl_sync(0xffffffffu, mykey, l);
+        if (mine >= 0 && l != lane && key_less(ok, mykey, a.key_is_signed)) ++rank;   // keys are unique => strict order
+      }
+      if (mine < 0) rank = -1;
+      for (int r = 0; r < cnt; ++r) {
+        const unsigned m = __ballot_sync(0xffffffffu, rank == r);
+        const int src = __ffs(m) - 1;
+        train_insert_key(a, b, __shfl_sync(0xffffffffu, mine, src), __shfl_sync(0xffffffffu, mykey, src), lane);
+      }
+    } else {
+      // long list (tiny tables / adversarial batches): repeated selection of the smallest key greater than the last inserted one
+      bool have_last = false; uint64_t last = 0;
+      for (int r = 0; r < cnt; ++r) {
+        uint64_t best = 0; int bu = -1; int idx = 0;
+        for (int cur = head; cur != -1; cur = a.next[cur], ++idx) {
+          if ((idx & 31) != lane) continue;
+          const uint64_t k = a.ukeys[cur];
+          if (have_last && !key_less(last, k, a.key_is_signed)) continue;
+          if (bu < 0 || key_less(k, best, a.key_is_signed)) { best = k; bu = cur; }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          const uint64_t ok = __shfl_xor_sync(0xffffffffu, best, d);
+          const int ou = __shfl_xor_sync(0xffffffffu, bu, d);
+          if (ou >= 0 && (bu < 0 || key_less(ok, best, a.key_is_signed))) { best = ok; bu = ou; }
+        }
+        train_insert_key(a, b, bu, best, lane);
+        last = best; have_last = true;
+      }
+    }
+    if (lane == 0) a.heads[b] = -1;                                               // leave the list heads clean for the next step
+  }
+}
+
+__global__ void counter_update_n_kernel(int32_t* counter, const int64_t* __restrict__ slots, const int64_t* __restrict__ tids,
+                                        const int64_t* __restrict__ bkt_off, int64_t C, const int64_t* __restrict__ n_dev, int delta) {
+  const int64_t n = *n_dev;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = slots[i];
+    if (s >= 0) atomicAdd(counter + bkt_off[tids ? tids[i] : 0] * C + s, delta);
+  }
+}
+__global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+int grid_for(int64_t n) { int64_t g = (n + kBlock - 1) / kBlock; return (int)(g < 1 ? 1 : (g > 148 * 32 ? 148 * 32 : g)); }
+}  // namespace
+
+extern "C" {
+
+int demb_fill_i32(int32_t* p, int64_t n, int32_t v, void* stream) {
+  if (n <= 0) return 0;
+  fill_i32_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(p, n, v);
+  DEMB_CHECK_LAST();
+  return 0;
+}
+
+int64_t demb_train_prefetch_workspace_bytes(int64_t n, int num_tables) {
+  return demb_segmented_unique_workspace_bytes(n, num_tables) + (int64_t)(2 * align256(4 * (size_t)(n > 0 ? n : 1)) + 512);
+}
+
+int demb_train_prefetch(void* storage, const int64_t* table_bucket_offsets, int64_t bucket_capacity, int num_scores, int32_t* bucket_sizes,
+                        int32_t* ref_counter, int32_t* bucket_heads, float* values, int64_t value_dim, int emb_dim, const int64_t* row_base,
+                        int64_t n, const void* keys, const int64_t* table_range, int num_tables, const int64_t* freq_in, int policy,
+                        const uint64_t* table_scores, uint64_t timestamp, int key_is_signed, int init_mode, float p0, float p1, float p2, float p3,
+                        uint64_t seed, float state_init, void* unique_keys, int64_t* reverse_indices, int64_t* unique_table_ids,
+                        int64_t* unique_freq, int64_t* slots, int64_t* rows, int64_t* num_unique, void* workspace, int64_t workspace_bytes,
+                        void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n <= 0) return demb_segmented_unique(0, keys, table_range, num_tables, nullptr, unique_keys, reverse_indices, nullptr, nullptr, nullptr, num_unique, workspace, workspace_bytes, stream_);
+  if (workspace_bytes < demb_train_prefetch_workspace_bytes(n, num_tables)) return DEMB_ERR_WORKSPACE;
+  if ((emb_dim & 3) || (value_dim & 3) || value_dim < emb_dim) return DEMB_ERR_ARG;
+  uint8_t* w = (uint8_t*)workspace;
+  int32_t* next = (int32_t*)w; w += align256(4 * (size_t)n);
+  int32_t* touched = (int32_t*)w; w += align256(4 * (size_t)n);
+  unsigned long long* n_touched = (unsigned long long*)w; w += 256;
+  const int64_t uws = (int64_t)((uint8_t*)workspace + workspace_bytes - w);
+  cudaMemsetAsync(n_touched, 0, 8, stream);
+  const bool need_freq = (policy == kAccumulate || policy == kLruLfu);
+  int rc = demb_segmented_unique(n, keys, table_range, num_tables, freq_in, unique_keys, reverse_indices, nullptr, need_freq ? unique_freq : nullptr,
+                                 unique_table_ids, num_unique, w, uws, stream_);
+  if (rc) return rc;
+  TrainArgs a;
+  a.t = Table{(uint8_t*)storage, table_bucket_offsets, bucket_capacity, num_scores};
+  a.bucket_sizes = bucket_sizes; a.counter = ref_counter; a.heads = bucket_heads;
+  a.values = values; a.vdim = value_dim; a.D = emb_dim; a.row_base = row_base;
+  a.ukeys = (const uint64_t*)unique_keys; a.utids = num_tables > 1 ? unique_table_ids : nullptr; a.n_u = num_unique;
+  a.pol = policy; a.table_scores = table_scores; a.freq = need_freq ? unique_freq : nullptr; a.ts = timestamp; a.key_is_signed = key_is_signed;
+  a.init = InitArgs{init_mode, p0, p1, p2, p3, seed}; a.state_init = state_init;
+  a.slots = slots; a.rows = rows; a.next = next; a.touched = touched; a.n_touched = n_touched;
+  train_lookup_kernel<<<grid_for(n), kBlock, 0, stream>>>(a);
+  train_insert_kernel<<<148 * 4, kBlock, 0, stream>>>(a);
+  DEMB_CHECK_LAST();
+  return 0;
+}
+
+int demb_counter_update_n(int32_t* ref_counter, const int64_t* slot_indices, const int64_t* table_ids, const int64_t* table_bucket_offsets,
+                          int64_t bucket_capacity, const int64_t* n_device, int64_t n_max, int delta, void* stream) {
+  if (n_max <= 0) return 0;
+  counter_update_n_kernel<<<grid_for(n_max), kBlock, 0, (cudaStream_t)stream>>>(ref_counter, slot_indices, table_ids, table_bucket_offsets, bucket_capacity,
+                                                                                n_device, delta);
+  DEMB_CHECK_LAST();
+  return 0;
+}
+
+}  // extern "C"

@@ -4,12 +4,12 @@
 // host wrapper hstu_ops_gpu.py:85-252); mask rule = hstu_blackwell/mask.py:61-127 (causal / local window,
 // target groups, contexts).  Hand-written tcgen05 / TMA / TMEM:
 //
-//   CTA = one 128-row Q tile of one (b, h); 8 warps:
+//   CTA = one 128-row Q tile of one (b, h); 12 warps:
 //     warp 0    TMA producer  : Q once, then K_j / V_j tiles (128 x D bf16, SWIZZLE_128B boxes of 64 columns) into 2-stage rings
 //     warp 1    MMA issuer    : S_j = Q K_j^T  (SS, K-major x K-major, fp32 in TMEM, double-buffered S0/S1 so QK^T(j+1) overlaps
 //                               the SiLU of tile j);  O += P_j V_j  (SS, P K-major from smem, V MN-major straight from its TMA tile)
 //     warp 2    TMEM alloc/dealloc (512 columns: S0 @0, S1 @128, O @256)
-//     warps 4-7 SiLU warpgroup: thread = accumulator row; tcgen05.ld 32 columns at a time -> h + h*tanh.approx(h), h = alpha/2*s
+//     warps 4-11 two SiLU warpgroups (64 score columns each): thread = accumulator row; tcgen05.ld 32 columns at a time -> h + h*tanh.approx(h), h = alpha/2*s
 //                               (1 FMUL + 1 MUFU + 1 FFMA per score), mask only on boundary tiles, bf16 pack, st.shared into the
 //                               swizzled K-major P tile; finally O: TMEM -> regs -> *1/N -> bf16 -> 16-byte global stores.
 //   The 1/N scale is applied once to O (linear), not to every P element.
@@ -51,7 +51,7 @@ struct FwdSmem {
 };
 
 template <int D>
-__global__ void __launch_bounds__(256, 1) hstu_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+__global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                                                           const __grid_constant__ CUtensorMap map_v, FwdParams p) {
   using SM = FwdSmem<D>;
   constexpr int NH = D / 64;                         // 64-column (128-byte) halves per tile row
@@ -81,10 +81,10 @@ __global__ void __launch_bounds__(256, 1) hstu_fwd_kernel(const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(&q_full, 1); mbar_init(&p_full, 4); mbar_init(&p_empty, 1); mbar_init(&o_full, 1);
+    mbar_init(&q_full, 1); mbar_init(&p_full, 8); mbar_init(&p_empty, 1); mbar_init(&o_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
     }
     fence_barrier_init();
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
@@ -166,64 +166,62 @@ __global__ void __launch_bounds__(256, 1) hstu_fwd_kernel(const __grid_constant_
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ SiLU warpgroup + epilogue
-    const int wq = warp - 4;                       // TMEM lane quadrant
+    // two SiLU warpgroups split the 128 score columns of every tile (warps 4-7: columns 0-63, warps 8-11: columns 64-127) so
+    // two warps per SM sub-partition hide each other's TMEM-load / MUFU latency
+    const int wq = warp & 3;                       // TMEM lane quadrant
+    const int ch = (warp - 4) >> 2;                // column half
     const int rit = wq * 32 + lane;                // row in tile
     const int row = r0 + rit;
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
-    uint8_t* sP = smem + SM::kP;
+    uint8_t* sP = smem + SM::kP + ch * 16384 + rit * 128;
     const Intervals iv = cols_of_row(mk, row);
     for (int j = 0; j < n_iter; ++j) {
       const int st = j & 1, ph = (j >> 1) & 1;
-      const int c_base = (nb0 + j) * 128;
-      const bool full = mk.tile_full(r0, r1, c_base, c_base + 127);
+      const int c_base = (nb0 + j) * 128 + ch * 64;
+      const bool full = mk.tile_full(r0, r1, c_base, c_base + 63);
       if (threadIdx.x == 128) HSTU_DBG(16, j + 1);
       mbar_wait(&s_full[st], ph);
       if (threadIdx.x == 128) HSTU_DBG(17, j + 1);
       tc_fence_after();
+      uint32_t s0[32], s1[32];
+      tmem_ld32(tS[st] + lane_off + ch * 64, s0);
+      tmem_ld32(tS[st] + lane_off + ch * 64 + 32, s1);
+      tmem_ld_wait();
+      tc_fence_before();                           // S_j fully read: hand the buffer back to the MMA warp
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+      uint32_t pk[32];
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t s[32];
-        tmem_ld32(tS[st] + lane_off + cc * 32, s);
-        tmem_ld_wait();
-        if (cc == 3) {                              // S_j fully read: hand the buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[st]);
+      for (int i = 0; i < 64; i += 2) {
+        const uint32_t a = i < 32 ? s0[i] : s1[i - 32], b = i < 32 ? s0[i + 1] : s1[i - 31];
+        float h0 = __uint_as_float(a) * p.half_alpha, h1 = __uint_as_float(b) * p.half_alpha;
+        float p0 = fmaf(h0, tanh_approx(h0), h0), p1 = fmaf(h1, tanh_approx(h1), h1);
+        if (!full) {
+          const int col = c_base + i;
+          p0 = iv.has(col) ? p0 : 0.f;
+          p1 = iv.has(col + 1) ? p1 : 0.f;
         }
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float h0 = __uint_as_float(s[i]) * p.half_alpha, h1 = __uint_as_float(s[i + 1]) * p.half_alpha;
-          float p0 = fmaf(h0, tanh_approx(h0), h0), p1 = fmaf(h1, tanh_approx(h1), h1);
-          if (!full) {
-            const int col = c_base + cc * 32 + i;
-            p0 = iv.has(col) ? p0 : 0.f;
-            p1 = iv.has(col + 1) ? p1 : 0.f;
-          }
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        if (cc == 0) mbar_wait(&p_empty, (j & 1) ^ 1);   // PV(j-1) has consumed the previous P tile
-        uint8_t* dst = sP + (cc >> 1) * 16384 + rit * 128;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int chunk = (cc & 1) * 4 + q4;
-          *reinterpret_cast<uint4*>(dst + ((chunk ^ (rit & 7)) << 4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-        }
+        pk[i >> 1] = pack_bf16x2(p0, p1);
       }
+      mbar_wait(&p_empty, (j & 1) ^ 1);            // PV(j-1) has consumed the previous P tile
+#pragma unroll
+      for (int q8 = 0; q8 < 8; ++q8)
+        *reinterpret_cast<uint4*>(sP + ((q8 ^ (rit & 7)) << 4)) = make_uint4(pk[4 * q8], pk[4 * q8 + 1], pk[4 * q8 + 2], pk[4 * q8 + 3]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full);
       if (threadIdx.x == 128) HSTU_DBG(18, j + 1);
     }
-    // epilogue
+    // epilogue: each warpgroup stores half of the D output columns of its rows
     mbar_wait(&o_full, 0);
     if (threadIdx.x == 128) HSTU_DBG(19, 1);
     tc_fence_after();
     __nv_bfloat16* orow = p.out + ((int64_t)(seq_start + row) * p.H + h) * D;
 #pragma unroll
-    for (int cc = 0; cc < D / 32; ++cc) {
+    for (int cc = 0; cc < D / 64; ++cc) {
+      const int c = ch * (D / 2) + cc * 32;
       uint32_t o[32];
-      tmem_ld32(tO + lane_off + cc * 32, o);
+      tmem_ld32(tO + lane_off + c, o);
       tmem_ld_wait();
       if (row < L) {
 #pragma unroll
@@ -233,7 +231,7 @@ __global__ void __launch_bounds__(256, 1) hstu_fwd_kernel(const __grid_constant_
           v.y = pack_bf16x2(__uint_as_float(o[8 * q4 + 2]) * p.inv_scale, __uint_as_float(o[8 * q4 + 3]) * p.inv_scale);
           v.z = pack_bf16x2(__uint_as_float(o[8 * q4 + 4]) * p.inv_scale, __uint_as_float(o[8 * q4 + 5]) * p.inv_scale);
           v.w = pack_bf16x2(__uint_as_float(o[8 * q4 + 6]) * p.inv_scale, __uint_as_float(o[8 * q4 + 7]) * p.inv_scale);
-          *reinterpret_cast<uint4*>(orow + cc * 32 + q4 * 8) = v;
+          *reinterpret_cast<uint4*>(orow + c + q4 * 8) = v;
         }
       }
     }
@@ -253,7 +251,7 @@ int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mkk, const CUtensorMap&
     configured = true;
   }
   dim3 grid((max_seqlen + 127) / 128, p.H, B);
-  hstu_fwd_kernel<D><<<grid, 256, smem, stream>>>(mq, mkk, mv, p);
+  hstu_fwd_kernel<D><<<grid, 384, smem, stream>>>(mq, mkk, mv, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

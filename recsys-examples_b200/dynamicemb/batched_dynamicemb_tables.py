@@ -68,7 +68,12 @@ class PrefetchState:
     unique_table_ids: torch.Tensor
     slot_indices: torch.Tensor      # table-local slot per unique key, -1 = insert failed
     rows: torch.Tensor              # global value row per unique key, -1 = absent
-    num_unique: int
+    num_unique_bound: int           # host-known upper bound of the unique count (sort width)
+    num_unique_dev: Optional[torch.Tensor] = None   # device-side count (fused path: buffers are sized by the bound)
+
+    @property
+    def num_unique(self) -> int:
+        return int(self.num_unique_dev.item()) if self.num_unique_dev is not None else self.num_unique_bound
 
 
 class _LookupFunction(torch.autograd.Function):
@@ -95,10 +100,10 @@ class _LookupFunction(torch.autograd.Function):
             grads = grads.clamp(-opt.args.max_gradient, opt.args.max_gradient)
         opt.step()
         pooled = ctx.combiner >= 0
-        ext.backward(m._values, m.max_D, st.reverse_indices, max(st.num_unique, 1), st.rows, grads, offsets=ctx.offsets if pooled else None,
+        ext.backward(m._values, m.max_D, st.reverse_indices, max(st.num_unique_bound, 1), st.rows, grads, offsets=ctx.offsets if pooled else None,
                      batch_size=ctx.batch_size if pooled else 0, num_features=m.feature_num if pooled else 0, combiner=ctx.combiner,
                      **opt.kernel_kwargs())
-        m._table.decrement_counter(st.slot_indices, st.unique_table_ids)
+        m._unpin(st)
         return None, None, None, None, None
 
 
@@ -186,6 +191,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         self.value_dim = (self.value_dim + 3) // 4 * 4
         self._values = torch.zeros(self._table.capacity_, self.value_dim, dtype=torch.float32, device=self._device)
         self._seed = int(kwargs.get("seed", 0))
+        self._fused_prefetch = bool(kwargs.get("fused_prefetch", True))     # False = op-by-op path (reference op order, 2 host syncs)
         self._prefetch_states: Deque[PrefetchState] = deque()
         self._empty_tensor = nn.Parameter(torch.empty(10, requires_grad=True, device=self._device, dtype=self.embedding_dtype))
         self.bounds_check_mode_int = int(bounds_check_mode)
@@ -221,10 +227,20 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
             return ScorePolicy.ACCUMULATE
         return ScorePolicy.ASSIGN
 
+    def _device_scores(self) -> torch.Tensor:
+        """Per-table ASSIGN scores kept on the device so a training step never copies host data (STEP scores advance with add_)."""
+        if getattr(self, "_scores_dev", None) is None:
+            self._scores_dev = torch.tensor([self._scores[nm] & 0x7FFFFFFFFFFFFFFF for nm in self._table_names], dtype=torch.int64, device=self._device)
+            self._step_mask = torch.tensor([1 if o.score_strategy == DynamicEmbScoreStrategy.STEP else 0 for o in self._dynamicemb_options],
+                                           dtype=torch.int64, device=self._device)
+        return self._scores_dev
+
     def _update_score(self):
         for name, o in zip(self._table_names, self._dynamicemb_options):
             if o.score_strategy == DynamicEmbScoreStrategy.STEP:
                 self._scores[name] = (self._scores[name] + 1) & 0xFFFFFFFFFFFFFFFF
+        if getattr(self, "_scores_dev", None) is not None:
+            self._scores_dev.add_(self._step_mask)
 
     def set_score(self, named_score: Dict[str, int]) -> None:
         for name, score in named_score.items():
@@ -236,6 +252,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
             assert self._dynamicemb_options[idx].score_strategy == DynamicEmbScoreStrategy.CUSTOMIZED, \
                 "Can only set score for table whose score_strategy is DynamicEmbScoreStrategy.CUSTOMIZED."
             self._scores[name] = score
+        self._scores_dev = None          # rebuilt lazily from the host copy
 
     def get_score(self) -> Dict[str, int]:
         out = {}
@@ -296,6 +313,9 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         T = len(self._dynamicemb_options)
         tb = self._table
         trange = ext.get_table_range(offsets, self.feature_offsets, self.feature_num) if T > 1 else None
+        if self._fused_prefetch:
+            self._prefetch_fused(indices, trange, T, frequency_counters)
+            return
         want_freq = self._score_policy() == ScorePolicy.ACCUMULATE
         freq_in = (frequency_counters.to(torch.int64) if frequency_counters is not None
                    else (torch.empty(0, dtype=torch.int64, device=self._device) if want_freq else None))
@@ -320,6 +340,32 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         self._prefetch_states.append(PrefetchState(ukeys, reverse, utids, slots, rows, nu))
         self._update_score()
 
+    def _prefetch_fused(self, indices, trange, T, frequency_counters) -> None:
+        """Same table image / rows as the op-by-op path, one C call, no host sync (csrc/demb_train.cu)."""
+        tb = self._table
+        policy = self._score_policy()
+        scores = None
+        if policy == ScorePolicy.ASSIGN:
+            for name in self._table_names:
+                if name not in self._scores:
+                    raise RuntimeError(f"Must set score for table '{name}' whose score_strategy is customized.")
+            scores = self._device_scores()
+        mode, p = _init_params(self._dynamicemb_options[0].initializer_args, self._dynamicemb_options[0].max_capacity)
+        uk, rev, utids, slots, rows, nu = ext.train_prefetch(
+            tb.table_storage_, tb.table_bucket_offsets_, tb.bucket_capacity_, tb.bucket_sizes, tb._ref_counter, tb._bucket_heads, self._values,
+            self.max_D, tb.row_base_, indices, trange, T, policy, scores, ext.device_timestamp(), mode, p, self._seed,
+            self._optimizer.initial_state_value, freq_in=frequency_counters, num_scores=tb.num_scores_)
+        self._prefetch_states.append(PrefetchState(uk, rev, utids if T > 1 else None, slots, rows, indices.numel(), nu))
+        self._update_score()
+
+    def _unpin(self, st: PrefetchState) -> None:
+        tb = self._table
+        if st.num_unique_dev is not None:
+            ext.table_update_counter_n(tb._ref_counter, st.slot_indices, -1, tb.table_bucket_offsets_, tb.bucket_capacity_, st.num_unique_dev,
+                                       table_ids=st.unique_table_ids)
+        else:
+            tb.decrement_counter(st.slot_indices, st.unique_table_ids)
+
     def forward(self, indices, offsets, per_sample_weights=None, feature_requires_grad=None, batch_size_per_feature_per_rank=None,
                 total_unique_indices=None) -> torch.Tensor:
         indices, offsets, B = self._split(indices, offsets)
@@ -330,7 +376,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         state = self._prefetch_states.popleft()
         if not torch.is_grad_enabled():
             out = _LookupFunction.forward(_NoCtx(), self, state, offsets, B, None)
-            self._table.decrement_counter(state.slot_indices, state.unique_table_ids)
+            self._unpin(state)
             return out
         return _LookupFunction.apply(self, state, offsets, B, self._empty_tensor)
 

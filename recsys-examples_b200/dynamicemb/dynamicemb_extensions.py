@@ -201,6 +201,42 @@ def table_export_batch(table_storage, bucket_capacity, batch, offset, key_dtype,
     return counter, keys, scores.view(torch.uint64), indices
 
 
+def fill_i32(t: torch.Tensor, v: int) -> None:
+    N.check(N.lib.demb_fill_i32(N.ptr(t), t.numel(), int(v), N.stream()), "fill_i32")
+
+
+def table_update_counter_n(counter, slot_indices, delta, table_bucket_offsets, bucket_capacity, n_device, table_ids=None) -> None:
+    """counter update whose element count lives on the device (fused training path: no host sync)."""
+    N.check(N.launch("counter_update", 1, N.lib.demb_counter_update_n, N.ptr(counter), N.ptr(slot_indices), N.ptr(table_ids),
+                     N.ptr(table_bucket_offsets), bucket_capacity, N.ptr(n_device), slot_indices.numel(), int(delta), N.stream()),
+            "counter_update_n")
+
+
+def train_prefetch(table_storage, table_bucket_offsets, bucket_capacity, bucket_sizes, ref_counter, bucket_heads, values, emb_dim, row_base,
+                   keys, table_range, num_tables, policy, table_scores, timestamp, init_mode, init_params, seed, state_init,
+                   freq_in=None, num_scores=1):
+    """Fused dedup + probe + insert/init + pin (demb_train.cu).  Returns (unique_keys[n], reverse[n], unique_table_ids[n], slots[n],
+    rows[n], num_unique[1] device) — only the first num_unique entries of the per-unique outputs are meaningful."""
+    n = keys.numel()
+    dev = keys.device
+    uk = torch.empty(n, dtype=keys.dtype, device=dev)
+    rev = torch.empty(n, dtype=torch.int64, device=dev)
+    utids = torch.empty(n, dtype=torch.int64, device=dev)
+    ufreq = torch.empty(n, dtype=torch.int64, device=dev) if int(policy) in (2, 4) else None
+    slots = torch.empty(n, dtype=torch.int64, device=dev)
+    rows = torch.empty(n, dtype=torch.int64, device=dev)
+    nu = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = N.workspace(N.lib.demb_train_prefetch_workspace_bytes(n, num_tables), dev)
+    p0, p1, p2, p3 = init_params
+    N.check(N.launch("train_prefetch", 6, N.lib.demb_train_prefetch, N.ptr(table_storage), N.ptr(table_bucket_offsets), bucket_capacity, num_scores,
+                     N.ptr(bucket_sizes), N.ptr(ref_counter), N.ptr(bucket_heads), N.ptr(values), values.stride(0), emb_dim, N.ptr(row_base), n,
+                     N.ptr(keys.contiguous()), N.ptr(table_range), num_tables, N.ptr(_i64(freq_in)), int(policy), N.ptr(table_scores), int(timestamp),
+                     1 if keys.dtype == torch.int64 else 0, int(init_mode), float(p0), float(p1), float(p2), float(p3), int(seed), float(state_init),
+                     N.ptr(uk), N.ptr(rev), N.ptr(utids), N.ptr(ufreq), N.ptr(slots), N.ptr(rows), N.ptr(nu), N.ptr(ws), ws.numel(), N.stream()),
+            "train_prefetch")
+    return uk, rev, utids, slots, rows, nu
+
+
 # ---------------------------------------------------------------------------------------------------
 # dedup
 # ---------------------------------------------------------------------------------------------------

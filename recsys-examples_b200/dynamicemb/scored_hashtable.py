@@ -90,6 +90,7 @@ class LinearBucketTable:
         self.keys_, self.digests_ = ext.table_partition(self.table_storage_, fields, C, self.num_buckets_)[:2]
         self.bucket_sizes = torch.zeros(self.num_buckets_, dtype=torch.int32, device=self.device)
         self._ref_counter = torch.zeros(self.capacity_, dtype=torch.int32, device=self.device)
+        self._bucket_heads = torch.empty(self.num_buckets_, dtype=torch.int32, device=self.device)   # per-bucket pending-insert lists (fused prefetch)
         self.reset()
 
     # ------------------------------------------------------------------ properties
@@ -113,6 +114,7 @@ class LinearBucketTable:
         ext.table_init(self.table_storage_, self.bucket_capacity_, self.num_scores_)
         self.bucket_sizes.zero_()
         self._ref_counter.zero_()
+        ext.fill_i32(self._bucket_heads, -1)
 
     def capacity(self, table_id: Optional[int] = None) -> int:
         return self.capacity_ if table_id is None else self.per_table_capacity_[table_id]

@@ -140,3 +140,30 @@ def test_eviction_steady_state_keeps_training(cuda):
         assert torch.isfinite(out).all()
     assert m.tables.size() <= 1024
     assert int(m.tables._ref_counter.sum().item()) == 0
+
+
+@pytest.mark.parametrize("pooling,T", [("none", 1), ("sum", 2)])
+def test_fused_prefetch_matches_op_by_op(cuda, pooling, T):
+    """The fused no-sync prefetch (csrc/demb_train.cu) must leave byte-identical table images, value rows and outputs as the
+    op-by-op path (lookup -> insert -> init_rows), including under eviction pressure (small table)."""
+    from dynamicemb import DynamicEmbPoolingMode, EmbOptimType
+    pm = {"none": DynamicEmbPoolingMode.NONE, "sum": DynamicEmbPoolingMode.SUM}[pooling]
+    ma = _module(cuda, EmbOptimType.EXACT_ADAGRAD, pm, D=64, n_tables=T, cap=2048, learning_rate=0.05, fused_prefetch=True)
+    mb = _module(cuda, EmbOptimType.EXACT_ADAGRAD, pm, D=64, n_tables=T, cap=2048, learning_rate=0.05, fused_prefetch=False)
+    ma.train(); mb.train()
+    rng = np.random.default_rng(42)
+    B = 32
+    for it in range(25):
+        lens = rng.integers(0, 12, size=T * B)
+        offsets = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)).to(cuda)
+        ids = torch.from_numpy((rng.zipf(1.2, size=int(lens.sum())) % 5000).astype(np.int64) * 7919).to(cuda)
+        oa, ob = ma(ids, offsets), mb(ids, offsets)
+        assert torch.equal(oa, ob), f"iter {it}: outputs differ"
+        g = torch.randn_like(oa)
+        oa.backward(g); ob.backward(g)
+        assert torch.equal(ma.tables.table_storage_, mb.tables.table_storage_), f"iter {it}: table image differs"
+        assert torch.equal(ma._values, mb._values), f"iter {it}: value rows differ"
+        assert torch.equal(ma.tables.bucket_sizes, mb.tables.bucket_sizes)
+        assert int(ma.tables._ref_counter.sum().item()) == 0 and int(mb.tables._ref_counter.sum().item()) == 0
+        assert int((ma.tables._bucket_heads != -1).sum().item()) == 0
+    assert ma.tables.size() > 1500      # the table did fill up => evictions happened

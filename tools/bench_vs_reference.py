@@ -174,6 +174,8 @@ def hstu():
         r["ref_fwd_tflops"] = fl / r["ref_fwd_ms"] / 1e9
         r["fwd_max_abs_diff_vs_ref_kernel"] = (out_r.float() - out_o.float()).abs().max().item()
         t0 = time.time()
+        qc, kc, vc = q.contiguous(), k.contiguous(), v.contiguous()      # the reference bwd rejects the strided uvqk views ("stride_order")
+        q, k, v = qc, kc, vc
         g = refk.hstu_varlen_bwd_100(do, q, k, v, cu, cu, S, S, None, None, None, None, None, 1, -1, 0, a, None, False, None, False)
         torch.cuda.synchronize()
         r["ref_bwd_jit_s"] = time.time() - t0
