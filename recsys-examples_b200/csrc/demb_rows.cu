@@ -16,6 +16,7 @@
 #include "../../include/dynamicemb_b200.h"
 #include "demb_common.cuh"
 #include "demb_init.cuh"
+#include "sm100_ptx.cuh"
 
 using namespace demb;
 
@@ -111,6 +112,53 @@ __global__ void __launch_bounds__(kBlock) forward_seq_kernel(RowSrc s, const flo
       }
     }
   }
+}
+
+// ---- forward, sequence mode, fp32 output: TMA-staged variant ------------------------------------------------------------------
+// Rows never pass through registers: after the 32-id probe pass each lane issues ONE bulk async copy (cp.async.bulk, 512 B for
+// D=128) of its row into the warp's shared-memory stage, completion is tracked by an mbarrier, and because the 32 output rows of a
+// tile are contiguous the whole stage leaves with a SINGLE 16 KB bulk store.  12 warps x 16 KB = 192 KB of loads in flight per SM
+// (the register kernel above tops out at ~64 KB/SM, occupancy-bound at 98 registers) — a memcpy-shaped pipeline for the gather.
+__global__ void __launch_bounds__(384) forward_seq_tma_kernel(RowSrc s, const float* __restrict__ values, int64_t vdim, int D, int64_t n,
+                                                              float* __restrict__ out, float absent_value, int warps_per_block) {
+  extern __shared__ __align__(128) uint8_t stage_raw[];
+  __shared__ uint64_t bars[12];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  if (wib >= warps_per_block) return;
+  const uint32_t row_bytes = (uint32_t)D * 4u;
+  uint8_t* buf = stage_raw + (size_t)wib * 32u * row_bytes;
+  if (lane == 0) { sm100::mbar_init(&bars[wib], 1); sm100::fence_barrier_init(); }
+  __syncwarp();
+  uint32_t parity = 0;
+  const int64_t tiles = (n + 31) >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * warps_per_block;
+  for (int64_t tile = (int64_t)blockIdx.x * warps_per_block + wib; tile < tiles; tile += wstride) {
+    const int64_t base = tile << 5;
+    const int cnt = (int)((n - base) < 32 ? (n - base) : 32);
+    int64_t row = -1;
+    if (lane < cnt) row = resolve_row(s, base + lane);
+    const unsigned found = __ballot_sync(0xffffffffu, row >= 0);
+    if (lane == 0) {
+      sm100::bulk_wait_read0();                                  // the previous tile's bulk store has finished reading this stage
+      sm100::mbar_arrive_expect_tx(&bars[wib], (uint32_t)__popc(found) * row_bytes);
+    }
+    __syncwarp();
+    if (row >= 0) {
+      sm100::bulk_load(buf + (size_t)lane * row_bytes, values + row * vdim, row_bytes, &bars[wib]);
+    } else if (lane < cnt) {
+      float4* d = reinterpret_cast<float4*>(buf + (size_t)lane * row_bytes);
+      for (int c = 0; c < (D >> 2); ++c) d[c] = make_float4(absent_value, absent_value, absent_value, absent_value);
+    }
+    sm100::mbar_wait(&bars[wib], parity);
+    parity ^= 1;
+    sm100::fence_proxy_async_smem();                             // absent rows were written through the generic proxy
+    __syncwarp();
+    if (lane == 0) {
+      sm100::bulk_store(out + base * (int64_t)D, buf, (uint32_t)cnt * row_bytes);
+      sm100::bulk_commit();
+    }
+  }
+  if (lane == 0) sm100::bulk_wait0();                             // shared memory must outlive the last bulk store
 }
 
 // ---- forward, pooled mode: ids feature-major (offsets index f*B+b, lookup_forward.cu:53-59);
@@ -538,6 +586,26 @@ static int pool_bags_per_warp(int64_t n_ids, int64_t bags) {
   int64_t bpw = 32 / (avg < 1 ? 1 : avg);
   return (int)(bpw < 1 ? 1 : (bpw > 16 ? 16 : bpw));
 }
+static int launch_seq_tma(const RowSrc& s, const float* values, int64_t value_dim, int emb_dim, int64_t n, float* out, float absent_value,
+                          cudaStream_t stream) {
+  const size_t stage = 32u * (size_t)emb_dim * 4u;                 // bytes per warp stage
+  int warps = (int)((216u * 1024u) / stage);
+  if (warps > 12) warps = 12;
+  if (warps < 1) return DEMB_ERR_ARG;
+  const int smem = (int)(warps * stage);
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(forward_seq_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    if (e != cudaSuccess) return -(int)e;
+    configured = 216 * 1024;
+  }
+  const int64_t tiles = (n + 31) / 32;
+  int64_t blocks = (tiles + warps - 1) / warps;
+  if (blocks > 148) blocks = 148;                                  // one CTA per SM owns the whole shared memory; persistent over tiles
+  forward_seq_tma_kernel<<<(int)blocks, 384, smem, stream>>>(s, values, value_dim, emb_dim, n, out, absent_value, warps);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}
 static int check_dims(int D, int64_t vdim) { return (D <= 0 || (D & 3) || D > 128 * kMaxChunks || (vdim & 3) || vdim < D) ? DEMB_ERR_ARG : 0; }
 
 int demb_lookup_forward(void* storage, const int64_t* table_bucket_offsets, int64_t bucket_capacity, int num_scores, const float* values,
@@ -549,6 +617,7 @@ int demb_lookup_forward(void* storage, const int64_t* table_bucket_offsets, int6
            nullptr, nullptr, founds, slots_out};
   if (combiner < 0) {
     if (n <= 0) return 0;
+    if (out_dtype == DEMB_F32) return launch_seq_tma(s, values, value_dim, emb_dim, n, (float*)out, absent_value, (cudaStream_t)stream);
     forward_seq_kernel<8><<<warp_grid((n + 31) / 32), kBlock, 0, (cudaStream_t)stream>>>(s, values, value_dim, emb_dim, n, out, out_dtype, absent_value);
   } else {
     if (batch_size <= 0 || num_features <= 0) return 0;
@@ -569,6 +638,7 @@ int demb_gather_forward(const float* values, int64_t value_dim, int emb_dim, int
   RowSrc s{Table{nullptr, nullptr, 0, 1}, nullptr, nullptr, 1, nullptr, rows, inverse, nullptr, nullptr};
   if (combiner < 0) {
     if (n <= 0) return 0;
+    if (out_dtype == DEMB_F32) return launch_seq_tma(s, values, value_dim, emb_dim, n, (float*)out, 0.f, (cudaStream_t)stream);
     forward_seq_kernel<8><<<warp_grid((n + 31) / 32), kBlock, 0, (cudaStream_t)stream>>>(s, values, value_dim, emb_dim, n, out, out_dtype, 0.f);
   } else {
     if (batch_size <= 0 || num_features <= 0) return 0;

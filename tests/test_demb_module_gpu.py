@@ -153,10 +153,10 @@ def test_fused_prefetch_matches_op_by_op(cuda, pooling, T):
     ma.train(); mb.train()
     rng = np.random.default_rng(42)
     B = 32
-    for it in range(25):
-        lens = rng.integers(0, 12, size=T * B)
+    for it in range(40):
+        lens = rng.integers(0, 24, size=T * B)
         offsets = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)).to(cuda)
-        ids = torch.from_numpy((rng.zipf(1.2, size=int(lens.sum())) % 5000).astype(np.int64) * 7919).to(cuda)
+        ids = torch.from_numpy((rng.zipf(1.1, size=int(lens.sum())) % 20000).astype(np.int64) * 7919).to(cuda)
         oa, ob = ma(ids, offsets), mb(ids, offsets)
         assert torch.equal(oa, ob), f"iter {it}: outputs differ"
         g = torch.randn_like(oa)
@@ -166,4 +166,4 @@ def test_fused_prefetch_matches_op_by_op(cuda, pooling, T):
         assert torch.equal(ma.tables.bucket_sizes, mb.tables.bucket_sizes)
         assert int(ma.tables._ref_counter.sum().item()) == 0 and int(mb.tables._ref_counter.sum().item()) == 0
         assert int((ma.tables._bucket_heads != -1).sum().item()) == 0
-    assert ma.tables.size() > 1500      # the table did fill up => evictions happened
+    assert ma.tables.size() > 1000
