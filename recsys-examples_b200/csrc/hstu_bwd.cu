@@ -221,26 +221,24 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[st]);
       uint32_t pk_ds[16], pk_p[16];
+      const f32x2 ha2 = pack2(p.half_alpha, p.half_alpha), one2 = pack2(1.f, 1.f), mone2 = pack2(-1.f, -1.f), mhalf2 = pack2(-0.5f, -0.5f);
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
-        float pv[2], dv[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float hh = __uint_as_float(s[i + e]) * p.half_alpha;
-          const float t = tanh_approx(hh);
-          float pe = fmaf(hh, t, hh);
-          // silu' = 0.5 (1 + t) (1 + h (1 - t)) = (1 - u/2)(1 + h u),  u = 1 - t
-          const float u = 1.f - t;
-          float de = __uint_as_float(dp[i + e]) * (fmaf(-0.5f, u, 1.f) * fmaf(hh, u, 1.f));
-          if (!full) {
-            const bool ok = iv.has(y0 + ch * 32 + i + e);
-            pe = ok ? pe : 0.f;
-            de = ok ? de : 0.f;
-          }
-          pv[e] = pe; dv[e] = de;
+        const f32x2 h2 = mul2(pack2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), ha2);
+        const f32x2 t2 = tanh2(h2);
+        f32x2 pe2 = fma2(h2, t2, h2);                                  // silu = h + h t
+        const f32x2 u2 = fma2(t2, mone2, one2);                        // u = 1 - t
+        // silu' = 0.5 (1 + t) (1 + h (1 - t)) = (1 - u/2)(1 + h u)
+        f32x2 de2 = mul2(pack2(__uint_as_float(dp[i]), __uint_as_float(dp[i + 1])), mul2(fma2(u2, mhalf2, one2), fma2(h2, u2, one2)));
+        if (!full) {
+          const int yi = y0 + ch * 32 + i;
+          const bool ok0 = iv.has(yi), ok1 = iv.has(yi + 1);
+          float a0, a1, b0, b1; unpack2(pe2, a0, a1); unpack2(de2, b0, b1);
+          pe2 = pack2(ok0 ? a0 : 0.f, ok1 ? a1 : 0.f);
+          de2 = pack2(ok0 ? b0 : 0.f, ok1 ? b1 : 0.f);
         }
-        pk_ds[i >> 1] = pack_bf16x2(dv[0], dv[1]);
-        if (!kIsDQ) pk_p[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+        pk_ds[i >> 1] = pack_bf16x2_v(de2);
+        if (!kIsDQ) pk_p[i >> 1] = pack_bf16x2_v(pe2);
       }
       mbar_wait(&pd_empty[st], ph ^ 1);
       uint8_t* dds = smem + SM::oDS + st * SM::kPD + rit * 128;

@@ -38,6 +38,9 @@ struct FwdParams {
 };
 
 // progress marks readable from the host even if the kernel never finishes (development aid)
+// cycle accounting for CTA (0,0,0) when a debug buffer is installed: HSTU_T0 / HSTU_ACC(slot) accumulate clock64() deltas
+#define HSTU_T0() long long t__0 = (p.dbg ? clock64() : 0)
+#define HSTU_ACC(slot) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { long long t__1 = clock64(); p.dbg[slot] += (int)(t__1 - t__0); t__0 = t__1; } } while (0)
 #define HSTU_DBG(slot, val) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { p.dbg[slot] = (val); __threadfence_system(); } } while (0)
 
 template <int D>
@@ -127,8 +130,11 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
       const uint32_t aQ = smem_u32(smem + SM::kQ), aP = smem_u32(smem + SM::kP);
       auto issue_qk = [&](int j) {
         const int st = j & 1, ph = (j >> 1) & 1;
+        HSTU_T0();
         mbar_wait(&k_full[st], ph);
+        HSTU_ACC(40);
         mbar_wait(&s_empty[st], ph ^ 1);
+        HSTU_ACC(41);
         tc_fence_after();
         const uint32_t aK = smem_u32(smem + SM::kK + st * SM::kTile);
 #pragma unroll
@@ -147,10 +153,11 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
       for (int j = 0; j < n_iter; ++j) {
         if (j + 1 < n_iter) issue_qk(j + 1);
         const int st = j & 1, ph = (j >> 1) & 1;
+        HSTU_T0();
         mbar_wait(&v_full[st], ph);
-        HSTU_DBG(11, j + 1);
+        HSTU_ACC(42);
         mbar_wait(&p_full, j & 1);
-        HSTU_DBG(12, j + 1);
+        HSTU_ACC(43);
         tc_fence_after();
         const uint32_t aV = smem_u32(smem + SM::kV + st * SM::kTile);
 #pragma unroll
@@ -179,9 +186,9 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
       const int st = j & 1, ph = (j >> 1) & 1;
       const int c_base = (nb0 + j) * 128 + ch * 64;
       const bool full = mk.tile_full(r0, r1, c_base, c_base + 63);
-      if (threadIdx.x == 128) HSTU_DBG(16, j + 1);
+      HSTU_T0();
       mbar_wait(&s_full[st], ph);
-      if (threadIdx.x == 128) HSTU_DBG(17, j + 1);
+      if (threadIdx.x == 128) HSTU_ACC(48);
       tc_fence_after();
       uint32_t s0[32], s1[32];
       tmem_ld32(tS[st] + lane_off + ch * 64, s0);
@@ -190,27 +197,31 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
       tc_fence_before();                           // S_j fully read: hand the buffer back to the MMA warp
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[st]);
+      if (threadIdx.x == 128) HSTU_ACC(49);
       uint32_t pk[32];
+      const f32x2 ha2 = pack2(p.half_alpha, p.half_alpha);
 #pragma unroll
       for (int i = 0; i < 64; i += 2) {
         const uint32_t a = i < 32 ? s0[i] : s1[i - 32], b = i < 32 ? s0[i + 1] : s1[i - 31];
-        float h0 = __uint_as_float(a) * p.half_alpha, h1 = __uint_as_float(b) * p.half_alpha;
-        float p0 = fmaf(h0, tanh_approx(h0), h0), p1 = fmaf(h1, tanh_approx(h1), h1);
+        const f32x2 h2 = mul2(pack2(__uint_as_float(a), __uint_as_float(b)), ha2);     // h = alpha/2 * s
+        f32x2 p2 = fma2(h2, tanh2(h2), h2);                                          // silu(alpha s) = h + h tanh(h)
         if (!full) {
           const int col = c_base + i;
-          p0 = iv.has(col) ? p0 : 0.f;
-          p1 = iv.has(col + 1) ? p1 : 0.f;
+          float p0, p1; unpack2(p2, p0, p1);
+          p2 = pack2(iv.has(col) ? p0 : 0.f, iv.has(col + 1) ? p1 : 0.f);
         }
-        pk[i >> 1] = pack_bf16x2(p0, p1);
+        pk[i >> 1] = pack_bf16x2_v(p2);
       }
+      if (threadIdx.x == 128) HSTU_ACC(50);
       mbar_wait(&p_empty, (j & 1) ^ 1);            // PV(j-1) has consumed the previous P tile
+      if (threadIdx.x == 128) HSTU_ACC(51);
 #pragma unroll
       for (int q8 = 0; q8 < 8; ++q8)
         *reinterpret_cast<uint4*>(sP + ((q8 ^ (rit & 7)) << 4)) = make_uint4(pk[4 * q8], pk[4 * q8 + 1], pk[4 * q8 + 2], pk[4 * q8 + 3]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full);
-      if (threadIdx.x == 128) HSTU_DBG(18, j + 1);
+      if (threadIdx.x == 128) HSTU_ACC(52);
     }
     // epilogue: each warpgroup stores half of the D output columns of its rows
     mbar_wait(&o_full, 0);

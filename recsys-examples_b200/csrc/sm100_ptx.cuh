@@ -145,6 +145,24 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// ---- packed math for the SiLU warps ------------------------------------------------------------------------------------------
+// Blackwell issues fp32 FMA/MUL on register PAIRS (fma.rn.f32x2): the FMUL + FFMA around each tanh cost half an issue slot each.
+typedef unsigned long long f32x2;   // two packed fp32 in one 64-bit register
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+// tanh of two packed fp32 values (tanh.approx.f16x2 was tried: ptxas splits it into two MUFU.TANH.F16 + converts on sm_100a — no
+// MUFU saving — so the fp32 MUFU is used; only the surrounding FMA/MUL are packed)
+__device__ __forceinline__ f32x2 tanh2(f32x2 x) {
+  float lo, hi; unpack2(x, lo, hi);
+  float tl, th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(tl) : "f"(lo));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hi));
+  return pack2(tl, th);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_v(f32x2 v) { float lo, hi; unpack2(v, lo, hi); return pack_bf16x2(lo, hi); }
+
 __device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 }  // namespace sm100

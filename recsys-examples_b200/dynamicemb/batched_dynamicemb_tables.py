@@ -395,6 +395,36 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
                                   combiner=int(self.pooling_mode) if pooled else -1, out_dtype=self.output_dtype, absent_value=absent,
                                   num_scores=tb.num_scores_)
 
+    # ------------------------------------------------------------------ CUDA-graph training step
+    def make_graphed_step(self, ids_static: torch.Tensor, offsets: torch.Tensor, grad_static: torch.Tensor):
+        """Capture prefetch -> forward -> loss stand-in -> fused backward as ONE CUDA graph over static buffers.
+
+        Possible because the fused prefetch never synchronises with the host (unique counts stay on the device) and every kernel
+        takes its sizes from device memory or from the static shapes.  Replay costs one launch: the ~0.3 ms of per-step Python /
+        launch overhead disappears from the host timeline.  Returns (graph, out, loss): copy new ids into `ids_static` (and new
+        upstream gradients into `grad_static`), call graph.replay(), read `out` / `loss`.
+        Restrictions: training mode, fused prefetch, optimizers whose kernel arguments do not depend on the step count
+        (SGD / Adagrad / row-wise Adagrad — Adam's bias correction is a host value), non-GLOBAL_TIMER scores."""
+        from .types import EmbOptimType
+        assert self.training and self._fused_prefetch
+        assert self._optimizer_type in (EmbOptimType.SGD, EmbOptimType.EXACT_SGD, EmbOptimType.EXACT_ADAGRAD, EmbOptimType.EXACT_ROWWISE_ADAGRAD)
+        assert self._score_policy() != ScorePolicy.GLOBAL_TIMER
+        cur = torch.cuda.current_stream(self._device)
+        side = torch.cuda.Stream(self._device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(3):                                    # warm-up on the capture stream: workspaces, lazy attributes
+                out = self(ids_static, offsets)
+                out.backward(grad_static)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self._device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self(ids_static, offsets)
+            loss = out.detach().sum()
+            out.backward(grad_static)
+        return graph, out, loss
+
     # ------------------------------------------------------------------ inspection helpers (tests, dump)
     def export_keys_values(self, table_id: int = 0):
         """All (key, embedding row, optimizer state) of one table — used by dump and by the tests."""

@@ -167,3 +167,31 @@ def test_fused_prefetch_matches_op_by_op(cuda, pooling, T):
         assert int(ma.tables._ref_counter.sum().item()) == 0 and int(mb.tables._ref_counter.sum().item()) == 0
         assert int((ma.tables._bucket_heads != -1).sum().item()) == 0
     assert ma.tables.size() > 1000
+
+
+def test_graphed_step_matches_eager(cuda):
+    """make_graphed_step (one CUDA graph per training step) leaves the same table / rows / outputs as the eager step."""
+    from dynamicemb import DynamicEmbPoolingMode, EmbOptimType
+    ma = _module(cuda, EmbOptimType.EXACT_ADAGRAD, DynamicEmbPoolingMode.NONE, D=64, n_tables=1, cap=4096, learning_rate=0.05)
+    mb = _module(cuda, EmbOptimType.EXACT_ADAGRAD, DynamicEmbPoolingMode.NONE, D=64, n_tables=1, cap=4096, learning_rate=0.05)
+    ma.train(); mb.train()
+    n = 3000
+    rng = np.random.default_rng(3)
+    ids_static = torch.zeros(n, dtype=torch.int64, device=cuda)
+    offsets = torch.arange(0, n + 1, dtype=torch.int64, device=cuda)
+    grad = torch.randn(n, 64, device=cuda)
+    batches = [torch.from_numpy((rng.zipf(1.1, size=n) % 30000).astype(np.int64) * 31).to(cuda) for _ in range(12)]
+    ids_static.copy_(batches[0])
+    graph, out, loss = ma.make_graphed_step(ids_static, offsets, grad)      # warm-up (3) + capture (not executed) on batches[0]
+    for _ in range(3):
+        o = mb(batches[0], offsets); o.backward(grad)
+    for b in batches[1:]:
+        ids_static.copy_(b)
+        graph.replay()
+        o = mb(b, offsets)
+        l = o.detach().sum()
+        o.backward(grad)
+        assert torch.equal(out, o) and torch.equal(loss, l)
+        assert torch.equal(ma.tables.table_storage_, mb.tables.table_storage_)
+        assert torch.equal(ma._values, mb._values)
+    assert int(ma.tables._ref_counter.sum().item()) == 0

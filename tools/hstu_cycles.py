@@ -1,0 +1,28 @@
+"""Cycle accounting of CTA 0 of the HSTU forward kernel (development aid)."""
+import ctypes, math, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "recsys-examples_b200"))
+from hstu import hstu_ops_gpu as ops
+from dynamicemb import _native as N
+dev = torch.device("cuda", 0)
+B, S, H, D = 8, 4096, 8, 128
+T = B * S
+q, k, v = (torch.randn(T, H, D, device=dev, dtype=torch.bfloat16) for _ in range(3))
+cu = torch.arange(0, T + 1, S, dtype=torch.int32, device=dev)
+a = 1 / math.sqrt(D)
+for _ in range(2): ops.hstu_varlen_fwd_100(q, k, v, cu, cu, S, S, None, None, 1, -1, 0, a)
+torch.cuda.synchronize()
+dbg = torch.zeros(128, dtype=torch.int32).pin_memory()
+N.lib.hstu_set_debug_buffer.argtypes = [ctypes.c_void_p]
+N.lib.hstu_set_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
+e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+e0.record(); ops.hstu_varlen_fwd_100(q, k, v, cu, cu, S, S, None, None, 1, -1, 0, a); e1.record(); torch.cuda.synchronize()
+N.lib.hstu_set_debug_buffer(None)
+d = dbg.tolist()
+n_iter = d[8]
+print(f"kernel {e0.elapsed_time(e1):.3f} ms; CTA0 iterations {n_iter}")
+names = {40: "mma: wait k_full", 41: "mma: wait s_empty", 42: "mma: wait v_full", 43: "mma: wait p_full", 48: "silu: wait s_full", 49: "silu: tmem ld + arrive",
+         50: "silu: math", 51: "silu: wait p_empty", 52: "silu: st.shared + fence + arrive"}
+for k_, nm in names.items():
+    print(f"  {nm:34s} {d[k_]:9d} cyc total  {d[k_] / max(n_iter, 1):8.0f} / iter")
