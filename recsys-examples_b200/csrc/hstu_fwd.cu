@@ -15,6 +15,8 @@
 //   The 1/N scale is applied once to O (linear), not to every P element.
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "../../include/hstu_b200.h"
 #include "hstu_mask.cuh"
 #include "sm100_ptx.cuh"
@@ -38,9 +40,11 @@ struct FwdParams {
 };
 
 // progress marks readable from the host even if the kernel never finishes (development aid)
-// cycle accounting for CTA (0,0,0) when a debug buffer is installed: HSTU_T0 / HSTU_ACC(slot) accumulate clock64() deltas
-#define HSTU_T0() long long t__0 = (p.dbg ? clock64() : 0)
-#define HSTU_ACC(slot) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { long long t__1 = clock64(); p.dbg[slot] += (int)(t__1 - t__0); t__0 = t__1; } } while (0)
+// Cycle accounting (kProf instantiation only, selected when a debug buffer is installed): clock64() deltas are accumulated in
+// REGISTERS and written to the host-mapped buffer once per role at the end (a host-memory RMW per mark would cost microseconds).
+#define HSTU_T0() long long t__0 = kProf ? clock64() : 0
+#define HSTU_ACC(i) do { if (kProf) { long long t__1 = clock64(); acc__[i] += (int)(t__1 - t__0); t__0 = t__1; } } while (0)
+#define HSTU_FLUSH(base, n) do { if (kProf && p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { for (int i__ = 0; i__ < (n); ++i__) p.dbg[(base) + i__] = acc__[i__]; __threadfence_system(); } } while (0)
 #define HSTU_DBG(slot, val) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { p.dbg[slot] = (val); __threadfence_system(); } } while (0)
 
 template <int D>
@@ -49,11 +53,11 @@ struct FwdSmem {
   static constexpr int kQ = 0;
   static constexpr int kK = kQ + kTile;             // 2 stages
   static constexpr int kV = kK + 2 * kTile;         // 2 stages
-  static constexpr int kP = kV + 2 * kTile;         // 128 x 128 bf16
-  static constexpr int kTotal = kP + 32768;
+  static constexpr int kP = kV + 2 * kTile;         // 2 x (128 x 128 bf16): SiLU(j+1) writes P while P_j V_j is still reading
+  static constexpr int kTotal = kP + 2 * 32768;
 };
 
-template <int D>
+template <int D, bool kProf>
 __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                                                           const __grid_constant__ CUtensorMap map_v, FwdParams p) {
   using SM = FwdSmem<D>;
@@ -79,14 +83,15 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], s_empty[2], p_full, p_empty, o_full;
+  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], s_empty[2], p_full[2], p_empty[2], o_full;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(&q_full, 1); mbar_init(&p_full, 8); mbar_init(&p_empty, 1); mbar_init(&o_full, 1);
+    mbar_init(&q_full, 1); mbar_init(&o_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&p_full[i], 8); mbar_init(&p_empty[i], 1);
       mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
     }
     fence_barrier_init();
@@ -103,7 +108,6 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      HSTU_DBG(0, 1);
       mbar_arrive_expect_tx(&q_full, SM::kTile);
 #pragma unroll
       for (int hf = 0; hf < NH; ++hf) tma_load_3d(smem + SM::kQ + hf * 16384, &map_q, &q_full, hf * 64, h, seq_start + r0);
@@ -111,12 +115,20 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
         const int st = j & 1, ph = (j >> 1) & 1;
         const int row = seq_start + (nb0 + j) * 128;
         mbar_wait(&k_empty[st], ph ^ 1);
-        HSTU_DBG(1, j + 1);
         mbar_arrive_expect_tx(&k_full[st], SM::kTile);
 #pragma unroll
         for (int hf = 0; hf < NH; ++hf) tma_load_3d(smem + SM::kK + st * SM::kTile + hf * 16384, &map_k, &k_full[st], hf * 64, h, row);
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ V producer: its own thread, so a V slot that is still
+    // being read by P_{j-2} V_{j-2} never delays the K tile the next QK^T is waiting for (measured: 4200 cycles/iteration of
+    // k_full stall with a single in-order producer)
+    if (lane == 0) {
+      for (int j = 0; j < n_iter; ++j) {
+        const int st = j & 1, ph = (j >> 1) & 1;
+        const int row = seq_start + (nb0 + j) * 128;
         mbar_wait(&v_empty[st], ph ^ 1);
-        HSTU_DBG(2, j + 1);
         mbar_arrive_expect_tx(&v_full[st], SM::kTile);
 #pragma unroll
         for (int hf = 0; hf < NH; ++hf) tma_load_3d(smem + SM::kV + st * SM::kTile + hf * 16384, &map_v, &v_full[st], hf * 64, h, row);
@@ -125,51 +137,51 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
+      int acc__[4] = {0, 0, 0, 0};
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, D, 0, 1);
-      const uint32_t aQ = smem_u32(smem + SM::kQ), aP = smem_u32(smem + SM::kP);
+      const uint32_t aQ = smem_u32(smem + SM::kQ), aP0 = smem_u32(smem + SM::kP);
       auto issue_qk = [&](int j) {
-        const int st = j & 1, ph = (j >> 1) & 1;
+        const int st = j & 1, ph = (j >> 1) & 1;           // S double buffer = K ring slot
+        const int ks = st, kph = ph;
         HSTU_T0();
-        mbar_wait(&k_full[st], ph);
-        HSTU_ACC(40);
+        mbar_wait(&k_full[ks], kph);
+        HSTU_ACC(0);
         mbar_wait(&s_empty[st], ph ^ 1);
-        HSTU_ACC(41);
+        HSTU_ACC(1);
         tc_fence_after();
-        const uint32_t aK = smem_u32(smem + SM::kK + st * SM::kTile);
+        const uint32_t aK = smem_u32(smem + SM::kK + ks * SM::kTile);
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
           const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
           umma_ss(tS[st], umma_desc_sw128(aQ + off, 16, 1024), umma_desc_sw128(aK + off, 16, 1024), idesc_qk, k > 0);
         }
         umma_commit(&s_full[st]);
-        umma_commit(&k_empty[st]);
+        umma_commit(&k_empty[ks]);
       };
       HSTU_DBG(8, n_iter);
       mbar_wait(&q_full, 0);
-      HSTU_DBG(9, 1);
       issue_qk(0);
-      HSTU_DBG(10, 1);
       for (int j = 0; j < n_iter; ++j) {
         if (j + 1 < n_iter) issue_qk(j + 1);
         const int st = j & 1, ph = (j >> 1) & 1;
         HSTU_T0();
         mbar_wait(&v_full[st], ph);
-        HSTU_ACC(42);
-        mbar_wait(&p_full, j & 1);
-        HSTU_ACC(43);
+        HSTU_ACC(2);
+        mbar_wait(&p_full[st], ph);
+        HSTU_ACC(3);
         tc_fence_after();
-        const uint32_t aV = smem_u32(smem + SM::kV + st * SM::kTile);
+        const uint32_t aV = smem_u32(smem + SM::kV + st * SM::kTile), aP = aP0 + st * 32768;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t offp = (k >> 2) * 16384 + (k & 3) * 32;
           umma_ss(tO, umma_desc_sw128(aP + offp, 16, 1024), umma_desc_sw128(aV + k * 2048, 16384, 1024), idesc_pv, (j > 0 || k > 0));
         }
         umma_commit(&v_empty[st]);
-        umma_commit(&p_empty);
+        umma_commit(&p_empty[st]);
       }
       umma_commit(&o_full);
-      HSTU_DBG(13, 1);
+      HSTU_FLUSH(40, 4);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ SiLU warpgroup + epilogue
@@ -180,52 +192,73 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
     const int rit = wq * 32 + lane;                // row in tile
     const int row = r0 + rit;
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
-    uint8_t* sP = smem + SM::kP + ch * 16384 + rit * 128;
+    const uint32_t sP0 = smem_u32(smem + SM::kP + ch * 16384 + rit * 128);
     const Intervals iv = cols_of_row(mk, row);
+    const f32x2 ha2 = pack2(p.half_alpha, p.half_alpha);
+    int acc__[5] = {0, 0, 0, 0, 0};
     for (int j = 0; j < n_iter; ++j) {
       const int st = j & 1, ph = (j >> 1) & 1;
       const int c_base = (nb0 + j) * 128 + ch * 64;
       const bool full = mk.tile_full(r0, r1, c_base, c_base + 63);
+      const uint32_t sP = sP0 + st * 32768;
       HSTU_T0();
       mbar_wait(&s_full[st], ph);
-      if (threadIdx.x == 128) HSTU_ACC(48);
+      HSTU_ACC(0);
+      mbar_wait(&p_empty[st], ph ^ 1);             // P_{j-2} V_{j-2} has finished reading this P buffer
+      HSTU_ACC(3);
       tc_fence_after();
-      uint32_t s0[32], s1[32];
-      tmem_ld32(tS[st] + lane_off + ch * 64, s0);
-      tmem_ld32(tS[st] + lane_off + ch * 64 + 32, s1);
-      tmem_ld_wait();
-      tc_fence_before();                           // S_j fully read: hand the buffer back to the MMA warp
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[st]);
-      if (threadIdx.x == 128) HSTU_ACC(49);
-      uint32_t pk[32];
-      const f32x2 ha2 = pack2(p.half_alpha, p.half_alpha);
+      // 16 score columns at a time (tcgen05.ld x16, the next chunk in flight while this one is in the SFU): 16 MUFU.TANH are issued
+      // back to back before the first dependent FFMA2, and no 64-register score / 32-register P arrays stay live (the x32 + pk[32]
+      // version ran at 2200 cycles per tile against the 1024-cycle MUFU floor: ptxas paired every two MUFU with their FFMA2)
+      // The mask test is hoisted out of the tile: a per-pair `if (!full)` split the unrolled loop into 32 basic blocks and ptxas could not
+      // schedule the MUFU latency across them.
+      const uint32_t t_s = tS[st] + lane_off + ch * 64;
+      auto tile = [&](auto masked_tag) {
+        constexpr bool kMasked = decltype(masked_tag)::value;
+        uint32_t sa[16], sb[16];
+        tmem_ld16(t_s, sa);
 #pragma unroll
-      for (int i = 0; i < 64; i += 2) {
-        const uint32_t a = i < 32 ? s0[i] : s1[i - 32], b = i < 32 ? s0[i + 1] : s1[i - 31];
-        const f32x2 h2 = mul2(pack2(__uint_as_float(a), __uint_as_float(b)), ha2);     // h = alpha/2 * s
-        f32x2 p2 = fma2(h2, tanh2(h2), h2);                                          // silu(alpha s) = h + h tanh(h)
-        if (!full) {
-          const int col = c_base + i;
-          float p0, p1; unpack2(p2, p0, p1);
-          p2 = pack2(iv.has(col) ? p0 : 0.f, iv.has(col + 1) ? p1 : 0.f);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&cur)[16] = (c & 1) ? sb : sa;
+          uint32_t (&nxt)[16] = (c & 1) ? sa : sb;
+          tmem_ld_wait();
+          if (c < 3) tmem_ld16(t_s + 16 * (c + 1), nxt);
+          else {
+            tc_fence_before();                       // S_j fully read: hand the buffer back to the MMA warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[st]);
+          }
+          f32x2 h2[8], t2[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) h2[i] = mul2(pack2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])), ha2);   // h = alpha/2 s
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t2[i] = tanh2(h2[i]);
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            f32x2 p2 = fma2(h2[i], t2[i], h2[i]);                                      // silu(alpha s) = h + h tanh(h)
+            if (kMasked) {
+              const int col = c_base + c * 16 + 2 * i;
+              float p0, p1; unpack2(p2, p0, p1);
+              p2 = pack2(iv.has(col) ? p0 : 0.f, iv.has(col + 1) ? p1 : 0.f);
+            }
+            pk[i] = pack_bf16x2_v(p2);
+          }
+          // row `rit` of the K-major SWIZZLE_128B P tile: 16-byte chunk q of the row lives at chunk (q ^ (rit & 7))
+          sts128(sP + (((2 * c) ^ (rit & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+          sts128(sP + (((2 * c + 1) ^ (rit & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
         }
-        pk[i >> 1] = pack_bf16x2_v(p2);
-      }
-      if (threadIdx.x == 128) HSTU_ACC(50);
-      mbar_wait(&p_empty, (j & 1) ^ 1);            // PV(j-1) has consumed the previous P tile
-      if (threadIdx.x == 128) HSTU_ACC(51);
-#pragma unroll
-      for (int q8 = 0; q8 < 8; ++q8)
-        *reinterpret_cast<uint4*>(sP + ((q8 ^ (rit & 7)) << 4)) = make_uint4(pk[4 * q8], pk[4 * q8 + 1], pk[4 * q8 + 2], pk[4 * q8 + 3]);
+      };
+      if (full) tile(std::false_type{}); else tile(std::true_type{});
+      HSTU_ACC(2);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full);
-      if (threadIdx.x == 128) HSTU_ACC(52);
+      if (lane == 0) mbar_arrive(&p_full[st]);
+      HSTU_ACC(4);
     }
+    if (threadIdx.x == 128) HSTU_FLUSH(48, 5);
     // epilogue: each warpgroup stores half of the D output columns of its rows
     mbar_wait(&o_full, 0);
-    if (threadIdx.x == 128) HSTU_DBG(19, 1);
     tc_fence_after();
     __nv_bfloat16* orow = p.out + ((int64_t)(seq_start + row) * p.H + h) * D;
 #pragma unroll
@@ -257,12 +290,14 @@ int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mkk, const CUtensorMap&
   constexpr int smem = FwdSmem<D>::kTotal + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(hstu_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(hstu_fwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(hstu_fwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return -(int)e;
     configured = true;
   }
   dim3 grid((max_seqlen + 127) / 128, p.H, B);
-  hstu_fwd_kernel<D><<<grid, 384, smem, stream>>>(mq, mkk, mv, p);
+  if (p.dbg) hstu_fwd_kernel<D, true><<<grid, 384, smem, stream>>>(mq, mkk, mv, p);
+  else hstu_fwd_kernel<D, false><<<grid, 384, smem, stream>>>(mq, mkk, mv, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

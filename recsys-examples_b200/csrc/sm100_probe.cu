@@ -6,6 +6,8 @@
 //   variant 1: C = A  * Bt    A[m][k] K-major,  Bt[k][n] MN-major B    (P V)
 //   variant 2: C = At^T * B^T At[k][m] MN-major A, B[n][k] K-major     (dS^T as A of dQ)
 //   variant 3: C = At^T * Bt  both MN-major                            (dQ = dS K)
+//   variant 4: C = A  * B^T   A from TENSOR MEMORY (.ts MMA, bf16x2 packed by tcgen05.st), B K-major
+//   variant 5: C = A  * Bt    A from tensor memory, Bt[k][n] MN-major  (P V with P kept in TMEM)
 #include "../../include/hstu_b200.h"
 #include "sm100_ptx.cuh"
 #include "tma_host.cuh"
@@ -18,6 +20,8 @@ struct ProbeParams {
   uint32_t a_lbo, a_sbo, a_kstep, a_khalf;   // descriptor bytes; kstep = start advance per UMMA_K; khalf = advance after 4 k-steps (K-major)
   uint32_t b_lbo, b_sbo, b_kstep, b_khalf;
   int a_mn, b_mn;
+  int a_tmem;                                // variants 4/5: A operand staged in tensor memory
+  const uint32_t* a_global;                  // A as packed bf16 pairs [128][64]
 };
 
 __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -30,11 +34,24 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
   __shared__ uint32_t tmem_base;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) { mbar_init(&bar_load, 1); mbar_init(&bar_mma, 1); fence_barrier_init(); }
-  if (warp == 0) tmem_alloc<128>(&tmem_base);
+  if (warp == 0) tmem_alloc<256>(&tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base;
+  if (p.a_tmem) {                            // thread = row m: 64 packed columns at TMEM columns 128..191
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    for (int c = 0; c < 64; c += 8) {
+      uint32_t r[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = p.a_global[threadIdx.x * 64 + c + i];
+      tmem_st8(tmem + lane_off + 128 + c, r);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(&bar_load, 65536);
     tma_load_3d(sA, &map_a, &bar_load, 0, 0, 0);
@@ -49,7 +66,8 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
       uint32_t b_off = (k & 3) * p.b_kstep + (k >> 2) * p.b_khalf;
       uint64_t da = umma_desc_sw128(smem_u32(sA) + a_off, p.a_lbo, p.a_sbo);
       uint64_t db = umma_desc_sw128(smem_u32(sB) + b_off, p.b_lbo, p.b_sbo);
-      umma_ss(tmem, da, db, idesc, k > 0);
+      if (p.a_tmem) umma_ts(tmem, tmem + 128 + k * 8, db, idesc, k > 0);   // 16 k values = 8 packed columns per step
+      else umma_ss(tmem, da, db, idesc, k > 0);
     }
     umma_commit(&bar_mma);
   }
@@ -66,7 +84,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<128>(tmem);
+  if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
 }  // namespace
@@ -83,7 +101,9 @@ extern "C" int sm100_probe_gemm(const void* A, const void* B, float* C, int vari
   // MN-major: LBO = next 64-element MN chunk (+16384), SBO = next 8-row k group (+1024); +2048 B per k-step (16 k rows)
   const uint32_t kmaj[4] = {16, 1024, 32, 16384}, mnmaj[4] = {16384, 1024, 2048, 8192};
   p.a_mn = (variant == 2 || variant == 3);
-  p.b_mn = (variant == 1 || variant == 3);
+  p.b_mn = (variant == 1 || variant == 3 || variant == 5);
+  p.a_tmem = (variant == 4 || variant == 5);
+  p.a_global = static_cast<const uint32_t*>(A);
   const uint32_t* a = p.a_mn ? mnmaj : kmaj;
   const uint32_t* b = p.b_mn ? mnmaj : kmaj;
   p.a_lbo = a[0]; p.a_sbo = a[1]; p.a_kstep = a[2]; p.a_khalf = a[3];

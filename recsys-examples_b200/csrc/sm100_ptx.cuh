@@ -65,6 +65,11 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// 16-byte store to a shared-window address (a generic-pointer store compiles to ST.E with 64-bit address arithmetic per store)
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // ---------------------------------------------------------------- TMEM
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {   // one full warp
@@ -89,6 +94,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// tcgen05.st 32 lanes x 32-bit, 8 consecutive columns <- 8 registers per thread (thread = lane = row).  Used to hand the bf16x2-packed
+// P tile to the tensor core as the TMEM A operand of a .ts MMA (column c of the A region holds k = 2c (low half) and 2c+1 (high half)).
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- UMMA descriptors
@@ -146,14 +167,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 // ---- packed math for the SiLU warps ------------------------------------------------------------------------------------------
-// Blackwell issues fp32 FMA/MUL on register PAIRS (fma.rn.f32x2): the FMUL + FFMA around each tanh cost half an issue slot each.
+// Blackwell issues fp32 FMA/MUL on register PAIRS (fma.rn.f32x2): packed forms cost half an issue slot per score.
 typedef unsigned long long f32x2;   // two packed fp32 in one 64-bit register
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-// tanh of two packed fp32 values (tanh.approx.f16x2 was tried: ptxas splits it into two MUFU.TANH.F16 + converts on sm_100a — no
-// MUFU saving — so the fp32 MUFU is used; only the surrounding FMA/MUL are packed)
+// tanh of two packed fp32 values.  Measured on B200 (tools/ubench/mufu_bench.cu): MUFU.TANH and MUFU.EX2 both issue one warp
+// instruction per 8 cycles per SM sub-partition (16 lanes/clk/SM); tanh.approx.bf16x2 splits into two MUFU (16 cycles) - no saving;
+// FFMA2 = 2 cycles (same flops as FFMA, half the issue slots); F2FP.BF16.PACK_AB = 5 cycles per warp instruction.
 __device__ __forceinline__ f32x2 tanh2(f32x2 x) {
   float lo, hi; unpack2(x, lo, hi);
   float tl, th;

@@ -409,20 +409,35 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         assert self.training and self._fused_prefetch
         assert self._optimizer_type in (EmbOptimType.SGD, EmbOptimType.EXACT_SGD, EmbOptimType.EXACT_ADAGRAD, EmbOptimType.EXACT_ROWWISE_ADAGRAD)
         assert self._score_policy() != ScorePolicy.GLOBAL_TIMER
+        indices, offsets_i, B = self._split(ids_static, offsets)
+        assert indices.data_ptr() == ids_static.data_ptr(), "ids_static must already be contiguous int64"
+
+        def step():
+            # the same kernels as forward() + backward(), called directly: autograd would make the capture stream wait on
+            # events of the streams that produced `grad_static` (cudaErrorStreamCaptureIsolation)
+            self.prefetch(indices, offsets_i)
+            st = self._prefetch_states.popleft()
+            out_ = _LookupFunction.forward(_NoCtx(), self, st, offsets_i, B, None)
+            loss_ = out_.sum()
+            self._optimizer.step()
+            pooled = self.pooling_mode != DynamicEmbPoolingMode.NONE
+            ext.backward(self._values, self.max_D, st.reverse_indices, max(st.num_unique_bound, 1), st.rows, grad_static,
+                         offsets=offsets_i if pooled else None, batch_size=B if pooled else 0, num_features=self.feature_num if pooled else 0,
+                         combiner=int(self.pooling_mode) if pooled else -1, **self._optimizer.kernel_kwargs())
+            self._unpin(st)
+            return out_, loss_
+
         cur = torch.cuda.current_stream(self._device)
         side = torch.cuda.Stream(self._device)
         side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            for _ in range(3):                                    # warm-up on the capture stream: workspaces, lazy attributes
-                out = self(ids_static, offsets)
-                out.backward(grad_static)
+        with torch.no_grad(), torch.cuda.stream(side):
+            for _ in range(3):                                    # warm-up on a side stream: workspaces, lazy attributes
+                step()
         cur.wait_stream(side)
         torch.cuda.synchronize(self._device)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            out = self(ids_static, offsets)
-            loss = out.detach().sum()
-            out.backward(grad_static)
+        with torch.no_grad(), torch.cuda.graph(graph):
+            out, loss = step()
         return graph, out, loss
 
     # ------------------------------------------------------------------ inspection helpers (tests, dump)

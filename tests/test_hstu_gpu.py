@@ -19,15 +19,15 @@ def test_sm100_descriptor_probe(cuda):
     A = torch.randn(128, 128, device=cuda).to(torch.bfloat16)
     Bm = torch.randn(128, 128, device=cuda).to(torch.bfloat16)
     Af, Bf = A.float(), Bm.float()
-    want = {0: Af @ Bf.t(), 1: Af @ Bf, 2: Af.t() @ Bf.t(), 3: Af.t() @ Bf}
+    want = {0: Af @ Bf.t(), 1: Af @ Bf, 2: Af.t() @ Bf.t(), 3: Af.t() @ Bf, 4: Af @ Bf.t(), 5: Af @ Bf}   # 4/5: A operand in tensor memory (.ts)
     msgs = []
-    for v in range(4):
+    for v in range(6):
         C = ops.probe_gemm(A, Bm, v)
         torch.cuda.synchronize()
         err = (C - want[v]).abs().max().item()
         msgs.append(f"variant {v}: max err {err:.4g}")
     print("\n".join(msgs))
-    for v in range(4):
+    for v in range(6):
         C = ops.probe_gemm(A, Bm, v)
         assert torch.allclose(C, want[v], rtol=1e-3, atol=1e-2), msgs[v]
 
