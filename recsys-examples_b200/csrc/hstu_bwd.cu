@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
   const uint32_t tA0 = tmem + 256, tA1 = tmem + 384;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(&x_full, 2 * SM::kX);
 #pragma unroll
       for (int hf = 0; hf < NH; ++hf) {
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);       // [128 x 64] = X (K-major) * Y^T (K-major)
       constexpr uint32_t idesc_acc = umma_idesc_bf16(128, D, 0, 1);      // [128 x D] += PD (K-major, K = 64) * Y (MN-major)
       const uint32_t aX1 = smem_u32(smem + SM::oX1), aX2 = smem_u32(smem + SM::oX2);

@@ -5,13 +5,20 @@
 // target groups, contexts).  Hand-written tcgen05 / TMA / TMEM:
 //
 //   CTA = one 128-row Q tile of one (b, h); 12 warps:
-//     warp 0    TMA producer  : Q once, then K_j / V_j tiles (128 x D bf16, SWIZZLE_128B boxes of 64 columns) into 2-stage rings
-//     warp 1    MMA issuer    : S_j = Q K_j^T  (SS, K-major x K-major, fp32 in TMEM, double-buffered S0/S1 so QK^T(j+1) overlaps
-//                               the SiLU of tile j);  O += P_j V_j  (SS, P K-major from smem, V MN-major straight from its TMA tile)
-//     warp 2    TMEM alloc/dealloc (512 columns: S0 @0, S1 @128, O @256)
-//     warps 4-11 two SiLU warpgroups (64 score columns each): thread = accumulator row; tcgen05.ld 32 columns at a time -> h + h*tanh.approx(h), h = alpha/2*s
-//                               (1 FMUL + 1 MUFU + 1 FFMA per score), mask only on boundary tiles, bf16 pack, st.shared into the
-//                               swizzled K-major P tile; finally O: TMEM -> regs -> *1/N -> bf16 -> 16-byte global stores.
+//     warp 0    K producer    : K_j tiles (128 x D bf16, SWIZZLE_128B boxes of 64 columns) into a 3-stage ring
+//     warp 3    V producer    : V_j tiles, own ring, own thread (a busy V slot must never delay the K tile the next QK^T needs)
+//     warp 1    MMA issuer    : S_j = Q K_j^T and O += P_j V_j, BOTH with the A operand in tensor memory (.ts):
+//                               Q is packed into TMEM once per CTA, P_j is written back over S_j by the SiLU warps.  Measured on
+//                               B200 (tools/ubench/umma_bench.cu): 128x128x16 .ss = 107 cycles (shared-memory operand bandwidth,
+//                               ~75 B/clk), .ts = 74 cycles.  S is double-buffered so QK^T(j+1) overlaps the SiLU of tile j.
+//                               The issuing thread is chosen with elect.sync: under `if (lane == 0)` ptxas wraps every UTCHMMA /
+//                               UTMALDG in an ELECT + BRA.U.ANY loop (94 cycles per MMA issue).
+//     warp 2    TMEM alloc/dealloc (512 columns: S0 @0, S1 @128, O @256, Q @384)
+//     warps 4-11 two SiLU warpgroups (64 score columns each): thread = accumulator row; tcgen05.ld 16 columns at a time ->
+//                               h + h*tanh.approx(h), h = alpha/2*s (packed FMUL2 / FFMA2 around one MUFU.TANH per score: the SFU
+//                               is the floor, 1024 cycles per 128x128 tile) -> bf16x2 -> tcgen05.st into the first half of the
+//                               warpgroup's own S columns (already read); finally O: TMEM -> regs -> *1/N -> bf16 -> global.
+//   No shared-memory traffic for Q or P at all: shared memory only holds the K / V rings.
 //   The 1/N scale is applied once to O (linear), not to every P element.
 #include <cuda_bf16.h>
 
@@ -30,38 +37,44 @@ struct FwdParams {
   const int32_t* cu_seqlens;
   const int32_t* num_targets;    // nullable
   const int32_t* num_contexts;   // nullable
+  const __nv_bfloat16* q;        // [T, H, D] with element strides q_t / q_h (rows are read straight into tensor memory)
+  int64_t q_t, q_h;
   __nv_bfloat16* out;            // [T, H, D] contiguous
   int H;
   float half_alpha;              // alpha / 2
   float inv_scale;               // 1 / scaling_seqlen
   int target_group;
   int win_left, win_right;       // -1 = unbounded
-  volatile int* dbg;             // optional host-mapped progress buffer (hstu_set_debug_buffer), nullptr in production
+  volatile int* dbg;             // optional host-mapped buffer (hstu_set_debug_buffer), nullptr in production
 };
 
-// progress marks readable from the host even if the kernel never finishes (development aid)
 // Cycle accounting (kProf instantiation only, selected when a debug buffer is installed): clock64() deltas are accumulated in
-// REGISTERS and written to the host-mapped buffer once per role at the end (a host-memory RMW per mark would cost microseconds).
+// REGISTERS and written to the host-mapped buffer once per role at the end (a host-memory store + fence per mark costs microseconds
+// and distorts exactly the pipeline it is meant to observe).
 #define HSTU_T0() long long t__0 = kProf ? clock64() : 0
 #define HSTU_ACC(i) do { if (kProf) { long long t__1 = clock64(); acc__[i] += (int)(t__1 - t__0); t__0 = t__1; } } while (0)
 #define HSTU_FLUSH(base, n) do { if (kProf && p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { for (int i__ = 0; i__ < (n); ++i__) p.dbg[(base) + i__] = acc__[i__]; __threadfence_system(); } } while (0)
-#define HSTU_DBG(slot, val) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { p.dbg[slot] = (val); __threadfence_system(); } } while (0)
 
 template <int D>
 struct FwdSmem {
   static constexpr int kTile = 128 * D * 2;         // bytes of one 128 x D bf16 tile
-  static constexpr int kQ = 0;
-  static constexpr int kK = kQ + kTile;             // 2 stages
-  static constexpr int kV = kK + 2 * kTile;         // 2 stages
-  static constexpr int kP = kV + 2 * kTile;         // 2 x (128 x 128 bf16): SiLU(j+1) writes P while P_j V_j is still reading
-  static constexpr int kTotal = kP + 2 * 32768;
+  static constexpr int kStages = 3;
+  static constexpr int kK = 0;
+  static constexpr int kV = kK + kStages * kTile;
+  static constexpr int kTotal = kV + kStages * kTile;
 };
 
+__device__ __forceinline__ uint4 ldg_nc_u4(const void* ptr) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  return v;
+}
+
 template <int D, bool kProf>
-__global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                                                          const __grid_constant__ CUtensorMap map_v, FwdParams p) {
+__global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, FwdParams p) {
   using SM = FwdSmem<D>;
   constexpr int NH = D / 64;                         // 64-column (128-byte) halves per tile row
+  constexpr int S = SM::kStages;
   const int b = blockIdx.z, h = blockIdx.y;
   const int m_tile = gridDim.x - 1 - blockIdx.x;     // heaviest (longest causal row) tiles first
   const int seq_start = p.cu_seqlens[b];
@@ -83,19 +96,16 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], s_empty[2], p_full[2], p_empty[2], o_full;
+  __shared__ uint64_t q_full, k_full[S], k_empty[S], v_full[S], v_empty[S], s_full[2], p_full[2], o_full;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(&q_full, 1); mbar_init(&o_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-      mbar_init(&p_full[i], 8); mbar_init(&p_empty[i], 1);
-      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
-    }
+    mbar_init(&q_full, 8); mbar_init(&o_full, 1);
+    for (int i = 0; i < S; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); }
     fence_barrier_init();
-    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+    tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
   }
   if (warp == 2) tmem_alloc<512>(&tmem_base_s);
   tc_fence_before();
@@ -104,87 +114,71 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
   const uint32_t tmem = tmem_base_s;
   const uint32_t tS[2] = {tmem, tmem + 128};
   const uint32_t tO = tmem + 256;
+  const uint32_t tQ = tmem + 384;                    // Q tile, bf16x2 packed: D / 2 columns
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&q_full, SM::kTile);
-#pragma unroll
-      for (int hf = 0; hf < NH; ++hf) tma_load_3d(smem + SM::kQ + hf * 16384, &map_q, &q_full, hf * 64, h, seq_start + r0);
+  if (warp == 0 || warp == 3) {
+    // ------------------------------------------------------------------ K (warp 0) / V (warp 3) producers
+    if (elect_one()) {
+      const CUtensorMap* map = warp == 0 ? &map_k : &map_v;
+      uint8_t* ring = smem + (warp == 0 ? SM::kK : SM::kV);
+      uint64_t* full = warp == 0 ? k_full : v_full;
+      uint64_t* empty = warp == 0 ? k_empty : v_empty;
       for (int j = 0; j < n_iter; ++j) {
-        const int st = j & 1, ph = (j >> 1) & 1;
+        const int st = j % S, ph = (j / S) & 1;
         const int row = seq_start + (nb0 + j) * 128;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], SM::kTile);
+        mbar_wait(&empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&full[st], SM::kTile);
 #pragma unroll
-        for (int hf = 0; hf < NH; ++hf) tma_load_3d(smem + SM::kK + st * SM::kTile + hf * 16384, &map_k, &k_full[st], hf * 64, h, row);
-      }
-    }
-  } else if (warp == 3) {
-    // ------------------------------------------------------------------ V producer: its own thread, so a V slot that is still
-    // being read by P_{j-2} V_{j-2} never delays the K tile the next QK^T is waiting for (measured: 4200 cycles/iteration of
-    // k_full stall with a single in-order producer)
-    if (lane == 0) {
-      for (int j = 0; j < n_iter; ++j) {
-        const int st = j & 1, ph = (j >> 1) & 1;
-        const int row = seq_start + (nb0 + j) * 128;
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], SM::kTile);
-#pragma unroll
-        for (int hf = 0; hf < NH; ++hf) tma_load_3d(smem + SM::kV + st * SM::kTile + hf * 16384, &map_v, &v_full[st], hf * 64, h, row);
+        for (int hf = 0; hf < NH; ++hf) tma_load_3d(ring + st * SM::kTile + hf * 16384, map, &full[st], hf * 64, h, row);
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (one elected thread)
+    if (elect_one()) {
       int acc__[4] = {0, 0, 0, 0};
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, D, 0, 1);
-      const uint32_t aQ = smem_u32(smem + SM::kQ), aP0 = smem_u32(smem + SM::kP);
       auto issue_qk = [&](int j) {
-        const int st = j & 1, ph = (j >> 1) & 1;           // S double buffer = K ring slot
-        const int ks = st, kph = ph;
+        const int st = j & 1;                              // S double buffer
+        const int ks = j % S, kph = (j / S) & 1;           // K ring
         HSTU_T0();
         mbar_wait(&k_full[ks], kph);
         HSTU_ACC(0);
-        mbar_wait(&s_empty[st], ph ^ 1);
-        HSTU_ACC(1);
         tc_fence_after();
         const uint32_t aK = smem_u32(smem + SM::kK + ks * SM::kTile);
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_ss(tS[st], umma_desc_sw128(aQ + off, 16, 1024), umma_desc_sw128(aK + off, 16, 1024), idesc_qk, k > 0);
-        }
+        for (int k = 0; k < D / 16; ++k)                   // A = Q from tensor memory: 16 k values = 8 packed columns per step
+          umma_ts(tS[st], tQ + k * 8, umma_desc_sw128(aK + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), idesc_qk, k > 0);
         umma_commit(&s_full[st]);
         umma_commit(&k_empty[ks]);
       };
-      HSTU_DBG(8, n_iter);
+      if (kProf && p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[8] = n_iter;
       mbar_wait(&q_full, 0);
+      tc_fence_after();
       issue_qk(0);
       for (int j = 0; j < n_iter; ++j) {
+        // S_{j+1} goes to the other S buffer; its previous tenant P_{j-1} was consumed by P_{j-1} V_{j-1}, issued before this MMA
+        // (the tensor pipe executes one thread's MMAs in issue order), so no "S empty" barrier is needed
         if (j + 1 < n_iter) issue_qk(j + 1);
         const int st = j & 1, ph = (j >> 1) & 1;
+        const int vs = j % S, vph = (j / S) & 1;
         HSTU_T0();
-        mbar_wait(&v_full[st], ph);
+        mbar_wait(&v_full[vs], vph);
         HSTU_ACC(2);
         mbar_wait(&p_full[st], ph);
         HSTU_ACC(3);
         tc_fence_after();
-        const uint32_t aV = smem_u32(smem + SM::kV + st * SM::kTile), aP = aP0 + st * 32768;
+        const uint32_t aV = smem_u32(smem + SM::kV + vs * SM::kTile);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t offp = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_ss(tO, umma_desc_sw128(aP + offp, 16, 1024), umma_desc_sw128(aV + k * 2048, 16384, 1024), idesc_pv, (j > 0 || k > 0));
-        }
-        umma_commit(&v_empty[st]);
-        umma_commit(&p_empty[st]);
+        for (int k = 0; k < 8; ++k)                        // A = P_j: keys 0-63 packed in S columns 0-31, keys 64-127 in columns 64-95
+          umma_ts(tO, tS[st] + (k >> 2) * 64 + (k & 3) * 8, umma_desc_sw128(aV + k * 2048, 16384, 1024), idesc_pv, (j > 0 || k > 0));
+        umma_commit(&v_empty[vs]);
       }
       umma_commit(&o_full);
       HSTU_FLUSH(40, 4);
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ SiLU warpgroup + epilogue
+    // ------------------------------------------------------------------ SiLU warpgroups + epilogue
     // two SiLU warpgroups split the 128 score columns of every tile (warps 4-7: columns 0-63, warps 8-11: columns 64-127) so
     // two warps per SM sub-partition hide each other's TMEM-load / MUFU latency
     const int wq = warp & 3;                       // TMEM lane quadrant
@@ -192,7 +186,21 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
     const int rit = wq * 32 + lane;                // row in tile
     const int row = r0 + rit;
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
-    const uint32_t sP0 = smem_u32(smem + SM::kP + ch * 16384 + rit * 128);
+    {
+      // Q row -> tensor memory (each warpgroup packs half of the D columns): straight from global, 16-byte loads
+      const __nv_bfloat16* qrow = p.q + (int64_t)(seq_start + row) * p.q_t + (int64_t)h * p.q_h + ch * (D / 2);
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint4 a = make_uint4(0, 0, 0, 0), bq = a;
+        if (row < L) { a = ldg_nc_u4(qrow + c * 16); bq = ldg_nc_u4(qrow + c * 16 + 8); }
+        const uint32_t r[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+        tmem_st8(tQ + lane_off + ch * (D / 4) + c * 8, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_full);
+    }
     const Intervals iv = cols_of_row(mk, row);
     const f32x2 ha2 = pack2(p.half_alpha, p.half_alpha);
     int acc__[5] = {0, 0, 0, 0, 0};
@@ -200,19 +208,14 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
       const int st = j & 1, ph = (j >> 1) & 1;
       const int c_base = (nb0 + j) * 128 + ch * 64;
       const bool full = mk.tile_full(r0, r1, c_base, c_base + 63);
-      const uint32_t sP = sP0 + st * 32768;
+      const uint32_t t_s = tS[st] + lane_off + ch * 64;
       HSTU_T0();
       mbar_wait(&s_full[st], ph);
       HSTU_ACC(0);
-      mbar_wait(&p_empty[st], ph ^ 1);             // P_{j-2} V_{j-2} has finished reading this P buffer
-      HSTU_ACC(3);
       tc_fence_after();
-      // 16 score columns at a time (tcgen05.ld x16, the next chunk in flight while this one is in the SFU): 16 MUFU.TANH are issued
-      // back to back before the first dependent FFMA2, and no 64-register score / 32-register P arrays stay live (the x32 + pk[32]
-      // version ran at 2200 cycles per tile against the 1024-cycle MUFU floor: ptxas paired every two MUFU with their FFMA2)
-      // The mask test is hoisted out of the tile: a per-pair `if (!full)` split the unrolled loop into 32 basic blocks and ptxas could not
-      // schedule the MUFU latency across them.
-      const uint32_t t_s = tS[st] + lane_off + ch * 64;
+      // 16 score columns at a time (tcgen05.ld x16, the next chunk in flight while this one is in the SFU); packed chunk c (8 columns)
+      // overwrites S columns 8c..8c+7 of this warpgroup's half, which chunks <= c have already read.  The mask test is hoisted out of the
+      // tile: a per-pair `if (!full)` split the unrolled loop into 32 basic blocks and ptxas could not cover the MUFU latency.
       auto tile = [&](auto masked_tag) {
         constexpr bool kMasked = decltype(masked_tag)::value;
         uint32_t sa[16], sb[16];
@@ -223,11 +226,6 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
           uint32_t (&nxt)[16] = (c & 1) ? sa : sb;
           tmem_ld_wait();
           if (c < 3) tmem_ld16(t_s + 16 * (c + 1), nxt);
-          else {
-            tc_fence_before();                       // S_j fully read: hand the buffer back to the MMA warp
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[st]);
-          }
           f32x2 h2[8], t2[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) h2[i] = mul2(pack2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])), ha2);   // h = alpha/2 s
@@ -244,14 +242,13 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
             }
             pk[i] = pack_bf16x2_v(p2);
           }
-          // row `rit` of the K-major SWIZZLE_128B P tile: 16-byte chunk q of the row lives at chunk (q ^ (rit & 7))
-          sts128(sP + (((2 * c) ^ (rit & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
-          sts128(sP + (((2 * c + 1) ^ (rit & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
+          tmem_st8(t_s + c * 8, pk);
         }
       };
       if (full) tile(std::false_type{}); else tile(std::true_type{});
       HSTU_ACC(2);
-      fence_proxy_async_smem();
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[st]);
       HSTU_ACC(4);
@@ -286,7 +283,7 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
 }
 
 template <int D>
-int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mkk, const CUtensorMap& mv, const FwdParams& p, int B, int max_seqlen, cudaStream_t stream) {
+int launch_fwd(const CUtensorMap& mkk, const CUtensorMap& mv, const FwdParams& p, int B, int max_seqlen, cudaStream_t stream) {
   constexpr int smem = FwdSmem<D>::kTotal + 1024;
   static bool configured = false;
   if (!configured) {
@@ -296,8 +293,8 @@ int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mkk, const CUtensorMap&
     configured = true;
   }
   dim3 grid((max_seqlen + 127) / 128, p.H, B);
-  if (p.dbg) hstu_fwd_kernel<D, true><<<grid, 384, smem, stream>>>(mq, mkk, mv, p);
-  else hstu_fwd_kernel<D, false><<<grid, 384, smem, stream>>>(mq, mkk, mv, p);
+  if (p.dbg) hstu_fwd_kernel<D, true><<<grid, 384, smem, stream>>>(mkk, mv, p);
+  else hstu_fwd_kernel<D, false><<<grid, 384, smem, stream>>>(mkk, mv, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }
@@ -317,17 +314,17 @@ extern "C" int hstu_fwd_sm100(const void* q, const void* k, const void* v, void*
   if (target_group_size < 1 || scaling_seqlen <= 0) return HSTU_ERR_ARG;
   for (int i = 0; i < 6; ++i) if (strides[i] % 8) return HSTU_ERR_ARG;                       // TMA: 16-byte aligned strides
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out)) & 15) return HSTU_ERR_ARG;
-  CUtensorMap mq, mk, mv;
+  CUtensorMap mk, mv;
   int rc;
-  if ((rc = tma::make_map_3d(&mq, q, head_dim, heads, total_tokens, strides[1] * 2, strides[0] * 2, 64, 1, 128))) return rc;
   if ((rc = tma::make_map_3d(&mk, k, head_dim, heads, total_tokens, strides[3] * 2, strides[2] * 2, 64, 1, 128))) return rc;
   if ((rc = tma::make_map_3d(&mv, v, head_dim, heads, total_tokens, strides[5] * 2, strides[4] * 2, 64, 1, 128))) return rc;
   hstu::FwdParams p;
   p.cu_seqlens = cu_seqlens; p.num_targets = num_targets; p.num_contexts = num_contexts;
+  p.q = static_cast<const __nv_bfloat16*>(q); p.q_t = strides[0]; p.q_h = strides[1];
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.H = heads; p.half_alpha = 0.5f * alpha; p.inv_scale = 1.0f / (float)scaling_seqlen;
   p.target_group = target_group_size; p.win_left = window_left; p.win_right = window_right;
   p.dbg = g_hstu_dbg;
-  if (head_dim == 128) return hstu::launch_fwd<128>(mq, mk, mv, p, batch, max_seqlen, (cudaStream_t)stream);
-  return hstu::launch_fwd<64>(mq, mk, mv, p, batch, max_seqlen, (cudaStream_t)stream);
+  if (head_dim == 128) return hstu::launch_fwd<128>(mk, mv, p, batch, max_seqlen, (cudaStream_t)stream);
+  return hstu::launch_fwd<64>(mk, mv, p, batch, max_seqlen, (cudaStream_t)stream);
 }
