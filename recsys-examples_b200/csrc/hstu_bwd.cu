@@ -17,6 +17,8 @@
 //   7 instead of 5 tile-GEMMs per (q,k) tile pair but needs no workspace, no atomics and is bit-reproducible.
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "../../include/hstu_b200.h"
 #include "hstu_mask.cuh"
 #include "sm100_ptx.cuh"
@@ -213,42 +215,56 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
       mbar_wait(&s_full[st], ph);
       if (threadIdx.x == 128) HSTU_DBG(17, j + 1);
       tc_fence_after();
-      uint32_t s[32], dp[32];
-      tmem_ld32(tS[st] + lane_off + ch * 32, s);
-      tmem_ld32(tDP[st] + lane_off + ch * 32, dp);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[st]);
-      uint32_t pk_ds[16], pk_p[16];
+      mbar_wait(&pd_empty[st], ph ^ 1);            // the accumulate GEMMs of tile j-2 have finished reading these operand buffers
+      const uint32_t dds = smem_u32(smem + SM::oDS + st * SM::kPD + rit * 128);
+      const uint32_t dpp = smem_u32(smem + SM::oP + st * SM::kPD + rit * 128);
       const f32x2 ha2 = pack2(p.half_alpha, p.half_alpha), one2 = pack2(1.f, 1.f), mone2 = pack2(-1.f, -1.f), mhalf2 = pack2(-0.5f, -0.5f);
+      // 16 score columns at a time, mask test hoisted out of the tile (see hstu_fwd.cu: a per-pair `if (!full)` splits the unrolled
+      // loop into basic blocks that ptxas cannot schedule the MUFU latency across; 64-register score arrays starve it of registers)
+      auto tile = [&](auto masked_tag) {
+        constexpr bool kMasked = decltype(masked_tag)::value;
+        uint32_t s[16], dp[16];
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const f32x2 h2 = mul2(pack2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), ha2);
-        const f32x2 t2 = tanh2(h2);
-        f32x2 pe2 = fma2(h2, t2, h2);                                  // silu = h + h t
-        const f32x2 u2 = fma2(t2, mone2, one2);                        // u = 1 - t
-        // silu' = 0.5 (1 + t) (1 + h (1 - t)) = (1 - u/2)(1 + h u)
-        f32x2 de2 = mul2(pack2(__uint_as_float(dp[i]), __uint_as_float(dp[i + 1])), mul2(fma2(u2, mhalf2, one2), fma2(h2, u2, one2)));
-        if (!full) {
-          const int yi = y0 + ch * 32 + i;
-          const bool ok0 = iv.has(yi), ok1 = iv.has(yi + 1);
-          float a0, a1, b0, b1; unpack2(pe2, a0, a1); unpack2(de2, b0, b1);
-          pe2 = pack2(ok0 ? a0 : 0.f, ok1 ? a1 : 0.f);
-          de2 = pack2(ok0 ? b0 : 0.f, ok1 ? b1 : 0.f);
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld16(tS[st] + lane_off + ch * 32 + c * 16, s);
+          tmem_ld16(tDP[st] + lane_off + ch * 32 + c * 16, dp);
+          tmem_ld_wait();
+          if (c == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[st]);
+          }
+          f32x2 h2[8], t2[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) h2[i] = mul2(pack2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), ha2);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t2[i] = tanh2(h2[i]);
+          uint32_t pk_ds[8], pk_p[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            f32x2 pe2 = fma2(h2[i], t2[i], h2[i]);                         // silu = h + h t
+            const f32x2 u2 = fma2(t2[i], mone2, one2);                     // u = 1 - t
+            // silu' = 0.5 (1 + t) (1 + h (1 - t)) = (1 - u/2)(1 + h u)
+            f32x2 de2 = mul2(pack2(__uint_as_float(dp[2 * i]), __uint_as_float(dp[2 * i + 1])), mul2(fma2(u2, mhalf2, one2), fma2(h2[i], u2, one2)));
+            if (kMasked) {
+              const int yi = y0 + ch * 32 + c * 16 + 2 * i;
+              const bool ok0 = iv.has(yi), ok1 = iv.has(yi + 1);
+              float a0, a1, b0, b1; unpack2(pe2, a0, a1); unpack2(de2, b0, b1);
+              pe2 = pack2(ok0 ? a0 : 0.f, ok1 ? a1 : 0.f);
+              de2 = pack2(ok0 ? b0 : 0.f, ok1 ? b1 : 0.f);
+            }
+            pk_ds[i] = pack_bf16x2_v(de2);
+            if (!kIsDQ) pk_p[i] = pack_bf16x2_v(pe2);
+          }
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const uint32_t sw = (uint32_t)((ch * 4 + c * 2 + q) ^ (rit & 7)) << 4;
+            sts128(dds + sw, pk_ds[4 * q], pk_ds[4 * q + 1], pk_ds[4 * q + 2], pk_ds[4 * q + 3]);
+            if (!kIsDQ) sts128(dpp + sw, pk_p[4 * q], pk_p[4 * q + 1], pk_p[4 * q + 2], pk_p[4 * q + 3]);
+          }
         }
-        pk_ds[i >> 1] = pack_bf16x2_v(de2);
-        if (!kIsDQ) pk_p[i >> 1] = pack_bf16x2_v(pe2);
-      }
-      mbar_wait(&pd_empty[st], ph ^ 1);
-      uint8_t* dds = smem + SM::oDS + st * SM::kPD + rit * 128;
-      uint8_t* dpp = smem + SM::oP + st * SM::kPD + rit * 128;
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        const int sw = ((ch * 4 + q4) ^ (rit & 7)) << 4;
-        *reinterpret_cast<uint4*>(dds + sw) = make_uint4(pk_ds[4 * q4], pk_ds[4 * q4 + 1], pk_ds[4 * q4 + 2], pk_ds[4 * q4 + 3]);
-        if (!kIsDQ) *reinterpret_cast<uint4*>(dpp + sw) = make_uint4(pk_p[4 * q4], pk_p[4 * q4 + 1], pk_p[4 * q4 + 2], pk_p[4 * q4 + 3]);
-      }
+      };
+      if (full) tile(std::false_type{}); else tile(std::true_type{});
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pd_full[st]);
