@@ -110,6 +110,21 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// thread = row: copy NCHUNK x 16 bf16 (two 16-byte global loads each) of one global row into 8 packed tensor-memory columns per chunk
+// (the layout a .ts MMA expects for its A operand: column c holds k = 2c | 2c+1).  Rows outside the sequence are zero-filled.
+template <int NCHUNK>
+__device__ __forceinline__ void rows_to_tmem(uint32_t taddr, const void* grow, bool valid) {
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    uint32_t r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (valid) {
+      const char* src = static_cast<const char*>(grow) + c * 32;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(src));
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(src + 16));
+    }
+    tmem_st8(taddr + c * 8, r);
+  }
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- UMMA descriptors

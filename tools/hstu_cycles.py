@@ -26,3 +26,20 @@ names = {40: "mma: wait k_full", 41: "mma: wait s_empty", 42: "mma: wait v_full"
          50: "silu: math", 51: "silu: wait p_empty", 52: "silu: st.shared + fence + arrive"}
 for k_, nm in names.items():
     print(f"  {nm:34s} {d[k_]:9d} cyc total  {d[k_] / max(n_iter, 1):8.0f} / iter")
+
+# ---- backward: dKV kernel slots 64.., dQ kernel slots 96..
+do = torch.randn_like(q)
+for _ in range(2): ops.hstu_varlen_bwd_100(do, q, k, v, cu, cu, S, S, None, None, None, None, None, 1, -1, 0, a)
+torch.cuda.synchronize()
+dbg.zero_()
+N.lib.hstu_set_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
+e0.record(); ops.hstu_varlen_bwd_100(do, q, k, v, cu, cu, S, S, None, None, None, None, None, 1, -1, 0, a); e1.record(); torch.cuda.synchronize()
+N.lib.hstu_set_debug_buffer(None)
+d = dbg.tolist()
+print(f"backward {e0.elapsed_time(e1):.3f} ms (two kernels)")
+for base, nm in ((64, "dKV"), (96, "dQ")):
+    n = max(d[base + 15], 1)
+    print(f" {nm} kernel, CTA0: {n} tiles of 128x64, MMA thread total {d[base + 3]} cyc = {d[base + 3] / n:.0f} / tile")
+    for off, what in ((0, "mma: wait y_full"), (1, "mma: wait s_empty"), (2, "mma: wait operand tile"), (8, "silu: wait pd_empty"), (9, "silu: wait s_full"),
+                      (10, "silu: ld + math + store"), (11, "silu: fence + arrive")):
+        print(f"   {what:28s} {d[base + off]:9d} cyc total {d[base + off] / n:8.0f} / tile")
