@@ -170,7 +170,7 @@ def run_reference_arm(args):
 
 def workload_config(args, n_ids):
     return {"workload": "dynamicemb_keyspace1e9_d128_fp32_adagrad_zipf1.05_seq", "ids_per_step_per_gpu": n_ids, "table_rows_per_gpu": args.capacity,
-            "bucket_capacity": 128, "score_strategy": "STEP", "prefill_load": 0.5, "parallelism": f"row-wise x{args.gpus} (hash_roundrobin, all_to_all)" if args.gpus > 1 else "single GPU",
+            "bucket_capacity": 128, "score_strategy": "STEP", "prefill_load": 0.5, "parallelism": f"row-wise x{args.gpus} (hash_roundrobin, index dedup, NCCL all_to_all of ids and rows; KJT = 1 feature x 4096 samples x {n_ids // 4096} ids per rank)" if args.gpus > 1 else "single GPU",
             "l2": "tables (32 GiB) and per-step id/gradient streams exceed the 126 MB L2; a fresh id batch every step"}
 
 
@@ -269,7 +269,8 @@ def main():
     if world > 1:
         from dynamicemb.shard import RowWiseShardedDynamicEmbedding
         model = RowWiseShardedDynamicEmbedding(m, None, dist_type="hash_roundrobin", use_index_dedup=True)
-        lengths = torch.ones(n_ids, dtype=torch.int64, device=dev)
+        samples = 4096                     # KJT shape per rank: one feature, 4096 samples x 256 ids (HSTU-like jagged sequences)
+        lengths = torch.full((samples,), n_ids // samples, dtype=torch.int64, device=dev)
         call = lambda ids: model(ids, lengths)
     else:
         offsets = torch.arange(0, n_ids + 1, dtype=torch.int64, device=dev)
@@ -300,24 +301,47 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
-    # ---- timed region: device-resident inputs
-    N.lib.demb_profile_enable(1)
-    N.PROFILE = {}
-    N.LAUNCHES[0] = 0
+    # ---- timed region: device-resident inputs.  N=1 runs the module's CUDA-graph step (make_graphed_step: prefetch + forward + fused
+    # backward captured once — the fused prefetch has no host sync — and replayed; the id batch is copied device-to-device into the
+    # graph's static input inside the timed region); N>1 (NCCL all_to_all in the step) runs the eager step.
+    dev_ids = torch.empty(n_ids, dtype=torch.int64, device=dev)
+    graphed, graph_err = None, None
+    if world == 1:
+        try:
+            dev_ids.copy_(batches[0])
+            graphed = m.make_graphed_step(dev_ids, offsets, grad)
+        except Exception as e:   # noqa: BLE001  (fall back to the eager step, say so in the JSON)
+            graphed, graph_err = None, repr(e)[:200]
+
+    def timed_step(ids):
+        if graphed is not None:
+            dev_ids.copy_(ids, non_blocking=True)
+            graphed[0].replay()
+        else:
+            step(ids)
+
+    for i in range(3):
+        timed_step(batches[i])
     clocks = ClockSampler(local)
     clocks.start()
     barrier()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
-    bwd_stage_ms = np.zeros(3)
     for i in range(args.steps):
-        step(batches[args.warmup + i])
-        if i == args.steps - 1:
-            pass
+        timed_step(batches[args.warmup + i])
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = N.LAUNCHES[0] // args.steps
+    clocks.stop()
+    # ---- per-kernel times for the roofline: a separate, un-reported pass of eager steps with CUDA events around every native launch
+    N.lib.demb_profile_enable(1)
+    N.PROFILE = {}
+    N.LAUNCHES[0] = 0
+    n_prof = min(args.steps, 8)
+    for i in range(n_prof):
+        step(batches[args.warmup + i])
+    torch.cuda.synchronize()
+    launches = N.LAUNCHES[0] // n_prof
     prof = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in N.PROFILE.items()}
     buf = (torch.zeros(3, dtype=torch.float32)).numpy()
     import ctypes
@@ -325,7 +349,6 @@ def main():
     bwd_stage_ms = buf.copy()
     N.PROFILE = None
     N.lib.demb_profile_enable(0)
-    clocks.stop()
     # the timed region lasts tens of ms — shorter than one nvidia-smi sample — so clocks / throttle reasons are sampled over a
     # ~2 s continuation of exactly the same steps (not part of any reported time)
     clocks = ClockSampler(local)
@@ -333,7 +356,7 @@ def main():
     t_end = time.time() + 2.0
     i = 0
     while time.time() < t_end:
-        step(batches[args.warmup + (i % args.steps)])
+        timed_step(batches[args.warmup + (i % args.steps)])
         i += 1
         if i % 8 == 0:
             torch.cuda.synchronize()
@@ -345,21 +368,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = world * n_ids * args.steps / (ms / 1e3)
+    step_mode = "cuda-graph step (module.make_graphed_step)" if graphed is not None else ("eager step" + (f" (graph capture failed: {graph_err})" if graph_err else ""))
 
     # ---- e2e: the public API with HOST inputs: pinned ids -> H2D, step (prefetch + forward + fused backward), loss stand-in
     # (sum of the looked-up rows) -> D2H, every step.  N=1 uses the module's CUDA-graph step (make_graphed_step): the fused
     # prefetch has no host sync, so the whole step replays as one graph launch.
     host_batches = [b.cpu().pin_memory() for b in batches[args.warmup:]]
-    dev_ids = torch.empty(n_ids, dtype=torch.int64, device=dev)
     host_res = torch.zeros(1, dtype=torch.float32).pin_memory()
-    graphed = None
-    if world == 1:
-        try:
-            dev_ids.copy_(host_batches[0])
-            graphed = m.make_graphed_step(dev_ids, offsets, grad)
-        except Exception as e:   # noqa: BLE001  (fall back to the eager step, say so in the JSON)
-            graphed = None
-            graph_err = repr(e)[:200]
     barrier()
     e0.record()
     for hb in host_batches:
@@ -378,7 +393,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n_ids * args.steps / (float(t.item()) / 1e3)
-    e2e_mode = "cuda-graph step (module.make_graphed_step)" if graphed is not None else "eager step"
+    e2e_mode = step_mode
 
     if rank == 0:
         hbm, tfl, which = peaks()
@@ -391,8 +406,14 @@ def main():
                  "backward_tiles_kernel": (float(bwd_stage_ms[1]), n_ids * (512 + 8) + nu * (2 * 1024 + 8))}
         dom = max(cands.items(), key=lambda kv: kv[1][0])
         kms, kbytes = dom[1]
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this command
+            with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
+                traffic = json.load(f).get(dom[0].split(" ")[0])
+        except (OSError, ValueError):
+            pass
         roof = {"kernel": dom[0], "bound": "hbm", "achieved": kbytes / kms / 1e6 if kms > 0 else None, "peak": hbm, "unit": "GB/s",
-                "frac": (kbytes / kms / 1e6 / hbm) if kms > 0 else None, "traffic": None, "peak_source": which,
+                "frac": (kbytes / kms / 1e6 / hbm) if kms > 0 else None, "traffic": traffic, "peak_source": which,
                 "algorithmic_bytes_per_launch": kbytes, "ms_per_launch": kms,
                 "other_kernels_ms": {**{k: round(v, 4) for k, v in prof.items()}, "backward.pairs+sort": float(bwd_stage_ms[0]),
                                      "backward.tiles": float(bwd_stage_ms[1]), "backward.spans": float(bwd_stage_ms[2])}}
@@ -411,7 +432,7 @@ def main():
                                         "lookups_per_s": n_ids / fms * 1e3}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": workload_config(args, n_ids), "clocks": clk,
+                "data": "synthetic", "config": {**workload_config(args, n_ids), "step_mode": step_mode}, "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_ids * 8, "d2h_bytes_per_step": 4, "mode": e2e_mode},
                 "gpu_launches": launches, "roofline": roof, "table_load": m.tables.size() / args.capacity}
         if world == 1 and not args.no_cpu:

@@ -178,6 +178,12 @@ int demb_block_bucketize_sparse_features(int64_t num_slots, int64_t batch_size, 
                                          const int64_t* block_sizes, const int32_t* dist_type_per_feature, const float* weights,
                                          int64_t* new_lengths, int64_t* new_ids, int64_t* unbucketize_permute, float* new_weights,
                                          void* workspace, int64_t workspace_bytes, void* stream);
+/* same, with the id count known on the host (ids.numel()): short slots (<= 4 ids on average, e.g. after index dedup) take a
+   thread-per-slot kernel pair instead of the warp-per-slot one.  num_ids < 0 = unknown. */
+int demb_block_bucketize_sparse_features_n(int64_t num_slots, int64_t batch_size, int world_size, int64_t num_ids, const int64_t* offsets,
+                                           const int64_t* ids, const int64_t* block_sizes, const int32_t* dist_type_per_feature,
+                                           const float* weights, int64_t* new_lengths, int64_t* new_ids, int64_t* unbucketize_permute,
+                                           float* new_weights, void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

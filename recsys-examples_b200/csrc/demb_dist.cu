@@ -69,6 +69,34 @@ __global__ void __launch_bounds__(kWarps * 32) bucketize_kernel(int64_t S, int64
     __syncwarp();
   }
 }
+// Short slots (index-dedup re-spreads the unique ids over the B samples, compute_dedup_lengths: most slots hold 0 or 1 id): a warp per
+// slot would idle 31 lanes, so one THREAD owns a slot, counts straight into new_lengths (zero-filled, entries private to the thread)
+// and in the scatter pass bumps its private new_offsets entries as cursors.  Same stable order as the warp kernel.
+template <int PASS>
+__global__ void __launch_bounds__(256) bucketize_short_kernel(int64_t S, int64_t B, int W, const int64_t* __restrict__ offsets, const int64_t* __restrict__ ids,
+                                                              const int64_t* __restrict__ block_sizes, const int32_t* __restrict__ dist_type,
+                                                              int64_t* __restrict__ new_lengths, int64_t* __restrict__ new_offsets,
+                                                              int64_t* __restrict__ new_ids, int64_t* __restrict__ unbucketize_permute,
+                                                              const float* __restrict__ weights, float* __restrict__ new_weights) {
+  for (int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < S; slot += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = slot / B;
+    const int dist = dist_type ? dist_type[f] : 0;
+    const uint64_t blk = (uint64_t)block_sizes[f];
+    const int64_t beg = offsets[slot], end = offsets[slot + 1];
+    for (int64_t i = beg; i < end; ++i) {
+      int p; uint64_t nid;
+      route((uint64_t)ids[i], dist, W, blk, p, nid);
+      if (!PASS) {
+        new_lengths[(int64_t)p * S + slot] += 1;
+      } else {
+        const int64_t at = new_offsets[(int64_t)p * S + slot]++;
+        new_ids[at] = (int64_t)nid;
+        if (unbucketize_permute) unbucketize_permute[i] = at;
+        if (weights) new_weights[at] = weights[i];
+      }
+    }
+  }
+}
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 }  // namespace
 
@@ -81,10 +109,24 @@ int64_t demb_bucketize_workspace_bytes(int64_t num_slots, int world_size) {
 }
 
 // offsets[S+1] (S = F*B slots, feature-major), ids[n].  Outputs: new_lengths[W*S], new_ids[n], unbucketize_permute[n] (nullable).
+int demb_block_bucketize_sparse_features_n(int64_t num_slots, int64_t batch_size, int world_size, int64_t num_ids, const int64_t* offsets,
+                                           const int64_t* ids, const int64_t* block_sizes, const int32_t* dist_type_per_feature, const float* weights,
+                                           int64_t* new_lengths, int64_t* new_ids, int64_t* unbucketize_permute, float* new_weights,
+                                           void* workspace, int64_t workspace_bytes, void* stream_);
+
 int demb_block_bucketize_sparse_features(int64_t num_slots, int64_t batch_size, int world_size, const int64_t* offsets, const int64_t* ids,
                                          const int64_t* block_sizes, const int32_t* dist_type_per_feature, const float* weights,
                                          int64_t* new_lengths, int64_t* new_ids, int64_t* unbucketize_permute, float* new_weights,
                                          void* workspace, int64_t workspace_bytes, void* stream_) {
+  return demb_block_bucketize_sparse_features_n(num_slots, batch_size, world_size, -1, offsets, ids, block_sizes, dist_type_per_feature, weights, new_lengths,
+                                                new_ids, unbucketize_permute, new_weights, workspace, workspace_bytes, stream_);
+}
+
+// num_ids >= 0 (known on the host, = ids.numel()) lets the launcher pick the thread-per-slot kernels when slots are short on average.
+int demb_block_bucketize_sparse_features_n(int64_t num_slots, int64_t batch_size, int world_size, int64_t num_ids, const int64_t* offsets,
+                                           const int64_t* ids, const int64_t* block_sizes, const int32_t* dist_type_per_feature, const float* weights,
+                                           int64_t* new_lengths, int64_t* new_ids, int64_t* unbucketize_permute, float* new_weights,
+                                           void* workspace, int64_t workspace_bytes, void* stream_) {
   if (world_size < 1 || world_size > kMaxRanks || batch_size <= 0) return DEMB_ERR_ARG;
   if (num_slots <= 0) return 0;
   if (workspace_bytes < demb_bucketize_workspace_bytes(num_slots, world_size)) return DEMB_ERR_WORKSPACE;
@@ -92,6 +134,20 @@ int demb_block_bucketize_sparse_features(int64_t num_slots, int64_t batch_size, 
   uint8_t* w = (uint8_t*)workspace;
   int64_t* new_offsets = (int64_t*)w; w += align256(8 * (size_t)(num_slots * world_size));
   size_t tmp_bytes = (size_t)((uint8_t*)workspace + workspace_bytes - w);
+  if (num_ids >= 0 && num_ids <= 4 * num_slots) {
+    const int64_t blocks = (num_slots + 255) / 256;
+    const int grid = (int)(blocks > 148 * 8 ? 148 * 8 : blocks);
+    cudaError_t e = cudaMemsetAsync(new_lengths, 0, 8 * (size_t)(num_slots * world_size), stream);
+    if (e != cudaSuccess) return -(int)e;
+    bucketize_short_kernel<0><<<grid, 256, 0, stream>>>(num_slots, batch_size, world_size, offsets, ids, block_sizes, dist_type_per_feature, new_lengths,
+                                                        nullptr, nullptr, nullptr, nullptr, nullptr);
+    e = cub::DeviceScan::ExclusiveSum(w, tmp_bytes, new_lengths, new_offsets, (int)(num_slots * world_size), stream);
+    if (e != cudaSuccess) return -(int)e;
+    bucketize_short_kernel<1><<<grid, 256, 0, stream>>>(num_slots, batch_size, world_size, offsets, ids, block_sizes, dist_type_per_feature, new_lengths,
+                                                        new_offsets, new_ids, unbucketize_permute, weights, new_weights);
+    DEMB_CHECK_LAST();
+    return 0;
+  }
   int64_t blocks = (num_slots + kWarps - 1) / kWarps;
   int grid = (int)(blocks > 148 * 16 ? 148 * 16 : blocks);
   bucketize_kernel<0><<<grid, kWarps * 32, 0, stream>>>(num_slots, batch_size, world_size, offsets, ids, block_sizes, dist_type_per_feature, new_lengths,

@@ -363,6 +363,7 @@ extern "C" int hstu_bwd_sm100(const void* dout, const void* q, const void* k, co
   for (int i = 0; i < 8; ++i) if (strides[i] % 8) return HSTU_ERR_ARG;
   cudaStream_t stream = (cudaStream_t)stream_;
   const void* ptr[4] = {q, k, v, dout};
+  tma::bind_context(q);
   CUtensorMap small[4];     // 64-row boxes of q, k, v, dO (the streamed operands; the stationary ones are read row-wise into tensor memory)
   for (int i = 0; i < 4; ++i) {
     if (reinterpret_cast<uintptr_t>(ptr[i]) & 15) return HSTU_ERR_ARG;

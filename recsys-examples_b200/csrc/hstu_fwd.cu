@@ -314,6 +314,7 @@ extern "C" int hstu_fwd_sm100(const void* q, const void* k, const void* v, void*
   if (target_group_size < 1 || scaling_seqlen <= 0) return HSTU_ERR_ARG;
   for (int i = 0; i < 6; ++i) if (strides[i] % 8) return HSTU_ERR_ARG;                       // TMA: 16-byte aligned strides
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out)) & 15) return HSTU_ERR_ARG;
+  tma::bind_context(q);
   CUtensorMap mk, mv;
   int rc;
   if ((rc = tma::make_map_3d(&mk, k, head_dim, heads, total_tokens, strides[3] * 2, strides[2] * 2, 64, 1, 128))) return rc;

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
 }  // namespace
 
 extern "C" int sm100_probe_gemm(const void* A, const void* B, float* C, int variant, const uint32_t* overrides /*8 host u32, nullable*/, void* stream) {
+  tma::bind_context(A);
   CUtensorMap ma, mb;
   // both operands are [128][128] bf16 row-major tensors; a 3D map (inner 128, 1, 128 rows), box (64, 1, 128), SWIZZLE_128B
   int rc = tma::make_map_3d(&ma, A, 128, 1, 128, 128 * 2, 128 * 2, 64, 1, 128);

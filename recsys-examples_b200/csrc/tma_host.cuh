@@ -35,4 +35,17 @@ inline int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d
   return r == CUDA_SUCCESS ? 0 : -2001 - (int)r;
 }
 
+// cuTensorMapEncodeTiled is a DRIVER entry point: it fails with CUDA_ERROR_INVALID_CONTEXT on a host thread that has not touched the
+// runtime yet (PyTorch's autograd worker calling the backward first).  Bind the primary context of the device that owns `p`.
+inline void bind_context(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != a.device) cudaSetDevice(a.device);
+  } else {
+    (void)cudaGetLastError();
+  }
+  cudaFree(nullptr);
+}
+
 }  // namespace tma

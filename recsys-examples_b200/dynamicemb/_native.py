@@ -54,6 +54,7 @@ _SIGS = {
     "demb_profile_read": (I32, [P]),
     "demb_bucketize_workspace_bytes": (I64, [I64, I32]),
     "demb_block_bucketize_sparse_features": (I32, [I64, I64, I32, P, P, P, P, P, P, P, P, P, P, I64, P]),
+    "demb_block_bucketize_sparse_features_n": (I32, [I64, I64, I32, I64, P, P, P, P, P, P, P, P, P, P, I64, P]),
 }
 for _name, (_res, _args) in _SIGS.items():
     _f = getattr(lib, _name)

@@ -403,7 +403,7 @@ def block_bucketize_sparse_features(lengths: torch.Tensor, indices: torch.Tensor
     new_w = torch.empty(n, dtype=torch.float32, device=dev) if weights is not None else None
     ws = N.workspace(N.lib.demb_bucketize_workspace_bytes(S, world_size), dev)
     dt = dist_type_per_feature.to(torch.int32).contiguous() if dist_type_per_feature is not None else None
-    N.check(N.launch("bucketize", 2, N.lib.demb_block_bucketize_sparse_features, S, batch_size, world_size, N.ptr(offsets), N.ptr(_i64(indices)),
+    N.check(N.launch("bucketize", 2, N.lib.demb_block_bucketize_sparse_features_n, S, batch_size, world_size, n, N.ptr(offsets), N.ptr(_i64(indices)),
                                                        N.ptr(_i64(block_sizes)), N.ptr(dt), N.ptr(weights), N.ptr(new_lengths), N.ptr(new_ids),
                                                        N.ptr(perm), N.ptr(new_w), N.ptr(ws), ws.numel(), N.stream()),
             "block_bucketize_sparse_features")

@@ -22,7 +22,7 @@ class DistContext:
     send_splits: List[int]        # ids sent to each rank
     recv_splits: List[int]        # ids received from each rank
     unbucketize_permute: torch.Tensor   # position of original id i inside the bucketized (rank-major) send buffer
-    recv_order: torch.Tensor      # permutation applied to received ids to make them feature-major for the local lookup
+    recv_order: Optional[torch.Tensor]   # permutation applied to received ids to make them feature-major for the local lookup (None = identity)
     num_ids: int
 
 
@@ -47,6 +47,43 @@ class _RowsAllToAll(torch.autograd.Function):
         return g, None, None, None
 
 
+class _PermuteRows(torch.autograd.Function):
+    """out = x[idx] for a PERMUTATION idx.  backward is the gather by the inverse permutation — never torch's
+    index_put_(accumulate=True), whose sort-based kernel took 40 ms per step on a [2^20, 128] gradient."""
+
+    @staticmethod
+    def forward(ctx, x, idx, inv_idx):
+        ctx.save_for_backward(inv_idx)
+        return x.index_select(0, idx)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (inv_idx,) = ctx.saved_tensors
+        return grad.index_select(0, inv_idx), None, None
+
+
+class _ExpandRows(torch.autograd.Function):
+    """out = x[idx] where idx repeats rows (un-dedup + un-bucketize in one gather).  backward reduces the gradient rows per source
+    row with the injected `reduce_fn(idx, grad, num_rows)` (the CUDA reduce_grads kernels on GPUs: fixed summation order)."""
+
+    @staticmethod
+    def forward(ctx, x, idx, reduce_fn):
+        ctx.save_for_backward(idx)
+        ctx.num_rows, ctx.reduce_fn = x.shape[0], reduce_fn
+        return x.index_select(0, idx)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (idx,) = ctx.saved_tensors
+        return ctx.reduce_fn(idx, grad.contiguous(), ctx.num_rows), None, None
+
+
+def _inverse_permutation(perm: torch.Tensor) -> torch.Tensor:
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(perm.numel(), device=perm.device, dtype=perm.dtype)
+    return inv
+
+
 def rw_input_dist(ids: torch.Tensor, lengths: torch.Tensor, batch_size: int, num_features: int, group,
                   bucketize_fn: Callable) -> Tuple[torch.Tensor, torch.Tensor, DistContext]:
     """ids[n] + lengths[F*B] (feature-major) of THIS rank's batch -> (ids_recv feature-major, lengths_recv[F*W*B], ctx).
@@ -58,11 +95,14 @@ def rw_input_dist(ids: torch.Tensor, lengths: torch.Tensor, batch_size: int, num
     # --- exchange lengths: every rank sends its [F*B] length vector for each destination
     recv_lengths = torch.empty_like(new_lengths)
     _all_to_all_single(recv_lengths, new_lengths, [S] * W, [S] * W, group)
-    send_splits = new_lengths.view(W, S).sum(dim=1).tolist()          # host sync (TorchRec KJTAllToAll does the same)
-    recv_splits = recv_lengths.view(W, S).sum(dim=1).tolist()
+    splits = torch.cat([new_lengths.view(W, S).sum(dim=1), recv_lengths.view(W, S).sum(dim=1)]).tolist()   # ONE host sync (TorchRec KJTAllToAll syncs here too)
+    send_splits, recv_splits = splits[:W], splits[W:]
     ids_recv = new_ids.new_empty(sum(recv_splits))
     _all_to_all_single(ids_recv, new_ids, recv_splits, send_splits, group)
     # --- received layout is (source rank, feature, sample); the lookup wants feature-major: (feature, source rank, sample)
+    if num_features == 1:                 # one feature: the received order already is feature-major, no regrouping pass
+        ctx = DistContext(send_splits, recv_splits, perm, None, int(ids.numel()))
+        return ids_recv, recv_lengths, ctx
     rl = recv_lengths.view(W, num_features, batch_size)
     lengths_fm = rl.permute(1, 0, 2).reshape(-1)                        # [F * W * B]
     # permutation of ids: compute start offset of each (r, f, b) segment in received order, then gather in (f, r, b) order
@@ -83,11 +123,16 @@ def rw_input_dist(ids: torch.Tensor, lengths: torch.Tensor, batch_size: int, num
     return ids_fm, lengths_fm, ctx
 
 
-def rw_output_dist(rows_fm: torch.Tensor, ctx: DistContext, group) -> torch.Tensor:
-    """rows of the locally looked-up ids (feature-major order) -> rows for this rank's original ids, original order."""
+def rw_output_dist(rows_fm: torch.Tensor, ctx: DistContext, group, expand: Optional[torch.Tensor] = None,
+                   reduce_fn: Optional[Callable] = None) -> torch.Tensor:
+    """rows of the locally looked-up ids (feature-major order) -> rows for this rank's original ids, original order.
+
+    expand: reverse indices of the per-rank index dedup (original id i -> position of its unique id), folded into the final gather;
+    reduce_fn(idx, grad[n, D], num_rows) -> [num_rows, D] sums the gradient rows that share a source row (needed with `expand`)."""
     # undo the feature-major regrouping, send every row back to the rank that asked, undo the bucketize permutation
-    inv = torch.empty_like(ctx.recv_order)
-    inv[ctx.recv_order] = torch.arange(ctx.recv_order.numel(), device=ctx.recv_order.device)
-    rows_recv_order = rows_fm[inv]
+    rows_recv_order = rows_fm if ctx.recv_order is None else _PermuteRows.apply(rows_fm, _inverse_permutation(ctx.recv_order), ctx.recv_order)
     back = _RowsAllToAll.apply(rows_recv_order, ctx.send_splits, ctx.recv_splits, group)
-    return back[ctx.unbucketize_permute]
+    if expand is None:
+        return _PermuteRows.apply(back, ctx.unbucketize_permute, _inverse_permutation(ctx.unbucketize_permute))
+    assert reduce_fn is not None
+    return _ExpandRows.apply(back, ctx.unbucketize_permute[expand], reduce_fn)

@@ -66,8 +66,12 @@ class RowWiseShardedDynamicEmbedding(nn.Module):
         offsets_fm = torch.zeros(lengths_fm.numel() + 1, dtype=torch.int64, device=ids.device)
         torch.cumsum(lengths_fm, 0, out=offsets_fm[1:])
         rows = self.local(ids_fm, offsets_fm)
-        out = rw_output_dist(rows, ctx, self.group)
-        return out[reverse] if reverse is not None else out
+        return rw_output_dist(rows, ctx, self.group, expand=reverse, reduce_fn=self._reduce_rows)
+
+    @staticmethod
+    def _reduce_rows(idx, grad, num_rows):
+        """sum of the gradient rows per source row: the reduce_grads kernels (sort -> tiles -> windows -> spans, fixed order)"""
+        return ext.reduce_grads(idx, grad, num_rows, 0, grad.shape[1])
 
 
 def _need_torchrec():

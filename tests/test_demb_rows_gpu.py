@@ -212,3 +212,24 @@ def test_block_bucketize(cuda):
         assert np.array_equal(nl.cpu().numpy(), enl)
         assert np.array_equal(ni.cpu().numpy(), eni)
         assert np.array_equal(perm.cpu().numpy(), eperm)
+
+
+def test_block_bucketize_short_slots(cuda):
+    """<= 4 ids per slot on average (what index dedup produces): the thread-per-slot kernels must give the warp kernels' exact output."""
+    from dynamicemb import dynamicemb_extensions as ext
+    from oracle import dynamicemb as orc
+    rng = np.random.default_rng(29)
+    B, F, W = 1000, 2, 3
+    lens = rng.integers(0, 4, size=F * B)
+    lens[rng.integers(0, F * B, size=5)] = 9            # a few longer slots inside the short regime
+    n = int(lens.sum())
+    assert n <= 4 * F * B
+    ids = rng.integers(0, 1 << 50, size=n, dtype=np.int64)
+    blk = np.array([1 << 40, 12345], dtype=np.int64)
+    for dts in ([0, 0], [1, 2], [2, 2]):
+        nl, ni, _, perm = ext.block_bucketize_sparse_features(torch.from_numpy(lens).to(cuda), torch.from_numpy(ids).to(cuda), B, W,
+                                                              torch.from_numpy(blk).to(cuda), torch.tensor(dts, dtype=torch.int32, device=cuda))
+        enl, eni, eperm = orc.block_bucketize(lens, ids, B, W, blk, dts)
+        assert np.array_equal(nl.cpu().numpy(), enl)
+        assert np.array_equal(ni.cpu().numpy(), eni)
+        assert np.array_equal(perm.cpu().numpy(), eperm)

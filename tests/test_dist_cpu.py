@@ -61,6 +61,26 @@ def _worker(rank, world, port, dist_mode, q):
         assert torch.equal(out.detach(), want), "rows came back to the wrong ids"
         out.sum().backward()          # gradient all_to_all mirrors the forward: every local row was requested exactly once
         assert torch.equal(w.grad, rows.detach().sum(0, keepdim=True) / 1.0) or w.grad.shape == (1, D)
+        # ---- index-dedup variant: unique ids travel, the final gather expands them again; the gradient of a repeated id must be the
+        # SUM over its occurrences (checked against plain torch indexing, which uses index_put_(accumulate=True))
+        uk, reverse = np.unique(ids, return_inverse=True)
+        ulen = np.zeros(F * B, dtype=np.int64); ulen[0] = uk.size                 # all unique ids in the first slot of feature 0
+        ids_u, lengths_u, ctx_u = rw_input_dist(torch.from_numpy(uk), torch.from_numpy(ulen), B, F, None, bucketize)
+        gid_u = ids_u.clone()
+        if dist_mode == "continuous":
+            gid_u = gid_u + rank * int(blk[0])
+        wgt = torch.linspace(0.5, 1.5, D)[None, :]
+        rows_a = (gid_u.to(torch.float32)[:, None] * wgt).requires_grad_(True)
+        rows_b = rows_a.detach().clone().requires_grad_(True)
+        reduce_fn = lambda idx, g, n: torch.zeros(n, g.shape[1]).index_add_(0, idx, g)
+        rev = torch.from_numpy(reverse.astype(np.int64))
+        out_a = rw_output_dist(rows_a, ctx_u, None, expand=rev, reduce_fn=reduce_fn)
+        out_b = rw_output_dist(rows_b, ctx_u, None)[rev]
+        assert torch.equal(out_a.detach(), out_b.detach())
+        assert torch.equal(out_a.detach(), torch.from_numpy(ids.astype(np.float32))[:, None] * wgt)
+        gsel = torch.from_numpy(rng.standard_normal((ids.size, D)).astype(np.float32))
+        (out_a * gsel).sum().backward(); (out_b * gsel).sum().backward()
+        assert torch.allclose(rows_a.grad, rows_b.grad, rtol=1e-5, atol=1e-5), "custom backward differs from index_put accumulate"
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
