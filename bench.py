@@ -305,18 +305,19 @@ def main():
     # backward captured once — the fused prefetch has no host sync — and replayed; the id batch is copied device-to-device into the
     # graph's static input inside the timed region); N>1 (NCCL all_to_all in the step) runs the eager step.
     dev_ids = torch.empty(n_ids, dtype=torch.int64, device=dev)
-    graphed, graph_err = None, None
+    graphed, graphed_noloss, graph_err = None, None, None
     if world == 1:
         try:
             dev_ids.copy_(batches[0])
-            graphed = m.make_graphed_step(dev_ids, offsets, grad)
+            graphed = m.make_graphed_step(dev_ids, offsets, grad)                          # e2e: + loss stand-in (out.sum()) read back every step
+            graphed_noloss = m.make_graphed_step(dev_ids, offsets, grad, with_loss=False)   # value: the step alone
         except Exception as e:   # noqa: BLE001  (fall back to the eager step, say so in the JSON)
-            graphed, graph_err = None, repr(e)[:200]
+            graphed, graphed_noloss, graph_err = None, None, repr(e)[:200]
 
     def timed_step(ids):
-        if graphed is not None:
+        if graphed_noloss is not None:
             dev_ids.copy_(ids, non_blocking=True)
-            graphed[0].replay()
+            graphed_noloss[0].replay()
         else:
             step(ids)
 

@@ -132,11 +132,14 @@ __global__ void __launch_bounds__(384) forward_seq_tma_kernel(RowSrc s, const fl
   uint32_t parity = 0;
   const int64_t tiles = (n + 31) >> 5;
   const int64_t wstride = (int64_t)gridDim.x * warps_per_block;
-  for (int64_t tile = (int64_t)blockIdx.x * warps_per_block + wib; tile < tiles; tile += wstride) {
+  int64_t tile = (int64_t)blockIdx.x * warps_per_block + wib;
+  // Software pipeline: the row ids of tile t+1 (a chain of dependent loads: digest -> key in probe mode, inverse -> rows in gather
+  // mode, ~2 us) are resolved while the bulk copies of tile t are in flight, not after them.
+  int64_t row = -1;
+  if (tile < tiles && (tile << 5) + lane < n) row = resolve_row(s, (tile << 5) + lane);
+  for (; tile < tiles; tile += wstride) {
     const int64_t base = tile << 5;
     const int cnt = (int)((n - base) < 32 ? (n - base) : 32);
-    int64_t row = -1;
-    if (lane < cnt) row = resolve_row(s, base + lane);
     const unsigned found = __ballot_sync(0xffffffffu, row >= 0);
     if (lane == 0) {
       sm100::bulk_wait_read0();                                  // the previous tile's bulk store has finished reading this stage
@@ -149,6 +152,9 @@ __global__ void __launch_bounds__(384) forward_seq_tma_kernel(RowSrc s, const fl
       float4* d = reinterpret_cast<float4*>(buf + (size_t)lane * row_bytes);
       for (int c = 0; c < (D >> 2); ++c) d[c] = make_float4(absent_value, absent_value, absent_value, absent_value);
     }
+    const int64_t nbase = (tile + wstride) << 5;
+    int64_t next_row = -1;
+    if (tile + wstride < tiles && nbase + lane < n) next_row = resolve_row(s, nbase + lane);
     sm100::mbar_wait(&bars[wib], parity);
     parity ^= 1;
     sm100::fence_proxy_async_smem();                             // absent rows were written through the generic proxy
@@ -157,6 +163,7 @@ __global__ void __launch_bounds__(384) forward_seq_tma_kernel(RowSrc s, const fl
       sm100::bulk_store(out + base * (int64_t)D, buf, (uint32_t)cnt * row_bytes);
       sm100::bulk_commit();
     }
+    row = next_row;
   }
   if (lane == 0) sm100::bulk_wait0();                             // shared memory must outlive the last bulk store
 }
@@ -354,15 +361,16 @@ struct BwdArgs {
   OptArgs opt;
 };
 
-template <int NCHUNK>
-__device__ __forceinline__ void finish_segment(const BwdArgs& a, int32_t u, const float4 (&acc)[NCHUNK], int lane) {
+// r = a.rows[u] when the caller already holds it (kRowKnown), else it is loaded here
+template <int NCHUNK, bool kRowKnown = false>
+__device__ __forceinline__ void finish_segment(const BwdArgs& a, int32_t u, const float4 (&acc)[NCHUNK], int lane, int64_t r_known = -1) {
   const int D4 = a.D >> 2;
   if (a.unique_grads) {
 #pragma unroll
     for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; if (c < D4) st_f4(a.unique_grads + (int64_t)u * a.D + 4 * c, acc[k]); }
   }
   if (a.rows && a.opt.type != DEMB_OPT_NONE) {
-    const int64_t r = a.rows[u];
+    const int64_t r = kRowKnown ? r_known : a.rows[u];
     if (r >= 0) apply_row<NCHUNK>(a.opt, a.values + r * a.vdim, a.D, acc, lane);
   }
 }
@@ -390,6 +398,18 @@ __global__ void __launch_bounds__(kBlock) backward_tiles_kernel(BwdArgs a) {
         mys = 1.0f / (float)len;                                   // lookup_backward.cu:209-241
       }
     }
+    // The optimizer's read-modify-write of a value row sits at the END of a dependent chain (pair -> rows[u] -> row); resolve the
+    // row id per lane up front and pull the row (embedding + optimizer state) into L2 now, so the RMW after the gradient rows have
+    // been summed finds it there instead of paying a DRAM round trip per segment.
+    int64_t myrow = -1;
+    if (lane < cnt && a.rows && a.opt.type != DEMB_OPT_NONE) {
+      myrow = a.rows[myu];
+      const int32_t up = __shfl_up_sync(__activemask(), myu, 1);
+      if (myrow >= 0 && (lane == 0 || up != myu)) {
+        const char* pr = reinterpret_cast<const char*>(a.values + myrow * a.vdim);
+        for (int64_t b = 0; b < a.vdim * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + b));
+      }
+    }
     const int32_t prev_u = base > 0 ? a.skey[base - 1] : -1;
     const int32_t next_u = base + 32 < a.n ? a.skey[base + 32] : -2;
     float4 acc[NCHUNK];
@@ -398,9 +418,9 @@ __global__ void __launch_bounds__(kBlock) backward_tiles_kernel(BwdArgs a) {
     bool incoming = (__shfl_sync(0xffffffffu, myu, 0) == prev_u);
     constexpr int U = 4;
     for (int j = 0; j < cnt; j += U) {
-      int32_t uu[U + 1]; int32_t rr[U]; float sc[U];
+      int32_t uu[U + 1]; int32_t rr[U]; float sc[U]; int64_t vr[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) { uu[u] = __shfl_sync(0xffffffffu, myu, (j + u) & 31); rr[u] = __shfl_sync(0xffffffffu, myr, (j + u) & 31); sc[u] = __shfl_sync(0xffffffffu, mys, (j + u) & 31); }
+      for (int u = 0; u < U; ++u) { uu[u] = __shfl_sync(0xffffffffu, myu, (j + u) & 31); rr[u] = __shfl_sync(0xffffffffu, myr, (j + u) & 31); sc[u] = __shfl_sync(0xffffffffu, mys, (j + u) & 31); vr[u] = __shfl_sync(0xffffffffu, myrow, (j + u) & 31); }
       uu[U] = __shfl_sync(0xffffffffu, myu, (j + U) & 31);
       float4 v[U][NCHUNK];
 #pragma unroll
@@ -425,7 +445,7 @@ __global__ void __launch_bounds__(kBlock) backward_tiles_kernel(BwdArgs a) {
 #pragma unroll
             for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; if (c < D4) st_f4(a.part_cont + tile * a.D + 4 * c, acc[k]); }
           } else {
-            finish_segment<NCHUNK>(a, uu[u], acc, lane);
+            finish_segment<NCHUNK, true>(a, uu[u], acc, lane, vr[u]);
           }
 #pragma unroll
           for (int k = 0; k < NCHUNK; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -396,13 +396,14 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
                                   num_scores=tb.num_scores_)
 
     # ------------------------------------------------------------------ CUDA-graph training step
-    def make_graphed_step(self, ids_static: torch.Tensor, offsets: torch.Tensor, grad_static: torch.Tensor):
+    def make_graphed_step(self, ids_static: torch.Tensor, offsets: torch.Tensor, grad_static: torch.Tensor, with_loss: bool = True):
         """Capture prefetch -> forward -> loss stand-in -> fused backward as ONE CUDA graph over static buffers.
 
         Possible because the fused prefetch never synchronises with the host (unique counts stay on the device) and every kernel
         takes its sizes from device memory or from the static shapes.  Replay costs one launch: the ~0.3 ms of per-step Python /
         launch overhead disappears from the host timeline.  Returns (graph, out, loss): copy new ids into `ids_static` (and new
-        upstream gradients into `grad_static`), call graph.replay(), read `out` / `loss`.
+        upstream gradients into `grad_static`), call graph.replay(), read `out` / `loss` (loss = out.sum(), a stand-in for the model's
+        scalar result; None with with_loss=False).
         Restrictions: training mode, fused prefetch, optimizers whose kernel arguments do not depend on the step count
         (SGD / Adagrad / row-wise Adagrad — Adam's bias correction is a host value), non-GLOBAL_TIMER scores."""
         from .types import EmbOptimType
@@ -418,7 +419,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
             self.prefetch(indices, offsets_i)
             st = self._prefetch_states.popleft()
             out_ = _LookupFunction.forward(_NoCtx(), self, st, offsets_i, B, None)
-            loss_ = out_.sum()
+            loss_ = out_.sum() if with_loss else None
             self._optimizer.step()
             pooled = self.pooling_mode != DynamicEmbPoolingMode.NONE
             ext.backward(self._values, self.max_D, st.reverse_indices, max(st.num_unique_bound, 1), st.rows, grad_static,
