@@ -45,15 +45,19 @@ struct FwdParams {
   float inv_scale;               // 1 / scaling_seqlen
   int target_group;
   int win_left, win_right;       // -1 = unbounded
-  volatile int* dbg;             // optional host-mapped buffer (hstu_set_debug_buffer), nullptr in production
+  int n_m, n_tiles;              // 128-query tiles per sequence (max_seqlen based), total tiles = n_m * H * B
+  int* tile_counter;             // zeroed before every launch: the persistent CTAs pull tile indices from it
+  volatile int* dbg;             // optional DEVICE buffer (hstu_set_debug_buffer), nullptr in production
 };
 
-// Cycle accounting (kProf instantiation only, selected when a debug buffer is installed): clock64() deltas are accumulated in
-// REGISTERS and written to the host-mapped buffer once per role at the end (a host-memory store + fence per mark costs microseconds
-// and distorts exactly the pipeline it is meant to observe).
+// Cycle accounting (kProf instantiation only, selected when a debug buffer — DEVICE memory, zeroed by the caller — is installed):
+// clock64() deltas are accumulated in REGISTERS and added to the buffer once per role per CTA, in units of 16 cycles, summed over ALL
+// CTAs (a store + fence per mark costs microseconds and distorts exactly the pipeline it is meant to observe).
+// Slots: 8 = iterations, 9 = CTAs, 10 = CTA lifetime, 11 = prologue (launch -> first S tile ready), 12 = epilogue (last P -> exit);
+// 40.. MMA thread waits (k_full, -, v_full, p_full), 48.. SiLU thread 128 (s_full wait, -, math, -, arrive).
 #define HSTU_T0() long long t__0 = kProf ? clock64() : 0
 #define HSTU_ACC(i) do { if (kProf) { long long t__1 = clock64(); acc__[i] += (int)(t__1 - t__0); t__0 = t__1; } } while (0)
-#define HSTU_FLUSH(base, n) do { if (kProf && p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { for (int i__ = 0; i__ < (n); ++i__) p.dbg[(base) + i__] = acc__[i__]; __threadfence_system(); } } while (0)
+#define HSTU_FLUSH(base, n) do { if (kProf && p.dbg) { for (int i__ = 0; i__ < (n); ++i__) atomicAdd(const_cast<int*>(p.dbg) + (base) + i__, acc__[i__] >> 4); } } while (0)
 
 template <int D>
 struct FwdSmem {
@@ -70,33 +74,53 @@ __device__ __forceinline__ uint4 ldg_nc_u4(const void* ptr) {
   return v;
 }
 
+// One unit of work: a 128-query tile of one (sequence, head).
+struct FwdTile {
+  int b, h, seq_start, L, r0, r1, nb0, n_iter;
+  SeqMask mk;
+};
+// What the scheduler thread publishes per tile: the global loads (cu_seqlens, contexts, targets) are done ONCE, by the otherwise idle
+// scheduler, instead of by each of the 11 consumers on its critical path.
+struct TileMsg { int w, seq_start, L, seqlen_c, num_t; };
+// tile index w (heavy-first inside each (b, h), the 32-ish tiles of one (b, h) adjacent so concurrently running CTAs share its K / V
+// through L2) -> geometry.  false: the tile lies beyond the end of its (jagged) sequence.
+__device__ __forceinline__ bool decode_tile(const FwdParams& p, const TileMsg& m, FwdTile& t) {
+  const int w = m.w;
+  const int bh = w / p.n_m, m_tile = p.n_m - 1 - (w - bh * p.n_m);
+  t.b = bh / p.H; t.h = bh - t.b * p.H;
+  t.seq_start = m.seq_start;
+  t.L = m.L;
+  t.r0 = m_tile * 128;
+  if (t.r0 >= t.L) return false;
+  t.r1 = min(t.L, t.r0 + 128) - 1;
+  SeqMask& mk = t.mk;
+  mk.L = t.L; mk.G = p.target_group; mk.wl = p.win_left; mk.wr = p.win_right;
+  mk.has_t = p.num_targets != nullptr; mk.has_c = p.num_contexts != nullptr;
+  mk.seqlen_c = m.seqlen_c;
+  mk.seqlen_h = t.L - m.num_t;
+  int n_end = (mk.wr >= 0) ? min(t.L, t.r1 + mk.wr + 1) : t.L;
+  if (mk.has_c && t.r0 < mk.seqlen_c) n_end = max(n_end, mk.seqlen_h);
+  t.nb0 = (mk.wl >= 0) ? max(0, t.r0 - mk.wl) / 128 : 0;
+  t.n_iter = (n_end + 127) / 128 - t.nb0;
+  return true;
+}
+
+// PERSISTENT kernel: one CTA per SM pulls tiles from a global counter (same order the hardware block scheduler used to give the
+// one-tile-per-CTA version: measured 6400 cycles of prologue + 2600 of epilogue on a 33000-cycle CTA, 27 % of the SM's time with the
+// tensor pipe idle).  Across tile boundaries the K / V producers keep prefetching, the MMA thread issues Q K^T of the next tile as
+// soon as its Q is in tensor memory, and only the O read-out of the SiLU warps is exposed.
 template <int D, bool kProf>
 __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, FwdParams p) {
   using SM = FwdSmem<D>;
   constexpr int NH = D / 64;                         // 64-column (128-byte) halves per tile row
   constexpr int S = SM::kStages;
-  const int b = blockIdx.z, h = blockIdx.y;
-  const int m_tile = gridDim.x - 1 - blockIdx.x;     // heaviest (longest causal row) tiles first
-  const int seq_start = p.cu_seqlens[b];
-  const int L = p.cu_seqlens[b + 1] - seq_start;
-  const int r0 = m_tile * 128;
-  if (r0 >= L) return;
-  const int r1 = min(L, r0 + 128) - 1;
-
-  SeqMask mk;
-  mk.L = L; mk.G = p.target_group; mk.wl = p.win_left; mk.wr = p.win_right;
-  mk.has_t = p.num_targets != nullptr; mk.has_c = p.num_contexts != nullptr;
-  mk.seqlen_c = mk.has_c ? p.num_contexts[b] : 0;
-  mk.seqlen_h = L - (mk.has_t ? p.num_targets[b] : 0);
-  int n_end = (mk.wr >= 0) ? min(L, r1 + mk.wr + 1) : L;
-  if (mk.has_c && r0 < mk.seqlen_c) n_end = max(n_end, mk.seqlen_h);
-  const int nb0 = (mk.wl >= 0) ? max(0, r0 - mk.wl) / 128 : 0;
-  const int nb1 = (n_end + 127) / 128;
-  const int n_iter = nb1 - nb0;
+  constexpr int kRing = 4;                           // tile-id ring between the scheduler thread and the 11 consumers
+  const long long t_cta0 = kProf ? clock64() : 0;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t q_full, k_full[S], k_empty[S], v_full[S], v_empty[S], s_full[2], p_full[2], o_full;
+  __shared__ uint64_t q_full, k_full[S], k_empty[S], v_full[S], v_empty[S], s_full[2], p_full[2], o_full, tile_full[kRing], tile_empty[kRing];
+  __shared__ TileMsg tile_ring[kRing];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -104,6 +128,7 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
     mbar_init(&q_full, 8); mbar_init(&o_full, 1);
     for (int i = 0; i < S; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); }
+    for (int i = 0; i < kRing; ++i) { mbar_init(&tile_full[i], 1); mbar_init(&tile_empty[i], 11); }
     fence_barrier_init();
     tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
   }
@@ -116,20 +141,62 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
   const uint32_t tO = tmem + 256;
   const uint32_t tQ = tmem + 384;                    // Q tile, bf16x2 packed: D / 2 columns
 
-  if (warp == 0 || warp == 3) {
+  // every consumer walks the ring with its own cursor; returns the next tile that exists (skipping tiles past the end of their
+  // sequence) or false when the scheduler has published the end marker
+  // (warp_wide: all 32 lanes call it together — the SiLU warps; the single-thread roles must not execute a warp barrier)
+  auto next_tile = [&](int& cursor, FwdTile& t, bool arrive_lane, bool warp_wide) -> bool {
+    for (;;) {
+      const int slot = cursor % kRing;
+      mbar_wait(&tile_full[slot], (cursor / kRing) & 1);
+      const TileMsg m = tile_ring[slot];
+      ++cursor;
+      if (m.w < 0) return false;                     // end marker: left in place, never released
+      if (warp_wide) __syncwarp();                   // every lane has read the slot before lane 0 hands it back
+      if (arrive_lane) mbar_arrive(&tile_empty[slot]);
+      if (decode_tile(p, m, t)) return true;
+    }
+  };
+
+  if (warp == 2) {
+    // ------------------------------------------------------------------ tile scheduler
+    if (elect_one()) {
+      for (int c = 0;; ++c) {
+        const int slot = c % kRing;
+        mbar_wait(&tile_empty[slot], ((c / kRing) & 1) ^ 1);
+        TileMsg m;
+        m.w = atomicAdd(p.tile_counter, 1);
+        if (m.w >= p.n_tiles) m.w = -1;
+        if (m.w >= 0) {
+          const int b = m.w / (p.n_m * p.H);
+          m.seq_start = p.cu_seqlens[b];
+          m.L = p.cu_seqlens[b + 1] - m.seq_start;
+          m.seqlen_c = p.num_contexts ? p.num_contexts[b] : 0;
+          m.num_t = p.num_targets ? p.num_targets[b] : 0;
+        }
+        const int w = m.w;
+        tile_ring[slot] = m;
+        mbar_arrive(&tile_full[slot]);               // release semantics: the store above is visible to the waiters
+        if (w < 0) break;
+      }
+    }
+  } else if (warp == 0 || warp == 3) {
     // ------------------------------------------------------------------ K (warp 0) / V (warp 3) producers
     if (elect_one()) {
       const CUtensorMap* map = warp == 0 ? &map_k : &map_v;
       uint8_t* ring = smem + (warp == 0 ? SM::kK : SM::kV);
       uint64_t* full = warp == 0 ? k_full : v_full;
       uint64_t* empty = warp == 0 ? k_empty : v_empty;
-      for (int j = 0; j < n_iter; ++j) {
-        const int st = j % S, ph = (j / S) & 1;
-        const int row = seq_start + (nb0 + j) * 128;
-        mbar_wait(&empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&full[st], SM::kTile);
+      int cursor = 0, c = 0;                         // c: running K / V tile count (ring slot and phase)
+      FwdTile t;
+      while (next_tile(cursor, t, true, false)) {
+        for (int j = 0; j < t.n_iter; ++j, ++c) {
+          const int st = c % S, ph = (c / S) & 1;
+          const int row = t.seq_start + (t.nb0 + j) * 128;
+          mbar_wait(&empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&full[st], SM::kTile);
 #pragma unroll
-        for (int hf = 0; hf < NH; ++hf) tma_load_3d(ring + st * SM::kTile + hf * 16384, map, &full[st], hf * 64, h, row);
+          for (int hf = 0; hf < NH; ++hf) tma_load_3d(ring + st * SM::kTile + hf * 16384, map, &full[st], hf * 64, t.h, row);
+        }
       }
     }
   } else if (warp == 1) {
@@ -138,43 +205,55 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
       int acc__[4] = {0, 0, 0, 0};
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, D, 0, 1);
-      auto issue_qk = [&](int j) {
-        const int st = j & 1;                              // S double buffer
-        const int ks = j % S, kph = (j / S) & 1;           // K ring
-        HSTU_T0();
-        mbar_wait(&k_full[ks], kph);
-        HSTU_ACC(0);
-        tc_fence_after();
-        const uint32_t aK = smem_u32(smem + SM::kK + ks * SM::kTile);
+      int cursor = 0, kc = 0, vc = 0, it = 0, tc = 0;   // running counts: K tiles issued, V tiles consumed, P tiles consumed, tiles
+      FwdTile t;
+      int n_total = 0;
+      while (next_tile(cursor, t, true, false)) {
+        n_total += t.n_iter;
+        auto issue_qk = [&](int sidx) {                  // sidx = running index of the score tile (S double buffer)
+          const int st = sidx & 1;
+          const int ks = kc % S, kph = (kc / S) & 1;       // K ring
+          HSTU_T0();
+          mbar_wait(&k_full[ks], kph);
+          HSTU_ACC(0);
+          tc_fence_after();
+          const uint32_t aK = smem_u32(smem + SM::kK + ks * SM::kTile);
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k)                   // A = Q from tensor memory: 16 k values = 8 packed columns per step
-          umma_ts(tS[st], tQ + k * 8, umma_desc_sw128(aK + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), idesc_qk, k > 0);
-        umma_commit(&s_full[st]);
-        umma_commit(&k_empty[ks]);
-      };
-      if (kProf && p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[8] = n_iter;
-      mbar_wait(&q_full, 0);
-      tc_fence_after();
-      issue_qk(0);
-      for (int j = 0; j < n_iter; ++j) {
-        // S_{j+1} goes to the other S buffer; its previous tenant P_{j-1} was consumed by P_{j-1} V_{j-1}, issued before this MMA
-        // (the tensor pipe executes one thread's MMAs in issue order), so no "S empty" barrier is needed
-        if (j + 1 < n_iter) issue_qk(j + 1);
-        const int st = j & 1, ph = (j >> 1) & 1;
-        const int vs = j % S, vph = (j / S) & 1;
-        HSTU_T0();
-        mbar_wait(&v_full[vs], vph);
-        HSTU_ACC(2);
-        mbar_wait(&p_full[st], ph);
-        HSTU_ACC(3);
+          for (int k = 0; k < D / 16; ++k)                   // A = Q from tensor memory: 16 k values = 8 packed columns per step
+            umma_ts(tS[st], tQ + k * 8, umma_desc_sw128(aK + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), idesc_qk, k > 0);
+          umma_commit(&s_full[st]);
+          umma_commit(&k_empty[ks]);
+          ++kc;
+        };
+        {
+          HSTU_T0();
+          mbar_wait(&q_full, tc & 1);                      // Q of this tile is in tensor memory (written after the previous tile's last S was read)
+          HSTU_ACC(1);
+        }
         tc_fence_after();
-        const uint32_t aV = smem_u32(smem + SM::kV + vs * SM::kTile);
+        issue_qk(it);
+        for (int j = 0; j < t.n_iter; ++j, ++it, ++vc) {
+          // S_{j+1} goes to the other S buffer; its previous tenant P_{j-1} was consumed by P_{j-1} V_{j-1}, issued before this MMA
+          // (the tensor pipe executes one thread's MMAs in issue order), so no "S empty" barrier is needed
+          if (j + 1 < t.n_iter) issue_qk(it + 1);
+          const int st = it & 1, ph = (it >> 1) & 1;
+          const int vs = vc % S, vph = (vc / S) & 1;
+          HSTU_T0();
+          mbar_wait(&v_full[vs], vph);
+          HSTU_ACC(2);
+          mbar_wait(&p_full[st], ph);                      // also: every SiLU warp has finished reading the previous tile's O
+          HSTU_ACC(3);
+          tc_fence_after();
+          const uint32_t aV = smem_u32(smem + SM::kV + vs * SM::kTile);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)                        // A = P_j: keys 0-63 packed in S columns 0-31, keys 64-127 in columns 64-95
-          umma_ts(tO, tS[st] + (k >> 2) * 64 + (k & 3) * 8, umma_desc_sw128(aV + k * 2048, 16384, 1024), idesc_pv, (j > 0 || k > 0));
-        umma_commit(&v_empty[vs]);
+          for (int k = 0; k < 8; ++k)                        // A = P_j: keys 0-63 packed in S columns 0-31, keys 64-127 in columns 64-95
+            umma_ts(tO, tS[st] + (k >> 2) * 64 + (k & 3) * 8, umma_desc_sw128(aV + k * 2048, 16384, 1024), idesc_pv, (j > 0 || k > 0));
+          umma_commit(&v_empty[vs]);
+        }
+        umma_commit(&o_full);
+        ++tc;
       }
-      umma_commit(&o_full);
+      if (kProf && p.dbg) { atomicAdd(const_cast<int*>(p.dbg) + 8, n_total); atomicAdd(const_cast<int*>(p.dbg) + 9, tc); }
       HSTU_FLUSH(40, 4);
     }
   } else if (warp >= 4) {
@@ -184,99 +263,137 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
     const int wq = warp & 3;                       // TMEM lane quadrant
     const int ch = (warp - 4) >> 2;                // column half
     const int rit = wq * 32 + lane;                // row in tile
-    const int row = r0 + rit;
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
-    {
-      // Q row -> tensor memory (each warpgroup packs half of the D columns): straight from global, 16-byte loads
-      const __nv_bfloat16* qrow = p.q + (int64_t)(seq_start + row) * p.q_t + (int64_t)h * p.q_h + ch * (D / 2);
+    const f32x2 ha2 = pack2(p.half_alpha, p.half_alpha);
+    int acc__[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_mark = kProf ? clock64() : 0;       // untracked-time accounting: 5 = between iterations, 6 = Q hand-over, 7 = tile fetch + setup
+#define HSTU_GAP(i) do { if (kProf) { long long t__g = clock64(); acc__[i] += (int)(t__g - t_mark); t_mark = t__g; } } while (0)
+#define HSTU_MARK() do { if (kProf) t_mark = clock64(); } while (0)
+    int cursor = 0, it = 0, tc = 0;
+    FwdTile t, tn;
+    uint4 qreg[D / 16];                            // this thread's half of the next tile's Q row (D/2 bf16)
+    auto q_load = [&](const FwdTile& tt) {         // issue the global loads (16-byte, straight from the strided q tensor)
+      const int row = tt.r0 + rit;
+      const __nv_bfloat16* qrow = p.q + (int64_t)(tt.seq_start + row) * p.q_t + (int64_t)tt.h * p.q_h + ch * (D / 2);
+#pragma unroll
+      for (int c = 0; c < D / 16; ++c) qreg[c] = row < tt.L ? ldg_nc_u4(qrow + c * 8) : make_uint4(0, 0, 0, 0);
+    };
+    auto q_store = [&]() {                         // registers -> packed tensor-memory columns, then signal the MMA thread
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
-        uint4 a = make_uint4(0, 0, 0, 0), bq = a;
-        if (row < L) { a = ldg_nc_u4(qrow + c * 16); bq = ldg_nc_u4(qrow + c * 16 + 8); }
-        const uint32_t r[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+        const uint32_t r[8] = {qreg[2 * c].x, qreg[2 * c].y, qreg[2 * c].z, qreg[2 * c].w, qreg[2 * c + 1].x, qreg[2 * c + 1].y, qreg[2 * c + 1].z, qreg[2 * c + 1].w};
         tmem_st8(tQ + lane_off + ch * (D / 4) + c * 8, r);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&q_full);
-    }
-    const Intervals iv = cols_of_row(mk, row);
-    const f32x2 ha2 = pack2(p.half_alpha, p.half_alpha);
-    int acc__[5] = {0, 0, 0, 0, 0};
-    for (int j = 0; j < n_iter; ++j) {
-      const int st = j & 1, ph = (j >> 1) & 1;
-      const int c_base = (nb0 + j) * 128 + ch * 64;
-      const bool full = mk.tile_full(r0, r1, c_base, c_base + 63);
-      const uint32_t t_s = tS[st] + lane_off + ch * 64;
-      HSTU_T0();
-      mbar_wait(&s_full[st], ph);
-      HSTU_ACC(0);
-      tc_fence_after();
-      // 16 score columns at a time (tcgen05.ld x16, the next chunk in flight while this one is in the SFU); packed chunk c (8 columns)
-      // overwrites S columns 8c..8c+7 of this warpgroup's half, which chunks <= c have already read.  The mask test is hoisted out of the
-      // tile: a per-pair `if (!full)` split the unrolled loop into 32 basic blocks and ptxas could not cover the MUFU latency.
-      auto tile = [&](auto masked_tag) {
-        constexpr bool kMasked = decltype(masked_tag)::value;
-        uint32_t sa[16], sb[16];
-        tmem_ld16(t_s, sa);
+    };
+    bool have = next_tile(cursor, t, lane == 0, true);
+    if (have) { q_load(t); q_store(); }
+    while (have) {
+      HSTU_MARK();
+      const bool have_next = next_tile(cursor, tn, lane == 0, true);     // known one tile ahead: its Q is fetched during the last iteration
+      const int row = t.r0 + rit;
+      const Intervals iv = cols_of_row(t.mk, row);
+      int c_base = t.nb0 * 128 + ch * 64;
+      bool full = t.mk.tile_full(t.r0, t.r1, c_base, c_base + 63);
+      for (int j = 0; j < t.n_iter; ++j, ++it) {
+        const int st = it & 1, ph = (it >> 1) & 1;
+        const uint32_t t_s = tS[st] + lane_off + ch * 64;
+        if (have_next && j == t.n_iter - 1) q_load(tn);
+        HSTU_GAP(j == 0 ? 7 : 5);
+        HSTU_T0();
+        mbar_wait(&s_full[st], ph);
+        HSTU_ACC(0);
+        tc_fence_after();
+        // 16 score columns at a time (tcgen05.ld x16, the next chunk in flight while this one is in the SFU); packed chunk c (8 columns)
+        // overwrites S columns 8c..8c+7 of this warpgroup's half, which chunks <= c have already read.  The mask test is hoisted out of the
+        // tile: a per-pair `if (!full)` split the unrolled loop into 32 basic blocks and ptxas could not cover the MUFU latency.
+        auto tile = [&](auto masked_tag) {
+          constexpr bool kMasked = decltype(masked_tag)::value;
+          uint32_t sa[16], sb[16];
+          tmem_ld16(t_s, sa);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t (&cur)[16] = (c & 1) ? sb : sa;
-          uint32_t (&nxt)[16] = (c & 1) ? sa : sb;
-          tmem_ld_wait();
-          if (c < 3) tmem_ld16(t_s + 16 * (c + 1), nxt);
-          f32x2 h2[8], t2[8];
+          for (int c = 0; c < 4; ++c) {
+            uint32_t (&cur)[16] = (c & 1) ? sb : sa;
+            uint32_t (&nxt)[16] = (c & 1) ? sa : sb;
+            tmem_ld_wait();
+            if (c < 3) tmem_ld16(t_s + 16 * (c + 1), nxt);
+            f32x2 h2[8], t2[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) h2[i] = mul2(pack2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])), ha2);   // h = alpha/2 s
+            for (int i = 0; i < 8; ++i) h2[i] = mul2(pack2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])), ha2);   // h = alpha/2 s
 #pragma unroll
-          for (int i = 0; i < 8; ++i) t2[i] = tanh2(h2[i]);
-          uint32_t pk[8];
+            for (int i = 0; i < 8; ++i) t2[i] = tanh2(h2[i]);
+            uint32_t pk[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            f32x2 p2 = fma2(h2[i], t2[i], h2[i]);                                      // silu(alpha s) = h + h tanh(h)
-            if (kMasked) {
-              const int col = c_base + c * 16 + 2 * i;
-              float p0, p1; unpack2(p2, p0, p1);
-              p2 = pack2(iv.has(col) ? p0 : 0.f, iv.has(col + 1) ? p1 : 0.f);
+            for (int i = 0; i < 8; ++i) {
+              f32x2 p2 = fma2(h2[i], t2[i], h2[i]);                                      // silu(alpha s) = h + h tanh(h)
+              if (kMasked) {
+                const int col = c_base + c * 16 + 2 * i;
+                float p0, p1; unpack2(p2, p0, p1);
+                p2 = pack2(iv.has(col) ? p0 : 0.f, iv.has(col + 1) ? p1 : 0.f);
+              }
+              pk[i] = pack_bf16x2_v(p2);
             }
-            pk[i] = pack_bf16x2_v(p2);
+            tmem_st8(t_s + c * 8, pk);
           }
-          tmem_st8(t_s + c * 8, pk);
-        }
-      };
-      if (full) tile(std::false_type{}); else tile(std::true_type{});
-      HSTU_ACC(2);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[st]);
-      HSTU_ACC(4);
-    }
-    if (threadIdx.x == 128) HSTU_FLUSH(48, 5);
-    // epilogue: each warpgroup stores half of the D output columns of its rows
-    mbar_wait(&o_full, 0);
-    tc_fence_after();
-    __nv_bfloat16* orow = p.out + ((int64_t)(seq_start + row) * p.H + h) * D;
+        };
+        if (full) tile(std::false_type{}); else tile(std::true_type{});
+        // next iteration's scalars, computed here (every PTX wrapper below is a compiler barrier: after the arrive they would sit on the
+        // critical path between two tiles)
+        c_base += 128;
+        full = t.mk.tile_full(t.r0, t.r1, c_base, c_base + 63);
+        HSTU_ACC(2);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[st]);
+        HSTU_ACC(4);
+        HSTU_MARK();
+      }
+      // every Q K^T of this tile has completed (its last S tile was read above): the next tile's Q may replace it now
+      if (have_next) q_store();
+      HSTU_GAP(6);
+      // epilogue: each warpgroup stores half of the D output columns of its rows.  The next tile's first P V (which overwrites O) waits
+      // for p_full, i.e. for all eight warps to be past this read-out: no "O empty" barrier.
+      const long long t_epi0 = kProf ? clock64() : 0;
+      {
+        HSTU_T0();
+        mbar_wait(&o_full, tc & 1);
+        HSTU_ACC(1);
+      }
+      tc_fence_after();
+      __nv_bfloat16* orow = p.out + ((int64_t)(t.seq_start + row) * p.H + t.h) * D;
 #pragma unroll
-    for (int cc = 0; cc < D / 64; ++cc) {
-      const int c = ch * (D / 2) + cc * 32;
-      uint32_t o[32];
-      tmem_ld32(tO + lane_off + c, o);
-      tmem_ld_wait();
-      if (row < L) {
+      for (int cc = 0; cc < D / 64; ++cc) {
+        const int c = ch * (D / 2) + cc * 32;
+        uint32_t o[32];
+        tmem_ld32(tO + lane_off + c, o);
+        tmem_ld_wait();
+        if (row < t.L) {
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(o[8 * q4 + 0]) * p.inv_scale, __uint_as_float(o[8 * q4 + 1]) * p.inv_scale);
-          v.y = pack_bf16x2(__uint_as_float(o[8 * q4 + 2]) * p.inv_scale, __uint_as_float(o[8 * q4 + 3]) * p.inv_scale);
-          v.z = pack_bf16x2(__uint_as_float(o[8 * q4 + 4]) * p.inv_scale, __uint_as_float(o[8 * q4 + 5]) * p.inv_scale);
-          v.w = pack_bf16x2(__uint_as_float(o[8 * q4 + 6]) * p.inv_scale, __uint_as_float(o[8 * q4 + 7]) * p.inv_scale);
-          *reinterpret_cast<uint4*>(orow + c + q4 * 8) = v;
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(o[8 * q4 + 0]) * p.inv_scale, __uint_as_float(o[8 * q4 + 1]) * p.inv_scale);
+            v.y = pack_bf16x2(__uint_as_float(o[8 * q4 + 2]) * p.inv_scale, __uint_as_float(o[8 * q4 + 3]) * p.inv_scale);
+            v.z = pack_bf16x2(__uint_as_float(o[8 * q4 + 4]) * p.inv_scale, __uint_as_float(o[8 * q4 + 5]) * p.inv_scale);
+            v.w = pack_bf16x2(__uint_as_float(o[8 * q4 + 6]) * p.inv_scale, __uint_as_float(o[8 * q4 + 7]) * p.inv_scale);
+            *reinterpret_cast<uint4*>(orow + c + q4 * 8) = v;
+          }
         }
       }
+      tc_fence_before();
+      {
+        if (kProf) acc__[3] += (int)(clock64() - t_epi0);   // o_full wait + O read-out + global stores
+      }
+      ++tc;
+      have = have_next;
+      if (have) t = tn;
     }
+    if (threadIdx.x == 128) HSTU_FLUSH(48, 9);
   }
+  if (kProf && threadIdx.x == 128 && p.dbg) atomicAdd(const_cast<int*>(p.dbg) + 10, (int)((clock64() - t_cta0) >> 4));
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<512>(tmem);
@@ -292,10 +409,26 @@ int launch_fwd(const CUtensorMap& mkk, const CUtensorMap& mv, const FwdParams& p
     if (e != cudaSuccess) return -(int)e;
     configured = true;
   }
-  dim3 grid((max_seqlen + 127) / 128, p.H, B);
-  if (p.dbg) hstu_fwd_kernel<D, true><<<grid, 384, smem, stream>>>(mkk, mv, p);
-  else hstu_fwd_kernel<D, false><<<grid, 384, smem, stream>>>(mkk, mv, p);
-  cudaError_t e = cudaGetLastError();
+  // tile counter: a small per-device pool, one slot per launch in rotation (launches on different streams never share a live slot)
+  static int* pool[16] = {nullptr};
+  static unsigned seq[16] = {0};
+  static int sms[16] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return HSTU_ERR_ARG;
+  if (!pool[dev]) {
+    if (cudaMalloc(&pool[dev], 64 * sizeof(int)) != cudaSuccess) return -(int)cudaGetLastError();
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  }
+  FwdParams q = p;
+  q.n_m = (max_seqlen + 127) / 128;
+  q.n_tiles = q.n_m * p.H * B;
+  q.tile_counter = pool[dev] + (seq[dev]++ & 63);
+  cudaError_t e = cudaMemsetAsync(q.tile_counter, 0, sizeof(int), stream);
+  if (e != cudaSuccess) return -(int)e;
+  const int grid = q.n_tiles < sms[dev] ? q.n_tiles : sms[dev];      // one persistent CTA per SM
+  if (p.dbg) hstu_fwd_kernel<D, true><<<grid, 384, smem, stream>>>(mkk, mv, q);
+  else hstu_fwd_kernel<D, false><<<grid, 384, smem, stream>>>(mkk, mv, q);
+  e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }
 

@@ -13,20 +13,33 @@ cu = torch.arange(0, T + 1, S, dtype=torch.int32, device=dev)
 a = 1 / math.sqrt(D)
 for _ in range(2): ops.hstu_varlen_fwd_100(q, k, v, cu, cu, S, S, None, None, 1, -1, 0, a)
 torch.cuda.synchronize()
-dbg = torch.zeros(128, dtype=torch.int32).pin_memory()
 N.lib.hstu_set_debug_buffer.argtypes = [ctypes.c_void_p]
-N.lib.hstu_set_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
 e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-e0.record(); ops.hstu_varlen_fwd_100(q, k, v, cu, cu, S, S, None, None, 1, -1, 0, a); e1.record(); torch.cuda.synchronize()
-N.lib.hstu_set_debug_buffer(None)
-d = dbg.tolist()
-n_iter = d[8]
-print(f"kernel {e0.elapsed_time(e1):.3f} ms; CTA0 iterations {n_iter}")
-names = {40: "mma: wait k_full", 41: "mma: wait s_empty", 42: "mma: wait v_full", 43: "mma: wait p_full", 48: "silu: wait s_full", 49: "silu: tmem ld + arrive",
-         50: "silu: math", 51: "silu: wait p_empty", 52: "silu: st.shared + fence + arrive"}
-for k_, nm in names.items():
-    print(f"  {nm:34s} {d[k_]:9d} cyc total  {d[k_] / max(n_iter, 1):8.0f} / iter")
-
+for Bf in (8, 32):
+    Tf = Bf * S
+    qf, kf, vf = (torch.randn(Tf, H, D, device=dev, dtype=torch.bfloat16) for _ in range(3))
+    cuf = torch.arange(0, Tf + 1, S, dtype=torch.int32, device=dev)
+    for _ in range(2): ops.hstu_varlen_fwd_100(qf, kf, vf, cuf, cuf, S, S, None, None, 1, -1, 0, a)
+    torch.cuda.synchronize()
+    e0.record(); ops.hstu_varlen_fwd_100(qf, kf, vf, cuf, cuf, S, S, None, None, 1, -1, 0, a); e1.record(); torch.cuda.synchronize()
+    t_prod = e0.elapsed_time(e1)
+    dbgd = torch.zeros(128, dtype=torch.int32, device=dev)          # device buffer: every CTA adds its counters (units of 16 cycles)
+    N.lib.hstu_set_debug_buffer(ctypes.c_void_p(dbgd.data_ptr()))
+    e0.record(); ops.hstu_varlen_fwd_100(qf, kf, vf, cuf, cuf, S, S, None, None, 1, -1, 0, a); e1.record(); torch.cuda.synchronize()
+    N.lib.hstu_set_debug_buffer(None)
+    d = [16 * x for x in dbgd.tolist()]
+    iters, ctas = d[8] // 16, d[9] // 16
+    print(f"forward B={Bf}: production kernel {t_prod:.3f} ms, accounting build {e0.elapsed_time(e1):.3f} ms; {ctas} CTAs, {iters} iterations ({iters / 148:.0f} per SM)")
+    print(f"  CTA lifetime {d[10] / ctas:9.0f} cyc avg = prologue {d[11] / ctas:.0f} + loop {(d[10] - d[11] - d[12]) / ctas:.0f} + epilogue {d[12] / ctas:.0f};"
+          f"  sum of lifetimes / 148 SMs = {d[10] / 148 / 1e6:.3f} Mcyc -> {d[10] / 148 / t_prod / 1e3:.0f} MHz if back to back")
+    names = {40: "mma: wait k_full", 42: "mma: wait v_full", 43: "mma: wait p_full", 48: "silu: wait s_full", 50: "silu: ld + math + st", 52: "silu: fence + arrive"}
+    for k_, nm in names.items():
+        print(f"  {nm:34s} {d[k_] / iters:8.0f} cyc / iteration")
+    for k_, nm in {41: "mma: wait q_full", 49: "silu: wait o_full", 51: "silu: o_full wait + O read-out + stores", 53: "silu: between iterations (sum)", 54: "silu: Q hand-over", 55: "silu: tile fetch + setup"}.items():
+        print(f"  {nm:34s} {d[k_] / ctas:8.0f} cyc / tile")
+    print(f"  per tile: {iters / ctas:.1f} iterations x {(d[48] + d[50] + d[52]) / iters:.0f} = {(d[48] + d[50] + d[52]) / ctas:.0f} cyc in the SiLU loop, tile period {d[10] / ctas:.0f}")
+    del qf, kf, vf
+dbg = torch.zeros(128, dtype=torch.int32).pin_memory()
 # ---- backward: dKV kernel slots 64.., dQ kernel slots 96..
 do = torch.randn_like(q)
 for _ in range(2): ops.hstu_varlen_bwd_100(do, q, k, v, cu, cu, S, S, None, None, None, None, None, 1, -1, 0, a)
