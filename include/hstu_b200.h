@@ -39,6 +39,11 @@ int hstu_bwd_sm100(const void* dout, const void* q, const void* k, const void* v
 
 /* development aid: one-CTA tcgen05 GEMM that pins the descriptor conventions (csrc/sm100_probe.cu) */
 int sm100_probe_gemm(const void* A, const void* B, float* C, int variant, const uint32_t* overrides, void* stream);
+/* development aid: install (or clear with NULL) a cycle-accounting buffer of 128 int32.  While installed, hstu_fwd_sm100 runs its
+   instrumented instantiation and adds per-role wait / work cycle counts of every CTA to the buffer (DEVICE memory, zeroed by the
+   caller); hstu_bwd_sm100 stores the counts of CTA (0,0,0) (device or host-mapped memory).  tools/hstu_cycles.py prints them.
+   Never installed on the product path. */
+int hstu_set_debug_buffer(int* buffer);
 
 #ifdef __cplusplus
 }
