@@ -110,25 +110,25 @@ __device__ __forceinline__ bool decode_tile(const FwdParams& p, const TileMsg& m
 // tensor pipe idle).  Across tile boundaries the K / V producers keep prefetching, the MMA thread issues Q K^T of the next tile as
 // soon as its Q is in tensor memory, and only the O read-out of the SiLU warps is exposed.
 template <int D, bool kProf>
-__global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, FwdParams p) {
+__global__ void __launch_bounds__(512, 1) hstu_fwd_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, FwdParams p) {
   using SM = FwdSmem<D>;
   constexpr int NH = D / 64;                         // 64-column (128-byte) halves per tile row
   constexpr int S = SM::kStages;
-  constexpr int kRing = 4;                           // tile-id ring between the scheduler thread and the 11 consumers
+  constexpr int kRing = 4;                           // tile ring between the scheduler thread and the 15 consumers (K, V, MMA, 8 SiLU warps, 4 I/O warps)
   const long long t_cta0 = kProf ? clock64() : 0;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t q_full, k_full[S], k_empty[S], v_full[S], v_empty[S], s_full[2], p_full[2], o_full, tile_full[kRing], tile_empty[kRing];
+  __shared__ uint64_t q_full[2], k_full[S], k_empty[S], v_full[S], v_empty[S], s_full[2], p_full[2], o_full, o_empty, tile_full[kRing], tile_empty[kRing];
   __shared__ TileMsg tile_ring[kRing];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(&q_full, 8); mbar_init(&o_full, 1);
+    mbar_init(&q_full[0], 4); mbar_init(&q_full[1], 4); mbar_init(&o_full, 1); mbar_init(&o_empty, 4);
     for (int i = 0; i < S; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); }
-    for (int i = 0; i < kRing; ++i) { mbar_init(&tile_full[i], 1); mbar_init(&tile_empty[i], 11); }
+    for (int i = 0; i < kRing; ++i) { mbar_init(&tile_full[i], 1); mbar_init(&tile_empty[i], 15); }
     fence_barrier_init();
     tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
   }
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
   const uint32_t tmem = tmem_base_s;
   const uint32_t tS[2] = {tmem, tmem + 128};
   const uint32_t tO = tmem + 256;
-  const uint32_t tQ = tmem + 384;                    // Q tile, bf16x2 packed: D / 2 columns
+  const uint32_t tQ[2] = {tmem + 384, tmem + 448};   // Q tiles, bf16x2 packed (D / 2 columns), double-buffered across tiles
 
   // every consumer walks the ring with its own cursor; returns the next tile that exists (skipping tiles past the end of their
   // sequence) or false when the scheduler has published the end marker
@@ -220,14 +220,14 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
           const uint32_t aK = smem_u32(smem + SM::kK + ks * SM::kTile);
 #pragma unroll
           for (int k = 0; k < D / 16; ++k)                   // A = Q from tensor memory: 16 k values = 8 packed columns per step
-            umma_ts(tS[st], tQ + k * 8, umma_desc_sw128(aK + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), idesc_qk, k > 0);
+            umma_ts(tS[st], tQ[tc & 1] + k * 8, umma_desc_sw128(aK + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), idesc_qk, k > 0);
           umma_commit(&s_full[st]);
           umma_commit(&k_empty[ks]);
           ++kc;
         };
         {
           HSTU_T0();
-          mbar_wait(&q_full, tc & 1);                      // Q of this tile is in tensor memory (written after the previous tile's last S was read)
+          mbar_wait(&q_full[tc & 1], (tc >> 1) & 1);       // Q of this tile is in tensor memory (written by the I/O warpgroup one tile ahead)
           HSTU_ACC(1);
         }
         tc_fence_after();
@@ -241,8 +241,9 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
           HSTU_T0();
           mbar_wait(&v_full[vs], vph);
           HSTU_ACC(2);
-          mbar_wait(&p_full[st], ph);                      // also: every SiLU warp has finished reading the previous tile's O
+          mbar_wait(&p_full[st], ph);
           HSTU_ACC(3);
+          if (j == 0 && tc > 0) mbar_wait(&o_empty, (tc - 1) & 1);   // the I/O warpgroup has pulled the previous tile's O into registers
           tc_fence_after();
           const uint32_t aV = smem_u32(smem + SM::kV + vs * SM::kTile);
 #pragma unroll
@@ -256,6 +257,74 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
       if (kProf && p.dbg) { atomicAdd(const_cast<int*>(p.dbg) + 8, n_total); atomicAdd(const_cast<int*>(p.dbg) + 9, tc); }
       HSTU_FLUSH(40, 4);
     }
+  } else if (warp >= 12) {
+    // ------------------------------------------------------------------ tile I/O warpgroup (warps 12-15, one per TMEM lane quadrant)
+    // Keeps everything that happens once per tile OFF the SiLU warps' critical path (measured there: O read-out 3400 cycles, Q hand-over
+    // 1500, per 16.5 iterations of 1250): packs the NEXT tile's Q rows into the other Q buffer, then reads the finished O accumulator,
+    // hands it back (o_empty) and stores it.  thread = row.
+    const int wq = warp & 3;
+    const int rit = wq * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    int acc__[4] = {0, 0, 0, 0};
+    int cursor = 0, tc = 0;
+    FwdTile t, tn;
+    auto q_put = [&](const FwdTile& tt, int buf) {   // whole row of D bf16 -> D/2 packed columns, then signal the MMA thread
+      const int row = tt.r0 + rit;
+      const __nv_bfloat16* qrow = p.q + (int64_t)(tt.seq_start + row) * p.q_t + (int64_t)tt.h * p.q_h;
+      uint4 qreg[D / 8];
+#pragma unroll
+      for (int c = 0; c < D / 8; ++c) qreg[c] = row < tt.L ? ldg_nc_u4(qrow + c * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int c = 0; c < D / 16; ++c) {
+        const uint32_t r[8] = {qreg[2 * c].x, qreg[2 * c].y, qreg[2 * c].z, qreg[2 * c].w, qreg[2 * c + 1].x, qreg[2 * c + 1].y, qreg[2 * c + 1].z, qreg[2 * c + 1].w};
+        tmem_st8(tQ[buf] + lane_off + c * 8, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_full[buf]);
+    };
+    bool have = next_tile(cursor, t, lane == 0, true);
+    if (have) q_put(t, 0);
+    while (have) {
+      const bool have_next = next_tile(cursor, tn, lane == 0, true);
+      // buffer (tc+1)&1 last held the Q of tile tc-1, whose MMAs all completed before its o_full, which this warp waited for below
+      if (have_next) q_put(tn, (tc + 1) & 1);
+      const int row = t.r0 + rit;
+      HSTU_T0();
+      mbar_wait(&o_full, tc & 1);
+      HSTU_ACC(0);
+      tc_fence_after();
+      __nv_bfloat16* orow = p.out + ((int64_t)(t.seq_start + row) * p.H + t.h) * D;
+#pragma unroll
+      for (int half = 0; half < D / 64; ++half) {
+        uint32_t o[64];
+        tmem_ld32(tO + lane_off + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+        tmem_ld32(tO + lane_off + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+        tmem_ld_wait();
+        if (half == D / 64 - 1) {                    // O is in registers: the next tile's first P V may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&o_empty);
+        }
+        if (row < t.L) {
+#pragma unroll
+          for (int q8 = 0; q8 < 8; ++q8) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(o[8 * q8 + 0]) * p.inv_scale, __uint_as_float(o[8 * q8 + 1]) * p.inv_scale);
+            v.y = pack_bf16x2(__uint_as_float(o[8 * q8 + 2]) * p.inv_scale, __uint_as_float(o[8 * q8 + 3]) * p.inv_scale);
+            v.z = pack_bf16x2(__uint_as_float(o[8 * q8 + 4]) * p.inv_scale, __uint_as_float(o[8 * q8 + 5]) * p.inv_scale);
+            v.w = pack_bf16x2(__uint_as_float(o[8 * q8 + 6]) * p.inv_scale, __uint_as_float(o[8 * q8 + 7]) * p.inv_scale);
+            *reinterpret_cast<uint4*>(orow + half * 64 + q8 * 8) = v;
+          }
+        }
+      }
+      HSTU_ACC(1);
+      ++tc;
+      have = have_next;
+      if (have) t = tn;
+    }
+    if (threadIdx.x == 384) HSTU_FLUSH(56, 2);
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ SiLU warpgroups + epilogue
     // two SiLU warpgroups split the 128 score columns of every tile (warps 4-7: columns 0-63, warps 8-11: columns 64-127) so
@@ -270,30 +339,9 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
 #define HSTU_GAP(i) do { if (kProf) { long long t__g = clock64(); acc__[i] += (int)(t__g - t_mark); t_mark = t__g; } } while (0)
 #define HSTU_MARK() do { if (kProf) t_mark = clock64(); } while (0)
     int cursor = 0, it = 0, tc = 0;
-    FwdTile t, tn;
-    uint4 qreg[D / 16];                            // this thread's half of the next tile's Q row (D/2 bf16)
-    auto q_load = [&](const FwdTile& tt) {         // issue the global loads (16-byte, straight from the strided q tensor)
-      const int row = tt.r0 + rit;
-      const __nv_bfloat16* qrow = p.q + (int64_t)(tt.seq_start + row) * p.q_t + (int64_t)tt.h * p.q_h + ch * (D / 2);
-#pragma unroll
-      for (int c = 0; c < D / 16; ++c) qreg[c] = row < tt.L ? ldg_nc_u4(qrow + c * 8) : make_uint4(0, 0, 0, 0);
-    };
-    auto q_store = [&]() {                         // registers -> packed tensor-memory columns, then signal the MMA thread
-#pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
-        const uint32_t r[8] = {qreg[2 * c].x, qreg[2 * c].y, qreg[2 * c].z, qreg[2 * c].w, qreg[2 * c + 1].x, qreg[2 * c + 1].y, qreg[2 * c + 1].z, qreg[2 * c + 1].w};
-        tmem_st8(tQ + lane_off + ch * (D / 4) + c * 8, r);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&q_full);
-    };
-    bool have = next_tile(cursor, t, lane == 0, true);
-    if (have) { q_load(t); q_store(); }
-    while (have) {
-      HSTU_MARK();
-      const bool have_next = next_tile(cursor, tn, lane == 0, true);     // known one tile ahead: its Q is fetched during the last iteration
+    FwdTile t;
+    HSTU_MARK();
+    while (next_tile(cursor, t, lane == 0, true)) {
       const int row = t.r0 + rit;
       const Intervals iv = cols_of_row(t.mk, row);
       int c_base = t.nb0 * 128 + ch * 64;
@@ -301,7 +349,6 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
       for (int j = 0; j < t.n_iter; ++j, ++it) {
         const int st = it & 1, ph = (it >> 1) & 1;
         const uint32_t t_s = tS[st] + lane_off + ch * 64;
-        if (have_next && j == t.n_iter - 1) q_load(tn);
         HSTU_GAP(j == 0 ? 7 : 5);
         HSTU_T0();
         mbar_wait(&s_full[st], ph);
@@ -352,44 +399,6 @@ __global__ void __launch_bounds__(384, 1) hstu_fwd_kernel(const __grid_constant_
         HSTU_ACC(4);
         HSTU_MARK();
       }
-      // every Q K^T of this tile has completed (its last S tile was read above): the next tile's Q may replace it now
-      if (have_next) q_store();
-      HSTU_GAP(6);
-      // epilogue: each warpgroup stores half of the D output columns of its rows.  The next tile's first P V (which overwrites O) waits
-      // for p_full, i.e. for all eight warps to be past this read-out: no "O empty" barrier.
-      const long long t_epi0 = kProf ? clock64() : 0;
-      {
-        HSTU_T0();
-        mbar_wait(&o_full, tc & 1);
-        HSTU_ACC(1);
-      }
-      tc_fence_after();
-      __nv_bfloat16* orow = p.out + ((int64_t)(t.seq_start + row) * p.H + t.h) * D;
-#pragma unroll
-      for (int cc = 0; cc < D / 64; ++cc) {
-        const int c = ch * (D / 2) + cc * 32;
-        uint32_t o[32];
-        tmem_ld32(tO + lane_off + c, o);
-        tmem_ld_wait();
-        if (row < t.L) {
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint4 v;
-            v.x = pack_bf16x2(__uint_as_float(o[8 * q4 + 0]) * p.inv_scale, __uint_as_float(o[8 * q4 + 1]) * p.inv_scale);
-            v.y = pack_bf16x2(__uint_as_float(o[8 * q4 + 2]) * p.inv_scale, __uint_as_float(o[8 * q4 + 3]) * p.inv_scale);
-            v.z = pack_bf16x2(__uint_as_float(o[8 * q4 + 4]) * p.inv_scale, __uint_as_float(o[8 * q4 + 5]) * p.inv_scale);
-            v.w = pack_bf16x2(__uint_as_float(o[8 * q4 + 6]) * p.inv_scale, __uint_as_float(o[8 * q4 + 7]) * p.inv_scale);
-            *reinterpret_cast<uint4*>(orow + c + q4 * 8) = v;
-          }
-        }
-      }
-      tc_fence_before();
-      {
-        if (kProf) acc__[3] += (int)(clock64() - t_epi0);   // o_full wait + O read-out + global stores
-      }
-      ++tc;
-      have = have_next;
-      if (have) t = tn;
     }
     if (threadIdx.x == 128) HSTU_FLUSH(48, 9);
   }
@@ -426,8 +435,8 @@ int launch_fwd(const CUtensorMap& mkk, const CUtensorMap& mv, const FwdParams& p
   cudaError_t e = cudaMemsetAsync(q.tile_counter, 0, sizeof(int), stream);
   if (e != cudaSuccess) return -(int)e;
   const int grid = q.n_tiles < sms[dev] ? q.n_tiles : sms[dev];      // one persistent CTA per SM
-  if (p.dbg) hstu_fwd_kernel<D, true><<<grid, 384, smem, stream>>>(mkk, mv, q);
-  else hstu_fwd_kernel<D, false><<<grid, 384, smem, stream>>>(mkk, mv, q);
+  if (p.dbg) hstu_fwd_kernel<D, true><<<grid, 512, smem, stream>>>(mkk, mv, q);
+  else hstu_fwd_kernel<D, false><<<grid, 512, smem, stream>>>(mkk, mv, q);
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }

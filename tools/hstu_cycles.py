@@ -35,7 +35,7 @@ for Bf in (8, 32):
     names = {40: "mma: wait k_full", 42: "mma: wait v_full", 43: "mma: wait p_full", 48: "silu: wait s_full", 50: "silu: ld + math + st", 52: "silu: fence + arrive"}
     for k_, nm in names.items():
         print(f"  {nm:34s} {d[k_] / iters:8.0f} cyc / iteration")
-    for k_, nm in {41: "mma: wait q_full", 49: "silu: wait o_full", 51: "silu: o_full wait + O read-out + stores", 53: "silu: between iterations (sum)", 54: "silu: Q hand-over", 55: "silu: tile fetch + setup"}.items():
+    for k_, nm in {41: "mma: wait q_full", 53: "silu: between iterations (sum)", 55: "silu: tile fetch + setup", 56: "io: wait o_full", 57: "io: O read-out + stores"}.items():
         print(f"  {nm:34s} {d[k_] / ctas:8.0f} cyc / tile")
     print(f"  per tile: {iters / ctas:.1f} iterations x {(d[48] + d[50] + d[52]) / iters:.0f} = {(d[48] + d[50] + d[52]) / ctas:.0f} cyc in the SiLU loop, tile period {d[10] / ctas:.0f}")
     del qf, kf, vf
