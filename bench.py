@@ -201,6 +201,34 @@ def bench_hstu(dev, tflops_peak, iters=10):
             ms = sorted(ts)[len(ts) // 10]            # P10 like hstu_attn_kernel_benchmark.py
             res[name] = {"ms": ms, "tflops": fl / ms / 1e9, "frac_of_bf16_peak": fl / ms / 1e9 / tflops_peak}
         res["samples_per_s_attn_only_8_layers"] = B / ((res["fwd"]["ms"] + res["bwd"]["ms"]) * 8 / 1e3)
+        # SURVEY 8(d) config 3, profile (ii): jagged lengths, Zipf alpha 1.2 in [1, 4096] (examples/commons/datasets/hstu_batch.py:156-170, numpy
+        # fallback branch), seed 1234; and the uniform profile with 256 targets per sequence (group size 1)
+        lens = np.clip(np.random.default_rng(1234).zipf(1.2, size=B), 1, S).astype(np.int64)
+        cuj = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device=dev)
+        Tj = int(lens.sum())
+        fl_j = float(2.0 * H * Dh * (lens.astype(np.float64) ** 2).sum())
+        nt = torch.full((B,), 256, dtype=torch.int32, device=dev)
+        variants = {"jagged_zipf1.2": (lambda: ops.hstu_varlen_fwd_100(q[:Tj], k[:Tj], v[:Tj], cuj, cuj, S, S, None, None, 1, -1, 0, alpha),
+                                       lambda: ops.hstu_varlen_bwd_100(dout[:Tj], q[:Tj], k[:Tj], v[:Tj], cuj, cuj, S, S, None, None, None, None, None, 1, -1, 0, alpha), fl_j),
+                    "uniform_256_targets": (lambda: ops.hstu_varlen_fwd_100(q, k, v, cu, cu, S, S, None, nt, 1, -1, 0, alpha),
+                                            lambda: ops.hstu_varlen_bwd_100(dout, q, k, v, cu, cu, S, S, None, None, None, None, nt, 1, -1, 0, alpha), None)}
+        for vn, (f_fwd, f_bwd, fl) in variants.items():
+            out_v = {}
+            for name, f in (("fwd", f_fwd), ("bwd", f_bwd)):
+                for _ in range(2):
+                    f()
+                torch.cuda.synchronize()
+                ts = []
+                for _ in range(5):
+                    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+                    e0.record(); f(); e1.record(); torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                out_v[name + "_ms"] = min(ts)
+                if fl is not None:
+                    out_v[name + "_tflops"] = fl * (1.0 if name == "fwd" else 2.5) / min(ts) / 1e9
+            if vn.startswith("jagged"):
+                out_v["tokens"] = Tj
+            res[vn] = out_v
         res["config"] = "B=32 S=4096 causal H=8 D=128 bf16, q/k/v strided views of one (T, 4HD) buffer"
         return res
     except Exception as e:  # report, never kill the embedding line
