@@ -1,0 +1,181 @@
+"""GPU, BASELINE.json's full sizes: size-independent properties instead of an oracle replay (the CPU oracle cannot finish 2^20 ids or
+B=32 x S=4096 attention in seconds) — round trips, idempotence, linearity, causality, checksums against plain torch ops, and, when the
+staged reference kernels are present (baseline/_ref/, travels with the snapshot, never /root/reference), agreement with the reference's
+own Blackwell HSTU kernels on the identical inputs."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+D = 128
+N_IDS = 1 << 20
+
+
+def _power_law(n, gen, dev, lo=1.0, hi=1e9, alpha=1.05):
+    y = torch.rand(n, generator=gen, device=dev, dtype=torch.float64)
+    g = 1.0 - alpha
+    x = ((hi ** g - lo ** g) * y + lo ** g) ** (1.0 / g)
+    return x.to(torch.int64)
+
+
+def test_unique_roundtrip_full_size(cuda):
+    from dynamicemb import dynamicemb_extensions as ext
+    gen = torch.Generator(device=cuda).manual_seed(7)
+    ids = _power_law(N_IDS, gen, cuda)
+    trange = torch.tensor([0, N_IDS], dtype=torch.int64, device=cuda)
+    num, uk, rev, toffs, _ = ext.segmented_unique_cuda(ids, trange, 1, None)
+    nu = int(num.item())
+    tu = torch.unique(ids)
+    assert nu == tu.numel() and int(toffs[1]) == nu
+    assert torch.equal(uk[:nu][rev], ids)                                   # round trip
+    assert torch.equal(torch.sort(uk[:nu]).values, tu)                      # same key set
+    first = torch.full((nu,), N_IDS, dtype=torch.int64, device=cuda).scatter_reduce_(0, rev, torch.arange(N_IDS, device=cuda), "amin")
+    assert bool((first[1:] > first[:-1]).all())                             # first-occurrence order
+    num2, uk2, rev2, _, _ = ext.segmented_unique_cuda(ids, trange, 1, None)  # idempotent / deterministic
+    assert torch.equal(uk2[:nu], uk[:nu]) and torch.equal(rev2, rev)
+
+
+def test_table_insert_lookup_idempotent_full_size(cuda):
+    from dynamicemb.scored_hashtable import LinearBucketTable, ScoreArg, ScoreSpec
+    from dynamicemb.dynamicemb_extensions import ScorePolicy
+    gen = torch.Generator(device=cuda).manual_seed(8)
+    keys = torch.unique(_power_law(N_IDS, gen, cuda))
+    n = keys.numel()
+    t = LinearBucketTable([4 * 1024 * 1024], [ScoreSpec("s", ScorePolicy.ASSIGN)], bucket_capacity=128, device=cuda)
+    z = torch.zeros(n, dtype=torch.int64, device=cuda)
+    ones = torch.ones(n, dtype=torch.int64, device=cuda)
+    slots = t.insert(keys, z, ScoreArg("s", ones, ScorePolicy.ASSIGN))
+    assert bool((slots >= 0).all()) and t.size() == n
+    assert torch.unique(slots).numel() == n                                 # one slot per key
+    _, found, idx = t.lookup(keys, z, ScoreArg("s", None, ScorePolicy.CONST))
+    assert bool(found.all()) and torch.equal(idx, slots)                    # encode -> decode
+    _, found2, idx2 = t.lookup(keys.flip(0), z, ScoreArg("s", None, ScorePolicy.CONST))
+    assert torch.equal(idx2.flip(0), slots)                                 # independent of presentation order
+    slots_again = t.insert(keys, z, ScoreArg("s", ones, ScorePolicy.ASSIGN))
+    assert torch.equal(slots_again, slots) and t.size() == n                # idempotent
+    # the key image really holds the keys at those slots
+    flat_keys = t.keys_.view(torch.int64).reshape(-1)
+    assert torch.equal(flat_keys[slots], keys)
+    half = keys[: n // 2]
+    t.erase(half, z[: n // 2])
+    _, f3, _ = t.lookup(keys, z, ScoreArg("s", None, ScorePolicy.CONST))
+    assert int(f3.sum()) == n - n // 2 and not bool(f3[: n // 2].any())     # erasures
+
+
+def _module(cuda, cap, opt):
+    from dynamicemb import (BatchedDynamicEmbeddingTablesV2, DynamicEmbInitializerArgs, DynamicEmbInitializerMode, DynamicEmbPoolingMode,
+                            DynamicEmbScoreStrategy, DynamicEmbTableOptions)
+    o = DynamicEmbTableOptions(dim=D, max_capacity=cap, local_hbm_for_values=1 << 50, score_strategy=DynamicEmbScoreStrategy.STEP,
+                               initializer_args=DynamicEmbInitializerArgs(mode=DynamicEmbInitializerMode.UNIFORM, lower=-0.01, upper=0.01))
+    return BatchedDynamicEmbeddingTablesV2([o], table_names=["t"], pooling_mode=DynamicEmbPoolingMode.NONE, optimizer=opt, learning_rate=0.5, device=cuda)
+
+
+def test_training_step_linearity_and_gather_checksum_full_size(cuda):
+    """forward = pure copy of the table rows (bit-exact against torch indexing); SGD update = -lr * (sum of the gradient rows of a key)."""
+    from dynamicemb import EmbOptimType
+    from dynamicemb.scored_hashtable import ScoreArg
+    from dynamicemb.dynamicemb_extensions import ScorePolicy
+    m = _module(cuda, 4 * 1024 * 1024, EmbOptimType.EXACT_SGD)
+    m.train()
+    gen = torch.Generator(device=cuda).manual_seed(9)
+    ids = _power_law(N_IDS, gen, cuda)
+    offsets = torch.arange(0, N_IDS + 1, dtype=torch.int64, device=cuda)
+    out = m(ids, offsets)
+    z = torch.zeros(N_IDS, dtype=torch.int64, device=cuda)
+    _, found, slots = m.tables.lookup(ids, z, ScoreArg("score", None, ScorePolicy.CONST))
+    assert bool(found.all())                                                # every id was inserted by the prefetch
+    before = m._values[:, :D].clone()
+    assert torch.equal(out.detach(), before[slots])                         # gather checksum, bit exact
+    grad = torch.randn(N_IDS, D, generator=gen, device=cuda)
+    out.backward(grad)
+    after = m._values[:, :D]
+    want = torch.zeros_like(before, dtype=torch.float64).index_add_(0, slots, grad.double())
+    delta = (after.double() - before.double())
+    # linear in the summed gradient.  The kernel sums in fp32 (fixed order); a Zipf-hot key sums ~1e5 rows, so the bound is relative to
+    # the sum of magnitudes of the key's gradient rows, not to the (possibly cancelling) result
+    absum = torch.zeros_like(before, dtype=torch.float64).index_add_(0, slots, grad.double().abs())
+    assert bool(((delta + 0.5 * want).abs() <= 0.5 * 4e-6 * absum + 1e-7).all())
+    touched = torch.zeros(before.shape[0], dtype=torch.bool, device=cuda)
+    touched[slots] = True
+    assert torch.equal(after[~touched], before[~touched])                   # nothing else moved
+    m.eval()
+    out2 = m(ids, offsets)
+    assert torch.equal(out2, after[slots])                                  # eval path (fused probe + gather) reads the same rows
+
+
+def _hstu_inputs(cuda, B, S, H, seed):
+    g = torch.Generator(device=cuda).manual_seed(seed)
+    T = B * S
+    buf = torch.randn(T, 4 * H * D, generator=g, device=cuda, dtype=torch.float32).to(torch.bfloat16)
+    _, v, q, k = (t.view(T, H, D) for t in buf.split(H * D, dim=-1))
+    dout = torch.randn(T, H, D, generator=g, device=cuda, dtype=torch.float32).to(torch.bfloat16)
+    cu = torch.arange(0, T + 1, S, dtype=torch.int32, device=cuda)
+    return q, k, v, dout, cu
+
+
+def test_hstu_full_size_causality_and_linearity(cuda):
+    from hstu import hstu_ops_gpu as ops
+    B, S, H = 32, 4096, 8
+    q, k, v, dout, cu = _hstu_inputs(cuda, B, S, H, 3)
+    a = 1 / math.sqrt(D)
+    out, _ = ops.hstu_varlen_fwd_100(q, k, v, cu, cu, S, S, None, None, 1, -1, 0, a)
+    assert bool(torch.isfinite(out.float()).all())
+    # causality: perturbing the LAST key/value of every sequence changes only the last query's output — every other row bit-identical
+    k2, v2 = k.clone(), v.clone()
+    last = torch.arange(S - 1, B * S, S, device=cuda)
+    k2[last] = -k2[last]; v2[last] = v2[last] * 2
+    out2, _ = ops.hstu_varlen_fwd_100(q, k2, v2, cu, cu, S, S, None, None, 1, -1, 0, a)
+    keep = torch.ones(B * S, dtype=torch.bool, device=cuda); keep[last] = False
+    assert torch.equal(out[keep], out2[keep])
+    assert not torch.equal(out[last], out2[last])
+    # sequences are independent: sequence 0 alone gives the same rows
+    cu1 = cu[:2].contiguous()
+    out_s0, _ = ops.hstu_varlen_fwd_100(q[:S], k[:S], v[:S], cu1, cu1, S, S, None, None, 1, -1, 0, a)
+    assert torch.equal(out_s0, out[:S])
+    # linearity in V (P does not depend on V): O(2V) = 2 O(V) exactly in bf16 (power-of-two scale)
+    out3, _ = ops.hstu_varlen_fwd_100(q, k, v * 2, cu, cu, S, S, None, None, 1, -1, 0, a)
+    assert torch.equal(out3.float(), out.float() * 2)
+    # determinism of the backward (no atomics, no workspace): two runs are bit-identical
+    g1 = ops.hstu_varlen_bwd_100(dout, q, k, v, cu, cu, S, S, None, None, None, None, None, 1, -1, 0, a)
+    g2 = ops.hstu_varlen_bwd_100(dout, q, k, v, cu, cu, S, S, None, None, None, None, None, 1, -1, 0, a)
+    for x, y in zip(g1[:3], g2[:3]):
+        assert torch.equal(x, y) and bool(torch.isfinite(x.float()).all())
+    # dV is linear in dO: dV(2 dO) = 2 dV(dO)
+    g3 = ops.hstu_varlen_bwd_100(dout * 2, q, k, v, cu, cu, S, S, None, None, None, None, None, 1, -1, 0, a)
+    assert torch.equal(g3[2].float(), g1[2].float() * 2)
+
+
+def test_hstu_full_size_matches_reference_blackwell_kernels(cuda):
+    """Same inputs through the reference's own CuTe-DSL sm100 kernels (staged copy under baseline/_ref, JIT on first call)."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "hstu_blackwell")):
+        pytest.skip("reference kernels not staged (baseline/fetch_ref_hstu.sh)")
+    sys.path.insert(0, ref_dir)
+    try:
+        from hstu_blackwell import hstu_ops_gpu as ref_ops
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"reference kernels not importable here: {e!r}"[:200])
+    from hstu import hstu_ops_gpu as ops
+    B, S, H = 32, 4096, 8
+    q, k, v, dout, cu = _hstu_inputs(cuda, B, S, H, 4)
+    a = 1 / math.sqrt(D)
+    out, _ = ops.hstu_varlen_fwd_100(q, k, v, cu, cu, S, S, None, None, 1, -1, 0, a)
+    r = ref_ops.hstu_varlen_fwd_100(q, k, v, cu, cu, S, S, None, None, 1, -1, 0, a, None, None)
+    ref_out = r[0] if isinstance(r, (tuple, list)) else r
+    torch.cuda.synchronize()
+    # both are bf16 roundings of the same fp32 sum: one ulp at the output scale (|O| < 0.06 here -> ulp 2.4e-4)
+    assert (out.float() - ref_out.float()).abs().max().item() <= 5e-4
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()      # the reference bwd rejects the strided uvqk views ("stride_order")
+    dq, dk, dv, _ = ops.hstu_varlen_bwd_100(dout, q, k, v, cu, cu, S, S, None, None, None, None, None, 1, -1, 0, a)
+    rb = ref_ops.hstu_varlen_bwd_100(dout, q, k, v, cu, cu, S, S, None, None, None, None, None, 1, -1, 0, a, None, False, None, False)
+    torch.cuda.synchronize()
+    rq, rk, rv = rb[0], rb[1], rb[2]
+    for nm, x, y in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
+        err = (x.float() - y.float()).abs().max().item()
+        scale = y.float().abs().max().item()
+        assert err <= 2e-2 * scale + 1e-6, f"{nm}: {err} vs scale {scale}"
