@@ -128,22 +128,25 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
   // TMEM columns: X1 @0, X2 @64 (bf16x2 packed stationary operands, D/2 columns each); acc0 @128 (dV | dQ); then
   //   dKV: acc1 @256 (dK), S^T @384, dP^T @448 — single buffers: the SiLU warps pull a tile into registers and hand it straight back
   //   dQ : S[2] @256,320, dP[2] @384,448 — double buffers: dS is written back over dP and stays there until dQ += dS K has read it
+  // Buffers and barriers are addressed arithmetically (tS0 + sb * 64, a_s_full + sb * 8): see hstu_fwd.cu.
   const uint32_t tX1 = tmem, tX2 = tmem + 64, tA0 = tmem + 128, tA1 = tmem + 256;
-  const uint32_t tS[2] = {tmem + (kIsDQ ? 256 : 384), tmem + (kIsDQ ? 320 : 384)};
-  const uint32_t tDP[2] = {tmem + (kIsDQ ? 384 : 448), tmem + 448};
+  const uint32_t tS0 = tmem + (kIsDQ ? 256 : 384), tDP0 = tmem + (kIsDQ ? 384 : 448);      // buffer sb at + sb * 64 (dQ only: sb in {0, 1})
+  const uint32_t a_x_full = smem_u32(&x_full), a_y_full = smem_u32(&y_full[0]), a_y_empty = smem_u32(&y_empty[0]), a_s_full = smem_u32(&s_full[0]),
+                 a_s_empty = smem_u32(&s_empty), a_pd_full = smem_u32(&pd_full[0]), a_pd_empty = smem_u32(&pd_empty[0]), a_acc_full = smem_u32(&acc_full);
+  const uint32_t a_smem = smem_u32(smem);
 
   if (warp == 0) {
     if (elect_one()) {          // elect.sync, not `lane == 0`: see hstu_fwd.cu
       for (int j = 0; j < n_iter; ++j) {
         const int st = j % NS, ph = (j / NS) & 1;
         const int row = seq_start + y_tile_of(j) * 64;
-        mbar_wait(&y_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&y_full[st], 2 * SM::kY);
-        uint8_t* y1 = smem + SM::oY + st * 2 * SM::kY;
+        mbar_wait(a_y_empty + st * 8, ph ^ 1);
+        mbar_arrive_expect_tx(a_y_full + st * 8, 2 * SM::kY);
+        const uint32_t y1 = a_smem + SM::oY + st * 2 * SM::kY;
 #pragma unroll
         for (int hf = 0; hf < NH; ++hf) {
-          tma_load_3d(y1 + hf * 8192, &map_y1, &y_full[st], hf * 64, h, row);
-          tma_load_3d(y1 + SM::kY + hf * 8192, &map_y2, &y_full[st], hf * 64, h, row);
+          tma_load_3d(y1 + hf * 8192, &map_y1, a_y_full + st * 8, hf * 64, h, row);
+          tma_load_3d(y1 + SM::kY + hf * 8192, &map_y2, a_y_full + st * 8, hf * 64, h, row);
         }
       }
     }
@@ -157,21 +160,21 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
         const int sb = kIsDQ ? (j & 1) : 0;                // S / dP buffer
         const int ys = j % NS, yph = (j / NS) & 1;         // streamed-tile ring
         BWD_T0();
-        mbar_wait(&y_full[ys], yph);
+        mbar_wait(a_y_full + ys * 8, yph);
         BWD_ACC(0);
-        if (!kIsDQ && j > 0) mbar_wait(&s_empty, (j - 1) & 1);   // SiLU(j-1) holds S^T / dP^T in registers
+        if (!kIsDQ && j > 0) mbar_wait(a_s_empty, (j - 1) & 1);   // SiLU(j-1) holds S^T / dP^T in registers
         BWD_ACC(1);
         tc_fence_after();
-        const uint32_t aY1 = smem_u32(smem + SM::oY + ys * 2 * SM::kY), aY2 = aY1 + SM::kY;
+        const uint32_t aY1 = a_smem + SM::oY + ys * 2 * SM::kY, aY2 = aY1 + SM::kY;
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
-          umma_ts(tS[sb], tX1 + k * 8, umma_desc_sw128(aY1 + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024), idesc_s, k > 0);
+          umma_ts(tS0 + sb * 64, tX1 + k * 8, umma_desc_sw128(aY1 + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024), idesc_s, k > 0);
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
-          umma_ts(tDP[sb], tX2 + k * 8, umma_desc_sw128(aY2 + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024), idesc_s, k > 0);
-        umma_commit(&s_full[sb]);
+          umma_ts(tDP0 + sb * 64, tX2 + k * 8, umma_desc_sw128(aY2 + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(a_s_full + sb * 8);
       };
-      mbar_wait(&x_full, 0);
+      mbar_wait(a_x_full, 0);
       tc_fence_after();
       issue_scores(0);
       for (int j = 0; j < n_iter; ++j) {
@@ -180,27 +183,27 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
         const int st = j & 1, ph = (j >> 1) & 1;
         const int ys = j % NS;
         BWD_T0();
-        mbar_wait(&pd_full[st], ph);
+        mbar_wait(a_pd_full + st * 8, ph);
         BWD_ACC(2);
         tc_fence_after();
-        const uint32_t aY1 = smem_u32(smem + SM::oY + ys * 2 * SM::kY), aY2 = aY1 + SM::kY;
+        const uint32_t aY1 = a_smem + SM::oY + ys * 2 * SM::kY, aY2 = aY1 + SM::kY;
         if (kIsDQ) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)    // A = dS from tensor memory: keys 0-31 packed in dP columns 0-15, keys 32-63 in columns 32-47
-            umma_ts(tA0, tDP[st] + (k >> 1) * 32 + (k & 1) * 8, umma_desc_sw128(aY1 + k * 2048, 8192, 1024), idesc_acc, (j > 0 || k > 0));
+            umma_ts(tA0, tDP0 + st * 64 + (k >> 1) * 32 + (k & 1) * 8, umma_desc_sw128(aY1 + k * 2048, 8192, 1024), idesc_acc, (j > 0 || k > 0));
         } else {
-          const uint32_t aDS = smem_u32(smem + SM::oDS + st * SM::kPD), aP = smem_u32(smem + SM::oP + st * SM::kPD);
+          const uint32_t aDS = a_smem + SM::oDS + st * SM::kPD, aP = a_smem + SM::oP + st * SM::kPD;
 #pragma unroll
           for (int k = 0; k < 4; ++k)    // K = 64 streamed rows: 4 steps of 16 rows (2048 B of the MN-major Y tile)
             umma_ss(tA1, umma_desc_sw128(aDS + k * 32, 16, 1024), umma_desc_sw128(aY1 + k * 2048, 8192, 1024), idesc_acc, (j > 0 || k > 0));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_ss(tA0, umma_desc_sw128(aP + k * 32, 16, 1024), umma_desc_sw128(aY2 + k * 2048, 8192, 1024), idesc_acc, (j > 0 || k > 0));
-          umma_commit(&pd_empty[st]);
+          umma_commit(a_pd_empty + st * 8);
         }
-        umma_commit(&y_empty[ys]);
+        umma_commit(a_y_empty + ys * 8);
       }
-      umma_commit(&acc_full);
+      umma_commit(a_acc_full);
       if (p.prof) { acc__[3] = (int)(clock64() - t_begin); BWD_FLUSH(0, 4); if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.prof[(kIsDQ ? 96 : 64) + 15] = n_iter; }
     }
   } else if (warp >= 4) {
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&x_full);
+      if (lane == 0) mbar_arrive(a_x_full);
     }
     const Intervals iv = kIsDQ ? hstu::cols_of_row(mk, xi) : hstu::rows_of_col(mk, xi);
     int acc__[4] = {0, 0, 0, 0};
@@ -228,13 +231,13 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
       const int y0 = y_tile_of(j) * 64;
       const bool full = kIsDQ ? mk.tile_full(x0, x1, y0, y0 + 63) : mk.tile_full(y0, y0 + 63, x0, x1);
       BWD_T0();
-      if (!kIsDQ) mbar_wait(&pd_empty[st], ph ^ 1);            // the accumulate GEMMs of tile j-2 have finished reading these operand buffers
+      if (!kIsDQ) mbar_wait(a_pd_empty + st * 8, ph ^ 1);            // the accumulate GEMMs of tile j-2 have finished reading these operand buffers
       BWD_ACC(0);
-      mbar_wait(&s_full[sb], sph);
+      mbar_wait(a_s_full + sb * 8, sph);
       BWD_ACC(1);
       tc_fence_after();
-      const uint32_t dds = smem_u32(smem + SM::oDS + st * SM::kPD + rit * 128);
-      const uint32_t dpp = smem_u32(smem + SM::oP + st * SM::kPD + rit * 128);
+      const uint32_t dds = a_smem + SM::oDS + st * SM::kPD + rit * 128;
+      const uint32_t dpp = a_smem + SM::oP + st * SM::kPD + rit * 128;
       // Mask test hoisted out of the tile (see hstu_fwd.cu: a per-pair `if (!full)` splits the unrolled loop into basic blocks that ptxas
       // cannot schedule the MUFU latency across).  dKV pulls all 32 + 32 columns into registers first so the single S^T / dP^T buffer
       // goes back to the MMA warp at once; dQ (double-buffered) works 16 columns at a time to keep registers free for the scheduler.
@@ -244,19 +247,19 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
         if (!kIsDQ) {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            tmem_ld16(tS[sb] + lane_off + ch * 32 + c * 16, s[c]);
-            tmem_ld16(tDP[sb] + lane_off + ch * 32 + c * 16, dp[c]);
+            tmem_ld16(tS0 + sb * 64 + lane_off + ch * 32 + c * 16, s[c]);
+            tmem_ld16(tDP0 + sb * 64 + lane_off + ch * 32 + c * 16, dp[c]);
           }
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty);
+          if (lane == 0) mbar_arrive(a_s_empty);
         }
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           if (kIsDQ) {
-            tmem_ld16(tS[sb] + lane_off + ch * 32 + c * 16, s[c]);
-            tmem_ld16(tDP[sb] + lane_off + ch * 32 + c * 16, dp[c]);
+            tmem_ld16(tS0 + sb * 64 + lane_off + ch * 32 + c * 16, s[c]);
+            tmem_ld16(tDP0 + sb * 64 + lane_off + ch * 32 + c * 16, dp[c]);
             tmem_ld_wait();
           }
           f32x2 h2[8], t2[8];
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
             if (!kIsDQ) pk_p[i] = pack_bf16x2_v(pe2);
           }
           if (kIsDQ) {
-            tmem_st8(tDP[sb] + lane_off + ch * 32 + c * 8, pk_ds);       // over dP columns this warpgroup has already read
+            tmem_st8(tDP0 + sb * 64 + lane_off + ch * 32 + c * 8, pk_ds);       // over dP columns this warpgroup has already read
           } else {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
@@ -298,12 +301,12 @@ __global__ void __launch_bounds__(384, 1) hstu_bwd_kernel(const __grid_constant_
       if (kIsDQ) { tmem_st_wait(); tc_fence_before(); }
       else fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pd_full[st]);
+      if (lane == 0) mbar_arrive(a_pd_full + st * 8);
       BWD_ACC(3);
     }
     if (threadIdx.x == 128) BWD_FLUSH(8, 4);
     // epilogue: dKV: warps 4-7 store dV (acc0), warps 8-11 store dK (acc1); dQ: the two warpgroups split the D columns
-    mbar_wait(&acc_full, 0);
+    mbar_wait(a_acc_full, 0);
     tc_fence_after();
     {
       // tcgen05.ld is warp-collective (.sync.aligned): every lane must execute it; only the global stores are predicated.

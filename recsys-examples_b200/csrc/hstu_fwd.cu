@@ -137,9 +137,14 @@ __global__ void __launch_bounds__(512, 1) hstu_fwd_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t tS[2] = {tmem, tmem + 128};
-  const uint32_t tO = tmem + 256;
-  const uint32_t tQ[2] = {tmem + 384, tmem + 448};   // Q tiles, bf16x2 packed (D / 2 columns), double-buffered across tiles
+  // TMEM columns: S0 @0, S1 @128, O @256, Q0 @384, Q1 @448 (bf16x2 packed Q tiles, D / 2 columns, double-buffered across tiles).
+  // Buffers and barriers are addressed arithmetically (tS0 + st * 128, a_s_full + st * 8): a runtime-indexed local array is a
+  // local-memory load, and smem_u32(&bar[st]) an S2R + address chain, in front of every wait of the inner loops.
+  const uint32_t tS0 = tmem, tO = tmem + 256, tQ0 = tmem + 384;
+  const uint32_t a_q_full = smem_u32(&q_full[0]), a_k_full = smem_u32(&k_full[0]), a_k_empty = smem_u32(&k_empty[0]), a_v_full = smem_u32(&v_full[0]),
+                 a_v_empty = smem_u32(&v_empty[0]), a_s_full = smem_u32(&s_full[0]), a_p_full = smem_u32(&p_full[0]), a_o_full = smem_u32(&o_full),
+                 a_o_empty = smem_u32(&o_empty), a_tile_full = smem_u32(&tile_full[0]), a_tile_empty = smem_u32(&tile_empty[0]);
+  const uint32_t a_smem = smem_u32(smem);
 
   // every consumer walks the ring with its own cursor; returns the next tile that exists (skipping tiles past the end of their
   // sequence) or false when the scheduler has published the end marker
@@ -147,12 +152,12 @@ __global__ void __launch_bounds__(512, 1) hstu_fwd_kernel(const __grid_constant_
   auto next_tile = [&](int& cursor, FwdTile& t, bool arrive_lane, bool warp_wide) -> bool {
     for (;;) {
       const int slot = cursor % kRing;
-      mbar_wait(&tile_full[slot], (cursor / kRing) & 1);
+      mbar_wait(a_tile_full + slot * 8, (cursor / kRing) & 1);
       const TileMsg m = tile_ring[slot];
       ++cursor;
       if (m.w < 0) return false;                     // end marker: left in place, never released
       if (warp_wide) __syncwarp();                   // every lane has read the slot before lane 0 hands it back
-      if (arrive_lane) mbar_arrive(&tile_empty[slot]);
+      if (arrive_lane) mbar_arrive(a_tile_empty + slot * 8);
       if (decode_tile(p, m, t)) return true;
     }
   };
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(512, 1) hstu_fwd_kernel(const __grid_constant_
     if (elect_one()) {
       for (int c = 0;; ++c) {
         const int slot = c % kRing;
-        mbar_wait(&tile_empty[slot], ((c / kRing) & 1) ^ 1);
+        mbar_wait(a_tile_empty + slot * 8, ((c / kRing) & 1) ^ 1);
         TileMsg m;
         m.w = atomicAdd(p.tile_counter, 1);
         if (m.w >= p.n_tiles) m.w = -1;
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(512, 1) hstu_fwd_kernel(const __grid_constant_
         }
         const int w = m.w;
         tile_ring[slot] = m;
-        mbar_arrive(&tile_full[slot]);               // release semantics: the store above is visible to the waiters
+        mbar_arrive(a_tile_full + slot * 8);         // release semantics: the store above is visible to the waiters
         if (w < 0) break;
       }
     }
@@ -183,19 +188,19 @@ __global__ void __launch_bounds__(512, 1) hstu_fwd_kernel(const __grid_constant_
     // ------------------------------------------------------------------ K (warp 0) / V (warp 3) producers
     if (elect_one()) {
       const CUtensorMap* map = warp == 0 ? &map_k : &map_v;
-      uint8_t* ring = smem + (warp == 0 ? SM::kK : SM::kV);
-      uint64_t* full = warp == 0 ? k_full : v_full;
-      uint64_t* empty = warp == 0 ? k_empty : v_empty;
+      const uint32_t ring = a_smem + (warp == 0 ? SM::kK : SM::kV);
+      const uint32_t full = warp == 0 ? a_k_full : a_v_full;
+      const uint32_t empty = warp == 0 ? a_k_empty : a_v_empty;
       int cursor = 0, c = 0;                         // c: running K / V tile count (ring slot and phase)
       FwdTile t;
       while (next_tile(cursor, t, true, false)) {
         for (int j = 0; j < t.n_iter; ++j, ++c) {
           const int st = c % S, ph = (c / S) & 1;
           const int row = t.seq_start + (t.nb0 + j) * 128;
-          mbar_wait(&empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&full[st], SM::kTile);
+          mbar_wait(empty + st * 8, ph ^ 1);
+          mbar_arrive_expect_tx(full + st * 8, SM::kTile);
 #pragma unroll
-          for (int hf = 0; hf < NH; ++hf) tma_load_3d(ring + st * SM::kTile + hf * 16384, map, &full[st], hf * 64, t.h, row);
+          for (int hf = 0; hf < NH; ++hf) tma_load_3d(ring + st * SM::kTile + hf * 16384, map, full + st * 8, hf * 64, t.h, row);
         }
       }
     }
@@ -214,20 +219,20 @@ __global__ void __launch_bounds__(512, 1) hstu_fwd_kernel(const __grid_constant_
           const int st = sidx & 1;
           const int ks = kc % S, kph = (kc / S) & 1;       // K ring
           HSTU_T0();
-          mbar_wait(&k_full[ks], kph);
+          mbar_wait(a_k_full + ks * 8, kph);
           HSTU_ACC(0);
           tc_fence_after();
-          const uint32_t aK = smem_u32(smem + SM::kK + ks * SM::kTile);
+          const uint32_t aK = a_smem + SM::kK + ks * SM::kTile;
 #pragma unroll
           for (int k = 0; k < D / 16; ++k)                   // A = Q from tensor memory: 16 k values = 8 packed columns per step
-            umma_ts(tS[st], tQ[tc & 1] + k * 8, umma_desc_sw128(aK + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), idesc_qk, k > 0);
-          umma_commit(&s_full[st]);
-          umma_commit(&k_empty[ks]);
+            umma_ts(tS0 + st * 128, tQ0 + (tc & 1) * 64 + k * 8, umma_desc_sw128(aK + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), idesc_qk, k > 0);
+          umma_commit(a_s_full + st * 8);
+          umma_commit(a_k_empty + ks * 8);
           ++kc;
         };
         {
           HSTU_T0();
-          mbar_wait(&q_full[tc & 1], (tc >> 1) & 1);       // Q of this tile is in tensor memory (written by the I/O warpgroup one tile ahead)
+          mbar_wait(a_q_full + (tc & 1) * 8, (tc >> 1) & 1);       // Q of this tile is in tensor memory (written by the I/O warpgroup one tile ahead)
           HSTU_ACC(1);
         }
         tc_fence_after();
@@ -239,19 +244,19 @@ __global__ void __launch_bounds__(512, 1) hstu_fwd_kernel(const __grid_constant_
           const int st = it & 1, ph = (it >> 1) & 1;
           const int vs = vc % S, vph = (vc / S) & 1;
           HSTU_T0();
-          mbar_wait(&v_full[vs], vph);
+          mbar_wait(a_v_full + vs * 8, vph);
           HSTU_ACC(2);
-          mbar_wait(&p_full[st], ph);
+          mbar_wait(a_p_full + st * 8, ph);
           HSTU_ACC(3);
-          if (j == 0 && tc > 0) mbar_wait(&o_empty, (tc - 1) & 1);   // the I/O warpgroup has pulled the previous tile's O into registers
+          if (j == 0 && tc > 0) mbar_wait(a_o_empty, (tc - 1) & 1);   // the I/O warpgroup has pulled the previous tile's O into registers
           tc_fence_after();
-          const uint32_t aV = smem_u32(smem + SM::kV + vs * SM::kTile);
+          const uint32_t aV = a_smem + SM::kV + vs * SM::kTile;
 #pragma unroll
           for (int k = 0; k < 8; ++k)                        // A = P_j: keys 0-63 packed in S columns 0-31, keys 64-127 in columns 64-95
-            umma_ts(tO, tS[st] + (k >> 2) * 64 + (k & 3) * 8, umma_desc_sw128(aV + k * 2048, 16384, 1024), idesc_pv, (j > 0 || k > 0));
-          umma_commit(&v_empty[vs]);
+            umma_ts(tO, tS0 + st * 128 + (k >> 2) * 64 + (k & 3) * 8, umma_desc_sw128(aV + k * 2048, 16384, 1024), idesc_pv, (j > 0 || k > 0));
+          umma_commit(a_v_empty + vs * 8);
         }
-        umma_commit(&o_full);
+        umma_commit(a_o_full);
         ++tc;
       }
       if (kProf && p.dbg) { atomicAdd(const_cast<int*>(p.dbg) + 8, n_total); atomicAdd(const_cast<int*>(p.dbg) + 9, tc); }
@@ -277,12 +282,12 @@ __global__ void __launch_bounds__(512, 1) hstu_fwd_kernel(const __grid_constant_
 #pragma unroll
       for (int c = 0; c < D / 16; ++c) {
         const uint32_t r[8] = {qreg[2 * c].x, qreg[2 * c].y, qreg[2 * c].z, qreg[2 * c].w, qreg[2 * c + 1].x, qreg[2 * c + 1].y, qreg[2 * c + 1].z, qreg[2 * c + 1].w};
-        tmem_st8(tQ[buf] + lane_off + c * 8, r);
+        tmem_st8(tQ0 + buf * 64 + lane_off + c * 8, r);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&q_full[buf]);
+      if (lane == 0) mbar_arrive(a_q_full + buf * 8);
     };
     bool have = next_tile(cursor, t, lane == 0, true);
     if (have) q_put(t, 0);
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(512, 1) hstu_fwd_kernel(const __grid_constant_
       if (have_next) q_put(tn, (tc + 1) & 1);
       const int row = t.r0 + rit;
       HSTU_T0();
-      mbar_wait(&o_full, tc & 1);
+      mbar_wait(a_o_full, tc & 1);
       HSTU_ACC(0);
       tc_fence_after();
       __nv_bfloat16* orow = p.out + ((int64_t)(t.seq_start + row) * p.H + t.h) * D;
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(512, 1) hstu_fwd_kernel(const __grid_constant_
         if (half == D / 64 - 1) {                    // O is in registers: the next tile's first P V may overwrite it
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&o_empty);
+          if (lane == 0) mbar_arrive(a_o_empty);
         }
         if (row < t.L) {
 #pragma unroll
@@ -348,10 +353,10 @@ __global__ void __launch_bounds__(512, 1) hstu_fwd_kernel(const __grid_constant_
       bool full = t.mk.tile_full(t.r0, t.r1, c_base, c_base + 63);
       for (int j = 0; j < t.n_iter; ++j, ++it) {
         const int st = it & 1, ph = (it >> 1) & 1;
-        const uint32_t t_s = tS[st] + lane_off + ch * 64;
+        const uint32_t t_s = tS0 + st * 128 + lane_off + ch * 64;
         HSTU_GAP(j == 0 ? 7 : 5);
         HSTU_T0();
-        mbar_wait(&s_full[st], ph);
+        mbar_wait(a_s_full + st * 8, ph);
         HSTU_ACC(0);
         tc_fence_after();
         // 16 score columns at a time (tcgen05.ld x16, the next chunk in flight while this one is in the SFU); packed chunk c (8 columns)
@@ -395,7 +400,7 @@ __global__ void __launch_bounds__(512, 1) hstu_fwd_kernel(const __grid_constant_
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[st]);
+        if (lane == 0) mbar_arrive(a_p_full + st * 8);
         HSTU_ACC(4);
         HSTU_MARK();
       }
