@@ -8,7 +8,12 @@
 
 namespace sm100 {
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+// Shared-window address of a pointer into this CTA's shared memory.  cvta yields the shared::cluster form, (rank of the CTA in its
+// cluster << 24) | offset, which ptxas lowers to an S2R SR_CgaCtaId + LEA and happily re-materialises inside inner loops (measured:
+// one S2R in front of every mbarrier wait of the HSTU SiLU warps).  None of these kernels is launched with clusters, so the rank is 0
+// and the 24-bit offset IS the address, for .shared::cta and .shared::cluster operands alike; masking lets ptxas fold static
+// addresses to immediates.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)) & 0x00FFFFFFu; }
 
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
