@@ -39,20 +39,26 @@ for Bf in (8, 32):
         print(f"  {nm:34s} {d[k_] / ctas:8.0f} cyc / tile")
     print(f"  per tile: {iters / ctas:.1f} iterations x {(d[48] + d[50] + d[52]) / iters:.0f} = {(d[48] + d[50] + d[52]) / ctas:.0f} cyc in the SiLU loop, tile period {d[10] / ctas:.0f}")
     del qf, kf, vf
-dbg = torch.zeros(128, dtype=torch.int32).pin_memory()
-# ---- backward: dKV kernel slots 64.., dQ kernel slots 96..
+# ---- backward: dKV kernel slots 64.., dQ kernel slots 96.. (every CTA adds its counters, units of 16 cycles)
 do = torch.randn_like(q)
-for _ in range(2): ops.hstu_varlen_bwd_100(do, q, k, v, cu, cu, S, S, None, None, None, None, None, 1, -1, 0, a)
-torch.cuda.synchronize()
-dbg.zero_()
-N.lib.hstu_set_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
-e0.record(); ops.hstu_varlen_bwd_100(do, q, k, v, cu, cu, S, S, None, None, None, None, None, 1, -1, 0, a); e1.record(); torch.cuda.synchronize()
-N.lib.hstu_set_debug_buffer(None)
-d = dbg.tolist()
-print(f"backward {e0.elapsed_time(e1):.3f} ms (two kernels)")
-for base, nm in ((64, "dKV"), (96, "dQ")):
-    n = max(d[base + 15], 1)
-    print(f" {nm} kernel, CTA0: {n} tiles of 128x64, MMA thread total {d[base + 3]} cyc = {d[base + 3] / n:.0f} / tile")
-    for off, what in ((0, "mma: wait y_full"), (1, "mma: wait s_empty"), (2, "mma: wait operand tile"), (8, "silu: wait pd_empty"), (9, "silu: wait s_full"),
-                      (10, "silu: ld + math + store"), (11, "silu: fence + arrive")):
-        print(f"   {what:28s} {d[base + off]:9d} cyc total {d[base + off] / n:8.0f} / tile")
+for Bf in (8, 32):
+    Tf = Bf * S
+    qf, kf, vf, dof = (torch.randn(Tf, H, D, device=dev, dtype=torch.bfloat16) for _ in range(4))
+    cuf = torch.arange(0, Tf + 1, S, dtype=torch.int32, device=dev)
+    for _ in range(2): ops.hstu_varlen_bwd_100(dof, qf, kf, vf, cuf, cuf, S, S, None, None, None, None, None, 1, -1, 0, a)
+    torch.cuda.synchronize()
+    e0.record(); ops.hstu_varlen_bwd_100(dof, qf, kf, vf, cuf, cuf, S, S, None, None, None, None, None, 1, -1, 0, a); e1.record(); torch.cuda.synchronize()
+    t_prod = e0.elapsed_time(e1)
+    dbgd = torch.zeros(128, dtype=torch.int32, device=dev)
+    N.lib.hstu_set_debug_buffer(ctypes.c_void_p(dbgd.data_ptr()))
+    ops.hstu_varlen_bwd_100(dof, qf, kf, vf, cuf, cuf, S, S, None, None, None, None, None, 1, -1, 0, a); torch.cuda.synchronize()
+    N.lib.hstu_set_debug_buffer(None)
+    d = dbgd.tolist()
+    print(f"backward B={Bf}: {t_prod:.3f} ms (dKV + dQ kernels)")
+    for base, nm in ((64, "dKV"), (96, "dQ")):
+        n, tiles = max(d[base + 15], 1), max(d[base + 14], 1)
+        print(f" {nm} kernel: {tiles} stationary tiles, {n} iterations of 128x64 ({n / 148:.0f} per SM); MMA-thread lifetime {16 * d[base + 3] / n:.0f} cyc / iteration")
+        for off, what in ((0, "mma: wait y_full"), (1, "mma: wait s_empty"), (2, "mma: wait operand tile"), (8, "silu: wait pd_empty"), (9, "silu: wait s_full"),
+                          (10, "silu: ld + math + store"), (11, "silu: fence + arrive")):
+            print(f"   {what:28s} {16 * d[base + off] / n:8.0f} cyc / iteration")
+    del qf, kf, vf, dof
