@@ -17,8 +17,9 @@
 //   * dQ kernel, query-stationary: a CTA owns 128 queries (Q and dO in TMEM) and streams 64-row K/V tiles: S = Q K^T, dP = dO V^T
 //       (double-buffered), the SiLU warps write dS back over dP in tensor memory -> dQ += dS K (.ts again; no shared-memory operand
 //       tile, no "empty" barriers: the tensor pipe executes one thread's MMAs in issue order).
-//   Measured per 128x64 tile (tools/hstu_cycles.py, MMA-thread time): dKV 1960 cycles, dQ 1340.  Splitting dKV into an all-.ts dV
-//   kernel and an all-.ts dK kernel was tried: 1070 + 1400 cycles per tile — slower than the fused kernel, so it was dropped.
+//   Both kernels are persistent (tile scheduler + tile I/O warpgroup, see the kernel comment).  Measured per 128x64 iteration
+//   (tools/hstu_cycles.py, all CTAs): dKV 1940 cycles, dQ 1320.  Splitting dKV into an all-.ts dV kernel and an all-.ts dK kernel was
+//   tried: 1070 + 1400 cycles — slower than the fused kernel, so it was dropped.
 //   The reference keeps one KV-stationary kernel and reduce-adds dQ tiles (TMA reduce) into a dense fp32
 //   [B, H, max_seqlen, D] workspace that is zero-filled before and converted after every call (hstu_ops_gpu.py:373-382,
 //   hstu_bwd.py:2177-2240): 3 extra passes over a padded tensor, non-deterministic.  Recomputing the two score GEMMs costs

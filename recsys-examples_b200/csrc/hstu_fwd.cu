@@ -4,20 +4,22 @@
 // host wrapper hstu_ops_gpu.py:85-252); mask rule = hstu_blackwell/mask.py:61-127 (causal / local window,
 // target groups, contexts).  Hand-written tcgen05 / TMA / TMEM:
 //
-//   CTA = one 128-row Q tile of one (b, h); 12 warps:
+//   PERSISTENT kernel, one 512-thread CTA per SM; work unit = one 128-row Q tile of one (b, h), pulled from a global counter; 16 warps:
 //     warp 0    K producer    : K_j tiles (128 x D bf16, SWIZZLE_128B boxes of 64 columns) into a 3-stage ring
 //     warp 3    V producer    : V_j tiles, own ring, own thread (a busy V slot must never delay the K tile the next QK^T needs)
 //     warp 1    MMA issuer    : S_j = Q K_j^T and O += P_j V_j, BOTH with the A operand in tensor memory (.ts):
-//                               Q is packed into TMEM once per CTA, P_j is written back over S_j by the SiLU warps.  Measured on
+//                               Q is packed into TMEM once per tile, P_j is written back over S_j by the SiLU warps.  Measured on
 //                               B200 (tools/ubench/umma_bench.cu): 128x128x16 .ss = 107 cycles (shared-memory operand bandwidth,
 //                               ~75 B/clk), .ts = 74 cycles.  S is double-buffered so QK^T(j+1) overlaps the SiLU of tile j.
 //                               The issuing thread is chosen with elect.sync: under `if (lane == 0)` ptxas wraps every UTCHMMA /
 //                               UTMALDG in an ELECT + BRA.U.ANY loop (94 cycles per MMA issue).
-//     warp 2    TMEM alloc/dealloc (512 columns: S0 @0, S1 @128, O @256, Q @384)
+//     warp 2    tile scheduler (atomicAdd on the tile counter, cu_seqlens loads, 4-deep ring of tile messages) + TMEM alloc/dealloc
+//               (512 columns: S0 @0, S1 @128, O @256, Q0 @384, Q1 @448)
 //     warps 4-11 two SiLU warpgroups (64 score columns each): thread = accumulator row; tcgen05.ld 16 columns at a time ->
 //                               h + h*tanh.approx(h), h = alpha/2*s (packed FMUL2 / FFMA2 around one MUFU.TANH per score: the SFU
 //                               is the floor, 1024 cycles per 128x128 tile) -> bf16x2 -> tcgen05.st into the first half of the
-//                               warpgroup's own S columns (already read); finally O: TMEM -> regs -> *1/N -> bf16 -> global.
+//                               warpgroup's own S columns (already read).  Nothing else: the loop is the critical path of the kernel.
+//     warps 12-15 tile I/O warpgroup: next tile's Q rows -> the other TMEM Q buffer; finished O: TMEM -> regs -> *1/N -> bf16 -> global.
 //   No shared-memory traffic for Q or P at all: shared memory only holds the K / V rings.
 //   The 1/N scale is applied once to O (linear), not to every P element.
 #include <cuda_bf16.h>
