@@ -403,26 +403,52 @@ def main():
     # (sum of the looked-up rows) -> D2H, every step.  N=1 uses the module's CUDA-graph step (make_graphed_step): the fused
     # prefetch has no host sync, so the whole step replays as one graph launch.
     host_batches = [b.cpu().pin_memory() for b in batches[args.warmup:]]
-    host_res = torch.zeros(1, dtype=torch.float32).pin_memory()
+    host_res = torch.zeros(len(host_batches), dtype=torch.float32).pin_memory()
+    # Input pipeline as a trainer runs it: the H2D copy of step i+1 goes through a copy stream into one of two staging buffers while step
+    # i computes; the 4-byte result of step i is read back asynchronously and consumed (host sync) one step later.  Every byte still
+    # crosses PCIe inside the timed region, once per step, in both directions.
+    copy_stream = torch.cuda.Stream(dev)
+    cur = torch.cuda.current_stream(dev)
+    staging = [torch.empty_like(dev_ids) for _ in range(2)]
+    h2d_done = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    res_done = [torch.cuda.Event() for _ in range(len(host_batches))]
+    for ev in consumed:
+        ev.record(cur)
+    def e2e_pass(hbs):
+        for i, hb in enumerate(hbs):
+            sl = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[sl])
+                staging[sl].copy_(hb, non_blocking=True)
+                h2d_done[sl].record(copy_stream)
+            cur.wait_event(h2d_done[sl])
+            dev_ids.copy_(staging[sl], non_blocking=True)
+            consumed[sl].record(cur)
+            if graphed is not None:
+                graphed[0].replay()
+                host_res[i : i + 1].copy_(graphed[2].reshape(1), non_blocking=True)
+            else:
+                out = call(dev_ids)
+                loss = out.detach().sum()
+                out.backward(grad)
+                host_res[i : i + 1].copy_(loss.reshape(1), non_blocking=True)
+            res_done[i].record(cur)
+            if i > 0:
+                res_done[i - 1].synchronize()          # the host consumes step i-1's result here
+        res_done[len(hbs) - 1].synchronize()
+
+    e2e_pass(host_batches[:3])                       # untimed warm-up of exactly this path (first launch of this graph, copy stream, staging)
     barrier()
     e0.record()
-    for hb in host_batches:
-        dev_ids.copy_(hb, non_blocking=True)
-        if graphed is not None:
-            graphed[0].replay()
-            host_res.copy_(graphed[2].reshape(1), non_blocking=False)
-        else:
-            out = call(dev_ids)
-            loss = out.detach().sum()
-            out.backward(grad)
-            host_res.copy_(loss.reshape(1), non_blocking=False)
+    e2e_pass(host_batches)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n_ids * args.steps / (float(t.item()) / 1e3)
-    e2e_mode = step_mode
+    e2e_mode = step_mode + "; H2D of step i+1 on a copy stream (2 staging buffers) overlaps step i, result of step i read back async and consumed at step i+1"
 
     if rank == 0:
         hbm, tfl, which = peaks()
