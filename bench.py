@@ -349,10 +349,8 @@ def main():
         else:
             step(ids)
 
-    for i in range(3):
+    for i in range(args.warmup):
         timed_step(batches[i])
-    clocks = ClockSampler(local)
-    clocks.start()
     barrier()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
@@ -361,7 +359,6 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks.stop()
     # ---- per-kernel times for the roofline: a separate, un-reported pass of eager steps with CUDA events around every native launch
     N.lib.demb_profile_enable(1)
     N.PROFILE = {}
