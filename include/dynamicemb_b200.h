@@ -144,6 +144,17 @@ int demb_backward(float* values, int64_t value_dim, int emb_dim, int64_t n, cons
                   const float* grads, int64_t grad_stride, const int64_t* offsets, int64_t batch_size, int num_features, int combiner,
                   int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
                   float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, void* stream);
+/* Split form: the gradient-independent half of demb_backward (pair list + radix sort by unique index) can be launched right after the
+   prefetch; it runs on the handle's own stream behind the work enqueued on `stream` so far and overlaps the forward gather.
+   demb_backward_prepared then joins it.  Same n / inverse / workspace in both calls; one outstanding prepare per workspace. */
+int demb_bwd_prep_create(void** handle);
+int demb_bwd_prep_destroy(void* handle);
+int demb_backward_prepare(void* handle, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound, const int64_t* offsets, int64_t batch_size,
+                          int num_features, int combiner, void* workspace, int64_t workspace_bytes, void* stream);
+int demb_backward_prepared(void* handle, float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound,
+                           const int64_t* rows, const float* grads, int64_t grad_stride, const int64_t* offsets, int64_t batch_size, int num_features,
+                           int combiner, int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
+                           float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, void* stream);
 /* {sgd,adam,adagrad,rowwise_adagrad}_update_for_flat_table (optimizer.cu): dense grads[n, D] -> rows */
 int demb_update_rows(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* rows, const float* grads, int64_t grad_stride,
                      int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,

@@ -708,19 +708,35 @@ int64_t demb_backward_workspace_bytes(int64_t n, int emb_dim) {
   return (int64_t)(4 * align256(4 * (size_t)n) + 2 * align256(tiles * (size_t)emb_dim * 4) + align256(((tiles + 31) / 32 + 1) * (size_t)emb_dim * 4) + align256(tmp) + 256);
 }
 
-// Fused backward: reduce gradients per unique id and apply the sparse optimizer to the value rows.
-//  grads: sequence mode [n, D] (row i = gradient of id i); pooled mode [B, F*D] viewed as [B*F, D].
-//  inverse[n]: id -> unique idx in [0, num_unique_bound).  rows[u]: global value row of unique u (<0 skip).
-//  unique_grads (nullable): also emit the reduced gradients [num_unique, D] (reference op reduce_grads).
-int demb_backward(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound, const int64_t* rows,
-                  const float* grads, int64_t grad_stride, const int64_t* offsets, int64_t batch_size, int num_features, int combiner,
-                  int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
-                  float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, void* stream_) {
+// Side stream + fork/join events for demb_backward_prepare (one per module).
+struct BwdPrep { cudaStream_t side; cudaEvent_t fork, join; };
+
+int demb_bwd_prep_create(void** handle) {
+  BwdPrep* h = new BwdPrep{};
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming) != cudaSuccess) { delete h; return DEMB_ERR_ARG; }
+  *handle = h;
+  return 0;
+}
+int demb_bwd_prep_destroy(void* handle) {
+  BwdPrep* h = (BwdPrep*)handle;
+  if (!h) return 0;
+  cudaStreamDestroy(h->side); cudaEventDestroy(h->fork); cudaEventDestroy(h->join);
+  delete h;
+  return 0;
+}
+
+// phase 0: everything on `stream`.  phase 1: only the gradient-independent part (pair list + radix sort by unique index), forked onto the
+// handle's side stream behind whatever `stream` has enqueued so far.  phase 2: the rest on `stream`, joined behind phase 1 (same workspace).
+static int backward_impl(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound, const int64_t* rows,
+                         const float* grads, int64_t grad_stride, const int64_t* offsets, int64_t batch_size, int num_features, int combiner,
+                         int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
+                         float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, cudaStream_t stream, BwdPrep* prep, int phase) {
   if (check_dims(emb_dim, value_dim > 0 ? value_dim : emb_dim)) return DEMB_ERR_ARG;
   if (n <= 0) return 0;
   if (n >= (1ll << 31) || num_unique_bound >= (1ll << 31)) return DEMB_ERR_ARG;
   if (workspace_bytes < demb_backward_workspace_bytes(n, emb_dim)) return DEMB_ERR_WORKSPACE;
-  cudaStream_t stream = (cudaStream_t)stream_;
+  if (phase != 0 && !prep) return DEMB_ERR_ARG;
   const int pooled = combiner >= 0;
   size_t tiles = ((size_t)n + 31) / 32;
   uint8_t* w = (uint8_t*)workspace;
@@ -732,11 +748,26 @@ int demb_backward(float* values, int64_t value_dim, int emb_dim, int64_t n, cons
   float* ps = (float*)w; w += align256(tiles * (size_t)emb_dim * 4);
   float* wc = (float*)w; w += align256(((tiles + 31) / 32 + 1) * (size_t)emb_dim * 4);
   size_t tmp_bytes = (size_t)((uint8_t*)workspace + workspace_bytes - w);
-  if (g_prof_on) cudaEventRecord(g_prof_ev[0], stream);
-  backward_pairs_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(n, inverse, pooled, batch_size, num_features, offsets, k0, v0);
-  int end_bit = 1; while (end_bit < 31 && (1ll << end_bit) < num_unique_bound) ++end_bit;
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(w, tmp_bytes, k0, k1, v0, v1, (int)n, 0, end_bit, stream);
-  if (e != cudaSuccess) return -(int)e;
+  if (phase != 2) {
+    cudaStream_t s1 = stream;
+    if (phase == 1) {
+      if (cudaEventRecord(prep->fork, stream) != cudaSuccess || cudaStreamWaitEvent(prep->side, prep->fork, 0) != cudaSuccess) return DEMB_ERR_ARG;
+      s1 = prep->side;
+    }
+    if (g_prof_on && phase == 0) cudaEventRecord(g_prof_ev[0], stream);
+    backward_pairs_kernel<<<(int)((n + 255) / 256), 256, 0, s1>>>(n, inverse, pooled, batch_size, num_features, offsets, k0, v0);
+    int end_bit = 1; while (end_bit < 31 && (1ll << end_bit) < num_unique_bound) ++end_bit;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(w, tmp_bytes, k0, k1, v0, v1, (int)n, 0, end_bit, s1);
+    if (e != cudaSuccess) return -(int)e;
+    if (phase == 1) {
+      if (cudaEventRecord(prep->join, prep->side) != cudaSuccess) return DEMB_ERR_ARG;
+      DEMB_CHECK_LAST();
+      return 0;
+    }
+  } else {
+    if (cudaStreamWaitEvent(stream, prep->join, 0) != cudaSuccess) return DEMB_ERR_ARG;
+    if (g_prof_on) cudaEventRecord(g_prof_ev[0], stream);
+  }
   BwdArgs a{grads, grad_stride, emb_dim, pooled, combiner, batch_size, num_features, offsets, k1, v1, n, rows, values, value_dim, unique_grads, pc, ps,
             OptArgs{opt_type, lr, eps, beta1, beta2, weight_decay, bias_correction1, bias_correction2}};
   if (g_prof_on) cudaEventRecord(g_prof_ev[1], stream);
@@ -749,6 +780,35 @@ int demb_backward(float* values, int64_t value_dim, int emb_dim, int64_t n, cons
   });
   DEMB_CHECK_LAST();
   return 0;
+}
+
+// Fused backward: reduce gradients per unique id and apply the sparse optimizer to the value rows.
+//  grads: sequence mode [n, D] (row i = gradient of id i); pooled mode [B, F*D] viewed as [B*F, D].
+//  inverse[n]: id -> unique idx in [0, num_unique_bound).  rows[u]: global value row of unique u (<0 skip).
+//  unique_grads (nullable): also emit the reduced gradients [num_unique, D] (reference op reduce_grads).
+int demb_backward(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound, const int64_t* rows,
+                  const float* grads, int64_t grad_stride, const int64_t* offsets, int64_t batch_size, int num_features, int combiner,
+                  int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
+                  float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, void* stream_) {
+  return backward_impl(values, value_dim, emb_dim, n, inverse, num_unique_bound, rows, grads, grad_stride, offsets, batch_size, num_features, combiner,
+                       opt_type, lr, eps, beta1, beta2, weight_decay, bias_correction1, bias_correction2, unique_grads, workspace, workspace_bytes,
+                       (cudaStream_t)stream_, nullptr, 0);
+}
+// The part of demb_backward that does not need the gradients (pair list + sort), launched EARLY — right after the prefetch, on the
+// handle's side stream — so it overlaps the forward gather instead of sitting in front of the gradient reduction.
+int demb_backward_prepare(void* handle, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound, const int64_t* offsets, int64_t batch_size,
+                          int num_features, int combiner, void* workspace, int64_t workspace_bytes, void* stream_) {
+  return backward_impl(nullptr, 0, emb_dim, n, inverse, num_unique_bound, nullptr, nullptr, 0, offsets, batch_size, num_features, combiner, 0, 0.f, 0.f, 0.f,
+                       0.f, 0.f, 1.f, 1.f, nullptr, workspace, workspace_bytes, (cudaStream_t)stream_, (BwdPrep*)handle, 1);
+}
+// demb_backward after demb_backward_prepare(handle, ... same n / inverse / workspace ...)
+int demb_backward_prepared(void* handle, float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound,
+                           const int64_t* rows, const float* grads, int64_t grad_stride, const int64_t* offsets, int64_t batch_size, int num_features,
+                           int combiner, int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
+                           float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, void* stream_) {
+  return backward_impl(values, value_dim, emb_dim, n, inverse, num_unique_bound, rows, grads, grad_stride, offsets, batch_size, num_features, combiner,
+                       opt_type, lr, eps, beta1, beta2, weight_decay, bias_correction1, bias_correction2, unique_grads, workspace, workspace_bytes,
+                       (cudaStream_t)stream_, (BwdPrep*)handle, 2);
 }
 
 int demb_profile_enable(int on) {

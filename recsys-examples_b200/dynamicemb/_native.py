@@ -44,6 +44,10 @@ _SIGS = {
     "demb_copy_rows": (I32, [P, I64, I32, I64, P, P, I64, I32, P]),
     "demb_backward_workspace_bytes": (I64, [I64, I32]),
     "demb_backward": (I32, [P, I64, I32, I64, P, I64, P, P, I64, P, I64, I32, I32, I32, F32, F32, F32, F32, F32, F32, F32, P, P, I64, P]),
+    "demb_bwd_prep_create": (I32, [P]),
+    "demb_bwd_prep_destroy": (I32, [P]),
+    "demb_backward_prepare": (I32, [P, I32, I64, P, I64, P, I64, I32, I32, P, I64, P]),
+    "demb_backward_prepared": (I32, [P, P, I64, I32, I64, P, I64, P, P, I64, P, I64, I32, I32, I32, F32, F32, F32, F32, F32, F32, F32, P, P, I64, P]),
     "demb_update_rows": (I32, [P, I64, I32, I64, P, P, I64, I32, F32, F32, F32, F32, F32, F32, F32, P]),
     "demb_fill_i32": (I32, [P, I64, I32, P]),
     "demb_train_prefetch_workspace_bytes": (I64, [I64, I32]),

@@ -70,6 +70,7 @@ class PrefetchState:
     rows: torch.Tensor              # global value row per unique key, -1 = absent
     num_unique_bound: int           # host-known upper bound of the unique count (sort width)
     num_unique_dev: Optional[torch.Tensor] = None   # device-side count (fused path: buffers are sized by the bound)
+    bwd_ws: Optional[torch.Tensor] = None           # workspace holding the pre-sorted (unique idx, gradient row) pairs (backward_prepare)
 
     @property
     def num_unique(self) -> int:
@@ -102,7 +103,7 @@ class _LookupFunction(torch.autograd.Function):
         pooled = ctx.combiner >= 0
         ext.backward(m._values, m.max_D, st.reverse_indices, max(st.num_unique_bound, 1), st.rows, grads, offsets=ctx.offsets if pooled else None,
                      batch_size=ctx.batch_size if pooled else 0, num_features=m.feature_num if pooled else 0, combiner=ctx.combiner,
-                     **opt.kernel_kwargs())
+                     prepared=(m._bwd_prep, st.bwd_ws) if st.bwd_ws is not None else None, **opt.kernel_kwargs())
         m._unpin(st)
         return None, None, None, None, None
 
@@ -192,6 +193,8 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         self._values = torch.zeros(self._table.capacity_, self.value_dim, dtype=torch.float32, device=self._device)
         self._seed = int(kwargs.get("seed", 0))
         self._fused_prefetch = bool(kwargs.get("fused_prefetch", True))     # False = op-by-op path (reference op order, 2 host syncs)
+        self._bwd_prep = None                                               # ext.BackwardPrep, created on first training prefetch
+        self._force_prepare = False
         self._prefetch_states: Deque[PrefetchState] = deque()
         self._empty_tensor = nn.Parameter(torch.empty(10, requires_grad=True, device=self._device, dtype=self.embedding_dtype))
         self.bounds_check_mode_int = int(bounds_check_mode)
@@ -355,7 +358,13 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
             tb.table_storage_, tb.table_bucket_offsets_, tb.bucket_capacity_, tb.bucket_sizes, tb._ref_counter, tb._bucket_heads, self._values,
             self.max_D, tb.row_base_, indices, trange, T, policy, scores, ext.device_timestamp(), mode, p, self._seed,
             self._optimizer.initial_state_value, freq_in=frequency_counters, num_scores=tb.num_scores_)
-        self._prefetch_states.append(PrefetchState(uk, rev, utids if T > 1 else None, slots, rows, indices.numel(), nu))
+        st = PrefetchState(uk, rev, utids if T > 1 else None, slots, rows, indices.numel(), nu)
+        if (self.training and self.pooling_mode == DynamicEmbPoolingMode.NONE and torch.is_grad_enabled()) or self._force_prepare:
+            # the gradient-independent half of the fused backward (pair list + sort) starts now, on a side stream, under the forward gather
+            if self._bwd_prep is None:
+                self._bwd_prep = ext.BackwardPrep()
+            st.bwd_ws = ext.backward_prepare(self._bwd_prep, self.max_D, rev, max(st.num_unique_bound, 1))
+        self._prefetch_states.append(st)
         self._update_score()
 
     def _unpin(self, st: PrefetchState) -> None:
@@ -416,7 +425,11 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         def step():
             # the same kernels as forward() + backward(), called directly: autograd would make the capture stream wait on
             # events of the streams that produced `grad_static` (cudaErrorStreamCaptureIsolation)
-            self.prefetch(indices, offsets_i)
+            self._force_prepare = self.pooling_mode == DynamicEmbPoolingMode.NONE     # no autograd here, but the backward does follow
+            try:
+                self.prefetch(indices, offsets_i)
+            finally:
+                self._force_prepare = False
             st = self._prefetch_states.popleft()
             out_ = _LookupFunction.forward(_NoCtx(), self, st, offsets_i, B, None)
             loss_ = out_.sum() if with_loss else None
@@ -424,7 +437,8 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
             pooled = self.pooling_mode != DynamicEmbPoolingMode.NONE
             ext.backward(self._values, self.max_D, st.reverse_indices, max(st.num_unique_bound, 1), st.rows, grad_static,
                          offsets=offsets_i if pooled else None, batch_size=B if pooled else 0, num_features=self.feature_num if pooled else 0,
-                         combiner=int(self.pooling_mode) if pooled else -1, **self._optimizer.kernel_kwargs())
+                         combiner=int(self.pooling_mode) if pooled else -1, prepared=(self._bwd_prep, st.bwd_ws) if st.bwd_ws is not None else None,
+                         **self._optimizer.kernel_kwargs())
             self._unpin(st)
             return out_, loss_
 

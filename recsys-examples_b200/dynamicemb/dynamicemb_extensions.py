@@ -6,6 +6,8 @@ exceptions on error — the same calling convention the reference Python package
 import enum
 from typing import List, Optional, Tuple
 
+import ctypes
+
 import torch
 
 from . import _native as N
@@ -334,18 +336,53 @@ def copy_rows(values, width, rows, dense, to_table: bool):
                                  1 if to_table else 0, N.stream()), "copy_rows")
 
 
+class BackwardPrep:
+    """Side stream + fork/join events for `backward_prepare` (one per module)."""
+
+    def __init__(self):
+        h = ctypes.c_void_p()
+        N.check(N.lib.demb_bwd_prep_create(ctypes.byref(h)), "bwd_prep_create")
+        self.handle = h
+
+    def __del__(self):
+        try:
+            N.lib.demb_bwd_prep_destroy(self.handle)
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
+def backward_prepare(prep: BackwardPrep, emb_dim: int, inverse: torch.Tensor, num_unique_bound: int) -> Optional[torch.Tensor]:
+    """Sequence mode: launch the gradient-independent half of `backward` (pair list + radix sort by unique index) NOW, on the prep handle's
+    stream, behind everything already enqueued on the current stream.  Returns the workspace to hand to backward(..., prepared=(prep, ws))."""
+    n = inverse.numel()
+    if n == 0:
+        return None
+    ws = torch.empty(N.lib.demb_backward_workspace_bytes(n, emb_dim), dtype=torch.uint8, device=inverse.device)
+    N.check(N.launch("backward_prepare", 2, N.lib.demb_backward_prepare, prep.handle, emb_dim, n, N.ptr(inverse), int(num_unique_bound), None, 0, 0, -1,
+                     N.ptr(ws), ws.numel(), N.stream()), "backward_prepare")
+    return ws
+
+
 def backward(values, emb_dim, inverse, num_unique_bound, rows, grads, *, offsets=None, batch_size=0, num_features=0, combiner=-1,
-             opt_type=0, lr=0.0, eps=1e-8, beta1=0.9, beta2=0.999, weight_decay=0.0, bc1=1.0, bc2=1.0, want_unique_grads=False):
-    """Fused reduce_grads + optimizer row update.  grads: [n, D] (sequence) or [B, F*D] (pooled)."""
+             opt_type=0, lr=0.0, eps=1e-8, beta1=0.9, beta2=0.999, weight_decay=0.0, bc1=1.0, bc2=1.0, want_unique_grads=False, prepared=None):
+    """Fused reduce_grads + optimizer row update.  grads: [n, D] (sequence) or [B, F*D] (pooled).
+    prepared = (BackwardPrep, workspace) from backward_prepare(same inverse / bound): only the gradient-dependent half runs here."""
     n = inverse.numel()
     dev = inverse.device
     ug = torch.zeros(num_unique_bound, emb_dim, dtype=torch.float32, device=dev) if want_unique_grads else None
     if n == 0:
         return ug
     grads = grads.contiguous()
+    vstride = values.stride(0) if values is not None else emb_dim
+    if prepared is not None and prepared[1] is not None:
+        prep, ws = prepared
+        N.check(N.launch("backward", 3, N.lib.demb_backward_prepared, prep.handle, N.ptr(values), vstride, emb_dim, n, N.ptr(inverse), int(num_unique_bound),
+                         N.ptr(rows), N.ptr(grads), emb_dim, N.ptr(_i64(offsets)), batch_size, num_features, combiner, int(opt_type), lr, eps, beta1, beta2,
+                         weight_decay, bc1, bc2, N.ptr(ug), N.ptr(ws), ws.numel(), N.stream()), "backward")
+        return ug
     ws_bytes = N.lib.demb_backward_workspace_bytes(n, emb_dim)
     ws = N.workspace(ws_bytes, dev)
-    N.check(N.launch("backward", 3, N.lib.demb_backward, N.ptr(values), values.stride(0) if values is not None else emb_dim, emb_dim, n, N.ptr(inverse),
+    N.check(N.launch("backward", 3, N.lib.demb_backward, N.ptr(values), vstride, emb_dim, n, N.ptr(inverse),
                                 int(num_unique_bound), N.ptr(rows), N.ptr(grads), emb_dim, N.ptr(_i64(offsets)), batch_size, num_features,
                                 combiner, int(opt_type), lr, eps, beta1, beta2, weight_decay, bc1, bc2, N.ptr(ug), N.ptr(ws), ws.numel(),
                                 N.stream()), "backward")
