@@ -352,7 +352,7 @@ def main():
     for i in range(args.warmup):
         timed_step(batches[i])
     # untimed settle of exactly the timed path (~0.5 s): clocks / power state reach the level they hold in a long-running job
-    t_settle = time.time() + 0.5
+    t_settle = time.time() + (0.5 if world == 1 else 0.0)      # N>1: a time-based loop would desynchronise the ranks' collective counts
     i = 0
     while time.time() < t_settle:
         timed_step(batches[i % total])
@@ -390,22 +390,21 @@ def main():
     N.lib.demb_profile_enable(0)
     # the timed region lasts tens of ms — shorter than one nvidia-smi sample — so clocks / throttle reasons are sampled over a
     # ~2 s continuation of exactly the same steps (not part of any reported time)
-    clocks = ClockSampler(local)
-    clocks.start()
-    t_end = time.time() + 2.0
-    i = 0
-    while time.time() < t_end:
-        timed_step(batches[args.warmup + (i % args.steps)])
-        i += 1
-        if i % 8 == 0:
-            torch.cuda.synchronize()
-    torch.cuda.synchronize()
-    clk = clocks.stop()
-    clk["note"] = "sampled every 100 ms over a 2 s continuation of the timed steps"
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    # the same number of continuation steps on every rank (a time-based loop would desynchronise the ranks' collective counts)
+    n_cont = max(8, int(2000.0 / max(ms / args.steps, 1e-3)))
+    clocks = ClockSampler(local)
+    clocks.start()
+    for i in range(n_cont):
+        timed_step(batches[args.warmup + (i % args.steps)])
+        if i % 8 == 7:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    clk["note"] = "sampled every 100 ms over a 2 s continuation of the timed steps"
     value = world * n_ids * args.steps / (ms / 1e3)
     step_mode = "cuda-graph step (module.make_graphed_step)" if graphed is not None else ("eager step" + (f" (graph capture failed: {graph_err})" if graph_err else ""))
 
