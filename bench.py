@@ -351,19 +351,11 @@ def main():
 
     for i in range(args.warmup):
         timed_step(batches[i])
-    # untimed settle of exactly the timed path (~0.5 s): clocks / power state reach the level they hold in a long-running job
-    t_settle = time.time() + (0.5 if world == 1 else 0.0)      # N>1: a time-based loop would desynchronise the ranks' collective counts
-    i = 0
-    while time.time() < t_settle:
-        timed_step(batches[i % total])
-        i += 1
-        if i % 8 == 0:
-            torch.cuda.synchronize()
     if world > 1:
         # the eager sharded step allocates temporaries whose sizes follow the per-step unique counts: give the caching allocator enough
         # untimed steps to stop calling cudaMalloc (each call synchronises the device) before the K timed steps
         for i in range(40):
-            timed_step(batches[i % total])
+            timed_step(power_law_ids(n_ids, gen, dev))               # fresh ids, like every timed step
     barrier()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
@@ -378,7 +370,7 @@ def main():
     N.LAUNCHES[0] = 0
     n_prof = min(args.steps, 8)
     for i in range(n_prof):
-        step(batches[args.warmup + i])
+        step(power_law_ids(n_ids, gen, dev))                        # fresh ids: the same mix of hits / new keys as the timed steps
     torch.cuda.synchronize()
     launches = N.LAUNCHES[0] // n_prof
     prof = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in N.PROFILE.items()}
@@ -411,7 +403,7 @@ def main():
     # ---- e2e: the public API with HOST inputs: pinned ids -> H2D, step (prefetch + forward + fused backward), loss stand-in
     # (sum of the looked-up rows) -> D2H, every step.  N=1 uses the module's CUDA-graph step (make_graphed_step): the fused
     # prefetch has no host sync, so the whole step replays as one graph launch.
-    host_batches = [b.cpu().pin_memory() for b in batches[args.warmup:]]
+    host_batches = [power_law_ids(n_ids, gen, dev).cpu().pin_memory() for _ in range(args.steps + 3)]      # fresh ids (3 for the warm-up pass)
     host_res = torch.zeros(len(host_batches), dtype=torch.float32).pin_memory()
     # Input pipeline as a trainer runs it: the H2D copy of step i+1 goes through a copy stream into one of two staging buffers while step
     # i computes; the 4-byte result of step i is read back asynchronously and consumed (host sync) one step later.  Every byte still
@@ -450,7 +442,7 @@ def main():
     e2e_pass(host_batches[:3])                       # untimed warm-up of exactly this path (first launch of this graph, copy stream, staging)
     barrier()
     e0.record()
-    e2e_pass(host_batches)
+    e2e_pass(host_batches[3:])
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
