@@ -102,4 +102,40 @@ __device__ __forceinline__ InsertOutcome warp_insert_one(const Table& t, int64_t
   return o;
 }
 
+// The same insert executed by ONE thread (its bucket must not be touched by any other thread of the grid): probe with probe_thread,
+// serial eviction scan.  Identical outcome to warp_insert_one — same probe order, same "first minimum in storage order" victim.
+__device__ __forceinline__ InsertOutcome thread_insert_one(const Table& t, int64_t b, uint64_t key, uint64_t score, int pol, uint64_t ts,
+                                                           int32_t* bucket_sizes, const int32_t* counter) {
+  uint8_t* bk = t.bucket(b);
+  uint64_t* keys = t.keys(bk);
+  uint8_t* dig = t.digests(bk);
+  const int64_t h = hash63(key);
+  int64_t empty = -1;
+  const int64_t hit = probe_thread(t, bk, key, h, &empty);
+  InsertOutcome o{kInit, -1, score, 0, 0};
+  if (hit >= 0) { o.result = kAssignHit; o.it = hit; }
+  else if (empty >= 0) { o.result = kInsert; o.it = empty; }
+  else {
+    uint64_t best = 0xFFFFFFFFFFFFFFFFull; int64_t bi = -1; uint64_t bkey = 0;
+    for (int64_t j = 0; j < t.C; ++j) {
+      const uint64_t s = __ldcv(t.scores(bk, j) + (t.ns - 1));
+      if (s < best) {
+        const uint64_t k = __ldcv(keys + j);
+        if (k != kLockedKey && k != kEmptyKey && !(counter && __ldcv(counter + b * t.C + j) > 0)) { best = s; bi = j; bkey = k; }
+      }
+    }
+    if (bi >= 0) { o.it = bi; o.ev_key = bkey; o.ev_score = best; o.result = (bkey == kReclaimKey) ? kReclaim : kEvict; }
+    else { o.result = kBusy; o.ev_key = key; o.ev_score = score; }
+  }
+  if (o.result <= kEvict) {
+    uint64_t* sc = t.scores(bk, o.it);
+    if (o.result == kInsert || o.result == kReclaim || o.result == kEvict) dig[o.it] = digest_of(h);
+    if (o.result == kInsert || o.result == kReclaim) bucket_sizes[b] += 1;
+    if (o.result == kEvict) for (int s = 0; s < t.ns; ++s) sc[s] = 0;
+    o.score = policy_update(pol, sc, score, ts, false);
+    *reinterpret_cast<volatile uint64_t*>(keys + o.it) = key;
+  }
+  return o;
+}
+
 }  // namespace demb

@@ -7,10 +7,15 @@
 //   2. train_lookup_kernel (thread per unique)    probe; hit: score update + pin + slot/row out
 //                                                 miss: push the key on its bucket's list (atomicExch on heads[bucket]); the first
 //                                                 pusher records the bucket in `touched`
-//   3. train_insert_kernel (warp per touched bucket, persistent grid, device-side count)
-//                                                 pops the bucket's list, orders it by key (the reference's deterministic order:
-//                                                 (bucket, key), scored_hashtable.py:1451-1557), inserts sequentially with the shared
-//                                                 warp_insert_one, initialises the new row [emb | optimizer state] and pins it.
+//   3. train_insert_thread_kernel (THREAD per touched bucket, device-side count)
+//                                                 a bucket that cannot overflow (size + new keys <= capacity — all of them until the table
+//                                                 fills up): walks the bucket's list in key order (the reference's deterministic order:
+//                                                 (bucket, key), scored_hashtable.py:1451-1557) and inserts with thread_insert_one; marks the
+//                                                 new keys.  ncu on the warp-per-bucket form: 500 warp instructions per inserted key with one
+//                                                 useful lane in most of them (116 M warp instructions per step, issue-bound at 211 us).
+//      train_insert_kernel (warp per bucket)      only the buckets that may have to evict (cooperative 128-slot victim scan); inserts,
+//                                                 initialises and pins inline as before.
+//   4. train_init_rows_kernel (warp per new key)  [emb | optimizer state] of the rows inserted by the thread kernel: pure streaming writes.
 // The resulting table image is identical to lookup + demb_table_insert + demb_init_rows run op by op (tests/test_demb_train_gpu.py).
 #include "../../include/dynamicemb_b200.h"
 #include "demb_common.cuh"
@@ -56,12 +61,13 @@ __global__ void train_lookup_kernel(TrainArgs a) {
         atomicAdd(a.counter + L.bucket * a.t.C + it, 1);                          // pin (increment_counter, :607)
       } else {
         const int old = atomicExch(a.heads + L.bucket, (int)u);
-        a.next[u] = old;
+        a.next[u] = old;                                                          // >= -1: list link
         if (old == -1) a.touched[atomicAdd(a.n_touched, 1ull)] = (int32_t)L.bucket;
       }
     }
     a.slots[u] = slot;
     a.rows[u] = row;
+    if (slot >= 0 || L.cap <= 0) a.next[u] = -3;                                  // not on any list (train_init_rows_kernel reads next[u] of every u)
   }
 }
 
@@ -133,6 +139,60 @@ __global__ void __launch_bounds__(kBlock) train_insert_kernel(TrainArgs a) {
   }
 }
 
+// Thread per touched bucket (see the file header).  Buckets that might overflow are handed to the warp kernel through touched2.
+__global__ void __launch_bounds__(kBlock) train_insert_thread_kernel(TrainArgs a, int32_t* __restrict__ touched2, unsigned long long* n_touched2) {
+  const int64_t nt = (int64_t)*a.n_touched;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nt; w += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = a.touched[w];
+    const int head = a.heads[b];
+    int cnt = 0;
+    for (int cur = head; cur != -1; cur = a.next[cur]) ++cnt;
+    if (a.bucket_sizes[b] + cnt > a.t.C) {                                        // may evict: cooperative scan in the warp kernel
+      touched2[atomicAdd(n_touched2, 1ull)] = (int32_t)b;
+      continue;
+    }
+    bool have_last = false; uint64_t last = 0;
+    for (int r = 0; r < cnt; ++r) {                                               // lists are 1-3 long: repeated selection of the next key in order
+      uint64_t best = 0; int bu = -1;
+      for (int cur = head; cur != -1; cur = a.next[cur]) {
+        const uint64_t k = a.ukeys[cur];
+        if (have_last && !key_less(last, k, a.key_is_signed)) continue;
+        if (bu < 0 || key_less(k, best, a.key_is_signed)) { best = k; bu = cur; }
+      }
+      const int64_t tid = a.utids ? a.utids[bu] : 0;
+      const InsertOutcome o = thread_insert_one(a.t, b, best, train_score(a, bu, tid), a.pol, a.ts, a.bucket_sizes, a.counter);
+      if (o.result <= kEvict) {
+        const int64_t slot = (b - a.t.bkt_off[tid]) * a.t.C + o.it;
+        a.slots[bu] = slot;
+        a.rows[bu] = (a.row_base ? a.row_base[tid] : 0) + slot;
+        atomicAdd(a.counter + b * a.t.C + o.it, 1);                               // pin
+      }
+      last = best; have_last = true;
+    }
+    for (int cur = head; cur != -1;) {                                            // the list is consumed: turn its links into "initialise me" marks
+      const int nx = a.next[cur];
+      a.next[cur] = a.slots[cur] >= 0 ? -2 : -4;
+      cur = nx;
+    }
+    a.heads[b] = -1;                                                              // leave the list heads clean for the next step
+  }
+}
+
+// Warp per unique key: rows inserted by the thread kernel (next[u] == -2) get initializer + optimizer state (fused A10 + A11).
+__global__ void __launch_bounds__(kBlock) train_init_rows_kernel(TrainArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = *a.n_u;
+  const int64_t wstride = (int64_t)gridDim.x * (kBlock / 32);
+  const int D4 = a.D >> 2, V4 = (int)(a.vdim >> 2);
+  for (int64_t u = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); u < n; u += wstride) {
+    if (a.next[u] != -2) continue;
+    const int64_t row = a.rows[u];
+    const uint64_t key = a.ukeys[u];
+    for (int c = lane; c < D4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, init4(a.init, key, c));
+    for (int c = D4 + lane; c < V4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, make_float4(a.state_init, a.state_init, a.state_init, a.state_init));
+  }
+}
+
 __global__ void counter_update_n_kernel(int32_t* counter, const int64_t* __restrict__ slots, const int64_t* __restrict__ tids,
                                         const int64_t* __restrict__ bkt_off, int64_t C, const int64_t* __restrict__ n_dev, int delta) {
   const int64_t n = *n_dev;
@@ -159,7 +219,7 @@ int demb_fill_i32(int32_t* p, int64_t n, int32_t v, void* stream) {
 }
 
 int64_t demb_train_prefetch_workspace_bytes(int64_t n, int num_tables) {
-  return demb_segmented_unique_workspace_bytes(n, num_tables) + (int64_t)(2 * align256(4 * (size_t)(n > 0 ? n : 1)) + 512);
+  return demb_segmented_unique_workspace_bytes(n, num_tables) + (int64_t)(3 * align256(4 * (size_t)(n > 0 ? n : 1)) + 512);
 }
 
 int demb_train_prefetch(void* storage, const int64_t* table_bucket_offsets, int64_t bucket_capacity, int num_scores, int32_t* bucket_sizes,
@@ -176,9 +236,11 @@ int demb_train_prefetch(void* storage, const int64_t* table_bucket_offsets, int6
   uint8_t* w = (uint8_t*)workspace;
   int32_t* next = (int32_t*)w; w += align256(4 * (size_t)n);
   int32_t* touched = (int32_t*)w; w += align256(4 * (size_t)n);
+  int32_t* touched2 = (int32_t*)w; w += align256(4 * (size_t)n);
   unsigned long long* n_touched = (unsigned long long*)w; w += 256;
+  unsigned long long* n_touched2 = n_touched + 1;
   const int64_t uws = (int64_t)((uint8_t*)workspace + workspace_bytes - w);
-  cudaMemsetAsync(n_touched, 0, 8, stream);
+  cudaMemsetAsync(n_touched, 0, 16, stream);
   const bool need_freq = (policy == kAccumulate || policy == kLruLfu);
   int rc = demb_segmented_unique(n, keys, table_range, num_tables, freq_in, unique_keys, reverse_indices, nullptr, need_freq ? unique_freq : nullptr,
                                  unique_table_ids, num_unique, w, uws, stream_);
@@ -192,7 +254,11 @@ int demb_train_prefetch(void* storage, const int64_t* table_bucket_offsets, int6
   a.init = InitArgs{init_mode, p0, p1, p2, p3, seed}; a.state_init = state_init;
   a.slots = slots; a.rows = rows; a.next = next; a.touched = touched; a.n_touched = n_touched;
   train_lookup_kernel<<<grid_for(n), kBlock, 0, stream>>>(a);
-  train_insert_kernel<<<148 * 4, kBlock, 0, stream>>>(a);
+  train_insert_thread_kernel<<<grid_for(n), kBlock, 0, stream>>>(a, touched2, n_touched2);
+  TrainArgs a2 = a;
+  a2.touched = touched2; a2.n_touched = n_touched2;
+  train_insert_kernel<<<148 * 4, kBlock, 0, stream>>>(a2);                       // buckets that may evict (none until the table fills up)
+  train_init_rows_kernel<<<148 * 8, kBlock, 0, stream>>>(a);
   DEMB_CHECK_LAST();
   return 0;
 }
