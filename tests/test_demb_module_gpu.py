@@ -169,6 +169,40 @@ def test_fused_prefetch_matches_op_by_op(cuda, pooling, T):
     assert ma.tables.size() > 1000
 
 
+def test_fused_prefetch_with_erasures_and_negative_keys(cuda):
+    """Same equivalence with the cases the thread-per-bucket insert adds: erased (reclaimable) slots inside buckets that are not
+    full, and negative int64 keys (the deterministic order inside a bucket is by SIGNED key)."""
+    from dynamicemb import DynamicEmbPoolingMode, EmbOptimType
+    ma = _module(cuda, EmbOptimType.EXACT_ADAGRAD, DynamicEmbPoolingMode.NONE, D=64, n_tables=1, cap=4096, learning_rate=0.05, fused_prefetch=True)
+    mb = _module(cuda, EmbOptimType.EXACT_ADAGRAD, DynamicEmbPoolingMode.NONE, D=64, n_tables=1, cap=4096, learning_rate=0.05, fused_prefetch=False)
+    ma.train(); mb.train()
+    rng = np.random.default_rng(77)
+    n = 600
+    offsets = torch.arange(0, n + 1, dtype=torch.int64, device=cuda)
+    seen = set()
+    for it in range(30):
+        raw = (rng.zipf(1.15, size=n) % 5000).astype(np.int64) * 104729
+        raw[rng.random(n) < 0.4] *= -1                                   # negative keys are legal (only the top four values are reserved)
+        ids = torch.from_numpy(raw).to(cuda)
+        oa, ob = ma(ids, offsets), mb(ids, offsets)
+        assert torch.equal(oa, ob), f"iter {it}: outputs differ"
+        g = torch.randn_like(oa)
+        oa.backward(g); ob.backward(g)
+        seen.update(raw.tolist())
+        if it % 3 == 2:                                                  # erase a third of what is there: leaves reclaimable slots behind
+            pool = np.array(sorted(seen), dtype=np.int64)
+            drop = rng.choice(pool, size=max(1, pool.size // 3), replace=False)
+            dk = torch.from_numpy(drop).to(cuda)
+            z = torch.zeros(drop.size, dtype=torch.int64, device=cuda)
+            ma.tables.erase(dk, z); mb.tables.erase(dk, z)
+            seen.difference_update(drop.tolist())
+        assert torch.equal(ma.tables.table_storage_, mb.tables.table_storage_), f"iter {it}: table image differs"
+        assert torch.equal(ma._values, mb._values), f"iter {it}: value rows differ"
+        assert torch.equal(ma.tables.bucket_sizes, mb.tables.bucket_sizes)
+        assert int(ma.tables._ref_counter.sum().item()) == 0 and int((ma.tables._bucket_heads != -1).sum().item()) == 0
+    assert ma.tables.size() > 200
+
+
 def test_graphed_step_matches_eager(cuda):
     """make_graphed_step (one CUDA graph per training step) leaves the same table / rows / outputs as the eager step."""
     from dynamicemb import DynamicEmbPoolingMode, EmbOptimType
