@@ -89,9 +89,8 @@ def _worker(rank, world, port, dist_mode, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dist_mode", ["roundrobin", "hash_roundrobin", "continuous"])
-def test_rw_dist_roundtrip_gloo(dist_mode):
-    world = 2
+@pytest.mark.parametrize("dist_mode,world", [("roundrobin", 2), ("hash_roundrobin", 2), ("continuous", 2), ("hash_roundrobin", 3)])
+def test_rw_dist_roundtrip_gloo(dist_mode, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
