@@ -122,3 +122,59 @@ def test_bench_reference_arm_prints_contract_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] in ("port", "reference")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_oracle_table_random_op_sequences():
+    """Property check of the oracle table on random insert / erase / lookup sequences (small table, so buckets fill up and evict).
+    After every operation: the key image has no duplicates; lookup finds exactly the keys of the image, at their slots; bucket_sizes
+    counts them; a successfully inserted key that was not evicted later is there; an evicted key that was not re-inserted is gone; the
+    four reserved key values are rejected as ILLEGAL; erased keys are gone."""
+    from hypothesis import given, settings, strategies as st
+    from oracle.dynamicemb import OracleTable
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.integers(0, 2 ** 31), st.lists(st.sampled_from(["ins", "ins", "ins", "erase", "look"]), min_size=3, max_size=12))
+    def run(seed, ops):
+        rng = np.random.default_rng(seed)
+        C = 16
+        o = OracleTable([C * 3], C)
+        step = 0
+
+        def image():
+            img = np.ascontiguousarray(o.keys_view()).reshape(-1).view(np.int64)
+            pos = np.nonzero((img != -1) & (img != -2) & (img != -3))[0]          # EmptyKey / ReclaimKey / LockedKey as int64
+            return {int(img[p]): int(p) for p in pos}, pos.size
+
+        for op in ops:
+            step += 1
+            if op == "ins":
+                keys = np.unique(rng.integers(-400, 400, size=int(rng.integers(1, 40)), dtype=np.int64))
+                idx, res, _, (ek, ei, es, _) = o.insert(keys, None, policy=1, score_in=np.full(keys.size, step, dtype=np.int64), use_counter=False)
+                ok = {int(k) for k, r in zip(keys.tolist(), res.tolist()) if r <= 3}
+                evicted = {int(k) for k in np.ascontiguousarray(ek).view(np.int64).tolist()}
+                for k, i, r in zip(keys.tolist(), idx.tolist(), res.tolist()):
+                    if -4 <= k <= -1:
+                        assert r == 6 and i < 0               # reserved values (types.cuh:117-121)
+                    else:
+                        assert r <= 3 or (r == 5 and i < 0)   # BUSY is the only failure of a legal key
+                now, _ = image()
+                assert all(k in now for k in ok - evicted)
+                assert all(k not in now for k in evicted - ok)
+            elif op == "erase":
+                now, _ = image()
+                if now:
+                    drop = rng.choice(np.array(sorted(now), dtype=np.int64), size=max(1, len(now) // 2), replace=False)
+                    o.erase(drop)
+                    after, _ = image()
+                    assert all(int(k) not in after for k in drop.tolist())
+            now, n_live = image()
+            assert n_live == len(now)                                             # no duplicate keys
+            assert int(o.bucket_sizes.sum()) == n_live
+            probe = np.unique(np.concatenate([np.array(sorted(now), dtype=np.int64), rng.integers(-400, 400, size=20, dtype=np.int64)]))
+            _, found, slots = o.lookup(probe, None, policy=0)
+            for k, f, s in zip(probe.tolist(), found.tolist(), slots.tolist()):
+                assert bool(f) == (int(k) in now), (k, f)
+                if f:
+                    assert s == now[int(k)]
+
+    run()
