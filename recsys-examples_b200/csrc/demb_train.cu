@@ -46,28 +46,44 @@ __device__ __forceinline__ uint64_t train_score(const TrainArgs& a, int64_t u, i
 
 __global__ void train_lookup_kernel(TrainArgs a) {
   const int64_t n = *a.n_u;
-  for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x) {
-    const uint64_t key = a.ukeys[u];
-    const int64_t tid = a.utids ? a.utids[u] : 0;
-    Locus L = locate(a.t, key, tid);
-    int64_t slot = -1, row = -1;
-    if (L.cap > 0) {
-      uint8_t* bk = a.t.bucket(L.bucket);
-      const int64_t it = probe_thread(a.t, bk, key, L.h, nullptr);
-      if (it >= 0) {
-        if (a.pol != kConst) policy_update(a.pol, a.t.scores(bk, it), train_score(a, u, tid), a.ts, false);
-        slot = (L.bucket - L.bkt_begin) * a.t.C + it;
-        row = (a.row_base ? a.row_base[tid] : 0) + slot;
-        atomicAdd(a.counter + L.bucket * a.t.C + it, 1);                          // pin (increment_counter, :607)
-      } else {
-        const int old = atomicExch(a.heads + L.bucket, (int)u);
-        a.next[u] = old;                                                          // >= -1: list link
-        if (old == -1) a.touched[atomicAdd(a.n_touched, 1ull)] = (int32_t)L.bucket;
+  const int lane = threadIdx.x & 31;
+  // warp-uniform trip count (lanes past the end idle inside): the `touched` append below is warp-aggregated — one atomicAdd on the shared
+  // counter per warp instead of one per bucket (~150 K same-address atomics per step serialised this kernel at ~100 us)
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t u0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); u0 < n; u0 += stride) {
+    const int64_t u = u0 + lane;
+    int32_t first_bucket = -1;                                                    // >= 0: this lane pushed the FIRST key of that bucket
+    if (u < n) {
+      const uint64_t key = a.ukeys[u];
+      const int64_t tid = a.utids ? a.utids[u] : 0;
+      Locus L = locate(a.t, key, tid);
+      int64_t slot = -1, row = -1;
+      if (L.cap > 0) {
+        uint8_t* bk = a.t.bucket(L.bucket);
+        const int64_t it = probe_thread(a.t, bk, key, L.h, nullptr);
+        if (it >= 0) {
+          if (a.pol != kConst) policy_update(a.pol, a.t.scores(bk, it), train_score(a, u, tid), a.ts, false);
+          slot = (L.bucket - L.bkt_begin) * a.t.C + it;
+          row = (a.row_base ? a.row_base[tid] : 0) + slot;
+          atomicAdd(a.counter + L.bucket * a.t.C + it, 1);                        // pin (increment_counter, :607)
+        } else {
+          const int old = atomicExch(a.heads + L.bucket, (int)u);
+          a.next[u] = old;                                                        // >= -1: list link
+          if (old == -1) first_bucket = (int32_t)L.bucket;
+        }
       }
+      a.slots[u] = slot;
+      a.rows[u] = row;
+      if (slot >= 0 || L.cap <= 0) a.next[u] = -3;                                // not on any list (train_init_rows_kernel reads next[u] of every u)
     }
-    a.slots[u] = slot;
-    a.rows[u] = row;
-    if (slot >= 0 || L.cap <= 0) a.next[u] = -3;                                  // not on any list (train_init_rows_kernel reads next[u] of every u)
+    const unsigned m = __ballot_sync(0xffffffffu, first_bucket >= 0);
+    if (m) {
+      const int leader = __ffs(m) - 1;
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(a.n_touched, (unsigned long long)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (first_bucket >= 0) a.touched[base + __popc(m & ((1u << lane) - 1u))] = first_bucket;
+    }
   }
 }
 
