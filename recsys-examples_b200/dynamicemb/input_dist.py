@@ -136,3 +136,37 @@ def rw_output_dist(rows_fm: torch.Tensor, ctx: DistContext, group, expand: Optio
         return _PermuteRows.apply(back, ctx.unbucketize_permute, _inverse_permutation(ctx.unbucketize_permute))
     assert reduce_fn is not None
     return _ExpandRows.apply(back, ctx.unbucketize_permute[expand], reduce_fn)
+
+
+def rw_sharded_lookup(ids: torch.Tensor, lengths: torch.Tensor, num_features: int, group, *, local_fn: Callable, bucketize_fn: Callable,
+                      unique_fn: Optional[Callable] = None, reduce_fn: Optional[Callable] = None) -> torch.Tensor:
+    """The whole row-wise sharded sequence lookup of one rank's batch, device work injected as callables (so the host logic — dedup
+    re-spread, exchanges, regrouping, un-bucketize / un-dedup and their backward — runs under gloo on CPU in the tests):
+
+      unique_fn(ids, table_range[F+1], F) -> (num_unique: int, unique_ids[>=num_unique], reverse[n], unique_offsets[F+1])   (None = no dedup)
+      bucketize_fn(lengths[F*B], ids)     -> (new_lengths[W*F*B] rank-major, new_ids rank-major, unbucketize_permute)
+      local_fn(ids_fm, offsets_fm)        -> rows [n_recv, D] of this rank's table for the received ids (feature-major), differentiable
+      reduce_fn(idx, grad[n, D], num_rows)-> [num_rows, D] per-source-row sums (backward of the final expanding gather)
+
+    Mirrors ShardedDynamicEmbeddingCollection.input_dist / compute / output_dist (shard/embedding.py:183-340)."""
+    F = num_features
+    B = lengths.numel() // F
+    reverse = None
+    if unique_fn is not None:
+        # _dedup_indices (shard/embedding.py:183-275): send each distinct id once per rank.  Unique ids of a feature are
+        # re-spread over that feature's B slots (compute_dedup_lengths, unique_op.cu:753) so the KJT stays well-formed.
+        offsets = torch.zeros(lengths.numel() + 1, dtype=torch.int64, device=ids.device)
+        torch.cumsum(lengths, 0, out=offsets[1:])
+        trange = offsets[:: B].contiguous()                      # one "table" per feature for dedup purposes
+        nu, uk, reverse, toffs = unique_fn(ids, trange, F)
+        ids = uk[:nu]
+        per_f = (toffs[1:] - toffs[:-1])                          # unique count per feature
+        base = per_f // B
+        rem = per_f - base * B
+        lengths = (base[:, None] + (torch.arange(B, device=ids.device)[None, :] < rem[:, None]).to(torch.int64)).reshape(-1)
+    ids_fm, lengths_fm, ctx = rw_input_dist(ids, lengths.to(torch.int64), B, F, group, bucketize_fn)
+    offsets_fm = torch.zeros(lengths_fm.numel() + 1, dtype=torch.int64, device=ids.device)
+    torch.cumsum(lengths_fm, 0, out=offsets_fm[1:])
+    rows = local_fn(ids_fm, offsets_fm)
+    return rw_output_dist(rows, ctx, group, expand=reverse, reduce_fn=reduce_fn)
+

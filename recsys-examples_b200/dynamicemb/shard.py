@@ -17,7 +17,7 @@ from torch import nn
 
 from . import dynamicemb_extensions as ext
 from .batched_dynamicemb_tables import BatchedDynamicEmbeddingTablesV2
-from .input_dist import rw_input_dist, rw_output_dist
+from .input_dist import rw_sharded_lookup
 from .types import DynamicEmbPoolingMode
 
 
@@ -45,28 +45,13 @@ class RowWiseShardedDynamicEmbedding(nn.Module):
         nl, ni, _, perm = ext.block_bucketize_sparse_features(lengths, ids, B, self.world_size, self._block_sizes, self._dist_type, sequence=True)
         return nl, ni, perm
 
+    def _unique(self, ids, trange, F):
+        num_u, uk, reverse, toffs, _ = ext.segmented_unique_cuda(ids, trange, F, None)
+        return int(num_u.item()), uk, reverse, toffs                 # host sync: the exchange sizes depend on it
+
     def forward(self, ids: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
-        F = self.local.feature_num
-        B = lengths.numel() // F
-        reverse = None
-        if self.use_index_dedup:
-            # _dedup_indices (shard/embedding.py:183-275): send each distinct id once per rank.  Unique ids of a feature are
-            # re-spread over that feature's B slots (compute_dedup_lengths, unique_op.cu:753) so the KJT stays well-formed.
-            offsets = torch.zeros(lengths.numel() + 1, dtype=torch.int64, device=ids.device)
-            torch.cumsum(lengths, 0, out=offsets[1:])
-            trange = offsets[:: B].contiguous()                      # one "table" per feature for dedup purposes
-            num_u, uk, reverse, toffs, _ = ext.segmented_unique_cuda(ids, trange, F, None)
-            nu = int(num_u.item())
-            ids = uk[:nu]
-            per_f = (toffs[1:] - toffs[:-1])                          # unique count per feature
-            base = per_f // B
-            rem = per_f - base * B
-            lengths = (base[:, None] + (torch.arange(B, device=ids.device)[None, :] < rem[:, None]).to(torch.int64)).reshape(-1)
-        ids_fm, lengths_fm, ctx = rw_input_dist(ids, lengths.to(torch.int64), B, F, self.group, self._bucketize)
-        offsets_fm = torch.zeros(lengths_fm.numel() + 1, dtype=torch.int64, device=ids.device)
-        torch.cumsum(lengths_fm, 0, out=offsets_fm[1:])
-        rows = self.local(ids_fm, offsets_fm)
-        return rw_output_dist(rows, ctx, self.group, expand=reverse, reduce_fn=self._reduce_rows)
+        return rw_sharded_lookup(ids, lengths, self.local.feature_num, self.group, local_fn=self.local, bucketize_fn=self._bucketize,
+                                 unique_fn=self._unique if self.use_index_dedup else None, reduce_fn=self._reduce_rows)
 
     @staticmethod
     def _reduce_rows(idx, grad, num_rows):

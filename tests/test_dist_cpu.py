@@ -102,3 +102,83 @@ def test_rw_dist_roundtrip_gloo(dist_mode, world):
         p.join(timeout=60)
     for r, msg in res:
         assert msg == "ok", f"rank {r}: {msg}"
+
+
+def _worker_sharded(rank, world, port, dedup, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "recsys-examples_b200"))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dynamicemb.input_dist import rw_sharded_lookup
+        from oracle import dynamicemb as orc
+        rng = np.random.default_rng(500 + rank)
+        B, F, D, M = 6, 2, 4, 997
+        lengths = rng.integers(0, 7, size=F * B).astype(np.int64)
+        ids = rng.integers(0, 60, size=int(lengths.sum()), dtype=np.int64) * 13          # many repeats inside a feature
+        blk = np.array([1 << 40] * F, dtype=np.int64)
+        dts = [2] * F                                                                   # hash_roundrobin
+
+        def bucketize(l, i):
+            nl, ni, perm = orc.block_bucketize(l.numpy(), i.numpy(), B, world, blk, dts)
+            return torch.from_numpy(nl), torch.from_numpy(ni), torch.from_numpy(perm)
+
+        def unique(i, trange, nf):
+            uk, inv, offs = orc.segmented_unique(i.numpy(), trange.numpy())
+            return int(uk.size), torch.from_numpy(uk), torch.from_numpy(inv), torch.from_numpy(offs)
+
+        torch.manual_seed(7)                                                            # the same "table" on every rank
+        W = torch.randn(M, D, requires_grad=True)
+        served = []
+
+        def local(ids_fm, offsets_fm):
+            assert int(offsets_fm[-1]) == ids_fm.numel() and offsets_fm.numel() == F * world * B + 1
+            owner = orc.dest_rank(ids_fm.numpy(), "hash_roundrobin", world, 1)
+            assert (owner == rank).all(), "received an id this rank does not own"
+            served.append(ids_fm.clone())
+            return W[ids_fm % M]
+
+        reduce_fn = lambda idx, g, n: torch.zeros(n, g.shape[1]).index_add_(0, idx, g)
+        out = rw_sharded_lookup(torch.from_numpy(ids), torch.from_numpy(lengths), F, None, local_fn=local, bucketize_fn=bucketize,
+                                unique_fn=unique if dedup else None, reduce_fn=reduce_fn)
+        tid = torch.from_numpy(ids)
+        assert torch.equal(out.detach(), W.detach()[tid % M]), "rows came back to the wrong ids"
+        if dedup:                                                                       # each distinct (feature, id) travels once per rank
+            per_feature = [np.unique(ids[int(lengths[:f * B].sum()): int(lengths[:(f + 1) * B].sum())]).size for f in range(F)]
+            sent = [None] * world
+            dist.all_gather_object(sent, int(sum(per_feature)))
+            got = [None] * world
+            dist.all_gather_object(got, int(served[0].numel()))
+            assert sum(sent) == sum(got)
+        g = torch.from_numpy(rng.standard_normal((ids.size, D)).astype(np.float32))
+        out.backward(g)
+        dist.all_reduce(W.grad)                                                         # every rank served part of every rank's gradient
+        everyone = [None] * world
+        dist.all_gather_object(everyone, (ids, g.numpy()))
+        want = torch.zeros(M, D)
+        for i_r, g_r in everyone:
+            want.index_add_(0, torch.from_numpy(i_r) % M, torch.from_numpy(g_r))
+        assert torch.allclose(W.grad, want, rtol=1e-5, atol=1e-5), "gradient did not reach the owning rows"
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,dedup", [(2, True), (2, False), (3, True)])
+def test_rw_sharded_lookup_end_to_end_gloo(world, dedup):
+    """The full host logic of RowWiseShardedDynamicEmbedding.forward/backward (dedup re-spread, exchanges, regrouping for F > 1,
+    un-bucketize + un-dedup gather and its reducing backward) with CPU stand-ins for the kernels."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_sharded, args=(r, world, port, dedup, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for r, msg in res:
+        assert msg == "ok", f"rank {r}: {msg}"
