@@ -59,6 +59,10 @@ extern "C" {
 #define DEMB_OPT_ADAGRAD 3
 #define DEMB_OPT_ROWWISE_ADAGRAD 4
 
+/* Per-table initializer arguments (device array indexed by table id; the reference builds one initializer per table,
+ * dynamicemb/batched_dynamicemb_tables.py:789-796).  Same meaning as the scalar (mode, p0..p3, seed) arguments below. */
+typedef struct { int32_t mode; float p0, p1, p2, p3; uint32_t reserved; uint64_t seed; } demb_init_args_t;
+
 /* ---- hash table (replaces src/table_operation/{lookup,insert,insert_and_evict,erase,export_batch,bucketize}.cu) ---- */
 
 /* scored_hashtable.py:476-496 _init_table: keys=~0, digests=digest(~0), scores=0 */
@@ -132,9 +136,11 @@ int demb_gather_forward(const float* values, int64_t value_dim, int emb_dim, int
 int demb_rows_from_slots(int64_t n, const int64_t* slots, const int64_t* table_ids, const int64_t* row_base, int64_t* rows, void* stream);
 /* initializer + store_to_flat fused (initializer.cu, dynamic_emb_op.cu:400-490): values[rows[i]] = [init(keys[i]) | state_init];
  * params: UNIFORM(p0=lower,p1=upper) NORMAL(p0=mean,p1=std) TRUNCATED_NORMAL(+p2=lower,p3=upper) CONSTANT(p0) DEBUG(key%100000).
+ * table_init (device, nullable) + table_ids[n] (nullable => 0): per-table arguments that override the scalars.
  * only_if[n] (nullable) masks rows; emb_out[n,D] (nullable) also receives the embedding. */
 int demb_init_rows(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* rows, const void* keys, int mode, float p0, float p1,
-                   float p2, float p3, uint64_t seed, float state_init, const uint8_t* only_if, float* emb_out, void* stream);
+                   float p2, float p3, uint64_t seed, const int64_t* table_ids, const demb_init_args_t* table_init, float state_init,
+                   const uint8_t* only_if, float* emb_out, void* stream);
 /* load_from_flat_table / store_to_flat_table (dynamic_emb_op.cu:295-490): copy `width` floats per row table<->dense */
 int demb_copy_rows(float* values, int64_t value_dim, int width, int64_t n, const int64_t* rows, float* dense, int64_t dense_stride, int to_table,
                    void* stream);
@@ -145,16 +151,14 @@ int demb_backward(float* values, int64_t value_dim, int emb_dim, int64_t n, cons
                   int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
                   float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, void* stream);
 /* Split form: the gradient-independent half of demb_backward (pair list + radix sort by unique index) can be launched right after the
-   prefetch; it runs on the handle's own stream behind the work enqueued on `stream` so far and overlaps the forward gather.
-   demb_backward_prepared then joins it.  Same n / inverse / workspace in both calls; one outstanding prepare per workspace. */
-int demb_bwd_prep_create(void** handle);
-int demb_bwd_prep_destroy(void* handle);
-int demb_backward_prepare(void* handle, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound, const int64_t* offsets, int64_t batch_size,
-                          int num_features, int combiner, void* workspace, int64_t workspace_bytes, void* stream);
-int demb_backward_prepared(void* handle, float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound,
-                           const int64_t* rows, const float* grads, int64_t grad_stride, const int64_t* offsets, int64_t batch_size, int num_features,
-                           int combiner, int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
-                           float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, void* stream);
+   prefetch, on a stream of the caller's, where it overlaps the forward gather; demb_backward_apply does the rest.  Same n / inverse /
+   workspace in both calls; the caller orders apply behind sort (events), one outstanding sort per workspace. */
+int demb_backward_sort(int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound, const int64_t* offsets, int64_t batch_size,
+                       int num_features, int combiner, void* workspace, int64_t workspace_bytes, void* stream);
+int demb_backward_apply(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound,
+                        const int64_t* rows, const float* grads, int64_t grad_stride, const int64_t* offsets, int64_t batch_size, int num_features,
+                        int combiner, int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
+                        float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, void* stream);
 /* {sgd,adam,adagrad,rowwise_adagrad}_update_for_flat_table (optimizer.cu): dense grads[n, D] -> rows */
 int demb_update_rows(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* rows, const float* grads, int64_t grad_stride,
                      int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
@@ -171,7 +175,8 @@ int demb_train_prefetch(void* storage, const int64_t* table_bucket_offsets, int6
                         int32_t* ref_counter, int32_t* bucket_heads, float* values, int64_t value_dim, int emb_dim, const int64_t* row_base,
                         int64_t n, const void* keys, const int64_t* table_range, int num_tables, const int64_t* freq_in, int policy,
                         const uint64_t* table_scores, uint64_t timestamp, int key_is_signed, int init_mode, float p0, float p1, float p2, float p3,
-                        uint64_t seed, float state_init, void* unique_keys, int64_t* reverse_indices, int64_t* unique_table_ids,
+                        uint64_t seed, const demb_init_args_t* table_init /* device [num_tables], nullable */, float state_init,
+                        void* unique_keys, int64_t* reverse_indices, int64_t* unique_table_ids,
                         int64_t* unique_freq, int64_t* slots, int64_t* rows, int64_t* num_unique, void* workspace, int64_t workspace_bytes,
                         void* stream);
 /* demb_counter_update with the element count read from device memory (*n_device <= n_max) */

@@ -24,18 +24,24 @@ extern "C" {
 #define HSTU_ERR_UNSUPPORTED (-1101)
 #define HSTU_ERR_WORKSPACE (-1102)
 
+/* Workspace: the persistent kernels pull tiles from a global counter that lives in caller memory (hstu_workspace_bytes() bytes of
+ * device memory per call, contents irrelevant; must stay alive until the call's kernels have run).  This is the "workspace-size query"
+ * of SURVEY 8(b); there is no dQ accumulation workspace (see hstu_bwd_sm100). */
+int64_t hstu_workspace_bytes(void);
+
 /* strides[6] = {q_token, q_head, k_token, k_head, v_token, v_head} in elements */
 int hstu_fwd_sm100(const void* q, const void* k, const void* v, void* out, const int32_t* cu_seqlens, const int32_t* num_contexts,
                    const int32_t* num_targets, int batch, int heads, int head_dim, int total_tokens, int max_seqlen, int scaling_seqlen,
-                   int target_group_size, int window_left, int window_right, float alpha, const int64_t* strides, void* stream);
+                   int target_group_size, int window_left, int window_right, float alpha, const int64_t* strides, void* workspace,
+                   int64_t workspace_bytes, void* stream);
 
-/* strides[8] = q,k,v as above + {do_token, do_head}.  dq/dk/dv contiguous (T,H,D) bf16.  No workspace: dK/dV come from a
+/* strides[8] = q,k,v as above + {do_token, do_head}.  dq/dk/dv contiguous (T,H,D) bf16.  No gradient workspace: dK/dV come from a
  * KV-stationary kernel and dQ from a Q-stationary kernel, so nothing is accumulated through global memory (the reference
  * zero-fills and reduce-adds a dense fp32 [B,H,max_seqlen,D] dQ workspace every call, hstu_ops_gpu.py:373-382). */
 int hstu_bwd_sm100(const void* dout, const void* q, const void* k, const void* v, void* dq, void* dk, void* dv, const int32_t* cu_seqlens,
                    const int32_t* num_contexts, const int32_t* num_targets, int batch, int heads, int head_dim, int total_tokens,
                    int max_seqlen, int scaling_seqlen, int target_group_size, int window_left, int window_right, float alpha,
-                   const int64_t* strides, void* stream);
+                   const int64_t* strides, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* development aid: one-CTA tcgen05 GEMM that pins the descriptor conventions (csrc/sm100_probe.cu) */
 int sm100_probe_gemm(const void* A, const void* B, float* C, int variant, const uint32_t* overrides, void* stream);

@@ -110,4 +110,7 @@ __device__ __forceinline__ int64_t probe_thread(const Table& t, uint8_t* bk, uin
 
 }  // namespace demb
 
+#include "device_info.cuh"
+namespace demb { using devinfo::kMaxDevices; using devinfo::current_device; using devinfo::sm_count; using devinfo::once_per_device; }
+
 #define DEMB_CHECK_LAST() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return -(int)e__; } while (0)

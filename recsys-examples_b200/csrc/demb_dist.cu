@@ -136,7 +136,7 @@ int demb_block_bucketize_sparse_features_n(int64_t num_slots, int64_t batch_size
   size_t tmp_bytes = (size_t)((uint8_t*)workspace + workspace_bytes - w);
   if (num_ids >= 0 && num_ids <= 4 * num_slots) {
     const int64_t blocks = (num_slots + 255) / 256;
-    const int grid = (int)(blocks > 148 * 8 ? 148 * 8 : blocks);
+    const int grid = (int)(blocks > (int64_t)sm_count() * 8 ? (int64_t)sm_count() * 8 : blocks);
     cudaError_t e = cudaMemsetAsync(new_lengths, 0, 8 * (size_t)(num_slots * world_size), stream);
     if (e != cudaSuccess) return -(int)e;
     bucketize_short_kernel<0><<<grid, 256, 0, stream>>>(num_slots, batch_size, world_size, offsets, ids, block_sizes, dist_type_per_feature, new_lengths,
@@ -149,7 +149,7 @@ int demb_block_bucketize_sparse_features_n(int64_t num_slots, int64_t batch_size
     return 0;
   }
   int64_t blocks = (num_slots + kWarps - 1) / kWarps;
-  int grid = (int)(blocks > 148 * 16 ? 148 * 16 : blocks);
+  int grid = (int)(blocks > (int64_t)sm_count() * 16 ? (int64_t)sm_count() * 16 : blocks);
   bucketize_kernel<0><<<grid, kWarps * 32, 0, stream>>>(num_slots, batch_size, world_size, offsets, ids, block_sizes, dist_type_per_feature, new_lengths,
                                                         nullptr, nullptr, nullptr, nullptr, nullptr);
   cudaError_t e = cub::DeviceScan::ExclusiveSum(w, tmp_bytes, new_lengths, new_offsets, (int)(num_slots * world_size), stream);

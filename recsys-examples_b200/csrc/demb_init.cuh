@@ -26,6 +26,7 @@ __device__ __forceinline__ void boxmuller(uint32_t a, uint32_t b, float& z0, flo
 }
 
 struct InitArgs { int mode; float p0, p1, p2, p3; uint64_t seed; };   // uniform(lower,upper) normal(mean,std) trunc(mean,std,lower,upper) const(value)
+static_assert(sizeof(InitArgs) == sizeof(demb_init_args_t) && sizeof(InitArgs) == 32, "InitArgs is the device image of demb_init_args_t");
 
 __device__ __forceinline__ float4 init4(const InitArgs& a, uint64_t key, int c /*float4 chunk*/) {
   if (a.mode == DEMB_INIT_CONSTANT) return make_float4(a.p0, a.p0, a.p0, a.p0);

@@ -28,7 +28,7 @@ constexpr int kMaxChunks = 8;   // D <= 1024 (reference limit, lookup_kernel.cuh
 
 inline int warp_grid(int64_t warps) {
   int64_t blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  int64_t cap = 148 * 8 * 4;   // persistent-ish: multiple of 148 SMs x 8 resident CTAs
+  int64_t cap = (int64_t)sm_count() * 8 * 4;   // persistent-ish: multiple of the SM count x 8 resident CTAs
   return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(384) forward_seq_tma_kernel(RowSrc s, const fl
 template <int NCHUNK>
 __global__ void __launch_bounds__(kBlock) forward_pool_kernel(RowSrc s, const float* __restrict__ values, int64_t vdim, int D, int64_t B, int F,
                                                               const int64_t* __restrict__ offsets, int combiner, void* __restrict__ out,
-                                                              int out_dtype, int64_t total_D, int bpw) {
+                                                              int out_dtype, int64_t total_D, int bpw, float absent_value) {
   const int lane = threadIdx.x & 31;
   const int D4 = D >> 2;
   const int64_t bags = B * (int64_t)F;
@@ -227,7 +227,9 @@ __global__ void __launch_bounds__(kBlock) forward_pool_kernel(RowSrc s, const fl
 #pragma unroll
           for (int k = 0; k < NCHUNK; ++k) {
             const int c = lane + 32 * k;
-            v[u][k] = (j + u < cnt && r[u] >= 0 && c < D4) ? ld_nc_f4(values + r[u] * vdim + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // absent ids contribute the eval initializer's constant (reference: eval initializer runs before pooling)
+            v[u][k] = (j + u < cnt && c < D4) ? (r[u] >= 0 ? ld_nc_f4(values + r[u] * vdim + 4 * c) : make_float4(absent_value, absent_value, absent_value, absent_value))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -249,7 +251,8 @@ __global__ void __launch_bounds__(kBlock) forward_pool_kernel(RowSrc s, const fl
 // warp per new row: rows[i] (global value row, <0 = skip), keys[i]; optional `emb_out[i,:D]` copy of the
 // initialised embedding (for non-admitted / eval-miss ids that are not stored).
 __global__ void __launch_bounds__(kBlock) init_rows_kernel(float* __restrict__ values, int64_t vdim, int D, int64_t n, const int64_t* __restrict__ rows,
-                                                           const uint64_t* __restrict__ keys, InitArgs a, float state_init,
+                                                           const uint64_t* __restrict__ keys, InitArgs a0, const int64_t* __restrict__ tids,
+                                                           const InitArgs* __restrict__ table_init, float state_init,
                                                            const uint8_t* __restrict__ only_if /*nullable: init only where !=0*/,
                                                            float* __restrict__ emb_out) {
   const int lane = threadIdx.x & 31;
@@ -259,6 +262,7 @@ __global__ void __launch_bounds__(kBlock) init_rows_kernel(float* __restrict__ v
     if (only_if && !only_if[i]) continue;
     const int64_t r = rows ? rows[i] : -1;
     const uint64_t key = keys[i];
+    const InitArgs a = table_init ? table_init[tids ? tids[i] : 0] : a0;
     for (int c = lane; c < D4; c += 32) {
       float4 v = init4(a, key, c);
       if (r >= 0) st_f4(values + r * vdim + 4 * c, v);
@@ -613,15 +617,12 @@ static int launch_seq_tma(const RowSrc& s, const float* values, int64_t value_di
   if (warps > 12) warps = 12;
   if (warps < 1) return DEMB_ERR_ARG;
   const int smem = (int)(warps * stage);
-  static int configured = 0;
-  if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(forward_seq_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
-    if (e != cudaSuccess) return -(int)e;
-    configured = 216 * 1024;
-  }
+  static std::atomic<int> configured[kMaxDevices];
+  cudaError_t ce = once_per_device(configured, [] { return cudaFuncSetAttribute(forward_seq_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); });
+  if (ce != cudaSuccess) return -(int)ce;
   const int64_t tiles = (n + 31) / 32;
   int64_t blocks = (tiles + warps - 1) / warps;
-  if (blocks > 148) blocks = 148;                                  // one CTA per SM owns the whole shared memory; persistent over tiles
+  if (blocks > sm_count()) blocks = sm_count();                    // one CTA per SM owns the whole shared memory; persistent over tiles
   forward_seq_tma_kernel<<<(int)blocks, 384, smem, stream>>>(s, values, value_dim, emb_dim, n, out, absent_value, warps);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
@@ -646,7 +647,7 @@ int demb_lookup_forward(void* storage, const int64_t* table_bucket_offsets, int6
     const int bpw = pool_bags_per_warp(n, bags);
     DISPATCH_NCHUNK(emb_dim, forward_pool_kernel<NC><<<warp_grid((bags + bpw - 1) / bpw), kBlock, 0, (cudaStream_t)stream>>>(
                                  s, values, value_dim, emb_dim, batch_size, num_features, offsets, combiner, out, out_dtype,
-                                 (int64_t)num_features * emb_dim, bpw));
+                                 (int64_t)num_features * emb_dim, bpw, absent_value));
   }
   DEMB_CHECK_LAST();
   return 0;
@@ -667,7 +668,7 @@ int demb_gather_forward(const float* values, int64_t value_dim, int emb_dim, int
     const int bpw = pool_bags_per_warp(n, bags);
     DISPATCH_NCHUNK(emb_dim, forward_pool_kernel<NC><<<warp_grid((bags + bpw - 1) / bpw), kBlock, 0, (cudaStream_t)stream>>>(
                                  s, values, value_dim, emb_dim, batch_size, num_features, offsets, combiner, out, out_dtype,
-                                 (int64_t)num_features * emb_dim, bpw));
+                                 (int64_t)num_features * emb_dim, bpw, 0.f));
   }
   DEMB_CHECK_LAST();
   return 0;
@@ -682,11 +683,13 @@ int demb_rows_from_slots(int64_t n, const int64_t* slots, const int64_t* table_i
 }
 
 int demb_init_rows(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* rows, const void* keys, int mode, float p0, float p1,
-                   float p2, float p3, uint64_t seed, float state_init, const uint8_t* only_if, float* emb_out, void* stream) {
+                   float p2, float p3, uint64_t seed, const int64_t* table_ids, const demb_init_args_t* table_init, float state_init,
+                   const uint8_t* only_if, float* emb_out, void* stream) {
   if (check_dims(emb_dim, value_dim)) return DEMB_ERR_ARG;
   if (n <= 0) return 0;
   InitArgs a{mode, p0, p1, p2, p3, seed};
-  init_rows_kernel<<<warp_grid(n), kBlock, 0, (cudaStream_t)stream>>>(values, value_dim, emb_dim, n, rows, (const uint64_t*)keys, a, state_init, only_if, emb_out);
+  init_rows_kernel<<<warp_grid(n), kBlock, 0, (cudaStream_t)stream>>>(values, value_dim, emb_dim, n, rows, (const uint64_t*)keys, a, table_ids,
+                                                                      reinterpret_cast<const InitArgs*>(table_init), state_init, only_if, emb_out);
   DEMB_CHECK_LAST();
   return 0;
 }
@@ -708,35 +711,17 @@ int64_t demb_backward_workspace_bytes(int64_t n, int emb_dim) {
   return (int64_t)(4 * align256(4 * (size_t)n) + 2 * align256(tiles * (size_t)emb_dim * 4) + align256(((tiles + 31) / 32 + 1) * (size_t)emb_dim * 4) + align256(tmp) + 256);
 }
 
-// Side stream + fork/join events for demb_backward_prepare (one per module).
-struct BwdPrep { cudaStream_t side; cudaEvent_t fork, join; };
-
-int demb_bwd_prep_create(void** handle) {
-  BwdPrep* h = new BwdPrep{};
-  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming) != cudaSuccess) { delete h; return DEMB_ERR_ARG; }
-  *handle = h;
-  return 0;
-}
-int demb_bwd_prep_destroy(void* handle) {
-  BwdPrep* h = (BwdPrep*)handle;
-  if (!h) return 0;
-  cudaStreamDestroy(h->side); cudaEventDestroy(h->fork); cudaEventDestroy(h->join);
-  delete h;
-  return 0;
-}
-
-// phase 0: everything on `stream`.  phase 1: only the gradient-independent part (pair list + radix sort by unique index), forked onto the
-// handle's side stream behind whatever `stream` has enqueued so far.  phase 2: the rest on `stream`, joined behind phase 1 (same workspace).
+// phase 0: everything.  phase 1: only the gradient-independent part (pair list + radix sort by unique index).  phase 2: the rest (same
+// workspace).  All on `stream`: a caller that wants phase 1 to overlap the forward gather launches it on a stream of its own and orders
+// phase 2 behind it with events (dynamicemb_extensions.BackwardPrep does, with torch streams so the caching allocator knows).
 static int backward_impl(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound, const int64_t* rows,
                          const float* grads, int64_t grad_stride, const int64_t* offsets, int64_t batch_size, int num_features, int combiner,
                          int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
-                         float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, cudaStream_t stream, BwdPrep* prep, int phase) {
+                         float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, cudaStream_t stream, int phase) {
   if (check_dims(emb_dim, value_dim > 0 ? value_dim : emb_dim)) return DEMB_ERR_ARG;
   if (n <= 0) return 0;
   if (n >= (1ll << 31) || num_unique_bound >= (1ll << 31)) return DEMB_ERR_ARG;
   if (workspace_bytes < demb_backward_workspace_bytes(n, emb_dim)) return DEMB_ERR_WORKSPACE;
-  if (phase != 0 && !prep) return DEMB_ERR_ARG;
   const int pooled = combiner >= 0;
   size_t tiles = ((size_t)n + 31) / 32;
   uint8_t* w = (uint8_t*)workspace;
@@ -750,22 +735,16 @@ static int backward_impl(float* values, int64_t value_dim, int emb_dim, int64_t 
   size_t tmp_bytes = (size_t)((uint8_t*)workspace + workspace_bytes - w);
   if (phase != 2) {
     cudaStream_t s1 = stream;
-    if (phase == 1) {
-      if (cudaEventRecord(prep->fork, stream) != cudaSuccess || cudaStreamWaitEvent(prep->side, prep->fork, 0) != cudaSuccess) return DEMB_ERR_ARG;
-      s1 = prep->side;
-    }
     if (g_prof_on && phase == 0) cudaEventRecord(g_prof_ev[0], stream);
     backward_pairs_kernel<<<(int)((n + 255) / 256), 256, 0, s1>>>(n, inverse, pooled, batch_size, num_features, offsets, k0, v0);
     int end_bit = 1; while (end_bit < 31 && (1ll << end_bit) < num_unique_bound) ++end_bit;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(w, tmp_bytes, k0, k1, v0, v1, (int)n, 0, end_bit, s1);
     if (e != cudaSuccess) return -(int)e;
     if (phase == 1) {
-      if (cudaEventRecord(prep->join, prep->side) != cudaSuccess) return DEMB_ERR_ARG;
       DEMB_CHECK_LAST();
       return 0;
     }
   } else {
-    if (cudaStreamWaitEvent(stream, prep->join, 0) != cudaSuccess) return DEMB_ERR_ARG;
     if (g_prof_on) cudaEventRecord(g_prof_ev[0], stream);
   }
   BwdArgs a{grads, grad_stride, emb_dim, pooled, combiner, batch_size, num_features, offsets, k1, v1, n, rows, values, value_dim, unique_grads, pc, ps,
@@ -792,23 +771,23 @@ int demb_backward(float* values, int64_t value_dim, int emb_dim, int64_t n, cons
                   float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, void* stream_) {
   return backward_impl(values, value_dim, emb_dim, n, inverse, num_unique_bound, rows, grads, grad_stride, offsets, batch_size, num_features, combiner,
                        opt_type, lr, eps, beta1, beta2, weight_decay, bias_correction1, bias_correction2, unique_grads, workspace, workspace_bytes,
-                       (cudaStream_t)stream_, nullptr, 0);
+                       (cudaStream_t)stream_, 0);
 }
-// The part of demb_backward that does not need the gradients (pair list + sort), launched EARLY — right after the prefetch, on the
-// handle's side stream — so it overlaps the forward gather instead of sitting in front of the gradient reduction.
-int demb_backward_prepare(void* handle, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound, const int64_t* offsets, int64_t batch_size,
-                          int num_features, int combiner, void* workspace, int64_t workspace_bytes, void* stream_) {
+// The part of demb_backward that does not need the gradients (pair list + sort).  Launch it EARLY — right after the prefetch, on a stream
+// of the caller's — so it overlaps the forward gather instead of sitting in front of the gradient reduction.
+int demb_backward_sort(int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound, const int64_t* offsets, int64_t batch_size,
+                       int num_features, int combiner, void* workspace, int64_t workspace_bytes, void* stream_) {
   return backward_impl(nullptr, 0, emb_dim, n, inverse, num_unique_bound, nullptr, nullptr, 0, offsets, batch_size, num_features, combiner, 0, 0.f, 0.f, 0.f,
-                       0.f, 0.f, 1.f, 1.f, nullptr, workspace, workspace_bytes, (cudaStream_t)stream_, (BwdPrep*)handle, 1);
+                       0.f, 0.f, 1.f, 1.f, nullptr, workspace, workspace_bytes, (cudaStream_t)stream_, 1);
 }
-// demb_backward after demb_backward_prepare(handle, ... same n / inverse / workspace ...)
-int demb_backward_prepared(void* handle, float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound,
-                           const int64_t* rows, const float* grads, int64_t grad_stride, const int64_t* offsets, int64_t batch_size, int num_features,
-                           int combiner, int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
-                           float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, void* stream_) {
+// demb_backward after demb_backward_sort(... same n / inverse / workspace ...); the caller orders it behind the sort
+int demb_backward_apply(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound,
+                        const int64_t* rows, const float* grads, int64_t grad_stride, const int64_t* offsets, int64_t batch_size, int num_features,
+                        int combiner, int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
+                        float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, void* stream_) {
   return backward_impl(values, value_dim, emb_dim, n, inverse, num_unique_bound, rows, grads, grad_stride, offsets, batch_size, num_features, combiner,
                        opt_type, lr, eps, beta1, beta2, weight_decay, bias_correction1, bias_correction2, unique_grads, workspace, workspace_bytes,
-                       (cudaStream_t)stream_, (BwdPrep*)handle, 2);
+                       (cudaStream_t)stream_, 2);
 }
 
 int demb_profile_enable(int on) {

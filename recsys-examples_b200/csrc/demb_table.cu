@@ -196,7 +196,7 @@ int demb_table_init(void* storage, int64_t num_buckets, int64_t bucket_capacity,
   if (bucket_capacity % 16) return DEMB_ERR_ARG;
   if (num_buckets <= 0) return 0;
   int64_t total16 = num_buckets * bucket_capacity * (9 + 8 * (int64_t)num_scores) / 16;
-  int grid = (int)((total16 + kBlock - 1) / kBlock < 148 * 16 ? (total16 + kBlock - 1) / kBlock : 148 * 16);
+  const int64_t gcap = (int64_t)sm_count() * 16; int grid = (int)((total16 + kBlock - 1) / kBlock < gcap ? (total16 + kBlock - 1) / kBlock : gcap);
   table_init_kernel<<<grid < 1 ? 1 : grid, kBlock, 0, (cudaStream_t)stream>>>((uint8_t*)storage, num_buckets, bucket_capacity, num_scores);
   DEMB_CHECK_LAST();
   return 0;
@@ -253,7 +253,7 @@ int demb_table_insert(void* storage, const int64_t* table_bucket_offsets, int64_
   InsertArgs a{(const uint64_t*)keys, table_ids, score_in, timestamp, policy, bucket_sizes, ref_counter, results, indices, score_out,
                (unsigned long long*)evicted_count, (uint64_t*)evicted_keys, evicted_scores, evicted_indices, evicted_table_ids};
   int64_t blocks = (n + (kBlock / 32) - 1) / (kBlock / 32);
-  int grid = (int)(blocks < 148 * 32 ? blocks : 148 * 32);
+  const int64_t gcap = (int64_t)sm_count() * 32; int grid = (int)(blocks < gcap ? blocks : gcap);
   table_insert_segments_kernel<<<grid, kBlock, 0, stream>>>(t, n, order_a, bkt_b, a);
   DEMB_CHECK_LAST();
   return 0;

@@ -16,7 +16,7 @@
 //      train_insert_kernel (warp per bucket)      only the buckets that may have to evict (cooperative 128-slot victim scan); inserts,
 //                                                 initialises and pins inline as before.
 //   4. train_init_rows_kernel (warp per new key)  [emb | optimizer state] of the rows inserted by the thread kernel: pure streaming writes.
-// The resulting table image is identical to lookup + demb_table_insert + demb_init_rows run op by op (tests/test_demb_train_gpu.py).
+// The resulting table image is identical to lookup + demb_table_insert + demb_init_rows run op by op (tests/test_demb_module_gpu.py::test_fused_prefetch_matches_op_by_op; against the CPU oracle: tests/test_train_oracle_gpu.py).
 #include "../../include/dynamicemb_b200.h"
 #include "demb_common.cuh"
 #include "demb_insert.cuh"
@@ -33,7 +33,7 @@ struct TrainArgs {
   float* values; int64_t vdim; int D; const int64_t* row_base;
   const uint64_t* ukeys; const int64_t* utids; const int64_t* n_u;
   int pol; const uint64_t* table_scores; const int64_t* freq; uint64_t ts; int key_is_signed;
-  InitArgs init; float state_init;
+  InitArgs init; const InitArgs* table_init; float state_init;   // table_init: per-table initializer (device, [T]), nullable => init
   int64_t* slots; int64_t* rows; int32_t* next; int32_t* touched; unsigned long long* n_touched;
 };
 
@@ -98,7 +98,8 @@ __device__ __forceinline__ void train_insert_key(const TrainArgs& a, int64_t b, 
     const int64_t row = (a.row_base ? a.row_base[tid] : 0) + slot;
     const int D4 = a.D >> 2, V4 = (int)(a.vdim >> 2);
     if (o.result != kAssignHit) {                                                   // new row: initializer + optimizer state (fused A10 + A11)
-      for (int c = lane; c < D4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, init4(a.init, key, c));
+      const InitArgs ia = a.table_init ? a.table_init[tid] : a.init;
+      for (int c = lane; c < D4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, init4(ia, key, c));
       for (int c = D4 + lane; c < V4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, make_float4(a.state_init, a.state_init, a.state_init, a.state_init));
     }
     if (lane == 0) { a.slots[u] = slot; a.rows[u] = row; atomicAdd(a.counter + b * a.t.C + o.it, 1); }
@@ -204,7 +205,8 @@ __global__ void __launch_bounds__(kBlock) train_init_rows_kernel(TrainArgs a) {
     if (a.next[u] != -2) continue;
     const int64_t row = a.rows[u];
     const uint64_t key = a.ukeys[u];
-    for (int c = lane; c < D4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, init4(a.init, key, c));
+    const InitArgs ia = a.table_init ? a.table_init[a.utids ? a.utids[u] : 0] : a.init;
+    for (int c = lane; c < D4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, init4(ia, key, c));
     for (int c = D4 + lane; c < V4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, make_float4(a.state_init, a.state_init, a.state_init, a.state_init));
   }
 }
@@ -222,7 +224,7 @@ __global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
 }
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-int grid_for(int64_t n) { int64_t g = (n + kBlock - 1) / kBlock; return (int)(g < 1 ? 1 : (g > 148 * 32 ? 148 * 32 : g)); }
+int grid_for(int64_t n) { int64_t g = (n + kBlock - 1) / kBlock; const int64_t cap = (int64_t)sm_count() * 32; return (int)(g < 1 ? 1 : (g > cap ? cap : g)); }
 }  // namespace
 
 extern "C" {
@@ -242,7 +244,7 @@ int demb_train_prefetch(void* storage, const int64_t* table_bucket_offsets, int6
                         int32_t* ref_counter, int32_t* bucket_heads, float* values, int64_t value_dim, int emb_dim, const int64_t* row_base,
                         int64_t n, const void* keys, const int64_t* table_range, int num_tables, const int64_t* freq_in, int policy,
                         const uint64_t* table_scores, uint64_t timestamp, int key_is_signed, int init_mode, float p0, float p1, float p2, float p3,
-                        uint64_t seed, float state_init, void* unique_keys, int64_t* reverse_indices, int64_t* unique_table_ids,
+                        uint64_t seed, const demb_init_args_t* table_init, float state_init, void* unique_keys, int64_t* reverse_indices, int64_t* unique_table_ids,
                         int64_t* unique_freq, int64_t* slots, int64_t* rows, int64_t* num_unique, void* workspace, int64_t workspace_bytes,
                         void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -267,14 +269,14 @@ int demb_train_prefetch(void* storage, const int64_t* table_bucket_offsets, int6
   a.values = values; a.vdim = value_dim; a.D = emb_dim; a.row_base = row_base;
   a.ukeys = (const uint64_t*)unique_keys; a.utids = num_tables > 1 ? unique_table_ids : nullptr; a.n_u = num_unique;
   a.pol = policy; a.table_scores = table_scores; a.freq = need_freq ? unique_freq : nullptr; a.ts = timestamp; a.key_is_signed = key_is_signed;
-  a.init = InitArgs{init_mode, p0, p1, p2, p3, seed}; a.state_init = state_init;
+  a.init = InitArgs{init_mode, p0, p1, p2, p3, seed}; a.table_init = reinterpret_cast<const InitArgs*>(table_init); a.state_init = state_init;
   a.slots = slots; a.rows = rows; a.next = next; a.touched = touched; a.n_touched = n_touched;
   train_lookup_kernel<<<grid_for(n), kBlock, 0, stream>>>(a);
   train_insert_thread_kernel<<<grid_for(n), kBlock, 0, stream>>>(a, touched2, n_touched2);
   TrainArgs a2 = a;
   a2.touched = touched2; a2.n_touched = n_touched2;
-  train_insert_kernel<<<148 * 4, kBlock, 0, stream>>>(a2);                       // buckets that may evict (none until the table fills up)
-  train_init_rows_kernel<<<148 * 8, kBlock, 0, stream>>>(a);
+  train_insert_kernel<<<sm_count() * 4, kBlock, 0, stream>>>(a2);                       // buckets that may evict (none until the table fills up)
+  train_init_rows_kernel<<<sm_count() * 8, kBlock, 0, stream>>>(a);
   DEMB_CHECK_LAST();
   return 0;
 }

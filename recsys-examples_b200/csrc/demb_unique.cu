@@ -16,7 +16,7 @@ using namespace demb;
 
 namespace {
 constexpr int kBlock = 256;
-inline int grid_for(int64_t n) { int64_t g = (n + kBlock - 1) / kBlock; return (int)(g < 1 ? 1 : (g > 148 * 64 ? 148 * 64 : g)); }
+inline int grid_for(int64_t n) { int64_t g = (n + kBlock - 1) / kBlock; const int64_t cap = (int64_t)sm_count() * 64; return (int)(g < 1 ? 1 : (g > cap ? cap : g)); }
 
 // table of position i given table_range[T+1] (ids are grouped by table; T is small)
 __device__ __forceinline__ int table_of(const int64_t* __restrict__ range, int T, int64_t i) {

@@ -32,6 +32,7 @@
 #include "hstu_mask.cuh"
 #include "sm100_ptx.cuh"
 #include "tma_host.cuh"
+#include "device_info.cuh"
 
 using namespace sm100;
 
@@ -463,31 +464,19 @@ __global__ void __launch_bounds__(512, 1) hstu_bwd_kernel(const __grid_constant_
 }
 
 template <int D, bool kIsDQ>
-int launch(const CUtensorMap& y1, const CUtensorMap& y2, const Params& p_in, int B, int max_seqlen, cudaStream_t stream) {
+int launch(const CUtensorMap& y1, const CUtensorMap& y2, const Params& p_in, int B, int max_seqlen, int* tile_counter, cudaStream_t stream) {
   constexpr int smem = Smem<D, kIsDQ>::kTotal + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(hstu_bwd_kernel<D, kIsDQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return -(int)e;
-    configured = true;
-  }
-  // tile counter: a small per-device pool, one slot per launch in rotation (launches on different streams never share a live slot)
-  static int* pool[16] = {nullptr};
-  static unsigned seq[16] = {0};
-  static int sms[16] = {0};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return HSTU_ERR_ARG;
-  if (!pool[dev]) {
-    if (cudaMalloc(&pool[dev], 64 * sizeof(int)) != cudaSuccess) return -(int)cudaGetLastError();
-    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
-  }
+  static std::atomic<int> configured[devinfo::kMaxDevices];          // the attribute is per device
+  cudaError_t e = devinfo::once_per_device(configured, [] { return cudaFuncSetAttribute(hstu_bwd_kernel<D, kIsDQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+  if (e != cudaSuccess) return -(int)e;
   Params p = p_in;
   p.n_x = (max_seqlen + 127) / 128;
   p.n_tiles = p.n_x * p.H * B;
-  p.tile_counter = pool[dev] + (seq[dev]++ & 63);
-  cudaError_t e = cudaMemsetAsync(p.tile_counter, 0, sizeof(int), stream);
+  p.tile_counter = tile_counter;                                      // caller workspace (one counter per launch)
+  e = cudaMemsetAsync(p.tile_counter, 0, sizeof(int), stream);
   if (e != cudaSuccess) return -(int)e;
-  const int grid = p.n_tiles < sms[dev] ? p.n_tiles : sms[dev];
+  const int sms = devinfo::sm_count();
+  const int grid = p.n_tiles < sms ? p.n_tiles : sms;
   hstu_bwd_kernel<D, kIsDQ><<<grid, 512, smem, stream>>>(y1, y2, p);
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
@@ -496,10 +485,14 @@ int launch(const CUtensorMap& y1, const CUtensorMap& y2, const Params& p_in, int
 }  // namespace hstu_bwd
 
 extern "C" volatile int* hstu_get_debug_buffer();
+extern "C" int64_t hstu_workspace_bytes();
 extern "C" int hstu_bwd_sm100(const void* dout, const void* q, const void* k, const void* v, void* dq, void* dk, void* dv, const int32_t* cu_seqlens,
                               const int32_t* num_contexts, const int32_t* num_targets, int batch, int heads, int head_dim, int total_tokens,
                               int max_seqlen, int scaling_seqlen, int target_group_size, int window_left, int window_right, float alpha,
-                              const int64_t* strides /*q_t,q_h,k_t,k_h,v_t,v_h,do_t,do_h*/, void* stream_) {
+                              const int64_t* strides /*q_t,q_h,k_t,k_h,v_t,v_h,do_t,do_h*/, void* workspace, int64_t workspace_bytes,
+                              void* stream_) {
+  if (!workspace || workspace_bytes < hstu_workspace_bytes()) return HSTU_ERR_WORKSPACE;
+  int* counters = (int*)workspace;
   if (batch <= 0 || total_tokens <= 0) return 0;
   if (head_dim != 64 && head_dim != 128) return HSTU_ERR_UNSUPPORTED;
   if (target_group_size < 1 || scaling_seqlen <= 0) return HSTU_ERR_ARG;
@@ -525,11 +518,11 @@ extern "C" int hstu_bwd_sm100(const void* dout, const void* q, const void* k, co
   // dK, dV: X = (K, V), Y = (Q, dO)
   p.out0 = reinterpret_cast<__nv_bfloat16*>(dv); p.out1 = reinterpret_cast<__nv_bfloat16*>(dk); p.scale0 = invN; p.scale1 = alpha * invN;
   p.x1 = bf(k); p.x1_t = strides[2]; p.x1_h = strides[3]; p.x2 = bf(v); p.x2_t = strides[4]; p.x2_h = strides[5];
-  rc = head_dim == 128 ? launch<128, false>(small[0], small[3], p, batch, max_seqlen, stream) : launch<64, false>(small[0], small[3], p, batch, max_seqlen, stream);
+  rc = head_dim == 128 ? launch<128, false>(small[0], small[3], p, batch, max_seqlen, counters, stream) : launch<64, false>(small[0], small[3], p, batch, max_seqlen, counters, stream);
   if (rc) return rc;
   // dQ: X = (Q, dO), Y = (K, V)
   p.out0 = reinterpret_cast<__nv_bfloat16*>(dq); p.out1 = nullptr; p.scale0 = alpha * invN; p.scale1 = 0.f;
   p.x1 = bf(q); p.x1_t = strides[0]; p.x1_h = strides[1]; p.x2 = bf(dout); p.x2_t = strides[6]; p.x2_h = strides[7];
-  rc = head_dim == 128 ? launch<128, true>(small[1], small[2], p, batch, max_seqlen, stream) : launch<64, true>(small[1], small[2], p, batch, max_seqlen, stream);
+  rc = head_dim == 128 ? launch<128, true>(small[1], small[2], p, batch, max_seqlen, counters + 8, stream) : launch<64, true>(small[1], small[2], p, batch, max_seqlen, counters + 8, stream);
   return rc;
 }

@@ -30,6 +30,7 @@
 #include "hstu_mask.cuh"
 #include "sm100_ptx.cuh"
 #include "tma_host.cuh"
+#include "device_info.cuh"
 
 using namespace sm100;
 
@@ -416,32 +417,22 @@ __global__ void __launch_bounds__(512, 1) hstu_fwd_kernel(const __grid_constant_
 }
 
 template <int D>
-int launch_fwd(const CUtensorMap& mkk, const CUtensorMap& mv, const FwdParams& p, int B, int max_seqlen, cudaStream_t stream) {
+int launch_fwd(const CUtensorMap& mkk, const CUtensorMap& mv, const FwdParams& p, int B, int max_seqlen, int* tile_counter, cudaStream_t stream) {
   constexpr int smem = FwdSmem<D>::kTotal + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(hstu_fwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(hstu_fwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return -(int)e;
-    configured = true;
-  }
-  // tile counter: a small per-device pool, one slot per launch in rotation (launches on different streams never share a live slot)
-  static int* pool[16] = {nullptr};
-  static unsigned seq[16] = {0};
-  static int sms[16] = {0};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return HSTU_ERR_ARG;
-  if (!pool[dev]) {
-    if (cudaMalloc(&pool[dev], 64 * sizeof(int)) != cudaSuccess) return -(int)cudaGetLastError();
-    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
-  }
+  static std::atomic<int> configured[devinfo::kMaxDevices];          // the attribute is per device
+  cudaError_t e = devinfo::once_per_device(configured, [] {
+    cudaError_t e1 = cudaFuncSetAttribute(hstu_fwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return e1 != cudaSuccess ? e1 : cudaFuncSetAttribute(hstu_fwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  });
+  if (e != cudaSuccess) return -(int)e;
   FwdParams q = p;
   q.n_m = (max_seqlen + 127) / 128;
   q.n_tiles = q.n_m * p.H * B;
-  q.tile_counter = pool[dev] + (seq[dev]++ & 63);
-  cudaError_t e = cudaMemsetAsync(q.tile_counter, 0, sizeof(int), stream);
+  q.tile_counter = tile_counter;                                      // caller workspace: one counter per launch, nothing shared between streams / graphs
+  e = cudaMemsetAsync(q.tile_counter, 0, sizeof(int), stream);
   if (e != cudaSuccess) return -(int)e;
-  const int grid = q.n_tiles < sms[dev] ? q.n_tiles : sms[dev];      // one persistent CTA per SM
+  const int sms = devinfo::sm_count();
+  const int grid = q.n_tiles < sms ? q.n_tiles : sms;                // one persistent CTA per SM
   if (p.dbg) hstu_fwd_kernel<D, true><<<grid, 512, smem, stream>>>(mkk, mv, q);
   else hstu_fwd_kernel<D, false><<<grid, 512, smem, stream>>>(mkk, mv, q);
   e = cudaGetLastError();
@@ -454,10 +445,12 @@ static volatile int* g_hstu_dbg = nullptr;
 extern "C" int hstu_set_debug_buffer(int* host_mapped) { g_hstu_dbg = host_mapped; return 0; }
 extern "C" volatile int* hstu_get_debug_buffer() { return g_hstu_dbg; }
 
+extern "C" int64_t hstu_workspace_bytes() { return 64; }
 extern "C" int hstu_fwd_sm100(const void* q, const void* k, const void* v, void* out, const int32_t* cu_seqlens, const int32_t* num_contexts,
                               const int32_t* num_targets, int batch, int heads, int head_dim, int total_tokens, int max_seqlen, int scaling_seqlen,
                               int target_group_size, int window_left, int window_right, float alpha, const int64_t* strides /*q_t,q_h,k_t,k_h,v_t,v_h (elements)*/,
-                              void* stream) {
+                              void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!workspace || workspace_bytes < hstu_workspace_bytes()) return HSTU_ERR_WORKSPACE;
   if (batch <= 0 || total_tokens <= 0) return 0;
   if (head_dim != 64 && head_dim != 128) return HSTU_ERR_UNSUPPORTED;
   if (target_group_size < 1 || scaling_seqlen <= 0) return HSTU_ERR_ARG;
@@ -475,6 +468,6 @@ extern "C" int hstu_fwd_sm100(const void* q, const void* k, const void* v, void*
   p.H = heads; p.half_alpha = 0.5f * alpha; p.inv_scale = 1.0f / (float)scaling_seqlen;
   p.target_group = target_group_size; p.win_left = window_left; p.win_right = window_right;
   p.dbg = g_hstu_dbg;
-  if (head_dim == 128) return hstu::launch_fwd<128>(mk, mv, p, batch, max_seqlen, (cudaStream_t)stream);
-  return hstu::launch_fwd<64>(mk, mv, p, batch, max_seqlen, (cudaStream_t)stream);
+  if (head_dim == 128) return hstu::launch_fwd<128>(mk, mv, p, batch, max_seqlen, (int*)workspace, (cudaStream_t)stream);
+  return hstu::launch_fwd<64>(mk, mv, p, batch, max_seqlen, (int*)workspace, (cudaStream_t)stream);
 }

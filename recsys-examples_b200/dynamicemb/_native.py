@@ -40,18 +40,16 @@ _SIGS = {
     "demb_lookup_forward": (I32, [P, P, I64, I32, P, I64, I32, P, I64, P, P, I32, P, I64, I32, I32, P, I32, F32, P, P, P]),
     "demb_gather_forward": (I32, [P, I64, I32, I64, P, P, P, I64, I32, I32, P, I32, P]),
     "demb_rows_from_slots": (I32, [I64, P, P, P, P, P]),
-    "demb_init_rows": (I32, [P, I64, I32, I64, P, P, I32, F32, F32, F32, F32, U64, F32, P, P, P]),
+    "demb_init_rows": (I32, [P, I64, I32, I64, P, P, I32, F32, F32, F32, F32, U64, P, P, F32, P, P, P]),
     "demb_copy_rows": (I32, [P, I64, I32, I64, P, P, I64, I32, P]),
     "demb_backward_workspace_bytes": (I64, [I64, I32]),
     "demb_backward": (I32, [P, I64, I32, I64, P, I64, P, P, I64, P, I64, I32, I32, I32, F32, F32, F32, F32, F32, F32, F32, P, P, I64, P]),
-    "demb_bwd_prep_create": (I32, [P]),
-    "demb_bwd_prep_destroy": (I32, [P]),
-    "demb_backward_prepare": (I32, [P, I32, I64, P, I64, P, I64, I32, I32, P, I64, P]),
-    "demb_backward_prepared": (I32, [P, P, I64, I32, I64, P, I64, P, P, I64, P, I64, I32, I32, I32, F32, F32, F32, F32, F32, F32, F32, P, P, I64, P]),
+    "demb_backward_sort": (I32, [I32, I64, P, I64, P, I64, I32, I32, P, I64, P]),
+    "demb_backward_apply": (I32, [P, I64, I32, I64, P, I64, P, P, I64, P, I64, I32, I32, I32, F32, F32, F32, F32, F32, F32, F32, P, P, I64, P]),
     "demb_update_rows": (I32, [P, I64, I32, I64, P, P, I64, I32, F32, F32, F32, F32, F32, F32, F32, P]),
     "demb_fill_i32": (I32, [P, I64, I32, P]),
     "demb_train_prefetch_workspace_bytes": (I64, [I64, I32]),
-    "demb_train_prefetch": (I32, [P, P, I64, I32, P, P, P, P, I64, I32, P, I64, P, P, I32, P, I32, P, U64, I32, I32, F32, F32, F32, F32, U64, F32,
+    "demb_train_prefetch": (I32, [P, P, I64, I32, P, P, P, P, I64, I32, P, I64, P, P, I32, P, I32, P, U64, I32, I32, F32, F32, F32, F32, U64, P, F32,
                                   P, P, P, P, P, P, P, P, I64, P]),
     "demb_counter_update_n": (I32, [P, P, P, P, I64, P, I64, I32, P]),
     "demb_profile_enable": (I32, [I32]),

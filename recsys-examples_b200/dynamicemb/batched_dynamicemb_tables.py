@@ -70,7 +70,7 @@ class PrefetchState:
     rows: torch.Tensor              # global value row per unique key, -1 = absent
     num_unique_bound: int           # host-known upper bound of the unique count (sort width)
     num_unique_dev: Optional[torch.Tensor] = None   # device-side count (fused path: buffers are sized by the bound)
-    bwd_ws: Optional[torch.Tensor] = None           # workspace holding the pre-sorted (unique idx, gradient row) pairs (backward_prepare)
+    bwd_ws: Optional[object] = None                 # ext.PreparedBackward: pre-sorted (unique idx, gradient row) pairs (backward_prepare)
 
     @property
     def num_unique(self) -> int:
@@ -103,7 +103,7 @@ class _LookupFunction(torch.autograd.Function):
         pooled = ctx.combiner >= 0
         ext.backward(m._values, m.max_D, st.reverse_indices, max(st.num_unique_bound, 1), st.rows, grads, offsets=ctx.offsets if pooled else None,
                      batch_size=ctx.batch_size if pooled else 0, num_features=m.feature_num if pooled else 0, combiner=ctx.combiner,
-                     prepared=(m._bwd_prep, st.bwd_ws) if st.bwd_ws is not None else None, **opt.kernel_kwargs())
+                     prepared=st.bwd_ws, **opt.kernel_kwargs())
         m._unpin(st)
         return None, None, None, None, None
 
@@ -149,6 +149,8 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
                 raise NotImplementedError("cache / external storage tiers are out of scope (HBM-direct only); see DESIGN.md")
             if o.embedding_dtype != torch.float32:
                 raise NotImplementedError("value rows are fp32 in this build")
+            if o.eval_initializer_args != opt0.eval_initializer_args:
+                raise NotImplementedError("all tables of one module must share eval_initializer_args (one absent-row constant per fused eval lookup)")
         self._dynamicemb_options = table_options
         self.index_type = opt0.index_type
         self.embedding_dtype = opt0.embedding_dtype
@@ -186,12 +188,20 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         self._create_score()
         # --- storage: key index map + value rows [capacity, emb_dim + state_dim] in HBM (key_value_table.py:346-356)
         policy = self._score_policy()
-        self._table = LinearBucketTable([o.max_capacity for o in table_options], [ScoreSpec(name="score", policy=policy)],
+        self._table = LinearBucketTable([o.max_capacity for o in table_options], [ScoreSpec(name="score", policy=policy)],   # LRU_LFU => 2 score words
                                         key_type=self.index_type, bucket_capacity=opt0.bucket_capacity, device=self._device)
         self.value_dim = self.max_D + self._optimizer.get_state_dim(self.max_D)
         self.value_dim = (self.value_dim + 3) // 4 * 4
         self._values = torch.zeros(self._table.capacity_, self.value_dim, dtype=torch.float32, device=self._device)
         self._seed = int(kwargs.get("seed", 0))
+        # one initializer per table (reference: _create_initializers, batched_dynamicemb_tables.py:789-796): mode / bounds from that table's
+        # initializer_args (default bound 1/sqrt(that table's capacity)), Philox seed mixed with the table id so the same key in two
+        # tables does not get the same row
+        self._init_per_table = []
+        for t, o in enumerate(table_options):
+            mode, p = _init_params(o.initializer_args, o.max_capacity)
+            self._init_per_table.append((mode, p, (self._seed + t * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF))
+        self._table_init_dev = ext.make_table_init(self._init_per_table, self._device) if len(table_options) > 1 else None
         self._fused_prefetch = bool(kwargs.get("fused_prefetch", True))     # False = op-by-op path (reference op order, 2 host syncs)
         self._bwd_prep = None                                               # ext.BackwardPrep, created on first training prefetch
         self._force_prepare = False
@@ -204,7 +214,14 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         self._scores: Dict[str, int] = {}
         for name, o in zip(self._table_names, self._dynamicemb_options):
             s = o.score_strategy
-            if s == DynamicEmbScoreStrategy.TIMESTAMP:
+            if isinstance(s, tuple):
+                # compound {TIMESTAMP, LFU} -> LruLfu: word 0 = last-access timestamp, word 1 = frequency, which drives eviction
+                # (key_value_table.py:136-177)
+                if frozenset(s) != frozenset({DynamicEmbScoreStrategy.TIMESTAMP, DynamicEmbScoreStrategy.LFU}) or len(s) != 2:
+                    raise NotImplementedError(f"Unsupported compound score_strategy {s}.")
+                o.evict_strategy = DynamicEmbEvictStrategy.LFU
+                self._scores[name] = 1
+            elif s == DynamicEmbScoreStrategy.TIMESTAMP:
                 o.evict_strategy = DynamicEmbEvictStrategy.LRU
                 self._scores[name] = 0
             elif s == DynamicEmbScoreStrategy.STEP:
@@ -224,6 +241,8 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
     def _score_policy(self) -> ScorePolicy:
         """key_value_table.py:136-177 strategy -> policy."""
         s = self._dynamicemb_options[0].score_strategy
+        if isinstance(s, tuple):
+            return ScorePolicy.LRU_LFU
         if s == DynamicEmbScoreStrategy.TIMESTAMP:
             return ScorePolicy.GLOBAL_TIMER
         if s == DynamicEmbScoreStrategy.LFU:
@@ -260,7 +279,8 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
     def get_score(self) -> Dict[str, int]:
         out = {}
         for name, o in zip(self._table_names, self._dynamicemb_options):
-            out[name] = ext.device_timestamp() if o.score_strategy == DynamicEmbScoreStrategy.TIMESTAMP else self._scores[name]
+            timed = o.score_strategy == DynamicEmbScoreStrategy.TIMESTAMP or isinstance(o.score_strategy, tuple)
+            out[name] = ext.device_timestamp() if timed else self._scores[name]
         return out
 
     def _score_arg(self, n: int, table_ids: torch.Tensor, freq: Optional[torch.Tensor], const: bool = False) -> ScoreArg:
@@ -269,7 +289,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         policy = self._score_policy()
         if policy == ScorePolicy.GLOBAL_TIMER:
             return ScoreArg(name="score", policy=policy)
-        if policy == ScorePolicy.ACCUMULATE:
+        if policy in (ScorePolicy.ACCUMULATE, ScorePolicy.LRU_LFU):
             v = freq if freq is not None else torch.ones(n, dtype=torch.int64, device=self._device)
             return ScoreArg(name="score", value=v.to(torch.int64), policy=policy)
         for name in self._table_names:
@@ -298,7 +318,9 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         torch.cuda.current_stream(self._device).synchronize()
 
     def reset_prefetch(self) -> None:
-        self._prefetch_states.clear()
+        """Drop the queued prefetches: their rows are unpinned (ref_counter) so they can be evicted again."""
+        while self._prefetch_states:
+            self._unpin(self._prefetch_states.popleft())
 
     # ------------------------------------------------------------------ prefetch / forward
     def _split(self, indices: torch.Tensor, offsets: torch.Tensor):
@@ -319,7 +341,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         if self._fused_prefetch:
             self._prefetch_fused(indices, trange, T, frequency_counters)
             return
-        want_freq = self._score_policy() == ScorePolicy.ACCUMULATE
+        want_freq = self._score_policy() in (ScorePolicy.ACCUMULATE, ScorePolicy.LRU_LFU)
         freq_in = (frequency_counters.to(torch.int64) if frequency_counters is not None
                    else (torch.empty(0, dtype=torch.int64, device=self._device) if want_freq else None))
         num_u, ukeys, reverse, toffs, freq, utids = ext.segmented_unique_cuda(indices, trange, T, freq_in, want_table_ids=True)
@@ -335,8 +357,9 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
             mf = freq[miss] if freq is not None else None
             new_slots = tb.insert(mk, mt, self._score_arg(mk.numel(), mt, mf), timestamp=ts)
             new_rows = ext.rows_from_slots(new_slots, mt, tb.row_base_)
-            mode, p = _init_params(self._dynamicemb_options[0].initializer_args, self._dynamicemb_options[0].max_capacity)
-            ext.init_rows(self._values, self.max_D, new_rows, mk, mode, *p, seed=self._seed, state_init=self._optimizer.initial_state_value)
+            mode, p, seed0 = self._init_per_table[0]
+            ext.init_rows(self._values, self.max_D, new_rows, mk, mode, *p, seed=seed0, state_init=self._optimizer.initial_state_value,
+                          table_ids=mt if self._table_init_dev is not None else None, table_init=self._table_init_dev)
             tb.increment_counter(new_slots, mt)
             slots[miss] = new_slots
         rows = ext.rows_from_slots(slots, utids, tb.row_base_)
@@ -353,16 +376,16 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
                 if name not in self._scores:
                     raise RuntimeError(f"Must set score for table '{name}' whose score_strategy is customized.")
             scores = self._device_scores()
-        mode, p = _init_params(self._dynamicemb_options[0].initializer_args, self._dynamicemb_options[0].max_capacity)
+        mode, p, seed0 = self._init_per_table[0]
         uk, rev, utids, slots, rows, nu = ext.train_prefetch(
             tb.table_storage_, tb.table_bucket_offsets_, tb.bucket_capacity_, tb.bucket_sizes, tb._ref_counter, tb._bucket_heads, self._values,
-            self.max_D, tb.row_base_, indices, trange, T, policy, scores, ext.device_timestamp(), mode, p, self._seed,
-            self._optimizer.initial_state_value, freq_in=frequency_counters, num_scores=tb.num_scores_)
+            self.max_D, tb.row_base_, indices, trange, T, policy, scores, ext.device_timestamp(), mode, p, seed0,
+            self._optimizer.initial_state_value, freq_in=frequency_counters, num_scores=tb.num_scores_, table_init=self._table_init_dev)
         st = PrefetchState(uk, rev, utids if T > 1 else None, slots, rows, indices.numel(), nu)
         if (self.training and self.pooling_mode == DynamicEmbPoolingMode.NONE and torch.is_grad_enabled()) or self._force_prepare:
             # the gradient-independent half of the fused backward (pair list + sort) starts now, on a side stream, under the forward gather
             if self._bwd_prep is None:
-                self._bwd_prep = ext.BackwardPrep()
+                self._bwd_prep = ext.BackwardPrep(self._device)
             st.bwd_ws = ext.backward_prepare(self._bwd_prep, self.max_D, rev, max(st.num_unique_bound, 1))
         self._prefetch_states.append(st)
         self._update_score()
@@ -414,11 +437,16 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         upstream gradients into `grad_static`), call graph.replay(), read `out` / `loss` (loss = out.sum(), a stand-in for the model's
         scalar result; None with with_loss=False).
         Restrictions: training mode, fused prefetch, optimizers whose kernel arguments do not depend on the step count
-        (SGD / Adagrad / row-wise Adagrad — Adam's bias correction is a host value), non-GLOBAL_TIMER scores."""
+        (SGD / Adagrad / row-wise Adagrad — Adam's bias correction is a host value), scores without a host timestamp (not TIMESTAMP /
+        compound LRU-LFU).
+        Side effects: the three warm-up steps before capture are REAL training steps on whatever `ids_static` / `grad_static` hold
+        (they insert those ids, apply the optimizer and advance STEP scores) — pass the first real batch, or zero `grad_static`.
+        The returned graph object's replay() also advances the host-side STEP scores and the optimizer's step count, so
+        get_score() and a later eager step stay consistent with the device."""
         from .types import EmbOptimType
         assert self.training and self._fused_prefetch
         assert self._optimizer_type in (EmbOptimType.SGD, EmbOptimType.EXACT_SGD, EmbOptimType.EXACT_ADAGRAD, EmbOptimType.EXACT_ROWWISE_ADAGRAD)
-        assert self._score_policy() != ScorePolicy.GLOBAL_TIMER
+        assert self._score_policy() not in (ScorePolicy.GLOBAL_TIMER, ScorePolicy.LRU_LFU)
         indices, offsets_i, B = self._split(ids_static, offsets)
         assert indices.data_ptr() == ids_static.data_ptr(), "ids_static must already be contiguous int64"
 
@@ -437,7 +465,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
             pooled = self.pooling_mode != DynamicEmbPoolingMode.NONE
             ext.backward(self._values, self.max_D, st.reverse_indices, max(st.num_unique_bound, 1), st.rows, grad_static,
                          offsets=offsets_i if pooled else None, batch_size=B if pooled else 0, num_features=self.feature_num if pooled else 0,
-                         combiner=int(self.pooling_mode) if pooled else -1, prepared=(self._bwd_prep, st.bwd_ws) if st.bwd_ws is not None else None,
+                         combiner=int(self.pooling_mode) if pooled else -1, prepared=st.bwd_ws,
                          **self._optimizer.kernel_kwargs())
             self._unpin(st)
             return out_, loss_
@@ -451,9 +479,13 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         cur.wait_stream(side)
         torch.cuda.synchronize(self._device)
         graph = torch.cuda.CUDAGraph()
+        host_scores, host_iter = dict(self._scores), self._optimizer.iter
         with torch.no_grad(), torch.cuda.graph(graph):
             out, loss = step()
-        return graph, out, loss
+        # capture ran step() on the host without executing it: undo its host-side bookkeeping, and roll the device STEP scores back too
+        # (the captured add_ advances them at every replay)
+        self._scores, self._optimizer.iter = host_scores, host_iter
+        return _GraphedStep(self, graph), out, loss
 
     # ------------------------------------------------------------------ inspection helpers (tests, dump)
     def export_keys_values(self, table_id: int = 0):
@@ -467,6 +499,21 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         if not ks:
             return torch.empty(0, dtype=self.index_type, device=self._device), torch.empty(0, self.value_dim, device=self._device)
         return torch.cat(ks), torch.cat(vs)
+
+
+class _GraphedStep:
+    """graph.replay() + the host-side bookkeeping of one training step (STEP scores, optimizer step count)."""
+
+    def __init__(self, module: BatchedDynamicEmbeddingTablesV2, graph: torch.cuda.CUDAGraph):
+        self.module, self.graph = module, graph
+
+    def replay(self) -> None:
+        self.graph.replay()
+        m = self.module
+        for name, o in zip(m._table_names, m._dynamicemb_options):
+            if o.score_strategy == DynamicEmbScoreStrategy.STEP:
+                m._scores[name] = (m._scores[name] + 1) & 0xFFFFFFFFFFFFFFFF
+        m._optimizer.iter += 1
 
 
 class _NoCtx:

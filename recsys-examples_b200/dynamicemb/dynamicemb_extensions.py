@@ -216,9 +216,10 @@ def table_update_counter_n(counter, slot_indices, delta, table_bucket_offsets, b
 
 def train_prefetch(table_storage, table_bucket_offsets, bucket_capacity, bucket_sizes, ref_counter, bucket_heads, values, emb_dim, row_base,
                    keys, table_range, num_tables, policy, table_scores, timestamp, init_mode, init_params, seed, state_init,
-                   freq_in=None, num_scores=1):
+                   freq_in=None, num_scores=1, table_init=None):
     """Fused dedup + probe + insert/init + pin (demb_train.cu).  Returns (unique_keys[n], reverse[n], unique_table_ids[n], slots[n],
-    rows[n], num_unique[1] device) — only the first num_unique entries of the per-unique outputs are meaningful."""
+    rows[n], num_unique[1] device) — only the first num_unique entries of the per-unique outputs are meaningful.
+    table_init: device tensor from `make_table_init` (one initializer per table), overrides (init_mode, init_params, seed)."""
     n = keys.numel()
     dev = keys.device
     uk = torch.empty(n, dtype=keys.dtype, device=dev)
@@ -233,8 +234,8 @@ def train_prefetch(table_storage, table_bucket_offsets, bucket_capacity, bucket_
     N.check(N.launch("train_prefetch", 6, N.lib.demb_train_prefetch, N.ptr(table_storage), N.ptr(table_bucket_offsets), bucket_capacity, num_scores,
                      N.ptr(bucket_sizes), N.ptr(ref_counter), N.ptr(bucket_heads), N.ptr(values), values.stride(0), emb_dim, N.ptr(row_base), n,
                      N.ptr(keys.contiguous()), N.ptr(table_range), num_tables, N.ptr(_i64(freq_in)), int(policy), N.ptr(table_scores), int(timestamp),
-                     1 if keys.dtype == torch.int64 else 0, int(init_mode), float(p0), float(p1), float(p2), float(p3), int(seed), float(state_init),
-                     N.ptr(uk), N.ptr(rev), N.ptr(utids), N.ptr(ufreq), N.ptr(slots), N.ptr(rows), N.ptr(nu), N.ptr(ws), ws.numel(), N.stream()),
+                     1 if keys.dtype == torch.int64 else 0, int(init_mode), float(p0), float(p1), float(p2), float(p3), int(seed), N.ptr(table_init),
+                     float(state_init), N.ptr(uk), N.ptr(rev), N.ptr(utids), N.ptr(ufreq), N.ptr(slots), N.ptr(rows), N.ptr(nu), N.ptr(ws), ws.numel(), N.stream()),
             "train_prefetch")
     return uk, rev, utids, slots, rows, nu
 
@@ -324,11 +325,23 @@ def rows_from_slots(slots, table_ids, row_base):
     return rows
 
 
-def init_rows(values, emb_dim, rows, keys, mode, p0=0.0, p1=1.0, p2=0.0, p3=0.0, seed=0, state_init=0.0, only_if=None, emb_out=None):
+def make_table_init(per_table, device) -> torch.Tensor:
+    """Device image of demb_init_args_t[T] (include/dynamicemb_b200.h) from [(mode, (p0, p1, p2, p3), seed), ...]."""
+    import numpy as np
+    dt = np.dtype([("mode", "<i4"), ("p", "<f4", (4,)), ("reserved", "<u4"), ("seed", "<u8")])
+    assert dt.itemsize == 32
+    a = np.zeros(len(per_table), dtype=dt)
+    for i, (mode, p, seed) in enumerate(per_table):
+        a[i]["mode"], a[i]["p"], a[i]["seed"] = int(mode), tuple(float(x) for x in p), int(seed) & 0xFFFFFFFFFFFFFFFF
+    return torch.from_numpy(a.view(np.uint8).copy()).to(device)
+
+
+def init_rows(values, emb_dim, rows, keys, mode, p0=0.0, p1=1.0, p2=0.0, p3=0.0, seed=0, state_init=0.0, only_if=None, emb_out=None,
+              table_ids=None, table_init=None):
     n = keys.numel()
     N.check(N.launch("init_rows", 1, N.lib.demb_init_rows, N.ptr(values), values.stride(0) if values is not None else emb_dim, emb_dim, n, N.ptr(rows),
                                  N.ptr(keys.contiguous()), int(mode), float(p0), float(p1), float(p2), float(p3), int(seed),
-                                 float(state_init), N.ptr(only_if), N.ptr(emb_out), N.stream()), "init_rows")
+                                 N.ptr(_i64(table_ids)), N.ptr(table_init), float(state_init), N.ptr(only_if), N.ptr(emb_out), N.stream()), "init_rows")
 
 
 def copy_rows(values, width, rows, dense, to_table: bool):
@@ -337,36 +350,45 @@ def copy_rows(values, width, rows, dense, to_table: bool):
 
 
 class BackwardPrep:
-    """Side stream + fork/join events for `backward_prepare` (one per module)."""
+    """Side stream for `backward_prepare` (one per module).  A torch stream, so the caching allocator can be told
+    (`record_stream`) that the sort workspace and `inverse` are in use there."""
 
-    def __init__(self):
-        h = ctypes.c_void_p()
-        N.check(N.lib.demb_bwd_prep_create(ctypes.byref(h)), "bwd_prep_create")
-        self.handle = h
-
-    def __del__(self):
-        try:
-            N.lib.demb_bwd_prep_destroy(self.handle)
-        except Exception:  # noqa: BLE001  (interpreter shutdown)
-            pass
+    def __init__(self, device=None):
+        self.stream = torch.cuda.Stream(device)
 
 
-def backward_prepare(prep: BackwardPrep, emb_dim: int, inverse: torch.Tensor, num_unique_bound: int) -> Optional[torch.Tensor]:
-    """Sequence mode: launch the gradient-independent half of `backward` (pair list + radix sort by unique index) NOW, on the prep handle's
-    stream, behind everything already enqueued on the current stream.  Returns the workspace to hand to backward(..., prepared=(prep, ws))."""
+class PreparedBackward:
+    """Workspace holding the pre-sorted (unique idx, gradient row) pairs + the event the gradient-dependent half waits on."""
+
+    def __init__(self, ws: torch.Tensor, done: torch.cuda.Event):
+        self.ws, self.done = ws, done
+
+
+def backward_prepare(prep: BackwardPrep, emb_dim: int, inverse: torch.Tensor, num_unique_bound: int) -> Optional[PreparedBackward]:
+    """Sequence mode: launch the gradient-independent half of `backward` (pair list + radix sort by unique index) NOW, on the prep
+    object's stream, behind everything already enqueued on the current stream.  Returns what backward(..., prepared=) needs.
+    A PreparedBackward that is dropped without a backward is safe: its tensors were recorded on the side stream, so the allocator
+    does not hand the memory out again before the sort has finished."""
     n = inverse.numel()
     if n == 0:
         return None
+    cur = torch.cuda.current_stream(inverse.device)
     ws = torch.empty(N.lib.demb_backward_workspace_bytes(n, emb_dim), dtype=torch.uint8, device=inverse.device)
-    N.check(N.launch("backward_prepare", 2, N.lib.demb_backward_prepare, prep.handle, emb_dim, n, N.ptr(inverse), int(num_unique_bound), None, 0, 0, -1,
-                     N.ptr(ws), ws.numel(), N.stream()), "backward_prepare")
-    return ws
+    prep.stream.wait_stream(cur)
+    with torch.cuda.stream(prep.stream):
+        N.check(N.launch("backward_prepare", 2, N.lib.demb_backward_sort, emb_dim, n, N.ptr(inverse), int(num_unique_bound), None, 0, 0, -1,
+                         N.ptr(ws), ws.numel(), N.stream()), "backward_sort")
+        done = torch.cuda.Event()
+        done.record(prep.stream)
+    ws.record_stream(prep.stream)
+    inverse.record_stream(prep.stream)
+    return PreparedBackward(ws, done)
 
 
 def backward(values, emb_dim, inverse, num_unique_bound, rows, grads, *, offsets=None, batch_size=0, num_features=0, combiner=-1,
              opt_type=0, lr=0.0, eps=1e-8, beta1=0.9, beta2=0.999, weight_decay=0.0, bc1=1.0, bc2=1.0, want_unique_grads=False, prepared=None):
     """Fused reduce_grads + optimizer row update.  grads: [n, D] (sequence) or [B, F*D] (pooled).
-    prepared = (BackwardPrep, workspace) from backward_prepare(same inverse / bound): only the gradient-dependent half runs here."""
+    prepared = PreparedBackward from backward_prepare(same inverse / bound): only the gradient-dependent half runs here."""
     n = inverse.numel()
     dev = inverse.device
     ug = torch.zeros(num_unique_bound, emb_dim, dtype=torch.float32, device=dev) if want_unique_grads else None
@@ -374,9 +396,10 @@ def backward(values, emb_dim, inverse, num_unique_bound, rows, grads, *, offsets
         return ug
     grads = grads.contiguous()
     vstride = values.stride(0) if values is not None else emb_dim
-    if prepared is not None and prepared[1] is not None:
-        prep, ws = prepared
-        N.check(N.launch("backward", 3, N.lib.demb_backward_prepared, prep.handle, N.ptr(values), vstride, emb_dim, n, N.ptr(inverse), int(num_unique_bound),
+    if prepared is not None:
+        ws = prepared.ws
+        torch.cuda.current_stream(dev).wait_event(prepared.done)
+        N.check(N.launch("backward", 3, N.lib.demb_backward_apply, N.ptr(values), vstride, emb_dim, n, N.ptr(inverse), int(num_unique_bound),
                          N.ptr(rows), N.ptr(grads), emb_dim, N.ptr(_i64(offsets)), batch_size, num_features, combiner, int(opt_type), lr, eps, beta1, beta2,
                          weight_decay, bc1, bc2, N.ptr(ug), N.ptr(ws), ws.numel(), N.stream()), "backward")
         return ug

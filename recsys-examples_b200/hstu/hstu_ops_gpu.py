@@ -10,9 +10,12 @@ from dynamicemb import _native as N   # shared ctypes loader of librecsys_b200.s
 
 P, I32, F32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 N.lib.hstu_fwd_sm100.restype = I32
-N.lib.hstu_fwd_sm100.argtypes = [P, P, P, P, P, P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, F32, P, P]
+N.lib.hstu_fwd_sm100.argtypes = [P, P, P, P, P, P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, F32, P, P, ctypes.c_int64, P]
 N.lib.hstu_bwd_sm100.restype = I32
-N.lib.hstu_bwd_sm100.argtypes = [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, F32, P, P]
+N.lib.hstu_bwd_sm100.argtypes = [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, F32, P, P, ctypes.c_int64, P]
+N.lib.hstu_workspace_bytes.restype = ctypes.c_int64
+N.lib.hstu_workspace_bytes.argtypes = []
+_WS_BYTES = int(N.lib.hstu_workspace_bytes())
 N.lib.sm100_probe_gemm.restype = I32
 N.lib.sm100_probe_gemm.argtypes = [P, P, P, I32, P, P]
 
@@ -49,7 +52,10 @@ def hstu_varlen_fwd_100(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_s
                         scaling_seqlen: int = -1) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     assert rab is None and func is None and paged_kv is None, "rab / arbitrary mask / paged KV are not on the training hot path (DESIGN.md)"
     assert q.dtype == torch.bfloat16 and k.dtype == q.dtype and v.dtype == q.dtype, "bf16 only"
-    assert cu_seqlens_q.data_ptr() == cu_seqlens_k.data_ptr() or torch.equal(cu_seqlens_q, cu_seqlens_k), "self attention (seqlen_q == seqlen_k) only"
+    # self attention only (seqlen_q == seqlen_k, the training case).  Distinct cu_seqlens tensors are accepted on shape / max_seqlen
+    # agreement; comparing their contents would be a host sync on every call.
+    assert cu_seqlens_q.data_ptr() == cu_seqlens_k.data_ptr() or (cu_seqlens_q.shape == cu_seqlens_k.shape and max_seqlen_q == max_seqlen_k
+                                                                  and k.shape[0] == q.shape[0]), "self attention (seqlen_q == seqlen_k) only"
     q, k, v = _prep(q), _prep(k), _prep(v)
     T, H, D = q.shape
     out = torch.empty(T, H, D, dtype=q.dtype, device=q.device)
@@ -59,9 +65,10 @@ def hstu_varlen_fwd_100(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_s
         scaling_seqlen = max_seqlen_q
     strides = (ctypes.c_int64 * 6)(q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1))
     nc, nt = _i32(num_contexts), _i32(num_targets)
+    ws = torch.empty(_WS_BYTES, dtype=torch.uint8, device=q.device)      # tile counter of this launch (stream-ordered allocation)
     _check(N.lib.hstu_fwd_sm100(N.ptr(q), N.ptr(k), N.ptr(v), N.ptr(out), N.ptr(cu), N.ptr(nc), N.ptr(nt), B, H, D, T, int(max_seqlen_q),
                                 int(scaling_seqlen), int(target_group_size), int(window_size_left), int(window_size_right), float(alpha),
-                                ctypes.cast(strides, P), N.stream()), "hstu_fwd_sm100")
+                                ctypes.cast(strides, P), N.ptr(ws), ws.numel(), N.stream()), "hstu_fwd_sm100")
     return out, None
 
 
@@ -80,9 +87,10 @@ def hstu_varlen_bwd_100(dout, q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q,
         scaling_seqlen = max_seqlen_q
     strides = (ctypes.c_int64 * 8)(q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1), dout.stride(0), dout.stride(1))
     nc, nt = _i32(num_contexts), _i32(num_targets)
+    ws = torch.empty(_WS_BYTES, dtype=torch.uint8, device=q.device)      # tile counters of the two launches
     _check(N.lib.hstu_bwd_sm100(N.ptr(dout), N.ptr(q), N.ptr(k), N.ptr(v), N.ptr(dq), N.ptr(dk), N.ptr(dv), N.ptr(cu), N.ptr(nc), N.ptr(nt),
                                 B, H, D, T, int(max_seqlen_q), int(scaling_seqlen), int(target_group_size), int(window_size_left),
-                                int(window_size_right), float(alpha), ctypes.cast(strides, P), N.stream()), "hstu_bwd_sm100")
+                                int(window_size_right), float(alpha), ctypes.cast(strides, P), N.ptr(ws), ws.numel(), N.stream()), "hstu_bwd_sm100")
     return dq, dk, dv, None
 
 

@@ -1,0 +1,149 @@
+"""GPU, world_size 2 (NCCL over NVLink): RowWiseShardedDynamicEmbedding against the UNSHARDED module on the same ids — the reference's
+own multi-GPU check (corelib/dynamicemb/test/unit_tests/test_sequence_embedding_fw.py, test_pooled_embedding_fw.py: sharded lookup vs
+a plain dict of rows).  Each rank feeds its own batch; forward rows must equal what one unsharded table holding every key returns, and
+after a training step the rows of every key (wherever they live) must equal the unsharded module's rows after the same step with the
+union of all ranks' gradients.  Skipped on boxes with fewer than 2 GPUs (run with `gpurun --gpus 2`; evidence: profiles/)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+D = 128
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _mk(dev, cap, pooling, opt, lr):
+    from dynamicemb import (BatchedDynamicEmbeddingTablesV2, DynamicEmbInitializerArgs, DynamicEmbInitializerMode, DynamicEmbScoreStrategy,
+                            DynamicEmbTableOptions)
+    o = DynamicEmbTableOptions(dim=D, max_capacity=cap, local_hbm_for_values=1 << 50, score_strategy=DynamicEmbScoreStrategy.STEP,
+                               initializer_args=DynamicEmbInitializerArgs(mode=DynamicEmbInitializerMode.DEBUG))
+    return BatchedDynamicEmbeddingTablesV2([o, o], table_names=["a", "b"], feature_table_map=[0, 1], pooling_mode=pooling, optimizer=opt,
+                                           learning_rate=lr, eps=1e-8, device=dev)
+
+
+def _rows_by_key(m):
+    out = {}
+    for t in range(2):
+        keys, vals = m.export_keys_values(t)
+        for k, v in zip(keys.tolist(), vals.cpu()):
+            out[(t, k)] = v
+    return out
+
+
+def _worker(rank, world, port, pooled, dedup, dist_type, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "recsys-examples_b200"))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from dynamicemb import DynamicEmbPoolingMode, EmbOptimType
+        from dynamicemb.shard import RowWiseShardedDynamicEmbedding
+        pm = DynamicEmbPoolingMode.SUM if pooled else DynamicEmbPoolingMode.NONE
+        lr = 0.05
+        F, B = 2, 257
+        local = _mk(dev, 1 << 16, pm, EmbOptimType.EXACT_ADAGRAD, lr)
+        local.train()
+        model = RowWiseShardedDynamicEmbedding(local, None, dist_type=dist_type, use_index_dedup=dedup, num_embeddings_per_feature=[1 << 20] * F)
+        ref = _mk(dev, 1 << 17, pm, EmbOptimType.EXACT_ADAGRAD, lr)       # unsharded: every rank replays the union of all batches
+        ref.train()
+        for step in range(4):
+            rng = np.random.default_rng(1000 * step + rank)
+            lengths_np = rng.integers(0, 12, size=F * B).astype(np.int64)
+            ids_np = (rng.zipf(1.2, size=int(lengths_np.sum())) % 5000).astype(np.int64) * 7 + 3
+            ids, lengths = torch.from_numpy(ids_np).to(dev), torch.from_numpy(lengths_np).to(dev)
+            out = model(ids, lengths)
+            # ---- the unsharded run of the union: KJT of world*B samples per feature (rank-major inside a feature)
+            everyone = [None] * world
+            dist.all_gather_object(everyone, (ids_np, lengths_np))
+            u_ids, u_len = [], []
+            for f in range(F):
+                for i_r, l_r in everyone:
+                    o_r = np.concatenate([[0], np.cumsum(l_r)])
+                    u_ids.append(i_r[o_r[f * B]: o_r[(f + 1) * B]])
+                    u_len.append(l_r[f * B:(f + 1) * B])
+            u_ids, u_len = np.concatenate(u_ids), np.concatenate(u_len)
+            u_off = torch.from_numpy(np.concatenate([[0], np.cumsum(u_len)]).astype(np.int64)).to(dev)
+            ref_out = ref(torch.from_numpy(u_ids).to(dev), u_off)
+            # my slice of the unsharded output
+            if pooled:
+                mine = ref_out[rank * B:(rank + 1) * B]                       # [W*B, F*D] -> my B samples
+            else:
+                pos, cur = [], 0
+                for f in range(F):
+                    for r, (i_r, l_r) in enumerate(everyone):
+                        cnt = int(l_r[f * B:(f + 1) * B].sum())
+                        if r == rank:
+                            pos.append(np.arange(cur, cur + cnt))
+                        cur += cnt
+                mine = ref_out[torch.from_numpy(np.concatenate(pos)).to(dev)]
+            assert out.shape == mine.shape, f"step {step}: {out.shape} vs {mine.shape}"
+            assert torch.equal(out.detach(), mine.detach()), f"step {step}: sharded forward differs from the unsharded module"
+            # ---- one training step with per-rank gradients; the unsharded module gets the union
+            g = torch.randn(out.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(77 * step + rank))
+            out.backward(g)
+            gl = [torch.empty_like(g) if r != rank else g for r in range(world)]
+            if pooled:
+                allg = [torch.empty(B, F * D, device=dev) for _ in range(world)]
+                dist.all_gather(allg, g.contiguous())
+                ref_out.backward(torch.cat(allg, 0))
+            else:
+                sizes = [int(l_r.sum()) for _, l_r in everyone]
+                allg = [torch.empty(s, D, device=dev) for s in sizes]
+                dist.all_gather(allg, g.contiguous())
+                ug, cur_r = [], [0] * world
+                for f in range(F):
+                    for r, (i_r, l_r) in enumerate(everyone):
+                        cnt = int(l_r[f * B:(f + 1) * B].sum())
+                        ug.append(allg[r][cur_r[r]: cur_r[r] + cnt])
+                        cur_r[r] += cnt
+                ref_out.backward(torch.cat(ug, 0))
+        # ---- rows after training: every key this rank owns == the unsharded module's row (fp32 sums in a different order: tolerance)
+        mine_rows = _rows_by_key(local)
+        ref_rows = _rows_by_key(ref)
+        owned = [None] * world
+        dist.all_gather_object(owned, sorted(mine_rows.keys()))
+        allk = sorted(k for o in owned for k in o)
+        assert allk == sorted(ref_rows.keys()), "the shards together do not hold exactly the keys of the unsharded table"
+        assert len(set(allk)) == len(allk), "a key lives on two ranks"
+        for k, v in mine_rows.items():
+            torch.testing.assert_close(v, ref_rows[k], rtol=2e-5, atol=2e-5)
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("pooled,dedup,dist_type", [(False, True, "hash_roundrobin"), (False, False, "roundrobin"), (True, False, "hash_roundrobin")])
+def test_sharded_matches_unsharded_nccl(pooled, dedup, dist_type):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, pooled, dedup, dist_type, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for r, msg in res:
+        assert msg == "ok", f"rank {r}: {msg}"
