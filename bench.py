@@ -446,7 +446,10 @@ def main():
     fill = prefill(m, gen, dev, world, rank, KEY_SPACE, args.plaw_draws, True, args.capacity)
     if world > 1:
         from dynamicemb.shard import RowWiseShardedDynamicEmbedding
-        model = RowWiseShardedDynamicEmbedding(m, None, dist_type="hash_roundrobin", use_index_dedup=True)
+        # exchange capacities (ids per step): a rank feeds n_ids, sends at most n_ids/2 unique ids to any single owner (hash_roundrobin
+        # spreads ~n_unique/W to each), and an owner accepts at most n_ids in total
+        model = RowWiseShardedDynamicEmbedding(m, None, dist_type="hash_roundrobin", use_index_dedup=True, max_ids_per_step=n_ids,
+                                               pair_capacity=n_ids // 2, recv_capacity=n_ids)
         samples = 4096                     # KJT shape per rank: one feature, 4096 samples x 256 ids (HSTU-like jagged sequences)
         lengths = torch.full((samples,), n_ids // samples, dtype=torch.int64, device=dev)
         call = lambda ids: model(ids, lengths)

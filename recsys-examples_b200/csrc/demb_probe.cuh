@@ -1,0 +1,128 @@
+// Warp-tile hash probe with shared-memory staging — the lookup path of the table for buckets of 128 slots.
+//
+// The reference (and our round-1 kernels) probe one key per THREAD: 16 digests per dependent step from the key's start position, a
+// dependent 8-byte key load per digest match, up to 8 steps when the bucket is full (kernels.cuh:83-187, types.cuh:309-396) — a chain of
+// up to ~10 dependent memory round trips executed in lock-step by the 32 lanes of a warp (ncu: 89 of 100 issue slots stalled on the
+// long scoreboard).  Here a warp probes a TILE of 32 keys:
+//   1. the whole 128-byte digest line of every key's bucket is fetched with coalesced 128-bit loads — eight lanes per line, four lines per
+//      warp-wide load, eight loads per tile — a full pipeline stage before it is needed (a first version staged the lines in shared
+//      memory with one cp.async.bulk per line: correct, but one more TMA operation per id, and the per-SM rate of small bulk copies, not
+//      bandwidth, was the limit: 0.24 ms against 0.14 ms for the gather alone);
+//   2. the line of a key is scanned by the EIGHT lanes that loaded it (16 digests each), four keys per step; every lane that sees a digest
+//      match loads that slot's key straight away — all candidate key loads of the tile are independent and in flight together — and the
+//      lane whose candidate equals the key publishes the slot through the warp's shared memory (the per-bucket result staging).
+// Result parity: a key is unique in its bucket and (because erase leaves Reclaim, not Empty, behind and insert takes the first Empty in
+// probe order) never lies behind an Empty slot of its probe sequence, so "the slot whose digest and key match, anywhere in the bucket"
+// is exactly the slot the reference's ordered probe returns, and "no such slot" is exactly its not-found.
+#pragma once
+#include "demb_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace demb {
+
+constexpr int kProbeC = 128;                       // bucket capacity this path is specialised for
+
+// per-lane description of one key of a tile
+struct ProbeKey {
+  uint64_t key;
+  int64_t bucket;        // global bucket
+  int64_t slot_base;     // (bucket - first bucket of its table) * C: table-local slot of position 0
+  int32_t tid;
+  bool valid;            // key legal and table non-empty
+};
+
+__device__ __forceinline__ ProbeKey make_probe_key(const Table& t, uint64_t key, int tid) {
+  ProbeKey p{key, 0, 0, tid, false};
+  if (key_is_valid(key)) {
+    const int64_t h = hash63(key);
+    const int64_t bb = t.bkt_off[tid];
+    const int64_t cap = (t.bkt_off[tid + 1] - bb) * t.C;
+    if (cap > 0) { p.bucket = bb + (h % cap) / t.C; p.slot_base = (p.bucket - bb) * t.C; p.valid = true; }
+  }
+  return p;
+}
+
+// The digest lines of a tile, in registers: lane l holds, for step j, the 16-byte chunk (l & 7) of the line of key (l >> 3) + 4 j — the
+// chunk it will scan.  One warp-wide 128-bit load covers the four 128-byte lines of four keys, fully coalesced (8 loads per tile);
+// issued one pipeline stage ahead of the scan.
+struct DigRegs { uint4 d[8]; };
+
+__device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+// all 32 lanes; lanes without a key pass valid=false
+__device__ __forceinline__ void tile_load_digests(const Table& t, const ProbeKey& p, DigRegs& r, int lane) {
+  const uint64_t my_line = p.valid ? reinterpret_cast<uint64_t>(t.digests(t.bucket(p.bucket))) : 0ull;
+  const int c = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint64_t line = __shfl_sync(0xffffffffu, my_line, (lane >> 3) + 4 * j);
+    r.d[j] = line ? ld_nc_u4(reinterpret_cast<const uint8_t*>(line) + c * 16) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+// 16-bit mask of the bytes of a 16-byte chunk that equal the byte replicated in w4 (bit b = byte b)
+__device__ __forceinline__ uint32_t match16(const uint4& d, uint32_t w4) {
+  const uint32_t m0 = __vcmpeq4(d.x, w4) & 0x01010101u, m1 = __vcmpeq4(d.y, w4) & 0x01010101u;
+  const uint32_t m2 = __vcmpeq4(d.z, w4) & 0x01010101u, m3 = __vcmpeq4(d.w, w4) & 0x01010101u;
+  // (m * 0x00204081) >> 21 gathers bits 0, 8, 16, 24 into bits 0..3 (the partial products do not collide)
+  return ((m0 * 0x00204081u) >> 21 & 0xFu) | (((m1 * 0x00204081u) >> 21 & 0xFu) << 4) | (((m2 * 0x00204081u) >> 21 & 0xFu) << 8) |
+         (((m3 * 0x00204081u) >> 21 & 0xFu) << 12);
+}
+
+// all 32 lanes; returns the position (0..127) of this lane's key in its bucket, or -1.  slot_sm: 32 ints of the warp's shared memory.
+__device__ __forceinline__ int tile_probe(const Table& t, const ProbeKey& p, const DigRegs& dig, int* slot_sm, int lane) {
+  slot_sm[lane] = -1;
+  __syncwarp();
+  const uint32_t want = (uint32_t)digest_of(hash63(p.key)) * 0x01010101u;
+  const uint64_t my_keys = p.valid ? reinterpret_cast<uint64_t>(t.keys(t.bucket(p.bucket))) : 0ull;
+  const int c = lane & 7;                          // 16-byte chunk of the line this lane scans
+  uint64_t cand_key[8]; uint32_t mask[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = (lane >> 3) + 4 * j;             // key of the tile this lane works for in step j
+    const uint32_t w4 = __shfl_sync(0xffffffffu, want, k);
+    const uint64_t* keys_k = reinterpret_cast<const uint64_t*>(__shfl_sync(0xffffffffu, my_keys, k));
+    mask[j] = 0; cand_key[j] = 0;
+    if (keys_k) {
+      mask[j] = match16(dig.d[j], w4);
+      if (mask[j]) cand_key[j] = keys_k[c * 16 + __ffs(mask[j]) - 1];     // independent loads: every candidate of the tile is in flight together
+    }
+  }
+  bool more = false;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = (lane >> 3) + 4 * j;
+    const uint64_t key_k = __shfl_sync(0xffffffffu, p.key, k);
+    if (mask[j]) {
+      if (cand_key[j] == key_k) slot_sm[k] = c * 16 + __ffs(mask[j]) - 1;
+      else if (mask[j] & (mask[j] - 1)) more = true;                       // a second digest match inside the same 16 bytes (rare)
+    }
+  }
+  if (__any_sync(0xffffffffu, more)) {               // slow path: remaining candidates of a chunk, one dependent load each
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = (lane >> 3) + 4 * j;
+      const uint64_t key_k = __shfl_sync(0xffffffffu, p.key, k);
+      const uint64_t* keys_k = reinterpret_cast<const uint64_t*>(__shfl_sync(0xffffffffu, my_keys, k));
+      // drop the candidate already checked; nothing left to do if it was the key, or an Empty slot: inside a 16-slot group ascending
+      // position is probe order, and a key never lies behind an Empty slot of its probe sequence (keys whose digest equals the empty
+      // digest would otherwise walk every empty slot of the chunk)
+      uint32_t m = (cand_key[j] == key_k || cand_key[j] == kEmptyKey) ? 0u : (mask[j] & (mask[j] - 1));
+      while (m) {
+        const int pos = c * 16 + __ffs(m) - 1;
+        m &= m - 1;
+        const uint64_t kk = keys_k[pos];
+        if (kk == key_k) { slot_sm[k] = pos; break; }
+        if (kk == kEmptyKey) break;
+      }
+    }
+  }
+  __syncwarp();
+  return slot_sm[lane];
+}
+
+}  // namespace demb

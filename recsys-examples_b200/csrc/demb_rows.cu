@@ -17,6 +17,7 @@
 #include "demb_common.cuh"
 #include "demb_init.cuh"
 #include "sm100_ptx.cuh"
+#include "demb_probe.cuh"
 
 using namespace demb;
 
@@ -65,6 +66,7 @@ struct RowSrc {
   const int64_t* inverse;     // indirect mode, nullable
   uint8_t* founds;            // optional outputs (probe mode)
   int64_t* slots_out;
+  const int64_t* n_dev;       // device-side id count (<= the launch bound n), nullable
 };
 __device__ __forceinline__ int64_t resolve_row(const RowSrc& s, int64_t i) {
   if (s.rows) { int64_t u = s.inverse ? s.inverse[i] : i; return s.rows[u]; }
@@ -86,6 +88,7 @@ __device__ __forceinline__ int64_t resolve_row(const RowSrc& s, int64_t i) {
 template <int U>
 __global__ void __launch_bounds__(kBlock) forward_seq_kernel(RowSrc s, const float* __restrict__ values, int64_t vdim, int D, int64_t n,
                                                              void* __restrict__ out, int out_dtype, float absent_value) {
+  if (s.n_dev) { const int64_t v = *s.n_dev; n = v < 0 ? 0 : (v < n ? v : n); }
   const int lane = threadIdx.x & 31;
   const int D4 = D >> 2;
   const int64_t tiles = (n + 31) >> 5;
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(384) forward_seq_tma_kernel(RowSrc s, const fl
   __shared__ uint64_t bars[12];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   if (wib >= warps_per_block) return;
+  if (s.n_dev) { const int64_t v = *s.n_dev; n = v < 0 ? 0 : (v < n ? v : n); }
   const uint32_t row_bytes = (uint32_t)D * 4u;
   uint8_t* buf = stage_raw + (size_t)wib * 32u * row_bytes;
   if (lane == 0) { sm100::mbar_init(&bars[wib], 1); sm100::fence_barrier_init(); }
@@ -164,6 +168,81 @@ __global__ void __launch_bounds__(384) forward_seq_tma_kernel(RowSrc s, const fl
       sm100::bulk_commit();
     }
     row = next_row;
+  }
+  if (lane == 0) sm100::bulk_wait0();                             // shared memory must outlive the last bulk store
+}
+
+// ---- forward, sequence mode, fp32 output, PROBE mode for 128-slot buckets: hash probe + row gather in one persistent kernel -----------
+// The 128-d lookup path of the north star.  One CTA per SM, `warps` independent warps, each running a three-deep software pipeline over
+// its tiles of 32 ids (demb_probe.cuh):
+//     tile t+2   coalesced loads of the 32 digest lines (one 128-B line per id's bucket) into registers                 [issued]
+//     tile t+1   scan the lines (8 lanes per line), confirm candidates by their keys -> 32 value-row ids                [one memory hop]
+//     tile t     one cp.async.bulk per row (512 B for D=128) into the warp's shared-memory stage, one 16-KB bulk store to the output
+// so a probe costs ONE exposed memory round trip (the candidate key loads), overlapped with the row copies of the previous tile, instead
+// of the per-thread chain digest chunk -> key -> next chunk ... of the reference's probe.
+constexpr int kProbeFwdWarps = 12;
+struct ProbeFwdSmem { uint64_t bar_row[kProbeFwdWarps]; int slot[kProbeFwdWarps][32]; };
+__global__ void __launch_bounds__(kProbeFwdWarps * 32) forward_seq_probe_kernel(RowSrc s, const float* __restrict__ values, int64_t vdim, int D, int64_t n,
+                                                                                float* __restrict__ out, float absent_value, int warps_per_block) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ ProbeFwdSmem sm;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  if (wib >= warps_per_block) return;
+  const uint32_t row_bytes = (uint32_t)D * 4u;
+  uint8_t* rowbuf = smem_raw + (size_t)wib * 32u * row_bytes;
+  if (lane == 0) { sm100::mbar_init(&sm.bar_row[wib], 1); sm100::fence_barrier_init(); }
+  __syncwarp();
+  const int64_t tiles = (n + 31) >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * warps_per_block;
+  int64_t tile = (int64_t)blockIdx.x * warps_per_block + wib;
+  auto load_key = [&](int64_t tl) -> ProbeKey {
+    const int64_t i = (tl << 5) + lane;
+    if (tl >= tiles || i >= n) return ProbeKey{0, 0, 0, 0, false};
+    const int tid = (s.T > 1 && s.table_range) ? table_of(s.table_range, s.T, i) : 0;
+    return make_probe_key(s.t, s.keys[i], tid);
+  };
+  auto row_of = [&](const ProbeKey& p, int pos, int64_t tl) -> int64_t {
+    const int64_t i = (tl << 5) + lane;
+    const int64_t slot = pos >= 0 ? p.slot_base + pos : -1;
+    if (tl < tiles && i < n) { if (s.founds) s.founds[i] = slot >= 0; if (s.slots_out) s.slots_out[i] = slot; }
+    return slot < 0 ? -1 : (s.row_base ? s.row_base[p.tid] : 0) + slot;
+  };
+  uint32_t par_row = 0;
+  // prologue: digests of the first two tiles, probe of the first
+  ProbeKey k0 = load_key(tile), k1 = load_key(tile + wstride);
+  DigRegs d0, d1;
+  tile_load_digests(s.t, k0, d0, lane);
+  tile_load_digests(s.t, k1, d1, lane);
+  int64_t row = row_of(k0, tile_probe(s.t, k0, d0, sm.slot[wib], lane), tile);
+  for (; tile < tiles; tile += wstride) {
+    const int64_t base = tile << 5;
+    const int cnt = (int)((n - base) < 32 ? (n - base) : 32);
+    const unsigned found = __ballot_sync(0xffffffffu, row >= 0);
+    if (lane == 0) {
+      sm100::bulk_wait_read0();                                  // the previous tile's bulk store has finished reading the row stage
+      sm100::mbar_arrive_expect_tx(&sm.bar_row[wib], (uint32_t)__popc(found) * row_bytes);
+    }
+    __syncwarp();
+    if (row >= 0) {
+      sm100::bulk_load(rowbuf + (size_t)lane * row_bytes, values + row * vdim, row_bytes, &sm.bar_row[wib]);
+    } else if (lane < cnt) {
+      float4* d = reinterpret_cast<float4*>(rowbuf + (size_t)lane * row_bytes);
+      for (int c = 0; c < (D >> 2); ++c) d[c] = make_float4(absent_value, absent_value, absent_value, absent_value);
+    }
+    // tile t+2: digest lines on their way while tile t+1 is probed and tile t is copied
+    const ProbeKey k2 = load_key(tile + 2 * wstride);
+    tile_load_digests(s.t, k2, d0, lane);
+    // tile t+1: probe while the row copies of tile t are in flight
+    const int64_t next_row = row_of(k1, tile_probe(s.t, k1, d1, sm.slot[wib], lane), tile + wstride);
+    sm100::mbar_wait(&sm.bar_row[wib], par_row);
+    par_row ^= 1;
+    sm100::fence_proxy_async_smem();                             // absent rows were written through the generic proxy
+    __syncwarp();
+    if (lane == 0) {
+      sm100::bulk_store(out + base * (int64_t)D, rowbuf, (uint32_t)cnt * row_bytes);
+      sm100::bulk_commit();
+    }
+    row = next_row; k1 = k2; d1 = d0;
   }
   if (lane == 0) sm100::bulk_wait0();                             // shared memory must outlive the last bulk store
 }
@@ -354,10 +433,14 @@ __device__ __forceinline__ void apply_row(const OptArgs& o, float* __restrict__ 
   }
 }
 
+struct BwdArgs;
+__device__ __forceinline__ int64_t bwd_n(const BwdArgs& a);
 struct BwdArgs {
   const float* grads; int64_t grad_stride;   // row r of the gradient matrix is grads + r*grad_stride
   int D; int pooled; int combiner; int64_t B; int F; const int64_t* offsets;   // pooled: row id = b*F+f, MEAN scale 1/len(bag f*B+b)
-  const int32_t* skey; const int32_t* sval; int64_t n;   // sorted (unique idx, gradient row id)
+  const int32_t* skey; const int32_t* sval; int64_t n;   // sorted (unique idx, gradient row id); n = launch bound
+  const int64_t* n_dev;     // device-side element count (<= n), nullable => n
+  const int64_t* ug_addr;   // optional per-unique destination ADDRESS of the reduced gradient row (may be peer memory), overrides unique_grads
   const int64_t* rows;      // unique idx -> global value row (<0: skip), nullable => emit only
   float* values; int64_t vdim;
   float* unique_grads;      // optional [n_unique, D] output of the reduced gradients (reduce_grads op), nullable
@@ -365,11 +448,23 @@ struct BwdArgs {
   OptArgs opt;
 };
 
+__device__ __forceinline__ int64_t bwd_n(const BwdArgs& a) {
+  if (!a.n_dev) return a.n;
+  const int64_t v = *a.n_dev;
+  return v < 0 ? 0 : (v > a.n ? a.n : v);
+}
+
 // r = a.rows[u] when the caller already holds it (kRowKnown), else it is loaded here
 template <int NCHUNK, bool kRowKnown = false>
 __device__ __forceinline__ void finish_segment(const BwdArgs& a, int32_t u, const float4 (&acc)[NCHUNK], int lane, int64_t r_known = -1) {
   const int D4 = a.D >> 2;
-  if (a.unique_grads) {
+  if (a.ug_addr) {                                              // reduced row goes straight to its owner (possibly over NVLink)
+    float* dst = reinterpret_cast<float*>(a.ug_addr[u]);
+    if (dst) {
+#pragma unroll
+      for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; if (c < D4) st_f4(dst + 4 * c, acc[k]); }
+    }
+  } else if (a.unique_grads) {
 #pragma unroll
     for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; if (c < D4) st_f4(a.unique_grads + (int64_t)u * a.D + 4 * c, acc[k]); }
   }
@@ -388,11 +483,12 @@ template <int NCHUNK>
 __global__ void __launch_bounds__(kBlock) backward_tiles_kernel(BwdArgs a) {
   const int lane = threadIdx.x & 31;
   const int D4 = a.D >> 2;
-  const int64_t tiles = (a.n + 31) >> 5;
+  const int64_t n_act = bwd_n(a);
+  const int64_t tiles = (n_act + 31) >> 5;
   const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
   for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); tile < tiles; tile += wstride) {
     const int64_t base = tile << 5;
-    const int cnt = (int)((a.n - base) < 32 ? (a.n - base) : 32);
+    const int cnt = (int)((n_act - base) < 32 ? (n_act - base) : 32);
     int32_t myu = -1, myr = 0; float mys = 1.f;
     if (lane < cnt) {
       myu = a.skey[base + lane]; myr = a.sval[base + lane];
@@ -415,7 +511,7 @@ __global__ void __launch_bounds__(kBlock) backward_tiles_kernel(BwdArgs a) {
       }
     }
     const int32_t prev_u = base > 0 ? a.skey[base - 1] : -1;
-    const int32_t next_u = base + 32 < a.n ? a.skey[base + 32] : -2;
+    const int32_t next_u = base + 32 < n_act ? a.skey[base + 32] : -2;
     float4 acc[NCHUNK];
 #pragma unroll
     for (int k = 0; k < NCHUNK; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -496,7 +592,7 @@ template <int NCHUNK>
 __global__ void __launch_bounds__(kBlock) backward_windows_kernel(BwdArgs a, float* __restrict__ win_cont) {
   const int lane = threadIdx.x & 31;
   const int D4 = a.D >> 2;
-  const int64_t tiles = (a.n + 31) >> 5;
+  const int64_t tiles = (bwd_n(a) + 31) >> 5;
   const int64_t windows = (tiles + 31) >> 5;
   const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
   for (int64_t w = 1 + (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); w < windows; w += wstride) {
@@ -521,7 +617,7 @@ template <int NCHUNK>
 __global__ void __launch_bounds__(kBlock) backward_spans_kernel(BwdArgs a, const float* __restrict__ win_cont) {
   const int lane = threadIdx.x & 31;
   const int D4 = a.D >> 2;
-  const int64_t tiles = (a.n + 31) >> 5;
+  const int64_t tiles = (bwd_n(a) + 31) >> 5;
   const int64_t windows = (tiles + 31) >> 5;
   const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
   for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); tile + 1 < tiles; tile += wstride) {
@@ -555,11 +651,17 @@ __global__ void __launch_bounds__(kBlock) backward_spans_kernel(BwdArgs a, const
 
 // sort keys / payload for backward: key = inverse[i] (unique idx); payload = gradient row id
 // (sequence: i; pooled: b*F+f of the bag holding id i — generate_gather_ids_pooled_kernel, lookup_backward.cu).
-__global__ void backward_pairs_kernel(int64_t n, const int64_t* __restrict__ inverse, int pooled, int64_t B, int F, const int64_t* __restrict__ offsets,
+// n_dev (nullable): real element count; positions beyond it get the key `pad_key` (> every unique idx) so they sort to the end.
+// grad_row_of (nullable, sequence mode): gradient row id of id i when the gradient rows are not stored in id order.
+__global__ void backward_pairs_kernel(int64_t n, const int64_t* __restrict__ n_dev, int32_t pad_key, const int64_t* __restrict__ inverse,
+                                      const int64_t* __restrict__ grad_row_of, int pooled, int64_t B, int F, const int64_t* __restrict__ offsets,
                                       int32_t* __restrict__ key, int32_t* __restrict__ val) {
+  int64_t n_act = n;
+  if (n_dev) { n_act = *n_dev; n_act = n_act < 0 ? 0 : (n_act > n ? n : n_act); }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i >= n_act) { key[i] = pad_key; val[i] = 0; continue; }
     key[i] = (int32_t)inverse[i];
-    if (!pooled) { val[i] = (int32_t)i; continue; }
+    if (!pooled) { val[i] = grad_row_of ? (int32_t)grad_row_of[i] : (int32_t)i; continue; }
     int64_t lo = 0, hi = B * F;   // bag g with offsets[g] <= i < offsets[g+1]
     while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (offsets[mid] <= i) lo = mid; else hi = mid; }
     int64_t f = lo / B, b = lo - f * B;
@@ -584,10 +686,61 @@ __global__ void __launch_bounds__(kBlock) update_rows_kernel(float* __restrict__
   }
 }
 
+// ---- flat multi-table load / store / update through per-table base pointers (dynamic_emb_op.cu:295-490, optimizer.cu) ---------------
+// The reference keeps one value buffer per table and hands kernels an int64 array of base pointers; rows may have different widths
+// per table (mixed embedding dims).  region: 0 = contiguous prefix of min(value_dim, dense_dim) floats, 1 = embedding only,
+// 2 = [emb | pad to max_emb_dim | optimizer state].  Warp per row; indices < 0 are skipped.
+struct FlatArgs {
+  const int64_t* table_ptrs; const int64_t* table_ids; int64_t scalar_table_id; const int64_t* indices; int64_t n;
+  const int64_t* value_dims; const int64_t* emb_dims; int64_t max_emb_dim;
+  float* dense; int64_t dense_stride; int64_t dense_dim; int region; int to_table;
+};
+__device__ __forceinline__ void copy_span(const float* __restrict__ src, float* __restrict__ dst, int64_t len, int lane) {
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  const int64_t v4 = vec ? (len >> 2) : 0;
+  for (int64_t c = lane; c < v4; c += 32) st_f4(dst + 4 * c, ld_f4(src + 4 * c));
+  for (int64_t i = 4 * v4 + lane; i < len; i += 32) dst[i] = src[i];
+}
+__global__ void __launch_bounds__(kBlock) flat_table_copy_kernel(FlatArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t i = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); i < a.n; i += wstride) {
+    const int64_t idx = a.indices[i];
+    if (idx < 0) continue;
+    const int64_t t = a.table_ids ? a.table_ids[i] : a.scalar_table_id;
+    const int64_t vdim = a.value_dims[t], edim = a.emb_dims[t];
+    float* row = reinterpret_cast<float*>(a.table_ptrs[t]) + idx * vdim;
+    float* d = a.dense + i * a.dense_stride;
+    int64_t len0, off_t1 = 0, off_d1 = 0, len1 = 0;
+    if (a.region == 0) len0 = vdim < a.dense_dim ? vdim : a.dense_dim;
+    else if (a.region == 1) len0 = edim < a.dense_dim ? edim : a.dense_dim;
+    else { len0 = edim; off_t1 = edim; off_d1 = a.max_emb_dim; len1 = vdim - edim; }
+    if (a.to_table) { copy_span(d, row, len0, lane); if (len1 > 0) copy_span(d + off_d1, row + off_t1, len1, lane); }
+    else { copy_span(row, d, len0, lane); if (len1 > 0) copy_span(row + off_t1, d + off_d1, len1, lane); }
+  }
+}
+template <int NCHUNK>
+__global__ void __launch_bounds__(kBlock) flat_table_update_kernel(FlatArgs a, const float* __restrict__ grads, int64_t grad_stride, OptArgs o) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
+  for (int64_t i = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); i < a.n; i += wstride) {
+    const int64_t idx = a.indices[i];
+    if (idx < 0) continue;
+    const int64_t t = a.table_ids ? a.table_ids[i] : a.scalar_table_id;
+    const int D = (int)a.emb_dims[t];
+    float* row = reinterpret_cast<float*>(a.table_ptrs[t]) + idx * a.value_dims[t];
+    float4 g[NCHUNK];
+#pragma unroll
+    for (int k = 0; k < NCHUNK; ++k) { const int c = lane + 32 * k; g[k] = c < (D >> 2) ? ld_nc_f4(grads + i * grad_stride + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f); }
+    apply_row<NCHUNK>(o, row, D, g, lane);
+  }
+}
+
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 inline int nchunk_of(int D) { return (D / 4 + 31) / 32; }
 
 // bench.py's roofline needs per-kernel device time of the multi-kernel backward: optional CUDA events around its stages.
+bool g_probe_kernel = true;     // demb_set_option(0, ...): 0 = the round-1 thread-per-key probe inside forward_seq_tma_kernel (A/B measurements)
 bool g_prof_on = false;
 cudaEvent_t g_prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
@@ -627,6 +780,23 @@ static int launch_seq_tma(const RowSrc& s, const float* values, int64_t value_di
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }
+static int launch_seq_probe(const RowSrc& s, const float* values, int64_t value_dim, int emb_dim, int64_t n, float* out, float absent_value,
+                            cudaStream_t stream) {
+  const size_t per_warp = 32u * (size_t)emb_dim * 4u;
+  int warps = (int)((216u * 1024u) / per_warp);
+  if (warps > kProbeFwdWarps) warps = kProbeFwdWarps;
+  if (warps < 1) return DEMB_ERR_ARG;
+  const int smem = (int)(warps * per_warp);
+  static std::atomic<int> configured[kMaxDevices];
+  cudaError_t ce = once_per_device(configured, [] { return cudaFuncSetAttribute(forward_seq_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); });
+  if (ce != cudaSuccess) return -(int)ce;
+  const int64_t tiles = (n + 31) / 32;
+  int64_t blocks = (tiles + warps - 1) / warps;
+  if (blocks > sm_count()) blocks = sm_count();
+  forward_seq_probe_kernel<<<(int)blocks, kProbeFwdWarps * 32, smem, stream>>>(s, values, value_dim, emb_dim, n, out, absent_value, warps);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}
 static int check_dims(int D, int64_t vdim) { return (D <= 0 || (D & 3) || D > 128 * kMaxChunks || (vdim & 3) || vdim < D) ? DEMB_ERR_ARG : 0; }
 
 int demb_lookup_forward(void* storage, const int64_t* table_bucket_offsets, int64_t bucket_capacity, int num_scores, const float* values,
@@ -635,9 +805,11 @@ int demb_lookup_forward(void* storage, const int64_t* table_bucket_offsets, int6
                         float absent_value, uint8_t* founds, int64_t* slots_out, void* stream) {
   if (check_dims(emb_dim, value_dim)) return DEMB_ERR_ARG;
   RowSrc s{Table{(uint8_t*)storage, table_bucket_offsets, bucket_capacity, num_scores}, (const uint64_t*)keys, table_range, num_tables, row_base,
-           nullptr, nullptr, founds, slots_out};
+           nullptr, nullptr, founds, slots_out, nullptr};
   if (combiner < 0) {
     if (n <= 0) return 0;
+    if (out_dtype == DEMB_F32 && bucket_capacity == kProbeC && emb_dim <= 1024 && g_probe_kernel)
+      return launch_seq_probe(s, values, value_dim, emb_dim, n, (float*)out, absent_value, (cudaStream_t)stream);
     if (out_dtype == DEMB_F32) return launch_seq_tma(s, values, value_dim, emb_dim, n, (float*)out, absent_value, (cudaStream_t)stream);
     forward_seq_kernel<8><<<warp_grid((n + 31) / 32), kBlock, 0, (cudaStream_t)stream>>>(s, values, value_dim, emb_dim, n, out, out_dtype, absent_value);
   } else {
@@ -654,9 +826,11 @@ int demb_lookup_forward(void* storage, const int64_t* table_bucket_offsets, int6
 }
 
 int demb_gather_forward(const float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* rows, const int64_t* inverse,
-                        const int64_t* offsets, int64_t batch_size, int num_features, int combiner, void* out, int out_dtype, void* stream) {
+                        const int64_t* offsets, int64_t batch_size, int num_features, int combiner, void* out, int out_dtype, const int64_t* n_dev,
+                        void* stream) {
   if (check_dims(emb_dim, value_dim)) return DEMB_ERR_ARG;
-  RowSrc s{Table{nullptr, nullptr, 0, 1}, nullptr, nullptr, 1, nullptr, rows, inverse, nullptr, nullptr};
+  if (n_dev && combiner >= 0) return DEMB_ERR_ARG;                  // a device-side count only makes sense for the sequence layout
+  RowSrc s{Table{nullptr, nullptr, 0, 1}, nullptr, nullptr, 1, nullptr, rows, inverse, nullptr, nullptr, n_dev};
   if (combiner < 0) {
     if (n <= 0) return 0;
     if (out_dtype == DEMB_F32) return launch_seq_tma(s, values, value_dim, emb_dim, n, (float*)out, 0.f, (cudaStream_t)stream);
@@ -717,7 +891,8 @@ int64_t demb_backward_workspace_bytes(int64_t n, int emb_dim) {
 static int backward_impl(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound, const int64_t* rows,
                          const float* grads, int64_t grad_stride, const int64_t* offsets, int64_t batch_size, int num_features, int combiner,
                          int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
-                         float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, cudaStream_t stream, int phase) {
+                         float bias_correction2, float* unique_grads, const int64_t* n_dev, const int64_t* grad_row_of, const int64_t* ug_addr,
+                         void* workspace, int64_t workspace_bytes, cudaStream_t stream, int phase) {
   if (check_dims(emb_dim, value_dim > 0 ? value_dim : emb_dim)) return DEMB_ERR_ARG;
   if (n <= 0) return 0;
   if (n >= (1ll << 31) || num_unique_bound >= (1ll << 31)) return DEMB_ERR_ARG;
@@ -736,8 +911,9 @@ static int backward_impl(float* values, int64_t value_dim, int emb_dim, int64_t 
   if (phase != 2) {
     cudaStream_t s1 = stream;
     if (g_prof_on && phase == 0) cudaEventRecord(g_prof_ev[0], stream);
-    backward_pairs_kernel<<<(int)((n + 255) / 256), 256, 0, s1>>>(n, inverse, pooled, batch_size, num_features, offsets, k0, v0);
-    int end_bit = 1; while (end_bit < 31 && (1ll << end_bit) < num_unique_bound) ++end_bit;
+    backward_pairs_kernel<<<(int)((n + 255) / 256), 256, 0, s1>>>(n, n_dev, (int32_t)num_unique_bound, inverse, grad_row_of, pooled, batch_size, num_features,
+                                                                  offsets, k0, v0);
+    int end_bit = 1; while (end_bit < 31 && (1ll << end_bit) < num_unique_bound + (n_dev ? 1 : 0)) ++end_bit;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(w, tmp_bytes, k0, k1, v0, v1, (int)n, 0, end_bit, s1);
     if (e != cudaSuccess) return -(int)e;
     if (phase == 1) {
@@ -747,8 +923,8 @@ static int backward_impl(float* values, int64_t value_dim, int emb_dim, int64_t 
   } else {
     if (g_prof_on) cudaEventRecord(g_prof_ev[0], stream);
   }
-  BwdArgs a{grads, grad_stride, emb_dim, pooled, combiner, batch_size, num_features, offsets, k1, v1, n, rows, values, value_dim, unique_grads, pc, ps,
-            OptArgs{opt_type, lr, eps, beta1, beta2, weight_decay, bias_correction1, bias_correction2}};
+  BwdArgs a{grads, grad_stride, emb_dim, pooled, combiner, batch_size, num_features, offsets, k1, v1, n, n_dev, ug_addr, rows, values, value_dim, unique_grads,
+            pc, ps, OptArgs{opt_type, lr, eps, beta1, beta2, weight_decay, bias_correction1, bias_correction2}};
   if (g_prof_on) cudaEventRecord(g_prof_ev[1], stream);
   DISPATCH_NCHUNK(emb_dim, {
     backward_tiles_kernel<NC><<<warp_grid((int64_t)tiles), kBlock, 0, stream>>>(a);
@@ -768,26 +944,35 @@ static int backward_impl(float* values, int64_t value_dim, int emb_dim, int64_t 
 int demb_backward(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound, const int64_t* rows,
                   const float* grads, int64_t grad_stride, const int64_t* offsets, int64_t batch_size, int num_features, int combiner,
                   int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
-                  float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, void* stream_) {
+                  float bias_correction2, float* unique_grads, const int64_t* n_dev, const int64_t* grad_row_of, const int64_t* unique_grad_addr,
+                  void* workspace, int64_t workspace_bytes, void* stream_) {
   return backward_impl(values, value_dim, emb_dim, n, inverse, num_unique_bound, rows, grads, grad_stride, offsets, batch_size, num_features, combiner,
-                       opt_type, lr, eps, beta1, beta2, weight_decay, bias_correction1, bias_correction2, unique_grads, workspace, workspace_bytes,
-                       (cudaStream_t)stream_, 0);
+                       opt_type, lr, eps, beta1, beta2, weight_decay, bias_correction1, bias_correction2, unique_grads, n_dev, grad_row_of, unique_grad_addr,
+                       workspace, workspace_bytes, (cudaStream_t)stream_, 0);
 }
 // The part of demb_backward that does not need the gradients (pair list + sort).  Launch it EARLY — right after the prefetch, on a stream
 // of the caller's — so it overlaps the forward gather instead of sitting in front of the gradient reduction.
 int demb_backward_sort(int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound, const int64_t* offsets, int64_t batch_size,
-                       int num_features, int combiner, void* workspace, int64_t workspace_bytes, void* stream_) {
+                       int num_features, int combiner, const int64_t* n_dev, const int64_t* grad_row_of, void* workspace, int64_t workspace_bytes,
+                       void* stream_) {
   return backward_impl(nullptr, 0, emb_dim, n, inverse, num_unique_bound, nullptr, nullptr, 0, offsets, batch_size, num_features, combiner, 0, 0.f, 0.f, 0.f,
-                       0.f, 0.f, 1.f, 1.f, nullptr, workspace, workspace_bytes, (cudaStream_t)stream_, 1);
+                       0.f, 0.f, 1.f, 1.f, nullptr, n_dev, grad_row_of, nullptr, workspace, workspace_bytes, (cudaStream_t)stream_, 1);
 }
 // demb_backward after demb_backward_sort(... same n / inverse / workspace ...); the caller orders it behind the sort
 int demb_backward_apply(float* values, int64_t value_dim, int emb_dim, int64_t n, const int64_t* inverse, int64_t num_unique_bound,
                         const int64_t* rows, const float* grads, int64_t grad_stride, const int64_t* offsets, int64_t batch_size, int num_features,
                         int combiner, int opt_type, float lr, float eps, float beta1, float beta2, float weight_decay, float bias_correction1,
-                        float bias_correction2, float* unique_grads, void* workspace, int64_t workspace_bytes, void* stream_) {
+                        float bias_correction2, float* unique_grads, const int64_t* n_dev, const int64_t* unique_grad_addr, void* workspace,
+                        int64_t workspace_bytes, void* stream_) {
   return backward_impl(values, value_dim, emb_dim, n, inverse, num_unique_bound, rows, grads, grad_stride, offsets, batch_size, num_features, combiner,
-                       opt_type, lr, eps, beta1, beta2, weight_decay, bias_correction1, bias_correction2, unique_grads, workspace, workspace_bytes,
-                       (cudaStream_t)stream_, 2);
+                       opt_type, lr, eps, beta1, beta2, weight_decay, bias_correction1, bias_correction2, unique_grads, n_dev, nullptr, unique_grad_addr,
+                       workspace, workspace_bytes, (cudaStream_t)stream_, 2);
+}
+
+// development / measurement switches.  option 0: 1 = tile probe kernel for the fused lookup forward (default), 0 = round-1 kernel
+int demb_set_option(int option, int value) {
+  if (option == 0) { g_probe_kernel = value != 0; return 0; }
+  return DEMB_ERR_ARG;
 }
 
 int demb_profile_enable(int on) {
@@ -800,6 +985,31 @@ int demb_profile_read(float* ms3) {
   if (!g_prof_ev[0]) return DEMB_ERR_ARG;
   if (cudaEventSynchronize(g_prof_ev[3]) != cudaSuccess) return DEMB_ERR_ARG;
   for (int i = 0; i < 3; ++i) if (cudaEventElapsedTime(&ms3[i], g_prof_ev[i], g_prof_ev[i + 1]) != cudaSuccess) return DEMB_ERR_ARG;
+  return 0;
+}
+
+// load_from_flat_table_{contiguous,emb,value} / store_to_flat_table_{contiguous,value} (dynamic_emb_op.cu:295-490): see FlatArgs above.
+int demb_flat_table_copy(const int64_t* table_ptrs, const int64_t* table_ids, int64_t scalar_table_id, const int64_t* indices, int64_t n,
+                         const int64_t* table_value_dims, const int64_t* table_emb_dims, int64_t max_emb_dim, float* dense, int64_t dense_stride,
+                         int64_t dense_dim, int region, int to_table, void* stream) {
+  if (region < 0 || region > 2 || !table_ptrs || !indices || !dense) return DEMB_ERR_ARG;
+  if (n <= 0) return 0;
+  FlatArgs a{table_ptrs, table_ids, scalar_table_id, indices, n, table_value_dims, table_emb_dims, max_emb_dim, dense, dense_stride, dense_dim, region, to_table};
+  flat_table_copy_kernel<<<warp_grid(n), kBlock, 0, (cudaStream_t)stream>>>(a);
+  DEMB_CHECK_LAST();
+  return 0;
+}
+// {sgd,adam,adagrad,rowwise_adagrad}_update_for_flat_table (optimizer.cu:416-447): grads[n, max_emb_dim] applied to rows addressed through
+// per-table base pointers; embedding dims must be multiples of 4 and <= 1024.
+int demb_flat_table_update(const int64_t* table_ptrs, const int64_t* table_ids, const int64_t* indices, int64_t n, const int64_t* table_value_dims,
+                           const int64_t* table_emb_dims, int64_t max_emb_dim, const float* grads, int64_t grad_stride, int opt_type, float lr,
+                           float eps, float beta1, float beta2, float weight_decay, float bias_correction1, float bias_correction2, void* stream) {
+  if (!table_ptrs || !indices || !grads || max_emb_dim <= 0 || (max_emb_dim & 3) || max_emb_dim > 128 * kMaxChunks) return DEMB_ERR_ARG;
+  if (n <= 0) return 0;
+  FlatArgs a{table_ptrs, table_ids, 0, indices, n, table_value_dims, table_emb_dims, max_emb_dim, nullptr, 0, 0, 0, 0};
+  OptArgs o{opt_type, lr, eps, beta1, beta2, weight_decay, bias_correction1, bias_correction2};
+  DISPATCH_NCHUNK((int)max_emb_dim, flat_table_update_kernel<NC><<<warp_grid(n), kBlock, 0, (cudaStream_t)stream>>>(a, grads, grad_stride, o));
+  DEMB_CHECK_LAST();
   return 0;
 }
 

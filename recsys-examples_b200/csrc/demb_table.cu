@@ -188,9 +188,29 @@ __global__ void table_export_kernel(Table t, int64_t begin, int64_t end, int64_t
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// global bucket of every key (bucketize.cu:38-58 BucketizeFunctor)
+__global__ void bucket_of_kernel(Table t, int64_t n, const uint64_t* __restrict__ keys, const int64_t* __restrict__ tids, int64_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tid = tids ? tids[i] : 0;
+    const int64_t bb = t.bkt_off[tid], cap = (t.bkt_off[tid + 1] - bb) * t.C;
+    out[i] = cap > 0 ? bb + (int64_t)((uint64_t)hash63(keys[i]) % (uint64_t)cap) / t.C : bb;
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+// bucket id of each key (the first half of the reference's bucketize_keys, table_operation/bucketize.cu:111)
+int demb_bucket_of(const int64_t* table_bucket_offsets, int64_t bucket_capacity, int64_t n, const void* keys, const int64_t* table_ids, int64_t* buckets,
+                   void* stream) {
+  if (n <= 0) return 0;
+  Table t{nullptr, table_bucket_offsets, bucket_capacity, 1};
+  const int64_t gcap = (int64_t)sm_count() * 16; int64_t g = (n + kBlock - 1) / kBlock;
+  bucket_of_kernel<<<(int)(g > gcap ? gcap : g), kBlock, 0, (cudaStream_t)stream>>>(t, n, (const uint64_t*)keys, table_ids, buckets);
+  DEMB_CHECK_LAST();
+  return 0;
+}
 
 int demb_table_init(void* storage, int64_t num_buckets, int64_t bucket_capacity, int num_scores, void* stream) {
   if (bucket_capacity % 16) return DEMB_ERR_ARG;

@@ -21,6 +21,7 @@
 #include "demb_common.cuh"
 #include "demb_insert.cuh"
 #include "demb_init.cuh"
+#include "demb_probe.cuh"
 
 using namespace demb;
 
@@ -35,6 +36,7 @@ struct TrainArgs {
   int pol; const uint64_t* table_scores; const int64_t* freq; uint64_t ts; int key_is_signed;
   InitArgs init; const InitArgs* table_init; float state_init;   // table_init: per-table initializer (device, [T]), nullable => init
   int64_t* slots; int64_t* rows; int32_t* next; int32_t* touched; unsigned long long* n_touched;
+  int32_t* init_list; unsigned long long* n_init;   // uniques inserted by the thread kernel: their rows are initialised by train_init_rows_kernel
 };
 
 __device__ __forceinline__ uint64_t train_score(const TrainArgs& a, int64_t u, int64_t tid) {
@@ -84,6 +86,61 @@ __global__ void train_lookup_kernel(TrainArgs a) {
       base = __shfl_sync(0xffffffffu, base, leader);
       if (first_bucket >= 0) a.touched[base + __popc(m & ((1u << lane) - 1u))] = first_bucket;
     }
+  }
+}
+
+// The same lookup for 128-slot buckets on the warp-tile probe (demb_probe.cuh): the digest lines of tile t+1 are loaded (coalesced, into
+// registers) while tile t is scanned, so a probe costs one exposed memory hop (the candidate key loads) instead of the per-thread chain.
+constexpr int kLookupWarps = 8;
+__global__ void __launch_bounds__(kLookupWarps * 32) train_lookup_tile_kernel(TrainArgs a) {
+  __shared__ int slot_sm[kLookupWarps][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t n = *a.n_u;
+  const int64_t tiles = (n + 31) >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * kLookupWarps;
+  int64_t tile = (int64_t)blockIdx.x * kLookupWarps + wib;
+  auto load_key = [&](int64_t tl) -> ProbeKey {
+    const int64_t u = (tl << 5) + lane;
+    if (tl >= tiles || u >= n) return ProbeKey{0, 0, 0, 0, false};
+    return make_probe_key(a.t, a.ukeys[u], a.utids ? (int)a.utids[u] : 0);
+  };
+  ProbeKey k0 = load_key(tile);
+  DigRegs d0, d1;
+  tile_load_digests(a.t, k0, d0, lane);
+  for (; tile < tiles; tile += wstride) {
+    const ProbeKey k1 = load_key(tile + wstride);
+    tile_load_digests(a.t, k1, d1, lane);
+    const int pos = tile_probe(a.t, k0, d0, slot_sm[wib], lane);
+    const int64_t u = (tile << 5) + lane;
+    int32_t first_bucket = -1;                                                    // >= 0: this lane pushed the FIRST key of that bucket
+    if (u < n) {
+      int64_t slot = -1, row = -1;
+      if (k0.valid) {
+        if (pos >= 0) {
+          uint8_t* bk = a.t.bucket(k0.bucket);
+          if (a.pol != kConst) policy_update(a.pol, a.t.scores(bk, pos), train_score(a, u, k0.tid), a.ts, false);
+          slot = k0.slot_base + pos;
+          row = (a.row_base ? a.row_base[k0.tid] : 0) + slot;
+          atomicAdd(a.counter + k0.bucket * a.t.C + pos, 1);                      // pin (increment_counter, :607)
+        } else {
+          const int old = atomicExch(a.heads + k0.bucket, (int)u);
+          a.next[u] = old;                                                        // >= -1: list link
+          if (old == -1) first_bucket = (int32_t)k0.bucket;
+        }
+      }
+      a.slots[u] = slot;
+      a.rows[u] = row;
+      if (slot >= 0 || !k0.valid) a.next[u] = -3;                                 // not on any list
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, first_bucket >= 0);
+    if (m) {
+      const int leader = __ffs(m) - 1;
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(a.n_touched, (unsigned long long)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (first_bucket >= 0) a.touched[base + __popc(m & ((1u << lane) - 1u))] = first_bucket;
+    }
+    k0 = k1; d0 = d1;
   }
 }
 
@@ -156,6 +213,119 @@ __global__ void __launch_bounds__(kBlock) train_insert_kernel(TrainArgs a) {
   }
 }
 
+// Warp per touched bucket that may evict, 128-slot buckets: the bucket's keys, reduction scores and pin counters are loaded ONCE into
+// registers (4 slots per lane, all loads independent), then every new key of the bucket (in key order) picks its slot from the registers —
+// first Empty slot in probe order, else the minimum-score unpinned slot, first minimum in storage order (types.cuh:417-465,
+// kernels.cuh:238-275) — and only the owning lane touches memory.  The per-key path above re-reads digests, scores, keys and counters of
+// the whole bucket for every key (7 dependent round trips per insert; 0.25 ms of a 1.0 ms step at eviction steady state, where EVERY new
+// key evicts).  A key on a bucket list is known to be absent (train_lookup), so there is no existence probe.
+__global__ void __launch_bounds__(kBlock) train_evict_kernel(TrainArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nt = (int64_t)*a.n_touched;
+  const int64_t wstride = (int64_t)gridDim.x * (kBlock / 32);
+  constexpr int C = kProbeC;
+  for (int64_t w = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); w < nt; w += wstride) {
+    const int64_t b = a.touched[w];
+    const int head = *reinterpret_cast<volatile int*>(a.heads + b);
+    uint8_t* bk = a.t.bucket(b);
+    // bucket state -> registers (issued before the list walk: independent of it)
+    uint64_t kreg[4], sreg[4]; int32_t creg[4];
+    {
+      const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(a.t.keys(bk) + lane * 4);
+      const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(a.t.keys(bk) + lane * 4 + 2);
+      kreg[0] = k01.x; kreg[1] = k01.y; kreg[2] = k23.x; kreg[3] = k23.y;
+      const int4 c4 = *reinterpret_cast<const int4*>(a.counter + b * C + lane * 4);
+      creg[0] = c4.x; creg[1] = c4.y; creg[2] = c4.z; creg[3] = c4.w;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sreg[q] = a.t.scores(bk, lane * 4 + q)[a.t.ns - 1];
+    }
+    int cnt = 0, mine = -1;
+    for (int cur = head; cur != -1; cur = a.next[cur]) { if (cnt == lane) mine = cur; ++cnt; }
+    if (cnt > 32) {                                                               // long list (tiny tables): per-key path, selection order
+      bool have_last = false; uint64_t last = 0;
+      for (int r = 0; r < cnt; ++r) {
+        uint64_t best = 0; int bu = -1; int idx = 0;
+        for (int cur = head; cur != -1; cur = a.next[cur], ++idx) {
+          if ((idx & 31) != lane) continue;
+          const uint64_t k = a.ukeys[cur];
+          if (have_last && !key_less(last, k, a.key_is_signed)) continue;
+          if (bu < 0 || key_less(k, best, a.key_is_signed)) { best = k; bu = cur; }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          const uint64_t ok = __shfl_xor_sync(0xffffffffu, best, d);
+          const int ou = __shfl_xor_sync(0xffffffffu, bu, d);
+          if (ou >= 0 && (bu < 0 || key_less(ok, best, a.key_is_signed))) { best = ok; bu = ou; }
+        }
+        train_insert_key(a, b, bu, best, lane);
+        last = best; have_last = true;
+      }
+      if (lane == 0) a.heads[b] = -1;
+      continue;
+    }
+    const uint64_t mykey = mine >= 0 ? a.ukeys[mine] : 0;
+    int rank = 0;
+    for (int l = 0; l < cnt; ++l) {
+      const uint64_t ok = __shfl_sync(0xffffffffu, mykey, l);
+      if (mine >= 0 && l != lane && key_less(ok, mykey, a.key_is_signed)) ++rank;   // keys are unique => strict order
+    }
+    if (mine < 0) rank = -1;
+    for (int r = 0; r < cnt; ++r) {
+      const unsigned sel = __ballot_sync(0xffffffffu, rank == r);
+      const int src = __ffs(sel) - 1;
+      const int u = __shfl_sync(0xffffffffu, mine, src);
+      const uint64_t key = __shfl_sync(0xffffffffu, mykey, src);
+      const int64_t tid = a.utids ? a.utids[u] : 0;
+      const int64_t h = hash63(key);
+      const int start = (int)(h % C) & ~15;
+      // first Empty slot in probe order: smallest (pos - start) mod C
+      int dmin = 1 << 20;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (kreg[q] == kEmptyKey) { const int d = ((lane * 4 + q) - start) & (C - 1); dmin = d < dmin ? d : dmin; }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) { const int o = __shfl_xor_sync(0xffffffffu, dmin, d); dmin = o < dmin ? o : dmin; }
+      int pos = -1; int result = kBusy;
+      if (dmin < (1 << 20)) { pos = (start + dmin) & (C - 1); result = kInsert; }
+      else {
+        uint64_t best = 0xFFFFFFFFFFFFFFFFull; int bi = -1;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (sreg[q] < best && kreg[q] != kLockedKey && kreg[q] != kEmptyKey && creg[q] <= 0) { best = sreg[q]; bi = lane * 4 + q; }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          const uint64_t os = __shfl_xor_sync(0xffffffffu, best, d);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+          if (oi >= 0 && (bi < 0 || os < best || (os == best && oi < bi))) { best = os; bi = oi; }
+        }
+        if (bi >= 0) { pos = bi; result = kEvict; }                               // Reclaim vs Evict decided by the owning lane
+      }
+      if (pos < 0) continue;                                                     // every slot pinned: insert fails, slots[u] / rows[u] stay -1
+      if (lane == (pos >> 2)) {
+        const int q = pos & 3;
+        uint64_t oldkey = 0;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) if (qq == q) { oldkey = kreg[qq]; kreg[qq] = key; creg[qq] += 1; }
+        if (result == kEvict && oldkey == kReclaimKey) result = kReclaim;
+        uint64_t* sc = a.t.scores(bk, pos);
+        a.t.digests(bk)[pos] = digest_of(h);
+        if (result != kEvict) a.bucket_sizes[b] += 1;
+        else for (int s2 = 0; s2 < a.t.ns; ++s2) sc[s2] = 0;
+        policy_update(a.pol, sc, train_score(a, u, tid), a.ts, false);
+        a.t.keys(bk)[pos] = key;
+        atomicAdd(a.counter + b * C + pos, 1);                                    // pin
+      }
+      const int64_t slot = (b - a.t.bkt_off[tid]) * C + pos;
+      const int64_t row = (a.row_base ? a.row_base[tid] : 0) + slot;
+      if (lane == 0) { a.slots[u] = slot; a.rows[u] = row; }
+      const InitArgs ia = a.table_init ? a.table_init[tid] : a.init;
+      const int D4 = a.D >> 2, V4 = (int)(a.vdim >> 2);
+      for (int c = lane; c < D4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, init4(ia, key, c));
+      for (int c = D4 + lane; c < V4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, make_float4(a.state_init, a.state_init, a.state_init, a.state_init));
+    }
+    if (lane == 0) a.heads[b] = -1;                                               // leave the list heads clean for the next step
+  }
+}
+
 // Thread per touched bucket (see the file header).  Buckets that might overflow are handed to the warp kernel through touched2.
 __global__ void __launch_bounds__(kBlock) train_insert_thread_kernel(TrainArgs a, int32_t* __restrict__ touched2, unsigned long long* n_touched2) {
   const int64_t nt = (int64_t)*a.n_touched;
@@ -186,23 +356,26 @@ __global__ void __launch_bounds__(kBlock) train_insert_thread_kernel(TrainArgs a
       }
       last = best; have_last = true;
     }
-    for (int cur = head; cur != -1;) {                                            // the list is consumed: turn its links into "initialise me" marks
-      const int nx = a.next[cur];
-      a.next[cur] = a.slots[cur] >= 0 ? -2 : -4;
-      cur = nx;
+    // the list is consumed: queue the inserted keys for row initialisation (one atomic per bucket)
+    int ins = 0;
+    for (int cur = head; cur != -1; cur = a.next[cur]) ins += a.slots[cur] >= 0 ? 1 : 0;
+    if (ins) {
+      unsigned long long at = atomicAdd(a.n_init, (unsigned long long)ins);
+      for (int cur = head; cur != -1; cur = a.next[cur]) if (a.slots[cur] >= 0) a.init_list[at++] = cur;
     }
     a.heads[b] = -1;                                                              // leave the list heads clean for the next step
   }
 }
 
-// Warp per unique key: rows inserted by the thread kernel (next[u] == -2) get initializer + optimizer state (fused A10 + A11).
+// Warp per queued key: rows inserted by the thread kernel get initializer + optimizer state (fused A10 + A11).  The queue is empty at
+// eviction steady state (every insert goes through the evict kernel, which initialises inline): the kernel then costs one load.
 __global__ void __launch_bounds__(kBlock) train_init_rows_kernel(TrainArgs a) {
   const int lane = threadIdx.x & 31;
-  const int64_t n = *a.n_u;
+  const int64_t n = (int64_t)*a.n_init;
   const int64_t wstride = (int64_t)gridDim.x * (kBlock / 32);
   const int D4 = a.D >> 2, V4 = (int)(a.vdim >> 2);
-  for (int64_t u = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); u < n; u += wstride) {
-    if (a.next[u] != -2) continue;
+  for (int64_t q = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); q < n; q += wstride) {
+    const int64_t u = a.init_list[q];
     const int64_t row = a.rows[u];
     const uint64_t key = a.ukeys[u];
     const InitArgs ia = a.table_init ? a.table_init[a.utids ? a.utids[u] : 0] : a.init;
@@ -223,6 +396,8 @@ __global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+__global__ void zero2_kernel(unsigned long long* p) { if (threadIdx.x < 3) p[threadIdx.x] = 0ull; }
+
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 int grid_for(int64_t n) { int64_t g = (n + kBlock - 1) / kBlock; const int64_t cap = (int64_t)sm_count() * 32; return (int)(g < 1 ? 1 : (g > cap ? cap : g)); }
 }  // namespace
@@ -237,31 +412,33 @@ int demb_fill_i32(int32_t* p, int64_t n, int32_t v, void* stream) {
 }
 
 int64_t demb_train_prefetch_workspace_bytes(int64_t n, int num_tables) {
-  return demb_segmented_unique_workspace_bytes(n, num_tables) + (int64_t)(3 * align256(4 * (size_t)(n > 0 ? n : 1)) + 512);
+  return demb_segmented_unique_workspace_bytes(n, num_tables) + (int64_t)(4 * align256(4 * (size_t)(n > 0 ? n : 1)) + 512);
 }
 
 int demb_train_prefetch(void* storage, const int64_t* table_bucket_offsets, int64_t bucket_capacity, int num_scores, int32_t* bucket_sizes,
                         int32_t* ref_counter, int32_t* bucket_heads, float* values, int64_t value_dim, int emb_dim, const int64_t* row_base,
-                        int64_t n, const void* keys, const int64_t* table_range, int num_tables, const int64_t* freq_in, int policy,
+                        int64_t n, const int64_t* n_dev, const void* keys, const int64_t* table_range, int num_tables, const int64_t* freq_in, int policy,
                         const uint64_t* table_scores, uint64_t timestamp, int key_is_signed, int init_mode, float p0, float p1, float p2, float p3,
                         uint64_t seed, const demb_init_args_t* table_init, float state_init, void* unique_keys, int64_t* reverse_indices, int64_t* unique_table_ids,
-                        int64_t* unique_freq, int64_t* slots, int64_t* rows, int64_t* num_unique, void* workspace, int64_t workspace_bytes,
-                        void* stream_) {
+                        int64_t* unique_freq, int64_t* slots, int64_t* rows, int64_t* num_unique, void* unique_scratch, void* workspace,
+                        int64_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (n <= 0) return demb_segmented_unique(0, keys, table_range, num_tables, nullptr, unique_keys, reverse_indices, nullptr, nullptr, nullptr, num_unique, workspace, workspace_bytes, stream_);
+  if (n <= 0) return demb_segmented_unique(0, nullptr, keys, table_range, num_tables, nullptr, unique_keys, reverse_indices, nullptr, nullptr, nullptr, num_unique, nullptr, workspace, workspace_bytes, stream_);
   if (workspace_bytes < demb_train_prefetch_workspace_bytes(n, num_tables)) return DEMB_ERR_WORKSPACE;
   if ((emb_dim & 3) || (value_dim & 3) || value_dim < emb_dim) return DEMB_ERR_ARG;
   uint8_t* w = (uint8_t*)workspace;
   int32_t* next = (int32_t*)w; w += align256(4 * (size_t)n);
   int32_t* touched = (int32_t*)w; w += align256(4 * (size_t)n);
   int32_t* touched2 = (int32_t*)w; w += align256(4 * (size_t)n);
+  int32_t* init_list = (int32_t*)w; w += align256(4 * (size_t)n);
   unsigned long long* n_touched = (unsigned long long*)w; w += 256;
   unsigned long long* n_touched2 = n_touched + 1;
+  unsigned long long* n_init = n_touched + 2;
   const int64_t uws = (int64_t)((uint8_t*)workspace + workspace_bytes - w);
-  cudaMemsetAsync(n_touched, 0, 16, stream);
+  zero2_kernel<<<1, 32, 0, stream>>>(n_touched);
   const bool need_freq = (policy == kAccumulate || policy == kLruLfu);
-  int rc = demb_segmented_unique(n, keys, table_range, num_tables, freq_in, unique_keys, reverse_indices, nullptr, need_freq ? unique_freq : nullptr,
-                                 unique_table_ids, num_unique, w, uws, stream_);
+  int rc = demb_segmented_unique(n, n_dev, keys, table_range, num_tables, freq_in, unique_keys, reverse_indices, nullptr, need_freq ? unique_freq : nullptr,
+                                 unique_table_ids, num_unique, unique_scratch, w, uws, stream_);
   if (rc) return rc;
   TrainArgs a;
   a.t = Table{(uint8_t*)storage, table_bucket_offsets, bucket_capacity, num_scores};
@@ -270,12 +447,19 @@ int demb_train_prefetch(void* storage, const int64_t* table_bucket_offsets, int6
   a.ukeys = (const uint64_t*)unique_keys; a.utids = num_tables > 1 ? unique_table_ids : nullptr; a.n_u = num_unique;
   a.pol = policy; a.table_scores = table_scores; a.freq = need_freq ? unique_freq : nullptr; a.ts = timestamp; a.key_is_signed = key_is_signed;
   a.init = InitArgs{init_mode, p0, p1, p2, p3, seed}; a.table_init = reinterpret_cast<const InitArgs*>(table_init); a.state_init = state_init;
-  a.slots = slots; a.rows = rows; a.next = next; a.touched = touched; a.n_touched = n_touched;
-  train_lookup_kernel<<<grid_for(n), kBlock, 0, stream>>>(a);
+  a.slots = slots; a.rows = rows; a.next = next; a.touched = touched; a.n_touched = n_touched; a.init_list = init_list; a.n_init = n_init;
+  if (bucket_capacity == kProbeC) {
+    int64_t blocks = ((n + 31) / 32 + kLookupWarps - 1) / kLookupWarps;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    train_lookup_tile_kernel<<<(int)(blocks > cap ? cap : blocks), kLookupWarps * 32, 0, stream>>>(a);
+  } else {
+    train_lookup_kernel<<<grid_for(n), kBlock, 0, stream>>>(a);
+  }
   train_insert_thread_kernel<<<grid_for(n), kBlock, 0, stream>>>(a, touched2, n_touched2);
   TrainArgs a2 = a;
   a2.touched = touched2; a2.n_touched = n_touched2;
-  train_insert_kernel<<<sm_count() * 4, kBlock, 0, stream>>>(a2);                       // buckets that may evict (none until the table fills up)
+  if (bucket_capacity == kProbeC) train_evict_kernel<<<sm_count() * 8, kBlock, 0, stream>>>(a2);   // buckets that may evict (all of them at steady state)
+  else train_insert_kernel<<<sm_count() * 4, kBlock, 0, stream>>>(a2);
   train_init_rows_kernel<<<sm_count() * 8, kBlock, 0, stream>>>(a);
   DEMB_CHECK_LAST();
   return 0;

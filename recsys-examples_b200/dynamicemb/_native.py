@@ -35,25 +35,45 @@ _SIGS = {
     "demb_table_export": (I32, [P, P, I64, I32, I64, I64, I64, U64, I32, I32, P, P, P, P, P]),
     "demb_get_table_range": (I32, [P, P, I32, I64, P, P]),
     "demb_segmented_unique_workspace_bytes": (I64, [I64, I32]),
-    "demb_segmented_unique": (I32, [I64, P, P, I32, P, P, P, P, P, P, P, P, I64, P]),
+    "demb_unique_scratch_bytes": (I64, [I64, I32]),
+    "demb_unique_scratch_init": (I32, [P, I64, P]),
+    "demb_segmented_unique": (I32, [I64, P, P, P, I32, P, P, P, P, P, P, P, P, P, I64, P]),
+    "demb_flagged_compact_workspace_bytes": (I64, [I64]),
+    "demb_flagged_compact": (I32, [I64, P, P, P, P, P, I32, P, I64, P]),
     "demb_expand_table_ids": (I32, [P, I32, I64, P, P]),
     "demb_lookup_forward": (I32, [P, P, I64, I32, P, I64, I32, P, I64, P, P, I32, P, I64, I32, I32, P, I32, F32, P, P, P]),
-    "demb_gather_forward": (I32, [P, I64, I32, I64, P, P, P, I64, I32, I32, P, I32, P]),
+    "demb_gather_forward": (I32, [P, I64, I32, I64, P, P, P, I64, I32, I32, P, I32, P, P]),
     "demb_rows_from_slots": (I32, [I64, P, P, P, P, P]),
     "demb_init_rows": (I32, [P, I64, I32, I64, P, P, I32, F32, F32, F32, F32, U64, P, P, F32, P, P, P]),
     "demb_copy_rows": (I32, [P, I64, I32, I64, P, P, I64, I32, P]),
     "demb_backward_workspace_bytes": (I64, [I64, I32]),
-    "demb_backward": (I32, [P, I64, I32, I64, P, I64, P, P, I64, P, I64, I32, I32, I32, F32, F32, F32, F32, F32, F32, F32, P, P, I64, P]),
-    "demb_backward_sort": (I32, [I32, I64, P, I64, P, I64, I32, I32, P, I64, P]),
-    "demb_backward_apply": (I32, [P, I64, I32, I64, P, I64, P, P, I64, P, I64, I32, I32, I32, F32, F32, F32, F32, F32, F32, F32, P, P, I64, P]),
+    "demb_backward": (I32, [P, I64, I32, I64, P, I64, P, P, I64, P, I64, I32, I32, I32, F32, F32, F32, F32, F32, F32, F32, P, P, P, P, P, I64, P]),
+    "demb_backward_sort": (I32, [I32, I64, P, I64, P, I64, I32, I32, P, P, P, I64, P]),
+    "demb_backward_apply": (I32, [P, I64, I32, I64, P, I64, P, P, I64, P, I64, I32, I32, I32, F32, F32, F32, F32, F32, F32, F32, P, P, P, P, I64, P]),
     "demb_update_rows": (I32, [P, I64, I32, I64, P, P, I64, I32, F32, F32, F32, F32, F32, F32, F32, P]),
+    "demb_flat_table_copy": (I32, [P, P, I64, P, I64, P, P, I64, P, I64, I64, I32, I32, P]),
+    "demb_flat_table_update": (I32, [P, P, P, I64, P, P, I64, P, I64, I32, F32, F32, F32, F32, F32, F32, F32, P]),
+    "demb_bucket_of": (I32, [P, I64, I64, P, P, P, P]),
     "demb_fill_i32": (I32, [P, I64, I32, P]),
     "demb_train_prefetch_workspace_bytes": (I64, [I64, I32]),
-    "demb_train_prefetch": (I32, [P, P, I64, I32, P, P, P, P, I64, I32, P, I64, P, P, I32, P, I32, P, U64, I32, I32, F32, F32, F32, F32, U64, P, F32,
-                                  P, P, P, P, P, P, P, P, I64, P]),
+    "demb_train_prefetch": (I32, [P, P, I64, I32, P, P, P, P, I64, I32, P, I64, P, P, P, I32, P, I32, P, U64, I32, I32, F32, F32, F32, F32, U64, P, F32,
+                                  P, P, P, P, P, P, P, P, P, I64, P]),
     "demb_counter_update_n": (I32, [P, P, P, P, I64, P, I64, I32, P]),
+    "demb_set_option": (I32, [I32, I32]),
     "demb_profile_enable": (I32, [I32]),
     "demb_profile_read": (I32, [P]),
+    "demb_shard_layout": (I32, [I32, I64, I64, I32, P]),
+    "demb_shard_route_workspace_bytes": (I64, [I64, I32, I32]),
+    "demb_shard_route": (I32, [I32, I32, I32, I32, I64, I64, P, P, I64, P, P, P, P, P, P, P, P, I64, P]),
+    "demb_shard_recv_workspace_bytes": (I64, [I32, I32]),
+    "demb_shard_recv": (I32, [I32, I32, I32, I32, I64, I64, I64, P, P, P, P, P, P, P, P, I64, P]),
+    "demb_shard_gather_to_peers": (I32, [P, I64, I32, I64, P, P, P, P, P]),
+    "demb_peer_barrier": (I32, [I32, I32, I64, I64, I32, P, P, I32, P, P]),
+    "demb_zero_i64": (I32, [P, I64, P]),
+    "demb_ipc_alloc": (I32, [I64, P, P]),
+    "demb_ipc_open": (I32, [P, P]),
+    "demb_ipc_close": (I32, [P]),
+    "demb_ipc_free": (I32, [P]),
     "demb_bucketize_workspace_bytes": (I64, [I64, I32]),
     "demb_block_bucketize_sparse_features": (I32, [I64, I64, I32, P, P, P, P, P, P, P, P, P, P, I64, P]),
     "demb_block_bucketize_sparse_features_n": (I32, [I64, I64, I32, I64, P, P, P, P, P, P, P, P, P, P, I64, P]),

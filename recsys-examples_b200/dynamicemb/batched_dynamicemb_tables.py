@@ -366,9 +366,26 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         self._prefetch_states.append(PrefetchState(ukeys, reverse, utids, slots, rows, nu))
         self._update_score()
 
-    def _prefetch_fused(self, indices, trange, T, frequency_counters) -> None:
+    def _unique_scratch(self, n: int) -> torch.Tensor:
+        """Module-owned persistent dedup scratch (left clean by every call): no per-step re-initialisation of 32 B per id."""
+        sc = getattr(self, "_uscratch", None)
+        if sc is None or self._uscratch_n < n:
+            assert not torch.cuda.is_current_stream_capturing(), "first use / growth of the dedup scratch must happen outside graph capture"
+            self._uscratch_n = max(n, 1024)
+            self._uscratch = sc = ext.unique_scratch(self._uscratch_n, len(self._dynamicemb_options), self._device)
+        return sc
+
+    def _prefetch_device_count(self, indices, trange, T, n_dev, scratch) -> PrefetchState:
+        """Fused prefetch of `indices[:n_dev]` (count on the device; indices.numel() bounds it) — the owner side of the row-wise sharded
+        step.  Returns the state instead of queueing it."""
+        self._prefetch_fused(indices, trange, T, None, n_dev=n_dev, scratch=scratch, prepare=False)
+        return self._prefetch_states.pop()
+
+    def _prefetch_fused(self, indices, trange, T, frequency_counters, n_dev=None, scratch=None, prepare=True) -> None:
         """Same table image / rows as the op-by-op path, one C call, no host sync (csrc/demb_train.cu)."""
         tb = self._table
+        if scratch is None:
+            scratch = self._unique_scratch(indices.numel())
         policy = self._score_policy()
         scores = None
         if policy == ScorePolicy.ASSIGN:
@@ -380,9 +397,10 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         uk, rev, utids, slots, rows, nu = ext.train_prefetch(
             tb.table_storage_, tb.table_bucket_offsets_, tb.bucket_capacity_, tb.bucket_sizes, tb._ref_counter, tb._bucket_heads, self._values,
             self.max_D, tb.row_base_, indices, trange, T, policy, scores, ext.device_timestamp(), mode, p, seed0,
-            self._optimizer.initial_state_value, freq_in=frequency_counters, num_scores=tb.num_scores_, table_init=self._table_init_dev)
+            self._optimizer.initial_state_value, freq_in=frequency_counters, num_scores=tb.num_scores_, table_init=self._table_init_dev,
+            n_dev=n_dev, unique_scratch=scratch)
         st = PrefetchState(uk, rev, utids if T > 1 else None, slots, rows, indices.numel(), nu)
-        if (self.training and self.pooling_mode == DynamicEmbPoolingMode.NONE and torch.is_grad_enabled()) or self._force_prepare:
+        if prepare and ((self.training and self.pooling_mode == DynamicEmbPoolingMode.NONE and torch.is_grad_enabled()) or self._force_prepare):
             # the gradient-independent half of the fused backward (pair list + sort) starts now, on a side stream, under the forward gather
             if self._bwd_prep is None:
                 self._bwd_prep = ext.BackwardPrep(self._device)

@@ -216,10 +216,11 @@ def table_update_counter_n(counter, slot_indices, delta, table_bucket_offsets, b
 
 def train_prefetch(table_storage, table_bucket_offsets, bucket_capacity, bucket_sizes, ref_counter, bucket_heads, values, emb_dim, row_base,
                    keys, table_range, num_tables, policy, table_scores, timestamp, init_mode, init_params, seed, state_init,
-                   freq_in=None, num_scores=1, table_init=None):
+                   freq_in=None, num_scores=1, table_init=None, n_dev=None, unique_scratch=None):
     """Fused dedup + probe + insert/init + pin (demb_train.cu).  Returns (unique_keys[n], reverse[n], unique_table_ids[n], slots[n],
     rows[n], num_unique[1] device) — only the first num_unique entries of the per-unique outputs are meaningful.
-    table_init: device tensor from `make_table_init` (one initializer per table), overrides (init_mode, init_params, seed)."""
+    table_init: device tensor from `make_table_init` (one initializer per table), overrides (init_mode, init_params, seed).
+    n_dev: device int64 scalar with the real id count (<= keys.numel()).  unique_scratch: persistent dedup scratch (`unique_scratch`)."""
     n = keys.numel()
     dev = keys.device
     uk = torch.empty(n, dtype=keys.dtype, device=dev)
@@ -233,10 +234,10 @@ def train_prefetch(table_storage, table_bucket_offsets, bucket_capacity, bucket_
     p0, p1, p2, p3 = init_params
     N.check(N.launch("train_prefetch", 6, N.lib.demb_train_prefetch, N.ptr(table_storage), N.ptr(table_bucket_offsets), bucket_capacity, num_scores,
                      N.ptr(bucket_sizes), N.ptr(ref_counter), N.ptr(bucket_heads), N.ptr(values), values.stride(0), emb_dim, N.ptr(row_base), n,
-                     N.ptr(keys.contiguous()), N.ptr(table_range), num_tables, N.ptr(_i64(freq_in)), int(policy), N.ptr(table_scores), int(timestamp),
+                     N.ptr(n_dev), N.ptr(keys.contiguous()), N.ptr(table_range), num_tables, N.ptr(_i64(freq_in)), int(policy), N.ptr(table_scores), int(timestamp),
                      1 if keys.dtype == torch.int64 else 0, int(init_mode), float(p0), float(p1), float(p2), float(p3), int(seed), N.ptr(table_init),
-                     float(state_init), N.ptr(uk), N.ptr(rev), N.ptr(utids), N.ptr(ufreq), N.ptr(slots), N.ptr(rows), N.ptr(nu), N.ptr(ws), ws.numel(), N.stream()),
-            "train_prefetch")
+                     float(state_init), N.ptr(uk), N.ptr(rev), N.ptr(utids), N.ptr(ufreq), N.ptr(slots), N.ptr(rows), N.ptr(nu), N.ptr(unique_scratch),
+                     N.ptr(ws), ws.numel(), N.stream()), "train_prefetch")
     return uk, rev, utids, slots, rows, nu
 
 
@@ -254,8 +255,16 @@ def get_table_range(offsets: torch.Tensor, feature_offsets: torch.Tensor, num_fe
     return out
 
 
+def unique_scratch(n_max: int, num_tables: int, device) -> torch.Tensor:
+    """Persistent dedup scratch for segmented_unique_cuda / train_prefetch calls of up to n_max ids: initialised once here, left clean by
+    every call, so the per-call 32 MB initialisation disappears.  Must not be used for anything else."""
+    t = torch.empty(N.lib.demb_unique_scratch_bytes(n_max, num_tables), dtype=torch.uint8, device=device)
+    N.check(N.lib.demb_unique_scratch_init(N.ptr(t), t.numel(), N.stream()), "unique_scratch_init")
+    return t
+
+
 def segmented_unique_cuda(keys: torch.Tensor, segment_range: Optional[torch.Tensor], num_tables: int,
-                          input_frequencies: Optional[torch.Tensor] = None, want_table_ids: bool = False):
+                          input_frequencies: Optional[torch.Tensor] = None, want_table_ids: bool = False, n_dev=None, scratch=None):
     """unique_op.cu:484.  Returns (num_uniques[1] device, unique_keys[n], reverse_indices[n], table_offsets[T+1], freq[n] or None
     [, unique_table_ids[n]]).  Unique order = first occurrence (deterministic)."""
     n = keys.numel()
@@ -270,9 +279,10 @@ def segmented_unique_cuda(keys: torch.Tensor, segment_range: Optional[torch.Tens
     utids = torch.empty(n, dtype=torch.int64, device=dev) if want_table_ids else None
     ws_bytes = N.lib.demb_segmented_unique_workspace_bytes(n, num_tables)
     ws = N.workspace(ws_bytes, dev)
-    N.check(N.launch("segmented_unique", 4, N.lib.demb_segmented_unique, n, N.ptr(keys.contiguous()), N.ptr(_i64(segment_range)) if num_tables > 1 else None, num_tables,
-                                        N.ptr(_i64(freq_in)), N.ptr(unique_keys), N.ptr(reverse), N.ptr(table_offsets), N.ptr(freq_out),
-                                        N.ptr(utids), N.ptr(num_unique), N.ptr(ws), ws.numel(), N.stream()), "segmented_unique")
+    N.check(N.launch("segmented_unique", 3, N.lib.demb_segmented_unique, n, N.ptr(n_dev), N.ptr(keys.contiguous()),
+                     N.ptr(_i64(segment_range)) if num_tables > 1 else None, num_tables, N.ptr(_i64(freq_in)), N.ptr(unique_keys), N.ptr(reverse),
+                     N.ptr(table_offsets), N.ptr(freq_out), N.ptr(utids), N.ptr(num_unique), N.ptr(scratch), N.ptr(ws), ws.numel(), N.stream()),
+            "segmented_unique")
     if want_table_ids:
         return num_unique, unique_keys, reverse, table_offsets, freq_out, utids
     return num_unique, unique_keys, reverse, table_offsets, freq_out
@@ -307,14 +317,16 @@ def lookup_forward(table_storage, table_bucket_offsets, bucket_capacity, values,
     return (out, founds, slots) if want_founds else out
 
 
-def gather_forward(values, emb_dim, rows, inverse, n, *, offsets=None, batch_size=0, num_features=0, combiner=-1, out_dtype=torch.float32):
+def gather_forward(values, emb_dim, rows, inverse, n, *, offsets=None, batch_size=0, num_features=0, combiner=-1, out_dtype=torch.float32, n_dev=None,
+                   out=None):
     dev = values.device
-    if combiner < 0:
-        out = torch.empty(n, emb_dim, dtype=out_dtype, device=dev)
-    else:
-        out = torch.empty(batch_size, num_features * emb_dim, dtype=out_dtype, device=dev)
+    if out is None:
+        if combiner < 0:
+            out = torch.empty(n, emb_dim, dtype=out_dtype, device=dev)
+        else:
+            out = torch.empty(batch_size, num_features * emb_dim, dtype=out_dtype, device=dev)
     N.check(N.launch("gather_forward", 1, N.lib.demb_gather_forward, N.ptr(values), values.stride(0), emb_dim, n, N.ptr(rows), N.ptr(inverse), N.ptr(_i64(offsets)),
-                                      batch_size, num_features, combiner, N.ptr(out), _OUT_DTYPE[out_dtype], N.stream()), "gather_forward")
+                                      batch_size, num_features, combiner, N.ptr(out), _OUT_DTYPE[out.dtype], N.ptr(n_dev), N.stream()), "gather_forward")
     return out
 
 
@@ -364,7 +376,7 @@ class PreparedBackward:
         self.ws, self.done = ws, done
 
 
-def backward_prepare(prep: BackwardPrep, emb_dim: int, inverse: torch.Tensor, num_unique_bound: int) -> Optional[PreparedBackward]:
+def backward_prepare(prep: BackwardPrep, emb_dim: int, inverse: torch.Tensor, num_unique_bound: int, n_dev=None, grad_row_of=None) -> Optional[PreparedBackward]:
     """Sequence mode: launch the gradient-independent half of `backward` (pair list + radix sort by unique index) NOW, on the prep
     object's stream, behind everything already enqueued on the current stream.  Returns what backward(..., prepared=) needs.
     A PreparedBackward that is dropped without a backward is safe: its tensors were recorded on the side stream, so the allocator
@@ -377,7 +389,7 @@ def backward_prepare(prep: BackwardPrep, emb_dim: int, inverse: torch.Tensor, nu
     prep.stream.wait_stream(cur)
     with torch.cuda.stream(prep.stream):
         N.check(N.launch("backward_prepare", 2, N.lib.demb_backward_sort, emb_dim, n, N.ptr(inverse), int(num_unique_bound), None, 0, 0, -1,
-                         N.ptr(ws), ws.numel(), N.stream()), "backward_sort")
+                         N.ptr(n_dev), N.ptr(grad_row_of), N.ptr(ws), ws.numel(), N.stream()), "backward_sort")
         done = torch.cuda.Event()
         done.record(prep.stream)
     ws.record_stream(prep.stream)
@@ -386,7 +398,8 @@ def backward_prepare(prep: BackwardPrep, emb_dim: int, inverse: torch.Tensor, nu
 
 
 def backward(values, emb_dim, inverse, num_unique_bound, rows, grads, *, offsets=None, batch_size=0, num_features=0, combiner=-1,
-             opt_type=0, lr=0.0, eps=1e-8, beta1=0.9, beta2=0.999, weight_decay=0.0, bc1=1.0, bc2=1.0, want_unique_grads=False, prepared=None):
+             opt_type=0, lr=0.0, eps=1e-8, beta1=0.9, beta2=0.999, weight_decay=0.0, bc1=1.0, bc2=1.0, want_unique_grads=False, prepared=None,
+             n_dev=None, grad_row_of=None, unique_grad_addr=None, grad_stride=None):
     """Fused reduce_grads + optimizer row update.  grads: [n, D] (sequence) or [B, F*D] (pooled).
     prepared = PreparedBackward from backward_prepare(same inverse / bound): only the gradient-dependent half runs here."""
     n = inverse.numel()
@@ -396,19 +409,20 @@ def backward(values, emb_dim, inverse, num_unique_bound, rows, grads, *, offsets
         return ug
     grads = grads.contiguous()
     vstride = values.stride(0) if values is not None else emb_dim
+    gstride = emb_dim if grad_stride is None else int(grad_stride)
     if prepared is not None:
         ws = prepared.ws
         torch.cuda.current_stream(dev).wait_event(prepared.done)
         N.check(N.launch("backward", 3, N.lib.demb_backward_apply, N.ptr(values), vstride, emb_dim, n, N.ptr(inverse), int(num_unique_bound),
-                         N.ptr(rows), N.ptr(grads), emb_dim, N.ptr(_i64(offsets)), batch_size, num_features, combiner, int(opt_type), lr, eps, beta1, beta2,
-                         weight_decay, bc1, bc2, N.ptr(ug), N.ptr(ws), ws.numel(), N.stream()), "backward")
+                         N.ptr(rows), N.ptr(grads), gstride, N.ptr(_i64(offsets)), batch_size, num_features, combiner, int(opt_type), lr, eps, beta1, beta2,
+                         weight_decay, bc1, bc2, N.ptr(ug), N.ptr(n_dev), N.ptr(unique_grad_addr), N.ptr(ws), ws.numel(), N.stream()), "backward")
         return ug
     ws_bytes = N.lib.demb_backward_workspace_bytes(n, emb_dim)
     ws = N.workspace(ws_bytes, dev)
     N.check(N.launch("backward", 3, N.lib.demb_backward, N.ptr(values), vstride, emb_dim, n, N.ptr(inverse),
-                                int(num_unique_bound), N.ptr(rows), N.ptr(grads), emb_dim, N.ptr(_i64(offsets)), batch_size, num_features,
-                                combiner, int(opt_type), lr, eps, beta1, beta2, weight_decay, bc1, bc2, N.ptr(ug), N.ptr(ws), ws.numel(),
-                                N.stream()), "backward")
+                                int(num_unique_bound), N.ptr(rows), N.ptr(grads), gstride, N.ptr(_i64(offsets)), batch_size, num_features,
+                                combiner, int(opt_type), lr, eps, beta1, beta2, weight_decay, bc1, bc2, N.ptr(ug), N.ptr(n_dev), N.ptr(grad_row_of),
+                                N.ptr(unique_grad_addr), N.ptr(ws), ws.numel(), N.stream()), "backward")
     return ug
 
 
@@ -423,7 +437,7 @@ def gather_embedding(unique_embs: torch.Tensor, output_embs: torch.Tensor, rever
     n = reverse_indices.numel()
     rows = torch.arange(unique_embs.shape[0], dtype=torch.int64, device=unique_embs.device)
     N.check(N.lib.demb_gather_forward(N.ptr(unique_embs), unique_embs.stride(0), unique_embs.shape[1], n, N.ptr(rows), N.ptr(reverse_indices),
-                                      None, 0, 0, -1, N.ptr(output_embs), _OUT_DTYPE[output_embs.dtype], N.stream()), "gather_embedding")
+                                      None, 0, 0, -1, N.ptr(output_embs), _OUT_DTYPE[output_embs.dtype], None, N.stream()), "gather_embedding")
 
 
 def gather_embedding_pooled(unique_embs, output_embs, reverse_indices, offsets, combiner, total_D, batch_size, D_offsets=None, max_D=0) -> None:
@@ -431,7 +445,7 @@ def gather_embedding_pooled(unique_embs, output_embs, reverse_indices, offsets, 
     F = total_D // D
     rows = torch.arange(unique_embs.shape[0], dtype=torch.int64, device=unique_embs.device)
     N.check(N.lib.demb_gather_forward(N.ptr(unique_embs), unique_embs.stride(0), D, reverse_indices.numel(), N.ptr(rows), N.ptr(reverse_indices),
-                                      N.ptr(_i64(offsets)), batch_size, F, combiner, N.ptr(output_embs), _OUT_DTYPE[output_embs.dtype],
+                                      N.ptr(_i64(offsets)), batch_size, F, combiner, N.ptr(output_embs), _OUT_DTYPE[output_embs.dtype], None,
                                       N.stream()), "gather_embedding_pooled")
 
 
@@ -439,6 +453,149 @@ def reduce_grads(reverse_indices, grads, num_unique, batch_size, out_dim, offset
     F = (total_D // out_dim) if offsets is not None else 0
     return backward(None, out_dim, reverse_indices, num_unique, None, grads, offsets=offsets, batch_size=batch_size if offsets is not None else 0,
                     num_features=F, combiner=combiner if offsets is not None else -1, want_unique_grads=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference-named ops over per-table base pointers (module_bind.cu: dynamic_emb_op.cu:839-876, optimizer.cu:416-447, initializer.cu:193-210,
+# index_calculation.cu:241, table_operation/table.cu:164) — same names, argument order and in-place conventions as the pybind module
+# ---------------------------------------------------------------------------------------------------
+def _flat_copy(table_ptrs, indices, table_ids, scalar_tid, dense, table_value_dims, table_emb_dims, max_emb_dim, region, to_table):
+    assert dense.dtype == torch.float32 and dense.stride(1) == 1, "fp32 rows (bf16/fp16 value rows are not built, DESIGN.md)"
+    N.check(N.lib.demb_flat_table_copy(N.ptr(_i64(table_ptrs)), N.ptr(_i64(table_ids)), int(scalar_tid), N.ptr(_i64(indices)), indices.numel(),
+                                       N.ptr(_i64(table_value_dims)), N.ptr(_i64(table_emb_dims)), int(max_emb_dim), N.ptr(dense), dense.stride(0),
+                                       dense.shape[1], region, 1 if to_table else 0, N.stream()), "flat_table_copy")
+
+
+def load_from_flat_table_contiguous(table_ptrs, indices, table_id, output, table_value_dims, table_emb_dims, max_emb_dim, all_dims_vec4=True) -> None:
+    _flat_copy(table_ptrs, indices, None, table_id, output, table_value_dims, table_emb_dims, max_emb_dim, 0, False)
+
+
+def load_from_flat_table_emb(table_ptrs, indices, table_ids, output, table_value_dims, table_emb_dims, max_emb_dim, all_dims_vec4=True) -> None:
+    _flat_copy(table_ptrs, indices, table_ids, 0, output, table_value_dims, table_emb_dims, max_emb_dim, 1, False)
+
+
+def load_from_flat_table_value(table_ptrs, indices, table_ids, output, table_value_dims, table_emb_dims, max_emb_dim, all_dims_vec4=True) -> None:
+    _flat_copy(table_ptrs, indices, table_ids, 0, output, table_value_dims, table_emb_dims, max_emb_dim, 2, False)
+
+
+def store_to_flat_table_contiguous(table_ptrs, indices, table_id, input, table_value_dims, table_emb_dims, max_emb_dim, all_dims_vec4=True) -> None:  # noqa: A002
+    _flat_copy(table_ptrs, indices, None, table_id, input, table_value_dims, table_emb_dims, max_emb_dim, 0, True)
+
+
+def store_to_flat_table_value(table_ptrs, indices, table_ids, input, table_value_dims, table_emb_dims, max_emb_dim, all_dims_vec4=True) -> None:  # noqa: A002
+    _flat_copy(table_ptrs, indices, table_ids, 0, input, table_value_dims, table_emb_dims, max_emb_dim, 2, True)
+
+
+def _flat_update(grads, indices, table_ptrs, table_ids, table_value_dims, table_emb_dims, max_emb_dim, opt_type, lr, eps=1e-8, beta1=0.9, beta2=0.999,
+                 weight_decay=0.0, bc1=1.0, bc2=1.0):
+    grads = grads.contiguous()
+    N.check(N.lib.demb_flat_table_update(N.ptr(_i64(table_ptrs)), N.ptr(_i64(table_ids)), N.ptr(_i64(indices)), indices.numel(), N.ptr(_i64(table_value_dims)),
+                                         N.ptr(_i64(table_emb_dims)), int(max_emb_dim), N.ptr(grads), grads.stride(0), int(opt_type), float(lr), float(eps),
+                                         float(beta1), float(beta2), float(weight_decay), float(bc1), float(bc2), N.stream()), "flat_table_update")
+
+
+def sgd_update_for_flat_table(grads, indices, table_ptrs, table_ids, table_value_dims, table_emb_dims, max_emb_dim, all_dims_vec4, lr, table_dtype=0) -> None:
+    _flat_update(grads, indices, table_ptrs, table_ids, table_value_dims, table_emb_dims, max_emb_dim, OptimizerType.SGD, lr)
+
+
+def adam_update_for_flat_table(grads, indices, table_ptrs, table_ids, table_value_dims, table_emb_dims, lr, beta1, beta2, eps, weight_decay, iter_num,
+                               max_emb_dim, all_dims_vec4, table_dtype=0) -> None:
+    it = max(int(iter_num), 1)
+    _flat_update(grads, indices, table_ptrs, table_ids, table_value_dims, table_emb_dims, max_emb_dim, OptimizerType.ADAM, lr, eps, beta1, beta2, weight_decay,
+                 1.0 - beta1 ** it, 1.0 - beta2 ** it)
+
+
+def adagrad_update_for_flat_table(grads, indices, table_ptrs, table_ids, table_value_dims, table_emb_dims, lr, eps, max_emb_dim, all_dims_vec4, table_dtype=0) -> None:
+    _flat_update(grads, indices, table_ptrs, table_ids, table_value_dims, table_emb_dims, max_emb_dim, OptimizerType.ADAGRAD, lr, eps)
+
+
+def rowwise_adagrad_for_flat_table(grads, indices, table_ptrs, table_ids, table_value_dims, table_emb_dims, lr, eps, max_emb_dim, all_dims_vec4, table_dtype=0) -> None:
+    _flat_update(grads, indices, table_ptrs, table_ids, table_value_dims, table_emb_dims, max_emb_dim, OptimizerType.ROWWISE_ADAGRAD, lr, eps)
+
+
+def flagged_compact(flags: torch.Tensor, inputs: List[Optional[torch.Tensor]]):
+    """index_calculation.cu:130.  Returns (count, indices[count], [compacted inputs or None]) like the reference (which reads the count
+    back: ONE host sync); `flagged_compact_device` keeps the count on the device."""
+    cnt, idx, outs = flagged_compact_device(flags, inputs)
+    c = int(cnt.item())
+    return c, idx[:c], [o[:c] if o is not None else None for o in outs]
+
+
+def flagged_compact_device(flags: torch.Tensor, inputs: List[Optional[torch.Tensor]]):
+    """(count[1] device, indices[n], outputs[n]...) — only the first count entries are meaningful; one launch, no host sync."""
+    assert flags.dtype == torch.bool, "flags must be bool"
+    n, dev = flags.numel(), flags.device
+    real = [t for t in inputs if t is not None]
+    assert len(real) <= 4 and all(t.dim() == 1 and t.element_size() == 8 and t.numel() == n for t in real), "up to 4 1-D 8-byte inputs of the flags' length"
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    idx = torch.empty(n, dtype=torch.int64, device=dev)
+    outs_real = [torch.empty_like(t) for t in real]
+    ins = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in real] + [None] * (4 - len(real)))
+    outs = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in outs_real] + [None] * (4 - len(real)))
+    ws = N.workspace(N.lib.demb_flagged_compact_workspace_bytes(n), dev)
+    N.check(N.launch("flagged_compact", 2, N.lib.demb_flagged_compact, n, N.ptr(flags), N.ptr(cnt), N.ptr(idx), ctypes.cast(ins, ctypes.c_void_p),
+                     ctypes.cast(outs, ctypes.c_void_p), len(real), N.ptr(ws), ws.numel(), N.stream()), "flagged_compact")
+    it = iter(outs_real)
+    return cnt, idx, [next(it) if t is not None else None for t in inputs]
+
+
+def bucketize_keys(keys: torch.Tensor, table_ids: torch.Tensor, table_bucket_offsets: torch.Tensor, num_buckets: int, bucket_capacity: int):
+    """table_operation/bucketize.cu:111: keys ordered by (global bucket, key), offsets[active buckets + 1] into that order, inverse (sorted
+    position -> input position).  Only the reference's DEMB_DETERMINISM_MODE helper calls it; our insert is deterministic by construction."""
+    n, dev = keys.numel(), keys.device
+    if n == 0:
+        z = torch.empty(0, dtype=torch.int64, device=dev)
+        return z, z.clone(), z.clone()
+    bkt = torch.empty(n, dtype=torch.int64, device=dev)
+    N.check(N.lib.demb_bucket_of(N.ptr(table_bucket_offsets), int(bucket_capacity), n, N.ptr(keys.contiguous()), N.ptr(_i64(table_ids)), N.ptr(bkt), N.stream()),
+            "bucket_of")
+    k_order = torch.sort(keys.view(torch.int64) if keys.dtype == torch.uint64 else keys, stable=True).indices     # signed order for int64 keys
+    b_sorted, order2 = torch.sort(bkt[k_order], stable=True)
+    inverse = k_order[order2]
+    ends = torch.nonzero(torch.cat([b_sorted[1:] != b_sorted[:-1], torch.ones(1, dtype=torch.bool, device=dev)])).flatten() + 1
+    offsets = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), ends])
+    return keys[inverse], offsets, inverse
+
+
+class CurandStateContext:
+    """initializer.cu:26-112 keeps a pool of curand states; our initializers are counter-based (Philox keyed by seed, key, column), so the
+    context only carries the seed."""
+
+    def __init__(self, seed: int = 0):
+        self.seed = seed
+
+    def ptr(self):
+        return self
+
+
+def _init_op(buffer, indices, mode, p, seed=0, keys=None):
+    """buffer[indices[i], :] = initializer(...) for indices >= 0 (initializer.cu:114-190).  The random stream is keyed by `keys` when given,
+    else by the row index."""
+    assert buffer.dim() == 2 and buffer.is_contiguous() and buffer.dtype == torch.float32, "dense fp32 [n, dim] buffer"
+    idx = _i64(indices)
+    k = keys if keys is not None else idx
+    N.check(N.launch("init_rows", 1, N.lib.demb_init_rows, N.ptr(buffer), buffer.stride(0), buffer.shape[1], idx.numel(), N.ptr(idx), N.ptr(k.contiguous()),
+                     int(mode), float(p[0]), float(p[1]), float(p[2]), float(p[3]), int(seed), None, None, 0.0, None, None, N.stream()), "init_op")
+
+
+def normal_init(buffer, indices, curand_state_context, mean, std_dev) -> None:
+    _init_op(buffer, indices, InitializerMode.NORMAL, (mean, std_dev, 0.0, 0.0), getattr(curand_state_context, "seed", 0))
+
+
+def truncated_normal_init(buffer, indices, curand_state_context, mean, std_dev, lower, upper) -> None:
+    _init_op(buffer, indices, InitializerMode.TRUNCATED_NORMAL, (mean, std_dev, lower, upper), getattr(curand_state_context, "seed", 0))
+
+
+def uniform_init(buffer, indices, curand_state_context, lower, upper) -> None:
+    _init_op(buffer, indices, InitializerMode.UNIFORM, (lower, upper, 0.0, 0.0), getattr(curand_state_context, "seed", 0))
+
+
+def const_init(buffer, indices, value) -> None:
+    _init_op(buffer, indices, InitializerMode.CONSTANT, (value, 0.0, 0.0, 0.0))
+
+
+def debug_init(buffer, indices, keys) -> None:
+    _init_op(buffer, indices, InitializerMode.DEBUG, (0.0, 0.0, 0.0, 0.0), keys=keys)
 
 
 # ---------------------------------------------------------------------------------------------------

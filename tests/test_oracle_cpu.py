@@ -178,3 +178,41 @@ def test_oracle_table_random_op_sequences():
                     assert s == now[int(k)]
 
     run()
+
+
+def test_ctypes_call_sites_match_the_declared_signatures():
+    """Every call of a C-ABI entry point in the host package passes exactly as many arguments as its ctypes signature (and the header)
+    declare — a mismatch only shows up on a GPU box otherwise."""
+    from dynamicemb import _native as N
+    pkg = os.path.join(ROOT, "recsys-examples_b200")
+    src = "".join(open(os.path.join(pkg, "dynamicemb", f)).read() for f in ("dynamicemb_extensions.py", "shard.py", "batched_dynamicemb_tables.py"))
+
+    def count_args(s, start):
+        depth, n, i = 0, 1, start
+        while True:
+            c = s[i]
+            if c in "([{":
+                depth += 1
+            elif c in ")]}":
+                if depth == 0:
+                    return n
+                depth -= 1
+            elif c == "," and depth == 0:
+                n += 1
+            i += 1
+
+    seen = 0
+    for pat in (r"N\.lib\.(demb_\w+)\(", r"N\.launch\(\"[\w_]+\", \d+, N\.lib\.(demb_\w+), "):
+        for m in re.finditer(pat, src):
+            name = m.group(1)
+            assert count_args(src, m.end()) == len(N._SIGS[name][1]), f"call of {name} does not match its ctypes signature"
+            seen += 1
+    assert seen >= 30
+    # and the header agrees with the ctypes table on the parameter count
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "dynamicemb_b200.h")).read(), flags=re.S)
+    for name, (_, args) in N._SIGS.items():
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", hdr, flags=re.S)
+        assert m, f"{name} not declared in include/dynamicemb_b200.h"
+        params = m.group(1).strip()
+        n_decl = 0 if params in ("", "void") else params.count(",") + 1
+        assert n_decl == len(args), f"{name}: header declares {n_decl} parameters, ctypes table {len(args)}"
