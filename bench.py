@@ -412,6 +412,7 @@ def main():
     ap.add_argument("--no-hstu", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the no-eviction variant / cfg-5 sweep")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the SURVEY cfg-4 end-to-end harness (HSTU-large + DynamicEmb, ours and reference kernels)")
     ap.add_argument("--ncu", action="store_true", help="wrap 2 eager steps + 1 eval lookup in cudaProfilerStart/Stop (ncu --profile-from-start off) and exit")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -643,11 +644,44 @@ def main():
                 a.record(); m(batches[-1 - i], offsets); b.record()
                 torch.cuda.synchronize()
                 ev.append(a.elapsed_time(b))
+            # the pooled (EmbeddingBagCollection) form of the same lookup: 2 features x 52428 bags x hotness 10, SUM, fused probe + pool
+            from dynamicemb import dynamicemb_extensions as ext
+            Fp, Bp = 2, n_ids // 20
+            np_ids = Fp * Bp * 10
+            poff = torch.arange(0, np_ids + 1, 10, dtype=torch.int64, device=dev)
+            tb = m.tables
+            pool_call = lambda k: ext.lookup_forward(tb.table_storage_, tb.table_bucket_offsets_, tb.bucket_capacity_, m._values, D, batches[-1 - k][:np_ids],
+                                                     row_base=tb.row_base_, offsets=poff, batch_size=Bp, num_features=Fp, combiner=0, num_scores=tb.num_scores_)
+            pev = []
+            for i in range(7):
+                a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+                a.record(); pool_call(i); b.record()
+                torch.cuda.synchronize()
+                pev.append(a.elapsed_time(b))
+            pms = sorted(pev)[len(pev) // 2]
+            nu_p = int(torch.unique(batches[-1][:np_ids]).numel())
+            b_pool = np_ids * 8 + nu_p * (24 + 512) + Fp * Bp * 512
+            roof["pooled_lookup_forward"] = {"kernel": "forward_pool_kernel (fused probe + SUM pooling, hotness 10)", "ms": pms, "algorithmic_bytes": b_pool,
+                                             "achieved_GBps": b_pool / pms / 1e6, "frac": b_pool / pms / 1e6 / hbm, "ids": np_ids, "bags": Fp * Bp}
+            # A/B of the three fused-lookup kernels on the same batches (option 0 of demb_set_option; 1 is the shipped default)
+            variants = {}
+            for opt_v, nm in ((0, "round-1 thread-per-key probe (forward_seq_tma_kernel)"), (2, "specialised probe / copy warps (forward_seq_probe2_kernel)"),
+                              (1, "one probe+copy pipeline per warp (forward_seq_probe_kernel, default)")):
+                N.lib.demb_set_option(0, opt_v)
+                tv = []
+                for i in range(7):
+                    a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+                    a.record(); m(batches[-1 - i], offsets); b.record()
+                    torch.cuda.synchronize()
+                    tv.append(a.elapsed_time(b))
+                variants[nm] = sorted(tv)[len(tv) // 2]
+            N.lib.demb_set_option(0, 1)
+            roof["fused_lookup_kernel_variants_ms"] = variants
             m.train()
             fms = sorted(ev)[len(ev) // 2]
-            roof.update({"kernel": "forward_seq_tma_kernel, probe mode (demb_lookup_forward: fused hash probe + row gather, the 128-d lookup path)",
+            roof.update({"kernel": "forward_seq_probe_kernel (demb_lookup_forward: fused hash probe + row gather, the 128-d lookup path)",
                          "achieved": b_fwd / fms / 1e6, "frac": b_fwd / fms / 1e6 / hbm, "ms_per_launch": fms, "algorithmic_bytes_per_launch": b_fwd,
-                         "traffic": traffic.get("forward_seq_tma_kernel_probe"), "lookups_per_s": n_ids / fms * 1e3})
+                         "traffic": traffic.get("forward_seq_probe_kernel"), "lookups_per_s": n_ids / fms * 1e3})
             tf_ms = prof.get("train_prefetch", 0.0) + prof.get("gather_forward", 0.0)
             roof["train_forward"] = {"kernels": "demb_train_prefetch (unique, probe, insert/evict, row init) + forward_seq_tma_kernel (gather)",
                                      "ms": tf_ms, "prefetch_ms": prof.get("train_prefetch"), "gather_ms": prof.get("gather_forward"),
@@ -736,6 +770,23 @@ def main():
             extra["cfg5_batch_sweep_keyspace1e10"] = sweep
         except Exception as e:  # noqa: BLE001
             extra["cfg5_batch_sweep_keyspace1e10"] = {"error": repr(e)[:300], "partial": sweep}
+
+    # ---- SURVEY cfg 4: HSTU-large + DynamicEmb end-to-end step, our kernels and the reference's own GPU kernels in the same harness
+    # (tools/e2e_harness.py); every rank takes part (the embedding is row-wise sharded at N > 1)
+    if not args.no_e2e:
+        try:
+            graphed = graphed_noloss = None
+            if model is not None and getattr(model, "_buf", None) is not None:
+                torch.cuda.synchronize()
+                dist.barrier()
+                model._buf.close()
+            model = m = None
+            batches = host_batches = eager_batches = None
+            torch.cuda.empty_cache()
+            from tools import e2e_harness
+            extra["cfg4_e2e_hstu_large"] = e2e_harness.run_both(dev, world, rank)
+        except Exception as e:  # noqa: BLE001
+            extra["cfg4_e2e_hstu_large"] = {"error": repr(e)[:300]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -9,7 +9,6 @@
 // 512-B row straight from the value table into the output (or the bag accumulator) with 16-B
 // no-allocate loads / streaming stores, 8 rows in flight per warp.  Backward sorts (unique idx, grad
 // row) pairs once, then fixed 32-row tiles reduce and apply the optimizer in place in the same kernel.
-#include <cub/device/device_radix_sort.cuh>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -18,6 +17,7 @@
 #include "demb_init.cuh"
 #include "sm100_ptx.cuh"
 #include "demb_probe.cuh"
+#include "demb_sort.cuh"
 
 using namespace demb;
 
@@ -247,6 +247,97 @@ __global__ void __launch_bounds__(kProbeFwdWarps * 32) forward_seq_probe_kernel(
   if (lane == 0) sm100::bulk_wait0();                             // shared memory must outlive the last bulk store
 }
 
+// ---- the same fused lookup with SPECIALISED warps: 8 probe warps resolve row ids and hand them through a shared-memory ring to 12 copy
+// warps that run exactly the loop of the indirect gather kernel (bulk row copies into the warp's stage, one bulk store per tile).  The
+// copy warps never wait on a probe: their iteration is the gather kernel's, so the kernel's throughput is the gather's as long as the
+// probe warps keep up (one tile per ~5 us per warp).  Tiles of a CTA are numbered i = 0, 1, ...; tile i is probed by warp 12 + i % 8 and
+// copied by warp i % 12; ring slot i % 24 therefore always has the same producer and the same consumer.
+constexpr int kCopyWarps = 12, kProbeWarps = 8, kRing = 24;
+struct Probe2Smem { uint64_t bar_row[kCopyWarps]; uint64_t full[kRing]; uint64_t empty[kRing]; int slot[kProbeWarps][32]; int64_t rowq[kRing][32]; };
+__global__ void __launch_bounds__((kCopyWarps + kProbeWarps) * 32, 1) forward_seq_probe2_kernel(RowSrc s, const float* __restrict__ values, int64_t vdim, int D,
+                                                                                              int64_t n, float* __restrict__ out, float absent_value) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ Probe2Smem sm;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t row_bytes = (uint32_t)D * 4u;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kCopyWarps; ++i) sm100::mbar_init(&sm.bar_row[i], 1);
+    for (int i = 0; i < kRing; ++i) { sm100::mbar_init(&sm.full[i], 1); sm100::mbar_init(&sm.empty[i], 1); }
+    sm100::fence_barrier_init();
+  }
+  __syncthreads();
+  const int64_t tiles = (n + 31) >> 5;
+  const int64_t my_tiles = tiles > (int64_t)blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // tiles blockIdx.x + i * gridDim.x
+  if (wib >= kCopyWarps) {
+    // ------------------------------------------------------------------ probe warps (producers): two warpgroups, take the registers the
+    // copy warpgroups give up (12 x 32 x 64 + 8 x 32 x 136 = 59392 <= 65536)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+    const int p = wib - kCopyWarps;
+    auto load_key = [&](int64_t i) -> ProbeKey {
+      const int64_t tl = (int64_t)blockIdx.x + i * gridDim.x;
+      const int64_t id = (tl << 5) + lane;
+      if (i >= my_tiles || id >= n) return ProbeKey{0, 0, 0, 0, false};
+      const int tid = (s.T > 1 && s.table_range) ? table_of(s.table_range, s.T, id) : 0;
+      return make_probe_key(s.t, s.keys[id], tid);
+    };
+    ProbeKey k0 = load_key(p);
+    DigRegs d0, d1;
+    tile_load_digests(s.t, k0, d0, lane);
+    for (int64_t i = p; i < my_tiles; i += kProbeWarps) {
+      const ProbeKey k1 = load_key(i + kProbeWarps);
+      tile_load_digests(s.t, k1, d1, lane);
+      const int pos = tile_probe(s.t, k0, d0, sm.slot[p], lane);
+      const int64_t id = ((((int64_t)blockIdx.x + i * gridDim.x)) << 5) + lane;
+      const int64_t slot = pos >= 0 ? k0.slot_base + pos : -1;
+      if (id < n) { if (s.founds) s.founds[id] = slot >= 0; if (s.slots_out) s.slots_out[id] = slot; }
+      const int64_t row = slot < 0 ? -1 : (s.row_base ? s.row_base[k0.tid] : 0) + slot;
+      const int q = (int)(i % kRing);
+      const uint32_t use = (uint32_t)(i / kRing);                 // how many times this slot has been used before
+      if (use > 0) sm100::mbar_wait(&sm.empty[q], (use - 1) & 1u);
+      sm.rowq[q][lane] = row;
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(&sm.full[q]);
+      k0 = k1; d0 = d1;
+    }
+    return;
+  }
+  // -------------------------------------------------------------------- copy warps (consumers): the gather kernel's loop
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+  uint8_t* buf = smem_raw + (size_t)wib * 32u * row_bytes;
+  uint32_t par_row = 0;
+  for (int64_t i = wib; i < my_tiles; i += kCopyWarps) {
+    const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
+    const int64_t base = tile << 5;
+    const int cnt = (int)((n - base) < 32 ? (n - base) : 32);
+    const int q = (int)(i % kRing);
+    sm100::mbar_wait(&sm.full[q], (uint32_t)(i / kRing) & 1u);
+    const int64_t row = lane < cnt ? sm.rowq[q][lane] : -1;
+    __syncwarp();
+    if (lane == 0) sm100::mbar_arrive(&sm.empty[q]);
+    const unsigned found = __ballot_sync(0xffffffffu, row >= 0);
+    if (lane == 0) {
+      sm100::bulk_wait_read0();
+      sm100::mbar_arrive_expect_tx(&sm.bar_row[wib], (uint32_t)__popc(found) * row_bytes);
+    }
+    __syncwarp();
+    if (row >= 0) {
+      sm100::bulk_load(buf + (size_t)lane * row_bytes, values + row * vdim, row_bytes, &sm.bar_row[wib]);
+    } else if (lane < cnt) {
+      float4* d = reinterpret_cast<float4*>(buf + (size_t)lane * row_bytes);
+      for (int c = 0; c < (D >> 2); ++c) d[c] = make_float4(absent_value, absent_value, absent_value, absent_value);
+    }
+    sm100::mbar_wait(&sm.bar_row[wib], par_row);
+    par_row ^= 1;
+    sm100::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      sm100::bulk_store(out + base * (int64_t)D, buf, (uint32_t)cnt * row_bytes);
+      sm100::bulk_commit();
+    }
+  }
+  if (lane == 0) sm100::bulk_wait0();
+}
+
 // ---- forward, pooled mode: ids feature-major (offsets index f*B+b, lookup_forward.cu:53-59);
 // out[b, f*D : (f+1)*D] = SUM or MEAN of the bag's rows, fp32 accumulation in id order (lookup_kernel.cuh:901-962).
 // A13 + A11 + A4 fused.  A warp takes `bpw` consecutive bags per pass (bpw ~ 32 / average bag length, chosen by the host):
@@ -257,6 +348,7 @@ template <int NCHUNK>
 __global__ void __launch_bounds__(kBlock) forward_pool_kernel(RowSrc s, const float* __restrict__ values, int64_t vdim, int D, int64_t B, int F,
                                                               const int64_t* __restrict__ offsets, int combiner, void* __restrict__ out,
                                                               int out_dtype, int64_t total_D, int bpw, float absent_value) {
+  __shared__ int pool_slot_sm[kWarpsPerBlock][32];
   const int lane = threadIdx.x & 31;
   const int D4 = D >> 2;
   const int64_t bags = B * (int64_t)F;
@@ -294,7 +386,19 @@ __global__ void __launch_bounds__(kBlock) forward_pool_kernel(RowSrc s, const fl
     for (int64_t base = beg; base < end; base += 32) {
       const int cnt = (int)((end - base) < 32 ? (end - base) : 32);
       int64_t row = -1;
-      if (lane < cnt) row = resolve_row(s, base + lane);
+      if (!s.rows && s.t.C == kProbeC) {
+        // probe mode, 128-slot buckets: the warp-tile probe (coalesced digest lines, all candidate keys in flight together)
+        ProbeKey pk{0, 0, 0, 0, false};
+        if (lane < cnt) pk = make_probe_key(s.t, s.keys[base + lane], (s.T > 1 && s.table_range) ? table_of(s.table_range, s.T, base + lane) : 0);
+        DigRegs dg;
+        tile_load_digests(s.t, pk, dg, lane);
+        const int pos = tile_probe(s.t, pk, dg, pool_slot_sm[threadIdx.x >> 5], lane);
+        const int64_t slot = pos >= 0 ? pk.slot_base + pos : -1;
+        if (lane < cnt) { if (s.founds) s.founds[base + lane] = slot >= 0; if (s.slots_out) s.slots_out[base + lane] = slot; }
+        row = slot < 0 ? -1 : (s.row_base ? s.row_base[pk.tid] : 0) + slot;
+      } else if (lane < cnt) {
+        row = resolve_row(s, base + lane);
+      }
       constexpr int U = 8;
       for (int j = 0; j < cnt; j += U) {
         int64_t r[U];
@@ -560,6 +664,96 @@ __global__ void __launch_bounds__(kBlock) backward_tiles_kernel(BwdArgs a) {
   }
 }
 
+// The same stage 1 with the 32 gradient rows of a tile STAGED THROUGH SHARED MEMORY by bulk async copies (one cp.async.bulk per row,
+// mbarrier-tracked): the register version keeps 4 rows (2 KB) in flight per warp; here every warp has its whole tile (16 KB for D=128)
+// in flight, 12 warps per SM — the pipeline that took the forward gather from 0.55 to 0.79 of the HBM roofline.  Arithmetic and its order
+// are unchanged (rows are added in sorted order from the stage), so results are bit-identical to backward_tiles_kernel.
+constexpr int kBwdTmaWarps = 12;
+template <int NCHUNK>
+__global__ void __launch_bounds__(kBwdTmaWarps * 32, 1) backward_tiles_tma_kernel(BwdArgs a, int warps_per_block) {
+  extern __shared__ __align__(128) uint8_t stage_raw[];
+  __shared__ uint64_t bars[kBwdTmaWarps];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  if (wib >= warps_per_block) return;
+  const int D4 = a.D >> 2;
+  const uint32_t row_bytes = (uint32_t)a.D * 4u;
+  const float* stage = reinterpret_cast<const float*>(stage_raw + (size_t)wib * 32u * row_bytes);
+  if (lane == 0) { sm100::mbar_init(&bars[wib], 1); sm100::fence_barrier_init(); }
+  __syncwarp();
+  uint32_t parity = 0;
+  const int64_t n_act = bwd_n(a);
+  const int64_t tiles = (n_act + 31) >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * warps_per_block;
+  for (int64_t tile = (int64_t)blockIdx.x * warps_per_block + wib; tile < tiles; tile += wstride) {
+    const int64_t base = tile << 5;
+    const int cnt = (int)((n_act - base) < 32 ? (n_act - base) : 32);
+    int32_t myu = -1, myr = 0; float mys = 1.f;
+    if (lane < cnt) {
+      myu = a.skey[base + lane]; myr = a.sval[base + lane];
+      if (a.pooled && a.combiner == 1) {
+        int64_t b = myr / a.F, f = myr - b * a.F;
+        int64_t len = a.offsets[f * a.B + b + 1] - a.offsets[f * a.B + b];
+        mys = 1.0f / (float)len;                                   // lookup_backward.cu:209-241
+      }
+    }
+    // gradient rows of the tile -> shared memory (all 32 copies in flight at once)
+    if (lane == 0) sm100::mbar_arrive_expect_tx(&bars[wib], (uint32_t)cnt * row_bytes);
+    __syncwarp();
+    if (lane < cnt) sm100::bulk_load(const_cast<float*>(stage) + (size_t)lane * a.D, a.grads + (int64_t)myr * a.grad_stride, row_bytes, &bars[wib]);
+    // value rows (embedding + optimizer state) of the segments that END in this tile: pull them into L2 now
+    int64_t myrow = -1;
+    if (lane < cnt && a.rows && a.opt.type != DEMB_OPT_NONE) {
+      myrow = a.rows[myu];
+      const int32_t up = __shfl_up_sync(__activemask(), myu, 1);
+      if (myrow >= 0 && (lane == 0 || up != myu)) {
+        const char* pr = reinterpret_cast<const char*>(a.values + myrow * a.vdim);
+        for (int64_t b = 0; b < a.vdim * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + b));
+      }
+    }
+    const int32_t prev_u = base > 0 ? a.skey[base - 1] : -1;
+    const int32_t next_u = base + 32 < n_act ? a.skey[base + 32] : -2;
+    float4 acc[NCHUNK];
+#pragma unroll
+    for (int k = 0; k < NCHUNK; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool incoming = (__shfl_sync(0xffffffffu, myu, 0) == prev_u);
+    sm100::mbar_wait(&bars[wib], parity);
+    parity ^= 1;
+    for (int j = 0; j < cnt; ++j) {
+      const int32_t uj = __shfl_sync(0xffffffffu, myu, j);
+      const int32_t un = __shfl_sync(0xffffffffu, myu, (j + 1) & 31);
+      const float sc = __shfl_sync(0xffffffffu, mys, j);
+      const int64_t vr = __shfl_sync(0xffffffffu, myrow, j);
+#pragma unroll
+      for (int k = 0; k < NCHUNK; ++k) {
+        const int c = lane + 32 * k;
+        if (c < D4) {
+          const float4 v = *reinterpret_cast<const float4*>(stage + (size_t)j * a.D + 4 * c);
+          acc[k].x = __fadd_rn(acc[k].x, __fmul_rn(v.x, sc)); acc[k].y = __fadd_rn(acc[k].y, __fmul_rn(v.y, sc));
+          acc[k].z = __fadd_rn(acc[k].z, __fmul_rn(v.z, sc)); acc[k].w = __fadd_rn(acc[k].w, __fmul_rn(v.w, sc));
+        }
+      }
+      const bool last_in_tile = (j == cnt - 1);
+      const int32_t nxt = last_in_tile ? next_u : un;
+      if (nxt != uj) {                          // segment ends at this row
+        if (incoming) {
+#pragma unroll
+          for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; if (c < D4) st_f4(a.part_cont + tile * a.D + 4 * c, acc[k]); }
+        } else {
+          finish_segment<NCHUNK, true>(a, uj, acc, lane, vr);
+        }
+#pragma unroll
+        for (int k = 0; k < NCHUNK; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        incoming = false;
+      } else if (last_in_tile) {                // runs past the tile end
+        float* dst = incoming ? a.part_cont : a.part_start;
+#pragma unroll
+        for (int k = 0; k < NCHUNK; ++k) { int c = lane + 32 * k; if (c < D4) st_f4(dst + tile * a.D + 4 * c, acc[k]); }
+      }
+    }
+    __syncwarp();                               // every lane is done reading the stage before the next tile's copies land in it
+  }
+}
+
 // Ordered sum of `count` consecutive [D]-float partial rows starting at `src` into acc: loads 8 deep, adds in order.
 template <int NCHUNK>
 __device__ __forceinline__ void add_partials(float4 (&acc)[NCHUNK], const float* __restrict__ src, int count, int D, int lane) {
@@ -740,7 +934,8 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 inline int nchunk_of(int D) { return (D / 4 + 31) / 32; }
 
 // bench.py's roofline needs per-kernel device time of the multi-kernel backward: optional CUDA events around its stages.
-bool g_probe_kernel = true;     // demb_set_option(0, ...): 0 = the round-1 thread-per-key probe inside forward_seq_tma_kernel (A/B measurements)
+bool g_bwd_tma = true;          // demb_set_option(1, v): gradient rows of the backward staged through shared memory (1, default) or registers (0)
+int g_probe_kernel = 1;         // demb_set_option(0, v): 1 = one probe + copy pipeline per warp (default), 2 = specialised probe / copy warps (measured slower), 0 = round-1 thread-per-key probe
 bool g_prof_on = false;
 cudaEvent_t g_prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
@@ -797,6 +992,19 @@ static int launch_seq_probe(const RowSrc& s, const float* values, int64_t value_
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }
+static int launch_seq_probe2(const RowSrc& s, const float* values, int64_t value_dim, int emb_dim, int64_t n, float* out, float absent_value,
+                             cudaStream_t stream) {
+  const int smem = kCopyWarps * 32 * emb_dim * 4;
+  static std::atomic<int> configured[kMaxDevices];
+  cudaError_t ce = once_per_device(configured, [] { return cudaFuncSetAttribute(forward_seq_probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+  if (ce != cudaSuccess) return -(int)ce;
+  const int64_t tiles = (n + 31) / 32;
+  int64_t blocks = (tiles + kCopyWarps - 1) / kCopyWarps;
+  if (blocks > sm_count()) blocks = sm_count();
+  forward_seq_probe2_kernel<<<(int)blocks, (kCopyWarps + kProbeWarps) * 32, smem, stream>>>(s, values, value_dim, emb_dim, n, out, absent_value);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}
 static int check_dims(int D, int64_t vdim) { return (D <= 0 || (D & 3) || D > 128 * kMaxChunks || (vdim & 3) || vdim < D) ? DEMB_ERR_ARG : 0; }
 
 int demb_lookup_forward(void* storage, const int64_t* table_bucket_offsets, int64_t bucket_capacity, int num_scores, const float* values,
@@ -808,6 +1016,8 @@ int demb_lookup_forward(void* storage, const int64_t* table_bucket_offsets, int6
            nullptr, nullptr, founds, slots_out, nullptr};
   if (combiner < 0) {
     if (n <= 0) return 0;
+    if (out_dtype == DEMB_F32 && bucket_capacity == kProbeC && g_probe_kernel == 2 && kCopyWarps * 32 * emb_dim * 4 <= 200 * 1024)
+      return launch_seq_probe2(s, values, value_dim, emb_dim, n, (float*)out, absent_value, (cudaStream_t)stream);
     if (out_dtype == DEMB_F32 && bucket_capacity == kProbeC && emb_dim <= 1024 && g_probe_kernel)
       return launch_seq_probe(s, values, value_dim, emb_dim, n, (float*)out, absent_value, (cudaStream_t)stream);
     if (out_dtype == DEMB_F32) return launch_seq_tma(s, values, value_dim, emb_dim, n, (float*)out, absent_value, (cudaStream_t)stream);
@@ -879,8 +1089,7 @@ int demb_copy_rows(float* values, int64_t value_dim, int width, int64_t n, const
 
 int64_t demb_backward_workspace_bytes(int64_t n, int emb_dim) {
   if (n <= 0) return 256;
-  size_t tmp = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const int32_t*)nullptr, (int32_t*)nullptr, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n);
+  const size_t tmp = rsort::workspace_bytes(n);
   size_t tiles = ((size_t)n + 31) / 32;
   return (int64_t)(4 * align256(4 * (size_t)n) + 2 * align256(tiles * (size_t)emb_dim * 4) + align256(((tiles + 31) / 32 + 1) * (size_t)emb_dim * 4) + align256(tmp) + 256);
 }
@@ -908,14 +1117,18 @@ static int backward_impl(float* values, int64_t value_dim, int emb_dim, int64_t 
   float* ps = (float*)w; w += align256(tiles * (size_t)emb_dim * 4);
   float* wc = (float*)w; w += align256(((tiles + 31) / 32 + 1) * (size_t)emb_dim * 4);
   size_t tmp_bytes = (size_t)((uint8_t*)workspace + workspace_bytes - w);
+  int end_bit = 1; while (end_bit < 31 && (1ll << end_bit) < num_unique_bound + (n_dev ? 1 : 0)) ++end_bit;
+  const bool in_first = n <= 1 || (rsort::num_passes(end_bit) % 2 == 0);                            // where the sorted pairs end up
+  const int32_t* skey = in_first ? k0 : k1;
+  const int32_t* sval = in_first ? v0 : v1;
   if (phase != 2) {
     cudaStream_t s1 = stream;
     if (g_prof_on && phase == 0) cudaEventRecord(g_prof_ev[0], stream);
     backward_pairs_kernel<<<(int)((n + 255) / 256), 256, 0, s1>>>(n, n_dev, (int32_t)num_unique_bound, inverse, grad_row_of, pooled, batch_size, num_features,
                                                                   offsets, k0, v0);
-    int end_bit = 1; while (end_bit < 31 && (1ll << end_bit) < num_unique_bound + (n_dev ? 1 : 0)) ++end_bit;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(w, tmp_bytes, k0, k1, v0, v1, (int)n, 0, end_bit, s1);
-    if (e != cudaSuccess) return -(int)e;
+    int32_t *sk = nullptr, *sv = nullptr;
+    const int rc = rsort::sort_pairs(k0, v0, k1, v1, n, end_bit, w, tmp_bytes, s1, &sk, &sv);       // own stable LSD radix sort (demb_sort.cuh)
+    if (rc) return rc;
     if (phase == 1) {
       DEMB_CHECK_LAST();
       return 0;
@@ -923,11 +1136,22 @@ static int backward_impl(float* values, int64_t value_dim, int emb_dim, int64_t 
   } else {
     if (g_prof_on) cudaEventRecord(g_prof_ev[0], stream);
   }
-  BwdArgs a{grads, grad_stride, emb_dim, pooled, combiner, batch_size, num_features, offsets, k1, v1, n, n_dev, ug_addr, rows, values, value_dim, unique_grads,
+  BwdArgs a{grads, grad_stride, emb_dim, pooled, combiner, batch_size, num_features, offsets, skey, sval, n, n_dev, ug_addr, rows, values, value_dim, unique_grads,
             pc, ps, OptArgs{opt_type, lr, eps, beta1, beta2, weight_decay, bias_correction1, bias_correction2}};
   if (g_prof_on) cudaEventRecord(g_prof_ev[1], stream);
   DISPATCH_NCHUNK(emb_dim, {
-    backward_tiles_kernel<NC><<<warp_grid((int64_t)tiles), kBlock, 0, stream>>>(a);
+    const size_t stage_b = 32u * (size_t)emb_dim * 4u;
+    int tw = (int)((216u * 1024u) / stage_b); if (tw > kBwdTmaWarps) tw = kBwdTmaWarps;
+    if (g_bwd_tma && tw >= 4 && (((uintptr_t)grads | (uintptr_t)(grad_stride * 4)) & 15) == 0) {
+      static std::atomic<int> configured[kMaxDevices];
+      cudaError_t ce = once_per_device(configured, [] { return cudaFuncSetAttribute(backward_tiles_tma_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); });
+      if (ce != cudaSuccess) return -(int)ce;
+      int64_t blocks = ((int64_t)tiles + tw - 1) / tw;
+      if (blocks > sm_count()) blocks = sm_count();
+      backward_tiles_tma_kernel<NC><<<(int)blocks, kBwdTmaWarps * 32, (size_t)tw * stage_b, stream>>>(a, tw);
+    } else {
+      backward_tiles_kernel<NC><<<warp_grid((int64_t)tiles), kBlock, 0, stream>>>(a);
+    }
     if (g_prof_on) cudaEventRecord(g_prof_ev[2], stream);
     if (tiles > 32) backward_windows_kernel<NC><<<warp_grid((int64_t)(tiles + 31) / 32), kBlock, 0, stream>>>(a, wc);
     if (tiles > 1) backward_spans_kernel<NC><<<warp_grid((int64_t)tiles - 1), kBlock, 0, stream>>>(a, wc);
@@ -969,9 +1193,10 @@ int demb_backward_apply(float* values, int64_t value_dim, int emb_dim, int64_t n
                        workspace, workspace_bytes, (cudaStream_t)stream_, 2);
 }
 
-// development / measurement switches.  option 0: 1 = tile probe kernel for the fused lookup forward (default), 0 = round-1 kernel
+// development / measurement switches.  option 0 = fused lookup forward kernel: 2 (default) / 1 / 0, see g_probe_kernel
 int demb_set_option(int option, int value) {
-  if (option == 0) { g_probe_kernel = value != 0; return 0; }
+  if (option == 0) { g_probe_kernel = value; return 0; }
+  if (option == 1) { g_bwd_tma = value != 0; return 0; }
   return DEMB_ERR_ARG;
 }
 

@@ -89,10 +89,10 @@ __global__ void train_lookup_kernel(TrainArgs a) {
   }
 }
 
-// The same lookup for 128-slot buckets on the warp-tile probe (demb_probe.cuh): the digest lines of tile t+1 are loaded (coalesced, into
-// registers) while tile t is scanned, so a probe costs one exposed memory hop (the candidate key loads) instead of the per-thread chain.
+// The same lookup for 128-slot buckets on the warp-tile probe (demb_probe.cuh): two memory hops per tile (the coalesced digest lines,
+// then all candidate key loads at once) instead of the per-thread chain of up to ten.
 constexpr int kLookupWarps = 8;
-__global__ void __launch_bounds__(kLookupWarps * 32) train_lookup_tile_kernel(TrainArgs a) {
+__global__ void __launch_bounds__(kLookupWarps * 32, 3) train_lookup_tile_kernel(TrainArgs a) {
   __shared__ int slot_sm[kLookupWarps][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t n = *a.n_u;
@@ -104,12 +104,12 @@ __global__ void __launch_bounds__(kLookupWarps * 32) train_lookup_tile_kernel(Tr
     if (tl >= tiles || u >= n) return ProbeKey{0, 0, 0, 0, false};
     return make_probe_key(a.t, a.ukeys[u], a.utids ? (int)a.utids[u] : 0);
   };
-  ProbeKey k0 = load_key(tile);
-  DigRegs d0, d1;
-  tile_load_digests(a.t, k0, d0, lane);
+  // no register double-buffering of the digest lines here: 24 warps per SM (3 CTAs) with one tile each in flight hide the latency, and
+  // the 32 registers a second DigRegs costs would drop the kernel to 2 CTAs per SM (ncu: 20 % warps active, 85 us)
   for (; tile < tiles; tile += wstride) {
-    const ProbeKey k1 = load_key(tile + wstride);
-    tile_load_digests(a.t, k1, d1, lane);
+    const ProbeKey k0 = load_key(tile);
+    DigRegs d0;
+    tile_load_digests(a.t, k0, d0, lane);
     const int pos = tile_probe(a.t, k0, d0, slot_sm[wib], lane);
     const int64_t u = (tile << 5) + lane;
     int32_t first_bucket = -1;                                                    // >= 0: this lane pushed the FIRST key of that bucket
@@ -140,7 +140,6 @@ __global__ void __launch_bounds__(kLookupWarps * 32) train_lookup_tile_kernel(Tr
       base = __shfl_sync(0xffffffffu, base, leader);
       if (first_bucket >= 0) a.touched[base + __popc(m & ((1u << lane) - 1u))] = first_bucket;
     }
-    k0 = k1; d0 = d1;
   }
 }
 
@@ -224,9 +223,23 @@ __global__ void __launch_bounds__(kBlock) train_evict_kernel(TrainArgs a) {
   const int64_t nt = (int64_t)*a.n_touched;
   const int64_t wstride = (int64_t)gridDim.x * (kBlock / 32);
   constexpr int C = kProbeC;
-  for (int64_t w = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); w < nt; w += wstride) {
-    const int64_t b = a.touched[w];
-    const int head = *reinterpret_cast<volatile int*>(a.heads + b);
+  int64_t w = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+  // software pipeline over this warp's buckets: the (bucket id -> list head) chain of the NEXT bucket is resolved, and its 2.6 KB of
+  // keys / digests / scores / pin counters pulled into L2, while the current bucket is processed (the kernel is latency-bound: one warp
+  // owns a bucket and walks a chain of dependent loads; ~24 warps per SM)
+  int64_t b = w < nt ? a.touched[w] : -1;
+  int head = b >= 0 ? *reinterpret_cast<volatile int*>(a.heads + b) : -1;
+  for (; w < nt; w += wstride) {
+    const int64_t wn = w + wstride;
+    const int64_t bn = wn < nt ? a.touched[wn] : -1;
+    int head_n = -1;
+    if (bn >= 0) {
+      head_n = *reinterpret_cast<volatile int*>(a.heads + bn);
+      const char* nb = reinterpret_cast<const char*>(a.t.bucket(bn));
+      const int64_t bytes = a.t.bucket_bytes();
+      if ((int64_t)lane * 128 < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + lane * 128));
+      if (lane < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(a.counter + bn * C) + lane * 128));
+    }
     uint8_t* bk = a.t.bucket(b);
     // bucket state -> registers (issued before the list walk: independent of it)
     uint64_t kreg[4], sreg[4]; int32_t creg[4];
@@ -261,6 +274,7 @@ __global__ void __launch_bounds__(kBlock) train_evict_kernel(TrainArgs a) {
         last = best; have_last = true;
       }
       if (lane == 0) a.heads[b] = -1;
+      b = bn; head = head_n;
       continue;
     }
     const uint64_t mykey = mine >= 0 ? a.ukeys[mine] : 0;
@@ -316,13 +330,12 @@ __global__ void __launch_bounds__(kBlock) train_evict_kernel(TrainArgs a) {
       }
       const int64_t slot = (b - a.t.bkt_off[tid]) * C + pos;
       const int64_t row = (a.row_base ? a.row_base[tid] : 0) + slot;
-      if (lane == 0) { a.slots[u] = slot; a.rows[u] = row; }
-      const InitArgs ia = a.table_init ? a.table_init[tid] : a.init;
-      const int D4 = a.D >> 2, V4 = (int)(a.vdim >> 2);
-      for (int c = lane; c < D4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, init4(ia, key, c));
-      for (int c = D4 + lane; c < V4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, make_float4(a.state_init, a.state_init, a.state_init, a.state_init));
+      // the row itself is initialised by train_init_rows_kernel (a streaming kernel over the marks): doing it here put ~500 Philox /
+      // store instructions per key on this latency-bound warp (ncu: 105 M warp instructions, 180 us)
+      if (lane == 0) { a.slots[u] = slot; a.rows[u] = row; a.next[u] = -2; }
     }
     if (lane == 0) a.heads[b] = -1;                                               // leave the list heads clean for the next step
+    b = bn; head = head_n;
   }
 }
 
@@ -356,31 +369,41 @@ __global__ void __launch_bounds__(kBlock) train_insert_thread_kernel(TrainArgs a
       }
       last = best; have_last = true;
     }
-    // the list is consumed: queue the inserted keys for row initialisation (one atomic per bucket)
-    int ins = 0;
-    for (int cur = head; cur != -1; cur = a.next[cur]) ins += a.slots[cur] >= 0 ? 1 : 0;
-    if (ins) {
-      unsigned long long at = atomicAdd(a.n_init, (unsigned long long)ins);
-      for (int cur = head; cur != -1; cur = a.next[cur]) if (a.slots[cur] >= 0) a.init_list[at++] = cur;
+    for (int cur = head; cur != -1;) {                                            // the list is consumed: turn its links into "initialise me" marks
+      const int nx = a.next[cur];
+      a.next[cur] = a.slots[cur] >= 0 ? -2 : -4;
+      cur = nx;
     }
     a.heads[b] = -1;                                                              // leave the list heads clean for the next step
   }
 }
 
-// Warp per queued key: rows inserted by the thread kernel get initializer + optimizer state (fused A10 + A11).  The queue is empty at
-// eviction steady state (every insert goes through the evict kernel, which initialises inline): the kernel then costs one load.
+// Rows of the keys inserted in this step (next[u] == -2) get initializer + optimizer state (fused A10 + A11): a warp reads 32 marks at a
+// time (coalesced), ballots, and initialises the marked rows one after the other with all 32 lanes — pure streaming writes, no dependent
+// loads, every warp of the grid busy.
 __global__ void __launch_bounds__(kBlock) train_init_rows_kernel(TrainArgs a) {
   const int lane = threadIdx.x & 31;
-  const int64_t n = (int64_t)*a.n_init;
+  const int64_t n = *a.n_u;
+  const int64_t tiles = (n + 31) >> 5;
   const int64_t wstride = (int64_t)gridDim.x * (kBlock / 32);
   const int D4 = a.D >> 2, V4 = (int)(a.vdim >> 2);
-  for (int64_t q = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); q < n; q += wstride) {
-    const int64_t u = a.init_list[q];
-    const int64_t row = a.rows[u];
-    const uint64_t key = a.ukeys[u];
-    const InitArgs ia = a.table_init ? a.table_init[a.utids ? a.utids[u] : 0] : a.init;
-    for (int c = lane; c < D4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, init4(ia, key, c));
-    for (int c = D4 + lane; c < V4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, make_float4(a.state_init, a.state_init, a.state_init, a.state_init));
+  for (int64_t tile = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); tile < tiles; tile += wstride) {
+    const int64_t u0 = (tile << 5) + lane;
+    const bool mine = u0 < n && a.next[u0] == -2;
+    unsigned m = __ballot_sync(0xffffffffu, mine);
+    const int64_t my_row = mine ? a.rows[u0] : -1;
+    const uint64_t my_key = mine ? a.ukeys[u0] : 0;
+    const int my_tid = (mine && a.utids) ? (int)a.utids[u0] : 0;
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const int64_t row = __shfl_sync(0xffffffffu, my_row, src);
+      const uint64_t key = __shfl_sync(0xffffffffu, my_key, src);
+      const int tid = __shfl_sync(0xffffffffu, my_tid, src);
+      const InitArgs ia = a.table_init ? a.table_init[tid] : a.init;
+      for (int c = lane; c < D4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, init4(ia, key, c));
+      for (int c = D4 + lane; c < V4; c += 32) st_f4(a.values + row * a.vdim + 4 * c, make_float4(a.state_init, a.state_init, a.state_init, a.state_init));
+    }
   }
 }
 
@@ -450,7 +473,7 @@ int demb_train_prefetch(void* storage, const int64_t* table_bucket_offsets, int6
   a.slots = slots; a.rows = rows; a.next = next; a.touched = touched; a.n_touched = n_touched; a.init_list = init_list; a.n_init = n_init;
   if (bucket_capacity == kProbeC) {
     int64_t blocks = ((n + 31) / 32 + kLookupWarps - 1) / kLookupWarps;
-    const int64_t cap = (int64_t)sm_count() * 8;
+    const int64_t cap = (int64_t)sm_count() * 3;
     train_lookup_tile_kernel<<<(int)(blocks > cap ? cap : blocks), kLookupWarps * 32, 0, stream>>>(a);
   } else {
     train_lookup_kernel<<<grid_for(n), kBlock, 0, stream>>>(a);

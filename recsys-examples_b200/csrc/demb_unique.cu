@@ -22,7 +22,7 @@ using namespace demb;
 
 namespace {
 constexpr int kBlock = 256;
-constexpr int kItems = 8;                       // ids per thread in the scan kernel
+constexpr int kItems = 4;                       // ids per thread in the scan kernel (1024-id tiles: 1024 CTAs for a 2^20-id step)
 constexpr int kTile = kBlock * kItems;
 inline int grid_for(int64_t n) { int64_t g = (n + kBlock - 1) / kBlock; const int64_t cap = (int64_t)sm_count() * 64; return (int)(g < 1 ? 1 : (g > cap ? cap : g)); }
 
