@@ -476,7 +476,12 @@ def main():
         for i in range(2):
             step(batches[args.warmup + i])
         if world == 1:
-            m.eval(); m(batches[-1], offsets); m.train()       # the fused probe+gather forward (eval path)
+            m.eval()
+            for opt_v in (1, 2):                               # the fused probe+gather forward (eval path), both tile-probe variants
+                N.lib.demb_set_option(0, opt_v)
+                m(batches[-1], offsets)
+            N.lib.demb_set_option(0, 1)
+            m.train()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return

@@ -31,13 +31,30 @@ struct ProbeKey {
   bool valid;            // key legal and table non-empty
 };
 
-__device__ __forceinline__ ProbeKey make_probe_key(const Table& t, uint64_t key, int tid) {
+// bucket = (h % (nb * 128)) / 128 = (h >> 7) % nb.  A 64-bit modulo by a run-time value is ~150 dependent instructions on this GPU (no
+// hardware divider) — more than the rest of a probe put together, and the fused lookup kernel is ALU-latency-bound on its 12 warps
+// (ncu: 53 M warp instructions against 13 M for the plain gather).  The table's bucket count is invariant over long runs of ids (ids are
+// grouped by table), so each thread caches (table id, first bucket, bucket count, magic = floor((2^64 - 1) / nb)) and reduces with one
+// 64-bit multiply-high + at most two corrections; the cache is refilled (one real division) only when the table id changes.
+struct TableCache { int32_t tid; int64_t bb; uint64_t nb; uint64_t magic; };
+__device__ __forceinline__ TableCache empty_table_cache() { return TableCache{-1, 0, 0, 0}; }
+
+__device__ __forceinline__ ProbeKey make_probe_key(const Table& t, uint64_t key, int tid, TableCache& tc) {
   ProbeKey p{key, 0, 0, tid, false};
   if (key_is_valid(key)) {
-    const int64_t h = hash63(key);
-    const int64_t bb = t.bkt_off[tid];
-    const int64_t cap = (t.bkt_off[tid + 1] - bb) * t.C;
-    if (cap > 0) { p.bucket = bb + (h % cap) / t.C; p.slot_base = (p.bucket - bb) * t.C; p.valid = true; }
+    if (tc.tid != tid) {
+      tc.tid = tid;
+      tc.bb = t.bkt_off[tid];
+      tc.nb = (uint64_t)(t.bkt_off[tid + 1] - tc.bb);
+      tc.magic = tc.nb ? 0xFFFFFFFFFFFFFFFFull / tc.nb : 0ull;
+    }
+    if (tc.nb > 0) {
+      const uint64_t x = (uint64_t)hash63(key) >> 7;               // C == 128
+      uint64_t r = x - __umul64hi(x, tc.magic) * tc.nb;              // quotient estimate is low by at most 2
+      if (r >= tc.nb) r -= tc.nb;
+      if (r >= tc.nb) r -= tc.nb;
+      p.bucket = tc.bb + (int64_t)r; p.slot_base = (int64_t)r * kProbeC; p.valid = true;
+    }
   }
   return p;
 }
@@ -71,6 +88,69 @@ __device__ __forceinline__ uint32_t match16(const uint4& d, uint32_t w4) {
   // (m * 0x00204081) >> 21 gathers bits 0, 8, 16, 24 into bits 0..3 (the partial products do not collide)
   return ((m0 * 0x00204081u) >> 21 & 0xFu) | (((m1 * 0x00204081u) >> 21 & 0xFu) << 4) | (((m2 * 0x00204081u) >> 21 & 0xFu) << 8) |
          (((m3 * 0x00204081u) >> 21 & 0xFu) << 12);
+}
+
+// The probe in two halves, so that a kernel can put other work (and its one long wait) between them:
+//   tile_probe_issue   digest scan -> per-lane candidate masks; ISSUES the first candidate key load of every (lane, step) — nothing waits
+//   tile_probe_finish  compares the keys that have arrived meanwhile, slow path for second candidates, publishes the slots
+struct ProbeCand { uint64_t key[8]; uint32_t mask[8]; };
+
+__device__ __forceinline__ uint64_t ld_u64_volatile_nc(const uint64_t* p) {   // issued where written, not sunk to the use
+  uint64_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void tile_probe_issue(const Table& t, const ProbeKey& p, const DigRegs& dig, ProbeCand& cand, int lane) {
+  const uint32_t want = (uint32_t)digest_of(hash63(p.key)) * 0x01010101u;
+  const uint64_t my_keys = p.valid ? reinterpret_cast<uint64_t>(t.keys(t.bucket(p.bucket))) : 0ull;
+  const int c = lane & 7;                          // 16-byte chunk of the line this lane scans
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = (lane >> 3) + 4 * j;             // key of the tile this lane works for in step j
+    const uint32_t w4 = __shfl_sync(0xffffffffu, want, k);
+    const uint64_t* keys_k = reinterpret_cast<const uint64_t*>(__shfl_sync(0xffffffffu, my_keys, k));
+    cand.mask[j] = 0; cand.key[j] = 0;
+    if (keys_k) {
+      cand.mask[j] = match16(dig.d[j], w4);
+      if (cand.mask[j]) cand.key[j] = ld_u64_volatile_nc(keys_k + c * 16 + __ffs(cand.mask[j]) - 1);
+    }
+  }
+}
+
+__device__ __forceinline__ int tile_probe_finish(const Table& t, const ProbeKey& p, const ProbeCand& cand, int* slot_sm, int lane) {
+  slot_sm[lane] = -1;
+  __syncwarp();
+  const uint64_t my_keys = p.valid ? reinterpret_cast<uint64_t>(t.keys(t.bucket(p.bucket))) : 0ull;
+  const int c = lane & 7;
+  bool more = false;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = (lane >> 3) + 4 * j;
+    const uint64_t key_k = __shfl_sync(0xffffffffu, p.key, k);
+    if (cand.mask[j]) {
+      if (cand.key[j] == key_k) slot_sm[k] = c * 16 + __ffs(cand.mask[j]) - 1;
+      else if ((cand.mask[j] & (cand.mask[j] - 1)) && cand.key[j] != kEmptyKey) more = true;
+    }
+  }
+  if (__any_sync(0xffffffffu, more)) {               // slow path: remaining candidates of a chunk, one dependent load each
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = (lane >> 3) + 4 * j;
+      const uint64_t key_k = __shfl_sync(0xffffffffu, p.key, k);
+      const uint64_t* keys_k = reinterpret_cast<const uint64_t*>(__shfl_sync(0xffffffffu, my_keys, k));
+      uint32_t m = (cand.key[j] == key_k || cand.key[j] == kEmptyKey) ? 0u : (cand.mask[j] & (cand.mask[j] - 1));
+      while (m) {
+        const int pos = c * 16 + __ffs(m) - 1;
+        m &= m - 1;
+        const uint64_t kk = keys_k[pos];
+        if (kk == key_k) { slot_sm[k] = pos; break; }
+        if (kk == kEmptyKey) break;
+      }
+    }
+  }
+  __syncwarp();
+  return slot_sm[lane];
 }
 
 // all 32 lanes; returns the position (0..127) of this lane's key in its bucket, or -1.  slot_sm: 32 ints of the warp's shared memory.

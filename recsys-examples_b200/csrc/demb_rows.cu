@@ -195,12 +195,7 @@ __global__ void __launch_bounds__(kProbeFwdWarps * 32) forward_seq_probe_kernel(
   const int64_t tiles = (n + 31) >> 5;
   const int64_t wstride = (int64_t)gridDim.x * warps_per_block;
   int64_t tile = (int64_t)blockIdx.x * warps_per_block + wib;
-  auto load_key = [&](int64_t tl) -> ProbeKey {
-    const int64_t i = (tl << 5) + lane;
-    if (tl >= tiles || i >= n) return ProbeKey{0, 0, 0, 0, false};
-    const int tid = (s.T > 1 && s.table_range) ? table_of(s.table_range, s.T, i) : 0;
-    return make_probe_key(s.t, s.keys[i], tid);
-  };
+  TableCache tc = empty_table_cache();
   auto row_of = [&](const ProbeKey& p, int pos, int64_t tl) -> int64_t {
     const int64_t i = (tl << 5) + lane;
     const int64_t slot = pos >= 0 ? p.slot_base + pos : -1;
@@ -208,12 +203,40 @@ __global__ void __launch_bounds__(kProbeFwdWarps * 32) forward_seq_probe_kernel(
     return slot < 0 ? -1 : (s.row_base ? s.row_base[p.tid] : 0) + slot;
   };
   uint32_t par_row = 0;
-  // prologue: digests of the first two tiles, probe of the first
-  ProbeKey k0 = load_key(tile), k1 = load_key(tile + wstride);
-  DigRegs d0, d1;
-  tile_load_digests(s.t, k0, d0, lane);
-  tile_load_digests(s.t, k1, d1, lane);
-  int64_t row = row_of(k0, tile_probe(s.t, k0, d0, sm.slot[wib], lane), tile);
+  // Software pipeline, four tiles deep.  The row stage is the scarce resource (in-flight bytes per SM), so the row copies of tile t are
+  // issued FIRST in an iteration — right after the previous tile's store — and all probe work for later tiles is done while they fly:
+  //   iteration t:  issue row copies (t)
+  //                 | compare candidate keys (t+1) [issued an iteration ago] -> its row ids
+  //                 | digest masks (t+2) [lines arrived] -> issue its candidate key loads
+  //                 | ids (t+3) [arrived] -> hash -> issue its digest-line loads | issue id load (t+4)
+  //                 | WAIT rows (t) (the one exposed wait), bulk-store them
+  auto load_id = [&](int64_t tl) -> uint64_t {
+    const int64_t i = (tl << 5) + lane;
+    return (tl < tiles && i < n) ? s.keys[i] : kEmptyKey;          // EmptyKey is a reserved (invalid) key: the lane takes no part
+  };
+  auto key_of = [&](int64_t tl, uint64_t id) -> ProbeKey {
+    const int64_t i = (tl << 5) + lane;
+    if (tl >= tiles || i >= n) return ProbeKey{0, 0, 0, 0, false};
+    const int tid = (s.T > 1 && s.table_range) ? table_of(s.table_range, s.T, i) : 0;
+    return make_probe_key(s.t, id, tid, tc);
+  };
+  // prologue: tile t probed completely; candidates of t+1 issued; digest lines of t+2 issued; ids of t+3 fetched
+  DigRegs dg;
+  ProbeCand cand;
+  ProbeKey k1, k2;
+  int64_t row;
+  {
+    const ProbeKey k0 = key_of(tile, load_id(tile));
+    tile_load_digests(s.t, k0, dg, lane);
+    tile_probe_issue(s.t, k0, dg, cand, lane);
+    row = row_of(k0, tile_probe_finish(s.t, k0, cand, sm.slot[wib], lane), tile);
+    k1 = key_of(tile + wstride, load_id(tile + wstride));
+    tile_load_digests(s.t, k1, dg, lane);
+    tile_probe_issue(s.t, k1, dg, cand, lane);
+    k2 = key_of(tile + 2 * wstride, load_id(tile + 2 * wstride));
+    tile_load_digests(s.t, k2, dg, lane);
+  }
+  uint64_t id3 = load_id(tile + 3 * wstride);
   for (; tile < tiles; tile += wstride) {
     const int64_t base = tile << 5;
     const int cnt = (int)((n - base) < 32 ? (n - base) : 32);
@@ -229,12 +252,12 @@ __global__ void __launch_bounds__(kProbeFwdWarps * 32) forward_seq_probe_kernel(
       float4* d = reinterpret_cast<float4*>(rowbuf + (size_t)lane * row_bytes);
       for (int c = 0; c < (D >> 2); ++c) d[c] = make_float4(absent_value, absent_value, absent_value, absent_value);
     }
-    // tile t+2: digest lines on their way while tile t+1 is probed and tile t is copied
-    const ProbeKey k2 = load_key(tile + 2 * wstride);
-    tile_load_digests(s.t, k2, d0, lane);
-    // tile t+1: probe while the row copies of tile t are in flight
-    const int64_t next_row = row_of(k1, tile_probe(s.t, k1, d1, sm.slot[wib], lane), tile + wstride);
-    sm100::mbar_wait(&sm.bar_row[wib], par_row);
+    const int64_t next_row = row_of(k1, tile_probe_finish(s.t, k1, cand, sm.slot[wib], lane), tile + wstride);   // tile t+1
+    tile_probe_issue(s.t, k2, dg, cand, lane);                                                                    // tile t+2
+    const ProbeKey k3 = key_of(tile + 3 * wstride, id3);                                                           // tile t+3
+    tile_load_digests(s.t, k3, dg, lane);
+    id3 = load_id(tile + 4 * wstride);                                                                             // tile t+4
+    sm100::mbar_wait(&sm.bar_row[wib], par_row);                  // the one exposed wait
     par_row ^= 1;
     sm100::fence_proxy_async_smem();                             // absent rows were written through the generic proxy
     __syncwarp();
@@ -242,7 +265,7 @@ __global__ void __launch_bounds__(kProbeFwdWarps * 32) forward_seq_probe_kernel(
       sm100::bulk_store(out + base * (int64_t)D, rowbuf, (uint32_t)cnt * row_bytes);
       sm100::bulk_commit();
     }
-    row = next_row; k1 = k2; d1 = d0;
+    row = next_row; k1 = k2; k2 = k3;
   }
   if (lane == 0) sm100::bulk_wait0();                             // shared memory must outlive the last bulk store
 }
@@ -273,12 +296,13 @@ __global__ void __launch_bounds__((kCopyWarps + kProbeWarps) * 32, 1) forward_se
     // copy warpgroups give up (12 x 32 x 64 + 8 x 32 x 136 = 59392 <= 65536)
     asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
     const int p = wib - kCopyWarps;
+    TableCache tc = empty_table_cache();
     auto load_key = [&](int64_t i) -> ProbeKey {
       const int64_t tl = (int64_t)blockIdx.x + i * gridDim.x;
       const int64_t id = (tl << 5) + lane;
       if (i >= my_tiles || id >= n) return ProbeKey{0, 0, 0, 0, false};
       const int tid = (s.T > 1 && s.table_range) ? table_of(s.table_range, s.T, id) : 0;
-      return make_probe_key(s.t, s.keys[id], tid);
+      return make_probe_key(s.t, s.keys[id], tid, tc);
     };
     ProbeKey k0 = load_key(p);
     DigRegs d0, d1;
@@ -349,6 +373,7 @@ __global__ void __launch_bounds__(kBlock) forward_pool_kernel(RowSrc s, const fl
                                                               const int64_t* __restrict__ offsets, int combiner, void* __restrict__ out,
                                                               int out_dtype, int64_t total_D, int bpw, float absent_value) {
   __shared__ int pool_slot_sm[kWarpsPerBlock][32];
+  TableCache pool_tc = empty_table_cache();
   const int lane = threadIdx.x & 31;
   const int D4 = D >> 2;
   const int64_t bags = B * (int64_t)F;
@@ -389,7 +414,7 @@ __global__ void __launch_bounds__(kBlock) forward_pool_kernel(RowSrc s, const fl
       if (!s.rows && s.t.C == kProbeC) {
         // probe mode, 128-slot buckets: the warp-tile probe (coalesced digest lines, all candidate keys in flight together)
         ProbeKey pk{0, 0, 0, 0, false};
-        if (lane < cnt) pk = make_probe_key(s.t, s.keys[base + lane], (s.T > 1 && s.table_range) ? table_of(s.table_range, s.T, base + lane) : 0);
+        if (lane < cnt) pk = make_probe_key(s.t, s.keys[base + lane], (s.T > 1 && s.table_range) ? table_of(s.table_range, s.T, base + lane) : 0, pool_tc);
         DigRegs dg;
         tile_load_digests(s.t, pk, dg, lane);
         const int pos = tile_probe(s.t, pk, dg, pool_slot_sm[threadIdx.x >> 5], lane);
@@ -934,7 +959,8 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 inline int nchunk_of(int D) { return (D / 4 + 31) / 32; }
 
 // bench.py's roofline needs per-kernel device time of the multi-kernel backward: optional CUDA events around its stages.
-bool g_bwd_tma = true;          // demb_set_option(1, v): gradient rows of the backward staged through shared memory (1, default) or registers (0)
+bool g_bwd_tma = false;         // demb_set_option(1, v): gradient rows of the backward staged through shared memory (1) or registers (0, default:
+                                // measured 0.293 ms against 0.367 ms — 12 resident warps cannot hide the per-segment row read-modify-write chain)
 int g_probe_kernel = 1;         // demb_set_option(0, v): 1 = one probe + copy pipeline per warp (default), 2 = specialised probe / copy warps (measured slower), 0 = round-1 thread-per-key probe
 bool g_prof_on = false;
 cudaEvent_t g_prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};

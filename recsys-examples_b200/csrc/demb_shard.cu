@@ -57,9 +57,16 @@ struct Shard {
 };
 
 // sparse_block_bucketize_features.cu:254-259 + :30-37: owning rank and the id the owner sees
+// x % W for a small W with 32-bit arithmetic only (a 64-bit modulo by a run-time value is ~150 instructions): exact, since
+// x = hi * 2^32 + lo  =>  x mod W = ((hi mod W) * (2^32 mod W) + lo mod W) mod W, every term < 2^32 for W <= 16
+__device__ __forceinline__ int mod_small(uint64_t x, int W) {
+  const uint32_t w = (uint32_t)W, hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
+  const uint32_t r32 = (uint32_t)(0x100000000ull % w);
+  return (int)(((hi % w) * r32 + lo % w) % w);
+}
 __device__ __forceinline__ void owner_of(uint64_t key, int dist_type, int64_t blk, int W, int& p, uint64_t& nid) {
-  if (dist_type == 1) { p = (int)(key % (uint64_t)W); nid = key; }
-  else if (dist_type == 2) { p = (int)(fmix64(key) % (uint64_t)W); nid = key; }
+  if (dist_type == 1) { p = mod_small(key, W); nid = key; }
+  else if (dist_type == 2) { p = mod_small(fmix64(key), W); nid = key; }
   else if (key < (uint64_t)blk * (uint64_t)W) { p = (int)(key / (uint64_t)blk); nid = key % (uint64_t)blk; }
   else { p = (int)(key % (uint64_t)W); nid = key / (uint64_t)W; }
 }
@@ -78,16 +85,18 @@ struct RouteArgs {
 
 __global__ void __launch_bounds__(kRouteTile) route_count_kernel(RouteArgs a) {
   __shared__ int cnt[kMaxW];
+  __shared__ int pt[kMaxW * kMaxT];            // per-(owner, table) counts of this tile: one global atomic per non-zero entry, not one per id
   const int64_t n = *a.n_u < a.n_max ? *a.n_u : a.n_max;
   const int64_t u = (int64_t)blockIdx.x * kRouteTile + threadIdx.x;
   if (threadIdx.x < kMaxW) cnt[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < a.s.W * a.s.T; i += kRouteTile) pt[i] = 0;
   __syncthreads();
   int p = -1;
   if (u < n) {
     const int t = a.utids ? (int)a.utids[u] : 0;
     uint64_t nid;
     owner_of(a.ukeys[u], a.dist_type[t], a.block_sizes[t], a.s.W, p, nid);
-    atomicAdd(reinterpret_cast<unsigned long long*>(a.pair_table_cnt + p * a.s.T + t), 1ull);      // order-independent sum
+    if (a.s.T > 1) atomicAdd(&pt[p * a.s.T + t], 1);
   }
   for (int d = 0; d < a.s.W; ++d) {
     const unsigned m = __ballot_sync(0xffffffffu, p == d);
@@ -95,6 +104,8 @@ __global__ void __launch_bounds__(kRouteTile) route_count_kernel(RouteArgs a) {
   }
   __syncthreads();
   if (threadIdx.x < a.s.W) a.tile_cnt[(int64_t)blockIdx.x * a.s.W + threadIdx.x] = cnt[threadIdx.x];
+  if (a.s.T == 1) { if (threadIdx.x < a.s.W && cnt[threadIdx.x]) atomicAdd(reinterpret_cast<unsigned long long*>(a.pair_table_cnt + threadIdx.x), (unsigned long long)cnt[threadIdx.x]); }
+  else for (int i = threadIdx.x; i < a.s.W * a.s.T; i += kRouteTile) if (pt[i]) atomicAdd(reinterpret_cast<unsigned long long*>(a.pair_table_cnt + i), (unsigned long long)pt[i]);
 }
 
 // one block: exclusive scan of the tile counts per destination, capacities, meta records to the owners

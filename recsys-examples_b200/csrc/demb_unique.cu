@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kBlock) unique_claim_kernel(UArgs a) {
       if (key == kEmptyKey) {
         p = base + size;
       } else {
-        int64_t q = (int64_t)(fmix64(key) % (uint64_t)size);
+        int64_t q = (int64_t)__umul64hi(fmix64(key), (uint64_t)size);          // multiply-shift range reduction: no 64-bit modulo (~150 instructions)
         while (true) {
           // test before the atomic: a Zipf-hot key is claimed once and then only READ (same-address atomics serialise in L2)
           unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(&a.slots[base + q].key);

@@ -126,6 +126,7 @@ class RowWiseShardedDynamicEmbedding(nn.Module):
         self._err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._epochs = torch.zeros(4, dtype=torch.int64, device=dev)
         self._empty = nn.Parameter(torch.empty(1, device=dev))        # gives autograd a reason to call backward
+        self._prep_req = self._prep_own = None                         # side streams of the two backward sorts
 
     # ------------------------------------------------------------------ setup
     def _ensure_buffers(self, n: int) -> None:
@@ -176,6 +177,12 @@ class RowWiseShardedDynamicEmbedding(nn.Module):
         # ---- requester: per-table dedup, route the unique ids to their owners (ids + counts are stored into the owners' buffers)
         trange = ext.get_table_range(offsets, m.feature_offsets, F) if T > 1 else None
         num_u, uk, rev, _toffs, _f, utids = ext.segmented_unique_cuda(ids, trange, T, None, want_table_ids=True, scratch=self._uscratch_req)
+        train = m.training
+        if train and self._prep_req is None:
+            self._prep_req, self._prep_own = ext.BackwardPrep(dev), ext.BackwardPrep(dev)
+        # the gradient-independent halves of both backward passes (pair list + radix sort) start now, on side streams, under the exchange
+        pooled = self.pooling_mode != DynamicEmbPoolingMode.NONE
+        prep_req = ext.backward_prepare(self._prep_req, D, rev, max(n, 1)) if (train and not pooled) else None
         send_pos = torch.empty(n, dtype=torch.int64, device=dev)
         ug_addr = torch.empty(n, dtype=torch.int64, device=dev)
         N.check(N.launch("shard_route", 3, N.lib.demb_shard_route, W, self.rank, T, D, self._pair_cap, self._n_cap, N.ptr(self._buf.peers), N.ptr(self._err), n,
@@ -193,17 +200,17 @@ class RowWiseShardedDynamicEmbedding(nn.Module):
                          N.ptr(ids_recv), N.ptr(trange_r), N.ptr(n_recv), N.ptr(src_pos), N.ptr(dst_addr), N.ptr(self._recv_ws), self._recv_ws.numel(),
                          N.stream()), "shard_recv")
         st = m._prefetch_device_count(ids_recv, trange_r if T > 1 else None, T, n_recv, self._uscratch_own)
+        prep_own = ext.backward_prepare(self._prep_own, D, st.reverse_indices, R, n_dev=n_recv, grad_row_of=src_pos) if train else None
         N.check(N.launch("gather_to_peers", 1, N.lib.demb_shard_gather_to_peers, N.ptr(m._values), m._values.stride(0), D, R, N.ptr(n_recv), N.ptr(st.rows),
                          N.ptr(st.reverse_indices), N.ptr(dst_addr), N.stream()), "gather_to_peers")
         self._barrier()
         # ---- requester: one gather from rows_back undoes routing + dedup; pooled modes pool here
-        pooled = self.pooling_mode != DynamicEmbPoolingMode.NONE
         out = ext.gather_forward(self._rows_back, D, send_pos, rev, n, offsets=offsets if pooled else None, batch_size=B if pooled else 0,
                                  num_features=F if pooled else 0, combiner=int(self.pooling_mode) if pooled else -1, out_dtype=m.output_dtype)
-        return out, (rev, ug_addr, offsets, B, st, n_recv, src_pos, n)
+        return out, (rev, ug_addr, offsets, B, st, n_recv, src_pos, n, prep_req, prep_own)
 
     def _backward_impl(self, grad: torch.Tensor, saved) -> None:
-        rev, ug_addr, offsets, B, st, n_recv, src_pos, n = saved
+        rev, ug_addr, offsets, B, st, n_recv, src_pos, n, prep_req, prep_own = saved
         m = self.local
         D, F = m.max_D, m.feature_num
         pooled = self.pooling_mode != DynamicEmbPoolingMode.NONE
@@ -213,11 +220,12 @@ class RowWiseShardedDynamicEmbedding(nn.Module):
             grad = grad.clamp(-opt.args.max_gradient, opt.args.max_gradient)
         # requester: reduce the gradient rows per unique id; every reduced row is stored straight into its owner's grads_in segment
         ext.backward(None, D, rev, max(n, 1), None, grad, offsets=offsets if pooled else None, batch_size=B if pooled else 0,
-                     num_features=F if pooled else 0, combiner=int(self.pooling_mode) if pooled else -1, unique_grad_addr=ug_addr)
+                     num_features=F if pooled else 0, combiner=int(self.pooling_mode) if pooled else -1, unique_grad_addr=ug_addr, prepared=prep_req)
         self._barrier()
         # owner: fused reduce across sources + optimizer row update on the received gradient rows
         opt.step()
-        ext.backward(m._values, D, st.reverse_indices, self._recv_cap, st.rows, self._grads_in, n_dev=n_recv, grad_row_of=src_pos, **opt.kernel_kwargs())
+        ext.backward(m._values, D, st.reverse_indices, self._recv_cap, st.rows, self._grads_in, n_dev=n_recv, grad_row_of=src_pos, prepared=prep_own,
+                     **opt.kernel_kwargs())
         m._unpin(st)
 
     def forward(self, ids: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:

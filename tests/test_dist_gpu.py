@@ -207,6 +207,53 @@ def test_sharded_world1_matches_unsharded(cuda):
             assert torch.equal(out, o) and torch.equal(loss, l)
             assert torch.equal(la.tables.table_storage_, lb.tables.table_storage_) and torch.equal(la._values, lb._values)
         ma.check(); mb.check()
+        # ---- planner + sharder classes (reference names: planner/planner.py:213, shard/embedding.py:343, shard/embeddingbag.py:79): a row-wise
+        # plan for two tables, sharder.shard() builds the rank's module from the (duck-typed) TorchRec configs and returns the wrapper
+        from dynamicemb import DynamicEmbInitializerArgs, DynamicEmbInitializerMode, DynamicEmbScoreStrategy, DynamicEmbTableOptions
+        from dynamicemb.shard import (DynamicEmbeddingBagCollectionSharder, DynamicEmbeddingCollectionSharder, DynamicEmbeddingShardingPlanner,
+                                      DynamicEmbParameterConstraints)
+
+        class _Cfg:
+            def __init__(self, name, dim, num, feats, pooling="SUM"):
+                self.name, self.embedding_dim, self.num_embeddings, self.feature_names, self.pooling = name, dim, num, feats, pooling
+
+        class _FakeCollection:
+            def __init__(self, cfgs):
+                self._c = cfgs
+
+            def embedding_configs(self):
+                return self._c
+
+            def embedding_bag_configs(self):
+                return self._c
+
+        def mk_opt():
+            return DynamicEmbTableOptions(score_strategy=DynamicEmbScoreStrategy.STEP, dist_type="hash_roundrobin",
+                                          initializer_args=DynamicEmbInitializerArgs(mode=DynamicEmbInitializerMode.DEBUG))
+        cons = {"user": DynamicEmbParameterConstraints(use_dynamicemb=True, dynamicemb_options=mk_opt()),
+                "item": DynamicEmbParameterConstraints(use_dynamicemb=True, dynamicemb_options=mk_opt())}
+        plan = DynamicEmbeddingShardingPlanner(cons, world_size=1).plan({"user": 50_000, "item": 200_000})
+        assert plan["user"]["local_capacity"] == 50_048 and plan["item"]["sharding_type"] == "row_wise"      # round_up(ceil(N / W), 128)
+        for nm in plan:
+            plan[nm]["dynamicemb_options"] = cons[nm].dynamicemb_options
+        cfgs = [_Cfg("user", D, 50_000, ["f_user"]), _Cfg("item", D, 200_000, ["f_item_a", "f_item_b"])]
+        for sharder, pooled in ((DynamicEmbeddingCollectionSharder(use_index_dedup=True, fused_params={"optimizer": EmbOptimType.SGD, "learning_rate": 0.5}), False),
+                                (DynamicEmbeddingBagCollectionSharder(fused_params={"optimizer": EmbOptimType.SGD, "learning_rate": 0.5}), True)):
+            sh = sharder.shard(_FakeCollection(cfgs), plan, env=None, device=cuda)
+            sh.local.train()
+            Bq = 16
+            lengths = torch.full((3 * Bq,), 2, dtype=torch.int64, device=cuda)
+            idsq = torch.arange(3 * Bq * 2, device=cuda, dtype=torch.int64) % 37 + 5
+            o = sh(idsq, lengths)
+            assert o.shape == ((Bq, 3 * D) if pooled else (idsq.numel(), D))
+            want = (idsq % 100000).float()
+            if pooled:
+                exp = want.view(3, Bq, 2).sum(-1).t().contiguous()           # [B, F] bag sums of the debug-initialised rows
+                assert torch.equal(o[:, ::D], exp)
+            else:
+                assert torch.equal(o[:, 0], want)
+            o.sum().backward()
+            sh.check()
     finally:
         if created:
             dist.destroy_process_group()
