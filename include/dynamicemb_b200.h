@@ -216,6 +216,7 @@ int demb_counter_update_n(int32_t* ref_counter, const int64_t* slot_indices, con
 
 /* measurement aid for bench.py: CUDA events around the stages of demb_backward; read returns ms of {pairs+sort, tiles, spans} */
 int demb_set_option(int option, int value);   /* A/B switches for measurements; see csrc/demb_rows.cu */
+int demb_get_option(int option);
 int demb_profile_enable(int on);
 int demb_profile_read(float* ms3);
 

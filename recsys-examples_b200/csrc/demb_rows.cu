@@ -959,6 +959,7 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 inline int nchunk_of(int D) { return (D / 4 + 31) / 32; }
 
 // bench.py's roofline needs per-kernel device time of the multi-kernel backward: optional CUDA events around its stages.
+int g_dev_opts[8] = {1, 1, 1, 1, 1, 1, 1, 1};   // demb_set_option(2..7): development toggles read by other translation units (demb_get_option)
 bool g_bwd_tma = false;         // demb_set_option(1, v): gradient rows of the backward staged through shared memory (1) or registers (0, default:
                                 // measured 0.293 ms against 0.367 ms — 12 resident warps cannot hide the per-segment row read-modify-write chain)
 int g_probe_kernel = 1;         // demb_set_option(0, v): 1 = one probe + copy pipeline per warp (default), 2 = specialised probe / copy warps (measured slower), 0 = round-1 thread-per-key probe
@@ -1223,8 +1224,11 @@ int demb_backward_apply(float* values, int64_t value_dim, int emb_dim, int64_t n
 int demb_set_option(int option, int value) {
   if (option == 0) { g_probe_kernel = value; return 0; }
   if (option == 1) { g_bwd_tma = value != 0; return 0; }
+  if (option >= 2 && option < 8) { g_dev_opts[option] = value; return 0; }
   return DEMB_ERR_ARG;
 }
+
+int demb_get_option(int option) { return (option >= 2 && option < 8) ? g_dev_opts[option] : -1; }
 
 int demb_profile_enable(int on) {
   if (on && !g_prof_ev[0]) for (int i = 0; i < 4; ++i) if (cudaEventCreate(&g_prof_ev[i]) != cudaSuccess) return DEMB_ERR_ARG;

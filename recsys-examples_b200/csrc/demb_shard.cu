@@ -72,7 +72,7 @@ __device__ __forceinline__ void owner_of(uint64_t key, int dist_type, int64_t bl
 }
 
 struct RouteArgs {
-  Shard s;
+  Shard s; int per_id_atomics;
   const uint64_t* ukeys; const int64_t* utids; const int64_t* n_u;   // unique ids grouped by table, device count
   int64_t n_max;
   const int32_t* dist_type; const int64_t* block_sizes;               // per table
@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(kRouteTile) route_count_kernel(RouteArgs a) {
     const int t = a.utids ? (int)a.utids[u] : 0;
     uint64_t nid;
     owner_of(a.ukeys[u], a.dist_type[t], a.block_sizes[t], a.s.W, p, nid);
-    if (a.s.T > 1) atomicAdd(&pt[p * a.s.T + t], 1);
+    if (a.per_id_atomics) atomicAdd(reinterpret_cast<unsigned long long*>(a.pair_table_cnt + p * a.s.T + t), 1ull);
+    else if (a.s.T > 1) atomicAdd(&pt[p * a.s.T + t], 1);
   }
   for (int d = 0; d < a.s.W; ++d) {
     const unsigned m = __ballot_sync(0xffffffffu, p == d);
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(kRouteTile) route_count_kernel(RouteArgs a) {
   }
   __syncthreads();
   if (threadIdx.x < a.s.W) a.tile_cnt[(int64_t)blockIdx.x * a.s.W + threadIdx.x] = cnt[threadIdx.x];
+  if (a.per_id_atomics) return;
   if (a.s.T == 1) { if (threadIdx.x < a.s.W && cnt[threadIdx.x]) atomicAdd(reinterpret_cast<unsigned long long*>(a.pair_table_cnt + threadIdx.x), (unsigned long long)cnt[threadIdx.x]); }
   else for (int i = threadIdx.x; i < a.s.W * a.s.T; i += kRouteTile) if (pt[i]) atomicAdd(reinterpret_cast<unsigned long long*>(a.pair_table_cnt + i), (unsigned long long)pt[i]);
 }
@@ -341,7 +343,7 @@ int demb_shard_route(int world, int rank, int num_tables, int emb_dim, int64_t p
   const int64_t tiles = (n_max + kRouteTile - 1) / kRouteTile;
   uint8_t* w = (uint8_t*)state;
   RouteArgs a;
-  a.s = s; a.ukeys = (const uint64_t*)unique_keys; a.utids = num_tables > 1 ? unique_table_ids : nullptr; a.n_u = n_unique_dev; a.n_max = n_max;
+  a.s = s; a.per_id_atomics = demb_get_option(2) == 0; a.ukeys = (const uint64_t*)unique_keys; a.utids = num_tables > 1 ? unique_table_ids : nullptr; a.n_u = n_unique_dev; a.n_max = n_max;
   a.dist_type = dist_type_per_table; a.block_sizes = block_size_per_table;
   a.tile_cnt = (int32_t*)w; w += align256(4 * (size_t)(tiles * world));
   a.pair_table_cnt = (int64_t*)w; w += align256(8 * (size_t)(world * num_tables));

@@ -34,7 +34,7 @@ struct TrainArgs {
   float* values; int64_t vdim; int D; const int64_t* row_base;
   const uint64_t* ukeys; const int64_t* utids; const int64_t* n_u;
   int pol; const uint64_t* table_scores; const int64_t* freq; uint64_t ts; int key_is_signed;
-  InitArgs init; const InitArgs* table_init; float state_init;   // table_init: per-table initializer (device, [T]), nullable => init
+  int full_shortcut; InitArgs init; const InitArgs* table_init; float state_init;   // table_init: per-table initializer (device, [T]), nullable => init
   int64_t* slots; int64_t* rows; int32_t* next; int32_t* touched; unsigned long long* n_touched;
   int32_t* init_list; unsigned long long* n_init;   // uniques inserted by the thread kernel: their rows are initialised by train_init_rows_kernel
 };
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kBlock) train_evict_kernel(TrainArgs a) {
     // A FULL bucket (bucket_sizes == C: the steady state) holds no Empty / Reclaim slot, so its keys are not needed to pick a victim:
     // 1 KB less to read per bucket and no first-empty search
     uint64_t kreg[4], sreg[4]; int32_t creg[4];
-    const bool full = a.bucket_sizes[b] >= C;
+    const bool full = a.full_shortcut && a.bucket_sizes[b] >= C;
     prev_full = full;
     {
       kreg[0] = kreg[1] = kreg[2] = kreg[3] = 0;
@@ -481,6 +481,7 @@ int demb_train_prefetch(void* storage, const int64_t* table_bucket_offsets, int6
   a.ukeys = (const uint64_t*)unique_keys; a.utids = num_tables > 1 ? unique_table_ids : nullptr; a.n_u = num_unique;
   a.pol = policy; a.table_scores = table_scores; a.freq = need_freq ? unique_freq : nullptr; a.ts = timestamp; a.key_is_signed = key_is_signed;
   a.init = InitArgs{init_mode, p0, p1, p2, p3, seed}; a.table_init = reinterpret_cast<const InitArgs*>(table_init); a.state_init = state_init;
+  a.full_shortcut = demb_get_option(3) != 0;
   a.slots = slots; a.rows = rows; a.next = next; a.touched = touched; a.n_touched = n_touched; a.init_list = init_list; a.n_init = n_init;
   if (bucket_capacity == kProbeC) {
     int64_t blocks = ((n + 31) / 32 + kLookupWarps - 1) / kLookupWarps;

@@ -49,7 +49,7 @@ __global__ void scratch_init_kernel(Slot* s, int64_t n) {
 }
 
 struct UArgs {
-  int64_t n_max; const int64_t* n_dev;
+  int64_t n_max; const int64_t* n_dev; int mulshift;
   const uint64_t* keys; const int64_t* range; int T;
   Slot* slots; int32_t* pslot; int32_t* slot_rank;
   const int64_t* freq_in; int need_freq;
@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(kBlock) unique_claim_kernel(UArgs a) {
       if (key == kEmptyKey) {
         p = base + size;
       } else {
-        int64_t q = (int64_t)__umul64hi(fmix64(key), (uint64_t)size);          // multiply-shift range reduction: no 64-bit modulo (~150 instructions)
+        int64_t q = a.mulshift ? (int64_t)__umul64hi(fmix64(key), (uint64_t)size)   // multiply-shift range reduction: no 64-bit modulo (~150 instructions)
+                               : (int64_t)(fmix64(key) % (uint64_t)size);
         while (true) {
           // test before the atomic: a Zipf-hot key is claimed once and then only READ (same-address atomics serialise in L2)
           unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(&a.slots[base + q].key);
@@ -252,7 +253,7 @@ int demb_segmented_unique(int64_t n, const int64_t* n_dev, const void* keys, con
   const int64_t n_tiles = (n + kTile - 1) / kTile;
   uint8_t* w = (uint8_t*)workspace;
   UArgs a;
-  a.n_max = n; a.n_dev = n_dev; a.keys = (const uint64_t*)keys; a.range = table_range; a.T = num_tables;
+  a.n_max = n; a.n_dev = n_dev; a.mulshift = demb_get_option(4) != 0; a.keys = (const uint64_t*)keys; a.range = table_range; a.T = num_tables;
   Slot* own = (Slot*)w; w += align256(sizeof(Slot) * slots);
   a.slots = scratch ? (Slot*)scratch : own;
   a.pslot = (int32_t*)w; w += align256(4 * (size_t)n);

@@ -60,6 +60,7 @@ _SIGS = {
                                   P, P, P, P, P, P, P, P, P, I64, P]),
     "demb_counter_update_n": (I32, [P, P, P, P, I64, P, I64, I32, P]),
     "demb_set_option": (I32, [I32, I32]),
+    "demb_get_option": (I32, [I32]),
     "demb_profile_enable": (I32, [I32]),
     "demb_profile_read": (I32, [P]),
     "demb_shard_layout": (I32, [I32, I64, I64, I32, P]),

@@ -503,7 +503,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         # capture ran step() on the host without executing it: undo its host-side bookkeeping, and roll the device STEP scores back too
         # (the captured add_ advances them at every replay)
         self._scores, self._optimizer.iter = host_scores, host_iter
-        return _GraphedStep(self, graph), out, loss
+        return _GraphedStep(self, graph, keepalive=(indices, offsets_i, grad_static)), out, loss
 
     # ------------------------------------------------------------------ inspection helpers (tests, dump)
     def export_keys_values(self, table_id: int = 0):
@@ -522,8 +522,10 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
 class _GraphedStep:
     """graph.replay() + the host-side bookkeeping of one training step (STEP scores, optimizer step count)."""
 
-    def __init__(self, module: BatchedDynamicEmbeddingTablesV2, graph: torch.cuda.CUDAGraph):
-        self.module, self.graph = module, graph
+    def __init__(self, module: BatchedDynamicEmbeddingTablesV2, graph: torch.cuda.CUDAGraph, keepalive=()):
+        # the graph holds RAW POINTERS of every tensor its kernels read: anything created outside the capture (offsets, converted ids)
+        # must live as long as the graph does
+        self.module, self.graph, self._keepalive = module, graph, tuple(keepalive)
 
     def replay(self) -> None:
         self.graph.replay()

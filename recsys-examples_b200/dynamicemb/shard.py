@@ -127,6 +127,7 @@ class RowWiseShardedDynamicEmbedding(nn.Module):
         self._epochs = torch.zeros(4, dtype=torch.int64, device=dev)
         self._empty = nn.Parameter(torch.empty(1, device=dev))        # gives autograd a reason to call backward
         self._prep_req = self._prep_own = None                         # side streams of the two backward sorts
+        self.prepare_sorts = 3                                         # bit 0: requester's sort, bit 1: owner's sort launched early on a side stream
 
     # ------------------------------------------------------------------ setup
     def _ensure_buffers(self, n: int) -> None:
@@ -182,7 +183,8 @@ class RowWiseShardedDynamicEmbedding(nn.Module):
             self._prep_req, self._prep_own = ext.BackwardPrep(dev), ext.BackwardPrep(dev)
         # the gradient-independent halves of both backward passes (pair list + radix sort) start now, on side streams, under the exchange
         pooled = self.pooling_mode != DynamicEmbPoolingMode.NONE
-        prep_req = ext.backward_prepare(self._prep_req, D, rev, max(n, 1)) if (train and not pooled) else None
+        _pm = self.prepare_sorts
+        prep_req = ext.backward_prepare(self._prep_req, D, rev, max(n, 1)) if (train and not pooled and (_pm & 1)) else None
         send_pos = torch.empty(n, dtype=torch.int64, device=dev)
         ug_addr = torch.empty(n, dtype=torch.int64, device=dev)
         N.check(N.launch("shard_route", 3, N.lib.demb_shard_route, W, self.rank, T, D, self._pair_cap, self._n_cap, N.ptr(self._buf.peers), N.ptr(self._err), n,
@@ -200,7 +202,7 @@ class RowWiseShardedDynamicEmbedding(nn.Module):
                          N.ptr(ids_recv), N.ptr(trange_r), N.ptr(n_recv), N.ptr(src_pos), N.ptr(dst_addr), N.ptr(self._recv_ws), self._recv_ws.numel(),
                          N.stream()), "shard_recv")
         st = m._prefetch_device_count(ids_recv, trange_r if T > 1 else None, T, n_recv, self._uscratch_own)
-        prep_own = ext.backward_prepare(self._prep_own, D, st.reverse_indices, R, n_dev=n_recv, grad_row_of=src_pos) if train else None
+        prep_own = ext.backward_prepare(self._prep_own, D, st.reverse_indices, R, n_dev=n_recv, grad_row_of=src_pos) if (train and (_pm & 2)) else None
         N.check(N.launch("gather_to_peers", 1, N.lib.demb_shard_gather_to_peers, N.ptr(m._values), m._values.stride(0), D, R, N.ptr(n_recv), N.ptr(st.rows),
                          N.ptr(st.reverse_indices), N.ptr(dst_addr), N.stream()), "gather_to_peers")
         self._barrier()
@@ -284,7 +286,7 @@ class RowWiseShardedDynamicEmbedding(nn.Module):
             out, loss = step()
         m._scores, m._optimizer.iter = host_scores, host_iter
         from .batched_dynamicemb_tables import _GraphedStep
-        return _GraphedStep(m, graph), out, loss
+        return _GraphedStep(m, graph, keepalive=(ids_static, lengths, offsets, grad_static, self)), out, loss
 
 
 class RowWiseShardedDynamicEmbeddingA2A(nn.Module):
