@@ -413,6 +413,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the no-eviction variant / cfg-5 sweep")
     ap.add_argument("--no-e2e", action="store_true", help="skip the SURVEY cfg-4 end-to-end harness (HSTU-large + DynamicEmb, ours and reference kernels)")
+    ap.add_argument("--opt", default="", help="development toggles, e.g. 5=1,2=0 (demb_set_option)")
     ap.add_argument("--ncu", action="store_true", help="wrap 2 eager steps + 1 eval lookup in cudaProfilerStart/Stop (ncu --profile-from-start off) and exit")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -428,6 +429,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from dynamicemb import _native as N
+    for kv in filter(None, args.opt.split(",")):
+        N.lib.demb_set_option(int(kv.split("=")[0]), int(kv.split("=")[1]))
 
     n_ids = args.ids
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -666,8 +669,12 @@ def main():
             pms = sorted(pev)[len(pev) // 2]
             nu_p = int(torch.unique(batches[-1][:np_ids]).numel())
             b_pool = np_ids * 8 + nu_p * (24 + 512) + Fp * Bp * 512
-            roof["pooled_lookup_forward"] = {"kernel": "forward_pool_kernel (fused probe + SUM pooling, hotness 10)", "ms": pms, "algorithmic_bytes": b_pool,
-                                             "achieved_GBps": b_pool / pms / 1e6, "frac": b_pool / pms / 1e6 / hbm, "ids": np_ids, "bags": Fp * Bp}
+            b_pool_nt = np_ids * (8 + 512) + Fp * Bp * 512            # SURVEY 8(a) accounting of gather_embedding_pooled: every id's row is read
+            roof["pooled_lookup_forward"] = {"kernel": "forward_pool_kernel (fused tile probe + SUM pooling, hotness 10)", "ms": pms, "algorithmic_bytes": b_pool,
+                                             "achieved_GBps": b_pool / pms / 1e6, "frac": b_pool / pms / 1e6 / hbm, "ids": np_ids, "bags": Fp * Bp,
+                                             "frac_counting_every_id_row": b_pool_nt / pms / 1e6 / hbm,
+                                             "note": "algorithmic_bytes counts each UNIQUE row once (hot rows are re-read from L2); the second fraction counts "
+                                                     "N_t x 512 B of row reads as SURVEY 8(a) does for gather_embedding_pooled"}
             # A/B of the three fused-lookup kernels on the same batches (option 0 of demb_set_option; 1 is the shipped default)
             variants = {}
             for opt_v, nm in ((0, "round-1 thread-per-key probe (forward_seq_tma_kernel)"), (2, "specialised probe / copy warps (forward_seq_probe2_kernel)"),

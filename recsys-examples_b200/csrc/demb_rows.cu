@@ -959,7 +959,8 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 inline int nchunk_of(int D) { return (D / 4 + 31) / 32; }
 
 // bench.py's roofline needs per-kernel device time of the multi-kernel backward: optional CUDA events around its stages.
-int g_dev_opts[8] = {1, 1, 1, 1, 1, 1, 1, 1};   // demb_set_option(2..7): development toggles read by other translation units (demb_get_option)
+int g_dev_opts[8] = {1, 1, 1, 1, 1, 0, 1, 1};   // [2] route histogram in smem, [3] full-bucket eviction shortcut, [4] multiply-shift in unique, [5] TMA-staged gather_to_peers
+int g_dev_opts_pad_;  //   // demb_set_option(2..7): development toggles read by other translation units (demb_get_option)
 bool g_bwd_tma = false;         // demb_set_option(1, v): gradient rows of the backward staged through shared memory (1) or registers (0, default:
                                 // measured 0.293 ms against 0.367 ms — 12 resident warps cannot hide the per-segment row read-modify-write chain)
 int g_probe_kernel = 1;         // demb_set_option(0, v): 1 = one probe + copy pipeline per warp (default), 2 = specialised probe / copy warps (measured slower), 0 = round-1 thread-per-key probe

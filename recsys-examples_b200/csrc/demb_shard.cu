@@ -20,6 +20,7 @@
 #include "../../include/dynamicemb_b200.h"
 #include "demb_common.cuh"
 #include "demb_scan.cuh"
+#include "sm100_ptx.cuh"
 
 #include <string.h>
 
@@ -278,6 +279,56 @@ __global__ void __launch_bounds__(256) gather_to_peers_kernel(const float* __res
   }
 }
 
+// The same copy with the rows STAGED THROUGH SHARED MEMORY by bulk async copies: 32 cp.async.bulk loads (value table -> stage), then 32
+// cp.async.bulk stores (stage -> the requester's rows_back, peer memory): the copy engine keeps many more NVLink writes in flight than
+// the register version's 8 rows per warp.  One persistent CTA per SM, 12 warps x 16 KB.
+constexpr int kG2PWarps = 12;
+__global__ void __launch_bounds__(kG2PWarps * 32, 1) gather_to_peers_tma_kernel(const float* __restrict__ values, int64_t vdim, int D, int64_t n_max,
+                                                                             const int64_t* __restrict__ n_dev, const int64_t* __restrict__ rows,
+                                                                             const int64_t* __restrict__ inverse, const int64_t* __restrict__ dst_addr,
+                                                                             int warps_per_block) {
+  extern __shared__ __align__(128) uint8_t stage_raw[];
+  __shared__ uint64_t bars[kG2PWarps];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  if (wib >= warps_per_block) return;
+  int64_t n = *n_dev; n = n < n_max ? n : n_max;
+  const uint32_t row_bytes = (uint32_t)D * 4u;
+  uint8_t* buf = stage_raw + (size_t)wib * 32u * row_bytes;
+  if (lane == 0) { sm100::mbar_init(&bars[wib], 1); sm100::fence_barrier_init(); }
+  __syncwarp();
+  uint32_t parity = 0;
+  const int64_t tiles = (n + 31) >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * warps_per_block;
+  for (int64_t tile = (int64_t)blockIdx.x * warps_per_block + wib; tile < tiles; tile += wstride) {
+    const int64_t base = tile << 5;
+    const int cnt = (int)((n - base) < 32 ? (n - base) : 32);
+    int64_t row = -1, dst = 0;
+    if (lane < cnt) { row = rows[inverse[base + lane]]; dst = dst_addr[base + lane]; }
+    const unsigned found = __ballot_sync(0xffffffffu, row >= 0);
+    if (lane == 0) {
+      sm100::bulk_wait_read0();                                  // the previous tile's stores have finished reading the stage
+      sm100::mbar_arrive_expect_tx(&bars[wib], (uint32_t)__popc(found) * row_bytes);
+    }
+    __syncwarp();
+    if (row >= 0) {
+      sm100::bulk_load(buf + (size_t)lane * row_bytes, values + row * vdim, row_bytes, &bars[wib]);
+    } else if (lane < cnt) {
+      float4* d = reinterpret_cast<float4*>(buf + (size_t)lane * row_bytes);
+      for (int c = 0; c < (D >> 2); ++c) d[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    sm100::mbar_wait(&bars[wib], parity);
+    parity ^= 1;
+    sm100::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane < cnt && dst) sm100::bulk_store(reinterpret_cast<void*>(dst), buf + (size_t)lane * row_bytes, row_bytes);
+    sm100::bulk_commit();                                          // every lane commits its own group (bulk_wait_read0 above is lane 0's)
+    // the other lanes must also have their stores drained before the stage is overwritten: wait per lane here (reads only)
+    sm100::bulk_wait_read0();
+    __syncwarp();
+  }
+  sm100::bulk_wait0();
+}
+
 // flag exchange barrier: every rank bumps its epoch, stores it into flag[channel][me] of every peer and waits until its own
 // flag[channel][*] all carry that epoch.  Writes of earlier kernels of this stream (to peers) are ordered before the signal.
 __global__ void peer_barrier_kernel(Shard s, int channel, unsigned long long* epochs) {
@@ -391,7 +442,18 @@ int demb_shard_gather_to_peers(const float* values, int64_t value_dim, int emb_d
   if (n_max <= 0) return 0;
   int64_t blocks = ((n_max + 31) / 32 + 7) / 8;
   const int64_t cap = (int64_t)sm_count() * 8;
-  gather_to_peers_kernel<8><<<(int)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream>>>(values, value_dim, emb_dim, n_max, n_dev, rows, inverse, dst_addr);
+  const size_t stage = 32u * (size_t)emb_dim * 4u;
+  int tw = (int)((200u * 1024u) / stage); if (tw > kG2PWarps) tw = kG2PWarps;
+  if (demb_get_option(5) != 0 && tw >= 2) {
+    static std::atomic<int> configured[kMaxDevices];
+    cudaError_t ce = once_per_device(configured, [] { return cudaFuncSetAttribute(gather_to_peers_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    if (ce != cudaSuccess) return -(int)ce;
+    int64_t tb = ((n_max + 31) / 32 + tw - 1) / tw;
+    if (tb > sm_count()) tb = sm_count();
+    gather_to_peers_tma_kernel<<<(int)tb, kG2PWarps * 32, (size_t)tw * stage, (cudaStream_t)stream>>>(values, value_dim, emb_dim, n_max, n_dev, rows, inverse, dst_addr, tw);
+  } else {
+    gather_to_peers_kernel<8><<<(int)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream>>>(values, value_dim, emb_dim, n_max, n_dev, rows, inverse, dst_addr);
+  }
   DEMB_CHECK_LAST();
   return 0;
 }

@@ -232,7 +232,7 @@ def train_prefetch(table_storage, table_bucket_offsets, bucket_capacity, bucket_
     nu = torch.zeros(1, dtype=torch.int64, device=dev)
     ws = N.workspace(N.lib.demb_train_prefetch_workspace_bytes(n, num_tables), dev)
     p0, p1, p2, p3 = init_params
-    N.check(N.launch("train_prefetch", 6, N.lib.demb_train_prefetch, N.ptr(table_storage), N.ptr(table_bucket_offsets), bucket_capacity, num_scores,
+    N.check(N.launch("train_prefetch", 8, N.lib.demb_train_prefetch, N.ptr(table_storage), N.ptr(table_bucket_offsets), bucket_capacity, num_scores,
                      N.ptr(bucket_sizes), N.ptr(ref_counter), N.ptr(bucket_heads), N.ptr(values), values.stride(0), emb_dim, N.ptr(row_base), n,
                      N.ptr(n_dev), N.ptr(keys.contiguous()), N.ptr(table_range), num_tables, N.ptr(_i64(freq_in)), int(policy), N.ptr(table_scores), int(timestamp),
                      1 if keys.dtype == torch.int64 else 0, int(init_mode), float(p0), float(p1), float(p2), float(p3), int(seed), N.ptr(table_init),
@@ -388,7 +388,7 @@ def backward_prepare(prep: BackwardPrep, emb_dim: int, inverse: torch.Tensor, nu
     ws = torch.empty(N.lib.demb_backward_workspace_bytes(n, emb_dim), dtype=torch.uint8, device=inverse.device)
     prep.stream.wait_stream(cur)
     with torch.cuda.stream(prep.stream):
-        N.check(N.launch("backward_prepare", 2, N.lib.demb_backward_sort, emb_dim, n, N.ptr(inverse), int(num_unique_bound), None, 0, 0, -1,
+        N.check(N.launch("backward_prepare", 7, N.lib.demb_backward_sort, emb_dim, n, N.ptr(inverse), int(num_unique_bound), None, 0, 0, -1,
                          N.ptr(n_dev), N.ptr(grad_row_of), N.ptr(ws), ws.numel(), N.stream()), "backward_sort")
         done = torch.cuda.Event()
         done.record(prep.stream)
@@ -419,7 +419,7 @@ def backward(values, emb_dim, inverse, num_unique_bound, rows, grads, *, offsets
         return ug
     ws_bytes = N.lib.demb_backward_workspace_bytes(n, emb_dim)
     ws = N.workspace(ws_bytes, dev)
-    N.check(N.launch("backward", 3, N.lib.demb_backward, N.ptr(values), vstride, emb_dim, n, N.ptr(inverse),
+    N.check(N.launch("backward", 10, N.lib.demb_backward, N.ptr(values), vstride, emb_dim, n, N.ptr(inverse),
                                 int(num_unique_bound), N.ptr(rows), N.ptr(grads), gstride, N.ptr(_i64(offsets)), batch_size, num_features,
                                 combiner, int(opt_type), lr, eps, beta1, beta2, weight_decay, bc1, bc2, N.ptr(ug), N.ptr(n_dev), N.ptr(grad_row_of),
                                 N.ptr(unique_grad_addr), N.ptr(ws), ws.numel(), N.stream()), "backward")
