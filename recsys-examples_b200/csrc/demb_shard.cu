@@ -320,7 +320,11 @@ __global__ void __launch_bounds__(kG2PWarps * 32, 1) gather_to_peers_tma_kernel(
     parity ^= 1;
     sm100::fence_proxy_async_smem();
     __syncwarp();
-    if (lane < cnt && dst) sm100::bulk_store(reinterpret_cast<void*>(dst), buf + (size_t)lane * row_bytes, row_bytes);
+    // consecutive received ids of one source go to consecutive rows of that source's rows_back: the common case is ONE 16-KB store per tile
+    const int64_t dst0 = __shfl_sync(0xffffffffu, dst, 0);
+    const bool contig = dst0 != 0 && __all_sync(0xffffffffu, lane >= cnt || dst == dst0 + (int64_t)lane * row_bytes);
+    if (contig) { if (lane == 0) sm100::bulk_store(reinterpret_cast<void*>(dst0), buf, (uint32_t)cnt * row_bytes); }
+    else if (lane < cnt && dst) sm100::bulk_store(reinterpret_cast<void*>(dst), buf + (size_t)lane * row_bytes, row_bytes);
     sm100::bulk_commit();                                          // every lane commits its own group (bulk_wait_read0 above is lane 0's)
     // the other lanes must also have their stores drained before the stage is overwritten: wait per lane here (reads only)
     sm100::bulk_wait_read0();
