@@ -678,6 +678,7 @@ def main():
             # A/B of the three fused-lookup kernels on the same batches (option 0 of demb_set_option; 1 is the shipped default)
             variants = {}
             for opt_v, nm in ((0, "round-1 thread-per-key probe (forward_seq_tma_kernel)"), (2, "specialised probe / copy warps (forward_seq_probe2_kernel)"),
+                              (3, "12 copy + 20 small probe warps (forward_seq_probe3_kernel<20>)"), (4, "12 copy + 12 small probe warps (forward_seq_probe3_kernel<12>)"),
                               (1, "one probe+copy pipeline per warp (forward_seq_probe_kernel, default)")):
                 N.lib.demb_set_option(0, opt_v)
                 tv = []

@@ -153,6 +153,57 @@ __device__ __forceinline__ int tile_probe_finish(const Table& t, const ProbeKey&
   return slot_sm[lane];
 }
 
+// The same probe for warps that must stay SMALL (64 registers: 32 warps per SM): nothing is carried between tiles; the eight steps
+// run as two halves of four (digest chunks -> masks -> first candidate keys -> compare), and the pointers are re-derived by shuffles
+// instead of being kept.  Two dependent round trips per half; meant for many resident warps, each behind an L2 prefetch of its lines.
+__device__ __forceinline__ int tile_probe_small(const Table& t, const ProbeKey& p, int* slot_sm, int lane) {
+  slot_sm[lane] = -1;
+  __syncwarp();
+  const uint32_t want = (uint32_t)digest_of(hash63(p.key)) * 0x01010101u;
+  const uint64_t my_bucket = p.valid ? reinterpret_cast<uint64_t>(t.bucket(p.bucket)) : 0ull;    // keys at +0, digests at +8 C
+  const int c = lane & 7;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint4 d[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t bk = __shfl_sync(0xffffffffu, my_bucket, (lane >> 3) + 4 * (4 * h + j));
+      d[j] = bk ? ld_nc_u4(reinterpret_cast<const uint8_t*>(bk) + 8 * kProbeC + c * 16) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    uint32_t m[4]; uint64_t ck[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = (lane >> 3) + 4 * (4 * h + j);
+      const uint32_t w4 = __shfl_sync(0xffffffffu, want, k);
+      const uint64_t bk = __shfl_sync(0xffffffffu, my_bucket, k);
+      m[j] = bk ? match16(d[j], w4) : 0u;
+      ck[j] = 0;
+      if (m[j]) ck[j] = ld_u64_volatile_nc(reinterpret_cast<const uint64_t*>(bk) + c * 16 + __ffs(m[j]) - 1);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = (lane >> 3) + 4 * (4 * h + j);
+      const uint64_t key_k = __shfl_sync(0xffffffffu, p.key, k);
+      const uint64_t bk = __shfl_sync(0xffffffffu, my_bucket, k);
+      if (m[j]) {
+        if (ck[j] == key_k) slot_sm[k] = c * 16 + __ffs(m[j]) - 1;
+        else if (ck[j] != kEmptyKey) {               // further digest matches inside the same 16 slots (rare): one dependent load each
+          uint32_t mm = m[j] & (m[j] - 1);
+          while (mm) {
+            const int pos = c * 16 + __ffs(mm) - 1;
+            mm &= mm - 1;
+            const uint64_t kk = reinterpret_cast<const uint64_t*>(bk)[pos];
+            if (kk == key_k) { slot_sm[k] = pos; break; }
+            if (kk == kEmptyKey) break;
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  return slot_sm[lane];
+}
+
 // all 32 lanes; returns the position (0..127) of this lane's key in its bucket, or -1.  slot_sm: 32 ints of the warp's shared memory.
 __device__ __forceinline__ int tile_probe(const Table& t, const ProbeKey& p, const DigRegs& dig, int* slot_sm, int lane) {
   slot_sm[lane] = -1;

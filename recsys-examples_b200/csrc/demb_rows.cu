@@ -362,6 +362,106 @@ __global__ void __launch_bounds__((kCopyWarps + kProbeWarps) * 32, 1) forward_se
   if (lane == 0) sm100::bulk_wait0();
 }
 
+// ---- third variant: the specialised layout again, but with MANY small probe warps instead of a few large ones.  probe2's eight probe
+// warps resolve ~1.5 tiles/us per SM — exactly the rate the twelve copy warps consume at gather speed, so the copy side starved.  Here a
+// CTA is 12 copy warps + 20 probe warps = 1024 threads at 64 registers (the whole register file, no setmaxnreg); a probe warp carries
+// nothing between tiles except the next tile's hashed keys, whose digest lines it has already pulled into L2 (prefetch.global.L2), and
+// probes with tile_probe_small.  Ring: tile i of the CTA -> slot i % 60, produced by probe warp i % 20, consumed by copy warp i % 12;
+// 60 is a multiple of both, so every slot has ONE producer and ONE consumer, each of which sees the slot's barrier phases in order (with
+// a ring of 32 two different probe warps shared a slot, one could overtake the other by a whole phase and the parity wait aliased: hang).
+template <int kProbe3Warps> struct Ring3 { static constexpr int value = kProbe3Warps == 20 ? 60 : 48; };   // a multiple of both warp counts
+template <int kProbe3Warps>
+struct Probe3Smem {
+  static constexpr int kRing3 = Ring3<kProbe3Warps>::value; uint64_t bar_row[kCopyWarps]; uint64_t full[kRing3]; uint64_t empty[kRing3]; int slot[kProbe3Warps][32]; int64_t rowq[kRing3][32]; };
+template <int kProbe3Warps>
+__global__ void __launch_bounds__((kCopyWarps + kProbe3Warps) * 32, 1) forward_seq_probe3_kernel(RowSrc s, const float* __restrict__ values, int64_t vdim, int D,
+                                                                                               int64_t n, float* __restrict__ out, float absent_value) {
+  constexpr int kRing3 = Ring3<kProbe3Warps>::value;
+  static_assert(kRing3 % kProbe3Warps == 0 && kRing3 % kCopyWarps == 0, "a ring slot must always have the same producer and the same consumer");
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ Probe3Smem<kProbe3Warps> sm;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t row_bytes = (uint32_t)D * 4u;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kCopyWarps; ++i) sm100::mbar_init(&sm.bar_row[i], 1);
+    for (int i = 0; i < kRing3; ++i) { sm100::mbar_init(&sm.full[i], 1); sm100::mbar_init(&sm.empty[i], 1); }
+    sm100::fence_barrier_init();
+  }
+  __syncthreads();
+  const int64_t tiles = (n + 31) >> 5;
+  const int64_t my_tiles = tiles > (int64_t)blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // tiles blockIdx.x + i * gridDim.x
+  if (wib >= kCopyWarps) {
+    // ------------------------------------------------------------------ probe warps (producers)
+    const int p = wib - kCopyWarps;
+    TableCache tc = empty_table_cache();
+    auto load_id = [&](int64_t i) -> uint64_t {
+      const int64_t id = ((((int64_t)blockIdx.x + i * gridDim.x)) << 5) + lane;
+      return (i < my_tiles && id < n) ? s.keys[id] : kEmptyKey;
+    };
+    auto key_of = [&](int64_t i, uint64_t key) -> ProbeKey {
+      const int64_t id = ((((int64_t)blockIdx.x + i * gridDim.x)) << 5) + lane;
+      if (i >= my_tiles || id >= n) return ProbeKey{0, 0, 0, 0, false};
+      const int tid = (s.T > 1 && s.table_range) ? table_of(s.table_range, s.T, id) : 0;
+      const ProbeKey k = make_probe_key(s.t, key, tid, tc);
+      if (k.valid) asm volatile("prefetch.global.L2 [%0];" ::"l"(s.t.digests(s.t.bucket(k.bucket))));
+      return k;
+    };
+    ProbeKey k0 = key_of(p, load_id(p));
+    uint64_t id1 = load_id(p + kProbe3Warps);
+    for (int64_t i = p; i < my_tiles; i += kProbe3Warps) {
+      const ProbeKey k1 = key_of(i + kProbe3Warps, id1);          // next tile: hash, digest lines towards L2
+      id1 = load_id(i + 2 * kProbe3Warps);
+      const int pos = tile_probe_small(s.t, k0, sm.slot[p], lane);
+      const int64_t id = ((((int64_t)blockIdx.x + i * gridDim.x)) << 5) + lane;
+      const int64_t slot = pos >= 0 ? k0.slot_base + pos : -1;
+      if (id < n) { if (s.founds) s.founds[id] = slot >= 0; if (s.slots_out) s.slots_out[id] = slot; }
+      const int64_t row = slot < 0 ? -1 : (s.row_base ? s.row_base[k0.tid] : 0) + slot;
+      const int q = (int)(i % kRing3);
+      const uint32_t use = (uint32_t)(i / kRing3);                // how many times this slot has been used before
+      if (use > 0) sm100::mbar_wait(&sm.empty[q], (use - 1) & 1u);
+      sm.rowq[q][lane] = row;
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(&sm.full[q]);
+      k0 = k1;
+    }
+    return;
+  }
+  // -------------------------------------------------------------------- copy warps (consumers): the gather kernel's loop
+  uint8_t* buf = smem_raw + (size_t)wib * 32u * row_bytes;
+  uint32_t par_row = 0;
+  for (int64_t i = wib; i < my_tiles; i += kCopyWarps) {
+    const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
+    const int64_t base = tile << 5;
+    const int cnt = (int)((n - base) < 32 ? (n - base) : 32);
+    const int q = (int)(i % kRing3);
+    sm100::mbar_wait(&sm.full[q], (uint32_t)(i / kRing3) & 1u);
+    const int64_t row = lane < cnt ? sm.rowq[q][lane] : -1;
+    __syncwarp();
+    if (lane == 0) sm100::mbar_arrive(&sm.empty[q]);
+    const unsigned found = __ballot_sync(0xffffffffu, row >= 0);
+    if (lane == 0) {
+      sm100::bulk_wait_read0();
+      sm100::mbar_arrive_expect_tx(&sm.bar_row[wib], (uint32_t)__popc(found) * row_bytes);
+    }
+    __syncwarp();
+    if (row >= 0) {
+      sm100::bulk_load(buf + (size_t)lane * row_bytes, values + row * vdim, row_bytes, &sm.bar_row[wib]);
+    } else if (lane < cnt) {
+      float4* d = reinterpret_cast<float4*>(buf + (size_t)lane * row_bytes);
+      for (int c = 0; c < (D >> 2); ++c) d[c] = make_float4(absent_value, absent_value, absent_value, absent_value);
+    }
+    sm100::mbar_wait(&sm.bar_row[wib], par_row);
+    par_row ^= 1;
+    sm100::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      sm100::bulk_store(out + base * (int64_t)D, buf, (uint32_t)cnt * row_bytes);
+      sm100::bulk_commit();
+    }
+  }
+  if (lane == 0) sm100::bulk_wait0();
+}
+
 // ---- forward, pooled mode: ids feature-major (offsets index f*B+b, lookup_forward.cu:53-59);
 // out[b, f*D : (f+1)*D] = SUM or MEAN of the bag's rows, fp32 accumulation in id order (lookup_kernel.cuh:901-962).
 // A13 + A11 + A4 fused.  A warp takes `bpw` consecutive bags per pass (bpw ~ 32 / average bag length, chosen by the host):
@@ -1033,6 +1133,23 @@ static int launch_seq_probe2(const RowSrc& s, const float* values, int64_t value
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }
+static int launch_seq_probe3(int pw, const RowSrc& s, const float* values, int64_t value_dim, int emb_dim, int64_t n, float* out, float absent_value,
+                             cudaStream_t stream) {
+  const int smem = kCopyWarps * 32 * emb_dim * 4;
+  static std::atomic<int> configured[kMaxDevices];
+  cudaError_t ce = once_per_device(configured, [] {
+    cudaError_t e = cudaFuncSetAttribute(forward_seq_probe3_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return e != cudaSuccess ? e : cudaFuncSetAttribute(forward_seq_probe3_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  });
+  if (ce != cudaSuccess) return -(int)ce;
+  const int64_t tiles = (n + 31) / 32;
+  int64_t blocks = (tiles + kCopyWarps - 1) / kCopyWarps;
+  if (blocks > sm_count()) blocks = sm_count();
+  if (pw == 20) forward_seq_probe3_kernel<20><<<(int)blocks, (kCopyWarps + 20) * 32, smem, stream>>>(s, values, value_dim, emb_dim, n, out, absent_value);
+  else forward_seq_probe3_kernel<12><<<(int)blocks, (kCopyWarps + 12) * 32, smem, stream>>>(s, values, value_dim, emb_dim, n, out, absent_value);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}
 static int check_dims(int D, int64_t vdim) { return (D <= 0 || (D & 3) || D > 128 * kMaxChunks || (vdim & 3) || vdim < D) ? DEMB_ERR_ARG : 0; }
 
 int demb_lookup_forward(void* storage, const int64_t* table_bucket_offsets, int64_t bucket_capacity, int num_scores, const float* values,
@@ -1044,6 +1161,10 @@ int demb_lookup_forward(void* storage, const int64_t* table_bucket_offsets, int6
            nullptr, nullptr, founds, slots_out, nullptr};
   if (combiner < 0) {
     if (n <= 0) return 0;
+    if (out_dtype == DEMB_F32 && bucket_capacity == kProbeC && g_probe_kernel == 4 && kCopyWarps * 32 * emb_dim * 4 <= 200 * 1024)
+      return launch_seq_probe3(12, s, values, value_dim, emb_dim, n, (float*)out, absent_value, (cudaStream_t)stream);
+    if (out_dtype == DEMB_F32 && bucket_capacity == kProbeC && g_probe_kernel == 3 && kCopyWarps * 32 * emb_dim * 4 <= 200 * 1024)
+      return launch_seq_probe3(20, s, values, value_dim, emb_dim, n, (float*)out, absent_value, (cudaStream_t)stream);
     if (out_dtype == DEMB_F32 && bucket_capacity == kProbeC && g_probe_kernel == 2 && kCopyWarps * 32 * emb_dim * 4 <= 200 * 1024)
       return launch_seq_probe2(s, values, value_dim, emb_dim, n, (float*)out, absent_value, (cudaStream_t)stream);
     if (out_dtype == DEMB_F32 && bucket_capacity == kProbeC && emb_dim <= 1024 && g_probe_kernel)

@@ -87,6 +87,39 @@ def test_fused_lookup_forward_sequence(cuda, D, out_dtype):
     assert torch.equal(out.cpu(), exp.to(out_dtype))       # pure copy (+ one rounding for bf16): bit-exact
 
 
+@pytest.mark.parametrize("n_per_table", [3300, 17, 600000])   # the last: > 2 ring revolutions per CTA in the specialised layouts
+def test_fused_lookup_kernel_variants_agree(cuda, n_per_table):
+    """demb_set_option(0, v): every fused-lookup kernel (round-1 thread-per-key probe, per-warp pipeline = default, the specialised
+    probe / copy layouts) must return the same rows, founds and slots; a ragged tail (n % 32 != 0), two tables, absent ids."""
+    from dynamicemb import dynamicemb_extensions as ext
+    from dynamicemb import _native as N
+    D = 128
+    rng = np.random.default_rng(n_per_table)
+    t, values, keys, tids, slots = _filled_table(cuda, rng, [128 * 40, 128 * 24], D, 4, 5000)
+    ids = []
+    for tb in range(2):
+        mine = keys[(tids == tb) & (slots >= 0)]
+        a = np.concatenate([mine[rng.integers(0, mine.size, size=n_per_table)], rng.integers(1 << 41, 1 << 42, size=n_per_table // 10 + 1, dtype=np.int64)])
+        rng.shuffle(a); ids.append(a)
+    trange = torch.tensor([0, ids[0].size, ids[0].size + ids[1].size], dtype=torch.int64, device=cuda)
+    idt = torch.from_numpy(np.concatenate(ids)).to(cuda)
+    res = {}
+    try:
+        for v in (1, 0, 2, 3, 4):
+            N.lib.demb_set_option(0, v)
+            out, founds, sl = ext.lookup_forward(t.table_storage_, t.table_bucket_offsets_, t.bucket_capacity_, values, D, idt, row_base=t.row_base_,
+                                                 table_range=trange, num_tables=2, out_dtype=torch.float32, absent_value=0.25, want_founds=True)
+            torch.cuda.synchronize()
+            res[v] = (out.clone(), founds.clone(), sl.clone())
+    finally:
+        N.lib.demb_set_option(0, 1)
+    assert int(res[1][1].sum()) >= 2 * n_per_table
+    for v in (0, 2, 3, 4):
+        assert torch.equal(res[v][2], res[1][2]), v
+        assert torch.equal(res[v][1], res[1][1]), v
+        assert torch.equal(res[v][0], res[1][0]), v
+
+
 @pytest.mark.parametrize("combiner", [0, 1])
 @pytest.mark.parametrize("D", [128, 64])
 def test_fused_lookup_forward_pooled(cuda, combiner, D):

@@ -1,6 +1,7 @@
-"""GPU, BASELINE.json's full sizes: size-independent properties instead of an oracle replay (the CPU oracle cannot finish 2^20 ids or
-B=32 x S=4096 attention in seconds) — round trips, idempotence, linearity, causality, checksums against plain torch ops, and, when the
-staged reference kernels are present (baseline/_ref/, travels with the snapshot, never /root/reference), agreement with the reference's
+"""GPU, BASELINE.json's full sizes: size-independent properties — round trips, idempotence, linearity, causality, checksums against plain
+torch ops (the direct ORACLE replays at 2^20 ids — fused prefetch with eviction, pooled forward, Adagrad update — live in
+tests/test_train_oracle_gpu.py; the eager attention oracle cannot hold B=32 x S=4096 fp32 scores), and, when the staged reference kernels
+are present (baseline/_ref/, travels with the snapshot, never /root/reference), agreement with the reference's
 own Blackwell HSTU kernels on the identical inputs."""
 import math
 import os
