@@ -414,6 +414,7 @@ def main():
     ap.add_argument("--no-variants", action="store_true", help="skip the no-eviction variant / cfg-5 sweep")
     ap.add_argument("--no-e2e", action="store_true", help="skip the SURVEY cfg-4 end-to-end harness (HSTU-large + DynamicEmb, ours and reference kernels)")
     ap.add_argument("--opt", default="", help="development toggles, e.g. 5=1,2=0 (demb_set_option)")
+    ap.add_argument("--no-overlap-hits", action="store_true", help="N>1: copy the rows back to the requesters only after the whole owner prefetch (A/B)")
     ap.add_argument("--ncu", action="store_true", help="wrap 2 eager steps + 1 eval lookup in cudaProfilerStart/Stop (ncu --profile-from-start off) and exit")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -454,6 +455,7 @@ def main():
         # spreads ~n_unique/W to each), and an owner accepts at most n_ids in total
         model = RowWiseShardedDynamicEmbedding(m, None, dist_type="hash_roundrobin", use_index_dedup=True, max_ids_per_step=n_ids,
                                                pair_capacity=n_ids // 2, recv_capacity=n_ids)
+        model.overlap_hits = not args.no_overlap_hits
         samples = 4096                     # KJT shape per rank: one feature, 4096 samples x 256 ids (HSTU-like jagged sequences)
         lengths = torch.full((samples,), n_ids // samples, dtype=torch.int64, device=dev)
         call = lambda ids: model(ids, lengths)
@@ -679,6 +681,7 @@ def main():
             variants = {}
             for opt_v, nm in ((0, "round-1 thread-per-key probe (forward_seq_tma_kernel)"), (2, "specialised probe / copy warps (forward_seq_probe2_kernel)"),
                               (3, "12 copy + 20 small probe warps (forward_seq_probe3_kernel<20>)"), (4, "12 copy + 12 small probe warps (forward_seq_probe3_kernel<12>)"),
+                              (5, "per-warp pipeline, second-generation tile probe (forward_seq_probe_kernel<2>)"),
                               (1, "one probe+copy pipeline per warp (forward_seq_probe_kernel, default)")):
                 N.lib.demb_set_option(0, opt_v)
                 tv = []

@@ -210,6 +210,11 @@ int demb_train_prefetch(void* storage, const int64_t* table_bucket_offsets, int6
                         void* unique_keys, int64_t* reverse_indices, int64_t* unique_table_ids,
                         int64_t* unique_freq, int64_t* slots, int64_t* rows, int64_t* num_unique, void* unique_scratch /* nullable, see
                         demb_segmented_unique */, void* workspace, int64_t workspace_bytes, void* stream);
+/* One-shot hook for the NEXT demb_train_prefetch issued by the calling host thread: hit_flags[u] (device int8, sized like the outputs,
+ * nullable) receives 1 for every unique key the lookup stage found, and `event` (cudaEvent_t, nullable) is recorded on the prefetch's
+ * stream right after that stage: rows[] / slots[] of found keys are final and pinned from there on.  (No reference counterpart: the
+ * reference's prefetch synchronises with the host between its stages.) */
+int demb_train_prefetch_hook(void* event, int8_t* hit_flags);
 /* demb_counter_update with the element count read from device memory (*n_device <= n_max) */
 int demb_counter_update_n(int32_t* ref_counter, const int64_t* slot_indices, const int64_t* table_ids, const int64_t* table_bucket_offsets,
                           int64_t bucket_capacity, const int64_t* n_device, int64_t n_max, int delta, void* stream);
@@ -252,6 +257,11 @@ int demb_shard_recv(int world, int rank, int num_tables, int emb_dim, int64_t pa
                     int64_t workspace_bytes, void* stream);
 int demb_shard_gather_to_peers(const float* values, int64_t value_dim, int emb_dim, int64_t n_max, const int64_t* n_dev, const int64_t* rows,
                                const int64_t* inverse, const int64_t* dst_addr, void* stream);
+/* the same copy restricted by per-UNIQUE-id flags (see demb_train_prefetch_hook): part 1 = ids whose key the prefetch's lookup stage
+ * found (may run on another stream once the hook's event has fired, concurrently with insert / evict / row init), part 2 = the others
+ * (after the prefetch), part 0 = all.  Lets the NVLink copy of the hit rows overlap the rest of the owner's prefetch. */
+int demb_shard_gather_to_peers_part(const float* values, int64_t value_dim, int emb_dim, int64_t n_max, const int64_t* n_dev, const int64_t* rows,
+                                    const int64_t* inverse, const int64_t* dst_addr, const int8_t* hit_flags, int part, void* stream);
 int demb_peer_barrier(int world, int rank, int64_t pair_cap, int64_t n_cap, int emb_dim, const int64_t* peers, int32_t* err, int channel,
                       uint64_t* epochs /* 4 x u64 local device memory, zero at start */, void* stream);
 int demb_zero_i64(int64_t* p, int64_t n, void* stream);

@@ -29,6 +29,7 @@ struct ProbeKey {
   int64_t slot_base;     // (bucket - first bucket of its table) * C: table-local slot of position 0
   int32_t tid;
   bool valid;            // key legal and table non-empty
+  uint32_t want4;        // the key's digest in all four bytes (kept so that a later pipeline stage does not hash again)
 };
 
 // bucket = (h % (nb * 128)) / 128 = (h >> 7) % nb.  A 64-bit modulo by a run-time value is ~150 dependent instructions on this GPU (no
@@ -40,7 +41,7 @@ struct TableCache { int32_t tid; int64_t bb; uint64_t nb; uint64_t magic; };
 __device__ __forceinline__ TableCache empty_table_cache() { return TableCache{-1, 0, 0, 0}; }
 
 __device__ __forceinline__ ProbeKey make_probe_key(const Table& t, uint64_t key, int tid, TableCache& tc) {
-  ProbeKey p{key, 0, 0, tid, false};
+  ProbeKey p{key, 0, 0, tid, false, 0u};
   if (key_is_valid(key)) {
     if (tc.tid != tid) {
       tc.tid = tid;
@@ -49,7 +50,9 @@ __device__ __forceinline__ ProbeKey make_probe_key(const Table& t, uint64_t key,
       tc.magic = tc.nb ? 0xFFFFFFFFFFFFFFFFull / tc.nb : 0ull;
     }
     if (tc.nb > 0) {
-      const uint64_t x = (uint64_t)hash63(key) >> 7;               // C == 128
+      const int64_t h = hash63(key);
+      p.want4 = (uint32_t)digest_of(h) * 0x01010101u;
+      const uint64_t x = (uint64_t)h >> 7;                            // C == 128
       uint64_t r = x - __umul64hi(x, tc.magic) * tc.nb;              // quotient estimate is low by at most 2
       if (r >= tc.nb) r -= tc.nb;
       if (r >= tc.nb) r -= tc.nb;
@@ -152,6 +155,142 @@ __device__ __forceinline__ int tile_probe_finish(const Table& t, const ProbeKey&
   __syncwarp();
   return slot_sm[lane];
 }
+
+// ---- second-generation tile probe (same results, fewer instructions and no exposed dependent load on the common path).  Measured on the
+// first generation (ncu source view, per tile of 32 ids): ~300 of ~1300 warp instructions were match16 (__vcmpeq4 is emulated), ~350
+// the per-step shuffles / compares / publishes of its EIGHT steps, and three tiles in four took the slow path (a second digest match
+// inside a 16-slot chunk, first candidate not the key) — a dependent key load with its full latency exposed.  Here:
+//   * FOUR lanes per line (two 16-byte pieces each: slots [16c, 16c+16) and [64+16c, 64+16c+16)), eight keys per step, FOUR steps;
+//     every warp-wide load still covers whole 32-byte sectors;
+//   * matches as a sparse 32-bit word straight from the SWAR zero-byte test ((y - 0x01..) & ~y & 0x80..: never misses a match; may flag
+//     the byte above one, which only costs a candidate whose key then does not compare equal) — no per-word gather multiply;
+//   * the first TWO candidates of every (lane, step) are loaded at once, so the slow path needs three digest matches in 32 slots with
+//     the key not among the first two (~1 tile in 10, against 3 in 4).
+// Candidates are visited in mask-bit order, not probe order; that is immaterial except for the stop-at-Empty rule, which only ever
+// applies to keys whose digest equals the empty digest (1 key in 256): those take the ordered walk in the slow path.
+struct DigRegs4 { uint4 d[4][2]; };
+struct ProbeCand4 { uint64_t key[4][2]; uint32_t mask[4]; uint32_t pos[4]; };   // pos: the two candidate positions, bytes 0 and 1
+
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t y) { return (y - 0x01010101u) & ~y & 0x80808080u; }
+// bit 8 b + w  <=>  byte b of word w of the 16-byte piece equals the byte replicated in w4  (slot 4 w + b of the piece)
+__device__ __forceinline__ uint32_t sparse16(const uint4& d, uint32_t w4) {
+  return (zero_bytes(d.x ^ w4) >> 7) | (zero_bytes(d.y ^ w4) >> 6) | (zero_bytes(d.z ^ w4) >> 5) | (zero_bytes(d.w ^ w4) >> 4);
+}
+// mask bit i of lane-quarter c -> position in the bucket: piece (i >> 2) & 1, word i & 3, byte i >> 3
+__device__ __forceinline__ int sparse_pos(int i, int c) { return ((i >> 2) & 1) * 64 + c * 16 + (i & 3) * 4 + (i >> 3); }
+
+__device__ __forceinline__ void tile_load_digests4(const Table& t, const ProbeKey& p, DigRegs4& r, int lane) {
+  const uint64_t my_line = p.valid ? reinterpret_cast<uint64_t>(t.digests(t.bucket(p.bucket))) : 0ull;
+  const int c = lane & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint64_t line = __shfl_sync(0xffffffffu, my_line, (lane >> 2) + 8 * j);
+    r.d[j][0] = line ? ld_nc_u4(reinterpret_cast<const uint8_t*>(line) + c * 16) : make_uint4(0u, 0u, 0u, 0u);
+    r.d[j][1] = line ? ld_nc_u4(reinterpret_cast<const uint8_t*>(line) + 64 + c * 16) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+__device__ __forceinline__ void tile_probe_issue4(const Table& t, const ProbeKey& p, const DigRegs4& dig, ProbeCand4& cand, int lane) {
+  const uint32_t want = p.want4;
+  const uint64_t my_keys = p.valid ? reinterpret_cast<uint64_t>(t.keys(t.bucket(p.bucket))) : 0ull;
+  const int c = lane & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = (lane >> 2) + 8 * j;             // key of the tile this lane works for in step j
+    const uint32_t w4 = __shfl_sync(0xffffffffu, want, k);
+    const uint64_t* keys_k = reinterpret_cast<const uint64_t*>(__shfl_sync(0xffffffffu, my_keys, k));
+    uint32_t u = 0;
+    cand.key[j][0] = 0; cand.key[j][1] = 0; cand.pos[j] = 0;
+    if (keys_k) {
+      u = sparse16(dig.d[j][0], w4) | (sparse16(dig.d[j][1], w4) << 4);
+      if (u) {
+        const int p0 = sparse_pos(__ffs(u) - 1, c);
+        cand.key[j][0] = ld_u64_volatile_nc(keys_k + p0);
+        cand.pos[j] = (uint32_t)p0;
+        const uint32_t u2 = u & (u - 1);
+        if (u2) {
+          const int p1 = sparse_pos(__ffs(u2) - 1, c);
+          cand.key[j][1] = ld_u64_volatile_nc(keys_k + p1);
+          cand.pos[j] |= (uint32_t)p1 << 8;
+        }
+      }
+    }
+    cand.mask[j] = u;
+  }
+}
+
+__device__ __forceinline__ int tile_probe_finish4(const Table& t, const ProbeKey& p, const ProbeCand4& cand, int* slot_sm, int lane) {
+  slot_sm[lane] = -1;
+  __syncwarp();
+  const int c = lane & 3;
+  bool more = false;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = (lane >> 2) + 8 * j;
+    const uint64_t key_k = __shfl_sync(0xffffffffu, p.key, k);
+    const uint32_t u = cand.mask[j];
+    if (u) {
+      if (cand.key[j][0] == key_k) slot_sm[k] = (int)(cand.pos[j] & 0xFFu);
+      else {
+        const uint32_t u2 = u & (u - 1);
+        if (u2) {
+          if (cand.key[j][1] == key_k) slot_sm[k] = (int)(cand.pos[j] >> 8);
+          else if (u2 & (u2 - 1)) more = true;
+        }
+      }
+    }
+  }
+  if (__any_sync(0xffffffffu, more)) {               // slow path: third and later candidates of a (lane, step), one dependent load each
+    const uint32_t want = p.want4;
+    const uint32_t emp4 = (uint32_t)empty_digest() * 0x01010101u;
+    const uint64_t my_keys = p.valid ? reinterpret_cast<uint64_t>(t.keys(t.bucket(p.bucket))) : 0ull;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = (lane >> 2) + 8 * j;
+      const uint64_t key_k = __shfl_sync(0xffffffffu, p.key, k);
+      const uint32_t w4 = __shfl_sync(0xffffffffu, want, k);
+      const uint64_t* keys_k = reinterpret_cast<const uint64_t*>(__shfl_sync(0xffffffffu, my_keys, k));
+      const uint32_t u = cand.mask[j], u2 = u & (u - 1), u3 = u2 & (u2 - 1);
+      if (u3 == 0 || cand.key[j][0] == key_k || cand.key[j][1] == key_k) continue;
+      if (w4 != emp4) {                              // no candidate can be an Empty slot: any order, until the key turns up
+        uint32_t m = u3;
+        while (m) {
+          const int pos = sparse_pos(__ffs(m) - 1, c);
+          m &= m - 1;
+          if (keys_k[pos] == key_k) { slot_sm[k] = pos; break; }
+        }
+      } else {                                       // digest == empty digest: ascending position inside each 16-slot piece, stop at Empty
+        bool done = false;
+        for (int piece = 0; piece < 2 && !done; ++piece)
+          for (int q = 0; q < 16; ++q) {             // q = 4 w + b
+            const int i = (q & 3) * 8 + piece * 4 + (q >> 2);
+            if (!((u >> i) & 1u)) continue;
+            const int pos = piece * 64 + c * 16 + q;
+            const uint64_t kk = keys_k[pos];
+            if (kk == key_k) { slot_sm[k] = pos; done = true; break; }
+            if (kk == kEmptyKey) break;
+          }
+      }
+    }
+  }
+  __syncwarp();
+  return slot_sm[lane];
+}
+
+// the two generations behind one name, for kernels templated on the probe
+template <int GEN> struct TileProbe;
+template <> struct TileProbe<1> {
+  using Dig = DigRegs; using Cand = ProbeCand;
+  static __device__ __forceinline__ void load(const Table& t, const ProbeKey& p, Dig& r, int lane) { tile_load_digests(t, p, r, lane); }
+  static __device__ __forceinline__ void issue(const Table& t, const ProbeKey& p, const Dig& d, Cand& c, int lane) { tile_probe_issue(t, p, d, c, lane); }
+  static __device__ __forceinline__ int finish(const Table& t, const ProbeKey& p, const Cand& c, int* sm, int lane) { return tile_probe_finish(t, p, c, sm, lane); }
+};
+template <> struct TileProbe<2> {
+  using Dig = DigRegs4; using Cand = ProbeCand4;
+  static __device__ __forceinline__ void load(const Table& t, const ProbeKey& p, Dig& r, int lane) { tile_load_digests4(t, p, r, lane); }
+  static __device__ __forceinline__ void issue(const Table& t, const ProbeKey& p, const Dig& d, Cand& c, int lane) { tile_probe_issue4(t, p, d, c, lane); }
+  static __device__ __forceinline__ int finish(const Table& t, const ProbeKey& p, const Cand& c, int* sm, int lane) { return tile_probe_finish4(t, p, c, sm, lane); }
+};
 
 // The same probe for warps that must stay SMALL (64 registers: 32 warps per SM): nothing is carried between tiles; the eight steps
 // run as two halves of four (digest chunks -> masks -> first candidate keys -> compare), and the pointers are re-derived by shuffles

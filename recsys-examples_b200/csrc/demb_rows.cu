@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(384) forward_seq_tma_kernel(RowSrc s, const fl
 // of the per-thread chain digest chunk -> key -> next chunk ... of the reference's probe.
 constexpr int kProbeFwdWarps = 12;
 struct ProbeFwdSmem { uint64_t bar_row[kProbeFwdWarps]; int slot[kProbeFwdWarps][32]; };
+template <int GEN>                                               // probe generation (demb_probe.cuh, TileProbe<GEN>)
 __global__ void __launch_bounds__(kProbeFwdWarps * 32) forward_seq_probe_kernel(RowSrc s, const float* __restrict__ values, int64_t vdim, int D, int64_t n,
                                                                                 float* __restrict__ out, float absent_value, int warps_per_block) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -221,20 +222,21 @@ __global__ void __launch_bounds__(kProbeFwdWarps * 32) forward_seq_probe_kernel(
     return make_probe_key(s.t, id, tid, tc);
   };
   // prologue: tile t probed completely; candidates of t+1 issued; digest lines of t+2 issued; ids of t+3 fetched
-  DigRegs dg;
-  ProbeCand cand;
+  using TP = TileProbe<GEN>;
+  typename TP::Dig dg;
+  typename TP::Cand cand;
   ProbeKey k1, k2;
   int64_t row;
   {
     const ProbeKey k0 = key_of(tile, load_id(tile));
-    tile_load_digests(s.t, k0, dg, lane);
-    tile_probe_issue(s.t, k0, dg, cand, lane);
-    row = row_of(k0, tile_probe_finish(s.t, k0, cand, sm.slot[wib], lane), tile);
+    TP::load(s.t, k0, dg, lane);
+    TP::issue(s.t, k0, dg, cand, lane);
+    row = row_of(k0, TP::finish(s.t, k0, cand, sm.slot[wib], lane), tile);
     k1 = key_of(tile + wstride, load_id(tile + wstride));
-    tile_load_digests(s.t, k1, dg, lane);
-    tile_probe_issue(s.t, k1, dg, cand, lane);
+    TP::load(s.t, k1, dg, lane);
+    TP::issue(s.t, k1, dg, cand, lane);
     k2 = key_of(tile + 2 * wstride, load_id(tile + 2 * wstride));
-    tile_load_digests(s.t, k2, dg, lane);
+    TP::load(s.t, k2, dg, lane);
   }
   uint64_t id3 = load_id(tile + 3 * wstride);
   for (; tile < tiles; tile += wstride) {
@@ -252,10 +254,10 @@ __global__ void __launch_bounds__(kProbeFwdWarps * 32) forward_seq_probe_kernel(
       float4* d = reinterpret_cast<float4*>(rowbuf + (size_t)lane * row_bytes);
       for (int c = 0; c < (D >> 2); ++c) d[c] = make_float4(absent_value, absent_value, absent_value, absent_value);
     }
-    const int64_t next_row = row_of(k1, tile_probe_finish(s.t, k1, cand, sm.slot[wib], lane), tile + wstride);   // tile t+1
-    tile_probe_issue(s.t, k2, dg, cand, lane);                                                                    // tile t+2
+    const int64_t next_row = row_of(k1, TP::finish(s.t, k1, cand, sm.slot[wib], lane), tile + wstride);   // tile t+1
+    TP::issue(s.t, k2, dg, cand, lane);                                                                    // tile t+2
     const ProbeKey k3 = key_of(tile + 3 * wstride, id3);                                                           // tile t+3
-    tile_load_digests(s.t, k3, dg, lane);
+    TP::load(s.t, k3, dg, lane);
     id3 = load_id(tile + 4 * wstride);                                                                             // tile t+4
     sm100::mbar_wait(&sm.bar_row[wib], par_row);                  // the one exposed wait
     par_row ^= 1;
@@ -1059,7 +1061,8 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 inline int nchunk_of(int D) { return (D / 4 + 31) / 32; }
 
 // bench.py's roofline needs per-kernel device time of the multi-kernel backward: optional CUDA events around its stages.
-int g_dev_opts[8] = {1, 1, 1, 1, 1, 0, 1, 1};   // [2] route histogram in smem, [3] full-bucket eviction shortcut, [4] multiply-shift in unique, [5] TMA-staged gather_to_peers
+int g_dev_opts[8] = {1, 1, 1, 1, 1, 0, 3, 1};   // [2] route histogram in smem, [3] full-bucket eviction shortcut, [4] multiply-shift in unique, [5] TMA-staged gather_to_peers,
+                                                // [6] CTAs per SM of evict / init when a consumer is hooked on the prefetch's lookup stage, [7] CTAs per SM of gather_to_peers part 1
 int g_dev_opts_pad_;  //   // demb_set_option(2..7): development toggles read by other translation units (demb_get_option)
 bool g_bwd_tma = false;         // demb_set_option(1, v): gradient rows of the backward staged through shared memory (1) or registers (0, default:
                                 // measured 0.293 ms against 0.367 ms — 12 resident warps cannot hide the per-segment row read-modify-write chain)
@@ -1103,7 +1106,7 @@ static int launch_seq_tma(const RowSrc& s, const float* values, int64_t value_di
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }
-static int launch_seq_probe(const RowSrc& s, const float* values, int64_t value_dim, int emb_dim, int64_t n, float* out, float absent_value,
+static int launch_seq_probe(int gen, const RowSrc& s, const float* values, int64_t value_dim, int emb_dim, int64_t n, float* out, float absent_value,
                             cudaStream_t stream) {
   const size_t per_warp = 32u * (size_t)emb_dim * 4u;
   int warps = (int)((216u * 1024u) / per_warp);
@@ -1111,12 +1114,16 @@ static int launch_seq_probe(const RowSrc& s, const float* values, int64_t value_
   if (warps < 1) return DEMB_ERR_ARG;
   const int smem = (int)(warps * per_warp);
   static std::atomic<int> configured[kMaxDevices];
-  cudaError_t ce = once_per_device(configured, [] { return cudaFuncSetAttribute(forward_seq_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); });
+  cudaError_t ce = once_per_device(configured, [] {
+    cudaError_t e = cudaFuncSetAttribute(forward_seq_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    return e != cudaSuccess ? e : cudaFuncSetAttribute(forward_seq_probe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+  });
   if (ce != cudaSuccess) return -(int)ce;
   const int64_t tiles = (n + 31) / 32;
   int64_t blocks = (tiles + warps - 1) / warps;
   if (blocks > sm_count()) blocks = sm_count();
-  forward_seq_probe_kernel<<<(int)blocks, kProbeFwdWarps * 32, smem, stream>>>(s, values, value_dim, emb_dim, n, out, absent_value, warps);
+  if (gen == 2) forward_seq_probe_kernel<2><<<(int)blocks, kProbeFwdWarps * 32, smem, stream>>>(s, values, value_dim, emb_dim, n, out, absent_value, warps);
+  else forward_seq_probe_kernel<1><<<(int)blocks, kProbeFwdWarps * 32, smem, stream>>>(s, values, value_dim, emb_dim, n, out, absent_value, warps);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e;
 }
@@ -1168,7 +1175,7 @@ int demb_lookup_forward(void* storage, const int64_t* table_bucket_offsets, int6
     if (out_dtype == DEMB_F32 && bucket_capacity == kProbeC && g_probe_kernel == 2 && kCopyWarps * 32 * emb_dim * 4 <= 200 * 1024)
       return launch_seq_probe2(s, values, value_dim, emb_dim, n, (float*)out, absent_value, (cudaStream_t)stream);
     if (out_dtype == DEMB_F32 && bucket_capacity == kProbeC && emb_dim <= 1024 && g_probe_kernel)
-      return launch_seq_probe(s, values, value_dim, emb_dim, n, (float*)out, absent_value, (cudaStream_t)stream);
+      return launch_seq_probe(g_probe_kernel == 5 ? 2 : 1, s, values, value_dim, emb_dim, n, (float*)out, absent_value, (cudaStream_t)stream);
     if (out_dtype == DEMB_F32) return launch_seq_tma(s, values, value_dim, emb_dim, n, (float*)out, absent_value, (cudaStream_t)stream);
     forward_seq_kernel<8><<<warp_grid((n + 31) / 32), kBlock, 0, (cudaStream_t)stream>>>(s, values, value_dim, emb_dim, n, out, out_dtype, absent_value);
   } else {

@@ -253,7 +253,7 @@ __global__ void recv_compact_kernel(RecvArgs a) {
 template <int U>
 __global__ void __launch_bounds__(256) gather_to_peers_kernel(const float* __restrict__ values, int64_t vdim, int D, int64_t n_max, const int64_t* __restrict__ n_dev,
                                                               const int64_t* __restrict__ rows, const int64_t* __restrict__ inverse,
-                                                              const int64_t* __restrict__ dst_addr) {
+                                                              const int64_t* __restrict__ dst_addr, const int8_t* __restrict__ hit_flags, int part) {
   int64_t n = *n_dev; n = n < n_max ? n : n_max;
   const int lane = threadIdx.x & 31;
   const int D4 = D >> 2;
@@ -263,7 +263,14 @@ __global__ void __launch_bounds__(256) gather_to_peers_kernel(const float* __res
     const int64_t base = tile << 5;
     const int cnt = (int)((n - base) < 32 ? (n - base) : 32);
     int64_t row = -1, dst = 0;
-    if (lane < cnt) { row = rows[inverse[base + lane]]; dst = dst_addr[base + lane]; }
+    if (lane < cnt) {
+      const int64_t u = inverse[base + lane];
+      // part 1: only the ids whose key the prefetch's lookup stage found (this launch may run BEFORE insert / evict / init have finished,
+      // so rows[] of the others is not read at all); part 2: only the others; part 0: all
+      const bool take = !hit_flags || part == 0 || (hit_flags[u] != 0) == (part == 1);
+      if (take) { row = rows[u]; dst = dst_addr[base + lane]; }
+    }
+    if (__ballot_sync(0xffffffffu, dst != 0) == 0u) continue;
     for (int j = 0; j < cnt; j += U) {
       int64_t r[U], d[U];
 #pragma unroll
@@ -286,7 +293,7 @@ constexpr int kG2PWarps = 12;
 __global__ void __launch_bounds__(kG2PWarps * 32, 1) gather_to_peers_tma_kernel(const float* __restrict__ values, int64_t vdim, int D, int64_t n_max,
                                                                              const int64_t* __restrict__ n_dev, const int64_t* __restrict__ rows,
                                                                              const int64_t* __restrict__ inverse, const int64_t* __restrict__ dst_addr,
-                                                                             int warps_per_block) {
+                                                                             const int8_t* __restrict__ hit_flags, int part, int warps_per_block) {
   extern __shared__ __align__(128) uint8_t stage_raw[];
   __shared__ uint64_t bars[kG2PWarps];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -303,7 +310,12 @@ __global__ void __launch_bounds__(kG2PWarps * 32, 1) gather_to_peers_tma_kernel(
     const int64_t base = tile << 5;
     const int cnt = (int)((n - base) < 32 ? (n - base) : 32);
     int64_t row = -1, dst = 0;
-    if (lane < cnt) { row = rows[inverse[base + lane]]; dst = dst_addr[base + lane]; }
+    if (lane < cnt) {
+      const int64_t u = inverse[base + lane];
+      const bool take = !hit_flags || part == 0 || (hit_flags[u] != 0) == (part == 1);   // see gather_to_peers_kernel
+      if (take) { row = rows[u]; dst = dst_addr[base + lane]; }
+    }
+    if (__ballot_sync(0xffffffffu, dst != 0) == 0u) continue;
     const unsigned found = __ballot_sync(0xffffffffu, row >= 0);
     if (lane == 0) {
       sm100::bulk_wait_read0();                                  // the previous tile's stores have finished reading the stage
@@ -312,7 +324,7 @@ __global__ void __launch_bounds__(kG2PWarps * 32, 1) gather_to_peers_tma_kernel(
     __syncwarp();
     if (row >= 0) {
       sm100::bulk_load(buf + (size_t)lane * row_bytes, values + row * vdim, row_bytes, &bars[wib]);
-    } else if (lane < cnt) {
+    } else if (lane < cnt && dst) {
       float4* d = reinterpret_cast<float4*>(buf + (size_t)lane * row_bytes);
       for (int c = 0; c < (D >> 2); ++c) d[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -440,26 +452,40 @@ int demb_shard_recv(int world, int rank, int num_tables, int emb_dim, int64_t pa
 }
 
 // Owner: out row of received id k = values[rows[inverse[k]]] (zeros when absent), written to dst_addr[k] (peer memory).
-int demb_shard_gather_to_peers(const float* values, int64_t value_dim, int emb_dim, int64_t n_max, const int64_t* n_dev, const int64_t* rows,
-                               const int64_t* inverse, const int64_t* dst_addr, void* stream) {
-  if (emb_dim <= 0 || (emb_dim & 3) || (value_dim & 3) || value_dim < emb_dim || !n_dev) return DEMB_ERR_ARG;
+// hit_flags (nullable, per UNIQUE id, from demb_train_prefetch_hook) with part 1 / 2 splits the copy: part 1 = the ids whose key the
+// prefetch's lookup stage found — may be launched on another stream as soon as that stage is done, concurrently with insert / evict /
+// row init — and part 2 = the rest, after the prefetch.  part 0 (or no flags) copies everything.
+static int gather_to_peers_impl(const float* values, int64_t value_dim, int emb_dim, int64_t n_max, const int64_t* n_dev, const int64_t* rows,
+                                const int64_t* inverse, const int64_t* dst_addr, const int8_t* hit_flags, int part, void* stream) {
+  if (emb_dim <= 0 || (emb_dim & 3) || (value_dim & 3) || value_dim < emb_dim || !n_dev || part < 0 || part > 2) return DEMB_ERR_ARG;
   if (n_max <= 0) return 0;
   int64_t blocks = ((n_max + 31) / 32 + 7) / 8;
-  const int64_t cap = (int64_t)sm_count() * 8;
+  // part 1 runs beside the owner's insert / evict / init kernels: one CTA per SM (option 7) fits into the registers those leave free
+  const int64_t cap = (int64_t)sm_count() * ((part == 1 && demb_get_option(7) > 0) ? demb_get_option(7) : 8);
   const size_t stage = 32u * (size_t)emb_dim * 4u;
   int tw = (int)((200u * 1024u) / stage); if (tw > kG2PWarps) tw = kG2PWarps;
-  if (demb_get_option(5) != 0 && tw >= 2) {
+  if (demb_get_option(5) != 0 && tw >= 2 && part != 1) {
     static std::atomic<int> configured[kMaxDevices];
     cudaError_t ce = once_per_device(configured, [] { return cudaFuncSetAttribute(gather_to_peers_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
     if (ce != cudaSuccess) return -(int)ce;
     int64_t tb = ((n_max + 31) / 32 + tw - 1) / tw;
     if (tb > sm_count()) tb = sm_count();
-    gather_to_peers_tma_kernel<<<(int)tb, kG2PWarps * 32, (size_t)tw * stage, (cudaStream_t)stream>>>(values, value_dim, emb_dim, n_max, n_dev, rows, inverse, dst_addr, tw);
+    gather_to_peers_tma_kernel<<<(int)tb, kG2PWarps * 32, (size_t)tw * stage, (cudaStream_t)stream>>>(values, value_dim, emb_dim, n_max, n_dev, rows, inverse, dst_addr,
+                                                                                                      hit_flags, part, tw);
   } else {
-    gather_to_peers_kernel<8><<<(int)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream>>>(values, value_dim, emb_dim, n_max, n_dev, rows, inverse, dst_addr);
+    gather_to_peers_kernel<8><<<(int)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream>>>(values, value_dim, emb_dim, n_max, n_dev, rows, inverse, dst_addr,
+                                                                                                     hit_flags, part);
   }
   DEMB_CHECK_LAST();
   return 0;
+}
+int demb_shard_gather_to_peers(const float* values, int64_t value_dim, int emb_dim, int64_t n_max, const int64_t* n_dev, const int64_t* rows,
+                               const int64_t* inverse, const int64_t* dst_addr, void* stream) {
+  return gather_to_peers_impl(values, value_dim, emb_dim, n_max, n_dev, rows, inverse, dst_addr, nullptr, 0, stream);
+}
+int demb_shard_gather_to_peers_part(const float* values, int64_t value_dim, int emb_dim, int64_t n_max, const int64_t* n_dev, const int64_t* rows,
+                                    const int64_t* inverse, const int64_t* dst_addr, const int8_t* hit_flags, int part, void* stream) {
+  return gather_to_peers_impl(values, value_dim, emb_dim, n_max, n_dev, rows, inverse, dst_addr, hit_flags, part, stream);
 }
 
 // All ranks call this the same number of times per channel (0..3), in the same order.  epochs: 4 uint64 of LOCAL device memory, zero at start.

@@ -37,6 +37,7 @@ struct TrainArgs {
   int full_shortcut; InitArgs init; const InitArgs* table_init; float state_init;   // table_init: per-table initializer (device, [T]), nullable => init
   int64_t* slots; int64_t* rows; int32_t* next; int32_t* touched; unsigned long long* n_touched;
   int32_t* init_list; unsigned long long* n_init;   // uniques inserted by the thread kernel: their rows are initialised by train_init_rows_kernel
+  int8_t* hit_flags;                                // nullable: 1 = found by the lookup stage (its row is valid and pinned from then on), 0 = not
 };
 
 __device__ __forceinline__ uint64_t train_score(const TrainArgs& a, int64_t u, int64_t tid) {
@@ -76,6 +77,7 @@ __global__ void train_lookup_kernel(TrainArgs a) {
       }
       a.slots[u] = slot;
       a.rows[u] = row;
+      if (a.hit_flags) a.hit_flags[u] = slot >= 0;
       if (slot >= 0 || L.cap <= 0) a.next[u] = -3;                                // not on any list (train_init_rows_kernel reads next[u] of every u)
     }
     const unsigned m = __ballot_sync(0xffffffffu, first_bucket >= 0);
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(kLookupWarps * 32, 3) train_lookup_tile_kernel
       }
       a.slots[u] = slot;
       a.rows[u] = row;
+      if (a.hit_flags) a.hit_flags[u] = slot >= 0;
       if (slot >= 0 || !k0.valid) a.next[u] = -3;                                 // not on any list
     }
     const unsigned m = __ballot_sync(0xffffffffu, first_bucket >= 0);
@@ -449,6 +452,13 @@ int64_t demb_train_prefetch_workspace_bytes(int64_t n, int num_tables) {
   return demb_segmented_unique_workspace_bytes(n, num_tables) + (int64_t)(4 * align256(4 * (size_t)(n > 0 ? n : 1)) + 512);
 }
 
+// One-shot hook for the NEXT demb_train_prefetch issued by this host thread: `hit_flags[u]` (device, sized like the outputs) receives 1 for
+// every unique key the lookup stage found, and `event` (a cudaEvent_t) is recorded on the prefetch's stream right after that stage —
+// the rows of found keys are final and pinned from there on, so a consumer on another stream (the row-wise sharded wrapper's
+// gather_to_peers) can start on them while insert / evict / row init are still running.  Either argument may be null.
+namespace { thread_local void* g_hook_event = nullptr; thread_local int8_t* g_hook_hits = nullptr; }
+int demb_train_prefetch_hook(void* event, int8_t* hit_flags) { g_hook_event = event; g_hook_hits = hit_flags; return 0; }
+
 int demb_train_prefetch(void* storage, const int64_t* table_bucket_offsets, int64_t bucket_capacity, int num_scores, int32_t* bucket_sizes,
                         int32_t* ref_counter, int32_t* bucket_heads, float* values, int64_t value_dim, int emb_dim, const int64_t* row_base,
                         int64_t n, const int64_t* n_dev, const void* keys, const int64_t* table_range, int num_tables, const int64_t* freq_in, int policy,
@@ -457,7 +467,12 @@ int demb_train_prefetch(void* storage, const int64_t* table_bucket_offsets, int6
                         int64_t* unique_freq, int64_t* slots, int64_t* rows, int64_t* num_unique, void* unique_scratch, void* workspace,
                         int64_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (n <= 0) return demb_segmented_unique(0, nullptr, keys, table_range, num_tables, nullptr, unique_keys, reverse_indices, nullptr, nullptr, nullptr, num_unique, nullptr, workspace, workspace_bytes, stream_);
+  void* hook_event = g_hook_event; int8_t* hook_hits = g_hook_hits;
+  g_hook_event = nullptr; g_hook_hits = nullptr;
+  if (n <= 0) {
+    if (hook_event) cudaEventRecord((cudaEvent_t)hook_event, stream);
+    return demb_segmented_unique(0, nullptr, keys, table_range, num_tables, nullptr, unique_keys, reverse_indices, nullptr, nullptr, nullptr, num_unique, nullptr, workspace, workspace_bytes, stream_);
+  }
   if (workspace_bytes < demb_train_prefetch_workspace_bytes(n, num_tables)) return DEMB_ERR_WORKSPACE;
   if ((emb_dim & 3) || (value_dim & 3) || value_dim < emb_dim) return DEMB_ERR_ARG;
   uint8_t* w = (uint8_t*)workspace;
@@ -483,6 +498,7 @@ int demb_train_prefetch(void* storage, const int64_t* table_bucket_offsets, int6
   a.init = InitArgs{init_mode, p0, p1, p2, p3, seed}; a.table_init = reinterpret_cast<const InitArgs*>(table_init); a.state_init = state_init;
   a.full_shortcut = demb_get_option(3) != 0;
   a.slots = slots; a.rows = rows; a.next = next; a.touched = touched; a.n_touched = n_touched; a.init_list = init_list; a.n_init = n_init;
+  a.hit_flags = hook_hits;
   if (bucket_capacity == kProbeC) {
     int64_t blocks = ((n + 31) / 32 + kLookupWarps - 1) / kLookupWarps;
     const int64_t cap = (int64_t)sm_count() * 3;
@@ -490,12 +506,18 @@ int demb_train_prefetch(void* storage, const int64_t* table_bucket_offsets, int6
   } else {
     train_lookup_kernel<<<grid_for(n), kBlock, 0, stream>>>(a);
   }
+  if (hook_event && cudaEventRecord((cudaEvent_t)hook_event, stream) != cudaSuccess) return DEMB_ERR_ARG;
   train_insert_thread_kernel<<<grid_for(n), kBlock, 0, stream>>>(a, touched2, n_touched2);
   TrainArgs a2 = a;
   a2.touched = touched2; a2.n_touched = n_touched2;
-  if (bucket_capacity == kProbeC) train_evict_kernel<<<sm_count() * 8, kBlock, 0, stream>>>(a2);   // buckets that may evict (all of them at steady state)
+  // With a consumer hooked on the lookup stage (the sharded wrapper's copy of the found rows, on another stream) the two long kernels
+  // leave a quarter of every SM's registers free — 3 resident CTAs instead of 4 at 64 registers x 256 threads — so that the consumer's CTAs
+  // can be resident beside them; without that the kernels only alternate (measured at N=2: the overlapped pair took exactly the sum).
+  const int hooked_bps = demb_get_option(6);
+  const int bps = (hook_event && hooked_bps > 0) ? hooked_bps : 8;
+  if (bucket_capacity == kProbeC) train_evict_kernel<<<sm_count() * bps, kBlock, 0, stream>>>(a2);   // buckets that may evict (all of them at steady state)
   else train_insert_kernel<<<sm_count() * 4, kBlock, 0, stream>>>(a2);
-  train_init_rows_kernel<<<sm_count() * 8, kBlock, 0, stream>>>(a);
+  train_init_rows_kernel<<<sm_count() * bps, kBlock, 0, stream>>>(a);
   DEMB_CHECK_LAST();
   return 0;
 }

@@ -69,6 +69,8 @@ _SIGS = {
     "demb_shard_recv_workspace_bytes": (I64, [I32, I32]),
     "demb_shard_recv": (I32, [I32, I32, I32, I32, I64, I64, I64, P, P, P, P, P, P, P, P, I64, P]),
     "demb_shard_gather_to_peers": (I32, [P, I64, I32, I64, P, P, P, P, P]),
+    "demb_shard_gather_to_peers_part": (I32, [P, I64, I32, I64, P, P, P, P, P, I32, P]),
+    "demb_train_prefetch_hook": (I32, [P, P]),
     "demb_peer_barrier": (I32, [I32, I32, I64, I64, I32, P, P, I32, P, P]),
     "demb_zero_i64": (I32, [P, I64, P]),
     "demb_ipc_alloc": (I32, [I64, P, P]),

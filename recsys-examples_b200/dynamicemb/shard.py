@@ -128,6 +128,10 @@ class RowWiseShardedDynamicEmbedding(nn.Module):
         self._empty = nn.Parameter(torch.empty(1, device=dev))        # gives autograd a reason to call backward
         self._prep_req = self._prep_own = None                         # side streams of the two backward sorts
         self.prepare_sorts = 3                                         # bit 0: requester's sort, bit 1: owner's sort launched early on a side stream
+        # owner side: rows of the ids the prefetch's lookup stage FOUND are final (and pinned) before insert / evict / row init run, so their
+        # NVLink copy back to the requesters starts right after that stage, on a side stream, and overlaps the rest of the prefetch
+        self.overlap_hits = True
+        self._g2p_stream = self._ev_lookup = self._ev_g2p = None
 
     # ------------------------------------------------------------------ setup
     def _ensure_buffers(self, n: int) -> None:
@@ -156,6 +160,10 @@ class RowWiseShardedDynamicEmbedding(nn.Module):
         self._uscratch_req = ext.unique_scratch(n_cap, T, dev)
         self._uscratch_own = ext.unique_scratch(recv_cap, T, dev)
         self._epochs.zero_()
+        if self._g2p_stream is None:
+            self._g2p_stream = torch.cuda.Stream(device=dev)
+            self._ev_lookup, self._ev_g2p = torch.cuda.Event(), torch.cuda.Event()
+            self._ev_lookup.record(); self._ev_g2p.record()             # materialise the cudaEvent handles (outside any graph capture)
 
     def _barrier(self) -> None:
         N.check(N.launch("peer_barrier", 1, N.lib.demb_peer_barrier, self.world_size, self.rank, self._pair_cap, self._n_cap, self.local.max_D,
@@ -201,10 +209,25 @@ class RowWiseShardedDynamicEmbedding(nn.Module):
         N.check(N.launch("shard_recv", 2, N.lib.demb_shard_recv, W, self.rank, T, D, self._pair_cap, self._n_cap, R, N.ptr(self._buf.peers), N.ptr(self._err),
                          N.ptr(ids_recv), N.ptr(trange_r), N.ptr(n_recv), N.ptr(src_pos), N.ptr(dst_addr), N.ptr(self._recv_ws), self._recv_ws.numel(),
                          N.stream()), "shard_recv")
+        overlap = self.overlap_hits
+        if overlap:
+            hit = torch.empty(R, dtype=torch.int8, device=dev)
+            N.check(N.lib.demb_train_prefetch_hook(ctypes.c_void_p(self._ev_lookup.cuda_event), N.ptr(hit)), "train_prefetch_hook")
         st = m._prefetch_device_count(ids_recv, trange_r if T > 1 else None, T, n_recv, self._uscratch_own)
         prep_own = ext.backward_prepare(self._prep_own, D, st.reverse_indices, R, n_dev=n_recv, grad_row_of=src_pos) if (train and (_pm & 2)) else None
-        N.check(N.launch("gather_to_peers", 1, N.lib.demb_shard_gather_to_peers, N.ptr(m._values), m._values.stride(0), D, R, N.ptr(n_recv), N.ptr(st.rows),
-                         N.ptr(st.reverse_indices), N.ptr(dst_addr), N.stream()), "gather_to_peers")
+        if overlap:
+            main, side = torch.cuda.current_stream(), self._g2p_stream
+            side.wait_event(self._ev_lookup)                            # recorded by the prefetch right after its lookup stage
+            with torch.cuda.stream(side):
+                N.check(N.launch("gather_to_peers.hits", 1, N.lib.demb_shard_gather_to_peers_part, N.ptr(m._values), m._values.stride(0), D, R, N.ptr(n_recv),
+                                 N.ptr(st.rows), N.ptr(st.reverse_indices), N.ptr(dst_addr), N.ptr(hit), 1, N.stream()), "gather_to_peers.hits")
+                self._ev_g2p.record(side)
+            N.check(N.launch("gather_to_peers", 1, N.lib.demb_shard_gather_to_peers_part, N.ptr(m._values), m._values.stride(0), D, R, N.ptr(n_recv),
+                             N.ptr(st.rows), N.ptr(st.reverse_indices), N.ptr(dst_addr), N.ptr(hit), 2, N.stream()), "gather_to_peers")
+            main.wait_event(self._ev_g2p)
+        else:
+            N.check(N.launch("gather_to_peers", 1, N.lib.demb_shard_gather_to_peers, N.ptr(m._values), m._values.stride(0), D, R, N.ptr(n_recv), N.ptr(st.rows),
+                             N.ptr(st.reverse_indices), N.ptr(dst_addr), N.stream()), "gather_to_peers")
         self._barrier()
         # ---- requester: one gather from rows_back undoes routing + dedup; pooled modes pool here
         out = ext.gather_forward(self._rows_back, D, send_pos, rev, n, offsets=offsets if pooled else None, batch_size=B if pooled else 0,

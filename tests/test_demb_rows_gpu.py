@@ -87,15 +87,15 @@ def test_fused_lookup_forward_sequence(cuda, D, out_dtype):
     assert torch.equal(out.cpu(), exp.to(out_dtype))       # pure copy (+ one rounding for bf16): bit-exact
 
 
-@pytest.mark.parametrize("n_per_table", [3300, 17, 600000])   # the last: > 2 ring revolutions per CTA in the specialised layouts
-def test_fused_lookup_kernel_variants_agree(cuda, n_per_table):
+@pytest.mark.parametrize("n_per_table,n_keys", [(3300, 5000), (17, 5000), (600000, 5000), (3300, 8150)])   # 600000: > 2 ring revolutions per CTA in the
+def test_fused_lookup_kernel_variants_agree(cuda, n_per_table, n_keys):                                        # specialised layouts; 8150 keys: buckets (nearly) full
     """demb_set_option(0, v): every fused-lookup kernel (round-1 thread-per-key probe, per-warp pipeline = default, the specialised
     probe / copy layouts) must return the same rows, founds and slots; a ragged tail (n % 32 != 0), two tables, absent ids."""
     from dynamicemb import dynamicemb_extensions as ext
     from dynamicemb import _native as N
     D = 128
     rng = np.random.default_rng(n_per_table)
-    t, values, keys, tids, slots = _filled_table(cuda, rng, [128 * 40, 128 * 24], D, 4, 5000)
+    t, values, keys, tids, slots = _filled_table(cuda, rng, [128 * 40, 128 * 24], D, 4, n_keys)
     ids = []
     for tb in range(2):
         mine = keys[(tids == tb) & (slots >= 0)]
@@ -105,7 +105,7 @@ def test_fused_lookup_kernel_variants_agree(cuda, n_per_table):
     idt = torch.from_numpy(np.concatenate(ids)).to(cuda)
     res = {}
     try:
-        for v in (1, 0, 2, 3, 4):
+        for v in (1, 0, 2, 3, 4, 5):
             N.lib.demb_set_option(0, v)
             out, founds, sl = ext.lookup_forward(t.table_storage_, t.table_bucket_offsets_, t.bucket_capacity_, values, D, idt, row_base=t.row_base_,
                                                  table_range=trange, num_tables=2, out_dtype=torch.float32, absent_value=0.25, want_founds=True)
@@ -114,7 +114,7 @@ def test_fused_lookup_kernel_variants_agree(cuda, n_per_table):
     finally:
         N.lib.demb_set_option(0, 1)
     assert int(res[1][1].sum()) >= 2 * n_per_table
-    for v in (0, 2, 3, 4):
+    for v in (0, 2, 3, 4, 5):
         assert torch.equal(res[v][2], res[1][2]), v
         assert torch.equal(res[v][1], res[1][1]), v
         assert torch.equal(res[v][0], res[1][0]), v
