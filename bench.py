@@ -449,6 +449,7 @@ def main():
 
     m = make_module(args.capacity, dev)
     fill = prefill(m, gen, dev, world, rank, KEY_SPACE, args.plaw_draws, True, args.capacity)
+    model = None
     if world > 1:
         from dynamicemb.shard import RowWiseShardedDynamicEmbedding
         # exchange capacities (ids per step): a rank feeds n_ids, sends at most n_ids/2 unique ids to any single owner (hash_roundrobin
@@ -726,7 +727,7 @@ def main():
     # ---- variants (N=1): the same graph step without eviction (SURVEY §8(d) cfg 2: "separately report a no-eviction run, key space 64 Mi")
     if world == 1 and not args.no_variants:
         try:
-            del graphed, graphed_noloss, model
+            graphed = graphed_noloss = model = None
             graphed = graphed_noloss = None
             m = None
             torch.cuda.empty_cache()
