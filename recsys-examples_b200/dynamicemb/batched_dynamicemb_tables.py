@@ -16,6 +16,7 @@ with the kernel sequence collapsed:
   load_from_flat, gather_embedding[_pooled]          gather_forward (one pass, no staging copy)
   reduce_grads (sort+2), optimizer, decrement        backward (sort + fused reduce/update), counter
 """
+import os
 import warnings
 from collections import deque
 from dataclasses import dataclass
@@ -505,18 +506,166 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         self._scores, self._optimizer.iter = host_scores, host_iter
         return _GraphedStep(self, graph, keepalive=(indices, offsets_i, grad_static)), out, loss
 
-    # ------------------------------------------------------------------ inspection helpers (tests, dump)
-    def export_keys_values(self, table_id: int = 0):
-        """All (key, embedding row, optimizer state) of one table — used by dump and by the tests."""
+    # ------------------------------------------------------------------ export / checkpoint (batched_dynamicemb_tables.py:1262-1440)
+    def _table_id(self, table) -> int:
+        return self._table_names.index(table) if isinstance(table, str) else int(table)
+
+    def _export_batches(self, table_id: int, batch_size: int = 65536):
+        """(keys, value rows [n, value_dim], scores) batches of one table: table scan by the export kernel, rows by the row-copy kernel.
+        scores: int64 [n], or [n, num_scores] in device order for multi-word scores (export_keys_values_iter, key_value_table.py:1073-1131)."""
         tb = self._table
+        base = int(tb.table_bucket_offsets_cpu_[table_id]) * tb.bucket_capacity_
+        for keys, scores, idx in tb.export(table_id, batch=batch_size):
+            dense = torch.empty(keys.numel(), self.value_dim, dtype=torch.float32, device=self._device)
+            ext.copy_rows(self._values, self.value_dim, (idx + base).contiguous(), dense, to_table=False)
+            sc = tb.gather_score_blocks(table_id, idx) if tb.num_scores_ > 1 else scores.view(torch.int64)
+            yield keys, dense, sc
+
+    def export_keys_values(self, table=0, device: Optional[torch.device] = None, batch_size: int = 65536):
+        """All (keys, rows) of one table, named as in the reference (:1420, `table_name`) or by index.  With `device` given the reference's
+        result is returned — (keys, embeddings [n, dim]) on that device; without it (keys, full value rows [n, dim + state]) on the GPU,
+        which is what the tests inspect."""
+        self.flush()
+        t = self._table_id(table)
         ks, vs = [], []
-        base = int(tb.row_base_[table_id].item())
-        for keys, _scores, idx in tb.export(table_id):
+        for keys, dense, _ in self._export_batches(t, batch_size):
             ks.append(keys)
-            vs.append(self._values[base + idx])
+            vs.append(dense)
         if not ks:
-            return torch.empty(0, dtype=self.index_type, device=self._device), torch.empty(0, self.value_dim, device=self._device)
-        return torch.cat(ks), torch.cat(vs)
+            ks, vs = [torch.empty(0, dtype=self.index_type, device=self._device)], [torch.empty(0, self.value_dim, device=self._device)]
+        keys, vals = torch.cat(ks), torch.cat(vs)
+        if device is None:
+            return keys, vals
+        return keys.to(device), vals[:, :self.dims[t]].contiguous().to(device)
+
+    def _evict_strategy_str(self, table_id: int) -> str:
+        # str() of the reference's pybind enum, which is what its meta json holds ("EvictStrategy.KLru", dynamic_emb_op.cu:814-819)
+        return f"EvictStrategy.{self._dynamicemb_options[table_id].evict_strategy.value.name}"
+
+    @staticmethod
+    def _rank_world(pg):
+        import torch.distributed as dist
+        if pg is None and not dist.is_initialized():          # single process: the reference's dump asserts, its load treats it as 1 rank
+            return 0, 1, False
+        return dist.get_rank(group=pg), dist.get_world_size(group=pg), True
+
+    def dump(self, save_dir: str, optim: bool = False, counter: bool = False, table_names: Optional[List[str]] = None, pg=None) -> None:
+        """Write every selected table of this rank in the reference's file layout (dynamicemb/checkpoint.py)."""
+        from . import checkpoint as ck
+        import torch.distributed as dist
+        names = set(self._table_names if table_names is None else table_names)
+        rank, world, distributed = self._rank_world(pg)
+        os.makedirs(save_dir, exist_ok=True)
+        self.flush()
+        for t, name in enumerate(self._table_names):
+            if name not in names:
+                continue
+            if distributed:
+                dist.barrier(group=pg)
+            ts = ext.device_timestamp()
+            o = self._dynamicemb_options[t]
+            if rank == 0:
+                meta = dict(self._optimizer.get_opt_args())
+                meta["evict_strategy"] = self._evict_strategy_str(t)
+                meta["dist_type"] = o.dist_type
+                if self._scores.get(name) is not None:
+                    meta["step_score"] = self._scores[name]
+                ck.save_to_json(meta, ck.encode_meta_json_file_path(save_dir, name))
+            D = self.dims[t]
+            sdim = self._optimizer.get_state_dim(D)
+            perm = ck.score_dump_permutation(o.score_strategy)
+            lru = o.evict_strategy == DynamicEmbEvictStrategy.LRU
+            path = lambda item: ck.encode_checkpoint_file_path(save_dir, name, rank, world, item)     # noqa: E731
+            with ck.TableFileWriter(path("keys"), path("values"), path("scores"), path("opt_values") if optim else None) as w:
+                for keys, dense, scores in self._export_batches(t):
+                    if scores.dim() == 2 and perm != list(range(scores.size(1))):
+                        scores = scores[:, perm].contiguous()
+                    if lru:
+                        scores = ts - scores                                     # age; restored relative to the loading time
+                    opt = None
+                    if optim and sdim > 0:
+                        opt = ck.truncate_optimizer_states_for_checkpoint(self._optimizer, D, dense[:, D:D + sdim])
+                    w.write(keys, dense[:, :D], scores, opt)
+            if counter:
+                warnings.warn(f"Counter table is none and will not dump it for table: {name}")     # admission counters: out of scope
+
+    def load(self, save_dir: str, optim: bool = False, counter: bool = False, table_names: Optional[List[str]] = None, pg=None) -> None:
+        """Read a checkpoint in the reference's layout: this rank's own files when the world size matches, otherwise every file filtered
+        to the keys this rank owns."""
+        from . import checkpoint as ck
+        import torch.distributed as dist
+        names = set(self._table_names if table_names is None else table_names)
+        rank, world, distributed = self._rank_world(pg)
+        for t, name in enumerate(self._table_names):
+            if name not in names:
+                continue
+            kf, vf, sf, of, _, _ = ck.get_loading_files(save_dir, name, rank=rank, world_size=world)
+            if not kf:
+                continue
+            if distributed:
+                dist.barrier(group=pg)
+            ts = ext.device_timestamp()
+            own_files = len(kf) == 1 and kf[0] == ck.encode_checkpoint_file_path(save_dir, name, rank, world, "keys")
+            for i in range(len(kf)):
+                loaded = self._load_table_files(t, ck.encode_meta_json_file_path(save_dir, name), kf[i], vf[i], sf[i] if sf else None,
+                                                of[i] if of else None, include_optim=optim, timestamp=ts,
+                                                filter_rank=None if own_files or world == 1 else (rank, world))
+                if loaded is not None and name in self._scores:
+                    self._scores[name] = loaded
+                    self._scores_dev = None
+            if counter:
+                warnings.warn(f"Counter table is none and will not load for table: {name}")
+
+    def _load_table_files(self, t: int, meta_path, key_path, value_path, score_path, opt_path, include_optim, timestamp, filter_rank=None):
+        """DynamicEmbStorage.load + _load_key_values (key_value_table.py:1909-1976, :1402-1517) on the native ops: insert the keys with the
+        stored scores (ASSIGN), copy [emb | state] rows to the slots they got."""
+        from . import checkpoint as ck
+        tb, o, D = self._table, self._dynamicemb_options[t], self.dims[t]
+        ns = tb.num_scores_
+        meta = ck.load_from_json(meta_path)
+        if score_path is None:
+            print(f"Score file {score_path} does not exist. Will not load score states.")
+        include_optim, file_sdim, _ = ck.validate_load_meta(meta, self._optimizer, self._evict_strategy_str(t), o.dist_type, D, ns, key_path,
+                                                           value_path, score_path, opt_path, include_optim)
+        sdim = self._optimizer.get_state_dim(D)
+        perm = ck.score_load_permutation(o.score_strategy) if ns > 1 else None
+        lru = o.evict_strategy == DynamicEmbEvictStrategy.LRU
+        base = int(tb.table_bucket_offsets_cpu_[t]) * tb.bucket_capacity_
+        rank, world = filter_rank if filter_rank is not None else (0, 1)
+        for keys, emb, scores, opt in ck.iter_batches_from_files(key_path, value_path, score_path, opt_path if include_optim else None, D,
+                                                                 file_sdim, self._device, num_scores=ns, rank=rank, world_size=world,
+                                                                 dist_type=o.dist_type):
+            n = keys.numel()
+            if n == 0:
+                continue
+            if scores is not None and perm is not None and perm != list(range(ns)):
+                scores = scores[:, perm].contiguous()
+            if scores is not None and lru:
+                scores = torch.clamp(timestamp - scores, min=0)
+            dense = torch.empty(n, self.value_dim, dtype=torch.float32, device=self._device)
+            dense[:, :D] = emb
+            if sdim > 0:
+                dense[:, D:D + sdim] = (self._optimizer.initial_state_value if opt is None else
+                                        ck.pad_optimizer_states_from_checkpoint(self._optimizer, D, opt, self._optimizer.initial_state_value,
+                                                                                torch.float32, self._device))
+            if self.value_dim > D + sdim:
+                dense[:, D + sdim:] = 0
+            tids = torch.full((n,), t, dtype=torch.int64, device=self._device)
+            keys = keys.to(self.index_type)
+            if ns > 1:
+                if scores is None or scores.dim() != 2 or scores.size(1) != ns or scores.size(0) != n:
+                    raise ValueError(f"multi-word load expects [{n}, {ns}] scores, got {None if scores is None else tuple(scores.shape)}")
+                slots = tb.insert(keys, tids, ScoreArg(name="score", policy=ScorePolicy.CONST), timestamp=timestamp)
+                tb.scatter_score_blocks(t, slots, scores)
+            elif scores is None:
+                assert lru, "scores is None is only allowed for the LRU evict strategy"
+                slots = tb.insert(keys, tids, ScoreArg(name="score", policy=ScorePolicy.GLOBAL_TIMER), timestamp=timestamp)
+            else:
+                slots = tb.insert(keys, tids, ScoreArg(name="score", value=scores.to(torch.int64).contiguous(), policy=ScorePolicy.ASSIGN),
+                                  timestamp=timestamp)
+            rows = torch.where(slots >= 0, slots + base, slots).contiguous()
+            ext.copy_rows(self._values, self.value_dim, rows, dense, to_table=True)
+        return meta.get("step_score", None)
 
 
 class _GraphedStep:

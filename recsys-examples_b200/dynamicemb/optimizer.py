@@ -67,3 +67,41 @@ class SparseOptimizer:
 
     def set_learning_rate(self, lr: float) -> None:
         self.args.learning_rate = lr
+
+    # ------------------------------------------------------------------ checkpoint metadata (reference optimizer.py:155-170, :248-260,
+    # :330-350, :410-430, :487-512): the `<table>_opt_args.json` a dump writes and a load validates / restores
+    _CKPT_NAME = {EmbOptimType.SGD: "sgd", EmbOptimType.EXACT_SGD: "sgd", EmbOptimType.ADAM: "adam",
+                  EmbOptimType.EXACT_ADAGRAD: "exact_adagrad", EmbOptimType.EXACT_ROWWISE_ADAGRAD: "exact_row_wise_adagrad"}
+
+    def get_opt_args(self) -> dict:
+        a, t = self.args, self.optimizer_type
+        if t == EmbOptimType.NONE:
+            return {}
+        out = {"opt_type": self._CKPT_NAME[t], "lr": a.learning_rate}
+        if t == EmbOptimType.ADAM:
+            out.update(iters=self.iter, beta1=a.beta1, beta2=a.beta2, eps=a.eps, weight_decay=a.weight_decay)
+        elif t in (EmbOptimType.EXACT_ADAGRAD, EmbOptimType.EXACT_ROWWISE_ADAGRAD):
+            out.update(eps=a.eps, initial_accumulator_value=a.initial_accumulator_value)
+        return out
+
+    def set_opt_args(self, args: dict) -> None:
+        def need(key):
+            if key not in args:
+                raise ValueError(f"Input args does not contain required optimizer argument: {key}")
+            return args[key]
+        a, t = self.args, self.optimizer_type
+        if t == EmbOptimType.NONE:
+            return
+        a.learning_rate = need("lr")
+        if t == EmbOptimType.ADAM:
+            self.iter = int(need("iters"))
+            a.beta1, a.beta2, a.eps, a.weight_decay = need("beta1"), need("beta2"), need("eps"), need("weight_decay")
+        elif t in (EmbOptimType.EXACT_ADAGRAD, EmbOptimType.EXACT_ROWWISE_ADAGRAD):
+            a.eps, a.initial_accumulator_value = need("eps"), need("initial_accumulator_value")
+
+    def get_ckpt_state_dim(self, dim: int) -> int:
+        """State elements per row in a checkpoint file: row-wise Adagrad keeps 16 bytes at run time but only its accumulator is stored
+        (reference optimizer.py:60-73)."""
+        if self.optimizer_type == EmbOptimType.EXACT_ROWWISE_ADAGRAD:
+            return 1
+        return self.get_state_dim(dim)

@@ -170,6 +170,33 @@ class LinearBucketTable:
         ext.table_update_counter_with_layout(self._ref_counter, slot_indices, -1, self.table_bucket_offsets_, self.bucket_capacity_,
                                              table_ids=table_ids)
 
+    # ------------------------------------------------------------------ whole score blocks (checkpoint of multi-word scores)
+    def _score_words(self) -> torch.Tensor:
+        """[num_buckets, C, num_scores] int64 strided view of the score words (AoS per key behind keys and digests of a bucket)."""
+        C, ns = self.bucket_capacity_, self.num_scores_
+        bucket_words = (9 + 8 * ns) * C // 8
+        flat = self.table_storage_.view(torch.uint8).reshape(-1)[9 * C:].view(torch.int64)
+        return torch.as_strided(flat, (self.num_buckets_, C, ns), (bucket_words, ns, 1))
+
+    def _global_slots(self, table_id: int, indices: torch.Tensor):
+        g = indices.to(torch.int64) + int(self.table_bucket_offsets_cpu_[table_id]) * self.bucket_capacity_
+        return torch.div(g, self.bucket_capacity_, rounding_mode="floor"), g % self.bucket_capacity_
+
+    def gather_score_blocks(self, table_id: int, indices: torch.Tensor) -> torch.Tensor:
+        """All score words of the given table-local slots, [n, num_scores] int64 in device (physical) order
+        (reference scored_hashtable.py gather_score_blocks, used by export_keys_values_iter key_value_table.py:1111-1113)."""
+        b, s = self._global_slots(table_id, indices)
+        return self._score_words()[b, s].contiguous()
+
+    def scatter_score_blocks(self, table_id: int, indices: torch.Tensor, blocks: torch.Tensor) -> None:
+        """Write [n, num_scores] score blocks at table-local slots; negative slots (failed inserts) are skipped
+        (reference scatter_score_blocks, key_value_table.py:1471-1474)."""
+        if blocks.dim() != 2 or blocks.size(1) != self.num_scores_ or blocks.size(0) != indices.numel():
+            raise ValueError(f"expects [{indices.numel()}, {self.num_scores_}] scores, got {tuple(blocks.shape)}")
+        ok = indices >= 0
+        b, s = self._global_slots(table_id, indices[ok])
+        self._score_words()[b, s] = blocks[ok].to(torch.int64)
+
     def export(self, table_id: int = 0, batch: int = 65536, threshold: Optional[int] = None):
         """Scan one logical table; yields (keys, scores, table-local slot indices) batches (BATCH_SIZE_PER_DUMP scan, :export)."""
         C = self.bucket_capacity_

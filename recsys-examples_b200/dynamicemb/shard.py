@@ -92,7 +92,23 @@ class _ShardedLookup(torch.autograd.Function):
         return None, None, None, None, None
 
 
-class RowWiseShardedDynamicEmbedding(nn.Module):
+class _ShardCheckpointMixin:
+    """dump / load of a row-wise sharded table: every rank writes / reads its own shard in the reference's per-rank file layout
+    (`<table>_emb_{keys,values,scores,opt_values}.rank_<r>.world_size_<W>`, dynamicemb/checkpoint.py); a checkpoint written by another
+    world size is re-sharded on load by the owner rule of this wrapper's dist_type."""
+
+    def _sync_dist_type(self, dist_type: str) -> None:
+        for o in self.local._dynamicemb_options:
+            o.dist_type = dist_type
+
+    def dump(self, save_dir: str, optim: bool = False, counter: bool = False, table_names=None) -> None:
+        self.local.dump(save_dir, optim=optim, counter=counter, table_names=table_names, pg=self.group)
+
+    def load(self, save_dir: str, optim: bool = False, counter: bool = False, table_names=None) -> None:
+        self.local.load(save_dir, optim=optim, counter=counter, table_names=table_names, pg=self.group)
+
+
+class RowWiseShardedDynamicEmbedding(_ShardCheckpointMixin, nn.Module):
     """forward(ids[n], lengths[F*B]) (KJT of THIS rank's batch, feature-major) ->
          pooling NONE: [n, D] rows in id order (EmbeddingCollection);  SUM / MEAN: [B, F*D] pooled bags (EmbeddingBagCollection).
     `local` is this rank's shard (its pooling_mode selects the output; its tables / value rows / optimizer are used directly).
@@ -110,6 +126,7 @@ class RowWiseShardedDynamicEmbedding(nn.Module):
         self.rank = dist.get_rank(self.group)
         self.use_index_dedup = use_index_dedup        # kept for API parity: ids are always deduplicated per table before they travel
         self.pooling_mode = local.pooling_mode
+        self._sync_dist_type(dist_type)
         F, T = local.feature_num, len(local._dynamicemb_options)
         dev = local._device
         self._dev = dev
@@ -312,7 +329,7 @@ class RowWiseShardedDynamicEmbedding(nn.Module):
         return _GraphedStep(m, graph, keepalive=(ids_static, lengths, offsets, grad_static, self)), out, loss
 
 
-class RowWiseShardedDynamicEmbeddingA2A(nn.Module):
+class RowWiseShardedDynamicEmbeddingA2A(_ShardCheckpointMixin, nn.Module):
     """The TorchRec-shaped variant of the same data flow over torch.distributed collectives (block bucketize -> all_to_all(lengths, ids) ->
     lookup -> all_to_all(rows), dynamicemb/input_dist.py): for process groups whose ranks do not share an NVLink/NVSwitch domain (multi
     node) and for the CPU (gloo) tests of the host logic.  Sequence mode only; two host synchronisations per step, as in TorchRec."""
@@ -323,6 +340,7 @@ class RowWiseShardedDynamicEmbeddingA2A(nn.Module):
         assert local.pooling_mode == DynamicEmbPoolingMode.NONE, "sequence mode wrapper"
         self.local, self.group, self.use_index_dedup = local, process_group, use_index_dedup
         self.world_size = dist.get_world_size(process_group)
+        self._sync_dist_type(dist_type)
         F, dev = local.feature_num, local._device
         self._dist_type = torch.full((F,), ext.DIST_TYPE[dist_type], dtype=torch.int32, device=dev)
         if num_embeddings_per_feature is None:
