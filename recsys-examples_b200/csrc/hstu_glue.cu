@@ -1,0 +1,546 @@
+// HSTU layer glue: the row-wise elementwise stages between the GEMMs and the attention kernel of one HSTU layer,
+//     y = LN(x)                      -> uvqk GEMM -> SiLU -> split u,v,q,k -> attention -> y = dropout(LN(attn) * u) -> proj GEMM + residual
+// as hand-written sm_100a kernels.  Replaces the reference's Triton kernels
+//     examples/hstu/ops/triton_ops/triton_layer_norm.py      (_weighted_layer_norm_fwd :80, _weighted_layer_norm_bwd_dx :171, _layer_norm_bwd_dwdb :284)
+//     examples/hstu/ops/triton_ops/triton_norm_mul_dropout.py (_ln_mul_dropout_fwd :37, _ln_mul_dropout_bwd_dx_du :131, _ln_mul_dropout_bwd_dwdb :332)
+//     examples/hstu/ops/triton_ops/triton_silu.py             (_silu_forward :48, _silu_backward :69)
+// as they are called from FusedHSTULayerFunction (examples/hstu/ops/fused_hstu_op.py:196-251, :421-483 and its backward).
+//
+// All of it is HBM-bound: a warp owns a row (hidden <= 1024: the row lives in registers, 16-byte loads, one pass), fp32 math, statistics by
+// warp shuffles.  What is fused that the reference runs as separate passes:
+//   * LN backward computes dx AND the weight / bias gradient partials in the same pass over dy and x (the reference re-reads both in
+//     `_layer_norm_bwd_dwdb`); a residual gradient can be added into dx on the way out (the layer's `+ x`);
+//   * LN*u*dropout backward produces dx, du, the dw / db partials and (optionally) the recomputed forward output y in one pass;
+//   * SiLU backward reads the four gradient pieces (du, dv, dq, dk) where the producers left them (own pointer / row stride each) and
+//     writes the dense [T, 4*H*D] gradient of the uvqk GEMM output: no torch.cat.
+// Dropout: counter-based Philox4x32-10 keyed by (seed, row, column group) — forward and backward regenerate the same mask, nothing is
+// stored.  The reference draws from Triton's tl.rand(seed, row * BLOCK_D + col); the two streams differ, the distribution does not
+// (keep probability quantised to 1/65536 here).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hstu_b200.h"
+#include "device_info.cuh"
+
+namespace glue {
+
+constexpr int kWarps = 4;
+constexpr int kThreads = kWarps * 32;
+constexpr int kMaxD = 1024;            // register-resident row: NV <= 4 vectors of 8 elements per lane
+
+#define GLUE_CHECK_LAST() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return -(int)e__; } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- 8 consecutive elements <-> 8 floats -------------------------------------------------------------------------------------------
+template <typename T> struct V8;
+template <> struct V8<float> {
+  static __device__ __forceinline__ void load(const float* p, float* v) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct V8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {              // bf16 -> fp32 is a 16-bit shift
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <> struct V8<__half> {
+  static __device__ __forceinline__ void load(const __half* p, float* v) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__half* p, const float* v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// ---- dropout mask ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+struct Drop {
+  uint64_t seed;
+  uint32_t thr;       // element kept iff its 16 random bits >= thr;  0 = keep everything (eval / ratio 0)
+  float scale;        // 1 / (1 - thr / 65536)
+};
+// keep-scale of the 8 elements of column group `cg` of `row`: scale or 0
+__device__ __forceinline__ void drop_scales(const Drop& d, int64_t row, int cg, float* m) {
+  if (d.thr == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = 1.0f;
+    return;
+  }
+  const uint4 r = philox4x32(make_uint4((uint32_t)cg, (uint32_t)row, (uint32_t)((uint64_t)row >> 32), 0x48535455u),
+                             make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = ((w[j >> 1] >> (16 * (j & 1))) & 0xffffu) >= d.thr ? d.scale : 0.0f;
+}
+static Drop make_drop(float ratio, uint64_t seed, int training) {
+  Drop d{seed, 0u, 1.0f};
+  if (training && ratio > 0.0f) {
+    long t = lroundf(ratio * 65536.0f);
+    if (t < 1) t = 1;
+    if (t > 65536) t = 65536;
+    d.thr = (uint32_t)t;
+    d.scale = t >= 65536 ? 0.0f : 1.0f / (1.0f - (float)t / 65536.0f);
+  }
+  return d;
+}
+
+// ---- forward: y = LN(x) [* u, dropout] ---------------------------------------------------------------------------------------------------
+template <typename T, int NV, bool MUL>
+__global__ void __launch_bounds__(kThreads) ln_fwd_kernel(const T* __restrict__ x, int64_t sx, const T* __restrict__ w, const T* __restrict__ b,
+                                                          const T* __restrict__ u, int64_t su, T* __restrict__ y, int64_t sy,
+                                                          float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int D, float eps, Drop drop) {
+  const int lane = threadIdx.x & 31;
+  const float invD = 1.0f / (float)D;
+  float wv[NV][8], bv[NV][8];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = (k * 32 + lane) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { wv[k][j] = 1.0f; bv[k][j] = 0.0f; }
+    if (c < D) {
+      if (w) V8<T>::load(w + c, wv[k]);
+      if (b) V8<T>::load(b + c, bv[k]);
+    }
+  }
+  const int64_t wstride = (int64_t)gridDim.x * kWarps;
+  for (int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); row < rows; row += wstride) {
+    float v[NV][8];
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * 8;
+      if (c < D) {
+        V8<T>::load(x + row * sx + c, v[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[k][j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[k][j] = 0.0f;
+      }
+    }
+    const float m = warp_sum(s) * invD;
+    float q = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * 8;
+      if (c < D) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[k][j] -= m; q += v[k][j] * v[k][j]; }
+      }
+    }
+    const float r = 1.0f / sqrtf(warp_sum(q) * invD + eps);
+    if (lane == 0) { mean[row] = m; rstd[row] = r; }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * 8;
+      if (c < D) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = v[k][j] * r * wv[k][j] + bv[k][j];
+        if (MUL) {
+          float uv[8], ms[8];
+          V8<T>::load(u + row * su + c, uv);
+          drop_scales(drop, row, c >> 3, ms);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = o[j] * uv[j] * ms[j];
+        }
+        V8<T>::store(y + row * sy + c, o);
+      }
+    }
+  }
+}
+
+// ---- backward: dx (+ residual gradient), [du, y], per-CTA partial dw / db -------------------------------------------------------------------
+// part[blockIdx.x][0][D] = sum over this CTA's rows of dln * xhat, part[blockIdx.x][1][D] = sum of dln   (dln = gradient at the LN output)
+template <typename T, int NV, bool MUL>
+__global__ void __launch_bounds__(kThreads) ln_bwd_kernel(const T* __restrict__ dy, int64_t sdy, const T* __restrict__ x, int64_t sx,
+                                                          const T* __restrict__ w, const T* __restrict__ b, const float* __restrict__ mean,
+                                                          const float* __restrict__ rstd, const T* __restrict__ u, int64_t su,
+                                                          const T* __restrict__ dx_add, int64_t sadd, T* __restrict__ dx, int64_t sdx,
+                                                          T* __restrict__ du, int64_t sdu, T* __restrict__ y_out, int64_t sy,
+                                                          float* __restrict__ part, int64_t rows, int D, Drop drop) {
+  extern __shared__ float red[];            // [(kWarps - 1)][D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float invD = 1.0f / (float)D;
+  float dwa[NV][8], dba[NV][8];
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dwa[k][j] = 0.0f; dba[k][j] = 0.0f; }
+  const int64_t wstride = (int64_t)gridDim.x * kWarps;
+  for (int64_t row = (int64_t)blockIdx.x * kWarps + warp; row < rows; row += wstride) {
+    const float m = mean[row], r = rstd[row];
+    float xh[NV][8], g[NV][8];              // xhat;  g: dy -> dln -> dln * w
+    float c1 = 0.0f, c2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * 8;
+      if (c < D) {
+        V8<T>::load(x + row * sx + c, xh[k]);
+        V8<T>::load(dy + row * sdy + c, g[k]);
+        float wv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { xh[k][j] = (xh[k][j] - m) * r; wv[j] = 1.0f; }
+        if (w) V8<T>::load(w + c, wv);
+        if (MUL) {
+          float uv[8], ms[8], bv[8], o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bv[j] = 0.0f;
+          if (b) V8<T>::load(b + c, bv);
+          V8<T>::load(u + row * su + c, uv);
+          drop_scales(drop, row, c >> 3, ms);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float ln = xh[k][j] * wv[j] + bv[j];
+            const float gj = g[k][j] * ms[j];          // gradient at ln * u
+            o[j] = gj * ln;                            // du
+            g[k][j] = gj * uv[j];                      // dln
+            bv[j] = ln * uv[j] * ms[j];                // y (recomputed forward output)
+          }
+          V8<T>::store(du + row * sdu + c, o);
+          if (y_out) V8<T>::store(y_out + row * sy + c, bv);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dwa[k][j] += g[k][j] * xh[k][j];
+          dba[k][j] += g[k][j];
+          g[k][j] *= wv[j];
+          c1 += g[k][j] * xh[k][j];
+          c2 += g[k][j];
+        }
+      }
+    }
+    c1 = warp_sum(c1) * invD;
+    c2 = warp_sum(c2) * invD;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * 8;
+      if (c < D) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (g[k][j] - (xh[k][j] * c1 + c2)) * r;
+        if (dx_add) {
+          float a[8];
+          V8<T>::load(dx_add + row * sadd + c, a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += a[j];
+        }
+        V8<T>::store(dx + row * sdx + c, o);
+      }
+    }
+  }
+  // CTA reduction of the weight / bias gradient partials: warps 1.. hand theirs to warp 0 through shared memory, dw then db
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    if (warp > 0) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = (k * 32 + lane) * 8;
+        if (c < D) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) red[(warp - 1) * D + c + j] = which == 0 ? dwa[k][j] : dba[k][j];
+        }
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = (k * 32 + lane) * 8;
+        if (c < D) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            o[j] = which == 0 ? dwa[k][j] : dba[k][j];
+#pragma unroll
+            for (int ww = 0; ww < kWarps - 1; ++ww) o[j] += red[ww * D + c + j];
+          }
+          V8<float>::store(part + ((int64_t)blockIdx.x * 2 + which) * D + c, o);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// dw[c] = sum_blocks part[blk][0][c], db[c] = sum_blocks part[blk][1][c]   (fixed order: bit-reproducible for a given grid)
+__global__ void colsum_kernel(const float* __restrict__ part, int nblocks, int D, float* __restrict__ dw, float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * D) return;
+  const int which = i / D, c = i - which * D;
+  float s = 0.0f;
+  for (int blk = 0; blk < nblocks; ++blk) s += part[((int64_t)blk * 2 + which) * D + c];
+  float* out = which == 0 ? dw : db;
+  if (out) out[c] = s;
+}
+
+// ---- SiLU -------------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) silu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n8) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8];
+    V8<T>::load(x + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = v[j] * sigmoidf_(v[j]);
+    V8<T>::store(y + i * 8, v);
+  }
+}
+
+struct Segs {                     // the gradient of silu's output arrives in up to 4 column segments, each with its own base / row stride
+  const void* p[4];
+  int64_t stride[4];
+  int begin[5];                   // column range of segment s: [begin[s], begin[s + 1])
+  int n;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) silu_bwd_kernel(Segs seg, const T* __restrict__ x, T* __restrict__ dx, int64_t rows, int W) {
+  const int W8 = W >> 3;
+  const int64_t n8 = rows * W8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / W8;
+    const int c = (int)(i - row * W8) * 8;
+    int s = 0;
+#pragma unroll
+    for (int t = 1; t < 4; ++t) s += (t < seg.n && c >= seg.begin[t]) ? 1 : 0;
+    float v[8], g[8];
+    V8<T>::load(x + i * 8, v);
+    V8<T>::load(reinterpret_cast<const T*>(seg.p[s]) + row * seg.stride[s] + (c - seg.begin[s]), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sg = sigmoidf_(v[j]);
+      v[j] = g[j] * sg * (1.0f + v[j] * (1.0f - sg));
+    }
+    V8<T>::store(dx + i * 8, v);
+  }
+}
+
+__global__ void dropout_mask_kernel(Drop drop, int64_t rows, int D, uint8_t* __restrict__ keep) {
+  const int D8 = D >> 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * D8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / D8;
+    const int cg = (int)(i - row * D8);
+    float m[8];
+    drop_scales(drop, row, cg, m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) keep[row * D + cg * 8 + j] = m[j] != 0.0f;
+  }
+}
+
+// ---- launch helpers ---------------------------------------------------------------------------------------------------------------------
+inline int row_grid(int64_t rows, int per_sm) {
+  const int64_t want = (rows + kWarps - 1) / kWarps;
+  const int64_t cap = (int64_t)devinfo::sm_count() * per_sm;
+  return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+inline int bwd_grid_max() { return devinfo::sm_count() * 4; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+#define GLUE_DISPATCH_NV(D, ...)                         \
+  do {                                                   \
+    if ((D) <= 256) { constexpr int NV = 1; __VA_ARGS__; } \
+    else if ((D) <= 512) { constexpr int NV = 2; __VA_ARGS__; } \
+    else { constexpr int NV = 4; __VA_ARGS__; }          \
+  } while (0)
+#define GLUE_DISPATCH_T(dtype, ...)                                        \
+  do {                                                                     \
+    if ((dtype) == 0) { using T = float; __VA_ARGS__; }                    \
+    else if ((dtype) == 1) { using T = __half; __VA_ARGS__; }              \
+    else { using T = __nv_bfloat16; __VA_ARGS__; }                         \
+  } while (0)
+
+static int check_rows(int64_t rows, int D, int dtype) {
+  if (rows < 0 || D <= 0 || (D & 7) || dtype < 0 || dtype > 2) return HSTU_ERR_ARG;
+  if (D > kMaxD) return HSTU_ERR_UNSUPPORTED;
+  return 0;
+}
+
+}  // namespace glue
+
+using namespace glue;
+
+extern "C" int64_t hstu_glue_workspace_bytes(int D) { return (int64_t)bwd_grid_max() * 2 * (int64_t)(D > 0 ? D : 0) * 4 + 256; }
+
+extern "C" int hstu_layer_norm_fwd(const void* x, int64_t x_stride, const void* weight, const void* bias, void* y, int64_t y_stride, float* mean,
+                                   float* rstd, int64_t rows, int D, float eps, int dtype, void* stream) {
+  if (int rc = check_rows(rows, D, dtype)) return rc;
+  if (!x || !y || !mean || !rstd || (x_stride & 7) || (y_stride & 7) || !aligned16(x) || !aligned16(y)) return HSTU_ERR_ARG;
+  if (rows == 0) return 0;
+  const Drop nodrop{0, 0u, 1.0f};
+  GLUE_DISPATCH_T(dtype, GLUE_DISPATCH_NV(D, (ln_fwd_kernel<T, NV, false><<<row_grid(rows, 8), kThreads, 0, (cudaStream_t)stream>>>(
+      (const T*)x, x_stride, (const T*)weight, (const T*)bias, nullptr, 0, (T*)y, y_stride, mean, rstd, rows, D, eps, nodrop))));
+  GLUE_CHECK_LAST();
+  return 0;
+}
+
+extern "C" int hstu_ln_mul_dropout_fwd(const void* x, int64_t x_stride, const void* u, int64_t u_stride, const void* weight, const void* bias, void* y,
+                                       int64_t y_stride, float* mean, float* rstd, int64_t rows, int D, float eps, float dropout_ratio,
+                                       uint64_t seed, int training, int dtype, void* stream) {
+  if (int rc = check_rows(rows, D, dtype)) return rc;
+  if (!x || !u || !y || !mean || !rstd || (x_stride & 7) || (u_stride & 7) || (y_stride & 7) || !aligned16(x) || !aligned16(u) || !aligned16(y) ||
+      dropout_ratio < 0.0f || dropout_ratio > 1.0f)
+    return HSTU_ERR_ARG;
+  if (rows == 0) return 0;
+  const Drop drop = make_drop(dropout_ratio, seed, training);
+  GLUE_DISPATCH_T(dtype, GLUE_DISPATCH_NV(D, (ln_fwd_kernel<T, NV, true><<<row_grid(rows, 8), kThreads, 0, (cudaStream_t)stream>>>(
+      (const T*)x, x_stride, (const T*)weight, (const T*)bias, (const T*)u, u_stride, (T*)y, y_stride, mean, rstd, rows, D, eps, drop))));
+  GLUE_CHECK_LAST();
+  return 0;
+}
+
+static int ln_bwd_launch(bool mul, const void* dy, int64_t sdy, const void* x, int64_t sx, const void* w, const void* b, const float* mean,
+                         const float* rstd, const void* u, int64_t su, const void* dx_add, int64_t sadd, void* dx, int64_t sdx, void* du, int64_t sdu,
+                         void* y_out, int64_t sy, float* dw, float* db, void* workspace, int64_t ws_bytes, int64_t rows, int D, Drop drop, int dtype,
+                         cudaStream_t st) {
+  const int grid = row_grid(rows, 4);
+  if (!workspace || ws_bytes < (int64_t)grid * 2 * D * 4) return HSTU_ERR_WORKSPACE;
+  float* part = reinterpret_cast<float*>(workspace);
+  const size_t smem = (size_t)(kWarps - 1) * D * sizeof(float);
+  if (mul) {
+    GLUE_DISPATCH_T(dtype, GLUE_DISPATCH_NV(D, (ln_bwd_kernel<T, NV, true><<<grid, kThreads, smem, st>>>(
+        (const T*)dy, sdy, (const T*)x, sx, (const T*)w, (const T*)b, mean, rstd, (const T*)u, su, (const T*)dx_add, sadd, (T*)dx, sdx, (T*)du, sdu,
+        (T*)y_out, sy, part, rows, D, drop))));
+  } else {
+    GLUE_DISPATCH_T(dtype, GLUE_DISPATCH_NV(D, (ln_bwd_kernel<T, NV, false><<<grid, kThreads, smem, st>>>(
+        (const T*)dy, sdy, (const T*)x, sx, (const T*)w, (const T*)b, mean, rstd, nullptr, 0, (const T*)dx_add, sadd, (T*)dx, sdx, nullptr, 0,
+        nullptr, 0, part, rows, D, drop))));
+  }
+  GLUE_CHECK_LAST();
+  if (dw || db) {
+    colsum_kernel<<<(2 * D + 255) / 256, 256, 0, st>>>(part, grid, D, dw, db);
+    GLUE_CHECK_LAST();
+  }
+  return 0;
+}
+
+extern "C" int hstu_layer_norm_bwd(const void* dy, int64_t dy_stride, const void* x, int64_t x_stride, const void* weight, const float* mean,
+                                   const float* rstd, const void* dx_add, int64_t dx_add_stride, void* dx, int64_t dx_stride, float* dweight,
+                                   float* dbias, void* workspace, int64_t workspace_bytes, int64_t rows, int D, int dtype, void* stream) {
+  if (int rc = check_rows(rows, D, dtype)) return rc;
+  if (!dy || !x || !dx || !mean || !rstd || (dy_stride & 7) || (x_stride & 7) || (dx_stride & 7) || (dx_add && (dx_add_stride & 7)) || !aligned16(dy) ||
+      !aligned16(x) || !aligned16(dx) || !aligned16(dx_add))
+    return HSTU_ERR_ARG;
+  if (rows == 0) {
+    if (dweight) cudaMemsetAsync(dweight, 0, (size_t)D * 4, (cudaStream_t)stream);
+    if (dbias) cudaMemsetAsync(dbias, 0, (size_t)D * 4, (cudaStream_t)stream);
+    return 0;
+  }
+  return ln_bwd_launch(false, dy, dy_stride, x, x_stride, weight, nullptr, mean, rstd, nullptr, 0, dx_add, dx_add_stride, dx, dx_stride, nullptr, 0,
+                       nullptr, 0, dweight, dbias, workspace, workspace_bytes, rows, D, Drop{0, 0u, 1.0f}, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int hstu_ln_mul_dropout_bwd(const void* dy, int64_t dy_stride, const void* x, int64_t x_stride, const void* u, int64_t u_stride,
+                                       const void* weight, const void* bias, const float* mean, const float* rstd, void* dx, int64_t dx_stride,
+                                       void* du, int64_t du_stride, void* y_out, int64_t y_stride, float* dweight, float* dbias, void* workspace,
+                                       int64_t workspace_bytes, int64_t rows, int D, float dropout_ratio, uint64_t seed, int training, int dtype,
+                                       void* stream) {
+  if (int rc = check_rows(rows, D, dtype)) return rc;
+  if (!dy || !x || !u || !dx || !du || !mean || !rstd || (dy_stride & 7) || (x_stride & 7) || (u_stride & 7) || (dx_stride & 7) || (du_stride & 7) ||
+      (y_out && (y_stride & 7)) || !aligned16(dy) || !aligned16(x) || !aligned16(u) || !aligned16(dx) || !aligned16(du) || !aligned16(y_out) ||
+      dropout_ratio < 0.0f || dropout_ratio > 1.0f)
+    return HSTU_ERR_ARG;
+  if (rows == 0) {
+    if (dweight) cudaMemsetAsync(dweight, 0, (size_t)D * 4, (cudaStream_t)stream);
+    if (dbias) cudaMemsetAsync(dbias, 0, (size_t)D * 4, (cudaStream_t)stream);
+    return 0;
+  }
+  return ln_bwd_launch(true, dy, dy_stride, x, x_stride, weight, bias, mean, rstd, u, u_stride, nullptr, 0, dx, dx_stride, du, du_stride, y_out,
+                       y_stride, dweight, dbias, workspace, workspace_bytes, rows, D, make_drop(dropout_ratio, seed, training), dtype,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int hstu_silu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream) {
+  if (n < 0 || (n & 7) || dtype < 0 || dtype > 2 || (n && (!x || !y)) || !aligned16(x) || !aligned16(y)) return HSTU_ERR_ARG;
+  if (n == 0) return 0;
+  const int64_t n8 = n >> 3;
+  const int64_t want = (n8 + 255) / 256, cap = (int64_t)devinfo::sm_count() * 16;
+  GLUE_DISPATCH_T(dtype, (silu_fwd_kernel<T><<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, n8)));
+  GLUE_CHECK_LAST();
+  return 0;
+}
+
+extern "C" int hstu_silu_bwd(int num_segments, const void* const* seg_ptr, const int64_t* seg_stride, const int32_t* seg_width, const void* x, void* dx,
+                             int64_t rows, int dtype, void* stream) {
+  if (num_segments < 1 || num_segments > 4 || !seg_ptr || !seg_stride || !seg_width || rows < 0 || dtype < 0 || dtype > 2) return HSTU_ERR_ARG;
+  Segs s{};
+  s.n = num_segments;
+  int W = 0;
+  for (int i = 0; i < 4; ++i) {
+    s.begin[i] = W;
+    if (i < num_segments) {
+      if (!seg_ptr[i] || seg_width[i] <= 0 || (seg_width[i] & 7) || (seg_stride[i] & 7) || !aligned16(seg_ptr[i])) return HSTU_ERR_ARG;
+      s.p[i] = seg_ptr[i];
+      s.stride[i] = seg_stride[i];
+      W += seg_width[i];
+    }
+  }
+  s.begin[4] = W;
+  for (int i = num_segments; i < 5; ++i) s.begin[i] = W;
+  if (rows == 0) return 0;
+  if (!x || !dx || !aligned16(x) || !aligned16(dx)) return HSTU_ERR_ARG;
+  const int64_t n8 = rows * (W >> 3);
+  const int64_t want = (n8 + 255) / 256, cap = (int64_t)devinfo::sm_count() * 16;
+  GLUE_DISPATCH_T(dtype, (silu_bwd_kernel<T><<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(s, (const T*)x, (T*)dx, rows, W)));
+  GLUE_CHECK_LAST();
+  return 0;
+}
+
+extern "C" int hstu_dropout_mask(int64_t rows, int D, float dropout_ratio, uint64_t seed, uint8_t* keep, void* stream) {
+  if (rows < 0 || D <= 0 || (D & 7) || !keep || dropout_ratio < 0.0f || dropout_ratio > 1.0f) return HSTU_ERR_ARG;
+  if (rows == 0) return 0;
+  const int64_t n = rows * (D >> 3);
+  const int64_t want = (n + 255) / 256, cap = (int64_t)devinfo::sm_count() * 16;
+  dropout_mask_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(make_drop(dropout_ratio, seed, 1), rows, D, keep);
+  GLUE_CHECK_LAST();
+  return 0;
+}

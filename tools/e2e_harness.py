@@ -12,6 +12,7 @@ hot paths and plain torch bf16 ops of the same shapes for everything else:
       -> mean -> backward through all of it -> fused sparse Adagrad update of the embedding rows            [arm-specific]
 
   arm "ours"      : this repo's kernels (hstu.hstu_attn_varlen_func, BatchedDynamicEmbeddingTablesV2 / RowWiseShardedDynamicEmbedding)
+  arm "ours_fused": arm "ours" with every HSTU layer run through hstu.fused_hstu_op (own layer-norm / SiLU / norm-mul-dropout kernels)
   arm "reference" : the reference's own GPU kernels, unmodified: hstu_blackwell CuTe-DSL fwd/bwd and the compiled dynamicemb_extensions
                     ops in the reference's HBM-direct op order (batched_dynamicemb_function.py:559-830, :1044-1300), exchanged with
                     torch.distributed all_to_all like TorchRec does (our input_dist host logic with the reference kernels injected).
@@ -65,6 +66,37 @@ class DenseStack(torch.nn.Module):
             a = self.attn_fn(q.view(T, HEADS, DH), k.view(T, HEADS, DH), v.view(T, HEADS, DH), cu, S)
             y = F.layer_norm(a.reshape(T, HID), (HID,)) * u
             x = y @ self.w_o[l] + x
+        return x.float().mean()
+
+
+class FusedStack(torch.nn.Module):
+    """The same stack through this repo's FusedHSTULayerFunction (hstu/fused_hstu_op.py: layer-norm / SiLU / norm-mul-dropout glue kernels of
+    csrc/hstu_glue.cu + the tcgen05 attention + cuBLAS GEMMs) — what the reference runs as its own fused layer (Triton glue + its attention,
+    examples/hstu/ops/fused_hstu_op.py).  Same weights / shapes as DenseStack; the layer norms carry affine parameters (ones / zeros) and a
+    zero uvqk bias because the fused op's signature requires them, which is slightly MORE work than DenseStack's plain F.layer_norm."""
+
+    def __init__(self, dev):
+        super().__init__()
+        g = torch.Generator(device=dev).manual_seed(42)
+        mk = lambda *s: torch.nn.Parameter((torch.randn(*s, device=dev, generator=g) * 0.02).to(torch.bfloat16))
+        self.w_in = mk(DEMB, HID)
+        self.w_uvqk = torch.nn.ParameterList([mk(HID, 4 * HID) for _ in range(LAYERS)])
+        self.w_o = torch.nn.ParameterList([mk(HID, HID) for _ in range(LAYERS)])
+        ones = lambda: torch.nn.Parameter(torch.ones(HID, device=dev, dtype=torch.bfloat16))
+        zeros = lambda n=HID: torch.nn.Parameter(torch.zeros(n, device=dev, dtype=torch.bfloat16))
+        self.in_w = torch.nn.ParameterList([ones() for _ in range(LAYERS)])
+        self.in_b = torch.nn.ParameterList([zeros() for _ in range(LAYERS)])
+        self.out_w = torch.nn.ParameterList([ones() for _ in range(LAYERS)])
+        self.out_b = torch.nn.ParameterList([zeros() for _ in range(LAYERS)])
+        self.b_uvqk = torch.nn.ParameterList([zeros(4 * HID) for _ in range(LAYERS)])
+
+    def forward(self, emb, cu, S):
+        from hstu.fused_hstu_op import fused_hstu_op
+        x = emb.to(torch.bfloat16) @ self.w_in
+        alpha = 1.0 / math.sqrt(DH)
+        for l in range(LAYERS):
+            x = fused_hstu_op(x, cu, S, S, self.w_uvqk[l], self.b_uvqk[l], self.w_o[l], HEADS, DH, DH, 1e-5, 0.0, True, self.in_w[l], self.in_b[l],
+                              self.out_w[l], self.out_b[l], None, None, None, 1, alpha, True, None, True)
         return x.float().mean()
 
 
@@ -210,9 +242,9 @@ def reference_embedding(dev, world, capacity, n_ids):
 # ---------------------------------------------------------------------------------------------------------------- driver
 def run(arm: str, dev, world: int, rank: int, steps: int = 6, warmup: int = 3, B: int = 32, S: int = 4096, capacity: int = 16 * 1024 * 1024):
     T = B * S
-    attn = ours_attention() if arm == "ours" else reference_attention()
-    emb = (ours_embedding if arm == "ours" else reference_embedding)(dev, world, capacity, T)
-    dense = DenseStack(dev, attn)
+    ours = arm in ("ours", "ours_fused")
+    emb = (ours_embedding if ours else reference_embedding)(dev, world, capacity, T)
+    dense = FusedStack(dev) if arm == "ours_fused" else DenseStack(dev, ours_attention() if ours else reference_attention())
     cu = torch.arange(0, T + 1, S, dtype=torch.int32, device=dev)
     gen = torch.Generator(device=dev).manual_seed(777 + rank)
     batches = [power_law_ids(T, gen, dev) for _ in range(steps + warmup)]
@@ -265,7 +297,7 @@ def run(arm: str, dev, world: int, rank: int, steps: int = 6, warmup: int = 3, B
 def run_both(dev, world, rank, **kw):
     out = {"config": "HSTU-large (8 layers, hidden 1024, 8 heads x 128, bf16) + DynamicEmb D=128 fp32 row-wise sharded, B=32 x S=4096 per GPU, "
                      "dense parts = torch bf16 ops of the same shapes in both arms (SURVEY 8(d) cfg 4)"}
-    for arm in ("ours", "reference"):
+    for arm in ("ours", "ours_fused", "reference"):
         try:
             out[arm] = run(arm, dev, world, rank, **kw)
         except Exception as e:  # noqa: BLE001
@@ -275,6 +307,12 @@ def run_both(dev, world, rank, **kw):
     if "ms_per_step" in out.get("ours", {}) and "ms_per_step" in out.get("reference", {}):
         out["ratio_samples_per_s_ours_over_reference"] = out["reference"]["ms_per_step"] / out["ours"]["ms_per_step"]
         out["ratio_embedding_ours_over_reference"] = out["reference"]["embedding_fwd_bwd_ms"] / out["ours"]["embedding_fwd_bwd_ms"]
+    if "ms_per_step" in out.get("ours_fused", {}) and "ms_per_step" in out.get("reference", {}):
+        # our fused layer (own glue kernels) against the reference's GPU kernels with EAGER torch glue: the reference's own fused layer uses
+        # Triton glue kernels that are not staged here, so this ratio flatters us by whatever those save; "ours" / "reference" above is the
+        # like-for-like (same eager glue on both sides) number
+        out["ratio_samples_per_s_ours_fused_over_reference_eager_glue"] = out["reference"]["ms_per_step"] / out["ours_fused"]["ms_per_step"]
+        out["fused_layer_gain_over_eager_glue_ours"] = out["ours"]["ms_per_step"] / out["ours_fused"]["ms_per_step"] if "ms_per_step" in out.get("ours", {}) else None
     return out
 
 
