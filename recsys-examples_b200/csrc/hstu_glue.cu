@@ -38,58 +38,75 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// ---- 8 consecutive elements <-> 8 floats -------------------------------------------------------------------------------------------
-template <typename T> struct V8;
-template <> struct V8<float> {
-  static __device__ __forceinline__ void load(const float* p, float* v) {
-    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+// ---- 8 consecutive elements: packed in registers (Raw8) <-> 8 floats ----------------------------------------------------------------------
+template <typename T> struct Raw8;
+template <> struct Raw8<float> { float4 a, b; };
+template <> struct Raw8<__nv_bfloat16> { uint4 r; };
+template <> struct Raw8<__half> { uint4 r; };
+
+__device__ __forceinline__ Raw8<float> load_raw(const float* p) {
+  Raw8<float> r;
+  r.a = *reinterpret_cast<const float4*>(p);
+  r.b = *reinterpret_cast<const float4*>(p + 4);
+  return r;
+}
+__device__ __forceinline__ Raw8<__nv_bfloat16> load_raw(const __nv_bfloat16* p) { Raw8<__nv_bfloat16> r; r.r = *reinterpret_cast<const uint4*>(p); return r; }
+__device__ __forceinline__ Raw8<__half> load_raw(const __half* p) { Raw8<__half> r; r.r = *reinterpret_cast<const uint4*>(p); return r; }
+
+__device__ __forceinline__ void unpack(const Raw8<float>& r, float* v) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+__device__ __forceinline__ void unpack(const Raw8<__nv_bfloat16>& r, float* v) {
+  const uint32_t w[4] = {r.r.x, r.r.y, r.r.z, r.r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {                // bf16 -> fp32 is a 16-bit shift
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
-  static __device__ __forceinline__ void store(float* p, const float* v) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void unpack(const Raw8<__half>& r, float* v) {
+  const uint32_t w[4] = {r.r.x, r.r.y, r.r.z, r.r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
   }
+}
+__device__ __forceinline__ void store8(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float* v) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ void store8(__half* p, const float* v) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+template <typename T> struct V8 {
+  static __device__ __forceinline__ void load(const T* p, float* v) { unpack(load_raw(p), v); }
+  static __device__ __forceinline__ void store(T* p, const float* v) { store8(p, v); }
 };
-template <> struct V8<__nv_bfloat16> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
-    const uint4 r = *reinterpret_cast<const uint4*>(p);
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+// a row's packed vectors: lane `lane` owns columns [(k * 32 + lane) * 8, +8) for k < NV
+template <typename T, int NV>
+__device__ __forceinline__ void load_row(const T* __restrict__ base, int lane, int D, Raw8<T>* r) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {              // bf16 -> fp32 is a 16-bit shift
-      v[2 * i] = __uint_as_float(w[i] << 16);
-      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-    }
+  for (int k = 0; k < NV; ++k) {
+    const int c = (k * 32 + lane) * 8;
+    if (c < D) r[k] = load_raw(base + c);
   }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-      w[i] = *reinterpret_cast<const uint32_t*>(&h);
-    }
-    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-};
-template <> struct V8<__half> {
-  static __device__ __forceinline__ void load(const __half* p, float* v) {
-    const uint4 r = *reinterpret_cast<const uint4*>(p);
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-      v[2 * i] = f.x; v[2 * i + 1] = f.y;
-    }
-  }
-  static __device__ __forceinline__ void store(__half* p, const float* v) {
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-      w[i] = *reinterpret_cast<const uint32_t*>(&h);
-    }
-    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-};
+}
 
 // ---- dropout mask ---------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
@@ -134,32 +151,28 @@ static Drop make_drop(float ratio, uint64_t seed, int training) {
 }
 
 // ---- forward: y = LN(x) [* u, dropout] ---------------------------------------------------------------------------------------------------
+// All global loads of a row (x and u) are issued before anything depends on them; weight / bias stay packed in registers.
 template <typename T, int NV, bool MUL>
 __global__ void __launch_bounds__(kThreads) ln_fwd_kernel(const T* __restrict__ x, int64_t sx, const T* __restrict__ w, const T* __restrict__ b,
                                                           const T* __restrict__ u, int64_t su, T* __restrict__ y, int64_t sy,
                                                           float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int D, float eps, Drop drop) {
   const int lane = threadIdx.x & 31;
   const float invD = 1.0f / (float)D;
-  float wv[NV][8], bv[NV][8];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int c = (k * 32 + lane) * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { wv[k][j] = 1.0f; bv[k][j] = 0.0f; }
-    if (c < D) {
-      if (w) V8<T>::load(w + c, wv[k]);
-      if (b) V8<T>::load(b + c, bv[k]);
-    }
-  }
+  Raw8<T> wr[NV], br[NV];
+  if (w) load_row<T, NV>(w, lane, D, wr);
+  if (b) load_row<T, NV>(b, lane, D, br);
   const int64_t wstride = (int64_t)gridDim.x * kWarps;
   for (int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); row < rows; row += wstride) {
+    Raw8<T> rx[NV], ru[NV];
+    load_row<T, NV>(x + row * sx, lane, D, rx);
+    if (MUL) load_row<T, NV>(u + row * su, lane, D, ru);
     float v[NV][8];
     float s = 0.0f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int c = (k * 32 + lane) * 8;
       if (c < D) {
-        V8<T>::load(x + row * sx + c, v[k]);
+        unpack(rx[k], v[k]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += v[k][j];
       } else {
@@ -183,17 +196,21 @@ __global__ void __launch_bounds__(kThreads) ln_fwd_kernel(const T* __restrict__ 
     for (int k = 0; k < NV; ++k) {
       const int c = (k * 32 + lane) * 8;
       if (c < D) {
-        float o[8];
+        float o[8], wv[8], bv[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = v[k][j] * r * wv[k][j] + bv[k][j];
+        for (int j = 0; j < 8; ++j) { wv[j] = 1.0f; bv[j] = 0.0f; }
+        if (w) unpack(wr[k], wv);
+        if (b) unpack(br[k], bv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = v[k][j] * r * wv[j] + bv[j];
         if (MUL) {
           float uv[8], ms[8];
-          V8<T>::load(u + row * su + c, uv);
+          unpack(ru[k], uv);
           drop_scales(drop, row, c >> 3, ms);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = o[j] * uv[j] * ms[j];
         }
-        V8<T>::store(y + row * sy + c, o);
+        store8(y + row * sy + c, o);
       }
     }
   }
@@ -201,7 +218,11 @@ __global__ void __launch_bounds__(kThreads) ln_fwd_kernel(const T* __restrict__ 
 
 // ---- backward: dx (+ residual gradient), [du, y], per-CTA partial dw / db -------------------------------------------------------------------
 // part[blockIdx.x][0][D] = sum over this CTA's rows of dln * xhat, part[blockIdx.x][1][D] = sum of dln   (dln = gradient at the LN output)
-template <typename T, int NV, bool MUL>
+// Per row: every load is issued up front (x, dy, u, residual gradient), and with PF the NEXT row's x / dy are already in flight while this
+// row's two warp reductions and stores run — at ~250 registers per thread only 8 warps fit an SM, so the latency has to be hidden
+// inside the warp (PF is off where it would spill: fp32 rows, and the LN*u backward at 1024 columns).  The row stays packed (bf16 / fp16) in registers and is unpacked where it is used; dln * w is the one fp32 array kept
+// across the reductions.
+template <typename T, int NV, bool MUL, bool PF>
 __global__ void __launch_bounds__(kThreads) ln_bwd_kernel(const T* __restrict__ dy, int64_t sdy, const T* __restrict__ x, int64_t sx,
                                                           const T* __restrict__ w, const T* __restrict__ b, const float* __restrict__ mean,
                                                           const float* __restrict__ rstd, const T* __restrict__ u, int64_t su,
@@ -216,46 +237,65 @@ __global__ void __launch_bounds__(kThreads) ln_bwd_kernel(const T* __restrict__ 
   for (int k = 0; k < NV; ++k)
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dwa[k][j] = 0.0f; dba[k][j] = 0.0f; }
+  Raw8<T> wr[NV], br[NV];
+  if (w) load_row<T, NV>(w, lane, D, wr);
+  if (MUL && b) load_row<T, NV>(b, lane, D, br);
   const int64_t wstride = (int64_t)gridDim.x * kWarps;
-  for (int64_t row = (int64_t)blockIdx.x * kWarps + warp; row < rows; row += wstride) {
-    const float m = mean[row], r = rstd[row];
-    float xh[NV][8], g[NV][8];              // xhat;  g: dy -> dln -> dln * w
+  int64_t row = (int64_t)blockIdx.x * kWarps + warp;
+  Raw8<T> rx[NV], rdy[NV], nx[NV], ndy[NV];
+  float m = 0.0f, r = 0.0f, nm = 0.0f, nr = 0.0f;
+  if (row < rows) {
+    load_row<T, NV>(x + row * sx, lane, D, rx);
+    load_row<T, NV>(dy + row * sdy, lane, D, rdy);
+    m = mean[row]; r = rstd[row];
+  }
+  for (; row < rows; row += wstride) {
+    Raw8<T> ru[NV], radd[NV];
+    if (MUL) load_row<T, NV>(u + row * su, lane, D, ru);
+    if (dx_add) load_row<T, NV>(dx_add + row * sadd, lane, D, radd);
+    const int64_t nrow = row + wstride;
+    if (PF && nrow < rows) {
+      load_row<T, NV>(x + nrow * sx, lane, D, nx);
+      load_row<T, NV>(dy + nrow * sdy, lane, D, ndy);
+      nm = mean[nrow]; nr = rstd[nrow];
+    }
+    float gw[NV][8];                        // dln * w
     float c1 = 0.0f, c2 = 0.0f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int c = (k * 32 + lane) * 8;
       if (c < D) {
-        V8<T>::load(x + row * sx + c, xh[k]);
-        V8<T>::load(dy + row * sdy + c, g[k]);
-        float wv[8];
+        float xh[8], g[8], wv[8];
+        unpack(rx[k], xh);
+        unpack(rdy[k], g);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { xh[k][j] = (xh[k][j] - m) * r; wv[j] = 1.0f; }
-        if (w) V8<T>::load(w + c, wv);
+        for (int j = 0; j < 8; ++j) { xh[j] = (xh[j] - m) * r; wv[j] = 1.0f; }
+        if (w) unpack(wr[k], wv);
         if (MUL) {
           float uv[8], ms[8], bv[8], o[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) bv[j] = 0.0f;
-          if (b) V8<T>::load(b + c, bv);
-          V8<T>::load(u + row * su + c, uv);
+          if (b) unpack(br[k], bv);
+          unpack(ru[k], uv);
           drop_scales(drop, row, c >> 3, ms);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float ln = xh[k][j] * wv[j] + bv[j];
-            const float gj = g[k][j] * ms[j];          // gradient at ln * u
+            const float ln = xh[j] * wv[j] + bv[j];
+            const float gj = g[j] * ms[j];             // gradient at ln * u
             o[j] = gj * ln;                            // du
-            g[k][j] = gj * uv[j];                      // dln
+            g[j] = gj * uv[j];                         // dln
             bv[j] = ln * uv[j] * ms[j];                // y (recomputed forward output)
           }
-          V8<T>::store(du + row * sdu + c, o);
-          if (y_out) V8<T>::store(y_out + row * sy + c, bv);
+          store8(du + row * sdu + c, o);
+          if (y_out) store8(y_out + row * sy + c, bv);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          dwa[k][j] += g[k][j] * xh[k][j];
-          dba[k][j] += g[k][j];
-          g[k][j] *= wv[j];
-          c1 += g[k][j] * xh[k][j];
-          c2 += g[k][j];
+          dwa[k][j] += g[j] * xh[j];
+          dba[k][j] += g[j];
+          gw[k][j] = g[j] * wv[j];
+          c1 += gw[k][j] * xh[j];
+          c2 += gw[k][j];
         }
       }
     }
@@ -265,17 +305,27 @@ __global__ void __launch_bounds__(kThreads) ln_bwd_kernel(const T* __restrict__ 
     for (int k = 0; k < NV; ++k) {
       const int c = (k * 32 + lane) * 8;
       if (c < D) {
-        float o[8];
+        float xh[8], o[8];
+        unpack(rx[k], xh);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (g[k][j] - (xh[k][j] * c1 + c2)) * r;
+        for (int j = 0; j < 8; ++j) o[j] = (gw[k][j] - ((xh[j] - m) * r * c1 + c2)) * r;
         if (dx_add) {
           float a[8];
-          V8<T>::load(dx_add + row * sadd + c, a);
+          unpack(radd[k], a);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] += a[j];
         }
-        V8<T>::store(dx + row * sdx + c, o);
+        store8(dx + row * sdx + c, o);
       }
+    }
+    if (PF) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) { rx[k] = nx[k]; rdy[k] = ndy[k]; }
+      m = nm; r = nr;
+    } else if (nrow < rows) {
+      load_row<T, NV>(x + nrow * sx, lane, D, rx);
+      load_row<T, NV>(dy + nrow * sdy, lane, D, rdy);
+      m = mean[nrow]; r = rstd[nrow];
     }
   }
   // CTA reduction of the weight / bias gradient partials: warps 1.. hand theirs to warp 0 through shared memory, dw then db
@@ -304,7 +354,7 @@ __global__ void __launch_bounds__(kThreads) ln_bwd_kernel(const T* __restrict__ 
 #pragma unroll
             for (int ww = 0; ww < kWarps - 1; ++ww) o[j] += red[ww * D + c + j];
           }
-          V8<float>::store(part + ((int64_t)blockIdx.x * 2 + which) * D + c, o);
+          store8(part + ((int64_t)blockIdx.x * 2 + which) * D + c, o);
         }
       }
     }
@@ -414,8 +464,8 @@ extern "C" int64_t hstu_glue_workspace_bytes(int D) { return (int64_t)bwd_grid_m
 extern "C" int hstu_layer_norm_fwd(const void* x, int64_t x_stride, const void* weight, const void* bias, void* y, int64_t y_stride, float* mean,
                                    float* rstd, int64_t rows, int D, float eps, int dtype, void* stream) {
   if (int rc = check_rows(rows, D, dtype)) return rc;
-  if (!x || !y || !mean || !rstd || (x_stride & 7) || (y_stride & 7) || !aligned16(x) || !aligned16(y)) return HSTU_ERR_ARG;
   if (rows == 0) return 0;
+  if (!x || !y || !mean || !rstd || (x_stride & 7) || (y_stride & 7) || !aligned16(x) || !aligned16(y)) return HSTU_ERR_ARG;
   const Drop nodrop{0, 0u, 1.0f};
   GLUE_DISPATCH_T(dtype, GLUE_DISPATCH_NV(D, (ln_fwd_kernel<T, NV, false><<<row_grid(rows, 8), kThreads, 0, (cudaStream_t)stream>>>(
       (const T*)x, x_stride, (const T*)weight, (const T*)bias, nullptr, 0, (T*)y, y_stride, mean, rstd, rows, D, eps, nodrop))));
@@ -427,6 +477,7 @@ extern "C" int hstu_ln_mul_dropout_fwd(const void* x, int64_t x_stride, const vo
                                        int64_t y_stride, float* mean, float* rstd, int64_t rows, int D, float eps, float dropout_ratio,
                                        uint64_t seed, int training, int dtype, void* stream) {
   if (int rc = check_rows(rows, D, dtype)) return rc;
+  if (rows == 0) return 0;
   if (!x || !u || !y || !mean || !rstd || (x_stride & 7) || (u_stride & 7) || (y_stride & 7) || !aligned16(x) || !aligned16(u) || !aligned16(y) ||
       dropout_ratio < 0.0f || dropout_ratio > 1.0f)
     return HSTU_ERR_ARG;
@@ -447,11 +498,11 @@ static int ln_bwd_launch(bool mul, const void* dy, int64_t sdy, const void* x, i
   float* part = reinterpret_cast<float*>(workspace);
   const size_t smem = (size_t)(kWarps - 1) * D * sizeof(float);
   if (mul) {
-    GLUE_DISPATCH_T(dtype, GLUE_DISPATCH_NV(D, (ln_bwd_kernel<T, NV, true><<<grid, kThreads, smem, st>>>(
+    GLUE_DISPATCH_T(dtype, GLUE_DISPATCH_NV(D, (ln_bwd_kernel<T, NV, true, (sizeof(T) == 2 && NV <= 2)><<<grid, kThreads, smem, st>>>(
         (const T*)dy, sdy, (const T*)x, sx, (const T*)w, (const T*)b, mean, rstd, (const T*)u, su, (const T*)dx_add, sadd, (T*)dx, sdx, (T*)du, sdu,
         (T*)y_out, sy, part, rows, D, drop))));
   } else {
-    GLUE_DISPATCH_T(dtype, GLUE_DISPATCH_NV(D, (ln_bwd_kernel<T, NV, false><<<grid, kThreads, smem, st>>>(
+    GLUE_DISPATCH_T(dtype, GLUE_DISPATCH_NV(D, (ln_bwd_kernel<T, NV, false, (sizeof(T) == 2)><<<grid, kThreads, smem, st>>>(
         (const T*)dy, sdy, (const T*)x, sx, (const T*)w, (const T*)b, mean, rstd, nullptr, 0, (const T*)dx_add, sadd, (T*)dx, sdx, nullptr, 0,
         nullptr, 0, part, rows, D, drop))));
   }
@@ -467,14 +518,14 @@ extern "C" int hstu_layer_norm_bwd(const void* dy, int64_t dy_stride, const void
                                    const float* rstd, const void* dx_add, int64_t dx_add_stride, void* dx, int64_t dx_stride, float* dweight,
                                    float* dbias, void* workspace, int64_t workspace_bytes, int64_t rows, int D, int dtype, void* stream) {
   if (int rc = check_rows(rows, D, dtype)) return rc;
-  if (!dy || !x || !dx || !mean || !rstd || (dy_stride & 7) || (x_stride & 7) || (dx_stride & 7) || (dx_add && (dx_add_stride & 7)) || !aligned16(dy) ||
-      !aligned16(x) || !aligned16(dx) || !aligned16(dx_add))
-    return HSTU_ERR_ARG;
   if (rows == 0) {
     if (dweight) cudaMemsetAsync(dweight, 0, (size_t)D * 4, (cudaStream_t)stream);
     if (dbias) cudaMemsetAsync(dbias, 0, (size_t)D * 4, (cudaStream_t)stream);
     return 0;
   }
+  if (!dy || !x || !dx || !mean || !rstd || (dy_stride & 7) || (x_stride & 7) || (dx_stride & 7) || (dx_add && (dx_add_stride & 7)) || !aligned16(dy) ||
+      !aligned16(x) || !aligned16(dx) || !aligned16(dx_add))
+    return HSTU_ERR_ARG;
   return ln_bwd_launch(false, dy, dy_stride, x, x_stride, weight, nullptr, mean, rstd, nullptr, 0, dx_add, dx_add_stride, dx, dx_stride, nullptr, 0,
                        nullptr, 0, dweight, dbias, workspace, workspace_bytes, rows, D, Drop{0, 0u, 1.0f}, dtype, (cudaStream_t)stream);
 }
@@ -485,15 +536,15 @@ extern "C" int hstu_ln_mul_dropout_bwd(const void* dy, int64_t dy_stride, const 
                                        int64_t workspace_bytes, int64_t rows, int D, float dropout_ratio, uint64_t seed, int training, int dtype,
                                        void* stream) {
   if (int rc = check_rows(rows, D, dtype)) return rc;
-  if (!dy || !x || !u || !dx || !du || !mean || !rstd || (dy_stride & 7) || (x_stride & 7) || (u_stride & 7) || (dx_stride & 7) || (du_stride & 7) ||
-      (y_out && (y_stride & 7)) || !aligned16(dy) || !aligned16(x) || !aligned16(u) || !aligned16(dx) || !aligned16(du) || !aligned16(y_out) ||
-      dropout_ratio < 0.0f || dropout_ratio > 1.0f)
-    return HSTU_ERR_ARG;
   if (rows == 0) {
     if (dweight) cudaMemsetAsync(dweight, 0, (size_t)D * 4, (cudaStream_t)stream);
     if (dbias) cudaMemsetAsync(dbias, 0, (size_t)D * 4, (cudaStream_t)stream);
     return 0;
   }
+  if (!dy || !x || !u || !dx || !du || !mean || !rstd || (dy_stride & 7) || (x_stride & 7) || (u_stride & 7) || (dx_stride & 7) || (du_stride & 7) ||
+      (y_out && (y_stride & 7)) || !aligned16(dy) || !aligned16(x) || !aligned16(u) || !aligned16(dx) || !aligned16(du) || !aligned16(y_out) ||
+      dropout_ratio < 0.0f || dropout_ratio > 1.0f)
+    return HSTU_ERR_ARG;
   return ln_bwd_launch(true, dy, dy_stride, x, x_stride, weight, bias, mean, rstd, u, u_stride, nullptr, 0, dx, dx_stride, du, du_stride, y_out,
                        y_stride, dweight, dbias, workspace, workspace_bytes, rows, D, make_drop(dropout_ratio, seed, training), dtype,
                        (cudaStream_t)stream);

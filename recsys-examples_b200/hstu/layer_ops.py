@@ -74,6 +74,8 @@ def weighted_layer_norm_fwd(x: torch.Tensor, weight: Optional[torch.Tensor], bia
     mean = torch.empty(n, dtype=torch.float32, device=x.device) if mean is None else mean
     rstd = torch.empty(n, dtype=torch.float32, device=x.device) if rstd is None else rstd
     w, b = _param(weight, x), _param(bias, x)
+    if n == 0:
+        return y, mean, rstd, 0, 0
     _check(N.launch("hstu_layer_norm_fwd", 1, N.lib.hstu_layer_norm_fwd, N.ptr(x), x.stride(0), N.ptr(w), N.ptr(b), N.ptr(y), y.stride(0), N.ptr(mean),
                     N.ptr(rstd), n, D, float(eps), _DTYPE[x.dtype], N.stream()), "layer_norm_fwd")
     return y, mean, rstd, 0, 0

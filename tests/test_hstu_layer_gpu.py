@@ -179,8 +179,8 @@ def test_fused_hstu_layer_matches_fp32_reference(cuda, recompute, with_targets):
     bf = lambda t: t.to(torch.bfloat16)                                           # noqa: E731
 
     def run(dtype, fused):
-        x = x32.to(dtype).requires_grad_(True)
-        p = {k: v.to(dtype).requires_grad_(True) for k, v in p32.items()}
+        x = x32.detach().clone().to(dtype).requires_grad_(True)            # fresh leaves every run
+        p = {k: v.detach().clone().to(dtype).requires_grad_(True) for k, v in p32.items()}
         if fused:
             out = fused_hstu_op(x, cu, S, S, p["w_uvqk"], p["b_uvqk"], p["w_proj"], H, Dh, Dh, eps, 0.0, True, p["in_w"], p["in_b"], p["out_w"], p["out_b"],
                                 None, nt, None, 1, alpha, True, None, True, None, None, recompute[0], recompute[1])
