@@ -162,10 +162,25 @@ __global__ void __launch_bounds__(kThreads) ln_fwd_kernel(const T* __restrict__ 
   if (w) load_row<T, NV>(w, lane, D, wr);
   if (b) load_row<T, NV>(b, lane, D, br);
   const int64_t wstride = (int64_t)gridDim.x * kWarps;
-  for (int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); row < rows; row += wstride) {
-    Raw8<T> rx[NV], ru[NV];
+  constexpr bool PF = false;                // row-ahead prefetch (as in the backward) costs 10-31 registers here (ptxas: 128 -> 138, 162 -> 193) = one
+                                            // resident CTA fewer per SM; with 12-16 warps per SM the other warps already cover the load latency: not enabled
+  int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  Raw8<T> rx[NV], ru[NV], nx[NV], nu[NV];
+  if (PF && row < rows) {
     load_row<T, NV>(x + row * sx, lane, D, rx);
     if (MUL) load_row<T, NV>(u + row * su, lane, D, ru);
+  }
+  for (; row < rows; row += wstride) {
+    if (PF) {
+      const int64_t nrow = row + wstride;
+      if (nrow < rows) {
+        load_row<T, NV>(x + nrow * sx, lane, D, nx);
+        if (MUL) load_row<T, NV>(u + nrow * su, lane, D, nu);
+      }
+    } else {
+      load_row<T, NV>(x + row * sx, lane, D, rx);
+      if (MUL) load_row<T, NV>(u + row * su, lane, D, ru);
+    }
     float v[NV][8];
     float s = 0.0f;
 #pragma unroll
@@ -212,6 +227,10 @@ __global__ void __launch_bounds__(kThreads) ln_fwd_kernel(const T* __restrict__ 
         }
         store8(y + row * sy + c, o);
       }
+    }
+    if (PF) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) { rx[k] = nx[k]; if (MUL) ru[k] = nu[k]; }
     }
   }
 }
@@ -376,14 +395,28 @@ __global__ void colsum_kernel(const float* __restrict__ part, int nblocks, int D
 // ---- SiLU -------------------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+constexpr int kSiluUnroll = 4;            // independent 16-byte vectors in flight per thread
 template <typename T>
 __global__ void __launch_bounds__(256) silu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n8) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
-    float v[8];
-    V8<T>::load(x + i * 8, v);
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n8; i0 += step * kSiluUnroll) {
+    Raw8<T> r[kSiluUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = v[j] * sigmoidf_(v[j]);
-    V8<T>::store(y + i * 8, v);
+    for (int t = 0; t < kSiluUnroll; ++t) {
+      const int64_t i = i0 + t * step;
+      if (i < n8) r[t] = load_raw(x + i * 8);
+    }
+#pragma unroll
+    for (int t = 0; t < kSiluUnroll; ++t) {
+      const int64_t i = i0 + t * step;
+      if (i < n8) {
+        float v[8];
+        unpack(r[t], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = v[j] * sigmoidf_(v[j]);
+        store8(y + i * 8, v);
+      }
+    }
   }
 }
 
@@ -397,21 +430,41 @@ template <typename T>
 __global__ void __launch_bounds__(256) silu_bwd_kernel(Segs seg, const T* __restrict__ x, T* __restrict__ dx, int64_t rows, int W) {
   const int W8 = W >> 3;
   const int64_t n8 = rows * W8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / W8;
-    const int c = (int)(i - row * W8) * 8;
-    int s = 0;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  constexpr int U = 2;                      // two (x, dy) vector pairs in flight per thread
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n8; i0 += step * U) {
+    Raw8<T> rx[U], rg[U];
 #pragma unroll
-    for (int t = 1; t < 4; ++t) s += (t < seg.n && c >= seg.begin[t]) ? 1 : 0;
-    float v[8], g[8];
-    V8<T>::load(x + i * 8, v);
-    V8<T>::load(reinterpret_cast<const T*>(seg.p[s]) + row * seg.stride[s] + (c - seg.begin[s]), g);
+    for (int t = 0; t < U; ++t) {
+      const int64_t i = i0 + t * step;
+      if (i < n8) {
+        const int64_t row = i / W8;
+        const int c = (int)(i - row * W8) * 8;
+        const void* gp = seg.p[0];            // segment select by compares: a dynamic index would copy the parameter struct to local memory
+        int64_t gs = seg.stride[0];
+        int gb = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float sg = sigmoidf_(v[j]);
-      v[j] = g[j] * sg * (1.0f + v[j] * (1.0f - sg));
+        for (int q = 1; q < 4; ++q)
+          if (q < seg.n && c >= seg.begin[q]) { gp = seg.p[q]; gs = seg.stride[q]; gb = seg.begin[q]; }
+        rx[t] = load_raw(x + i * 8);
+        rg[t] = load_raw(reinterpret_cast<const T*>(gp) + row * gs + (c - gb));
+      }
     }
-    V8<T>::store(dx + i * 8, v);
+#pragma unroll
+    for (int t = 0; t < U; ++t) {
+      const int64_t i = i0 + t * step;
+      if (i < n8) {
+        float v[8], g[8];
+        unpack(rx[t], v);
+        unpack(rg[t], g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float sg = sigmoidf_(v[j]);
+          v[j] = g[j] * sg * (1.0f + v[j] * (1.0f - sg));
+        }
+        store8(dx + i * 8, v);
+      }
+    }
   }
 }
 
