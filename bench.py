@@ -822,6 +822,12 @@ def main():
             batches = host_batches = None
             torch.cuda.empty_cache()
             line["hstu_attn"] = bench_hstu(dev, tfl)
+            try:                                   # HSTU layer glue kernels at the HSTU-large shape, eager torch beside them
+                torch.cuda.empty_cache()
+                from tools import bench_hstu_glue
+                line["hstu_layer_glue"] = bench_hstu_glue.run(dev)
+            except Exception as e:  # noqa: BLE001
+                line["hstu_layer_glue"] = {"error": repr(e)[:300]}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -33,3 +33,34 @@ def run():
     # --- HSTU attention fwd+bwd, vs oracle
     from tests import smoke_hstu
     smoke_hstu.run(dev)
+
+    # --- HSTU layer glue: one fused layer (layer norm -> uvqk GEMM -> SiLU -> attention -> LN*u -> proj + residual) fwd + bwd vs fp32 torch
+    import math
+    import torch.nn.functional as F
+    from hstu.fused_hstu_op import fused_hstu_op
+    from oracle.hstu_attn import hstu_attention
+    H, Dh, HID = 2, 64, 128
+    cu = torch.tensor([0, 90, 200], dtype=torch.int32, device=dev)
+    T, S, alpha = 200, 128, 1.0 / math.sqrt(Dh)
+    g = torch.Generator(device=dev).manual_seed(5)
+    mk = lambda *s, sc=1.0: (torch.randn(*s, device=dev, generator=g) * sc).to(torch.bfloat16)      # noqa: E731
+    x, dout = mk(T, HID), mk(T, HID)
+    P = dict(w_uvqk=mk(HID, 4 * H * Dh, sc=0.1), b_uvqk=mk(4 * H * Dh, sc=0.1), w_proj=mk(H * Dh, HID, sc=0.1), in_w=1 + mk(HID, sc=0.1),
+             in_b=mk(HID, sc=0.1), out_w=1 + mk(H * Dh, sc=0.1), out_b=mk(H * Dh, sc=0.1))
+    xq = x.clone().requires_grad_(True)
+    pq = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    out = fused_hstu_op(xq, cu, S, S, pq["w_uvqk"], pq["b_uvqk"], pq["w_proj"], H, Dh, Dh, 1e-5, 0.0, True, pq["in_w"], pq["in_b"], pq["out_w"], pq["out_b"],
+                        None, None, None, 1, alpha)
+    out.backward(dout)
+    xr = x.float().requires_grad_(True)
+    pr = {k: v.float().requires_grad_(True) for k, v in P.items()}
+    n = F.layer_norm(xr, (HID,), pr["in_w"], pr["in_b"], 1e-5)
+    u, v, q, k = F.silu(torch.addmm(pr["b_uvqk"], n, pr["w_uvqk"])).split(H * Dh, dim=-1)
+    a = hstu_attention(q.reshape(T, H, Dh), k.reshape(T, H, Dh), v.reshape(T, H, Dh), cu, S, alpha, S)
+    ref = torch.addmm(xr, F.layer_norm(a.reshape(T, H * Dh), (H * Dh,), pr["out_w"], pr["out_b"], 1e-5) * u, pr["w_proj"])
+    ref.backward(dout.float())
+    for name, got, want in [("out", out, ref), ("d_input", xq.grad, xr.grad), ("d_w_uvqk", pq["w_uvqk"].grad, pr["w_uvqk"].grad),
+                            ("d_out_w", pq["out_w"].grad, pr["out_w"].grad)]:
+        err, scale = (got.float() - want).abs().max().item(), want.abs().max().item()
+        assert err <= 0.06 * scale + 1e-3, f"fused HSTU layer {name}: max abs err {err:.3e} against scale {scale:.3e}"
+    print("smoke: hstu fused layer ok")

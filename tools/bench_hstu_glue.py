@@ -31,9 +31,9 @@ def timeit(fn, iters=20, warm=5):
     return e0.elapsed_time(e1) / iters
 
 
-def main():
+def run(dev=None):
     from hstu import layer_ops as L
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", 0) if dev is None else dev
     T, D, W = 32 * 4096, 1024, 4096
     peak = 6586.1
     try:
@@ -90,8 +90,8 @@ def main():
     t_nf = timeit(lambda: F.layer_norm(xg, (D,), wg, bg, 1e-5) * ug)
     rec("ln_mul_dropout_bwd (dx, du, dw, db + recomputed y)", timeit(lambda: L.layer_norm_mul_dropout_bwd(dy, x, u, w, b, m2, r2, 0, 0, 1e-5, True, 0.0, seed,
                                                                                                       False, True)), 6 * rowb, timeit(torch_nmd_bwd) - t_nf)
-    print(json.dumps(out))
+    return out
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(run()))
