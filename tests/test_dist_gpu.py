@@ -207,6 +207,31 @@ def test_sharded_world1_matches_unsharded(cuda):
             assert torch.equal(out, o) and torch.equal(loss, l)
             assert torch.equal(la.tables.table_storage_, lb.tables.table_storage_) and torch.equal(la._values, lb._values)
         ma.check(); mb.check()
+        # ---- checkpoint through the wrapper (dynamicemb/checkpoint.py): every rank dumps its own shard under the process group's rank /
+        # world size, the meta file carries the WRAPPER's dist_type; a fresh wrapper loads it back to identical lookups
+        import json
+        import tempfile
+        from dynamicemb import checkpoint as ck
+        with tempfile.TemporaryDirectory() as ckdir:
+            mb.dump(ckdir, optim=True)
+            name = lb.table_names[0]
+            assert json.load(open(ck.encode_meta_json_file_path(ckdir, name)))["dist_type"] == "hash_roundrobin"
+            for item in ("keys", "values", "scores", "opt_values"):
+                assert os.path.getsize(ck.encode_checkpoint_file_path(ckdir, name, 0, 1, item)) > 0
+            lc = _mk(cuda, 1 << 17, DynamicEmbPoolingMode.NONE, EmbOptimType.EXACT_ADAGRAD, 0.05)      # another capacity: other slots
+            mc = RowWiseShardedDynamicEmbedding(lc, None, max_ids_per_step=4096)
+            mc.load(ckdir, optim=True)
+            lc.train()
+            with torch.no_grad():
+                for b in batches[:3]:
+                    assert torch.equal(mb(b, lengths), mc(b, lengths))
+            ka, va = lb.export_keys_values(0)
+            kc, vc = lc.export_keys_values(0)
+            oa, oc = torch.argsort(ka), torch.argsort(kc)
+            assert torch.equal(ka[oa], kc[oc]) and torch.equal(va[oa], vc[oc])            # embeddings AND Adagrad accumulators
+            lo = _mk(cuda, 1 << 16, DynamicEmbPoolingMode.NONE, EmbOptimType.EXACT_ADAGRAD, 0.05)
+            with pytest.raises(ValueError, match="dist_type mismatch"):                      # an unsharded module defaults to roundrobin
+                lo.load(ckdir)
         # ---- planner + sharder classes (reference names: planner/planner.py:213, shard/embedding.py:343, shard/embeddingbag.py:79): a row-wise
         # plan for two tables, sharder.shard() builds the rank's module from the (duck-typed) TorchRec configs and returns the wrapper
         from dynamicemb import DynamicEmbInitializerArgs, DynamicEmbInitializerMode, DynamicEmbScoreStrategy, DynamicEmbTableOptions
