@@ -79,6 +79,13 @@ int hstu_silu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream);
  * each a multiple of 8) — du / dv / dq / dk are read where their producers left them; x, dx contiguous [rows, W] */
 int hstu_silu_bwd(int num_segments, const void* const* seg_ptr, const int64_t* seg_stride, const int32_t* seg_width, const void* x, void* dx,
                   int64_t rows, int dtype, void* stream);
+/* the same with the column sums of dx on the way: dbias[W] (fp32) = sum over rows of dx — the bias gradient of the GEMM in front of the SiLU
+ * (`dy = torch.sum(dz, dim=0)` in triton_addmm_silu_bwd, triton_addmm.py:293-294: a separate pass over dz there).  Needs
+ * hstu_silu_bwd_bias_workspace_bytes(W) bytes of scratch; that query returns 0 when W / 8 cannot be made to divide the launch (then call
+ * hstu_silu_bwd and sum separately; HSTU_ERR_UNSUPPORTED from this entry point). */
+int64_t hstu_silu_bwd_bias_workspace_bytes(int W);
+int hstu_silu_bwd_bias(int num_segments, const void* const* seg_ptr, const int64_t* seg_stride, const int32_t* seg_width, const void* x, void* dx,
+                       float* dbias, void* workspace, int64_t workspace_bytes, int64_t rows, int dtype, void* stream);
 /* test aid: keep[rows, D] (uint8) = the dropout mask the two ln_mul_dropout calls apply for (ratio, seed) */
 int hstu_dropout_mask(int64_t rows, int D, float dropout_ratio, uint64_t seed, uint8_t* keep, void* stream);
 

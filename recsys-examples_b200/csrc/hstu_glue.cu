@@ -239,7 +239,9 @@ __global__ void __launch_bounds__(kThreads) ln_fwd_kernel(const T* __restrict__ 
 // part[blockIdx.x][0][D] = sum over this CTA's rows of dln * xhat, part[blockIdx.x][1][D] = sum of dln   (dln = gradient at the LN output)
 // Per row: every load is issued up front (x, dy, u, residual gradient), and with PF the NEXT row's x / dy are already in flight while this
 // row's two warp reductions and stores run — at ~250 registers per thread only 8 warps fit an SM, so the latency has to be hidden
-// inside the warp (PF is off where it would spill: fp32 rows, and the LN*u backward at 1024 columns).  The row stays packed (bf16 / fp16) in registers and is unpacked where it is used; dln * w is the one fp32 array kept
+// inside the warp (PF is off where it would spill: fp32 rows, and the LN*u backward at 1024 columns — moving its dw / db accumulators to
+// shared memory was tried and does NOT remove those spills: ptxas stays at 255 registers + 240 B, the pressure is the unrolled per-row
+// temporaries, not the accumulators).  The row stays packed (bf16 / fp16) in registers and is unpacked where it is used; dln * w is the one fp32 array kept
 // across the reductions.
 template <typename T, int NV, bool MUL, bool PF>
 __global__ void __launch_bounds__(kThreads) ln_bwd_kernel(const T* __restrict__ dy, int64_t sdy, const T* __restrict__ x, int64_t sx,
@@ -450,12 +452,19 @@ struct Segs {                     // the gradient of silu's output arrives in up
   int begin[5];                   // column range of segment s: [begin[s], begin[s + 1])
   int n;
 };
-template <typename T>
-__global__ void __launch_bounds__(256) silu_bwd_kernel(Segs seg, const T* __restrict__ x, T* __restrict__ dx, int64_t rows, int W) {
+// COLSUM: the launcher makes gridDim.x * 256 a multiple of W / 8, so every vector of a thread lies in the SAME 8 columns; the thread sums its
+// dx values per column and leaves them in colpart[(blockIdx.x * 256 + threadIdx.x)][8] — read as a [gridDim.x * 256 / (W / 8)][W] matrix of
+// partial column sums, reduced by colsum_rows_kernel.  That is the uvqk bias gradient (dz.sum(0) in the reference, a separate pass over 1 GB).
+template <typename T, bool COLSUM>
+__global__ void __launch_bounds__(256) silu_bwd_kernel(Segs seg, const T* __restrict__ x, T* __restrict__ dx, int64_t rows, int W,
+                                                       float* __restrict__ colpart) {
   const int W8 = W >> 3;
   const int64_t n8 = rows * W8;
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
   constexpr int U = 2;                      // two (x, dy) vector pairs in flight per thread
+  float bacc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bacc[j] = 0.0f;
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n8; i0 += step * U) {
     Raw8<T> rx[U], rg[U];
 #pragma unroll
@@ -485,10 +494,30 @@ __global__ void __launch_bounds__(256) silu_bwd_kernel(Segs seg, const T* __rest
         for (int j = 0; j < 8; ++j) {
           const float sg = sigmoid_t<T>(v[j]);
           v[j] = g[j] * sg * (1.0f + v[j] * (1.0f - sg));
+          if (COLSUM) bacc[j] += v[j];
         }
         store8(dx + i * 8, v);
       }
     }
+  }
+  if (COLSUM) store8(colpart + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8, bacc);
+}
+
+// out[c] = sum_r part[r][c] for a row-major [nrows][ncols] matrix of partial sums; 32 columns x 32 row lanes per CTA, fixed combine order
+__global__ void __launch_bounds__(1024) colsum_rows_kernel(const float* __restrict__ part, int nrows, int ncols, float* __restrict__ out) {
+  __shared__ float sm[32][33];
+  const int cx = threadIdx.x & 31, cy = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float s = 0.0f;
+  if (c < ncols)
+    for (int r = cy; r < nrows; r += 32) s += part[(int64_t)r * ncols + c];
+  sm[cy][cx] = s;
+  __syncthreads();
+  if (cy == 0 && c < ncols) {
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += sm[k][cx];
+    out[c] = t;
   }
 }
 
@@ -637,8 +666,26 @@ extern "C" int hstu_silu_fwd(const void* x, void* y, int64_t n, int dtype, void*
   return 0;
 }
 
-extern "C" int hstu_silu_bwd(int num_segments, const void* const* seg_ptr, const int64_t* seg_stride, const int32_t* seg_width, const void* x, void* dx,
-                             int64_t rows, int dtype, void* stream) {
+// grid for the column-sum variant: a multiple of q = (W/8) / gcd(W/8, 256) blocks, so that gridDim.x * 256 is a multiple of W/8; 0 = not possible
+static int silu_colsum_grid(int W, int64_t n8) {
+  const int W8 = W >> 3;
+  int a = W8, b = 256;
+  while (b) { const int t = a % b; a = b; b = t; }
+  const int64_t q = W8 / a, cap = (int64_t)devinfo::sm_count() * 16;
+  if (q > cap) return 0;
+  int64_t want = ((n8 + 255) / 256 + q - 1) / q * q;
+  const int64_t most = cap / q * q;
+  if (want > most) want = most;
+  return (int)(want < q ? q : want);
+}
+extern "C" int64_t hstu_silu_bwd_bias_workspace_bytes(int W) {
+  if (W <= 0 || (W & 7)) return 0;
+  const int g = silu_colsum_grid(W, (int64_t)1 << 40);
+  return g == 0 ? 0 : (int64_t)g * 256 * 8 * 4 + 256;
+}
+
+static int silu_bwd_impl(int num_segments, const void* const* seg_ptr, const int64_t* seg_stride, const int32_t* seg_width, const void* x, void* dx,
+                         float* dbias, void* workspace, int64_t workspace_bytes, int64_t rows, int dtype, void* stream) {
   if (num_segments < 1 || num_segments > 4 || !seg_ptr || !seg_stride || !seg_width || rows < 0 || dtype < 0 || dtype > 2) return HSTU_ERR_ARG;
   Segs s{};
   s.n = num_segments;
@@ -654,13 +701,39 @@ extern "C" int hstu_silu_bwd(int num_segments, const void* const* seg_ptr, const
   }
   s.begin[4] = W;
   for (int i = num_segments; i < 5; ++i) s.begin[i] = W;
-  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows == 0) {
+    if (dbias) cudaMemsetAsync(dbias, 0, (size_t)W * 4, st);
+    return 0;
+  }
   if (!x || !dx || !aligned16(x) || !aligned16(dx)) return HSTU_ERR_ARG;
   const int64_t n8 = rows * (W >> 3);
-  const int64_t want = (n8 + 255) / 256, cap = (int64_t)devinfo::sm_count() * 16;
-  GLUE_DISPATCH_T(dtype, (silu_bwd_kernel<T><<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(s, (const T*)x, (T*)dx, rows, W)));
+  if (!dbias) {
+    const int64_t want = (n8 + 255) / 256, cap = (int64_t)devinfo::sm_count() * 16;
+    GLUE_DISPATCH_T(dtype, (silu_bwd_kernel<T, false><<<(int)(want < cap ? want : cap), 256, 0, st>>>(s, (const T*)x, (T*)dx, rows, W, nullptr)));
+    GLUE_CHECK_LAST();
+    return 0;
+  }
+  const int grid = silu_colsum_grid(W, n8);
+  if (grid == 0) return HSTU_ERR_UNSUPPORTED;
+  if (!workspace || !aligned16(workspace) || workspace_bytes < (int64_t)grid * 256 * 8 * 4) return HSTU_ERR_WORKSPACE;
+  float* colpart = reinterpret_cast<float*>(workspace);
+  GLUE_DISPATCH_T(dtype, (silu_bwd_kernel<T, true><<<grid, 256, 0, st>>>(s, (const T*)x, (T*)dx, rows, W, colpart)));
+  GLUE_CHECK_LAST();
+  colsum_rows_kernel<<<(W + 31) / 32, 1024, 0, st>>>(colpart, (int)((int64_t)grid * 256 / (W >> 3)), W, dbias);
   GLUE_CHECK_LAST();
   return 0;
+}
+
+extern "C" int hstu_silu_bwd(int num_segments, const void* const* seg_ptr, const int64_t* seg_stride, const int32_t* seg_width, const void* x, void* dx,
+                             int64_t rows, int dtype, void* stream) {
+  return silu_bwd_impl(num_segments, seg_ptr, seg_stride, seg_width, x, dx, nullptr, nullptr, 0, rows, dtype, stream);
+}
+
+extern "C" int hstu_silu_bwd_bias(int num_segments, const void* const* seg_ptr, const int64_t* seg_stride, const int32_t* seg_width, const void* x,
+                                  void* dx, float* dbias, void* workspace, int64_t workspace_bytes, int64_t rows, int dtype, void* stream) {
+  if (!dbias) return HSTU_ERR_ARG;
+  return silu_bwd_impl(num_segments, seg_ptr, seg_stride, seg_width, x, dx, dbias, workspace, workspace_bytes, rows, dtype, stream);
 }
 
 extern "C" int hstu_dropout_mask(int64_t rows, int D, float dropout_ratio, uint64_t seed, uint8_t* keep, void* stream) {

@@ -15,7 +15,9 @@ Backward, where it differs from the reference's op order:
   * the output-norm backward kernel also RECOMPUTES y (the proj GEMM's weight-gradient operand): y is not saved by the forward;
   * the attention backward writes dq / dk / dv contiguous and the SiLU backward kernel gathers du / dv / dq / dk from where they are
     (the reference lets its attention kernel write into slices of one uvqk gradient buffer; ours needs contiguous outputs);
-  * the input-norm backward adds the residual gradient into dx in the same pass (the reference: dx_accumulate, same thing).
+  * the input-norm backward adds the residual gradient into dx in the same pass (the reference: dx_accumulate, same thing);
+  * the uvqk bias gradient (column sums of the SiLU backward's output) is accumulated by the SiLU backward kernel itself (the reference sums
+    dz in a separate pass, triton_addmm.py:293-294).
 `wgrad_stream` / `wgrad_event` (weight-gradient GEMMs on a side stream) are honoured the way the reference does it: the two weight-gradient
 GEMMs run on `wgrad_stream` when given, and `wgrad_event` is recorded after them.
 Limits: Blackwell attention kernel only (attn_backend is accepted and ignored), linear_dim_per_head == attention_dim_per_head in (64, 128),
@@ -117,8 +119,11 @@ class FusedHSTULayerFunction(torch.autograd.Function):
                                                   seqlen_offsets, c["max_seqlen"], c["max_seqlen"], None, None, None, None, num_targets,
                                                   c["target_group_size"], -1, 0, c["alpha"], scaling_seqlen=c["scaling_seqlen"])
         # 3. silu backward over (du | dv | dq | dk), read in place -> gradient of the uvqk GEMM output
-        dpre = silu_bwd_segments([du, dv.view(T, H * Dh), dq.view(T, H * Dh), dk.view(T, H * Dh)], pre)
-        d_bias = dpre.sum(dim=0) if c["has_bias_grad"] else None
+        if c["has_bias_grad"]:                                            # the bias gradient is the column sum of dpre: same kernel
+            dpre, d_bias = silu_bwd_segments([du, dv.view(T, H * Dh), dq.view(T, H * Dh), dk.view(T, H * Dh)], pre, with_bias_grad=True)
+            d_bias = d_bias.to(pre.dtype)
+        else:
+            dpre, d_bias = silu_bwd_segments([du, dv.view(T, H * Dh), dq.view(T, H * Dh), dk.view(T, H * Dh)], pre), None
         d_normed = torch.mm(dpre, w_uvqk.t())
         if normed is None:                                                # recompute_input_layernorm
             normed = weighted_layer_norm_fwd(input, in_w, in_b, c["eps"])[0]

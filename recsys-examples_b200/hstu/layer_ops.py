@@ -23,6 +23,8 @@ _SIGS = {
     "hstu_ln_mul_dropout_bwd": (I32, [P, I64, P, I64, P, I64, P, P, P, P, P, I64, P, I64, P, I64, P, P, P, I64, I64, I32, F32, U64, I32, I32, P]),
     "hstu_silu_fwd": (I32, [P, P, I64, I32, P]),
     "hstu_silu_bwd": (I32, [I32, P, P, P, P, P, I64, I32, P]),
+    "hstu_silu_bwd_bias_workspace_bytes": (I64, [I32]),
+    "hstu_silu_bwd_bias": (I32, [I32, P, P, P, P, P, P, P, I64, I64, I32, P]),
     "hstu_dropout_mask": (I32, [I64, I32, F32, U64, P, P]),
 }
 for _name, (_res, _args) in _SIGS.items():
@@ -181,9 +183,11 @@ def silu_fwd(input: torch.Tensor) -> torch.Tensor:  # noqa: A002
     return y.view(input.shape)
 
 
-def silu_bwd_segments(grad_segments: Sequence[torch.Tensor], input: torch.Tensor) -> torch.Tensor:  # noqa: A002
+def silu_bwd_segments(grad_segments: Sequence[torch.Tensor], input: torch.Tensor, with_bias_grad: bool = False):  # noqa: A002
     """d(silu) for `input` [rows, W] whose output gradient arrives as 1..4 column segments [rows, w_i] (sum w_i = W), each a row view with
-    its own base and stride — du / dv / dq / dk are read where the layer-norm and attention backward kernels left them (no torch.cat)."""
+    its own base and stride — du / dv / dq / dk are read where the layer-norm and attention backward kernels left them (no torch.cat).
+    with_bias_grad: also return dx.sum(0) (fp32 [W]) — the bias gradient of the GEMM in front of the SiLU — accumulated by the same kernel
+    instead of a second pass over dx; returns (dx, dbias)."""
     x = input.contiguous()
     rows, W = x.shape
     segs = [_rows(g.reshape(rows, -1).to(x.dtype)) for g in grad_segments]
@@ -192,8 +196,18 @@ def silu_bwd_segments(grad_segments: Sequence[torch.Tensor], input: torch.Tensor
     ptrs = (ctypes.c_void_p * len(segs))(*[s.data_ptr() for s in segs])
     strides = (ctypes.c_int64 * len(segs))(*[s.stride(0) for s in segs])
     widths = (ctypes.c_int32 * len(segs))(*[s.shape[1] for s in segs])
+    if with_bias_grad:
+        ws_bytes = int(N.lib.hstu_silu_bwd_bias_workspace_bytes(W))
+        if ws_bytes > 0:
+            dbias = torch.empty(W, dtype=torch.float32, device=x.device)
+            ws = N.workspace(ws_bytes, x.device)
+            _check(N.launch("hstu_silu_bwd_bias", 2, N.lib.hstu_silu_bwd_bias, len(segs), ctypes.cast(ptrs, P), ctypes.cast(strides, P),
+                            ctypes.cast(widths, P), N.ptr(x), N.ptr(dx), N.ptr(dbias), N.ptr(ws), ws.numel(), rows, _DTYPE[x.dtype], N.stream()), "silu_bwd_bias")
+            return dx, dbias
     _check(N.launch("hstu_silu_bwd", 1, N.lib.hstu_silu_bwd, len(segs), ctypes.cast(ptrs, P), ctypes.cast(strides, P), ctypes.cast(widths, P), N.ptr(x),
                     N.ptr(dx), rows, _DTYPE[x.dtype], N.stream()), "silu_bwd")
+    if with_bias_grad:                                      # width that cannot be tiled onto the launch: separate sum
+        return dx, dx.sum(dim=0, dtype=torch.float32)
     return dx
 
 

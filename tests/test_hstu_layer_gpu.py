@@ -145,6 +145,26 @@ def test_silu_fwd_bwd_matches_torch(cuda, dt):
     torch.testing.assert_close(L.triton_silu_bwd(g.to(dtype), x).float(), xr.grad, **TOL[dt])
 
 
+@pytest.mark.parametrize("dt", ["fp32", "bf16"])
+@pytest.mark.parametrize("rows,W", [(777, 4096), (1000, 192), (33, 1000), (5, 8 * 2377)])
+def test_silu_bwd_with_bias_grad(cuda, dt, rows, W):
+    """The column sums of the SiLU backward's output (the bias gradient of the GEMM in front) accumulated by the same kernel; widths whose
+    W / 8 cannot be tiled onto the launch (the last case) fall back to a separate sum."""
+    from hstu import layer_ops as L
+    dtype = DT[dt]
+    x = _mk(cuda, (rows, W), dtype, 31, 2.0)
+    cuts = [0, W // 8 * 2, W // 8 * 5, W] if W % 64 == 0 else [0, W]
+    g = _mk(cuda, (rows, W), dtype, 32)
+    segs = [g[:, a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    dx, dbias = L.silu_bwd_segments(segs, x, with_bias_grad=True)
+    xr = x.float().requires_grad_(True)
+    F.silu(xr).backward(g.float())
+    torch.testing.assert_close(dx.float(), xr.grad, **TOL[dt])
+    assert dbias.dtype == torch.float32 and dbias.shape == (W,)
+    assert torch.equal(dx, L.silu_bwd_segments(segs, x))                       # same dx with and without the column sums
+    assert bool(((dbias - xr.grad.sum(0)).abs() <= TOL[dt]["rtol"] * xr.grad.abs().sum(0) + 1e-4).all())
+
+
 def _layer_ref(x, cu, S, p, H, Dh, eps, alpha, num_targets=None):
     """The layer in fp32 torch ops with the oracle attention (oracle/hstu_attn.py)."""
     from oracle.hstu_attn import hstu_attention

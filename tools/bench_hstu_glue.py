@@ -78,6 +78,9 @@ def run(dev=None):
         torch.autograd.grad(F.silu(pg), pg, g)
     rec("silu_bwd (4 gradient segments read in place)", timeit(lambda: L.silu_bwd_segments([du, dv, dq, dk], pre)), 3 * T * W * 2,
         timeit(torch_silu_bwd) - timeit(lambda: F.silu(pg)))
+    rec("silu_bwd + uvqk bias gradient (column sums in the same kernel)", timeit(lambda: L.silu_bwd_segments([du, dv, dq, dk], pre, with_bias_grad=True)),
+        3 * T * W * 2, timeit(lambda: L.silu_bwd_segments([du, dv, dq, dk], pre).sum(dim=0)))
+    out["kernels"]["silu_bwd + uvqk bias gradient (column sums in the same kernel)"]["torch_eager_ms_is"] = "our silu_bwd followed by a separate dx.sum(0)"
     y2, m2, r2, _, _, seed = L.layer_norm_mul_dropout_fwd(x, u, w, b, 1e-5, 0.0, True)
     rec("ln_mul_dropout_fwd", timeit(lambda: L.layer_norm_mul_dropout_fwd(x, u, w, b, 1e-5, 0.0, True)), 3 * rowb,
         timeit(lambda: F.layer_norm(x, (D,), w, b, 1e-5) * u))
