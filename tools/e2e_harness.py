@@ -396,8 +396,8 @@ def run_both(dev, world, rank, **kw):
     refs = [out[a]["ms_per_step"] for a in ("reference", "reference_fused") if "ms_per_step" in out.get(a, {})]
     if refs and "ms_per_step" in out.get("ours_fused", {}):
         # the robust headline: our fused layer against the FASTER of the reference's two configurations.  `reference_fused` depends on which
-        # configuration Triton's autotuner picks for the reference's layer-norm backward kernels during warm-up: 92-93 ms in most runs, 163 ms
-        # in one (profiles/r02_e2e_cfg4_n1_fused_layer*.json)
+        # configuration Triton's autotuner picks for the reference's layer-norm backward kernels during warm-up: 92-93 ms in four runs,
+        # 163-174 ms in two (profiles/r02_e2e_cfg4_n1_fused_layer*.json, r02_bench_line.json)
         out["ratio_samples_per_s_ours_fused_over_best_reference"] = min(refs) / out["ours_fused"]["ms_per_step"]
     if "ms_per_step" in out.get("ours_fused", {}) and "ms_per_step" in out.get("ours", {}):
         out["fused_layer_gain_over_eager_glue_ours"] = out["ours"]["ms_per_step"] / out["ours_fused"]["ms_per_step"]
