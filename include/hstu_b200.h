@@ -49,8 +49,8 @@ int hstu_bwd_sm100(const void* dout, const void* q, const void* k, const void* v
  *   hstu_layer_norm_fwd / _bwd        <- triton_weighted_layer_norm_fwd / _bwd      (ops/triton_ops/triton_layer_norm.py:313, :386)
  *   hstu_ln_mul_dropout_fwd / _bwd    <- triton_layer_norm_mul_dropout_fwd / _bwd   (ops/triton_ops/triton_norm_mul_dropout.py:361, :426; concat_ux=False)
  *   hstu_silu_fwd / _bwd              <- triton_silu_fwd / _bwd                     (ops/triton_ops/triton_silu.py:91, :108)
- * Conventions: raw DEVICE pointers, 16-byte aligned; rows = tokens; D = normalised width, multiple of 8, <= 1024 (HSTU_ERR_UNSUPPORTED
- * above: the row is register resident); strides in ELEMENTS, multiples of 8 (strided views of the fused uvqk buffer are read in place);
+ * Conventions: raw DEVICE pointers, 16-byte aligned; rows = tokens; D = normalised width, multiple of 8, <= 8192 (HSTU_ERR_UNSUPPORTED
+ * above; <= 1024 a warp owns a row, above that a CTA does — the row is register resident either way); strides in ELEMENTS, multiples of 8 (strided views of the fused uvqk buffer are read in place);
  * dtype 0 = fp32, 1 = fp16, 2 = bf16 for every tensor argument of a call (weight / bias included), statistics (mean, rstd) and the
  * weight / bias gradients are fp32; math is fp32; nothing allocates or synchronises.  weight / bias may be NULL (plain normalisation).
  * Backward calls need hstu_glue_workspace_bytes(D) bytes of device scratch (per-CTA dw / db partials, summed in a fixed order).

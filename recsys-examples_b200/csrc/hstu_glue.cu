@@ -28,7 +28,7 @@ namespace glue {
 
 constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * 32;
-constexpr int kMaxD = 1024;            // register-resident row: NV <= 4 vectors of 8 elements per lane
+constexpr int kMaxD = 1024;            // warp-per-row kernels: NV <= 4 vectors of 8 elements per lane; wider rows take the CTA-per-row kernels
 
 #define GLUE_CHECK_LAST() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return -(int)e__; } while (0)
 
@@ -383,6 +383,191 @@ __global__ void __launch_bounds__(kThreads) ln_bwd_kernel(const T* __restrict__ 
   }
 }
 
+// ---- wide rows (1024 < D <= 8192): one CTA of 256 threads per row ------------------------------------------------------------------------
+// Same math and the same column ownership idea as the warp-per-row kernels — thread t owns columns [(k * 256 + t) * 8, +8), k < NVW <= 4, so the
+// weight / bias gradient accumulators stay in registers over all rows of the CTA and go straight to its partial row (no cross-warp hand-over) —
+// with the row statistics combined through shared memory (two block reductions per row forward, one pair backward).
+constexpr int kWideThreads = 256;
+constexpr int kMaxWideD = 8192;
+
+// sum over the CTA; `sm` holds 2 x 8 floats and is used alternately (parity) so one __syncthreads per reduction is enough
+__device__ __forceinline__ float block_sum(float v, float* sm, int parity) {
+  v = warp_sum(v);
+  float* s = sm + parity * 8;
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kWideThreads / 32; ++i) t += s[i];
+  return t;
+}
+
+template <typename T, int NVW>
+__device__ __forceinline__ void load_row_wide(const T* __restrict__ base, int D, Raw8<T>* r) {
+#pragma unroll
+  for (int k = 0; k < NVW; ++k) {
+    const int c = (k * kWideThreads + (int)threadIdx.x) * 8;
+    if (c < D) r[k] = load_raw(base + c);
+  }
+}
+
+template <typename T, int NVW, bool MUL>
+__global__ void __launch_bounds__(kWideThreads) ln_fwd_wide_kernel(const T* __restrict__ x, int64_t sx, const T* __restrict__ w, const T* __restrict__ b,
+                                                                   const T* __restrict__ u, int64_t su, T* __restrict__ y, int64_t sy,
+                                                                   float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int D, float eps,
+                                                                   Drop drop) {
+  __shared__ float sm[16];
+  const float invD = 1.0f / (float)D;
+  int parity = 0;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    Raw8<T> rx[NVW], ru[NVW];
+    load_row_wide<T, NVW>(x + row * sx, D, rx);
+    if (MUL) load_row_wide<T, NVW>(u + row * su, D, ru);
+    float v[NVW][8];
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NVW; ++k) {
+      const int c = (k * kWideThreads + (int)threadIdx.x) * 8;
+      if (c < D) {
+        unpack(rx[k], v[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[k][j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[k][j] = 0.0f;
+      }
+    }
+    const float m = block_sum(s, sm, parity) * invD;
+    parity ^= 1;
+    float q = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NVW; ++k) {
+      const int c = (k * kWideThreads + (int)threadIdx.x) * 8;
+      if (c < D) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[k][j] -= m; q += v[k][j] * v[k][j]; }
+      }
+    }
+    const float r = 1.0f / sqrtf(block_sum(q, sm, parity) * invD + eps);
+    parity ^= 1;
+    if (threadIdx.x == 0) { mean[row] = m; rstd[row] = r; }
+#pragma unroll
+    for (int k = 0; k < NVW; ++k) {
+      const int c = (k * kWideThreads + (int)threadIdx.x) * 8;
+      if (c < D) {
+        float o[8], wv[8], bv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { wv[j] = 1.0f; bv[j] = 0.0f; }
+        if (w) V8<T>::load(w + c, wv);
+        if (b) V8<T>::load(b + c, bv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = v[k][j] * r * wv[j] + bv[j];
+        if (MUL) {
+          float uv[8], ms[8];
+          unpack(ru[k], uv);
+          drop_scales(drop, row, c >> 3, ms);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = o[j] * uv[j] * ms[j];
+        }
+        store8(y + row * sy + c, o);
+      }
+    }
+  }
+}
+
+template <typename T, int NVW, bool MUL>
+__global__ void __launch_bounds__(kWideThreads) ln_bwd_wide_kernel(const T* __restrict__ dy, int64_t sdy, const T* __restrict__ x, int64_t sx,
+                                                                   const T* __restrict__ w, const T* __restrict__ b, const float* __restrict__ mean,
+                                                                   const float* __restrict__ rstd, const T* __restrict__ u, int64_t su,
+                                                                   const T* __restrict__ dx_add, int64_t sadd, T* __restrict__ dx, int64_t sdx,
+                                                                   T* __restrict__ du, int64_t sdu, T* __restrict__ y_out, int64_t sy,
+                                                                   float* __restrict__ part, int64_t rows, int D, Drop drop) {
+  __shared__ float sm[32];                  // two reductions per row (c1, c2), each with its own pair of parity buffers
+  const float invD = 1.0f / (float)D;
+  float dwa[NVW][8], dba[NVW][8];
+#pragma unroll
+  for (int k = 0; k < NVW; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dwa[k][j] = 0.0f; dba[k][j] = 0.0f; }
+  int parity = 0;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    Raw8<T> rx[NVW], rdy[NVW], ru[NVW], radd[NVW];
+    load_row_wide<T, NVW>(x + row * sx, D, rx);
+    load_row_wide<T, NVW>(dy + row * sdy, D, rdy);
+    if (MUL) load_row_wide<T, NVW>(u + row * su, D, ru);
+    if (dx_add) load_row_wide<T, NVW>(dx_add + row * sadd, D, radd);
+    const float m = mean[row], r = rstd[row];
+    float gw[NVW][8];
+    float c1 = 0.0f, c2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NVW; ++k) {
+      const int c = (k * kWideThreads + (int)threadIdx.x) * 8;
+      if (c < D) {
+        float xh[8], g[8], wv[8];
+        unpack(rx[k], xh);
+        unpack(rdy[k], g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { xh[j] = (xh[j] - m) * r; wv[j] = 1.0f; }
+        if (w) V8<T>::load(w + c, wv);
+        if (MUL) {
+          float uv[8], ms[8], bv[8], o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bv[j] = 0.0f;
+          if (b) V8<T>::load(b + c, bv);
+          unpack(ru[k], uv);
+          drop_scales(drop, row, c >> 3, ms);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float ln = xh[j] * wv[j] + bv[j];
+            const float gj = g[j] * ms[j];
+            o[j] = gj * ln;
+            g[j] = gj * uv[j];
+            bv[j] = ln * uv[j] * ms[j];
+          }
+          store8(du + row * sdu + c, o);
+          if (y_out) store8(y_out + row * sy + c, bv);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dwa[k][j] += g[j] * xh[j];
+          dba[k][j] += g[j];
+          gw[k][j] = g[j] * wv[j];
+          c1 += gw[k][j] * xh[j];
+          c2 += gw[k][j];
+        }
+      }
+    }
+    c1 = block_sum(c1, sm, parity) * invD;
+    c2 = block_sum(c2, sm + 16, parity) * invD;
+    parity ^= 1;
+#pragma unroll
+    for (int k = 0; k < NVW; ++k) {
+      const int c = (k * kWideThreads + (int)threadIdx.x) * 8;
+      if (c < D) {
+        float xh[8], o[8];
+        unpack(rx[k], xh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (gw[k][j] - ((xh[j] - m) * r * c1 + c2)) * r;
+        if (dx_add) {
+          float a[8];
+          unpack(radd[k], a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += a[j];
+        }
+        store8(dx + row * sdx + c, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NVW; ++k) {
+    const int c = (k * kWideThreads + (int)threadIdx.x) * 8;
+    if (c < D) {
+      store8(part + ((int64_t)blockIdx.x * 2 + 0) * D + c, dwa[k]);
+      store8(part + ((int64_t)blockIdx.x * 2 + 1) * D + c, dba[k]);
+    }
+  }
+}
+
 // dw[c] = sum_blocks part[blk][0][c], db[c] = sum_blocks part[blk][1][c].  One CTA = 32 columns x 32 chunk lanes: lane (cx, cy) adds the partials of
 // blocks cy, cy + 32, ... for its column (128-byte coalesced across cx), the 32 chunk sums are combined through shared memory in a fixed order
 // => bit-reproducible for a given grid.  (First version: one thread per column walking all ~600 partials, 8 CTAs — 49 us, a fifth of the LN
@@ -555,9 +740,20 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
     else { using T = __nv_bfloat16; __VA_ARGS__; }                         \
   } while (0)
 
+#define GLUE_DISPATCH_NVW(D, ...)                          \
+  do {                                                     \
+    if ((D) <= 2048) { constexpr int NVW = 1; __VA_ARGS__; } \
+    else if ((D) <= 4096) { constexpr int NVW = 2; __VA_ARGS__; } \
+    else { constexpr int NVW = 4; __VA_ARGS__; }           \
+  } while (0)
+inline int wide_grid(int64_t rows, int per_sm) {
+  const int64_t cap = (int64_t)devinfo::sm_count() * per_sm;
+  return (int)(rows < cap ? (rows < 1 ? 1 : rows) : cap);
+}
+
 static int check_rows(int64_t rows, int D, int dtype) {
   if (rows < 0 || D <= 0 || (D & 7) || dtype < 0 || dtype > 2) return HSTU_ERR_ARG;
-  if (D > kMaxD) return HSTU_ERR_UNSUPPORTED;
+  if (D > kMaxWideD) return HSTU_ERR_UNSUPPORTED;
   return 0;
 }
 
@@ -573,6 +769,12 @@ extern "C" int hstu_layer_norm_fwd(const void* x, int64_t x_stride, const void* 
   if (rows == 0) return 0;
   if (!x || !y || !mean || !rstd || (x_stride & 7) || (y_stride & 7) || !aligned16(x) || !aligned16(y)) return HSTU_ERR_ARG;
   const Drop nodrop{0, 0u, 1.0f};
+  if (D > kMaxD) {
+    GLUE_DISPATCH_T(dtype, GLUE_DISPATCH_NVW(D, (ln_fwd_wide_kernel<T, NVW, false><<<wide_grid(rows, 8), kWideThreads, 0, (cudaStream_t)stream>>>(
+        (const T*)x, x_stride, (const T*)weight, (const T*)bias, nullptr, 0, (T*)y, y_stride, mean, rstd, rows, D, eps, nodrop))));
+    GLUE_CHECK_LAST();
+    return 0;
+  }
   GLUE_DISPATCH_T(dtype, GLUE_DISPATCH_NV(D, (ln_fwd_kernel<T, NV, false><<<row_grid(rows, 8), kThreads, 0, (cudaStream_t)stream>>>(
       (const T*)x, x_stride, (const T*)weight, (const T*)bias, nullptr, 0, (T*)y, y_stride, mean, rstd, rows, D, eps, nodrop))));
   GLUE_CHECK_LAST();
@@ -589,6 +791,12 @@ extern "C" int hstu_ln_mul_dropout_fwd(const void* x, int64_t x_stride, const vo
     return HSTU_ERR_ARG;
   if (rows == 0) return 0;
   const Drop drop = make_drop(dropout_ratio, seed, training);
+  if (D > kMaxD) {
+    GLUE_DISPATCH_T(dtype, GLUE_DISPATCH_NVW(D, (ln_fwd_wide_kernel<T, NVW, true><<<wide_grid(rows, 8), kWideThreads, 0, (cudaStream_t)stream>>>(
+        (const T*)x, x_stride, (const T*)weight, (const T*)bias, (const T*)u, u_stride, (T*)y, y_stride, mean, rstd, rows, D, eps, drop))));
+    GLUE_CHECK_LAST();
+    return 0;
+  }
   GLUE_DISPATCH_T(dtype, GLUE_DISPATCH_NV(D, (ln_fwd_kernel<T, NV, true><<<row_grid(rows, 8), kThreads, 0, (cudaStream_t)stream>>>(
       (const T*)x, x_stride, (const T*)weight, (const T*)bias, (const T*)u, u_stride, (T*)y, y_stride, mean, rstd, rows, D, eps, drop))));
   GLUE_CHECK_LAST();
@@ -599,11 +807,22 @@ static int ln_bwd_launch(bool mul, const void* dy, int64_t sdy, const void* x, i
                          const float* rstd, const void* u, int64_t su, const void* dx_add, int64_t sadd, void* dx, int64_t sdx, void* du, int64_t sdu,
                          void* y_out, int64_t sy, float* dw, float* db, void* workspace, int64_t ws_bytes, int64_t rows, int D, Drop drop, int dtype,
                          cudaStream_t st) {
-  const int grid = row_grid(rows, 4);
+  const bool wide = D > kMaxD;
+  const int grid = wide ? wide_grid(rows, 4) : row_grid(rows, 4);
   if (!workspace || ws_bytes < (int64_t)grid * 2 * D * 4) return HSTU_ERR_WORKSPACE;
   float* part = reinterpret_cast<float*>(workspace);
   const size_t smem = (size_t)(kWarps - 1) * D * sizeof(float);
-  if (mul) {
+  if (wide) {
+    if (mul) {
+      GLUE_DISPATCH_T(dtype, GLUE_DISPATCH_NVW(D, (ln_bwd_wide_kernel<T, NVW, true><<<grid, kWideThreads, 0, st>>>(
+          (const T*)dy, sdy, (const T*)x, sx, (const T*)w, (const T*)b, mean, rstd, (const T*)u, su, (const T*)dx_add, sadd, (T*)dx, sdx, (T*)du, sdu,
+          (T*)y_out, sy, part, rows, D, drop))));
+    } else {
+      GLUE_DISPATCH_T(dtype, GLUE_DISPATCH_NVW(D, (ln_bwd_wide_kernel<T, NVW, false><<<grid, kWideThreads, 0, st>>>(
+          (const T*)dy, sdy, (const T*)x, sx, (const T*)w, (const T*)b, mean, rstd, nullptr, 0, (const T*)dx_add, sadd, (T*)dx, sdx, nullptr, 0,
+          nullptr, 0, part, rows, D, drop))));
+    }
+  } else if (mul) {
     GLUE_DISPATCH_T(dtype, GLUE_DISPATCH_NV(D, (ln_bwd_kernel<T, NV, true, (sizeof(T) == 2 && NV <= 2)><<<grid, kThreads, smem, st>>>(
         (const T*)dy, sdy, (const T*)x, sx, (const T*)w, (const T*)b, mean, rstd, (const T*)u, su, (const T*)dx_add, sadd, (T*)dx, sdx, (T*)du, sdu,
         (T*)y_out, sy, part, rows, D, drop))));

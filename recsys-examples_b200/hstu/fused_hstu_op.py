@@ -21,7 +21,7 @@ Backward, where it differs from the reference's op order:
 `wgrad_stream` / `wgrad_event` (weight-gradient GEMMs on a side stream) are honoured the way the reference does it: the two weight-gradient
 GEMMs run on `wgrad_stream` when given, and `wgrad_event` is recorded after them.
 Limits: Blackwell attention kernel only (attn_backend is accepted and ignored), linear_dim_per_head == attention_dim_per_head in (64, 128),
-hidden size and heads * linear_dim <= 1024 (register-resident rows), no contextual tokens (as the reference on sm_100, :60-71).
+hidden size and heads * linear_dim <= 8192 (<= 1024: warp-per-row glue kernels, above: CTA-per-row), no contextual tokens (as the reference on sm_100, :60-71).
 """
 from typing import Optional, Union
 

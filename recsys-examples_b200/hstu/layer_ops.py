@@ -33,8 +33,8 @@ for _name, (_res, _args) in _SIGS.items():
 
 _DTYPE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 _ERR = {-1100: "invalid argument (pointers 16-byte aligned, strides / widths multiples of 8 elements)",
-        -1101: "unsupported: the normalised width must be <= 1024", -1102: "workspace too small"}
-MAX_NORM_DIM = 1024
+        -1101: "unsupported: the normalised width must be <= 8192", -1102: "workspace too small"}
+MAX_NORM_DIM = 8192          # <= 1024: warp-per-row kernels (the HSTU-large case); up to 8192: CTA-per-row kernels
 
 
 def _check(rc: int, what: str) -> None:
