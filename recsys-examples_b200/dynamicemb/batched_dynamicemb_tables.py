@@ -521,12 +521,12 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
             sc = tb.gather_score_blocks(table_id, idx) if tb.num_scores_ > 1 else scores.view(torch.int64)
             yield keys, dense, sc
 
-    def export_keys_values(self, table=0, device: Optional[torch.device] = None, batch_size: int = 65536):
-        """All (keys, rows) of one table, named as in the reference (:1420, `table_name`) or by index.  With `device` given the reference's
+    def export_keys_values(self, table_name=0, device: Optional[torch.device] = None, batch_size: int = 65536):
+        """All (keys, rows) of one table, named as in the reference (:1411, `table_name`) or by index.  With `device` given the reference's
         result is returned — (keys, embeddings [n, dim]) on that device; without it (keys, full value rows [n, dim + state]) on the GPU,
         which is what the tests inspect."""
         self.flush()
-        t = self._table_id(table)
+        t = self._table_id(table_name)
         ks, vs = [], []
         for keys, dense, _ in self._export_batches(t, batch_size):
             ks.append(keys)

@@ -1,0 +1,66 @@
+"""Golden API signatures: parameter names, order and literal defaults of the reference's boundary functions on the two hot paths, read from
+the reference's source with `ast` (nothing is imported or executed).  Not run by the test suite; rerun by hand:
+    python tests/golden/gen_golden_sigs.py        -> tests/golden/api_signatures.json
+`tests/test_api_signatures_cpu.py` compares this package's functions of the same names against it."""
+import ast
+import json
+import os
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "api_signatures.json")
+
+TARGETS = {
+    "examples/hstu/ops/fused_hstu_op.py": ["fused_hstu_op", "FusedHSTULayerFunction.forward"],
+    "examples/hstu/ops/triton_ops/triton_layer_norm.py": ["triton_weighted_layer_norm_fwd", "triton_weighted_layer_norm_bwd"],
+    "examples/hstu/ops/triton_ops/triton_norm_mul_dropout.py": ["triton_layer_norm_mul_dropout_fwd", "triton_layer_norm_mul_dropout_bwd"],
+    "examples/hstu/ops/triton_ops/triton_silu.py": ["triton_silu_fwd", "triton_silu_bwd"],
+    "third_party/FBGEMM/fbgemm_gpu/experimental/hstu/hstu/cuda_hstu_attention.py": ["hstu_attn_varlen_func"],
+    "corelib/dynamicemb/dynamicemb/batched_dynamicemb_tables.py": [
+        "BatchedDynamicEmbeddingTablesV2.__init__", "BatchedDynamicEmbeddingTablesV2.forward", "BatchedDynamicEmbeddingTablesV2.prefetch",
+        "BatchedDynamicEmbeddingTablesV2.dump", "BatchedDynamicEmbeddingTablesV2.load", "BatchedDynamicEmbeddingTablesV2.export_keys_values",
+        "BatchedDynamicEmbeddingTablesV2.set_score", "BatchedDynamicEmbeddingTablesV2.set_learning_rate",
+        "encode_meta_json_file_path", "encode_checkpoint_file_path", "encode_counter_checkpoint_file_path", "find_files", "get_loading_files"],
+}
+
+
+def literal(node):
+    try:
+        return {"value": ast.literal_eval(node)}
+    except Exception:  # noqa: BLE001  (enum members, calls: keep the source text)
+        return {"source": ast.unparse(node)}
+
+
+def signature(fn: ast.FunctionDef):
+    a = fn.args
+    pos = [x.arg for x in a.posonlyargs + a.args]
+    defaults = [None] * (len(pos) - len(a.defaults)) + [literal(d) for d in a.defaults]
+    out = [{"name": n, "default": d} for n, d in zip(pos, defaults)]
+    if a.vararg:
+        out.append({"name": "*" + a.vararg.arg, "default": None})
+    for x, d in zip(a.kwonlyargs, a.kw_defaults):
+        out.append({"name": x.arg, "default": literal(d) if d is not None else None, "kwonly": True})
+    if a.kwarg:
+        out.append({"name": "**" + a.kwarg.arg, "default": None})
+    return [p for p in out if p["name"] not in ("self", "ctx")]
+
+
+def main():
+    rec = {}
+    for rel, names in TARGETS.items():
+        tree = ast.parse(open(os.path.join(REF, rel)).read())
+        index = {}
+        for node in tree.body:
+            if isinstance(node, ast.FunctionDef):
+                index[node.name] = node
+            elif isinstance(node, ast.ClassDef):
+                for sub in node.body:
+                    if isinstance(sub, ast.FunctionDef):
+                        index[f"{node.name}.{sub.name}"] = sub
+        for n in names:
+            rec[n] = {"file": rel, "line": index[n].lineno, "params": signature(index[n])}
+    json.dump(rec, open(OUT, "w"), indent=1)
+    print(OUT, len(rec), "signatures")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,71 @@
+"""The drop-in boundary, checked on CPU: every function this package offers under a reference name takes the reference's parameters — same
+names, same order, same literal defaults — as recorded in tests/golden/api_signatures.json (read from the reference's source by
+tests/golden/gen_golden_sigs.py).  A caller written against the reference, positional or by keyword, binds identically here."""
+import inspect
+import json
+import os
+
+import pytest
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "api_signatures.json")
+
+
+def _ours():
+    from dynamicemb import BatchedDynamicEmbeddingTablesV2 as M
+    from dynamicemb import checkpoint as ck
+    from hstu import fused_hstu_op as fo
+    from hstu import hstu_attn_varlen_func, layer_ops as L
+    return {
+        "fused_hstu_op": fo.fused_hstu_op, "FusedHSTULayerFunction.forward": fo.FusedHSTULayerFunction.forward,
+        "triton_weighted_layer_norm_fwd": L.triton_weighted_layer_norm_fwd, "triton_weighted_layer_norm_bwd": L.triton_weighted_layer_norm_bwd,
+        "triton_layer_norm_mul_dropout_fwd": L.triton_layer_norm_mul_dropout_fwd, "triton_layer_norm_mul_dropout_bwd": L.triton_layer_norm_mul_dropout_bwd,
+        "triton_silu_fwd": L.triton_silu_fwd, "triton_silu_bwd": L.triton_silu_bwd, "hstu_attn_varlen_func": hstu_attn_varlen_func,
+        "BatchedDynamicEmbeddingTablesV2.__init__": M.__init__, "BatchedDynamicEmbeddingTablesV2.forward": M.forward,
+        "BatchedDynamicEmbeddingTablesV2.prefetch": M.prefetch, "BatchedDynamicEmbeddingTablesV2.dump": M.dump, "BatchedDynamicEmbeddingTablesV2.load": M.load,
+        "BatchedDynamicEmbeddingTablesV2.export_keys_values": M.export_keys_values, "BatchedDynamicEmbeddingTablesV2.set_score": M.set_score,
+        "BatchedDynamicEmbeddingTablesV2.set_learning_rate": M.set_learning_rate,
+        "encode_meta_json_file_path": ck.encode_meta_json_file_path, "encode_checkpoint_file_path": ck.encode_checkpoint_file_path,
+        "encode_counter_checkpoint_file_path": ck.encode_counter_checkpoint_file_path, "find_files": ck.find_files, "get_loading_files": ck.get_loading_files,
+    }
+
+
+def _params(fn):
+    out = []
+    for name, p in inspect.signature(fn).parameters.items():
+        if name in ("self", "ctx"):
+            continue
+        prefix = "*" if p.kind == p.VAR_POSITIONAL else "**" if p.kind == p.VAR_KEYWORD else ""
+        out.append((prefix + name, p.default))
+    return out
+
+
+def test_every_golden_signature_is_covered():
+    gold = json.load(open(G))
+    assert set(gold) == set(_ours())
+
+
+@pytest.mark.parametrize("name", sorted(json.load(open(G))))
+def test_parameters_match_reference(name):
+    gold = json.load(open(G))[name]
+    ours = _params(_ours()[name])
+    want_names = [p["name"] for p in gold["params"]]
+    assert [n for n, _ in ours] == want_names, f"{name} ({gold['file']}:{gold['line']})"
+    for (n, default), p in zip(ours, gold["params"]):
+        d = p["default"]
+        if d is None:
+            continue                                    # required in the reference: a default here only widens what is accepted
+        assert default is not inspect.Parameter.empty, f"{name}: `{n}` has a default in the reference"
+        if "value" in d and n not in ("table_name",):      # literal default: must be equal.  Enum-member defaults (kept as source text) are checked below
+            mine = list(default) if isinstance(default, tuple) else default          # the golden file is JSON: tuples are lists there
+            assert mine == d["value"] and type(mine) is type(d["value"]), f"{name}: default of `{n}` is {default!r}, reference {d['value']!r}"
+
+
+def test_enum_defaults_match_reference_members():
+    """Defaults the reference writes as enum members (recorded as source text in the golden file)."""
+    from dynamicemb import BatchedDynamicEmbeddingTablesV2 as M, BoundsCheckMode, DynamicEmbPoolingMode, EmbOptimType
+    gold = {p["name"]: p["default"] for p in json.load(open(G))["BatchedDynamicEmbeddingTablesV2.__init__"]["params"] if p["default"]}
+    sig = inspect.signature(M.__init__).parameters
+    assert gold["pooling_mode"]["source"] == "DynamicEmbPoolingMode.SUM" and sig["pooling_mode"].default is DynamicEmbPoolingMode.SUM
+    assert gold["bounds_check_mode"]["source"] == "BoundsCheckMode.WARNING" and sig["bounds_check_mode"].default is BoundsCheckMode.WARNING
+    assert gold["optimizer"]["source"] == "EmbOptimType.SGD" and sig["optimizer"].default is EmbOptimType.SGD
+    assert gold["output_dtype"]["source"] == "torch.float32"
