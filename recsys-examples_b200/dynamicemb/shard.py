@@ -453,15 +453,51 @@ class DynamicEmbeddingBagCollectionSharder(_SharderBase):
 
 
 class DynamicEmbeddingShardingPlanner:
-    """planner/planner.py:213 — plans the DynamicEmb tables row-wise itself (`plan_row_wise`); tables without use_dynamicemb are left to
-    TorchRec's EmbeddingShardingPlanner when torchrec is importable."""
+    """planner/planner.py:213 — same constructor arguments as the reference (`eb_configs, topology, batch_size, enumerator,
+    storage_reservation, proposer, partitioner, performance_model, stats, constraints, debug`); plans the DynamicEmb tables row-wise itself
+    (`plan_row_wise`: what the reference's constructor does in `_prepare_dynemb_table_options` + its `_dyn_emb_plan` loop, :271-350); the
+    TorchRec-side arguments are kept for tables without `use_dynamicemb`, which are left to TorchRec's EmbeddingShardingPlanner (needs torchrec).
+    World size: `world_size=` if given, else `topology.world_size`, else the default process group's size, else 1.
+    Also accepted (this package's earlier call form): `DynamicEmbeddingShardingPlanner(constraints_dict, world_size=W).plan({table: rows})`."""
 
-    def __init__(self, constraints: Optional[Dict[str, DynamicEmbParameterConstraints]] = None, world_size: Optional[int] = None, **kwargs):
-        self.constraints, self.world_size, self.kwargs = constraints or {}, world_size, kwargs
+    def __init__(self, eb_configs=None, topology=None, batch_size: Optional[int] = None, enumerator=None, storage_reservation=None, proposer=None,
+                 partitioner=None, performance_model=None, stats=None, constraints: Optional[Dict[str, DynamicEmbParameterConstraints]] = None,
+                 debug: bool = True, world_size: Optional[int] = None):
+        if isinstance(eb_configs, dict) and constraints is None:          # constraints passed first
+            constraints, eb_configs = eb_configs, None
+        self.constraints = constraints or {}
+        self.eb_configs = list(eb_configs or [])
+        self.topology, self.batch_size, self.debug = topology, batch_size, debug
+        self.torchrec_args = dict(enumerator=enumerator, storage_reservation=storage_reservation, proposer=proposer, partitioner=partitioner,
+                                  performance_model=performance_model, stats=stats)
+        self.world_size = world_size if world_size is not None else getattr(topology, "world_size", None)
 
-    def plan(self, num_embeddings: Dict[str, int]) -> Dict[str, dict]:
-        W = self.world_size if self.world_size is not None else (dist.get_world_size() if dist.is_initialized() else 1)
-        return plan_row_wise(self.constraints, num_embeddings, W)
+    def _world(self, pg=None) -> int:
+        if self.world_size is not None:
+            return int(self.world_size)
+        if dist.is_initialized():
+            return dist.get_world_size(pg) if pg is not None else dist.get_world_size()
+        return 1
+
+    def plan(self, num_embeddings: Optional[Dict[str, int]] = None, sharders=None, pg=None) -> Dict[str, dict]:
+        """{table: {sharding_type, compute_kernel, ranks, local_capacity, dist_type}} for every `use_dynamicemb` table.  `num_embeddings`
+        defaults to the `num_embeddings` of the constructor's `eb_configs` (the reference reads them from there)."""
+        if num_embeddings is not None and not isinstance(num_embeddings, dict):       # reference call form: plan(module, sharders)
+            num_embeddings = None
+        if num_embeddings is None:
+            num_embeddings = {c.name: c.num_embeddings for c in self.eb_configs}
+        missing = [n for n, c in self.constraints.items() if c.use_dynamicemb and n not in num_embeddings]
+        if missing:
+            raise ValueError(f"no num_embeddings for DynamicEmb tables {missing}: pass eb_configs to the constructor or a dict to plan()")
+        out = plan_row_wise(self.constraints, num_embeddings, self._world(pg))
+        for name in out:
+            out[name]["dynamicemb_options"] = self.constraints[name].dynamicemb_options
+        return out
+
+    def collective_plan(self, module=None, sharders=None, pg=None) -> Dict[str, dict]:
+        """planner/planner.py:351 — every rank computes the same plan (it depends only on the constraints and the world size), so there is
+        nothing to broadcast."""
+        return self.plan(None, sharders, pg)
 
 
 ShardedDynamicEmbedding = RowWiseShardedDynamicEmbedding
