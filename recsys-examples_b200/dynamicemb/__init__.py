@@ -9,7 +9,8 @@ from .batched_dynamicemb_tables import BatchedDynamicEmbeddingTablesV2
 from .dynamicemb_extensions import EvictStrategy, InsertResult, ScorePolicy
 from .optimizer import OptimizerArgs, SparseOptimizer, get_optimizer_state_dim
 from .scored_hashtable import LinearBucketTable, ScoreArg, ScoreSpec, get_scored_table, murmur3_hash_64bits
-from .types import (BoundsCheckMode, DynamicEmbCheckMode, DynamicEmbEvictStrategy, DynamicEmbInitializerArgs, DynamicEmbInitializerMode,
+from .embedding_admission import FrequencyAdmissionStrategy, KVCounter, MultiTableKVCounter
+from .types import (AdmissionStrategy, BoundsCheckMode, Counter, DynamicEmbCheckMode, DynamicEmbEvictStrategy, DynamicEmbInitializerArgs, DynamicEmbInitializerMode,
                     DynamicEmbPoolingMode, DynamicEmbScoreStrategy, DynamicEmbTableOptions, EmbOptimType, get_sharded_table_capacity)
 
 __all__ = [
@@ -17,7 +18,7 @@ __all__ = [
     "DynamicEmbPoolingMode", "DynamicEmbScoreStrategy", "DynamicEmbEvictStrategy", "DynamicEmbCheckMode", "EmbOptimType",
     "BoundsCheckMode", "LinearBucketTable", "ScoreArg", "ScoreSpec", "ScorePolicy", "InsertResult", "EvictStrategy",
     "get_scored_table", "murmur3_hash_64bits", "get_sharded_table_capacity", "OptimizerArgs", "SparseOptimizer",
-    "get_optimizer_state_dim",
+    "get_optimizer_state_dim", "AdmissionStrategy", "Counter", "FrequencyAdmissionStrategy", "KVCounter", "MultiTableKVCounter",
 ]
 
 

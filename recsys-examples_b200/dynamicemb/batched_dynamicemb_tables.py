@@ -72,6 +72,7 @@ class PrefetchState:
     num_unique_bound: int           # host-known upper bound of the unique count (sort width)
     num_unique_dev: Optional[torch.Tensor] = None   # device-side count (fused path: buffers are sized by the bound)
     bwd_ws: Optional[object] = None                 # ext.PreparedBackward: pre-sorted (unique idx, gradient row) pairs (backward_prepare)
+    non_admitted_positions: Optional[torch.Tensor] = None   # unique-list positions of keys the admission strategy kept out (rows = -1)
 
     @property
     def num_unique(self) -> int:
@@ -90,6 +91,8 @@ class _LookupFunction(torch.autograd.Function):
         out = ext.gather_forward(module._values, module.max_D, state.rows, state.reverse_indices, n, offsets=offsets if pooled else None,
                                  batch_size=batch_size if pooled else 0, num_features=module.feature_num if pooled else 0,
                                  combiner=combiner, out_dtype=module.output_dtype)
+        if state.non_admitted_positions is not None and state.non_admitted_positions.numel() > 0:
+            out = module._add_non_admitted(out, state, offsets, batch_size, combiner)
         ctx.module, ctx.state, ctx.offsets, ctx.batch_size, ctx.combiner = module, state, offsets, batch_size, combiner
         return out
 
@@ -204,11 +207,49 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
             self._init_per_table.append((mode, p, (self._seed + t * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF))
         self._table_init_dev = ext.make_table_init(self._init_per_table, self._device) if len(table_options) > 1 else None
         self._fused_prefetch = bool(kwargs.get("fused_prefetch", True))     # False = op-by-op path (reference op order, 2 host syncs)
+        # admission (batched_dynamicemb_tables.py:526,624,798-812): table 0's strategy, one fused counter over all tables.  A module with
+        # a strategy runs the op-by-op prefetch (the decision needs the missing keys on the host side of the op sequence, as in the
+        # reference); without one nothing changes.
+        self._admit_strategy = opt0.admit_strategy
+        self._admission_counter = self._create_admission_counter(table_options)
+        if self._admit_strategy is not None and self._admission_counter is None:
+            raise ValueError("admit_strategy needs an admission_counter (KVCounter) in every table's options")
         self._bwd_prep = None                                               # ext.BackwardPrep, created on first training prefetch
         self._force_prepare = False
         self._prefetch_states: Deque[PrefetchState] = deque()
         self._empty_tensor = nn.Parameter(torch.empty(10, requires_grad=True, device=self._device, dtype=self.embedding_dtype))
         self.bounds_check_mode_int = int(bounds_check_mode)
+
+    def _create_admission_counter(self, table_options):
+        """One fused counter table for all tables (batched_dynamicemb_tables.py:798-812)."""
+        counters = [o.admission_counter for o in table_options]
+        if all(c is None for c in counters):
+            return None
+        assert all(c is not None for c in counters), "All tables must either have or not have an admission counter"
+        from .embedding_admission import MultiTableKVCounter
+        return MultiTableKVCounter(counters, device=self._device)
+
+    def _add_non_admitted(self, out, state: PrefetchState, offsets, batch_size, combiner):
+        """Ids whose key was not admitted read a freshly initialised row that is NOT stored (DynamicEmbeddingFunction.forward,
+        batched_dynamicemb_function.py:1090-1097: the table's initializer over the non-admitted positions).  The rows are initialised
+        into a scratch [n_na, value_dim] by the same init kernel, gathered / pooled by the same forward kernel (every other id reads
+        zeros there) and added to the main result; the stored rows contributed zeros at those ids, so sequence outputs are exact."""
+        na = state.non_admitted_positions
+        n_na = na.numel()
+        keys = state.unique_keys[na].contiguous()
+        tids = state.unique_table_ids[na].contiguous() if state.unique_table_ids is not None else None
+        scratch = torch.empty(n_na, self.value_dim, dtype=torch.float32, device=self._device)
+        mode, p, seed0 = self._init_per_table[0]
+        ext.init_rows(scratch, self.max_D, torch.arange(n_na, dtype=torch.int64, device=self._device), keys, mode, *p, seed=seed0, state_init=0.0,
+                      table_ids=tids if self._table_init_dev is not None else None, table_init=self._table_init_dev)
+        rows2 = torch.full((max(state.num_unique_bound, 1),), -1, dtype=torch.int64, device=self._device)
+        rows2[na] = torch.arange(n_na, dtype=torch.int64, device=self._device)
+        pooled = combiner >= 0
+        n = state.reverse_indices.numel()
+        extra = ext.gather_forward(scratch, self.max_D, rows2, state.reverse_indices, n, offsets=offsets if pooled else None,
+                                   batch_size=batch_size if pooled else 0, num_features=self.feature_num if pooled else 0,
+                                   combiner=combiner, out_dtype=torch.float32)
+        return out + extra if out.dtype == torch.float32 else (out.to(torch.float32) + extra).to(out.dtype)
 
     # ------------------------------------------------------------------ scores (batched_dynamicemb_tables.py:1210-1260)
     def _create_score(self):
@@ -339,7 +380,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         T = len(self._dynamicemb_options)
         tb = self._table
         trange = ext.get_table_range(offsets, self.feature_offsets, self.feature_num) if T > 1 else None
-        if self._fused_prefetch:
+        if self._fused_prefetch and self._admit_strategy is None:
             self._prefetch_fused(indices, trange, T, frequency_counters)
             return
         want_freq = self._score_policy() in (ScorePolicy.ACCUMULATE, ScorePolicy.LRU_LFU)
@@ -353,6 +394,15 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         _, founds, slots = tb.lookup(ukeys, utids, self._score_arg(nu, utids, freq), timestamp=ts)
         tb.increment_counter(slots, utids)                       # pin found rows before anything can evict them (:607)
         miss = (~founds).nonzero(as_tuple=True)[0]               # host sync #2 (reference: flagged_compact)
+        non_admitted = None
+        if miss.numel() > 0 and self._admit_strategy is not None:
+            # _prefetch_hbm_direct_path :615-641: count the missing keys, insert only the admitted ones; the others keep slot -1 (their
+            # ids read an initialised row that is not stored, and their gradients are dropped)
+            from .embedding_admission import admission_split
+            admit_mask, _ = admission_split(ukeys[miss], utids[miss], freq[miss] if freq is not None else None, self._admit_strategy,
+                                            self._admission_counter)
+            non_admitted = miss[~admit_mask]
+            miss = miss[admit_mask]
         if miss.numel() > 0:
             mk, mt = ukeys[miss], utids[miss]
             mf = freq[miss] if freq is not None else None
@@ -364,7 +414,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
             tb.increment_counter(new_slots, mt)
             slots[miss] = new_slots
         rows = ext.rows_from_slots(slots, utids, tb.row_base_)
-        self._prefetch_states.append(PrefetchState(ukeys, reverse, utids, slots, rows, nu))
+        self._prefetch_states.append(PrefetchState(ukeys, reverse, utids, slots, rows, nu, non_admitted_positions=non_admitted))
         self._update_score()
 
     def _unique_scratch(self, n: int) -> torch.Tensor:
@@ -464,6 +514,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         get_score() and a later eager step stay consistent with the device."""
         from .types import EmbOptimType
         assert self.training and self._fused_prefetch
+        assert self._admit_strategy is None, "admission decides on the host side of the op sequence: no CUDA-graph step"
         assert self._optimizer_type in (EmbOptimType.SGD, EmbOptimType.EXACT_SGD, EmbOptimType.EXACT_ADAGRAD, EmbOptimType.EXACT_ROWWISE_ADAGRAD)
         assert self._score_policy() not in (ScorePolicy.GLOBAL_TIMER, ScorePolicy.LRU_LFU)
         indices, offsets_i, B = self._split(ids_static, offsets)
@@ -587,7 +638,11 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
                         opt = ck.truncate_optimizer_states_for_checkpoint(self._optimizer, D, dense[:, D:D + sdim])
                     w.write(keys, dense[:, :D], scores, opt)
             if counter:
-                warnings.warn(f"Counter table is none and will not dump it for table: {name}")     # admission counters: out of scope
+                if self._admission_counter is not None:
+                    self._admission_counter.dump(ck.encode_counter_checkpoint_file_path(save_dir, name, rank, world, "keys"),
+                                                 ck.encode_counter_checkpoint_file_path(save_dir, name, rank, world, "frequencies"), t)
+                else:
+                    warnings.warn(f"Counter table is none and will not dump it for table: {name}")
 
     def load(self, save_dir: str, optim: bool = False, counter: bool = False, table_names: Optional[List[str]] = None, pg=None) -> None:
         """Read a checkpoint in the reference's layout: this rank's own files when the world size matches, otherwise every file filtered
@@ -599,7 +654,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         for t, name in enumerate(self._table_names):
             if name not in names:
                 continue
-            kf, vf, sf, of, _, _ = ck.get_loading_files(save_dir, name, rank=rank, world_size=world)
+            kf, vf, sf, of, ckf, cff = ck.get_loading_files(save_dir, name, rank=rank, world_size=world)
             if not kf:
                 continue
             if distributed:
@@ -614,7 +669,11 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
                     self._scores[name] = loaded
                     self._scores_dev = None
             if counter:
-                warnings.warn(f"Counter table is none and will not load for table: {name}")
+                if self._admission_counter is None:
+                    warnings.warn(f"Counter table is none and will not load for table: {name}")
+                    continue
+                for i in range(len(ckf)):
+                    self._admission_counter.load(ckf[i], cff[i], t)
 
     def _load_table_files(self, t: int, meta_path, key_path, value_path, score_path, opt_path, include_optim, timestamp, filter_rank=None):
         """DynamicEmbStorage.load + _load_key_values (key_value_table.py:1909-1976, :1402-1517) on the native ops: insert the keys with the

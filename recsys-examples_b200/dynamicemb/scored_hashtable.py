@@ -8,7 +8,7 @@ DEMB_DETERMINISM_MODE and one launch per wave), no overflow bucket, single Score
 """
 import warnings
 from dataclasses import dataclass
-from typing import List, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
@@ -208,6 +208,72 @@ class LinearBucketTable:
             c = int(counter.item())
             if c:
                 yield keys[:c], scores[:c], idx[:c]
+
+    # ------------------------------------------------------------------ file round trip of one logical table (admission counters)
+    def dump(self, key_file: str, score_files: Dict[str, str], table_id: Optional[int] = None) -> None:
+        """ScoredHashTable.dump (scored_hashtable.py:1083-1126): raw little-endian int64 keys and uint64 scores of the live slots, one
+        logical table (or all of them, table after table); GLOBAL_TIMER scores are written as ages."""
+        name = self.score_names_[0]
+        fscore = None
+        for score_name, path in score_files.items():
+            if score_name != name:
+                print(f"Score name {score_name} not existed, will not dump to {path}.")
+            else:
+                fscore = open(path, "wb")
+        timed = self.score_specs_[0].policy == ScorePolicy.GLOBAL_TIMER
+        ts = ext.device_timestamp() if timed else 0
+        with open(key_file, "wb") as fkey:
+            for tid in ([table_id] if table_id is not None else range(self.num_tables_)):
+                for keys, scores, _ in self.export(tid):
+                    fkey.write(keys.cpu().numpy().tobytes())
+                    if fscore is not None:
+                        s = scores.view(torch.int64)
+                        fscore.write(((ts - s) if timed else s).cpu().numpy().tobytes())
+        if fscore is not None:
+            fscore.close()
+
+    def load(self, key_file: str, score_files: Dict[str, str], table_id: Optional[int] = None, batch_size: int = 65536) -> None:
+        """ScoredHashTable.load (scored_hashtable.py:848-950): insert the keys of the file into logical table `table_id` (default 0) with
+        their stored scores (ASSIGN); with more than one rank each rank keeps `key % world_size == rank` like the reference."""
+        import os
+        import numpy as np
+        import torch.distributed as dist
+        name = self.score_names_[0]
+        tid = table_id if table_id is not None else 0
+        score_path = score_files.get(name)
+        if score_path is None or not os.path.exists(score_path):
+            print(f"Will not load scores for {name}, as not provide the file path or file path not existed.")
+            score_path = None
+        num_keys = os.path.getsize(key_file) // 8
+        if score_path is not None and os.path.getsize(score_path) // 8 != num_keys:
+            raise ValueError(f"The number of keys({num_keys}) in {key_file} does not match with number of scores"
+                             f"({os.path.getsize(score_path) // 8}) in {score_path}.")
+        world, rank = (dist.get_world_size(), dist.get_rank()) if dist.is_initialized() else (1, 0)
+        timed = self.score_specs_[0].policy == ScorePolicy.GLOBAL_TIMER
+        ts = ext.device_timestamp()
+        fscore = open(score_path, "rb") if score_path is not None else None
+        with open(key_file, "rb") as fkey:
+            for start in range(0, num_keys, batch_size):
+                m = min(batch_size, num_keys - start)
+                keys = np.frombuffer(fkey.read(8 * m), dtype=np.int64)
+                scores = np.frombuffer(fscore.read(8 * m), dtype=np.int64) if fscore is not None else None
+                if world > 1:
+                    keep = (keys.view(np.uint64) % np.uint64(world)) == np.uint64(rank)
+                    keys, scores = keys[keep], (scores[keep] if scores is not None else None)
+                if keys.size == 0:
+                    continue
+                k = torch.from_numpy(keys.copy()).to(self.device)
+                t = torch.full((k.numel(),), tid, dtype=torch.int64, device=self.device)
+                if scores is None:      # no score file: timed tables stamp the loading time, the others start from 1
+                    v = None if timed else torch.ones(k.numel(), dtype=torch.int64, device=self.device)
+                    self.insert(k, t, ScoreArg(name=name, value=v), timestamp=ts)
+                else:
+                    s = torch.from_numpy(scores.copy()).to(self.device)
+                    if timed:
+                        s = torch.clamp(ts - s, min=0)
+                    self.insert(k, t, ScoreArg(name=name, value=s, policy=ScorePolicy.ASSIGN), timestamp=ts)
+        if fscore is not None:
+            fscore.close()
 
 
 def get_scored_table(capacity: List[int], bucket_capacity: Optional[int] = None, key_type: Optional[torch.dtype] = torch.int64,

@@ -120,6 +120,9 @@ class RowWiseShardedDynamicEmbedding(_ShardCheckpointMixin, nn.Module):
                  num_embeddings_per_feature: Optional[List[int]] = None, use_index_dedup: bool = True, max_ids_per_step: Optional[int] = None,
                  pair_capacity: Optional[int] = None, recv_capacity: Optional[int] = None):
         super().__init__()
+        if getattr(local, "_admit_strategy", None) is not None:
+            raise NotImplementedError("admission runs the op-by-op prefetch with host-side decisions; the peer-memory step keeps every count "
+                                      "on the device — use RowWiseShardedDynamicEmbeddingA2A for a shard with an admission strategy")
         self.local = local
         self.group = process_group if process_group is not None else dist.group.WORLD
         self.world_size = dist.get_world_size(self.group)

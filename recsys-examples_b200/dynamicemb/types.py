@@ -1,6 +1,7 @@
 """Config enums / dataclasses of the DynamicEmb boundary.  Field names and defaults follow
 /root/reference/corelib/dynamicemb/dynamicemb/{types.py:33-110, dynamicemb_config.py:62-165,448-478}
 so user code written against the reference constructs the same objects."""
+import abc
 import enum
 import math
 from dataclasses import dataclass, field
@@ -140,3 +141,47 @@ def get_sharded_table_capacity(num_embeddings: int, world_size: int, bucket_capa
         raise ValueError(f"bucket_capacity ({bucket_capacity}) must be a positive multiple of {BUCKET_ALIGNMENT}")
     shard_rows = math.ceil(int(num_embeddings) / world_size)
     return align_to_table_size(shard_rows, bucket_capacity)
+
+
+class MemoryType(enum.Enum):
+    """types.py:26-30 of the reference."""
+    DEVICE = "device"
+    MANAGED = "managed"
+    PINNED_HOST = "pinned_host"
+    HOST = "host"
+
+
+class Counter(abc.ABC):
+    """key -> counter map with logical tables (reference types.py:333-398); `MultiTableKVCounter` is the shipped one."""
+
+    @abc.abstractmethod
+    def add(self, keys: torch.Tensor, table_ids: torch.Tensor, frequencies: torch.Tensor) -> torch.Tensor:
+        """Add `frequencies` to the (unique) `keys`; returns the accumulated counter of every key."""
+
+    @abc.abstractmethod
+    def erase(self, keys: torch.Tensor, table_ids: torch.Tensor) -> None:
+        ...
+
+    @abc.abstractmethod
+    def memory_usage(self, mem_type=MemoryType.DEVICE) -> int:
+        ...
+
+    @abc.abstractmethod
+    def load(self, key_file, counter_file, table_id: int) -> None:
+        ...
+
+    @abc.abstractmethod
+    def dump(self, key_file, counter_file, table_id: int) -> None:
+        ...
+
+
+class AdmissionStrategy(abc.ABC):
+    """Decides which missing keys may enter the table (reference types.py:401-420)."""
+
+    @abc.abstractmethod
+    def admit(self, keys: torch.Tensor, frequencies: torch.Tensor) -> torch.Tensor:
+        """Boolean mask over `keys`: True = insert."""
+
+    @abc.abstractmethod
+    def initialize_non_admitted_embeddings(self, buffer: torch.Tensor, indices: torch.Tensor) -> bool:
+        """Fill the rows of keys that were not admitted; False = nothing done (the table's initializer is used)."""

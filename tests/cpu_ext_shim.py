@@ -1,0 +1,260 @@
+"""TEST INFRASTRUCTURE ONLY: a CPU stand-in for the native op layer (`dynamicemb.dynamicemb_extensions`), backed by the oracle.
+
+The product has no CPU path — every op of `dynamicemb_extensions` launches a kernel of librecsys_b200.so.  The HOST logic above the op
+layer (the module's op-by-op prefetch, admission, checkpoint plumbing) is plain Python over tensors, though, and this shim lets the CPU
+suite run it end to end: each native op used by that logic is restated here on the oracle (`oracle/dynamicemb.py`, the C restatement of
+the reference's table) or on torch CPU ops, with the SAME signatures and return conventions as the real op layer.  `patched_module()`
+swaps it into the module / table namespaces for the duration of a test and makes the module allocate on the CPU.
+
+It is only meaningful for small inputs (python loops) and for initializer modes that do not draw random numbers (DEBUG, CONSTANT).
+"""
+import contextlib
+import ctypes
+
+import numpy as np
+import torch
+
+from oracle import dynamicemb as orc
+
+_SENTINEL_MIN = np.uint64(0xFFFFFFFFFFFFFFFD)     # Locked / Reclaim / Empty (types.cuh:117-121)
+
+
+def _np(t, dtype=None):
+    if t is None:
+        return None
+    a = t.detach().contiguous().numpy()
+    return a if dtype is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+def _table(storage, bkt_off, C, ns, bucket_sizes=None, counter=None):
+    """An OracleTable VIEW over the tensors of a LinearBucketTable (the oracle mutates them in place)."""
+    o = orc.OracleTable.__new__(orc.OracleTable)
+    o.C, o.ns = int(C), int(ns)
+    o.bkt_off = np.ascontiguousarray(bkt_off.numpy(), dtype=np.int64)
+    o.num_buckets = int(o.bkt_off[-1])
+    assert storage.is_contiguous()
+    o.storage = storage.numpy()
+    o.bucket_sizes = bucket_sizes.numpy() if bucket_sizes is not None else np.zeros(o.num_buckets, dtype=np.int32)
+    o.counter = counter.numpy() if counter is not None else np.zeros(o.num_buckets * o.C, dtype=np.int32)
+    return o
+
+
+class CpuExt:
+    """Attribute lookups fall through to the real op layer (enums, pure-torch helpers); native ops are overridden below."""
+
+    def __init__(self, real):
+        self._real = real
+        self._clock = 1000
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+    # ------------------------------------------------------------------ table
+    def device_timestamp(self):
+        self._clock += 1
+        return self._clock
+
+    def table_init(self, table_storage, bucket_capacity, num_scores=1):
+        nb = table_storage.numel() // ((9 + 8 * num_scores) * bucket_capacity)
+        orc.lib().orc_table_init(ctypes.c_void_p(table_storage.data_ptr()), ctypes.c_int64(nb), ctypes.c_int64(bucket_capacity), ctypes.c_int64(num_scores))
+
+    def fill_i32(self, t, v):
+        t.fill_(v)
+
+    def table_lookup(self, table_storage, table_bucket_offsets, bucket_capacity, keys, table_ids, score_input, policy_type, num_scores=1, timestamp=0):
+        o = _table(table_storage, table_bucket_offsets, bucket_capacity, num_scores)
+        so, f, idx = o.lookup(_np(keys), _np(table_ids, np.int64), policy=int(policy_type), score_in=_np(score_input), timer=int(timestamp))
+        return torch.from_numpy(so), torch.from_numpy(f), torch.from_numpy(idx)
+
+    def table_insert(self, table_storage, table_bucket_offsets, bucket_capacity, bucket_sizes, keys, table_ids, score_input, policy_type, counter,
+                     insert_results=None, score_output=None, num_scores=1, timestamp=0):
+        if keys.numel() == 0:
+            return torch.empty(0, dtype=torch.int64)
+        o = _table(table_storage, table_bucket_offsets, bucket_capacity, num_scores, bucket_sizes, counter)
+        idx, res, so, _ = o.insert(_np(keys), _np(table_ids, np.int64), policy=int(policy_type), score_in=_np(score_input), timer=int(timestamp),
+                                   use_counter=counter is not None)
+        if insert_results is not None:
+            insert_results.copy_(torch.from_numpy(res))
+        if score_output is not None:
+            score_output.copy_(torch.from_numpy(so))
+        return torch.from_numpy(idx)
+
+    def table_erase(self, table_storage, table_bucket_offsets, bucket_capacity, bucket_sizes, keys, table_ids, indices=None, num_scores=1):
+        if keys.numel():
+            _table(table_storage, table_bucket_offsets, bucket_capacity, num_scores, bucket_sizes).erase(_np(keys), _np(table_ids, np.int64))
+
+    def table_update_counter_with_layout(self, counter, slot_indices, delta, table_bucket_offsets, bucket_capacity, total_capacity=None,
+                                         num_tables=None, table_ids=None, overflow_output_offsets=None, overflow_bucket_capacity=0):
+        s = slot_indices.to(torch.int64)
+        ok = s >= 0
+        base = table_bucket_offsets[:-1] * bucket_capacity
+        g = s + (base[table_ids.to(torch.int64)] if table_ids is not None else 0)
+        counter.index_add_(0, g[ok], torch.full((int(ok.sum()),), int(delta), dtype=counter.dtype))
+
+    def table_export_batch(self, table_storage, bucket_capacity, batch, offset, key_dtype, threshold=None, table_begin=0, num_scores=1, score_index=0):
+        C = bucket_capacity
+        nb = table_storage.numel() // ((9 + 8 * num_scores) * C)
+        o = _table(table_storage, torch.tensor([0, nb]), C, num_scores)
+        keys = o.keys_view().reshape(-1)[offset:offset + batch]
+        scores = o.scores_view()[:, :, score_index].reshape(-1)[offset:offset + batch]
+        live = keys < _SENTINEL_MIN
+        if threshold is not None:
+            live &= scores >= np.uint64(threshold)
+        sel = np.nonzero(live)[0]
+        kout = torch.zeros(batch, dtype=key_dtype)
+        sout = torch.zeros(batch, dtype=torch.int64)
+        iout = torch.zeros(batch, dtype=torch.int64)
+        kout[:sel.size] = torch.from_numpy(keys[sel].copy().view(np.int64)).view(key_dtype) if key_dtype != torch.int64 else torch.from_numpy(keys[sel].copy().view(np.int64))
+        sout[:sel.size] = torch.from_numpy(scores[sel].copy().view(np.int64))
+        iout[:sel.size] = torch.from_numpy(sel.astype(np.int64) + offset - table_begin)
+        return torch.tensor([sel.size], dtype=torch.int64), kout, sout, iout
+
+    # ------------------------------------------------------------------ dedup
+    def get_table_range(self, offsets, feature_offsets, num_features=None):
+        if num_features is None:
+            num_features = int(feature_offsets[-1])
+        B = (offsets.numel() - 1) // num_features if num_features > 0 else 0
+        return offsets.to(torch.int64)[feature_offsets.to(torch.int64) * B].contiguous()
+
+    def segmented_unique_cuda(self, keys, segment_range, num_tables, input_frequencies=None, want_table_ids=False, n_dev=None, scratch=None):
+        n = keys.numel()
+        rng = _np(segment_range, np.int64) if (segment_range is not None and num_tables > 1) else np.array([0, n], dtype=np.int64)
+        uk, inv, offs = orc.segmented_unique(_np(keys), rng)
+        nu = uk.size
+        ukeys = torch.zeros(n, dtype=keys.dtype)
+        ukeys[:nu] = torch.from_numpy(uk)
+        freq = None
+        if input_frequencies is not None:
+            w = _np(input_frequencies, np.int64) if input_frequencies.numel() == n and n > 0 else np.ones(n, dtype=np.int64)
+            f = np.zeros(n, dtype=np.int64)
+            np.add.at(f, inv, w)
+            freq = torch.from_numpy(f)
+        utids = torch.zeros(n, dtype=torch.int64)
+        for t in range(len(offs) - 1):
+            utids[int(offs[t]):int(offs[t + 1])] = t
+        out = (torch.tensor([nu], dtype=torch.int64), ukeys, torch.from_numpy(inv), torch.from_numpy(offs), freq)
+        return out + (utids,) if want_table_ids else out
+
+    # ------------------------------------------------------------------ rows
+    def rows_from_slots(self, slots, table_ids, row_base):
+        base = row_base[table_ids.to(torch.int64)] if (row_base is not None and table_ids is not None) else (row_base[0] if row_base is not None else 0)
+        return torch.where(slots >= 0, slots + base, torch.full_like(slots, -1))
+
+    def init_rows(self, values, emb_dim, rows, keys, mode, p0=0.0, p1=1.0, p2=0.0, p3=0.0, seed=0, state_init=0.0, only_if=None, emb_out=None,
+                  table_ids=None, table_init=None):
+        M = self._real.InitializerMode
+        modes, consts = [int(mode)] * keys.numel(), [float(p0)] * keys.numel()
+        if table_init is not None:
+            img = table_init.numpy().view(np.dtype([("mode", "<i4"), ("p", "<f4", (4,)), ("reserved", "<u4"), ("seed", "<u8")]))
+            tid = table_ids.tolist() if table_ids is not None else [0] * keys.numel()
+            modes, consts = [int(img["mode"][t]) for t in tid], [float(img["p"][t][0]) for t in tid]
+        ku = _np(keys).view(np.uint64)
+        for i in range(keys.numel()):
+            if only_if is not None and not bool(only_if[i]):
+                continue
+            if modes[i] == int(M.DEBUG):
+                v = float(int(ku[i]) % 100000)
+            elif modes[i] == int(M.CONSTANT):
+                v = consts[i]
+            else:
+                raise NotImplementedError("the CPU shim only restates the deterministic initializers (DEBUG, CONSTANT)")
+            r = int(rows[i]) if rows is not None else -1
+            if r >= 0:
+                values[r, :emb_dim] = v
+                values[r, emb_dim:] = state_init
+            if emb_out is not None:
+                emb_out[i, :emb_dim] = v
+
+    def copy_rows(self, values, width, rows, dense, to_table):
+        ok = rows >= 0
+        if to_table:
+            values[rows[ok], :width] = dense[ok, :width]
+        else:
+            dense[:, :width] = 0
+            dense[ok, :width] = values[rows[ok], :width]
+
+    def gather_forward(self, values, emb_dim, rows, inverse, n, *, offsets=None, batch_size=0, num_features=0, combiner=-1, out_dtype=torch.float32,
+                       n_dev=None, out=None):
+        per_id = rows[inverse] if inverse is not None else rows
+        if combiner < 0:
+            res = torch.from_numpy(orc.gather_rows(values.numpy(), emb_dim, _np(per_id, np.int64))) if n else torch.zeros(0, emb_dim)
+        else:
+            res = torch.from_numpy(orc.pool_rows(values.numpy(), emb_dim, _np(offsets, np.int64), _np(per_id, np.int64), combiner, batch_size, num_features))
+        res = res.to(out_dtype)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+    def backward(self, values, emb_dim, inverse, num_unique_bound, rows, grads, *, offsets=None, batch_size=0, num_features=0, combiner=-1,
+                 opt_type=0, lr=0.0, eps=1e-8, beta1=0.9, beta2=0.999, weight_decay=0.0, bc1=1.0, bc2=1.0, want_unique_grads=False, prepared=None,
+                 n_dev=None, grad_row_of=None, unique_grad_addr=None, grad_stride=None):
+        """Per-unique gradient sums (torch index_add in fp32; the GPU kernel's summation order is covered by the GPU tests) + the
+        oracle's optimizer update on rows >= 0."""
+        n = inverse.numel()
+        D = emb_dim
+        g = grads.to(torch.float32)
+        if combiner >= 0:       # pooled: every id of bag (f, b) receives grads[b, f*D:(f+1)*D] (scaled by 1/len for MEAN)
+            off = offsets.to(torch.int64)
+            lens = off[1:] - off[:-1]
+            bag = torch.repeat_interleave(torch.arange(lens.numel()), lens)
+            f, b = bag // batch_size, bag % batch_size
+            per_id = g.view(batch_size, num_features, D)[b, f]
+            if combiner == 1:
+                per_id = per_id / lens[bag].clamp(min=1).to(torch.float32).unsqueeze(1)
+        else:
+            per_id = g.view(n, D)
+        ug = torch.zeros(num_unique_bound, D, dtype=torch.float32)
+        ug.index_add_(0, inverse, per_id)
+        if values is not None and int(opt_type) != 0:
+            ok = (rows[:num_unique_bound] >= 0).nonzero(as_tuple=True)[0]
+            name = {1: "sgd", 2: "adam", 3: "adagrad", 4: "rowwise_adagrad"}[int(opt_type)]
+            step = 1
+            if int(opt_type) == 2:      # bc1 = 1 - beta1^step
+                import math
+                step = max(1, round(math.log(max(1.0 - bc1, 1e-300)) / math.log(beta1)))
+            orc.optimizer_update(values.numpy(), D, _np(rows[ok], np.int64), ug[ok].numpy(), name, lr, eps=eps, beta1=beta1, beta2=beta2,
+                                 weight_decay=weight_decay, step=step)
+        return ug if want_unique_grads else None
+
+
+class _CudaStub:
+    def current_device(self):
+        return 0
+
+    def is_current_stream_capturing(self):
+        return False
+
+    def current_stream(self, *a, **k):
+        class _S:
+            def synchronize(self):
+                pass
+        return _S()
+
+
+class _TorchProxy:
+    """`torch` as the module sees it during a CPU test: every device is the CPU, `torch.cuda` is a stub."""
+
+    def __init__(self):
+        self.cuda = _CudaStub()
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
+
+    def device(self, *a, **k):
+        return torch.device("cpu")
+
+
+@contextlib.contextmanager
+def patched_module():
+    """Swap the CPU shim into the module, table and admission namespaces; yields the shim."""
+    import dynamicemb.batched_dynamicemb_tables as btm
+    import dynamicemb.scored_hashtable as sht
+    real = btm.ext
+    shim = CpuExt(real)
+    saved = (btm.ext, sht.ext, btm.torch)
+    btm.ext, sht.ext, btm.torch = shim, shim, _TorchProxy()
+    try:
+        yield shim
+    finally:
+        btm.ext, sht.ext, btm.torch = saved
