@@ -276,3 +276,17 @@ def test_module_admission_lfu_counts_occurrences_cpu_shim():
 def test_counter_matches_dictionary_cpu_shim():
     with patched_module():
         scenario_counter_dictionary(CPU)
+
+
+def test_module_without_admission_op_by_op_cpu_shim():
+    """The op-by-op prefetch without a strategy: every new key is inserted at once and trains (host logic of the reference's op order)."""
+    with patched_module():
+        m = _module({"fused_prefetch": False}, None)
+        m.train()
+        ids = torch.tensor([3, 4, 3, 5], dtype=torch.int64)
+        off = torch.arange(0, 5, dtype=torch.int64)
+        out = m(ids, off)
+        assert out[:, 0].tolist() == [3.0, 4.0, 3.0, 5.0]
+        out.backward(torch.ones_like(out))
+        snap = _snapshot(m)
+        assert set(snap) == {3, 4, 5} and snap[3][0].item() == 3.0 - 0.5 * 2 and snap[4][0].item() == 4.0 - 0.5
