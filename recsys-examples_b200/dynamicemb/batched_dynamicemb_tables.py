@@ -589,6 +589,41 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
             return keys, vals
         return keys.to(device), vals[:, :self.dims[t]].contiguous().to(device)
 
+    def incremental_dump(self, named_thresholds: Dict[str, int] = None, pg=None):
+        """Keys / embeddings whose score is not below the table's threshold (batched_dynamicemb_tables.py:1432-1482,
+        key_value_table.py:1977-2036).  Tables whose score carries a timestamp (TIMESTAMP, or the compound (TIMESTAMP, LFU): word 0)
+        are thresholded on it — "touched since `threshold`", pass what the previous call returned; the others on the score value.
+        Returns ({table: (keys, embeddings [n, dim])}, {table: next threshold}): CPU tensors; with a process group of more than one rank
+        every rank gets all ranks' rows, concatenated in rank order.  The table scan is the export kernel, the filter a torch mask."""
+        from . import checkpoint as ck
+        import torch.distributed as dist
+        self.flush()
+        gather = pg is not None and dist.is_initialized() and dist.get_world_size(group=pg) > 1
+        ret_tensors, ret_scores, ts = {}, {}, None
+        for name, threshold in (named_thresholds or {}).items():
+            if name not in self._table_names:
+                warnings.warn(f"incremental_dump: table_name '{name}' is not in this module (available: {self._table_names}); skipping.",
+                              UserWarning, stacklevel=2)
+                continue
+            t = self._table_names.index(name)
+            D = self.dims[t]
+            ks, vs = [], []
+            for keys, dense, scores in self._export_batches(t):
+                word = scores[:, 0] if scores.dim() == 2 else scores
+                keep = word >= int(threshold)
+                ks.append(keys[keep])
+                vs.append(dense[keep][:, :D])
+            keys = torch.cat(ks) if ks else torch.empty(0, dtype=self.index_type, device=self._device)
+            vals = torch.cat(vs) if vs else torch.empty(0, D, dtype=torch.float32, device=self._device)
+            ret_tensors[name] = ck.all_gather_keys_values(keys, vals, pg) if gather else (keys.cpu(), vals.cpu())
+            s = self._dynamicemb_options[t].score_strategy
+            if s == DynamicEmbScoreStrategy.TIMESTAMP or (isinstance(s, tuple) and DynamicEmbScoreStrategy.TIMESTAMP in s):
+                ts = ext.device_timestamp() if ts is None else ts
+                ret_scores[name] = ts
+            else:
+                ret_scores[name] = self._scores[name]
+        return ret_tensors, ret_scores
+
     def _evict_strategy_str(self, table_id: int) -> str:
         # str() of the reference's pybind enum, which is what its meta json holds ("EvictStrategy.KLru", dynamic_emb_op.cu:814-819)
         return f"EvictStrategy.{self._dynamicemb_options[table_id].evict_strategy.value.name}"

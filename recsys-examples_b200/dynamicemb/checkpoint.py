@@ -306,3 +306,26 @@ def validate_load_meta(meta: dict, optimizer, evict_strategy_str: str, dist_type
             if file_optstate_dim != want:
                 raise ValueError(f"Optimizer state width in checkpoint is {file_optstate_dim}; expected {want}.")
     return include_optim, file_optstate_dim, num_keys
+
+
+def all_gather_keys_values(keys: torch.Tensor, values: torch.Tensor, pg) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Every rank's (keys [n_r], values [n_r, D]) concatenated in rank order, on the CPU (key_value_table.py:75-111: counts first, then
+    the rows padded to the largest count — all_gather needs equal shapes)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group=pg)
+    n = keys.numel()
+    count = torch.tensor([n], dtype=torch.long, device=keys.device)
+    counts = [torch.empty_like(count) for _ in range(world)]
+    dist.all_gather(counts, count, group=pg)
+    counts = [int(c.item()) for c in counts]
+    max_n = max(counts)
+    kpad = torch.zeros(max_n, dtype=torch.int64, device=keys.device)
+    vpad = torch.zeros(max_n, values.shape[1], dtype=values.dtype, device=values.device)
+    if n > 0:
+        kpad[:n] = keys.view(torch.int64) if keys.dtype != torch.int64 else keys
+        vpad[:n] = values
+    gk = [torch.empty_like(kpad) for _ in range(world)]
+    gv = [torch.empty_like(vpad) for _ in range(world)]
+    dist.all_gather(gk, kpad, group=pg)
+    dist.all_gather(gv, vpad, group=pg)
+    return (torch.cat([gk[i][:counts[i]] for i in range(world)]).cpu(), torch.cat([gv[i][:counts[i]] for i in range(world)]).cpu())

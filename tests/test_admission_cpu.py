@@ -290,3 +290,24 @@ def test_module_without_admission_op_by_op_cpu_shim():
         out.backward(torch.ones_like(out))
         snap = _snapshot(m)
         assert set(snap) == {3, 4, 5} and snap[3][0].item() == 3.0 - 0.5 * 2 and snap[4][0].item() == 4.0 - 0.5
+
+
+def test_incremental_dump_cpu_shim():
+    """STEP scores: rows touched at or after the given step are returned with their embeddings; unknown tables warn."""
+    with patched_module():
+        m = _module({"fused_prefetch": False}, None)
+        m.train()
+        off = lambda n: torch.arange(0, n + 1, dtype=torch.int64)       # noqa: E731
+        for ids in ([1, 2, 3], [3, 4], [5]):
+            x = torch.tensor(ids, dtype=torch.int64)
+            out = m(x, off(len(ids)))
+            out.backward(torch.zeros_like(out))
+        # STEP score of a row = the step of its last access (1, 2, 3)
+        tensors, nxt = m.incremental_dump({"t0": 2})
+        keys, vals = tensors["t0"]
+        assert sorted(keys.tolist()) == [3, 4, 5] and vals.shape == (3, 8) and keys.device.type == "cpu"
+        assert all(float(v[0]) == float(k) for k, v in zip(keys.tolist(), vals))
+        assert nxt == {"t0": m.get_score()["t0"]}
+        assert sorted(m.incremental_dump({"t0": 0})[0]["t0"][0].tolist()) == [1, 2, 3, 4, 5]
+        with pytest.warns(UserWarning):
+            assert m.incremental_dump({"nope": 1}) == ({}, {})
