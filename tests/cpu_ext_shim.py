@@ -218,6 +218,19 @@ class CpuExt:
         return ug if want_unique_grads else None
 
 
+    def reduce_grads(self, reverse_indices, grads, num_unique, batch_size, out_dim, offsets=None, D_offsets=None, combiner=-1, total_D=0):
+        F = (total_D // out_dim) if offsets is not None else 0
+        return self.backward(None, out_dim, reverse_indices, num_unique, None, grads, offsets=offsets, batch_size=batch_size if offsets is not None else 0,
+                             num_features=F, combiner=combiner if offsets is not None else -1, want_unique_grads=True)
+
+    # ------------------------------------------------------------------ row-wise input dist
+    def block_bucketize_sparse_features(self, lengths, indices, batch_size, world_size, block_sizes, dist_type_per_feature=None, weights=None,
+                                        sequence=True):
+        dts = dist_type_per_feature.tolist() if dist_type_per_feature is not None else [0] * (lengths.numel() // max(batch_size, 1))
+        nl, ni, perm = orc.block_bucketize(_np(lengths, np.int64), _np(indices, np.int64), batch_size, world_size, _np(block_sizes, np.int64), dts)
+        return torch.from_numpy(nl), torch.from_numpy(ni), None, (torch.from_numpy(perm) if sequence else None)
+
+
 class _CudaStub:
     def current_device(self):
         return 0
@@ -250,11 +263,12 @@ def patched_module():
     """Swap the CPU shim into the module, table and admission namespaces; yields the shim."""
     import dynamicemb.batched_dynamicemb_tables as btm
     import dynamicemb.scored_hashtable as sht
+    import dynamicemb.shard as shd
     real = btm.ext
     shim = CpuExt(real)
-    saved = (btm.ext, sht.ext, btm.torch)
-    btm.ext, sht.ext, btm.torch = shim, shim, _TorchProxy()
+    saved = (btm.ext, sht.ext, btm.torch, shd.ext)
+    btm.ext, sht.ext, btm.torch, shd.ext = shim, shim, _TorchProxy(), shim
     try:
         yield shim
     finally:
-        btm.ext, sht.ext, btm.torch = saved
+        btm.ext, sht.ext, btm.torch, shd.ext = saved
