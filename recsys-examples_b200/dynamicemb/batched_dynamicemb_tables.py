@@ -356,6 +356,68 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
     def set_learning_rate(self, lr: float) -> None:
         self._optimizer.set_learning_rate(lr)
 
+    # --- the rest of the reference module's small public surface (batched_dynamicemb_tables.py:942-1000); the cache-tier entries are
+    # no-ops here because the only storage tier is HBM-direct
+    @property
+    def cache(self):
+        return None
+
+    def reset_cache_states(self) -> None:
+        pass
+
+    def set_record_cache_metrics(self, record: bool) -> None:
+        pass
+
+    @property
+    def enable_prefetch(self) -> bool:
+        return self._enable_prefetch
+
+    @enable_prefetch.setter
+    def enable_prefetch(self, value: bool) -> None:
+        self._enable_prefetch = value
+
+    def split_embedding_weights(self) -> List[torch.Tensor]:
+        """One placeholder per table, like the reference (:942-953): dynamic tables have no dense weight to split."""
+        return [torch.empty((1, 1), device=self._device, dtype=self.embedding_dtype) for _ in self._dynamicemb_options]
+
+    def fill_tables(self, load_factor: float = 0.95, tolerance: float = 1e-5) -> None:
+        """Raise every table's occupancy to `load_factor` (clamped to 0.95) with uniformly random keys — only the key map is written,
+        value rows stay as allocated (reference :1182-1209, DynamicEmbStorage.fill_tables key_value_table.py:1669-1790).  Batches of
+        random keys are deduplicated, looked up, and the missing ones inserted with the table's current score until the target count (or
+        `abs(load - load_factor) <= tolerance`) is reached."""
+        if load_factor < 0.0:
+            raise ValueError(f"load_factor must be non-negative, got {load_factor}")
+        if tolerance < 0.0:
+            raise ValueError(f"tolerance must be non-negative, got {tolerance}")
+        load_factor = min(load_factor, 0.95)
+        tb = self._table
+        lfu = self._score_policy() in (ScorePolicy.ACCUMULATE, ScorePolicy.LRU_LFU)
+        for t in range(len(self._dynamicemb_options)):
+            cap = tb.capacity(t)
+            if cap == 0:
+                continue
+            remaining = max(0, min(cap, int(load_factor * cap)) - tb.size(t))
+            stale = 0
+            while remaining > 0:
+                n_gen = min(min(262144, max(4096, remaining * 4)), remaining * 8 + 1024)
+                keys = torch.randint(0, torch.iinfo(torch.int64).max, (n_gen,), device=self._device, dtype=torch.int64).to(self.index_type)
+                keys, counts = torch.unique(keys, return_counts=True)
+                tids = torch.full((keys.numel(),), t, dtype=torch.int64, device=self._device)
+                ts = ext.device_timestamp()
+                _, founds, _ = tb.lookup(keys, tids, self._score_arg(keys.numel(), tids, counts if lfu else None), timestamp=ts)
+                new = (~founds).nonzero(as_tuple=True)[0][:remaining]
+                if new.numel() == 0:
+                    stale += 1
+                    if stale > 1000:
+                        raise RuntimeError(f"fill_tables: stalled on table {t}")
+                    continue
+                stale = 0
+                nk, nt = keys[new].contiguous(), tids[new].contiguous()
+                tb.insert(nk, nt, self._score_arg(nk.numel(), nt, counts[new] if lfu else None), timestamp=ts)
+                remaining -= int(nk.numel())
+                if tolerance > 0.0 and abs(tb.size(t) / cap - load_factor) <= tolerance:
+                    break
+
     def flush(self) -> None:
         torch.cuda.current_stream(self._device).synchronize()
 

@@ -33,8 +33,8 @@ class MultiTableKVCounter(Counter):
 
     `add` = insert with ScorePolicy.ACCUMULATE (a key that is new gets `frequencies[i]`, a resident key `old + frequencies[i]`; a full
     bucket evicts its least-frequent key, which is the reference's behaviour too) followed by a read-only lookup of the stored values.
-    The reference reads them from the insert's `score_out`; the stored value is the same number and the read-only lookup is the path
-    the oracle-checked tests cover for every policy."""
+    The reference reads them from the insert's `score_out`; the stored value is the same number, and the read-only lookup is the path
+    the GPU parity tests cover for every policy."""
 
     def __init__(self, kv_counters: List[KVCounter], device: torch.device):
         if not kv_counters:
@@ -42,7 +42,7 @@ class MultiTableKVCounter(Counter):
         self.score_name_ = "counter"
         self.score_specs_ = [ScoreSpec(name=self.score_name_, policy=ScorePolicy.ACCUMULATE)]
         self.table_ = get_scored_table([kv.capacity for kv in kv_counters], kv_counters[0].bucket_capacity, kv_counters[0].key_type,
-                                       self.score_specs_, device)
+                                       self.score_specs_, device)          # positional order of the reference's call (:72-78)
 
     def add(self, keys: torch.Tensor, table_ids: torch.Tensor, frequencies: torch.Tensor) -> torch.Tensor:
         n = keys.numel()

@@ -6,6 +6,7 @@ Host-side mirror of /root/reference/corelib/dynamicemb/dynamicemb/scored_hashtab
 results.  Differences: insert is always deterministic (the reference needs
 DEMB_DETERMINISM_MODE and one launch per wave), no overflow bucket, single ScoreSpec.
 """
+import enum
 import warnings
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
@@ -276,8 +277,25 @@ class LinearBucketTable:
             fscore.close()
 
 
+class ProbingType(enum.Enum):
+    """scored_hashtable.py:72-75"""
+    LINEAR = "linear"
+    CHAINED = "separate_chain"
+
+
+@enum.unique
+class ReductionType(enum.Enum):
+    """scored_hashtable.py:77-80"""
+    LINEAR = "linear"
+    DOUBLY_LINKED = "doubly_linked"
+
+
 def get_scored_table(capacity: List[int], bucket_capacity: Optional[int] = None, key_type: Optional[torch.dtype] = torch.int64,
-                     score_specs: Optional[List[ScoreSpec]] = None, device: torch.device = None, enable_overflow: bool = False) -> LinearBucketTable:
+                     score_specs: Optional[List[ScoreSpec]] = None, device: torch.device = None, probing_type=ProbingType.LINEAR,
+                     reduction_type=ReductionType.LINEAR, bucket_load_factor=0.5, enable_overflow: bool = False) -> LinearBucketTable:
+    """scored_hashtable.py:1734-1757 (linear probing + linear reduction is the only table the reference builds either)."""
+    if probing_type != ProbingType.LINEAR or reduction_type != ReductionType.LINEAR:
+        raise NotImplementedError
     if score_specs is None:
         score_specs = [ScoreSpec(name="timestamp", policy=ScorePolicy.GLOBAL_TIMER)]
     return LinearBucketTable(capacity, score_specs, key_type=key_type, bucket_capacity=bucket_capacity, device=device,

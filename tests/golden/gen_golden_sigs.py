@@ -19,7 +19,17 @@ TARGETS = {
         "BatchedDynamicEmbeddingTablesV2.__init__", "BatchedDynamicEmbeddingTablesV2.forward", "BatchedDynamicEmbeddingTablesV2.prefetch",
         "BatchedDynamicEmbeddingTablesV2.dump", "BatchedDynamicEmbeddingTablesV2.load", "BatchedDynamicEmbeddingTablesV2.export_keys_values",
         "BatchedDynamicEmbeddingTablesV2.set_score", "BatchedDynamicEmbeddingTablesV2.set_learning_rate",
+        "BatchedDynamicEmbeddingTablesV2.incremental_dump", "BatchedDynamicEmbeddingTablesV2.fill_tables",
+        "BatchedDynamicEmbeddingTablesV2.split_embedding_weights", "BatchedDynamicEmbeddingTablesV2.reset_cache_states",
+        "BatchedDynamicEmbeddingTablesV2.set_record_cache_metrics", "BatchedDynamicEmbeddingTablesV2.flush", "BatchedDynamicEmbeddingTablesV2.get_score",
         "encode_meta_json_file_path", "encode_checkpoint_file_path", "encode_counter_checkpoint_file_path", "find_files", "get_loading_files"],
+    "corelib/dynamicemb/dynamicemb/embedding_admission.py": [
+        "KVCounter.__init__", "MultiTableKVCounter.__init__", "MultiTableKVCounter.add", "MultiTableKVCounter.erase",
+        "MultiTableKVCounter.memory_usage", "MultiTableKVCounter.load", "MultiTableKVCounter.dump",
+        "FrequencyAdmissionStrategy.__init__", "FrequencyAdmissionStrategy.admit", "FrequencyAdmissionStrategy.initialize_non_admitted_embeddings"],
+    "corelib/dynamicemb/dynamicemb/scored_hashtable.py": [
+        "LinearBucketTable.__init__", "LinearBucketTable.lookup", "LinearBucketTable.insert", "LinearBucketTable.insert_and_evict",
+        "LinearBucketTable.erase", "LinearBucketTable.load", "LinearBucketTable.dump", "get_scored_table"],
 }
 
 

@@ -311,3 +311,23 @@ def test_incremental_dump_cpu_shim():
         assert sorted(m.incremental_dump({"t0": 0})[0]["t0"][0].tolist()) == [1, 2, 3, 4, 5]
         with pytest.warns(UserWarning):
             assert m.incremental_dump({"nope": 1}) == ({}, {})
+
+
+def test_small_public_surface_and_fill_tables_cpu_shim():
+    """cache-tier no-ops, enable_prefetch, split_embedding_weights, fill_tables (reference batched_dynamicemb_tables.py:942-1000,:1182)."""
+    with patched_module():
+        m = _module({"fused_prefetch": False}, None, T=2, cap=1024)
+        assert m.cache is None and m.enable_prefetch is False
+        m.enable_prefetch = True
+        assert m.enable_prefetch is True
+        m.reset_cache_states(), m.set_record_cache_metrics(True)
+        assert [tuple(w.shape) for w in m.split_embedding_weights()] == [(1, 1), (1, 1)]
+        torch.manual_seed(0)
+        m.fill_tables(0.5)
+        for t in range(2):
+            assert abs(m.tables.size(t) - 512) <= 8, m.tables.size(t)       # a full bucket evicts instead of growing: a few keys may be lost
+        m.fill_tables(2.0)                                                   # clamped to 0.95
+        for t in range(2):
+            assert 0.9 * 1024 <= m.tables.size(t) <= int(0.95 * 1024)
+        with pytest.raises(ValueError):
+            m.fill_tables(-0.1)
