@@ -1,9 +1,10 @@
 """BatchedDynamicEmbeddingTablesV2 — the TBE-shaped module TorchRec's row-wise sharding wrapper calls.
 
 Drop-in for /root/reference/corelib/dynamicemb/dynamicemb/batched_dynamicemb_tables.py:452-1440
-(ctor :462-508, forward :999-1088, prefetch :1090) restricted to the HBM-direct storage tier
-(`DynamicEmbStorage`, key_value_table.py:1654; cache / host / external tiers are out of scope,
-"no CPU fallback").  Orchestration follows batched_dynamicemb_function.py
+(ctor :462-508, forward :999-1088, prefetch :1090) for the HBM-direct storage tier
+(`DynamicEmbStorage`, key_value_table.py:1654) and, with `caching=True`, an HBM cache in front of a table whose value rows live in pinned
+host memory (`DynamicEmbCache`, `_prefetch_cache_path` batched_dynamicemb_function.py:296-556; every row is still moved by the GPU
+kernels — "no CPU fallback"; external parameter servers and the cache-less hybrid tier are out of scope).  Orchestration follows batched_dynamicemb_function.py
 (dynamicemb_prefetch :699, _prefetch_hbm_direct_path :559, DynamicEmbeddingFunction :1044/:1194)
 with the kernel sequence collapsed:
 
@@ -88,7 +89,7 @@ class _LookupFunction(torch.autograd.Function):
         pooled = module.pooling_mode != DynamicEmbPoolingMode.NONE
         combiner = int(module.pooling_mode) if pooled else -1
         n = state.reverse_indices.numel()
-        out = ext.gather_forward(module._values, module.max_D, state.rows, state.reverse_indices, n, offsets=offsets if pooled else None,
+        out = ext.gather_forward(module._hot_values, module.max_D, state.rows, state.reverse_indices, n, offsets=offsets if pooled else None,
                                  batch_size=batch_size if pooled else 0, num_features=module.feature_num if pooled else 0,
                                  combiner=combiner, out_dtype=module.output_dtype)
         if state.non_admitted_positions is not None and state.non_admitted_positions.numel() > 0:
@@ -105,7 +106,7 @@ class _LookupFunction(torch.autograd.Function):
             grads = grads.clamp(-opt.args.max_gradient, opt.args.max_gradient)
         opt.step()
         pooled = ctx.combiner >= 0
-        ext.backward(m._values, m.max_D, st.reverse_indices, max(st.num_unique_bound, 1), st.rows, grads, offsets=ctx.offsets if pooled else None,
+        ext.backward(m._hot_values, m.max_D, st.reverse_indices, max(st.num_unique_bound, 1), st.rows, grads, offsets=ctx.offsets if pooled else None,
                      batch_size=ctx.batch_size if pooled else 0, num_features=m.feature_num if pooled else 0, combiner=ctx.combiner,
                      prepared=st.bwd_ws, **opt.kernel_kwargs())
         m._unpin(st)
@@ -149,8 +150,8 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         opt0 = table_options[0]
         for o in table_options:
             assert o.get_grouped_key() == opt0.get_grouped_key(), "All tables must match in grouped keys."
-            if o.caching or o.external_storage is not None:
-                raise NotImplementedError("cache / external storage tiers are out of scope (HBM-direct only); see DESIGN.md")
+            if o.external_storage is not None:
+                raise NotImplementedError("external parameter-server storage is out of scope; see DESIGN.md")
             if o.embedding_dtype != torch.float32:
                 raise NotImplementedError("value rows are fp32 in this build")
             if o.eval_initializer_args != opt0.eval_initializer_args:
@@ -196,7 +197,14 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
                                         key_type=self.index_type, bucket_capacity=opt0.bucket_capacity, device=self._device)
         self.value_dim = self.max_D + self._optimizer.get_state_dim(self.max_D)
         self.value_dim = (self.value_dim + 3) // 4 * 4
-        self._values = torch.zeros(self._table.capacity_, self.value_dim, dtype=torch.float32, device=self._device)
+        self._caching, self._cache, self._cache_values = False, None, None
+        if any(o.caching for o in table_options):
+            self._create_cache_storage(table_options, policy)
+        else:
+            self._values = torch.zeros(self._table.capacity_, self.value_dim, dtype=torch.float32, device=self._device)
+        # the tier forward / backward read and write, and whose pin counters protect the rows of a prefetched batch
+        self._hot_values = self._cache_values if self._caching else self._values
+        self._hot_table = self._cache if self._caching else self._table
         self._seed = int(kwargs.get("seed", 0))
         # one initializer per table (reference: _create_initializers, batched_dynamicemb_tables.py:789-796): mode / bounds from that table's
         # initializer_args (default bound 1/sqrt(that table's capacity)), Philox seed mixed with the table id so the same key in two
@@ -219,6 +227,30 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         self._prefetch_states: Deque[PrefetchState] = deque()
         self._empty_tensor = nn.Parameter(torch.empty(10, requires_grad=True, device=self._device, dtype=self.embedding_dtype))
         self.bounds_check_mode_int = int(bounds_check_mode)
+
+    def _create_cache_storage(self, table_options, policy) -> None:
+        """caching=True (batched_dynamicemb_tables.py:637-700): when the value rows do not fit `local_hbm_for_values`, an HBM cache of
+        `capacity * local_hbm / total` rows per table (1024-slot buckets) fronts the full table, whose value rows are allocated in pinned
+        host memory and read / written by the same row-copy kernels over the host link.  If everything fits, the module stays HBM-only."""
+        assert all(o.caching for o in table_options), "caching is a grouped option: set it on every table of the module"
+        if self._table.num_scores_ != 1:
+            raise NotImplementedError("caching with the compound (TIMESTAMP, LFU) score is not built")
+        total = sum(o.max_capacity * 4 * self.value_dim for o in table_options)
+        local_hbm = sum(o.local_hbm_for_values for o in table_options)
+        if total <= local_hbm:
+            self._values = torch.zeros(self._table.capacity_, self.value_dim, dtype=torch.float32, device=self._device)
+            return
+        if local_hbm <= 0:
+            raise ValueError("Can't use caching mode as the reserved HBM size is too small.")
+        scale = local_hbm / total
+        caps = [min(o.max_capacity, max(1, int(o.max_capacity * scale))) for o in table_options]
+        # a NO_EVICTION backing table keeps its policy; its cache must be able to evict: LRU (reference :662-669)
+        self._cache_policy = (ScorePolicy.GLOBAL_TIMER if table_options[0].score_strategy == DynamicEmbScoreStrategy.NO_EVICTION else policy)
+        self._cache = LinearBucketTable(caps, [ScoreSpec(name="score", policy=self._cache_policy)], key_type=self.index_type,
+                                        bucket_capacity=1024, device=self._device)
+        self._cache_values = torch.zeros(self._cache.capacity_, self.value_dim, dtype=torch.float32, device=self._device)
+        self._values = ext.host_values(self._table.capacity_, self.value_dim)
+        self._caching = True
 
     def _create_admission_counter(self, table_options):
         """One fused counter table for all tables (batched_dynamicemb_tables.py:798-812)."""
@@ -325,10 +357,10 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
             out[name] = ext.device_timestamp() if timed else self._scores[name]
         return out
 
-    def _score_arg(self, n: int, table_ids: torch.Tensor, freq: Optional[torch.Tensor], const: bool = False) -> ScoreArg:
+    def _score_arg(self, n: int, table_ids: torch.Tensor, freq: Optional[torch.Tensor], const: bool = False, policy=None) -> ScoreArg:
         if const:
             return ScoreArg(name="score", policy=ScorePolicy.CONST)
-        policy = self._score_policy()
+        policy = self._score_policy() if policy is None else policy
         if policy == ScorePolicy.GLOBAL_TIMER:
             return ScoreArg(name="score", policy=policy)
         if policy in (ScorePolicy.ACCUMULATE, ScorePolicy.LRU_LFU):
@@ -357,13 +389,17 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         self._optimizer.set_learning_rate(lr)
 
     # --- the rest of the reference module's small public surface (batched_dynamicemb_tables.py:942-1000); the cache-tier entries are
-    # no-ops here because the only storage tier is HBM-direct
+    # no-ops without caching=True
     @property
     def cache(self):
-        return None
+        """The cache tier's table (None without caching)."""
+        return self._cache
 
     def reset_cache_states(self) -> None:
-        pass
+        """Empty the cache WITHOUT writing it back (reference :959-962); call flush() first to keep its rows."""
+        if self._caching:
+            self.reset_prefetch()
+            self._cache.reset()
 
     def set_record_cache_metrics(self, record: bool) -> None:
         pass
@@ -419,6 +455,9 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
                     break
 
     def flush(self) -> None:
+        """Write the cache back to the backing table (reference :955-957), then wait for the stream."""
+        if self._caching:
+            self._flush_cache()
         torch.cuda.current_stream(self._device).synchronize()
 
     def reset_prefetch(self) -> None:
@@ -442,7 +481,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         T = len(self._dynamicemb_options)
         tb = self._table
         trange = ext.get_table_range(offsets, self.feature_offsets, self.feature_num) if T > 1 else None
-        if self._fused_prefetch and self._admit_strategy is None:
+        if self._fused_prefetch and self._admit_strategy is None and not self._caching:
             self._prefetch_fused(indices, trange, T, frequency_counters)
             return
         want_freq = self._score_policy() in (ScorePolicy.ACCUMULATE, ScorePolicy.LRU_LFU)
@@ -452,6 +491,9 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         nu = int(num_u.item())                                   # host sync #1 (reference: batched_dynamicemb_function.py:141-142)
         ukeys, utids = ukeys[:nu], utids[:nu]
         freq = freq[:nu] if freq is not None else None
+        if self._caching:
+            self._prefetch_cached(ukeys, utids, freq, reverse, nu)
+            return
         ts = ext.device_timestamp()
         _, founds, slots = tb.lookup(ukeys, utids, self._score_arg(nu, utids, freq), timestamp=ts)
         tb.increment_counter(slots, utids)                       # pin found rows before anything can evict them (:607)
@@ -478,6 +520,127 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         rows = ext.rows_from_slots(slots, utids, tb.row_base_)
         self._prefetch_states.append(PrefetchState(ukeys, reverse, utids, slots, rows, nu, non_admitted_positions=non_admitted))
         self._update_score()
+
+    def _prefetch_cached(self, ukeys, utids, freq, reverse, nu) -> None:
+        """_prefetch_cache_path (batched_dynamicemb_function.py:296-556) on the table / row-copy kernels: cache lookup -> backing-table
+        lookup of the misses (+ admission of keys found in neither) -> insert into the cache with eviction -> the evicted rows are read
+        out of the cache BEFORE their slots are overwritten -> rows found in the backing table are copied into their cache slots, new keys
+        initialised there -> evicted rows written back to the backing table -> pin.  Keys the cache cannot place (every slot of the
+        bucket pinned) keep slot -1 like a failed insert of the HBM-direct path (the reference parks them in an overflow bucket)."""
+        cache, st, V = self._cache, self._table, self.value_dim
+        ts = ext.device_timestamp()
+        _, founds, cslots = cache.lookup(ukeys, utids, self._score_arg(nu, utids, freq, policy=self._cache_policy), timestamp=ts)
+        slots = cslots.clone()
+        cache.increment_counter(cslots, utids)                  # pins the hits (slot -1 is skipped)
+        miss = (~founds).nonzero(as_tuple=True)[0]
+        non_admitted = None
+        if miss.numel() > 0:
+            mk, mt = ukeys[miss].contiguous(), utids[miss].contiguous()
+            mf = freq[miss] if freq is not None else None
+            s_score, s_found, s_slots = st.lookup(mk, mt, self._score_arg(mk.numel(), mt, mf), timestamp=ts)
+            ins_mask = s_found.clone()
+            new_in_miss = ~s_found
+            if bool(new_in_miss.any()):
+                if self._admit_strategy is not None:
+                    from .embedding_admission import admission_split
+                    admit_mask, _ = admission_split(mk[new_in_miss], mt[new_in_miss], mf[new_in_miss] if mf is not None else None,
+                                                    self._admit_strategy, self._admission_counter)
+                    ins_mask[new_in_miss] = admit_mask
+                    if not bool(ins_mask.all()):
+                        non_admitted = miss[~ins_mask]
+                else:
+                    ins_mask[:] = True
+            ins = ins_mask.nonzero(as_tuple=True)[0]
+            if ins.numel() > 0:
+                ik, it = mk[ins].contiguous(), mt[ins].contiguous()
+                iscore = None
+                if mf is not None:                               # a frequency score travels with the row: backing-table count + this batch
+                    mf = torch.where(s_found, s_score, mf)
+                    iscore = mf[ins]
+                cidx, nev, ek, ei, es, et = cache.insert_and_evict(ik, it, self._score_arg(ik.numel(), it, iscore, policy=self._cache_policy),
+                                                                   timestamp=ts)
+                # A key inserted by this call can be evicted again by a later key of the SAME call when new keys carry the lowest score of
+                # the bucket (LFU): its slot index is stale and its "evicted" record has no row yet.  A read-only lookup tells which
+                # inserted keys really own their slot; the others count as failed inserts (slot -1) and their records are dropped.
+                _, f2, s2 = cache.lookup(ik, it, ScoreArg(name="score", policy=ScorePolicy.CONST))
+                lost = ~(f2 & (s2 == cidx)) & (cidx >= 0)
+                keep = ei >= 0                                   # BUSY records (the new key itself, negative index) carry no row
+                if bool(lost.any()):
+                    cidx = torch.where(lost, torch.full_like(cidx, -1), cidx)
+                    for t in range(len(self._dynamicemb_options)):
+                        keep &= ~((et == t) & torch.isin(ek, ik[lost & (it == t)]))
+                ek, ei, es, et = ek[keep].contiguous(), ei[keep].contiguous(), es[keep].contiguous(), et[keep].contiguous()
+                ev_vals = torch.empty(ek.numel(), V, dtype=torch.float32, device=self._device)
+                if ek.numel() > 0:
+                    ext.copy_rows(self._cache_values, V, ext.rows_from_slots(ei, et, cache.row_base_), ev_vals, to_table=False)
+                crow = ext.rows_from_slots(cidx, it, cache.row_base_)
+                sf = s_found[ins]
+                if bool(sf.any()):
+                    tmp = torch.empty(int(sf.sum()), V, dtype=torch.float32, device=self._device)
+                    ext.copy_rows(self._values, V, ext.rows_from_slots(s_slots[ins][sf].contiguous(), it[sf].contiguous(), st.row_base_), tmp,
+                                  to_table=False)
+                    ext.copy_rows(self._cache_values, V, crow[sf].contiguous(), tmp, to_table=True)
+                nw = ~sf
+                if bool(nw.any()):
+                    mode, p, seed0 = self._init_per_table[0]
+                    ext.init_rows(self._cache_values, self.max_D, crow[nw].contiguous(), ik[nw].contiguous(), mode, *p, seed=seed0,
+                                  state_init=self._optimizer.initial_state_value,
+                                  table_ids=it[nw].contiguous() if self._table_init_dev is not None else None, table_init=self._table_init_dev)
+                if ek.numel() > 0:
+                    self._write_back(ek, et, es, ev_vals, ts)
+                cache.increment_counter(cidx, it)
+                slots[miss[ins]] = cidx
+        rows = ext.rows_from_slots(slots, utids, cache.row_base_)
+        self._prefetch_states.append(PrefetchState(ukeys, reverse, utids, slots, rows, nu, non_admitted_positions=non_admitted))
+        self._update_score()
+
+    def _write_back(self, keys, tids, scores, vals, ts) -> None:
+        """Rows leaving the cache go to the backing table under their cache score (storage.insert of the evicted, :527-530)."""
+        st = self._table
+        sslots = st.insert(keys, tids, ScoreArg(name="score", value=scores.to(torch.int64).contiguous(), policy=ScorePolicy.ASSIGN), timestamp=ts)
+        ext.copy_rows(self._values, self.value_dim, ext.rows_from_slots(sslots, tids, st.row_base_), vals, to_table=True)
+
+    def _flush_cache(self) -> None:
+        """flush_cache (key_value_table.py): every cached row is written to the backing table; the cache keeps its (now clean) content."""
+        cache, V = self._cache, self.value_dim
+        ts = ext.device_timestamp()
+        for t in range(len(self._dynamicemb_options)):
+            base = int(cache.table_bucket_offsets_cpu_[t]) * cache.bucket_capacity_
+            for keys, scores, idx in cache.export(t):
+                vals = torch.empty(keys.numel(), V, dtype=torch.float32, device=self._device)
+                ext.copy_rows(self._cache_values, V, (idx + base).contiguous(), vals, to_table=False)
+                tids = torch.full((keys.numel(),), t, dtype=torch.int64, device=self._device)
+                self._write_back(keys, tids, scores, vals, ts)
+
+    def _eval_forward_cached(self, indices, offsets, B) -> torch.Tensor:
+        """Read-only lookup through both tiers (dynamicemb_eval_forward with a cache, :836-1040): an id reads its cached row, else its
+        row of the backing table, else the eval initializer's constant.  Two gathers (ids absent from a tier read zeros there) + the constant."""
+        cache, st, D = self._cache, self._table, self.max_D
+        T = len(self._dynamicemb_options)
+        n = indices.numel()
+        if T > 1:
+            trange = ext.get_table_range(offsets, self.feature_offsets, self.feature_num)
+            tids = torch.repeat_interleave(torch.arange(T, device=self._device), trange[1:] - trange[:-1], output_size=n)
+        else:
+            tids = torch.zeros(n, dtype=torch.int64, device=self._device)
+        const = ScoreArg(name="score", policy=ScorePolicy.CONST)
+        _, cf, cs = cache.lookup(indices, tids, const)
+        _, sf, ss = st.lookup(indices, tids, const)
+        crow = ext.rows_from_slots(cs, tids, cache.row_base_)
+        srow = ext.rows_from_slots(torch.where(cf, torch.full_like(ss, -1), ss), tids, st.row_base_)
+        pooled = self.pooling_mode != DynamicEmbPoolingMode.NONE
+        kw = dict(offsets=offsets if pooled else None, batch_size=B if pooled else 0, num_features=self.feature_num if pooled else 0,
+                  combiner=int(self.pooling_mode) if pooled else -1, out_dtype=torch.float32)
+        shape = (B, self.feature_num * D) if pooled else (n, D)
+        new = lambda: torch.empty(shape, dtype=torch.float32, device=self._device)       # noqa: E731  (the host-resident tier cannot size `out`)
+        out = ext.gather_forward(self._cache_values, D, crow, None, n, out=new(), **kw) + ext.gather_forward(self._values, D, srow, None, n, out=new(), **kw)
+        ea = self._dynamicemb_options[0].eval_initializer_args
+        absent = ea.value if ea.mode == DynamicEmbInitializerMode.CONSTANT else 0.0
+        if absent != 0.0:
+            fill = torch.empty(1, self.value_dim, dtype=torch.float32, device=self._device).fill_(absent)
+            arow = torch.where(cf | sf, torch.full_like(cs, -1), torch.zeros_like(cs))
+            out = out + ext.gather_forward(fill, D, arow, None, n, out=new(), **kw)
+        return out.to(self.output_dtype)
 
     def _unique_scratch(self, n: int) -> torch.Tensor:
         """Module-owned persistent dedup scratch (left clean by every call): no per-step re-initialisation of 32 B per id."""
@@ -522,7 +685,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         self._update_score()
 
     def _unpin(self, st: PrefetchState) -> None:
-        tb = self._table
+        tb = self._hot_table
         if st.num_unique_dev is not None:
             ext.table_update_counter_n(tb._ref_counter, st.slot_indices, -1, tb.table_bucket_offsets_, tb.bucket_capacity_, st.num_unique_dev,
                                        table_ids=st.unique_table_ids)
@@ -546,6 +709,8 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
     def _eval_forward(self, indices, offsets, B) -> torch.Tensor:
         """dynamicemb_eval_forward (batched_dynamicemb_function.py:836): read-only fused probe+gather; absent ids take the
         eval initializer (constant, default 0)."""
+        if self._caching:
+            return self._eval_forward_cached(indices, offsets, B)
         tb = self._table
         T = len(self._dynamicemb_options)
         trange = ext.get_table_range(offsets, self.feature_offsets, self.feature_num) if T > 1 else None
@@ -577,6 +742,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         from .types import EmbOptimType
         assert self.training and self._fused_prefetch
         assert self._admit_strategy is None, "admission decides on the host side of the op sequence: no CUDA-graph step"
+        assert not self._caching, "the cache path compacts its misses on the host: no CUDA-graph step"
         assert self._optimizer_type in (EmbOptimType.SGD, EmbOptimType.EXACT_SGD, EmbOptimType.EXACT_ADAGRAD, EmbOptimType.EXACT_ROWWISE_ADAGRAD)
         assert self._score_policy() not in (ScorePolicy.GLOBAL_TIMER, ScorePolicy.LRU_LFU)
         indices, offsets_i, B = self._split(ids_static, offsets)
@@ -748,6 +914,8 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         import torch.distributed as dist
         names = set(self._table_names if table_names is None else table_names)
         rank, world, distributed = self._rank_world(pg)
+        if self._caching:
+            self.reset_cache_states()          # the files replace the backing table's content: cached copies would be stale
         for t, name in enumerate(self._table_names):
             if name not in names:
                 continue

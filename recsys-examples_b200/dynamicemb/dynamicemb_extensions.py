@@ -356,6 +356,13 @@ def init_rows(values, emb_dim, rows, keys, mode, p0=0.0, p1=1.0, p2=0.0, p3=0.0,
                                  N.ptr(_i64(table_ids)), N.ptr(table_init), float(state_init), N.ptr(only_if), N.ptr(emb_out), N.stream()), "init_rows")
 
 
+def host_values(rows: int, width: int) -> torch.Tensor:
+    """Zeroed fp32 value rows of a backing table in PINNED HOST memory (cache tier, key_value_table.py host-resident `DynamicEmbStorage`).
+    Page-locked through the CUDA host allocator, so with unified addressing the row-copy kernels dereference `data_ptr()` directly over
+    the host link; no CPU code touches the rows."""
+    return torch.zeros(rows, width, dtype=torch.float32, pin_memory=True)
+
+
 def copy_rows(values, width, rows, dense, to_table: bool):
     N.check(N.lib.demb_copy_rows(N.ptr(values), values.stride(0), width, rows.numel(), N.ptr(rows), N.ptr(dense), dense.stride(0),
                                  1 if to_table else 0, N.stream()), "copy_rows")

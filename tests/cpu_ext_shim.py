@@ -79,6 +79,28 @@ class CpuExt:
             score_output.copy_(torch.from_numpy(so))
         return torch.from_numpy(idx)
 
+    def table_insert_and_evict(self, table_storage, table_bucket_offsets, bucket_capacity, bucket_sizes, keys, table_ids, score_input, policy_type,
+                               counter, insert_results=None, score_output=None, num_scores=1, timestamp=0):
+        n = keys.numel()
+        z = lambda: torch.zeros(n, dtype=torch.int64)      # noqa: E731
+        if n == 0:
+            return torch.empty(0, dtype=torch.int64), torch.zeros(1, dtype=torch.int64), torch.zeros(0, dtype=keys.dtype), z(), z(), z()
+        o = _table(table_storage, table_bucket_offsets, bucket_capacity, num_scores, bucket_sizes, counter)
+        idx, res, so, (ek, ei, es, et) = o.insert(_np(keys), _np(table_ids, np.int64), policy=int(policy_type), score_in=_np(score_input),
+                                                  timer=int(timestamp), use_counter=counter is not None)
+        if insert_results is not None:
+            insert_results.copy_(torch.from_numpy(res))
+        if score_output is not None:
+            score_output.copy_(torch.from_numpy(so))
+        outk, outi, outs, outt = torch.zeros(n, dtype=keys.dtype), z(), z(), z()
+        m = ek.size
+        outk[:m] = torch.from_numpy(ek.view(np.int64).copy())
+        outi[:m], outs[:m], outt[:m] = torch.from_numpy(ei.copy()), torch.from_numpy(es.copy()), torch.from_numpy(et.copy())
+        return torch.from_numpy(idx), torch.tensor([m], dtype=torch.int64), outk, outi, outs, outt
+
+    def host_values(self, rows, width):
+        return torch.zeros(rows, width, dtype=torch.float32)
+
     def table_erase(self, table_storage, table_bucket_offsets, bucket_capacity, bucket_sizes, keys, table_ids, indices=None, num_scores=1):
         if keys.numel():
             _table(table_storage, table_bucket_offsets, bucket_capacity, num_scores, bucket_sizes).erase(_np(keys), _np(table_ids, np.int64))
@@ -164,6 +186,26 @@ class CpuExt:
                 values[r, emb_dim:] = state_init
             if emb_out is not None:
                 emb_out[i, :emb_dim] = v
+
+    def lookup_forward(self, table_storage, table_bucket_offsets, bucket_capacity, values, emb_dim, keys, *, row_base=None, table_range=None,
+                       num_tables=1, offsets=None, batch_size=0, num_features=0, combiner=-1, out_dtype=torch.float32, absent_value=0.0,
+                       want_founds=False, num_scores=1):
+        """Read-only probe + gather (the fused eval kernel): ids in table-major order, absent ids read `absent_value`."""
+        n = keys.numel()
+        if table_range is not None and num_tables > 1:
+            tr = table_range.to(torch.int64)
+            tids = torch.repeat_interleave(torch.arange(num_tables), tr[1:] - tr[:-1])
+        else:
+            tids = torch.zeros(n, dtype=torch.int64)
+        _, founds, slots = self.table_lookup(table_storage, table_bucket_offsets, bucket_capacity, keys, tids, None, 0, num_scores=num_scores)
+        rows = self.rows_from_slots(slots, tids, row_base)
+        kw = dict(offsets=offsets, batch_size=batch_size, num_features=num_features, combiner=combiner, out_dtype=torch.float32)
+        out = self.gather_forward(values, emb_dim, rows, None, n, **kw)
+        if absent_value != 0.0:
+            fill = torch.full((1, values.shape[1]), float(absent_value))
+            out = out + self.gather_forward(fill, emb_dim, torch.where(founds, torch.full_like(slots, -1), torch.zeros_like(slots)), None, n, **kw)
+        out = out.to(out_dtype)
+        return (out, founds, slots) if want_founds else out
 
     def copy_rows(self, values, width, rows, dense, to_table):
         ok = rows >= 0

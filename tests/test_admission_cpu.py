@@ -66,13 +66,14 @@ def test_strategy_validation_and_non_admitted_initializer():
     assert bool((buf[[1, 3]] == 0.5).all()) and bool((buf[[0, 2]] == 1).all())
 
 
-def _module(btm_kwargs, threshold, T=1, pooling=None, score_strategy=None, cap=2048, counter_cap=4096, dim=8):
+def _module(btm_kwargs, threshold, T=1, pooling=None, score_strategy=None, cap=2048, counter_cap=4096, dim=8, caching=False, local_hbm=0):
     from dynamicemb import (BatchedDynamicEmbeddingTablesV2, DynamicEmbInitializerArgs, DynamicEmbInitializerMode, DynamicEmbPoolingMode,
                             DynamicEmbScoreStrategy, DynamicEmbTableOptions, EmbOptimType, FrequencyAdmissionStrategy, KVCounter)
     strat = FrequencyAdmissionStrategy(threshold=threshold) if threshold is not None else None
     opts = [DynamicEmbTableOptions(dim=dim, max_capacity=cap, bucket_capacity=128,
                                    initializer_args=DynamicEmbInitializerArgs(mode=DynamicEmbInitializerMode.DEBUG),
                                    score_strategy=score_strategy if score_strategy is not None else DynamicEmbScoreStrategy.STEP,
+                                   caching=caching, local_hbm_for_values=local_hbm,
                                    admit_strategy=strat, admission_counter=KVCounter(counter_cap, bucket_capacity=128) if strat is not None else None)
             for _ in range(T)]
     return BatchedDynamicEmbeddingTablesV2(opts, table_names=[f"t{i}" for i in range(T)], feature_table_map=list(range(T)),

@@ -1,0 +1,183 @@
+"""Cache tier host logic on the CPU (cache half): `caching=True` = an HBM cache table in front of a backing table
+whose value rows live in host memory (reference `_prefetch_cache_path`, batched_dynamicemb_function.py:296-556).  The module runs on
+the oracle-backed op-layer shim (tests/cpu_ext_shim.py); the model is a dictionary key -> row that knows nothing about tiers, so every
+assertion crosses cache eviction, write-back and re-fetch.  tests/test_zz_cache_tier_gpu.py runs the same scenarios on the kernels."""
+import numpy as np
+import pytest
+import torch
+
+from tests.cpu_ext_shim import patched_module
+from tests.test_admission_cpu import _module, _snapshot
+
+D, LR = 8, 0.5
+
+
+def _cached_module(dev, threshold=None, T=1, pooling=None, score_strategy=None, cap=8192):
+    # value row = 8 fp32 (SGD): HBM budget of 1024 rows per table => cache of 1024 slots (one 1024-slot bucket) per table
+    return _module({"device": dev}, threshold, T=T, pooling=pooling, score_strategy=score_strategy, cap=cap, dim=D, caching=True,
+                   local_hbm=1024 * D * 4)
+
+
+def scenario_cache_train_evict_refetch(dev, score_strategy=None, key_space=3000):
+    """Six training steps of 600 distinct keys out of `key_space` through a 1024-row cache: outputs always equal the dictionary model
+    (rows come back from the backing table with every update they received while cached), and after flush() the backing table holds
+    exactly the model.  With a frequency score new keys carry the LOWEST score of a full bucket and would evict each other inside one
+    insert call (the reference's kernel has the same property); that strategy runs with a key space the cache can hold and checks that
+    the frequencies reach the backing table instead."""
+    rng = np.random.default_rng(0)
+    m = _cached_module(dev, score_strategy=score_strategy)
+    assert m.cache is not None and m.cache.capacity() == 1024 and m._values.shape[0] == 8192
+    m.train()
+    model, seen = {}, {}
+    for step in range(6):
+        uniq = rng.choice(np.arange(1, key_space + 1), size=600, replace=False)
+        ids = np.concatenate([uniq, rng.choice(uniq, size=200)]).astype(np.int64)       # some repeats
+        rng.shuffle(ids)
+        x = torch.from_numpy(ids).to(dev)
+        off = torch.arange(0, ids.size + 1, dtype=torch.int64, device=dev)
+        out = m(x, off)
+        want = torch.tensor([model.get(int(k), float(k % 100000)) for k in ids], dtype=torch.float32)
+        assert torch.equal(out[:, 0].cpu(), want), f"step {step}: forward differs from the model"
+        assert bool((out == out[:, :1]).all())
+        out.backward(torch.ones_like(out))
+        for k in ids.tolist():
+            model[k] = model.get(k, float(k % 100000)) - LR
+            seen[k] = seen.get(k, 0) + 1
+        assert m.cache.size() <= 1024
+    assert (len(model) > 1024) == (key_space > 1024), "the scenario must overflow the cache exactly when the key space does"
+    m.flush()
+    if key_space <= 1024:           # frequency scores: the count of every key travelled cache -> backing table
+        keys, scores, _ = next(m.tables.export(0))
+        assert dict(zip(keys.tolist(), scores.tolist())) == seen
+    snap = _snapshot(m)
+    assert set(snap) == set(model)
+    for k, row in snap.items():
+        assert float(row[0]) == model[k] and bool((row[:D] == row[0]).all()), k
+    # eval: cached, backing-only and absent ids in one batch
+    m.eval()
+    some = list(model)[:50] + [5000, 5001]
+    out = m(torch.tensor(some, dtype=torch.int64, device=dev), torch.arange(0, len(some) + 1, dtype=torch.int64, device=dev))
+    want = torch.tensor([model.get(k, 0.0) for k in some], dtype=torch.float32)
+    assert torch.equal(out[:, 0].cpu(), want)
+    # reset_cache_states drops the cache; the backing table alone still answers
+    m.reset_cache_states()
+    assert m.cache.size() == 0
+    out = m(torch.tensor(some, dtype=torch.int64, device=dev), torch.arange(0, len(some) + 1, dtype=torch.int64, device=dev))
+    assert torch.equal(out[:, 0].cpu(), want)
+
+
+def scenario_cache_pooled_two_tables(dev, mean):
+    """SUM / MEAN pooling over two cached tables, forward values against the model; checkpoint round trip through the backing table."""
+    from dynamicemb import DynamicEmbPoolingMode
+    rng = np.random.default_rng(2)
+    T, B = 2, 64
+    m = _cached_module(dev, T=T, pooling=DynamicEmbPoolingMode.MEAN if mean else DynamicEmbPoolingMode.SUM)
+    m.train()
+    model = [{}, {}]
+    for step in range(4):
+        lens = rng.integers(0, 12, size=T * B)
+        ids = rng.integers(1, 2500, size=int(lens.sum())).astype(np.int64)
+        off_np = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        out = m(torch.from_numpy(ids).to(dev), torch.from_numpy(off_np).to(dev))
+        want = torch.zeros(B, T * D, dtype=torch.float64)
+        for f in range(T):
+            for b in range(B):
+                s, e = off_np[f * B + b], off_np[f * B + b + 1]
+                for k in ids[s:e].tolist():
+                    want[b, f * D:(f + 1) * D] += model[f].get(k, float(k % 100000)) / ((e - s) if mean else 1)
+        assert torch.allclose(out.cpu().double(), want, rtol=1e-5, atol=1e-2), f"step {step}"
+        g = torch.ones_like(out)
+        out.backward(g)
+        for f in range(T):
+            for b in range(B):
+                s, e = off_np[f * B + b], off_np[f * B + b + 1]
+                for k in ids[s:e].tolist():
+                    model[f][k] = model[f].get(k, float(k % 100000)) - LR / ((e - s) if mean else 1)
+    m.flush()
+    for f in range(T):
+        snap = _snapshot(m, f)
+        assert set(snap) == set(model[f])
+        for k, row in snap.items():
+            assert abs(float(row[0]) - model[f][k]) <= 1e-3 * max(1.0, abs(model[f][k])), (f, k)
+
+
+def scenario_cache_with_admission(dev):
+    """Admission in front of the cache (reference :377-410): a key enters the cache at its second presentation, not before; keys the
+    backing table already holds are never counted."""
+    m = _cached_module(dev, threshold=2)
+    m.train()
+    ids = torch.arange(1, 301, dtype=torch.int64, device=dev)
+    off = torch.arange(0, 301, dtype=torch.int64, device=dev)
+    out = m(ids, off)
+    assert torch.equal(out[:, 0].cpu(), torch.arange(1, 301, dtype=torch.float32))      # initializer rows, unstored
+    out.backward(torch.ones_like(out))
+    assert m.cache.size() == 0 and m.tables.size() == 0
+    out = m(ids, off)
+    out.backward(torch.ones_like(out))
+    assert m.cache.size() == 300
+    out = m(ids, off)
+    assert torch.equal(out[:, 0].cpu(), torch.arange(1, 301, dtype=torch.float32) - LR)  # trained once (step 2)
+    out.backward(torch.zeros_like(out))
+    m.flush()
+    assert set(_snapshot(m)) == set(range(1, 301))
+
+
+CPU = torch.device("cpu")
+
+
+@pytest.mark.parametrize("strategy", ["step", "lfu", "timestamp", "no_eviction"])
+def test_cache_train_evict_refetch_cpu_shim(strategy):
+    from dynamicemb import DynamicEmbScoreStrategy as S
+    with patched_module():
+        scenario_cache_train_evict_refetch(CPU, {"step": S.STEP, "lfu": S.LFU, "timestamp": S.TIMESTAMP, "no_eviction": S.NO_EVICTION}[strategy],
+                                           key_space=900 if strategy == "lfu" else 3000)
+
+
+@pytest.mark.parametrize("mean", [False, True])
+def test_cache_pooled_two_tables_cpu_shim(mean):
+    with patched_module():
+        scenario_cache_pooled_two_tables(CPU, mean)
+
+
+def test_cache_with_admission_cpu_shim():
+    with patched_module():
+        scenario_cache_with_admission(CPU)
+
+
+def test_cache_configuration_rules_cpu_shim():
+    """Budget rules of the reference (batched_dynamicemb_tables.py:637-700): everything fits -> HBM only; no budget -> error."""
+    from dynamicemb import DynamicEmbScoreStrategy as S
+    with patched_module():
+        m = _module({}, None, cap=1024, caching=True, local_hbm=1 << 30)
+        assert m.cache is None and m._values.shape[0] == 1024
+        with pytest.raises(ValueError):
+            _module({}, None, cap=8192, caching=True, local_hbm=0)
+        with pytest.raises(NotImplementedError):
+            _module({}, None, cap=8192, caching=True, local_hbm=1024 * 32, score_strategy=(S.TIMESTAMP, S.LFU))
+        m = _cached_module(CPU)
+        m.train()
+        with pytest.raises(AssertionError):
+            m.make_graphed_step(torch.zeros(4, dtype=torch.int64), torch.arange(5), torch.zeros(4, 8))
+
+
+def test_cache_checkpoint_round_trip_cpu_shim(tmp_path):
+    """dump() flushes the cache first; load() drops a stale cache: a cached module's checkpoint restores into another cached module and
+    into an HBM-direct one with identical lookups."""
+    with patched_module():
+        m = _cached_module(CPU)
+        m.train()
+        ids = torch.arange(1, 1501, dtype=torch.int64)                   # more keys than the cache holds
+        for lo in (0, 500, 1000):
+            x = ids[lo:lo + 500]
+            out = m(x, torch.arange(0, 501, dtype=torch.int64))
+            out.backward(torch.ones_like(out))
+        m.dump(str(tmp_path), optim=True)
+        want = ids.to(torch.float32) - LR
+        for fresh in (_cached_module(CPU), _module({"device": CPU, "fused_prefetch": False}, None, cap=8192, dim=D)):
+            fresh.train()
+            stale = fresh(ids[:10], torch.arange(0, 11, dtype=torch.int64))       # something in the cache / table before the load
+            stale.backward(torch.zeros_like(stale))
+            fresh.load(str(tmp_path), optim=True)
+            fresh.eval()
+            out = fresh(ids, torch.arange(0, 1501, dtype=torch.int64))
+            assert torch.equal(out[:, 0], want)
