@@ -4,8 +4,9 @@ all_to_all of rows and of row gradients), with the op layer replaced by the orac
 
 The check is the reference's sharded-vs-unsharded check (corelib/dynamicemb/test/unit_tests/test_sequence_embedding_fw.py) in closed
 form: with the DEBUG initializer a row starts at key % 100000 and SGD moves it by -lr * (number of occurrences of the key over ALL ranks),
-whatever rank owns it — so outputs of step 2 prove that ids, rows and gradients crossed the ranks correctly.  A second variant puts an
-admission strategy on the shards: a key is stored by its owner only at its second presentation.
+whatever rank owns it — so outputs of step 2 prove that ids, rows and gradients crossed the ranks correctly.  Further variants put an
+admission strategy on the shards (a key is stored by its owner only at its second presentation) and / or make every shard a cached
+module (HBM cache over a host-resident table).
 """
 import os
 import sys
@@ -21,7 +22,7 @@ from tests.test_dist_cpu import ROOT, _free_port
 LR = 0.5
 
 
-def _worker(rank, world, port, dedup, threshold, q):
+def _worker(rank, world, port, dedup, threshold, cached, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "recsys-examples_b200"))
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -32,7 +33,8 @@ def _worker(rank, world, port, dedup, threshold, q):
         from dynamicemb.shard import RowWiseShardedDynamicEmbeddingA2A
         T, B, D = 2, 4, 8
         with patched_module():
-            local = _module({"fused_prefetch": False}, threshold, T=T, dim=D)
+            local = _module({"fused_prefetch": False}, threshold, T=T, dim=D, caching=cached, local_hbm=1024 * D * 4 if cached else 0)
+            assert (local.cache is not None) == cached
             local.train()
             sharded = RowWiseShardedDynamicEmbeddingA2A(local, dist.group.WORLD, dist_type="roundrobin", use_index_dedup=dedup)
             # every rank can compute every rank's batch (same generator), so the global occurrence counts are known everywhere
@@ -82,13 +84,13 @@ def _worker(rank, world, port, dedup, threshold, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dedup,threshold", [(True, None), (False, None), (True, 2)])
-def test_sharded_module_matches_closed_form_gloo(dedup, threshold):
+@pytest.mark.parametrize("dedup,threshold,cached", [(True, None, False), (False, None, False), (True, 2, False), (True, None, True), (True, 2, True)])
+def test_sharded_module_matches_closed_form_gloo(dedup, threshold, cached):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, dedup, threshold, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, dedup, threshold, cached, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in procs]
