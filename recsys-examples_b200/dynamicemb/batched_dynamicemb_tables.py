@@ -94,6 +94,8 @@ class _LookupFunction(torch.autograd.Function):
                                  combiner=combiner, out_dtype=module.output_dtype)
         if state.non_admitted_positions is not None and state.non_admitted_positions.numel() > 0:
             out = module._add_non_admitted(out, state, offsets, batch_size, combiner)
+        if module._mixed_D:
+            out = out.index_select(1, module._col_index)          # [B, F*max_D] -> [B, total_D]
         ctx.module, ctx.state, ctx.offsets, ctx.batch_size, ctx.combiner = module, state, offsets, batch_size, combiner
         return out
 
@@ -106,6 +108,8 @@ class _LookupFunction(torch.autograd.Function):
             grads = grads.clamp(-opt.args.max_gradient, opt.args.max_gradient)
         opt.step()
         pooled = ctx.combiner >= 0
+        if m._mixed_D:                                             # [B, total_D] -> [B, F*max_D], zeros in the padding columns
+            grads = torch.zeros(grads.size(0), m.feature_num * m.max_D, dtype=torch.float32, device=grads.device).index_copy_(1, m._col_index, grads)
         ext.backward(m._hot_values, m.max_D, st.reverse_indices, max(st.num_unique_bound, 1), st.rows, grads, offsets=ctx.offsets if pooled else None,
                      batch_size=ctx.batch_size if pooled else 0, num_features=m.feature_num if pooled else 0, combiner=ctx.combiner,
                      prepared=st.bwd_ws, **opt.kernel_kwargs())
@@ -167,7 +171,12 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         self.device_id = torch.device(device).index if device is not None and torch.device(device).index is not None else torch.cuda.current_device()
         self._device = torch.device("cuda", self.device_id)
         self.dims = [o.dim for o in table_options]
-        assert all(d == self.dims[0] for d in self.dims), "this build requires a uniform embedding dim per module (planner splits mixed dims)"
+        # mixed embedding dims (pooled modules only, like the reference's D_offsets output, lookup_kernel.cuh:901-962): every table's rows
+        # are stored max_D wide and the kernels run at max_D; the module slices / scatters the [B, F*max_D] pooled layout to the
+        # [B, total_D] one the caller sees, so a narrower table's padding columns receive zero gradients and are never read
+        self._mixed_D = any(d != self.dims[0] for d in self.dims)
+        if self._mixed_D and DynamicEmbPoolingMode(pooling_mode) == DynamicEmbPoolingMode.NONE:
+            raise NotImplementedError("mixed embedding dims need a pooling mode (sequence outputs have one width); split the tables by dim")
         T_ = len(table_options)
         self.feature_table_map = feature_table_map if feature_table_map is not None else list(range(T_))
         assert sorted(set(self.feature_table_map)) == list(range(T_)), "Each table must have at least one feature!"
@@ -190,6 +199,11 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         self._optimizer = SparseOptimizer(self._optimizer_type, OptimizerArgs(
             learning_rate=learning_rate, eps=eps, initial_accumulator_value=initial_accumulator_value, beta1=beta1, beta2=beta2,
             weight_decay=weight_decay, gradient_clipping=gradient_clipping, max_gradient=max_gradient))
+        if self._mixed_D:
+            if self._optimizer_type == EmbOptimType.EXACT_ROWWISE_ADAGRAD:
+                raise NotImplementedError("row-wise Adagrad averages g^2 over the table's own dim; not available with mixed dims in one module")
+            cols = [f * max(self.dims) + c for f, t in enumerate(self.feature_table_map) for c in range(self.dims[t])]
+            self._col_index = torch.tensor(cols, dtype=torch.int64, device=self._device)       # [total_D] -> column of the max_D layout
         self._create_score()
         # --- storage: key index map + value rows [capacity, emb_dim + state_dim] in HBM (key_value_table.py:346-356)
         policy = self._score_policy()
@@ -640,6 +654,8 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
             fill = torch.empty(1, self.value_dim, dtype=torch.float32, device=self._device).fill_(absent)
             arow = torch.where(cf | sf, torch.full_like(cs, -1), torch.zeros_like(cs))
             out = out + ext.gather_forward(fill, D, arow, None, n, out=new(), **kw)
+        if self._mixed_D:
+            out = out.index_select(1, self._col_index)
         return out.to(self.output_dtype)
 
     def _unique_scratch(self, n: int) -> torch.Tensor:
@@ -717,11 +733,12 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         pooled = self.pooling_mode != DynamicEmbPoolingMode.NONE
         ea = self._dynamicemb_options[0].eval_initializer_args
         absent = ea.value if ea.mode == DynamicEmbInitializerMode.CONSTANT else 0.0
-        return ext.lookup_forward(tb.table_storage_, tb.table_bucket_offsets_, tb.bucket_capacity_, self._values, self.max_D, indices,
-                                  row_base=tb.row_base_, table_range=trange, num_tables=T, offsets=offsets if pooled else None,
-                                  batch_size=B if pooled else 0, num_features=self.feature_num if pooled else 0,
-                                  combiner=int(self.pooling_mode) if pooled else -1, out_dtype=self.output_dtype, absent_value=absent,
-                                  num_scores=tb.num_scores_)
+        out = ext.lookup_forward(tb.table_storage_, tb.table_bucket_offsets_, tb.bucket_capacity_, self._values, self.max_D, indices,
+                                 row_base=tb.row_base_, table_range=trange, num_tables=T, offsets=offsets if pooled else None,
+                                 batch_size=B if pooled else 0, num_features=self.feature_num if pooled else 0,
+                                 combiner=int(self.pooling_mode) if pooled else -1, out_dtype=self.output_dtype, absent_value=absent,
+                                 num_scores=tb.num_scores_)
+        return out.index_select(1, self._col_index) if self._mixed_D else out
 
     # ------------------------------------------------------------------ CUDA-graph training step
     def make_graphed_step(self, ids_static: torch.Tensor, offsets: torch.Tensor, grad_static: torch.Tensor, with_loss: bool = True):
@@ -743,6 +760,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         assert self.training and self._fused_prefetch
         assert self._admit_strategy is None, "admission decides on the host side of the op sequence: no CUDA-graph step"
         assert not self._caching, "the cache path compacts its misses on the host: no CUDA-graph step"
+        assert not self._mixed_D, "mixed dims slice / scatter the pooled layout in torch: use forward() / backward()"
         assert self._optimizer_type in (EmbOptimType.SGD, EmbOptimType.EXACT_SGD, EmbOptimType.EXACT_ADAGRAD, EmbOptimType.EXACT_ROWWISE_ADAGRAD)
         assert self._score_policy() not in (ScorePolicy.GLOBAL_TIMER, ScorePolicy.LRU_LFU)
         indices, offsets_i, B = self._split(ids_static, offsets)
@@ -852,6 +870,15 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
                 ret_scores[name] = self._scores[name]
         return ret_tensors, ret_scores
 
+    def _state_columns(self, dense: torch.Tensor, t: int) -> torch.Tensor:
+        """[n, state_dim(dims[t])] optimizer state of table t out of full value rows.  A narrower table of a mixed-dim module keeps its
+        state in blocks laid out for max_D (Adagrad: [M, M+D); Adam: m [M, M+D), v [2M, 2M+D))."""
+        D, M = self.dims[t], self.max_D
+        sdim = self._optimizer.get_state_dim(D)
+        if D == M:
+            return dense[:, D:D + sdim]
+        return torch.cat([dense[:, (b + 1) * M:(b + 1) * M + D] for b in range(sdim // D)], dim=1)
+
     def _evict_strategy_str(self, table_id: int) -> str:
         # str() of the reference's pybind enum, which is what its meta json holds ("EvictStrategy.KLru", dynamic_emb_op.cu:814-819)
         return f"EvictStrategy.{self._dynamicemb_options[table_id].evict_strategy.value.name}"
@@ -898,7 +925,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
                         scores = ts - scores                                     # age; restored relative to the loading time
                     opt = None
                     if optim and sdim > 0:
-                        opt = ck.truncate_optimizer_states_for_checkpoint(self._optimizer, D, dense[:, D:D + sdim])
+                        opt = ck.truncate_optimizer_states_for_checkpoint(self._optimizer, D, self._state_columns(dense, t))
                     w.write(keys, dense[:, :D], scores, opt)
             if counter:
                 if self._admission_counter is not None:
@@ -967,13 +994,24 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
             if scores is not None and lru:
                 scores = torch.clamp(timestamp - scores, min=0)
             dense = torch.empty(n, self.value_dim, dtype=torch.float32, device=self._device)
-            dense[:, :D] = emb
+            state = None
             if sdim > 0:
-                dense[:, D:D + sdim] = (self._optimizer.initial_state_value if opt is None else
-                                        ck.pad_optimizer_states_from_checkpoint(self._optimizer, D, opt, self._optimizer.initial_state_value,
-                                                                                torch.float32, self._device))
-            if self.value_dim > D + sdim:
-                dense[:, D + sdim:] = 0
+                state = (self._optimizer.initial_state_value if opt is None else
+                         ck.pad_optimizer_states_from_checkpoint(self._optimizer, D, opt, self._optimizer.initial_state_value, torch.float32,
+                                                                 self._device))
+            if D != self.max_D:                                     # narrower table of a mixed-dim module: blocks laid out for max_D
+                dense.zero_()
+                dense[:, :D] = emb
+                if sdim > 0:
+                    for b in range(sdim // D):
+                        lo = (b + 1) * self.max_D
+                        dense[:, lo:lo + D] = state if opt is None else state[:, b * D:(b + 1) * D]
+            else:
+                dense[:, :D] = emb
+                if sdim > 0:
+                    dense[:, D:D + sdim] = state
+                if self.value_dim > D + sdim:
+                    dense[:, D + sdim:] = 0
             tids = torch.full((n,), t, dtype=torch.int64, device=self._device)
             keys = keys.to(self.index_type)
             if ns > 1:

@@ -123,6 +123,8 @@ class RowWiseShardedDynamicEmbedding(_ShardCheckpointMixin, nn.Module):
         if getattr(local, "_admit_strategy", None) is not None:
             raise NotImplementedError("admission runs the op-by-op prefetch with host-side decisions; the peer-memory step keeps every count "
                                       "on the device — use RowWiseShardedDynamicEmbeddingA2A for a shard with an admission strategy")
+        if getattr(local, "_mixed_D", False):
+            raise NotImplementedError("mixed embedding dims inside one sharded module are not built: shard the tables of each dim separately")
         if getattr(local, "_caching", False):
             raise NotImplementedError("the cache tier compacts its misses on the host; the peer-memory step keeps every count on the device — "
                                       "use RowWiseShardedDynamicEmbeddingA2A for a cached shard")
