@@ -216,9 +216,6 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
             self._create_cache_storage(table_options, policy)
         else:
             self._values = torch.zeros(self._table.capacity_, self.value_dim, dtype=torch.float32, device=self._device)
-        # the tier forward / backward read and write, and whose pin counters protect the rows of a prefetched batch
-        self._hot_values = self._cache_values if self._caching else self._values
-        self._hot_table = self._cache if self._caching else self._table
         self._seed = int(kwargs.get("seed", 0))
         # one initializer per table (reference: _create_initializers, batched_dynamicemb_tables.py:789-796): mode / bounds from that table's
         # initializer_args (default bound 1/sqrt(that table's capacity)), Philox seed mixed with the table id so the same key in two
@@ -241,6 +238,15 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         self._prefetch_states: Deque[PrefetchState] = deque()
         self._empty_tensor = nn.Parameter(torch.empty(10, requires_grad=True, device=self._device, dtype=self.embedding_dtype))
         self.bounds_check_mode_int = int(bounds_check_mode)
+
+    # the tier forward / backward read and write, and whose pin counters protect the rows of a prefetched batch
+    @property
+    def _hot_values(self) -> torch.Tensor:
+        return self._cache_values if self._caching else self._values
+
+    @property
+    def _hot_table(self) -> LinearBucketTable:
+        return self._cache if self._caching else self._table
 
     def _create_cache_storage(self, table_options, policy) -> None:
         """caching=True (batched_dynamicemb_tables.py:637-700): when the value rows do not fit `local_hbm_for_values`, an HBM cache of
