@@ -6,6 +6,8 @@ cd "$(dirname "$0")/.."
 O=gpurun_out
 R=${ROUND:-r02}
 timeout 900 python -m pytest tests -m gpu -q --tb=short > $O/${R}_pytest_gpu.log 2>&1; tail -4 $O/${R}_pytest_gpu.log
+# the opt-in tests of the features added after the GPU budget of round 2 was spent (admission, cache tier, mixed dims): first hardware run
+RECSYS_B200_UNVERIFIED_GPU_TESTS=1 timeout 600 python -m pytest tests -m gpu -q --tb=short -k "zz_" > $O/${R}_pytest_gpu_optin.log 2>&1; tail -4 $O/${R}_pytest_gpu_optin.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/${R}_smoke.log 2>&1; tail -2 $O/${R}_smoke.log
 timeout 900 python bench.py > $O/${R}_bench_line.json 2> $O/${R}_bench.err; tail -c 600 $O/${R}_bench_line.json; tail -3 $O/${R}_bench.err
 timeout 400 python bench.py --impl reference --steps 5 --warmup 3 > $O/${R}_bench_ref.json 2> $O/${R}_bench_ref.err; tail -c 400 $O/${R}_bench_ref.json
