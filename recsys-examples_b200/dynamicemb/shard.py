@@ -443,6 +443,10 @@ class _SharderBase:
         fp = {k: v for k, v in self.fused_params.items() if k not in ("dynamicemb_options",)}
         local = BatchedDynamicEmbeddingTablesV2(opts, table_names=names, feature_table_map=fmap, pooling_mode=pooling, device=device,
                                                 optimizer=fp.pop("optimizer", EmbOptimType.SGD), **fp)
+        if not self.pooled and (local._admit_strategy is not None or local._caching):
+            # admission / cache tier decide on the host side of the op sequence: the all_to_all wrapper carries them (sequence mode)
+            return RowWiseShardedDynamicEmbeddingA2A(local, pg, dist_type=opts[0].dist_type, num_embeddings_per_feature=hash_sizes,
+                                                     use_index_dedup=self.use_index_dedup)
         return RowWiseShardedDynamicEmbedding(local, pg, dist_type=opts[0].dist_type, num_embeddings_per_feature=hash_sizes,
                                               use_index_dedup=self.use_index_dedup)
 

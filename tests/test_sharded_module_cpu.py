@@ -98,3 +98,84 @@ def test_sharded_module_matches_closed_form_gloo(dedup, threshold, cached):
         p.join(timeout=60)
     for r, msg in res:
         assert msg == "ok", f"rank {r}: {msg}"
+
+
+class _Cfg:
+    """What the sharder reads of a TorchRec EmbeddingConfig."""
+
+    def __init__(self, name, dim, num):
+        self.name, self.embedding_dim, self.num_embeddings, self.feature_names = name, dim, num, [f"f_{name}"]
+
+
+class _Collection:
+    def __init__(self, cfgs):
+        self._cfgs = cfgs
+
+    def embedding_configs(self):
+        return self._cfgs
+
+
+class _Env:
+    def __init__(self, pg):
+        self.process_group = pg
+
+
+def _worker_planner(rank, world, port, q):
+    """The user-level flow of the reference (apply_dmp: constraints -> planner.plan -> sharder.shard -> sharded module) for a table with
+    an admission strategy: the sharder hands such a shard to the all_to_all wrapper."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "recsys-examples_b200"))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests.cpu_ext_shim import patched_module
+        from dynamicemb import (DynamicEmbInitializerArgs, DynamicEmbInitializerMode, DynamicEmbScoreStrategy, DynamicEmbTableOptions, EmbOptimType,
+                                FrequencyAdmissionStrategy, KVCounter, get_sharded_table_capacity)
+        from dynamicemb.shard import (DynamicEmbeddingCollectionSharder, DynamicEmbeddingShardingPlanner, DynamicEmbParameterConstraints,
+                                      RowWiseShardedDynamicEmbeddingA2A)
+        D = 8
+        with patched_module():
+            opt = DynamicEmbTableOptions(score_strategy=DynamicEmbScoreStrategy.STEP, dist_type="roundrobin",
+                                         initializer_args=DynamicEmbInitializerArgs(mode=DynamicEmbInitializerMode.DEBUG),
+                                         admit_strategy=FrequencyAdmissionStrategy(2), admission_counter=KVCounter(4096, bucket_capacity=128))
+            cons = {"item": DynamicEmbParameterConstraints(use_dynamicemb=True, dynamicemb_options=opt)}
+            cfgs = [_Cfg("item", D, 10_000)]
+            plan = DynamicEmbeddingShardingPlanner(eb_configs=cfgs, constraints=cons, world_size=world).plan()
+            assert plan["item"]["local_capacity"] == get_sharded_table_capacity(10_000, world, 128)
+            sharder = DynamicEmbeddingCollectionSharder(use_index_dedup=True, fused_params={"optimizer": EmbOptimType.SGD, "learning_rate": LR,
+                                                                                            "fused_prefetch": False})
+            sharded = sharder.shard(_Collection(cfgs), plan, env=_Env(dist.group.WORLD), device=torch.device("cpu"))
+            assert isinstance(sharded, RowWiseShardedDynamicEmbeddingA2A) and sharded.local.tables.capacity() == plan["item"]["local_capacity"]
+            sharded.local.train()
+            ids = torch.tensor([3 + rank, 10, 11, 10], dtype=torch.int64)             # 10 and 11 are asked by both ranks
+            ln = torch.tensor([4], dtype=torch.int64)
+            init = ids.to(torch.float32)[:, None].expand(-1, D)
+            for step, want in ((1, init), (2, init)):                                  # counted, then stored (untrained) at step 2
+                out = sharded(ids, ln)
+                assert torch.equal(out, want), f"step {step}"
+                out.backward(torch.ones_like(out))
+            out = sharded(ids, ln)                                                     # step 2's gradients: both ranks' occurrences
+            occ = torch.tensor([1.0, 4.0, 2.0, 4.0])[:, None]
+            assert torch.allclose(out, init - LR * occ), "step 3"
+            out.backward(torch.zeros_like(out))
+        q.put((rank, "ok"))
+    except Exception as e:      # noqa: BLE001
+        import traceback
+        q.put((rank, f"{type(e).__name__}: {e}\n{traceback.format_exc()}"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_planner_sharder_flow_with_admission_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_planner, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for r, msg in res:
+        assert msg == "ok", f"rank {r}: {msg}"
