@@ -66,7 +66,7 @@ def test_strategy_validation_and_non_admitted_initializer():
     assert bool((buf[[1, 3]] == 0.5).all()) and bool((buf[[0, 2]] == 1).all())
 
 
-def _module(btm_kwargs, threshold, T=1, pooling=None, score_strategy=None, cap=2048, counter_cap=4096, dim=8, caching=False, local_hbm=0):
+def _module(btm_kwargs, threshold, T=1, pooling=None, score_strategy=None, cap=2048, counter_cap=4096, dim=32, caching=False, local_hbm=0):
     from dynamicemb import (BatchedDynamicEmbeddingTablesV2, DynamicEmbInitializerArgs, DynamicEmbInitializerMode, DynamicEmbPoolingMode,
                             DynamicEmbScoreStrategy, DynamicEmbTableOptions, EmbOptimType, FrequencyAdmissionStrategy, KVCounter)
     strat = FrequencyAdmissionStrategy(threshold=threshold) if threshold is not None else None
@@ -95,7 +95,7 @@ def scenario_sequence(dev):
     """Keys enter the table exactly when their presentation count reaches the threshold; until then their ids read the initializer's
     row (DEBUG: key % 100000) without being stored, and their gradients are dropped; admitted rows train as usual."""
     rng = np.random.default_rng(0)
-    thr, D = 3, 8
+    thr, D = 3, 32          # 32 / 64 / 128 are the embedding widths the GPU suite validates
     if True:
         m = _module({"device": dev}, thr, dim=D)
         m.train()
@@ -136,7 +136,7 @@ def scenario_pooled_two_tables(dev, mean):
     """Pooled output with non-admitted ids = pooling of (stored row | initializer row) per id, two tables with separate counters."""
     from dynamicemb import DynamicEmbPoolingMode
     rng = np.random.default_rng(1)
-    thr, D, B, T = 2, 8, 6, 2
+    thr, D, B, T = 2, 32, 6, 2
     if True:
         m = _module({"device": dev}, thr, T=T, pooling=DynamicEmbPoolingMode.MEAN if mean else DynamicEmbPoolingMode.SUM, dim=D)
         m.train()
@@ -202,7 +202,7 @@ def test_admission_needs_counter_and_excludes_graph_step():
         m = _module({}, 2)
         m.train()
         with pytest.raises(AssertionError):
-            m.make_graphed_step(torch.zeros(4, dtype=torch.int64), torch.arange(5), torch.zeros(4, 8))
+            m.make_graphed_step(torch.zeros(4, dtype=torch.int64), torch.arange(5), torch.zeros(4, 32))
 
 
 def scenario_lfu(dev):
@@ -306,7 +306,7 @@ def test_incremental_dump_cpu_shim():
         # STEP score of a row = the step of its last access (1, 2, 3)
         tensors, nxt = m.incremental_dump({"t0": 2})
         keys, vals = tensors["t0"]
-        assert sorted(keys.tolist()) == [3, 4, 5] and vals.shape == (3, 8) and keys.device.type == "cpu"
+        assert sorted(keys.tolist()) == [3, 4, 5] and vals.shape == (3, 32) and keys.device.type == "cpu"
         assert all(float(v[0]) == float(k) for k, v in zip(keys.tolist(), vals))
         assert nxt == {"t0": m.get_score()["t0"]}
         assert sorted(m.incremental_dump({"t0": 0})[0]["t0"][0].tolist()) == [1, 2, 3, 4, 5]

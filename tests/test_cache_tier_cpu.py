@@ -9,11 +9,11 @@ import torch
 from tests.cpu_ext_shim import patched_module
 from tests.test_admission_cpu import _module, _snapshot
 
-D, LR = 8, 0.5
+D, LR = 32, 0.5          # 32 / 64 / 128 are the embedding widths the GPU suite validates
 
 
 def _cached_module(dev, threshold=None, T=1, pooling=None, score_strategy=None, cap=8192):
-    # value row = 8 fp32 (SGD): HBM budget of 1024 rows per table => cache of 1024 slots (one 1024-slot bucket) per table
+    # value row = 32 fp32 (SGD): HBM budget of 1024 rows per table => cache of 1024 slots (one 1024-slot bucket) per table
     return _module({"device": dev}, threshold, T=T, pooling=pooling, score_strategy=score_strategy, cap=cap, dim=D, caching=True,
                    local_hbm=1024 * D * 4)
 
@@ -153,11 +153,11 @@ def test_cache_configuration_rules_cpu_shim():
         with pytest.raises(ValueError):
             _module({}, None, cap=8192, caching=True, local_hbm=0)
         with pytest.raises(NotImplementedError):
-            _module({}, None, cap=8192, caching=True, local_hbm=1024 * 32, score_strategy=(S.TIMESTAMP, S.LFU))
+            _module({}, None, cap=8192, caching=True, local_hbm=1024 * D * 4, score_strategy=(S.TIMESTAMP, S.LFU))
         m = _cached_module(CPU)
         m.train()
         with pytest.raises(AssertionError):
-            m.make_graphed_step(torch.zeros(4, dtype=torch.int64), torch.arange(5), torch.zeros(4, 8))
+            m.make_graphed_step(torch.zeros(4, dtype=torch.int64), torch.arange(5), torch.zeros(4, D))
 
 
 def test_cache_checkpoint_round_trip_cpu_shim(tmp_path):

@@ -30,7 +30,7 @@ def _worker(rank, world, port, q):
             keys, vals = tensors["t0"]
             want = [11, 12] + [21, 22, 23]
             assert sorted(keys[:2].tolist()) == want[:2] and sorted(keys[2:].tolist()) == want[2:], keys.tolist()
-            assert vals.shape == (5, 8) and all(float(v[0]) == float(k) for k, v in zip(keys.tolist(), vals))
+            assert vals.shape == (5, 32) and all(float(v[0]) == float(k) for k, v in zip(keys.tolist(), vals))
             assert nxt == {"t0": 3}
             # an empty rank still takes part in the gather
             tensors, _ = m.incremental_dump({"t0": 3 if rank == 0 else 0}, pg=dist.group.WORLD)

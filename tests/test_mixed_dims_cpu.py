@@ -24,11 +24,12 @@ def _mixed_module(dev, dims, fmap, optimizer, mean=False, **kw):
 def scenario_mixed_dims(dev, optimizer_name, mean, tmp_path=None):
     from dynamicemb import EmbOptimType
     opt = {"sgd": EmbOptimType.SGD, "adagrad": EmbOptimType.EXACT_ADAGRAD, "adam": EmbOptimType.ADAM}[optimizer_name]
-    dims, fmap, B = [8, 16, 4], [0, 1, 1, 2], 5            # table 1 serves two features
+    dims, fmap, B = [32, 64, 128], [0, 1, 1, 2], 5       # table 1 serves two features; widths the GPU suite validates
     F = len(fmap)
     doff = np.concatenate([[0], np.cumsum([dims[t] for t in fmap])])
     m = _mixed_module(dev, dims, fmap, opt, mean)
-    assert m.total_D == int(doff[-1]) == 44 and m.max_D == 16
+    TD = int(doff[-1])
+    assert m.total_D == TD == 288 and m.max_D == 128
     m.train()
     rng = np.random.default_rng(3)
     # model per table: key -> (weight vector, optimizer state) in float64; DEBUG init = key % 100000 in every column
@@ -39,8 +40,8 @@ def scenario_mixed_dims(dev, optimizer_name, mean, tmp_path=None):
         ids = rng.integers(1, 30, size=int(lens.sum())).astype(np.int64)
         off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
         out = m(torch.from_numpy(ids).to(dev), torch.from_numpy(off).to(dev))
-        assert tuple(out.shape) == (B, 44)
-        want = np.zeros((B, 44))
+        assert tuple(out.shape) == (B, TD)
+        want = np.zeros((B, TD))
         for f, t in enumerate(fmap):
             for b in range(B):
                 s, e = off[f * B + b], off[f * B + b + 1]
@@ -48,7 +49,7 @@ def scenario_mixed_dims(dev, optimizer_name, mean, tmp_path=None):
                     w = W[t].get(k, np.full(dims[t], float(k % 100000)))
                     want[b, doff[f]:doff[f + 1]] += w / ((e - s) if mean else 1)
         assert np.allclose(out.detach().cpu().numpy(), want, rtol=1e-5, atol=1e-3), f"step {step} forward"
-        g = rng.standard_normal((B, 44)).astype(np.float32)
+        g = rng.standard_normal((B, TD)).astype(np.float32)
         out.backward(torch.from_numpy(g).to(dev))
         # per-key gradient = sum over its occurrences of the bag's gradient slice (divided by the bag length for MEAN)
         G = [dict() for _ in dims]
@@ -86,7 +87,7 @@ def scenario_mixed_dims(dev, optimizer_name, mean, tmp_path=None):
         lens = rng.integers(1, 4, size=F * B)
         ids = rng.integers(1, 30, size=int(lens.sum())).astype(np.int64)
         off = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)).to(dev)
-        g = torch.from_numpy(rng.standard_normal((B, 44)).astype(np.float32)).to(dev)
+        g = torch.from_numpy(rng.standard_normal((B, TD)).astype(np.float32)).to(dev)
         outs = []
         for mod in (m, m2):
             o = mod(torch.from_numpy(ids).to(dev), off)
@@ -112,8 +113,8 @@ def test_mixed_dims_rules_cpu_shim():
     from dynamicemb import DynamicEmbPoolingMode, EmbOptimType
     with patched_module():
         with pytest.raises(NotImplementedError):
-            _mixed_module(CPU, [8, 16], [0, 1], EmbOptimType.EXACT_ROWWISE_ADAGRAD)
+            _mixed_module(CPU, [32, 64], [0, 1], EmbOptimType.EXACT_ROWWISE_ADAGRAD)
         from dynamicemb import BatchedDynamicEmbeddingTablesV2, DynamicEmbTableOptions
         with pytest.raises(NotImplementedError):
-            BatchedDynamicEmbeddingTablesV2([DynamicEmbTableOptions(dim=8, max_capacity=256), DynamicEmbTableOptions(dim=16, max_capacity=256)],
+            BatchedDynamicEmbeddingTablesV2([DynamicEmbTableOptions(dim=32, max_capacity=256), DynamicEmbTableOptions(dim=64, max_capacity=256)],
                                             pooling_mode=DynamicEmbPoolingMode.NONE, device=CPU)
