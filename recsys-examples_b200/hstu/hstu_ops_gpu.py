@@ -72,11 +72,11 @@ def hstu_varlen_fwd_100(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_s
     return out, None
 
 
-def hstu_varlen_bwd_100(dout, q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, dq, dk, dv, num_contexts, num_targets,
-                        target_group_size, window_size_left, window_size_right, alpha, rab_padded=None, has_drab=False, func=None,
+def hstu_varlen_bwd_100(do, q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, dq, dk, dv, num_contexts, num_targets,
+                        target_group_size, window_size_left, window_size_right, alpha, rab=None, has_drab=False, func=None,
                         deterministic=False, scaling_seqlen: int = -1):
-    assert rab_padded is None and not has_drab and func is None
-    q, k, v, dout = _prep(q), _prep(k), _prep(v), _prep(dout)
+    assert rab is None and not has_drab and func is None
+    q, k, v, dout = _prep(q), _prep(k), _prep(v), _prep(do)          # parameter names are the reference's (hstu_blackwell/hstu_ops_gpu.py:257)
     T, H, D = q.shape
     dq = torch.empty(T, H, D, dtype=q.dtype, device=q.device) if dq is None else dq
     dk = torch.empty(T, H, D, dtype=q.dtype, device=q.device) if dk is None else dk

@@ -15,6 +15,7 @@ TARGETS = {
     "examples/hstu/ops/triton_ops/triton_norm_mul_dropout.py": ["triton_layer_norm_mul_dropout_fwd", "triton_layer_norm_mul_dropout_bwd"],
     "examples/hstu/ops/triton_ops/triton_silu.py": ["triton_silu_fwd", "triton_silu_bwd"],
     "third_party/FBGEMM/fbgemm_gpu/experimental/hstu/hstu/cuda_hstu_attention.py": ["hstu_attn_varlen_func"],
+    "third_party/FBGEMM/fbgemm_gpu/experimental/hstu/src/hstu_blackwell/hstu_ops_gpu.py": ["hstu_varlen_fwd_100", "hstu_varlen_bwd_100"],
     "corelib/dynamicemb/dynamicemb/batched_dynamicemb_tables.py": [
         "BatchedDynamicEmbeddingTablesV2.__init__", "BatchedDynamicEmbeddingTablesV2.forward", "BatchedDynamicEmbeddingTablesV2.prefetch",
         "BatchedDynamicEmbeddingTablesV2.dump", "BatchedDynamicEmbeddingTablesV2.load", "BatchedDynamicEmbeddingTablesV2.export_keys_values",

@@ -15,12 +15,13 @@ def _ours():
     from dynamicemb import FrequencyAdmissionStrategy as FA, KVCounter, LinearBucketTable as LT, MultiTableKVCounter as MC, get_scored_table
     from dynamicemb import checkpoint as ck
     from hstu import fused_hstu_op as fo
-    from hstu import hstu_attn_varlen_func, layer_ops as L
+    from hstu import hstu_attn_varlen_func, hstu_ops_gpu as HO, layer_ops as L
     return {
         "fused_hstu_op": fo.fused_hstu_op, "FusedHSTULayerFunction.forward": fo.FusedHSTULayerFunction.forward,
         "triton_weighted_layer_norm_fwd": L.triton_weighted_layer_norm_fwd, "triton_weighted_layer_norm_bwd": L.triton_weighted_layer_norm_bwd,
         "triton_layer_norm_mul_dropout_fwd": L.triton_layer_norm_mul_dropout_fwd, "triton_layer_norm_mul_dropout_bwd": L.triton_layer_norm_mul_dropout_bwd,
         "triton_silu_fwd": L.triton_silu_fwd, "triton_silu_bwd": L.triton_silu_bwd, "hstu_attn_varlen_func": hstu_attn_varlen_func,
+        "hstu_varlen_fwd_100": HO.hstu_varlen_fwd_100, "hstu_varlen_bwd_100": HO.hstu_varlen_bwd_100,
         "BatchedDynamicEmbeddingTablesV2.__init__": M.__init__, "BatchedDynamicEmbeddingTablesV2.forward": M.forward,
         "BatchedDynamicEmbeddingTablesV2.prefetch": M.prefetch, "BatchedDynamicEmbeddingTablesV2.dump": M.dump, "BatchedDynamicEmbeddingTablesV2.load": M.load,
         "BatchedDynamicEmbeddingTablesV2.export_keys_values": M.export_keys_values, "BatchedDynamicEmbeddingTablesV2.set_score": M.set_score,
