@@ -154,6 +154,9 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         opt0 = table_options[0]
         for o in table_options:
             assert o.get_grouped_key() == opt0.get_grouped_key(), "All tables must match in grouped keys."
+            # one key map and one value tensor per module: these two also have to agree (the reference keeps a table object per dim)
+            assert o.bucket_capacity == opt0.bucket_capacity and o.embedding_dtype == opt0.embedding_dtype, \
+                "tables of one module share bucket_capacity and embedding_dtype"
             if o.external_storage is not None:
                 raise NotImplementedError("external parameter-server storage is out of scope; see DESIGN.md")
             if o.embedding_dtype != torch.float32:

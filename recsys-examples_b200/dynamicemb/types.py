@@ -116,17 +116,56 @@ class DynamicEmbTableOptions:
     admission_counter: Any = None
 
     def __post_init__(self):
+        # reference :480-492: the eval initializer is a constant, dist_type is one of the three routings, score_strategy is canonical
+        assert self.eval_initializer_args.mode == DynamicEmbInitializerMode.CONSTANT, "eval_initializer_args must be constant initialization"
         if self.index_type is None:
             self.index_type = DEFAULT_INDEX_TYPE
         if self.embedding_dtype is None:
             self.embedding_dtype = torch.float32
         if self.dist_type not in SUPPORTED_DIST_TYPES:
-            raise ValueError(f"dist_type must be one of {SUPPORTED_DIST_TYPES}, got {self.dist_type}")
-        if isinstance(self.score_strategy, tuple) and len(self.score_strategy) == 1:
-            self.score_strategy = self.score_strategy[0]
+            raise ValueError(f"Unsupported dist_type {self.dist_type!r}. Supported values: {SUPPORTED_DIST_TYPES}.")
+        self.score_strategy = normalize_score_strategy(self.score_strategy)
 
+    # tables are grouped into one module by these fields only (reference :494-520); options compare / hash by them
     def get_grouped_key(self):
-        return (self.embedding_dtype, self.training, self.caching, self.score_strategy, self.bucket_capacity, self.index_type)
+        return {"training": self.training, "caching": self.caching, "external_storage": self.external_storage, "index_type": self.index_type,
+                "dist_type": self.dist_type, "score_strategy": self.score_strategy, "admit_strategy": self.admit_strategy}
+
+    def __eq__(self, other):
+        if not isinstance(other, DynamicEmbTableOptions):
+            return NotImplemented
+        return self.get_grouped_key() == other.get_grouped_key()
+
+    def __ne__(self, other):
+        if not isinstance(other, DynamicEmbTableOptions):
+            return NotImplemented
+        return not (self == other)
+
+    def __hash__(self):
+        return hash(tuple(self.get_grouped_key().items()))
+
+
+SUPPORTED_COMPOUND_SCORE_STRATEGIES = (frozenset({DynamicEmbScoreStrategy.TIMESTAMP, DynamicEmbScoreStrategy.LFU}),)
+
+
+def normalize_score_strategy(score_strategy):
+    """dynamicemb_config.py:166-212: None passes through; `(X,)` -> X; a longer tuple must be a supported compound set without duplicates."""
+    if score_strategy is None:
+        return None
+    if isinstance(score_strategy, tuple):
+        for element in score_strategy:
+            if not isinstance(element, DynamicEmbScoreStrategy):
+                raise TypeError(f"score_strategy tuple elements must be DynamicEmbScoreStrategy, got {type(element)}.")
+        if len(score_strategy) == 0:
+            raise NotImplementedError("score_strategy tuple must be non-empty.")
+        if len(score_strategy) == 1:
+            return score_strategy[0]
+        if len(score_strategy) != len(frozenset(score_strategy)) or frozenset(score_strategy) not in SUPPORTED_COMPOUND_SCORE_STRATEGIES:
+            raise NotImplementedError(f"Unsupported compound score_strategy {score_strategy}.")
+        return score_strategy
+    if not isinstance(score_strategy, DynamicEmbScoreStrategy):
+        raise TypeError(f"score_strategy must be a DynamicEmbScoreStrategy or a tuple of them, got {type(score_strategy)}.")
+    return score_strategy
 
 
 def align_to_table_size(n: int, alignment: int) -> int:

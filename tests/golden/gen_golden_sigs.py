@@ -75,3 +75,36 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# dataclass fields (name, literal default) and enum members (name, literal value) of the configuration objects a caller constructs
+CLASSES = {
+    "corelib/dynamicemb/dynamicemb/dynamicemb_config.py": ["DynamicEmbTableOptions", "DynamicEmbInitializerArgs", "DynamicEmbInitializerMode",
+                                                           "DynamicEmbCheckMode", "DynamicEmbPoolingMode", "DynamicEmbScoreStrategy",
+                                                           "DynamicEmbEvictStrategy"],
+    "corelib/dynamicemb/dynamicemb/types.py": ["DynamicEmbInitializerArgs", "DynamicEmbInitializerMode", "MemoryType"],
+    "corelib/dynamicemb/dynamicemb/scored_hashtable.py": ["ScoreSpec", "ScoreArg", "ProbingType", "ReductionType"],
+}
+OUT_CLASSES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "api_classes.json")
+
+
+def main_classes():
+    rec = {}
+    for rel, names in CLASSES.items():
+        tree = ast.parse(open(os.path.join(REF, rel)).read())
+        for node in tree.body:
+            if isinstance(node, ast.ClassDef) and node.name in names and node.name not in rec:
+                fields = []
+                for sub in node.body:
+                    if isinstance(sub, ast.AnnAssign) and isinstance(sub.target, ast.Name):
+                        fields.append({"name": sub.target.id, "default": literal(sub.value) if sub.value is not None else None})
+                    elif isinstance(sub, ast.Assign) and len(sub.targets) == 1 and isinstance(sub.targets[0], ast.Name):
+                        fields.append({"name": sub.targets[0].id, "default": literal(sub.value)})
+                rec[node.name] = {"file": rel, "line": node.lineno, "bases": [ast.unparse(b) for b in node.bases], "fields": fields}
+    json.dump(rec, open(OUT_CLASSES, "w"), indent=1)
+    print(OUT_CLASSES, sorted(rec))
+
+
+if __name__ == "__main__":
+    main_classes()

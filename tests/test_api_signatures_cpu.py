@@ -87,3 +87,62 @@ def test_enum_defaults_match_reference_members():
     assert gold["bounds_check_mode"]["source"] == "BoundsCheckMode.WARNING" and sig["bounds_check_mode"].default is BoundsCheckMode.WARNING
     assert gold["optimizer"]["source"] == "EmbOptimType.SGD" and sig["optimizer"].default is EmbOptimType.SGD
     assert gold["output_dtype"]["source"] == "torch.float32"
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# configuration objects: dataclass fields (order, literal defaults) and enum members (order, literal values) — tests/golden/api_classes.json
+GC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "api_classes.json")
+
+
+def _our_class(name):
+    import dynamicemb
+    from dynamicemb import scored_hashtable, types
+    for mod in (dynamicemb, types, scored_hashtable):
+        if hasattr(mod, name):
+            return getattr(mod, name)
+    raise AssertionError(f"{name} is not offered by this package")
+
+
+@pytest.mark.parametrize("name", sorted(json.load(open(GC))))
+def test_config_classes_match_reference(name):
+    import dataclasses
+    import enum
+    gold = json.load(open(GC))[name]
+    cls = _our_class(name)
+    if any("Enum" in b for b in gold["bases"]):
+        assert issubclass(cls, enum.Enum) and (issubclass(cls, enum.IntEnum) == any("IntEnum" in b for b in gold["bases"]))
+        assert [m.name for m in cls] == [f["name"] for f in gold["fields"]], f"{name} members ({gold['file']}:{gold['line']})"
+        for m, f in zip(cls, gold["fields"]):
+            if "value" in f["default"]:
+                assert m.value == f["default"]["value"], f"{name}.{m.name}"
+        return
+    assert dataclasses.is_dataclass(cls), name
+    ours = dataclasses.fields(cls)
+    assert [f.name for f in ours] == [f["name"] for f in gold["fields"]], f"{name} fields ({gold['file']}:{gold['line']})"
+    for mine, f in zip(ours, gold["fields"]):
+        d = f["default"]
+        if d is None:
+            assert mine.default is dataclasses.MISSING and mine.default_factory is dataclasses.MISSING, f"{name}.{mine.name} is required in the reference"
+        elif "value" in d:
+            assert mine.default == d["value"] and type(mine.default) is type(d["value"]), f"{name}.{mine.name}: {mine.default!r} vs {d['value']!r}"
+        else:
+            assert mine.default is not dataclasses.MISSING or mine.default_factory is not dataclasses.MISSING, f"{name}.{mine.name} has a default in the reference"
+
+
+def test_table_options_group_and_validate_like_the_reference():
+    """dynamicemb_config.py:480-520: grouped key = 7 fields, options compare / hash by it; eval initializer must be constant; one-element
+    score tuples unwrap, unsupported compounds raise."""
+    from dynamicemb import DynamicEmbInitializerArgs, DynamicEmbInitializerMode, DynamicEmbScoreStrategy as S, DynamicEmbTableOptions as O
+    a, b = O(dim=8, max_capacity=10, bucket_capacity=64), O(dim=128, max_capacity=99)
+    assert list(a.get_grouped_key()) == ["training", "caching", "external_storage", "index_type", "dist_type", "score_strategy", "admit_strategy"]
+    assert a == b and hash(a) == hash(b) and a != O(caching=True) and a != O(dist_type="continuous")
+    assert O(score_strategy=(S.LFU,)).score_strategy is S.LFU and O(score_strategy=(S.LFU, S.TIMESTAMP)).score_strategy == (S.LFU, S.TIMESTAMP)
+    for bad in ((S.LFU, S.STEP), (S.LFU, S.TIMESTAMP, S.LFU), ()):
+        with pytest.raises(NotImplementedError):
+            O(score_strategy=bad)
+    with pytest.raises(TypeError):
+        O(score_strategy=3)
+    with pytest.raises(ValueError):
+        O(dist_type="modulo")
+    with pytest.raises(AssertionError):
+        O(eval_initializer_args=DynamicEmbInitializerArgs(mode=DynamicEmbInitializerMode.UNIFORM))
