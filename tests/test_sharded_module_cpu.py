@@ -22,12 +22,29 @@ from tests.test_dist_cpu import ROOT, _free_port
 LR = 0.5
 
 
-def _worker(rank, world, port, dedup, threshold, cached, q):
+CONFIGS = [(True, None, False), (False, None, False), (True, 2, False), (True, None, True), (True, 2, True)]      # (dedup, threshold, cached)
+
+
+def _worker(rank, world, port, q):
+    """One process group, every configuration in turn (a spawn costs ~10 s of imports)."""
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "recsys-examples_b200"))
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        for dedup, threshold, cached in CONFIGS:
+            _run_config(rank, world, dedup, threshold, cached)
+        q.put((rank, "ok"))
+    except Exception as e:      # noqa: BLE001
+        import traceback
+        q.put((rank, f"{type(e).__name__}: {e}\n{traceback.format_exc()}"))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_config(rank, world, dedup, threshold, cached):
+    tag = f"dedup={dedup} threshold={threshold} cached={cached}: "
+    if True:
         from tests.cpu_ext_shim import patched_module
         from tests.test_admission_cpu import _module
         from dynamicemb.shard import RowWiseShardedDynamicEmbeddingA2A
@@ -56,7 +73,7 @@ def _worker(rank, world, port, dedup, threshold, cached, q):
             moved = torch.tensor([count[(f, k)] for f, k in zip(feat.tolist(), ids.tolist())], dtype=torch.float32)[:, None]
             # step 1: every row is at its initial value (stored or not)
             out = sharded(x, ln)
-            assert torch.equal(out, init), "step 1 output"
+            assert torch.equal(out, init), tag + "step 1 output"
             out.backward(torch.ones_like(out))
             # step 2, same batch
             out = sharded(x, ln)
@@ -64,33 +81,26 @@ def _worker(rank, world, port, dedup, threshold, cached, q):
                 want = init - LR * moved                          # step 1 trained every key with the gradients of all ranks
             else:
                 want = init                                       # threshold 2: step 1 only counted; nothing was stored or trained
-            assert torch.allclose(out, want), "step 2 output"
+            assert torch.allclose(out, want), tag + "step 2 output"
             out.backward(torch.ones_like(out))
             # step 3: with admission the keys were stored at step 2 (untrained copy of the initializer) and trained once
             out = sharded(x, ln)
             want = init - LR * moved * (2 if threshold is None else 1)
-            assert torch.allclose(out, want), "step 3 output"
+            assert torch.allclose(out, want), tag + "step 3 output"
             out.backward(torch.zeros_like(out))
             # ownership: roundrobin => this rank's table holds exactly the keys with key % world == rank
             for t in range(T):
                 keys, _ = local.export_keys_values(t)
                 allk = {k for (f, k) in count if f == t}
-                assert set(keys.tolist()) == {k for k in allk if k % world == rank}, f"table {t} ownership"
-        q.put((rank, "ok"))
-    except Exception as e:      # noqa: BLE001
-        import traceback
-        q.put((rank, f"{type(e).__name__}: {e}\n{traceback.format_exc()}"))
-    finally:
-        dist.destroy_process_group()
+                assert set(keys.tolist()) == {k for k in allk if k % world == rank}, tag + f"table {t} ownership"
 
 
-@pytest.mark.parametrize("dedup,threshold,cached", [(True, None, False), (False, None, False), (True, 2, False), (True, None, True), (True, 2, True)])
-def test_sharded_module_matches_closed_form_gloo(dedup, threshold, cached):
+def test_sharded_module_matches_closed_form_gloo():
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, dedup, threshold, cached, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in procs]
