@@ -14,6 +14,8 @@ from .dynamicemb_extensions import EvictStrategy
 DEFAULT_INDEX_TYPE = torch.int64
 DEFAULT_BUCKET_CAPACITY = 128
 BUCKET_ALIGNMENT = 16
+DEMB_TABLE_ALIGN_SIZE = 16
+MAX_BUCKET_CAPACITY: int = 2 ** 63 - 1        # sentinel bucket_capacity: the whole per-rank shard is one bucket (types.py:118-120)
 DEBUG_EMB_INITIALIZER_MOD = 100_000
 BATCH_SIZE_PER_DUMP = 65536
 SUPPORTED_DIST_TYPES = ("continuous", "roundrobin", "hash_roundrobin")
@@ -172,14 +174,100 @@ def align_to_table_size(n: int, alignment: int) -> int:
     return ((int(n) + alignment - 1) // alignment) * alignment
 
 
-def get_sharded_table_capacity(num_embeddings: int, world_size: int, bucket_capacity: int = DEFAULT_BUCKET_CAPACITY) -> int:
-    """dynamicemb_config.py:696-765: shard_rows = ceil(N/W); capacity = round_up(shard_rows, bucket_capacity)."""
+def _sharded_table_bucket_layout(embedding_config, world_size: int, bucket_capacity: int) -> Tuple[int, int]:
+    """(num_buckets, effective bucket width) of one rank's shard (dynamicemb_config.py:696-731).  `embedding_config` is the reference's
+    argument — a TorchRec table config, of which only `.num_embeddings` is read — or the row count itself."""
     if world_size <= 0:
         raise ValueError(f"world_size must be positive, got {world_size}")
-    if bucket_capacity <= 0 or bucket_capacity % BUCKET_ALIGNMENT != 0:
-        raise ValueError(f"bucket_capacity ({bucket_capacity}) must be a positive multiple of {BUCKET_ALIGNMENT}")
-    shard_rows = math.ceil(int(num_embeddings) / world_size)
-    return align_to_table_size(shard_rows, bucket_capacity)
+    num_global = int(getattr(embedding_config, "num_embeddings", embedding_config))
+    shard_rows = math.ceil(num_global / world_size)
+    if bucket_capacity == MAX_BUCKET_CAPACITY:               # sentinel: the whole shard is one bucket
+        return 1, align_to_table_size(shard_rows, BUCKET_ALIGNMENT)
+    if bucket_capacity <= 0:
+        raise ValueError(f"bucket_capacity must be positive when not MAX_BUCKET_CAPACITY, got {bucket_capacity}")
+    if bucket_capacity % BUCKET_ALIGNMENT != 0:
+        raise ValueError(f"bucket_capacity ({bucket_capacity}) must be a multiple of BUCKET_ALIGNMENT ({BUCKET_ALIGNMENT}) when not using "
+                         "MAX_BUCKET_CAPACITY.")
+    return align_to_table_size(shard_rows, bucket_capacity) // bucket_capacity, bucket_capacity
+
+
+def get_sharded_table_capacity(embedding_config, world_size: int, bucket_capacity: int = DEFAULT_BUCKET_CAPACITY) -> int:
+    """dynamicemb_config.py:733-765: shard_rows = ceil(N/W); capacity = round_up(shard_rows, bucket_capacity) — what the planner writes to
+    `DynamicEmbTableOptions.max_capacity`."""
+    num_buckets, width = _sharded_table_bucket_layout(embedding_config, world_size, bucket_capacity)
+    return int(num_buckets * width)
+
+
+def dtype_to_bytes(dtype: torch.dtype) -> int:
+    return torch.empty((), dtype=dtype).element_size()
+
+
+def get_table_value_bytes(embedding_config, optimizer_type: EmbOptimType, world_size: int, bucket_capacity: int = DEFAULT_BUCKET_CAPACITY) -> int:
+    """Bytes of value storage (embedding + optimizer state) of one table over all ranks (dynamicemb_config.py:768-803)."""
+    from .optimizer import get_optimizer_state_dim
+    total_rows = get_sharded_table_capacity(embedding_config, world_size, bucket_capacity) * world_size
+    dim = embedding_config.embedding_dim
+    dtype = data_type_to_dtype(embedding_config.data_type) if hasattr(embedding_config, "data_type") else torch.float32
+    return int(dtype_to_bytes(dtype) * (dim + get_optimizer_state_dim(optimizer_type, dim, dtype)) * total_rows)
+
+
+class DynamicEmbDataType(enum.IntEnum):
+    """src/utils.h:31-40 (pybind enum of the reference)."""
+    Float32 = 0
+    Float16 = 1
+    BFloat16 = 2
+    Int64 = 3
+    UInt64 = 4
+    Int32 = 5
+    UInt32 = 6
+    Size_t = 7
+
+
+_TORCH_OF_DYN = {DynamicEmbDataType.Float32: torch.float32, DynamicEmbDataType.BFloat16: torch.bfloat16, DynamicEmbDataType.Float16: torch.float16,
+                 DynamicEmbDataType.Int64: torch.int64, DynamicEmbDataType.UInt64: torch.uint64, DynamicEmbDataType.Int32: torch.int32,
+                 DynamicEmbDataType.UInt32: torch.uint32, DynamicEmbDataType.Size_t: torch.int64}
+# torchrec.types.DataType member NAME -> (torch dtype, DynamicEmbDataType); matched by name so torchrec is not needed at import time
+_OF_TORCHREC = {"FP32": (torch.float32, DynamicEmbDataType.Float32), "FP16": (torch.float16, DynamicEmbDataType.Float16),
+                "BF16": (torch.bfloat16, DynamicEmbDataType.BFloat16), "INT64": (torch.int64, DynamicEmbDataType.Int64),
+                "INT32": (torch.int32, DynamicEmbDataType.Int32), "INT8": (torch.int8, None), "UINT8": (torch.uint8, None)}
+
+
+def dyn_emb_to_torch(data_type: DynamicEmbDataType) -> torch.dtype:
+    """dynamicemb_config.py:562-580"""
+    if data_type not in _TORCH_OF_DYN:
+        raise ValueError(f"Unsupported DynamicEmbDataType: {data_type}")
+    return _TORCH_OF_DYN[data_type]
+
+
+def torch_to_dyn_emb(torch_dtype: torch.dtype) -> DynamicEmbDataType:
+    """utils.py:41-57"""
+    for k, v in _TORCH_OF_DYN.items():
+        if v == torch_dtype and k != DynamicEmbDataType.Size_t:
+            return k
+    raise ValueError(f"Unsupported torch dtype: {torch_dtype}")
+
+
+def data_type_to_dtype(data_type) -> torch.dtype:
+    """TorchRec DataType -> torch dtype (dynamicemb_config.py:543-559)."""
+    name = getattr(data_type, "name", str(data_type)).upper()
+    if name not in _OF_TORCHREC:
+        raise ValueError(f"DataType {data_type} cannot be converted to torch.dtype")
+    return _OF_TORCHREC[name][0]
+
+
+def data_type_to_dyn_emb(data_type) -> DynamicEmbDataType:
+    """TorchRec DataType -> DynamicEmbDataType (dynamicemb_config.py:522-540)."""
+    name = getattr(data_type, "name", str(data_type)).upper()
+    if name not in _OF_TORCHREC or _OF_TORCHREC[name][1] is None:
+        raise ValueError(f"DataType {data_type} cannot be converted to DynamicEmbDataType")
+    return _OF_TORCHREC[name][1]
+
+
+def string_to_evict_strategy(strategy_str: str) -> EvictStrategy:
+    """dynamicemb_config.py:604-616"""
+    if strategy_str not in ("KLru", "KLfu", "KEpochLru", "KEpochLfu", "KCustomized"):
+        raise ValueError(f"Invalid EvictStrategy string: {strategy_str}")
+    return EvictStrategy[strategy_str]
 
 
 class MemoryType(enum.Enum):

@@ -24,6 +24,10 @@ TARGETS = {
         "BatchedDynamicEmbeddingTablesV2.split_embedding_weights", "BatchedDynamicEmbeddingTablesV2.reset_cache_states",
         "BatchedDynamicEmbeddingTablesV2.set_record_cache_metrics", "BatchedDynamicEmbeddingTablesV2.flush", "BatchedDynamicEmbeddingTablesV2.get_score",
         "encode_meta_json_file_path", "encode_checkpoint_file_path", "encode_counter_checkpoint_file_path", "find_files", "get_loading_files"],
+    "corelib/dynamicemb/dynamicemb/dump_load.py": ["find_sharded_modules", "get_dynamic_emb_module", "DynamicEmbDump", "DynamicEmbLoad"],
+    "corelib/dynamicemb/dynamicemb/incremental_dump.py": ["set_score", "get_score", "incremental_dump", "is_valid_score_threshold"],
+    "corelib/dynamicemb/dynamicemb/dynamicemb_config.py": ["get_sharded_table_capacity", "get_table_value_bytes", "string_to_evict_strategy",
+                                                           "dyn_emb_to_torch", "data_type_to_dtype", "data_type_to_dyn_emb"],
     "corelib/dynamicemb/dynamicemb/embedding_admission.py": [
         "KVCounter.__init__", "MultiTableKVCounter.__init__", "MultiTableKVCounter.add", "MultiTableKVCounter.erase",
         "MultiTableKVCounter.memory_usage", "MultiTableKVCounter.load", "MultiTableKVCounter.dump",
@@ -108,3 +112,22 @@ def main_classes():
 
 if __name__ == "__main__":
     main_classes()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# names the reference package exports (`dynamicemb.__all__`) and the model-level checkpoint / score functions
+OUT_EXPORTS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "api_exports.json")
+
+
+def main_exports():
+    tree = ast.parse(open(os.path.join(REF, "corelib/dynamicemb/dynamicemb/__init__.py")).read())
+    names = []
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Assign) and isinstance(node.targets[0], ast.Name) and node.targets[0].id == "__all__":
+            names = ast.literal_eval(node.value)
+    json.dump({"dynamicemb.__all__": sorted(names)}, open(OUT_EXPORTS, "w"), indent=1)
+    print(OUT_EXPORTS, len(names), "names")
+
+
+if __name__ == "__main__":
+    main_exports()

@@ -13,7 +13,7 @@ G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "api_sign
 def _ours():
     from dynamicemb import BatchedDynamicEmbeddingTablesV2 as M
     from dynamicemb import FrequencyAdmissionStrategy as FA, KVCounter, LinearBucketTable as LT, MultiTableKVCounter as MC, get_scored_table
-    from dynamicemb import checkpoint as ck
+    from dynamicemb import checkpoint as ck, dump_load as dl, types as ty
     from hstu import fused_hstu_op as fo
     from hstu import hstu_attn_varlen_func, hstu_ops_gpu as HO, layer_ops as L
     return {
@@ -38,6 +38,11 @@ def _ours():
         "LinearBucketTable.__init__": LT.__init__, "LinearBucketTable.lookup": LT.lookup, "LinearBucketTable.insert": LT.insert,
         "LinearBucketTable.insert_and_evict": LT.insert_and_evict, "LinearBucketTable.erase": LT.erase, "LinearBucketTable.load": LT.load,
         "LinearBucketTable.dump": LT.dump, "get_scored_table": get_scored_table,
+        "find_sharded_modules": dl.find_sharded_modules, "get_dynamic_emb_module": dl.get_dynamic_emb_module, "DynamicEmbDump": dl.DynamicEmbDump,
+        "DynamicEmbLoad": dl.DynamicEmbLoad, "set_score": dl.set_score, "get_score": dl.get_score, "incremental_dump": dl.incremental_dump,
+        "is_valid_score_threshold": dl.is_valid_score_threshold, "get_sharded_table_capacity": ty.get_sharded_table_capacity,
+        "get_table_value_bytes": ty.get_table_value_bytes, "string_to_evict_strategy": ty.string_to_evict_strategy,
+        "dyn_emb_to_torch": ty.dyn_emb_to_torch, "data_type_to_dtype": ty.data_type_to_dtype, "data_type_to_dyn_emb": ty.data_type_to_dyn_emb,
         "encode_meta_json_file_path": ck.encode_meta_json_file_path, "encode_checkpoint_file_path": ck.encode_checkpoint_file_path,
         "encode_counter_checkpoint_file_path": ck.encode_counter_checkpoint_file_path, "find_files": ck.find_files, "get_loading_files": ck.get_loading_files,
     }
@@ -146,3 +151,12 @@ def test_table_options_group_and_validate_like_the_reference():
         O(dist_type="modulo")
     with pytest.raises(AssertionError):
         O(eval_initializer_args=DynamicEmbInitializerArgs(mode=DynamicEmbInitializerMode.UNIFORM))
+
+
+def test_package_exports_every_name_of_the_reference():
+    """`from dynamicemb import X` works for every X of the reference's `__all__` (tests/golden/api_exports.json)."""
+    import dynamicemb
+    names = json.load(open(os.path.join(os.path.dirname(G), "api_exports.json")))["dynamicemb.__all__"]
+    assert len(names) >= 28
+    missing = [n for n in names if not hasattr(dynamicemb, n)]
+    assert not missing, missing
