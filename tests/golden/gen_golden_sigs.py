@@ -131,3 +131,32 @@ def main_exports():
 
 if __name__ == "__main__":
     main_exports()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# import sites: what the reference's USER code (examples/, corelib/dynamicemb/example, corelib/dynamicemb/benchmark) imports from dynamicemb
+OUT_IMPORTS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "api_imports.json")
+
+
+def main_imports():
+    sites = {}
+    for top in ("examples", "corelib/dynamicemb/example", "corelib/dynamicemb/benchmark"):
+        for dp, _, fs in os.walk(os.path.join(REF, top)):
+            for f in fs:
+                if not f.endswith(".py"):
+                    continue
+                try:
+                    tree = ast.parse(open(os.path.join(dp, f)).read())
+                except SyntaxError:
+                    continue
+                for node in ast.walk(tree):
+                    if isinstance(node, ast.ImportFrom) and node.module and (node.module == "dynamicemb" or node.module.startswith("dynamicemb.")
+                                                                             or node.module == "dynamicemb_extensions"):
+                        for a in node.names:
+                            sites.setdefault(node.module, set()).add(a.name)
+    json.dump({k: sorted(v) for k, v in sorted(sites.items())}, open(OUT_IMPORTS, "w"), indent=1)
+    print(OUT_IMPORTS, {k: len(v) for k, v in sites.items()})
+
+
+if __name__ == "__main__":
+    main_imports()

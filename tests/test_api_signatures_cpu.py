@@ -160,3 +160,29 @@ def test_package_exports_every_name_of_the_reference():
     assert len(names) >= 28
     missing = [n for n in names if not hasattr(dynamicemb, n)]
     assert not missing, missing
+
+
+# import sites of the reference's user code (examples/, corelib/dynamicemb/example, benchmark): tests/golden/api_imports.json
+_NOT_ON_THE_PATH = {
+    "dynamicemb.exportable_tables": "inference export (torch.export of embedding collections) — SURVEY §2 out of scope",
+    "dynamicemb.get_planner": "convenience wrapper around TorchRec's Topology / planner objects (needs torchrec)",
+    "dynamicemb.benchmark.dataset_generator": "benchmark data generator; bench.py restates its power-law stream",
+    "dynamicemb.utils": "TORCHREC_TYPES (a tuple of TorchRec classes; needs torchrec)",
+}
+
+
+def test_user_import_sites_of_the_reference_resolve():
+    """Every `from dynamicemb[...] import name` the reference's examples and benchmarks contain resolves against this package, module path
+    included, except the modules listed (with the reason) in _NOT_ON_THE_PATH."""
+    import importlib
+    sites = json.load(open(os.path.join(os.path.dirname(G), "api_imports.json")))
+    assert set(_NOT_ON_THE_PATH) <= set(sites)
+    checked = 0
+    for module, names in sites.items():
+        if module in _NOT_ON_THE_PATH:
+            continue
+        mod = importlib.import_module(module)
+        for n in names:
+            assert hasattr(mod, n), f"from {module} import {n}"
+            checked += 1
+    assert checked >= 28
