@@ -186,3 +186,13 @@ def test_user_import_sites_of_the_reference_resolve():
             assert hasattr(mod, n), f"from {module} import {n}"
             checked += 1
     assert checked >= 28
+
+
+def test_hstu_import_sites_of_the_reference_resolve():
+    """examples/hstu imports `from hstu import hstu_attn_varlen_func`, `import hstu.hstu_ops_gpu` and, in its fused layer,
+    `from hstu.hstu_blackwell import hstu_ops_gpu` (ops/fused_hstu_op.py:19-20, :50-58)."""
+    import hstu
+    import hstu.hstu_ops_gpu as ops
+    from hstu import hstu_attn_varlen_func  # noqa: F401
+    from hstu.hstu_blackwell import hstu_ops_gpu as bw
+    assert bw.hstu_varlen_fwd_100 is ops.hstu_varlen_fwd_100 and bw.hstu_varlen_bwd_100 is ops.hstu_varlen_bwd_100 and hstu.hstu_ops_gpu is ops
