@@ -210,6 +210,33 @@ class LinearBucketTable:
             if c:
                 yield keys[:c], scores[:c], idx[:c]
 
+    def incremental_dump(self, score_threshold: Dict[str, int], table_id: int, batch_size: int = 65536, pg=None, return_index: bool = False):
+        """Keys (and scores, optionally slot indices) of one logical table whose score is not below the threshold, as CPU tensors; with a
+        process group of more than one rank every rank receives all ranks' entries in rank order (scored_hashtable.py:1128-1260).
+        The scan is the export kernel, the filter a torch mask."""
+        import torch.distributed as dist
+        name, threshold = None, 0
+        for score_name, thr in score_threshold.items():
+            if score_name not in self.score_names_:
+                print(f"Score name {score_name} not existed, will not dump it.")
+            else:
+                name, threshold = score_name, int(thr)
+        ks, ss, ix = [], [], []
+        for keys, scores, idx in self.export(table_id, batch=batch_size):
+            keep = scores >= threshold
+            ks.append(keys[keep]); ss.append(scores[keep]); ix.append(idx[keep])
+        cat = lambda xs, dt: torch.cat(xs) if xs else torch.empty(0, dtype=dt, device=self.device)      # noqa: E731
+        keys, scores, idx = cat(ks, self.key_type_), cat(ss, torch.int64), cat(ix, torch.int64)
+        if pg is not None and dist.is_initialized() and dist.get_world_size(group=pg) > 1:
+            from .checkpoint import all_gather_keys_values
+            both = torch.stack([scores, idx], dim=1)
+            keys, both = all_gather_keys_values(keys, both, pg)
+            scores, idx = both[:, 0].contiguous(), both[:, 1].contiguous()
+        else:
+            keys, scores, idx = keys.cpu(), scores.cpu(), idx.cpu()
+        out_scores = {name: scores} if name is not None else {}
+        return (keys, out_scores, idx) if return_index else (keys, out_scores)
+
     # ------------------------------------------------------------------ file round trip of one logical table (admission counters)
     def dump(self, key_file: str, score_files: Dict[str, str], table_id: Optional[int] = None) -> None:
         """ScoredHashTable.dump (scored_hashtable.py:1083-1126): raw little-endian int64 keys and uint64 scores of the live slots, one

@@ -160,3 +160,44 @@ def main_imports():
 
 if __name__ == "__main__":
     main_imports()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# call sites: keyword arguments (and positional counts) the reference's user code passes to the boundary classes / functions
+OUT_CALLS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "api_call_sites.json")
+CALLEES = ["DynamicEmbTableOptions", "DynamicEmbInitializerArgs", "DynamicEmbParameterConstraints", "DynamicEmbeddingShardingPlanner",
+           "DynamicEmbeddingEnumerator", "DynamicEmbeddingCollectionSharder", "DynamicEmbeddingBagCollectionSharder", "FrequencyAdmissionStrategy",
+           "KVCounter", "BatchedDynamicEmbeddingTablesV2", "DynamicEmbDump", "DynamicEmbLoad", "dynamic_emb_save", "dynamic_emb_load",
+           "get_sharded_table_capacity", "get_table_value_bytes", "hstu_attn_varlen_func", "incremental_dump", "get_score", "set_score"]
+
+
+def main_calls():
+    sites = {}
+    for top in ("examples", "corelib/dynamicemb/example", "corelib/dynamicemb/benchmark", "corelib/dynamicemb/test"):
+        for dp, _, fs in os.walk(os.path.join(REF, top)):
+            for f in fs:
+                if not f.endswith(".py"):
+                    continue
+                try:
+                    tree = ast.parse(open(os.path.join(dp, f)).read())
+                except SyntaxError:
+                    continue
+                for node in ast.walk(tree):
+                    if not isinstance(node, ast.Call):
+                        continue
+                    fn = node.func
+                    name = fn.id if isinstance(fn, ast.Name) else fn.attr if isinstance(fn, ast.Attribute) else None
+                    if name not in CALLEES or any(isinstance(a, ast.Starred) for a in node.args):
+                        continue
+                    kws = sorted(k.arg for k in node.keywords if k.arg is not None)
+                    rec = {"file": os.path.relpath(os.path.join(dp, f), REF), "line": node.lineno, "positional": len(node.args), "keywords": kws,
+                           "star_kwargs": any(k.arg is None for k in node.keywords)}
+                    key = (rec["positional"], tuple(kws))
+                    sites.setdefault(name, {}).setdefault(str(key), rec)          # one example per distinct call shape
+    out = {k: list(v.values()) for k, v in sorted(sites.items())}
+    json.dump(out, open(OUT_CALLS, "w"), indent=1)
+    print(OUT_CALLS, {k: len(v) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main_calls()

@@ -312,6 +312,11 @@ def test_incremental_dump_cpu_shim():
         assert sorted(m.incremental_dump({"t0": 0})[0]["t0"][0].tolist()) == [1, 2, 3, 4, 5]
         with pytest.warns(UserWarning):
             assert m.incremental_dump({"nope": 1}) == ({}, {})
+        # the table-level form (ScoredHashTable.incremental_dump): keys, {score name: scores}, slot indices
+        k, sc, ix = m.tables.incremental_dump({"score": 2}, table_id=0, return_index=True)
+        assert sorted(zip(k.tolist(), sc["score"].tolist())) == [(3, 2), (4, 2), (5, 3)] and ix.numel() == 3 and k.device.type == "cpu"
+        k2, sc2 = m.tables.incremental_dump({"unknown": 0}, 0)
+        assert k2.numel() == 5 and sc2 == {}
 
 
 def test_small_public_surface_and_fill_tables_cpu_shim():

@@ -196,3 +196,46 @@ def test_hstu_import_sites_of_the_reference_resolve():
     from hstu import hstu_attn_varlen_func  # noqa: F401
     from hstu.hstu_blackwell import hstu_ops_gpu as bw
     assert bw.hstu_varlen_fwd_100 is ops.hstu_varlen_fwd_100 and bw.hstu_varlen_bwd_100 is ops.hstu_varlen_bwd_100 and hstu.hstu_ops_gpu is ops
+
+
+def _callee(name):
+    import dynamicemb
+    from dynamicemb import dump_load as dl, planner, shard
+    from hstu import hstu_attn_varlen_func
+    table = {"dynamic_emb_save": dl.DynamicEmbDump, "dynamic_emb_load": dl.DynamicEmbLoad, "hstu_attn_varlen_func": hstu_attn_varlen_func,
+             "incremental_dump": None, "get_score": None, "set_score": None}         # module-level AND method forms exist: checked separately
+    if name in table:
+        return table[name]
+    for mod in (dynamicemb, planner, shard, dl):
+        if hasattr(mod, name):
+            return getattr(mod, name)
+    raise AssertionError(name)
+
+
+def test_call_shapes_of_the_reference_bind():
+    """Every distinct (positional count, keyword set) with which the reference's examples, benchmarks and tests call a boundary class or
+    function (tests/golden/api_call_sites.json) binds against this package's signature of the same name."""
+    from dynamicemb import BatchedDynamicEmbeddingTablesV2 as M, LinearBucketTable as LT, dump_load as dl
+    sites = json.load(open(os.path.join(os.path.dirname(G), "api_call_sites.json")))
+    bound = 0
+    for name, shapes in sites.items():
+        target = _callee(name)
+        for s in shapes:
+            where = f"{name} at {s['file']}:{s['line']}"
+            # three homonyms in the reference: function(model, ...), module.method(...), table.method(...)
+            candidates = [target] if target is not None else [getattr(dl, name), getattr(M, name)] + ([getattr(LT, name)] if hasattr(LT, name) else [])
+            errors = []
+            for fn in candidates:
+                sig = inspect.signature(fn)
+                params = [p for p in sig.parameters.values() if p.name not in ("self",)]
+                sig = sig.replace(parameters=params)
+                try:
+                    binder = sig.bind_partial if s["star_kwargs"] else sig.bind
+                    binder(*([None] * s["positional"]), **{k: None for k in s["keywords"]})
+                    break
+                except TypeError as e:
+                    errors.append(str(e))
+            else:
+                raise AssertionError(f"{where}: {errors}")
+            bound += 1
+    assert bound >= 60
