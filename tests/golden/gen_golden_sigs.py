@@ -168,7 +168,8 @@ OUT_CALLS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "api_call_s
 CALLEES = ["DynamicEmbTableOptions", "DynamicEmbInitializerArgs", "DynamicEmbParameterConstraints", "DynamicEmbeddingShardingPlanner",
            "DynamicEmbeddingEnumerator", "DynamicEmbeddingCollectionSharder", "DynamicEmbeddingBagCollectionSharder", "FrequencyAdmissionStrategy",
            "KVCounter", "BatchedDynamicEmbeddingTablesV2", "DynamicEmbDump", "DynamicEmbLoad", "dynamic_emb_save", "dynamic_emb_load",
-           "get_sharded_table_capacity", "get_table_value_bytes", "hstu_attn_varlen_func", "incremental_dump", "get_score", "set_score"]
+           "get_sharded_table_capacity", "get_table_value_bytes", "hstu_attn_varlen_func", "incremental_dump", "get_score", "set_score",
+           "fused_hstu_op", "hstu_varlen_fwd_100", "hstu_varlen_bwd_100"]
 
 
 def main_calls():

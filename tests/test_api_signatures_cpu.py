@@ -201,8 +201,10 @@ def test_hstu_import_sites_of_the_reference_resolve():
 def _callee(name):
     import dynamicemb
     from dynamicemb import dump_load as dl, planner, shard
-    from hstu import hstu_attn_varlen_func
-    table = {"dynamic_emb_save": dl.DynamicEmbDump, "dynamic_emb_load": dl.DynamicEmbLoad, "hstu_attn_varlen_func": hstu_attn_varlen_func,
+    from hstu import hstu_attn_varlen_func, hstu_ops_gpu
+    from hstu.fused_hstu_op import fused_hstu_op
+    table = {"fused_hstu_op": fused_hstu_op, "hstu_varlen_fwd_100": hstu_ops_gpu.hstu_varlen_fwd_100, "hstu_varlen_bwd_100": hstu_ops_gpu.hstu_varlen_bwd_100,
+             "dynamic_emb_save": dl.DynamicEmbDump, "dynamic_emb_load": dl.DynamicEmbLoad, "hstu_attn_varlen_func": hstu_attn_varlen_func,
              "incremental_dump": None, "get_score": None, "set_score": None}         # module-level AND method forms exist: checked separately
     if name in table:
         return table[name]
