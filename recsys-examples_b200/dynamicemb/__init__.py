@@ -10,7 +10,7 @@ from .dynamicemb_extensions import EvictStrategy, InsertResult, ScorePolicy
 from .optimizer import OptimizerArgs, SparseOptimizer, get_optimizer_state_dim
 from .scored_hashtable import LinearBucketTable, ScoreArg, ScoreSpec, get_scored_table, murmur3_hash_64bits
 from .embedding_admission import FrequencyAdmissionStrategy, KVCounter, MultiTableKVCounter
-from .dump_load import DynamicEmbDump, DynamicEmbLoad, get_score, incremental_dump, set_score
+from .dump_load import DynamicEmbDump, DynamicEmbLoad      # get_score / set_score / incremental_dump: `dynamicemb.incremental_dump`, as in the reference
 from .types import (BATCH_SIZE_PER_DUMP, BUCKET_ALIGNMENT, DEMB_TABLE_ALIGN_SIZE, MAX_BUCKET_CAPACITY, DynamicEmbDataType, ScoreStrategy,
                     align_to_table_size, data_type_to_dtype, data_type_to_dyn_emb, dyn_emb_to_torch, get_table_value_bytes,
                     string_to_evict_strategy, torch_to_dyn_emb)
@@ -22,7 +22,7 @@ __all__ = [
     "DynamicEmbPoolingMode", "DynamicEmbScoreStrategy", "DynamicEmbEvictStrategy", "DynamicEmbCheckMode", "EmbOptimType",
     "BoundsCheckMode", "LinearBucketTable", "ScoreArg", "ScoreSpec", "ScorePolicy", "InsertResult", "EvictStrategy",
     "get_scored_table", "murmur3_hash_64bits", "get_sharded_table_capacity", "OptimizerArgs", "SparseOptimizer",
-    "get_optimizer_state_dim", "DynamicEmbDump", "DynamicEmbLoad", "incremental_dump", "set_score", "get_score", "BATCH_SIZE_PER_DUMP",
+    "get_optimizer_state_dim", "DynamicEmbDump", "DynamicEmbLoad", "BATCH_SIZE_PER_DUMP",
     "BUCKET_ALIGNMENT", "DEMB_TABLE_ALIGN_SIZE", "MAX_BUCKET_CAPACITY", "DynamicEmbDataType", "ScoreStrategy", "align_to_table_size",
     "data_type_to_dtype", "data_type_to_dyn_emb", "dyn_emb_to_torch", "get_table_value_bytes", "string_to_evict_strategy", "torch_to_dyn_emb",
     "AdmissionStrategy", "Counter", "FrequencyAdmissionStrategy", "KVCounter", "MultiTableKVCounter",

@@ -74,6 +74,8 @@ class PrefetchState:
     num_unique_dev: Optional[torch.Tensor] = None   # device-side count (fused path: buffers are sized by the bound)
     bwd_ws: Optional[object] = None                 # ext.PreparedBackward: pre-sorted (unique idx, gradient row) pairs (backward_prepare)
     non_admitted_positions: Optional[torch.Tensor] = None   # unique-list positions of keys the admission strategy kept out (rows = -1)
+    cold_slots: Optional[torch.Tensor] = None       # hybrid storage: slot / value row of the keys that live in the HOST tier (-1 for the
+    cold_rows: Optional[torch.Tensor] = None        # others; `slot_indices` / `rows` are -1 for them)
 
     @property
     def num_unique(self) -> int:
@@ -92,6 +94,11 @@ class _LookupFunction(torch.autograd.Function):
         out = ext.gather_forward(module._hot_values, module.max_D, state.rows, state.reverse_indices, n, offsets=offsets if pooled else None,
                                  batch_size=batch_size if pooled else 0, num_features=module.feature_num if pooled else 0,
                                  combiner=combiner, out_dtype=module.output_dtype)
+        if state.cold_rows is not None:                             # hybrid storage: the rest of the rows sit in the host tier
+            cold = ext.gather_forward(module._values, module.max_D, state.cold_rows, state.reverse_indices, n, offsets=offsets if pooled else None,
+                                      batch_size=batch_size if pooled else 0, num_features=module.feature_num if pooled else 0,
+                                      combiner=combiner, out_dtype=torch.float32, out=torch.empty(out.shape, dtype=torch.float32, device=out.device))
+            out = out + cold if out.dtype == torch.float32 else (out.to(torch.float32) + cold).to(out.dtype)
         if state.non_admitted_positions is not None and state.non_admitted_positions.numel() > 0:
             out = module._add_non_admitted(out, state, offsets, batch_size, combiner)
         if module._mixed_D:
@@ -113,6 +120,10 @@ class _LookupFunction(torch.autograd.Function):
         ext.backward(m._hot_values, m.max_D, st.reverse_indices, max(st.num_unique_bound, 1), st.rows, grads, offsets=ctx.offsets if pooled else None,
                      batch_size=ctx.batch_size if pooled else 0, num_features=m.feature_num if pooled else 0, combiner=ctx.combiner,
                      prepared=st.bwd_ws, **opt.kernel_kwargs())
+        if st.cold_rows is not None:                                # hybrid storage: the same reduce, applied to the host tier's rows
+            ext.backward(m._values, m.max_D, st.reverse_indices, max(st.num_unique_bound, 1), st.cold_rows, grads,
+                         offsets=ctx.offsets if pooled else None, batch_size=ctx.batch_size if pooled else 0,
+                         num_features=m.feature_num if pooled else 0, combiner=ctx.combiner, **opt.kernel_kwargs())
         m._unpin(st)
         return None, None, None, None, None
 
@@ -214,9 +225,13 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
                                         key_type=self.index_type, bucket_capacity=opt0.bucket_capacity, device=self._device)
         self.value_dim = self.max_D + self._optimizer.get_state_dim(self.max_D)
         self.value_dim = (self.value_dim + 3) // 4 * 4
-        self._caching, self._cache, self._cache_values = False, None, None
+        self._caching, self._hybrid, self._cache, self._cache_values = False, False, None, None
+        total_bytes = sum(o.max_capacity * 4 * self.value_dim for o in table_options)
+        local_hbm = sum(o.local_hbm_for_values for o in table_options)
         if any(o.caching for o in table_options):
             self._create_cache_storage(table_options, policy)
+        elif 0 < local_hbm < total_bytes:
+            self._create_hybrid_storage(table_options, policy, local_hbm / total_bytes)
         else:
             self._values = torch.zeros(self._table.capacity_, self.value_dim, dtype=torch.float32, device=self._device)
         self._seed = int(kwargs.get("seed", 0))
@@ -245,11 +260,11 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
     # the tier forward / backward read and write, and whose pin counters protect the rows of a prefetched batch
     @property
     def _hot_values(self) -> torch.Tensor:
-        return self._cache_values if self._caching else self._values
+        return self._cache_values if (self._caching or self._hybrid) else self._values
 
     @property
     def _hot_table(self) -> LinearBucketTable:
-        return self._cache if self._caching else self._table
+        return self._cache if (self._caching or self._hybrid) else self._table
 
     def _create_cache_storage(self, table_options, policy) -> None:
         """caching=True (batched_dynamicemb_tables.py:637-700): when the value rows do not fit `local_hbm_for_values`, an HBM cache of
@@ -274,6 +289,24 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         self._cache_values = torch.zeros(self._cache.capacity_, self.value_dim, dtype=torch.float32, device=self._device)
         self._values = ext.host_values(self._table.capacity_, self.value_dim)
         self._caching = True
+
+    def _create_hybrid_storage(self, table_options, policy, scale: float) -> None:
+        """HybridStorage (key_value_table.py:2107-2404; module :701-742): 0 < local_hbm_for_values < table bytes WITHOUT caching = two
+        disjoint tiers, an HBM table of `capacity * scale` rows per table (1024-slot buckets) and a host table of `capacity * (1 - scale)`
+        rows whose value rows sit in pinned host memory.  New keys enter the HBM tier, what it evicts moves to the host tier, a key found
+        in the host tier stays there: forward / fused backward run once per tier (rows of the other tier read zeros / are skipped)."""
+        if self._table.num_scores_ != 1:
+            raise NotImplementedError("hybrid storage with the compound (TIMESTAMP, LFU) score is not built")
+        hbm_caps = [min(o.max_capacity, max(1, int(o.max_capacity * scale))) for o in table_options]
+        host_caps = [min(o.max_capacity, max(1, int(o.max_capacity * (1.0 - scale)))) for o in table_options]
+        self._cache_policy = (ScorePolicy.GLOBAL_TIMER if table_options[0].score_strategy == DynamicEmbScoreStrategy.NO_EVICTION else policy)
+        self._cache = LinearBucketTable(hbm_caps, [ScoreSpec(name="score", policy=self._cache_policy)], key_type=self.index_type,
+                                        bucket_capacity=1024, device=self._device)
+        self._cache_values = torch.zeros(self._cache.capacity_, self.value_dim, dtype=torch.float32, device=self._device)
+        self._table = LinearBucketTable(host_caps, [ScoreSpec(name="score", policy=policy)], key_type=self.index_type,
+                                        bucket_capacity=table_options[0].bucket_capacity, device=self._device)
+        self._values = ext.host_values(self._table.capacity_, self.value_dim)
+        self._hybrid = True
 
     def _create_admission_counter(self, table_options):
         """One fused counter table for all tables (batched_dynamicemb_tables.py:798-812)."""
@@ -415,8 +448,8 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
     # no-ops without caching=True
     @property
     def cache(self):
-        """The cache tier's table (None without caching)."""
-        return self._cache
+        """The cache tier's table (None without caching; the HBM tier of a hybrid-storage module is not a cache)."""
+        return self._cache if self._caching else None
 
     def reset_cache_states(self) -> None:
         """Empty the cache WITHOUT writing it back (reference :959-962); call flush() first to keep its rows."""
@@ -504,7 +537,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         T = len(self._dynamicemb_options)
         tb = self._table
         trange = ext.get_table_range(offsets, self.feature_offsets, self.feature_num) if T > 1 else None
-        if self._fused_prefetch and self._admit_strategy is None and not self._caching:
+        if self._fused_prefetch and self._admit_strategy is None and not self._caching and not self._hybrid:
             self._prefetch_fused(indices, trange, T, frequency_counters)
             return
         want_freq = self._score_policy() in (ScorePolicy.ACCUMULATE, ScorePolicy.LRU_LFU)
@@ -514,7 +547,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         nu = int(num_u.item())                                   # host sync #1 (reference: batched_dynamicemb_function.py:141-142)
         ukeys, utids = ukeys[:nu], utids[:nu]
         freq = freq[:nu] if freq is not None else None
-        if self._caching:
+        if self._caching or self._hybrid:
             self._prefetch_cached(ukeys, utids, freq, reverse, nu)
             return
         ts = ext.device_timestamp()
@@ -561,7 +594,14 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
             mk, mt = ukeys[miss].contiguous(), utids[miss].contiguous()
             mf = freq[miss] if freq is not None else None
             s_score, s_found, s_slots = st.lookup(mk, mt, self._score_arg(mk.numel(), mt, mf), timestamp=ts)
-            ins_mask = s_found.clone()
+            # cache: rows found in the backing table are PROMOTED into the cache; hybrid: they stay in the host tier (pinned there)
+            promote = self._caching
+            ins_mask = s_found.clone() if promote else torch.zeros_like(s_found)
+            cold_slots = None
+            if not promote:
+                cold_slots = torch.full_like(slots, -1)
+                cold_slots[miss] = s_slots                       # -1 where not found
+                st.increment_counter(s_slots, mt)
             new_in_miss = ~s_found
             if bool(new_in_miss.any()):
                 if self._admit_strategy is not None:
@@ -569,10 +609,12 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
                     admit_mask, _ = admission_split(mk[new_in_miss], mt[new_in_miss], mf[new_in_miss] if mf is not None else None,
                                                     self._admit_strategy, self._admission_counter)
                     ins_mask[new_in_miss] = admit_mask
-                    if not bool(ins_mask.all()):
-                        non_admitted = miss[~ins_mask]
+                    rejected = new_in_miss.clone()
+                    rejected[new_in_miss] = ~admit_mask
+                    if bool(rejected.any()):
+                        non_admitted = miss[rejected]
                 else:
-                    ins_mask[:] = True
+                    ins_mask[new_in_miss] = True
             ins = ins_mask.nonzero(as_tuple=True)[0]
             if ins.numel() > 0:
                 ik, it = mk[ins].contiguous(), mt[ins].contiguous()
@@ -614,7 +656,10 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
                 cache.increment_counter(cidx, it)
                 slots[miss[ins]] = cidx
         rows = ext.rows_from_slots(slots, utids, cache.row_base_)
-        self._prefetch_states.append(PrefetchState(ukeys, reverse, utids, slots, rows, nu, non_admitted_positions=non_admitted))
+        state = PrefetchState(ukeys, reverse, utids, slots, rows, nu, non_admitted_positions=non_admitted)
+        if self._hybrid and miss.numel() > 0:
+            state.cold_slots, state.cold_rows = cold_slots, ext.rows_from_slots(cold_slots, utids, st.row_base_)
+        self._prefetch_states.append(state)
         self._update_score()
 
     def _write_back(self, keys, tids, scores, vals, ts) -> None:
@@ -710,6 +755,8 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         self._update_score()
 
     def _unpin(self, st: PrefetchState) -> None:
+        if st.cold_slots is not None:
+            self._table.decrement_counter(st.cold_slots, st.unique_table_ids)
         tb = self._hot_table
         if st.num_unique_dev is not None:
             ext.table_update_counter_n(tb._ref_counter, st.slot_indices, -1, tb.table_bucket_offsets_, tb.bucket_capacity_, st.num_unique_dev,
@@ -734,7 +781,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
     def _eval_forward(self, indices, offsets, B) -> torch.Tensor:
         """dynamicemb_eval_forward (batched_dynamicemb_function.py:836): read-only fused probe+gather; absent ids take the
         eval initializer (constant, default 0)."""
-        if self._caching:
+        if self._caching or self._hybrid:
             return self._eval_forward_cached(indices, offsets, B)
         tb = self._table
         T = len(self._dynamicemb_options)
@@ -768,7 +815,7 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
         from .types import EmbOptimType
         assert self.training and self._fused_prefetch
         assert self._admit_strategy is None, "admission decides on the host side of the op sequence: no CUDA-graph step"
-        assert not self._caching, "the cache path compacts its misses on the host: no CUDA-graph step"
+        assert not self._caching and not self._hybrid, "the tiered paths compact their misses on the host: no CUDA-graph step"
         assert not self._mixed_D, "mixed dims slice / scatter the pooled layout in torch: use forward() / backward()"
         assert self._optimizer_type in (EmbOptimType.SGD, EmbOptimType.EXACT_SGD, EmbOptimType.EXACT_ADAGRAD, EmbOptimType.EXACT_ROWWISE_ADAGRAD)
         assert self._score_policy() not in (ScorePolicy.GLOBAL_TIMER, ScorePolicy.LRU_LFU)
@@ -819,13 +866,15 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
     def _export_batches(self, table_id: int, batch_size: int = 65536):
         """(keys, value rows [n, value_dim], scores) batches of one table: table scan by the export kernel, rows by the row-copy kernel.
         scores: int64 [n], or [n, num_scores] in device order for multi-word scores (export_keys_values_iter, key_value_table.py:1073-1131)."""
-        tb = self._table
-        base = int(tb.table_bucket_offsets_cpu_[table_id]) * tb.bucket_capacity_
-        for keys, scores, idx in tb.export(table_id, batch=batch_size):
-            dense = torch.empty(keys.numel(), self.value_dim, dtype=torch.float32, device=self._device)
-            ext.copy_rows(self._values, self.value_dim, (idx + base).contiguous(), dense, to_table=False)
-            sc = tb.gather_score_blocks(table_id, idx) if tb.num_scores_ > 1 else scores.view(torch.int64)
-            yield keys, dense, sc
+        # a cache is flushed into the backing table before any export (flush()); hybrid storage holds disjoint key sets in its two tiers
+        tiers = [(self._cache, self._cache_values), (self._table, self._values)] if self._hybrid else [(self._table, self._values)]
+        for tb, values in tiers:
+            base = int(tb.table_bucket_offsets_cpu_[table_id]) * tb.bucket_capacity_
+            for keys, scores, idx in tb.export(table_id, batch=batch_size):
+                dense = torch.empty(keys.numel(), self.value_dim, dtype=torch.float32, device=self._device)
+                ext.copy_rows(values, self.value_dim, (idx + base).contiguous(), dense, to_table=False)
+                sc = tb.gather_score_blocks(table_id, idx) if tb.num_scores_ > 1 else scores.view(torch.int64)
+                yield keys, dense, sc
 
     def export_keys_values(self, table_name=0, device: Optional[torch.device] = None, batch_size: int = 65536):
         """All (keys, rows) of one table, named as in the reference (:1411, `table_name`) or by index.  With `device` given the reference's
@@ -1023,6 +1072,8 @@ class BatchedDynamicEmbeddingTablesV2(nn.Module):
                     dense[:, D + sdim:] = 0
             tids = torch.full((n,), t, dtype=torch.int64, device=self._device)
             keys = keys.to(self.index_type)
+            if self._hybrid:                                        # the file is authoritative: no second copy in the HBM tier
+                self._cache.erase(keys, tids)
             if ns > 1:
                 if scores is None or scores.dim() != 2 or scores.size(1) != ns or scores.size(0) != n:
                     raise ValueError(f"multi-word load expects [{n}, {ns}] scores, got {None if scores is None else tuple(scores.shape)}")

@@ -125,9 +125,9 @@ class RowWiseShardedDynamicEmbedding(_ShardCheckpointMixin, nn.Module):
                                       "on the device — use RowWiseShardedDynamicEmbeddingA2A for a shard with an admission strategy")
         if getattr(local, "_mixed_D", False):
             raise NotImplementedError("mixed embedding dims inside one sharded module are not built: shard the tables of each dim separately")
-        if getattr(local, "_caching", False):
-            raise NotImplementedError("the cache tier compacts its misses on the host; the peer-memory step keeps every count on the device — "
-                                      "use RowWiseShardedDynamicEmbeddingA2A for a cached shard")
+        if getattr(local, "_caching", False) or getattr(local, "_hybrid", False):
+            raise NotImplementedError("the cache / hybrid tiers compact their misses on the host; the peer-memory step keeps every count on the device — "
+                                      "use RowWiseShardedDynamicEmbeddingA2A for such a shard")
         self.local = local
         self.group = process_group if process_group is not None else dist.group.WORLD
         self.world_size = dist.get_world_size(self.group)
@@ -443,7 +443,7 @@ class _SharderBase:
         fp = {k: v for k, v in self.fused_params.items() if k not in ("dynamicemb_options",)}
         local = BatchedDynamicEmbeddingTablesV2(opts, table_names=names, feature_table_map=fmap, pooling_mode=pooling, device=device,
                                                 optimizer=fp.pop("optimizer", EmbOptimType.SGD), **fp)
-        if not self.pooled and (local._admit_strategy is not None or local._caching):
+        if not self.pooled and (local._admit_strategy is not None or local._caching or local._hybrid):
             # admission / cache tier decide on the host side of the op sequence: the all_to_all wrapper carries them (sequence mode)
             return RowWiseShardedDynamicEmbeddingA2A(local, pg, dist_type=opts[0].dist_type, num_embeddings_per_feature=hash_sizes,
                                                      use_index_dedup=self.use_index_dedup)

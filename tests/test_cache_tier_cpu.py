@@ -181,3 +181,89 @@ def test_cache_checkpoint_round_trip_cpu_shim(tmp_path):
             fresh.eval()
             out = fresh(ids, torch.arange(0, 1501, dtype=torch.int64))
             assert torch.equal(out[:, 0], want)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# hybrid storage: 0 < local_hbm_for_values < table bytes WITHOUT caching = two disjoint tiers (reference HybridStorage,
+# key_value_table.py:2107-2404): new keys enter the HBM tier, its evictions move to the host tier, host-tier keys stay there
+def _hybrid_module(dev, threshold=None, T=1, pooling=None, score_strategy=None, cap=8192):
+    return _module({"device": dev}, threshold, T=T, pooling=pooling, score_strategy=score_strategy, cap=cap, dim=D, caching=False,
+                   local_hbm=1024 * D * 4)
+
+
+def scenario_hybrid_train(dev, score_strategy=None):
+    """Six training steps of 600 distinct keys out of 3000: the HBM tier (1024 rows) overflows into the host tier; outputs follow the
+    tier-agnostic dictionary model at every step (rows are trained in whichever tier they sit), the tiers stay disjoint, an export sees
+    both, a checkpoint round-trips."""
+    rng = np.random.default_rng(5)
+    m = _hybrid_module(dev, score_strategy=score_strategy)
+    assert m._hybrid and m.cache is None and m._cache.capacity() == 1024 and m.tables.capacity() == 7168
+    m.train()
+    model = {}
+    for step in range(6):
+        uniq = rng.choice(np.arange(1, 3001), size=600, replace=False)
+        ids = np.concatenate([uniq, rng.choice(uniq, size=200)]).astype(np.int64)
+        rng.shuffle(ids)
+        out = m(torch.from_numpy(ids).to(dev), torch.arange(0, ids.size + 1, dtype=torch.int64, device=dev))
+        want = torch.tensor([model.get(int(k), float(k % 100000)) for k in ids], dtype=torch.float32)
+        assert torch.equal(out[:, 0].cpu(), want), f"step {step}: forward differs from the model"
+        out.backward(torch.ones_like(out))
+        for k in ids.tolist():
+            model[k] = model.get(k, float(k % 100000)) - LR
+    hot = set(next(m._cache.export(0))[0].tolist())
+    cold = set()
+    for keys, _, _ in m.tables.export(0):
+        cold |= set(keys.tolist())
+    assert hot and cold and not (hot & cold) and (hot | cold) == set(model), "two disjoint tiers that together hold every key"
+    assert m._cache._ref_counter.sum().item() == 0 and m.tables._ref_counter.sum().item() == 0, "every pin released"
+    snap = _snapshot(m)
+    assert set(snap) == set(model) and all(float(snap[k][0]) == model[k] for k in model)
+    m.eval()
+    some = list(model)[:40] + [5000]
+    out = m(torch.tensor(some, dtype=torch.int64, device=dev), torch.arange(0, len(some) + 1, dtype=torch.int64, device=dev))
+    assert torch.equal(out[:, 0].cpu(), torch.tensor([model.get(k, 0.0) for k in some], dtype=torch.float32))
+    return m, model
+
+
+def scenario_hybrid_pooled_checkpoint(dev, tmp_path):
+    from dynamicemb import DynamicEmbPoolingMode
+    rng = np.random.default_rng(6)
+    T, B = 2, 64
+    m = _hybrid_module(dev, T=T, pooling=DynamicEmbPoolingMode.SUM)
+    m.train()
+    model = [{}, {}]
+    for step in range(4):
+        lens = rng.integers(0, 12, size=T * B)
+        ids = rng.integers(1, 2500, size=int(lens.sum())).astype(np.int64)
+        off_np = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        out = m(torch.from_numpy(ids).to(dev), torch.from_numpy(off_np).to(dev))
+        want = torch.zeros(B, T * D, dtype=torch.float64)
+        for f in range(T):
+            for b in range(B):
+                for k in ids[off_np[f * B + b]:off_np[f * B + b + 1]].tolist():
+                    want[b, f * D:(f + 1) * D] += model[f].get(k, float(k % 100000))
+        assert torch.allclose(out.cpu().double(), want, rtol=1e-5, atol=1e-2), f"step {step}"
+        out.backward(torch.ones_like(out))
+        for f in range(T):
+            for b in range(B):
+                for k in ids[off_np[f * B + b]:off_np[f * B + b + 1]].tolist():
+                    model[f][k] = model[f].get(k, float(k % 100000)) - LR
+    m.dump(str(tmp_path), optim=True)
+    m2 = _hybrid_module(dev, T=T, pooling=DynamicEmbPoolingMode.SUM)
+    m2.load(str(tmp_path), optim=True)
+    for f in range(T):
+        snap = _snapshot(m2, f)
+        assert set(snap) == set(model[f])
+        assert all(abs(float(snap[k][0]) - model[f][k]) <= 1e-3 * max(1.0, abs(model[f][k])) for k in model[f])
+
+
+@pytest.mark.parametrize("strategy", ["step", "timestamp"])
+def test_hybrid_train_cpu_shim(strategy):
+    from dynamicemb import DynamicEmbScoreStrategy as S
+    with patched_module():
+        scenario_hybrid_train(CPU, {"step": S.STEP, "timestamp": S.TIMESTAMP}[strategy])
+
+
+def test_hybrid_pooled_checkpoint_cpu_shim(tmp_path):
+    with patched_module():
+        scenario_hybrid_pooled_checkpoint(CPU, tmp_path)

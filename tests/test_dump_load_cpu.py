@@ -37,7 +37,8 @@ def _train(m, ids):
 
 
 def test_model_level_dump_load_scores_cpu_shim(tmp_path):
-    from dynamicemb import DynamicEmbDump, DynamicEmbLoad, DynamicEmbScoreStrategy as S, get_score, incremental_dump, set_score
+    from dynamicemb import DynamicEmbDump, DynamicEmbLoad, DynamicEmbScoreStrategy as S
+    from dynamicemb.incremental_dump import get_score, incremental_dump, set_score
     from dynamicemb.dump_load import find_sharded_modules, get_dynamic_emb_module
     with patched_module():
         mk = lambda strat: _module({"fused_prefetch": False}, None, T=2, score_strategy=strat)          # noqa: E731

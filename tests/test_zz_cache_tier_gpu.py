@@ -10,7 +10,8 @@ import os
 
 import pytest
 
-from tests.test_cache_tier_cpu import scenario_cache_pooled_two_tables, scenario_cache_train_evict_refetch, scenario_cache_with_admission
+from tests.test_cache_tier_cpu import (scenario_cache_pooled_two_tables, scenario_cache_train_evict_refetch, scenario_cache_with_admission,
+                                       scenario_hybrid_pooled_checkpoint, scenario_hybrid_train)
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("RECSYS_B200_UNVERIFIED_GPU_TESTS") != "1",
@@ -31,3 +32,13 @@ def test_cache_pooled_two_tables(cuda, mean):
 
 def test_cache_with_admission(cuda):
     scenario_cache_with_admission(cuda)
+
+
+@pytest.mark.parametrize("strategy", ["step", "timestamp"])
+def test_hybrid_train(cuda, strategy):
+    from dynamicemb import DynamicEmbScoreStrategy as S
+    scenario_hybrid_train(cuda, {"step": S.STEP, "timestamp": S.TIMESTAMP}[strategy])
+
+
+def test_hybrid_pooled_checkpoint(cuda, tmp_path):
+    scenario_hybrid_pooled_checkpoint(cuda, tmp_path)
