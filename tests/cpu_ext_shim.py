@@ -131,6 +131,51 @@ class CpuExt:
         iout[:sel.size] = torch.from_numpy(sel.astype(np.int64) + offset - table_begin)
         return torch.tensor([sel.size], dtype=torch.int64), kout, sout, iout
 
+    # ------------------------------------------------------------------ fused training prefetch (one C call in the product)
+    def unique_scratch(self, n_max, num_tables, device):
+        return torch.empty(0, dtype=torch.uint8)
+
+    def table_update_counter_n(self, counter, slot_indices, delta, table_bucket_offsets, bucket_capacity, n_device, table_ids=None):
+        n = int(n_device.item())
+        self.table_update_counter_with_layout(counter, slot_indices[:n], delta, table_bucket_offsets, bucket_capacity,
+                                              table_ids=table_ids[:n] if table_ids is not None else None)
+
+    def train_prefetch(self, table_storage, table_bucket_offsets, bucket_capacity, bucket_sizes, ref_counter, bucket_heads, values, emb_dim, row_base,
+                       keys, table_range, num_tables, policy, table_scores, timestamp, init_mode, init_params, seed, state_init,
+                       freq_in=None, num_scores=1, table_init=None, n_dev=None, unique_scratch=None):
+        """unique -> lookup (hits scored + pinned) -> insert the misses -> init their rows -> pin; outputs padded to n with -1 / 0."""
+        n = keys.numel()
+        n_real = int(n_dev.item()) if n_dev is not None else n
+        want_freq = int(policy) in (2, 4)
+        fin = (freq_in if freq_in is not None else torch.empty(0, dtype=torch.int64)) if want_freq else None
+        num_u, uk, rev, _, freq, utids = self.segmented_unique_cuda(keys[:n_real], table_range, num_tables, fin, want_table_ids=True)
+        nu = int(num_u.item())
+        k, t = uk[:nu].contiguous(), utids[:nu].contiguous()
+        if int(policy) == 1:
+            score = table_scores[t]
+        elif want_freq:
+            score = freq[:nu]
+        else:
+            score = None
+        args = (table_storage, table_bucket_offsets, bucket_capacity)
+        _, founds, slots = self.table_lookup(*args, k, t, score, policy, num_scores=num_scores, timestamp=timestamp)
+        self.table_update_counter_with_layout(ref_counter, slots, 1, table_bucket_offsets, bucket_capacity, table_ids=t)
+        miss = (~founds).nonzero(as_tuple=True)[0]
+        if miss.numel():
+            mk, mt = k[miss].contiguous(), t[miss].contiguous()
+            new = self.table_insert(*args, bucket_sizes, mk, mt, score[miss].contiguous() if score is not None else None, policy, ref_counter,
+                                    num_scores=num_scores, timestamp=timestamp)
+            p0, p1, p2, p3 = init_params
+            self.init_rows(values, emb_dim, self.rows_from_slots(new, mt, row_base), mk, init_mode, p0, p1, p2, p3, seed=seed, state_init=state_init,
+                           table_ids=mt if table_init is not None else None, table_init=table_init)
+            self.table_update_counter_with_layout(ref_counter, new, 1, table_bucket_offsets, bucket_capacity, table_ids=mt)
+            slots[miss] = new
+        pad = lambda x, fill: torch.cat([x, torch.full((n - x.numel(),), fill, dtype=x.dtype)])      # noqa: E731
+        rows = self.rows_from_slots(slots, t, row_base)
+        rev_full = torch.zeros(n, dtype=torch.int64)
+        rev_full[:n_real] = rev[:n_real]
+        return pad(k, 0), rev_full, pad(t, 0), pad(slots, -1), pad(rows, -1), torch.tensor([nu], dtype=torch.int64)
+
     # ------------------------------------------------------------------ dedup
     def get_table_range(self, offsets, feature_offsets, num_features=None):
         if num_features is None:
