@@ -6,7 +6,8 @@ suite run it end to end: each native op used by that logic is restated here on t
 the reference's table) or on torch CPU ops, with the SAME signatures and return conventions as the real op layer.  `patched_module()`
 swaps it into the module / table namespaces for the duration of a test and makes the module allocate on the CPU.
 
-It is only meaningful for small inputs (python loops) and for initializer modes that do not draw random numbers (DEBUG, CONSTANT).
+It is only meaningful for small inputs (python loops).  The random initializer modes are deterministic per (seed, key, column) like the
+product's Philox, but are not the kernels' numbers.
 """
 import contextlib
 import ctypes
@@ -210,21 +211,30 @@ class CpuExt:
     def init_rows(self, values, emb_dim, rows, keys, mode, p0=0.0, p1=1.0, p2=0.0, p3=0.0, seed=0, state_init=0.0, only_if=None, emb_out=None,
                   table_ids=None, table_init=None):
         M = self._real.InitializerMode
-        modes, consts = [int(mode)] * keys.numel(), [float(p0)] * keys.numel()
+        nk = keys.numel()
+        modes, params, seeds = [int(mode)] * nk, [(float(p0), float(p1), float(p2), float(p3))] * nk, [int(seed)] * nk
         if table_init is not None:
             img = table_init.numpy().view(np.dtype([("mode", "<i4"), ("p", "<f4", (4,)), ("reserved", "<u4"), ("seed", "<u8")]))
-            tid = table_ids.tolist() if table_ids is not None else [0] * keys.numel()
-            modes, consts = [int(img["mode"][t]) for t in tid], [float(img["p"][t][0]) for t in tid]
+            tid = table_ids.tolist() if table_ids is not None else [0] * nk
+            modes, params = [int(img["mode"][t]) for t in tid], [tuple(float(x) for x in img["p"][t]) for t in tid]
+            seeds = [int(img["seed"][t]) for t in tid]
         ku = _np(keys).view(np.uint64)
-        for i in range(keys.numel()):
+        for i in range(nk):
             if only_if is not None and not bool(only_if[i]):
                 continue
+            a, b, lo, up = params[i]
             if modes[i] == int(M.DEBUG):
                 v = float(int(ku[i]) % 100000)
             elif modes[i] == int(M.CONSTANT):
-                v = consts[i]
+                v = a
             else:
-                raise NotImplementedError("the CPU shim only restates the deterministic initializers (DEBUG, CONSTANT)")
+                # random modes: like the product's Philox, a function of (seed, key, column) only — NOT the same numbers as the kernels
+                g = np.random.default_rng([seeds[i] & 0xFFFFFFFF, seeds[i] >> 32, int(ku[i]) & 0xFFFFFFFF, int(ku[i]) >> 32])
+                if modes[i] == int(M.UNIFORM):
+                    v = torch.from_numpy(g.uniform(a, b, emb_dim).astype(np.float32))
+                else:
+                    z = g.standard_normal(emb_dim) * b + a
+                    v = torch.from_numpy((np.clip(z, lo, up) if modes[i] == int(M.TRUNCATED_NORMAL) else z).astype(np.float32))
             r = int(rows[i]) if rows is not None else -1
             if r >= 0:
                 values[r, :emb_dim] = v
@@ -304,6 +314,15 @@ class CpuExt:
                                  weight_decay=weight_decay, step=step)
         return ug if want_unique_grads else None
 
+
+    class BackwardPrep:
+        """The product's side stream for the gradient-independent half of the backward; nothing to prepare on the CPU."""
+
+        def __init__(self, device=None):
+            pass
+
+    def backward_prepare(self, prep, emb_dim, inverse, num_unique_bound, n_dev=None, grad_row_of=None):
+        return None
 
     def reduce_grads(self, reverse_indices, grads, num_unique, batch_size, out_dim, offsets=None, D_offsets=None, combiner=-1, total_D=0):
         F = (total_D // out_dim) if offsets is not None else 0
