@@ -267,3 +267,37 @@ def test_hybrid_train_cpu_shim(strategy):
 def test_hybrid_pooled_checkpoint_cpu_shim(tmp_path):
     with patched_module():
         scenario_hybrid_pooled_checkpoint(CPU, tmp_path)
+
+
+@pytest.mark.parametrize("tier", ["cache", "hybrid"])
+def test_tiered_eval_absent_constant_cpu_shim(tier):
+    """Eval through both tiers with a non-zero eval constant: stored ids read their row (wherever it sits), absent ids the constant —
+    sequence and SUM-pooled, two tables."""
+    from dynamicemb import (BatchedDynamicEmbeddingTablesV2, DynamicEmbInitializerArgs, DynamicEmbInitializerMode as IM, DynamicEmbPoolingMode as P,
+                            DynamicEmbScoreStrategy, DynamicEmbTableOptions, EmbOptimType)
+    with patched_module():
+        for pooling in (P.NONE, P.SUM):
+            opts = [DynamicEmbTableOptions(dim=D, max_capacity=8192, bucket_capacity=128, score_strategy=DynamicEmbScoreStrategy.STEP,
+                                           caching=(tier == "cache"), local_hbm_for_values=1024 * D * 4,
+                                           initializer_args=DynamicEmbInitializerArgs(mode=IM.DEBUG),
+                                           eval_initializer_args=DynamicEmbInitializerArgs(mode=IM.CONSTANT, value=-3.0)) for _ in range(2)]
+            m = BatchedDynamicEmbeddingTablesV2(opts, table_names=["a", "b"], feature_table_map=[0, 1], pooling_mode=pooling, optimizer=EmbOptimType.SGD,
+                                                learning_rate=LR, device=CPU)
+            assert (m._caching, m._hybrid) == ((True, False) if tier == "cache" else (False, True))
+            m.train()
+            # fill past the 1024-row hot tier so that stored keys sit in both tiers
+            for lo in range(1, 2401, 600):
+                ids = torch.arange(lo, lo + 600, dtype=torch.int64).repeat(2)             # the same keys in table a and table b
+                off = (torch.arange(0, 1201, dtype=torch.int64) if pooling == P.NONE else torch.arange(0, 1201, 75, dtype=torch.int64))
+                out = m(ids, off)
+                out.backward(torch.zeros_like(out))
+            m.eval()
+            q = torch.tensor([5, 2399, 9000, 700, 9001, 1500, 9002, 42], dtype=torch.int64)     # per table: 2 stored, 1 absent, 1 stored
+            off = torch.arange(0, 9, dtype=torch.int64) if pooling == P.NONE else torch.tensor([0, 2, 4, 6, 8], dtype=torch.int64)
+            out = m(q, off)
+            val = lambda k: float(k) if k < 2401 else -3.0                               # noqa: E731
+            if pooling == P.NONE:
+                assert out[:, 0].tolist() == [val(int(k)) for k in q]
+            else:                                                                        # [B=2, 2 tables]: bags of 2 ids
+                want = [[val(5) + val(2399), val(9001) + val(1500)], [val(9000) + val(700), val(9002) + val(42)]]
+                assert [[float(out[b, f * D]) for f in range(2)] for b in range(2)] == want
