@@ -166,7 +166,6 @@ def test_package_exports_every_name_of_the_reference():
 _NOT_ON_THE_PATH = {
     "dynamicemb.exportable_tables": "inference export (torch.export of embedding collections) — SURVEY §2 out of scope",
     "dynamicemb.get_planner": "convenience wrapper around TorchRec's Topology / planner objects (needs torchrec)",
-    "dynamicemb.benchmark.dataset_generator": "benchmark data generator; bench.py restates its power-law stream",
     "dynamicemb.utils": "TORCHREC_TYPES (a tuple of TorchRec classes; needs torchrec)",
 }
 
@@ -241,3 +240,21 @@ def test_call_shapes_of_the_reference_bind():
                 raise AssertionError(f"{where}: {errors}")
             bound += 1
     assert bound >= 60
+
+
+def test_benchmark_id_generators():
+    """dynamicemb.benchmark.dataset_generator (import site of examples/commons/datasets/hstu_batch.py:161): ranges, dtype and skew."""
+    import torch
+    from dynamicemb.benchmark.dataset_generator import PowerLaw, gen_key, translateToPowerLaw, zipf
+    torch.manual_seed(0)
+    ids = PowerLaw(1, 10 ** 9, 1.05, 200_000, device=torch.device("cpu"))
+    assert ids.dtype == torch.int64 and int(ids.min()) >= 1 and int(ids.max()) < 10 ** 9
+    assert float((ids < 1000).float().mean()) > 0.25 and float((ids > 10 ** 6).float().mean()) > 0.15      # heavy head AND a long tail
+    x = torch.tensor([0.0, 0.5, 1.0 - 1e-12], dtype=torch.float64)
+    y = translateToPowerLaw(1, 100, 1.05, x)
+    assert float(y[0]) == 1.0 and 1.0 < float(y[1]) < 99.0 and float(y[2]) < 100.0 and int(y[2]) == 99
+    assert gen_key(4, 3, 1.05, 1000, torch.device("cpu")).numel() == 12
+    z = zipf(5, 105, 1.2, 50_000, torch.device("cpu"))
+    assert z.dtype == torch.int64 and int(z.min()) >= 5 and int(z.max()) < 105
+    counts = torch.bincount(z - 5, minlength=100).sort(descending=True).values.float()
+    assert counts[0] / counts[9] > 8.0                                                                      # rank-1 vs rank-10: 10^1.2 = 15.8
