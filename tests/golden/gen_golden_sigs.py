@@ -24,6 +24,8 @@ TARGETS = {
         "BatchedDynamicEmbeddingTablesV2.split_embedding_weights", "BatchedDynamicEmbeddingTablesV2.reset_cache_states",
         "BatchedDynamicEmbeddingTablesV2.set_record_cache_metrics", "BatchedDynamicEmbeddingTablesV2.flush", "BatchedDynamicEmbeddingTablesV2.get_score",
         "encode_meta_json_file_path", "encode_checkpoint_file_path", "encode_counter_checkpoint_file_path", "find_files", "get_loading_files"],
+    "corelib/dynamicemb/dynamicemb/get_planner.py": ["get_planner"],
+    "corelib/dynamicemb/benchmark/dataset_generator.py": ["translateToPowerLaw", "PowerLaw", "gen_key", "zipf"],
     "corelib/dynamicemb/dynamicemb/dump_load.py": ["find_sharded_modules", "get_dynamic_emb_module", "DynamicEmbDump", "DynamicEmbLoad"],
     "corelib/dynamicemb/dynamicemb/incremental_dump.py": ["set_score", "get_score", "incremental_dump", "is_valid_score_threshold"],
     "corelib/dynamicemb/dynamicemb/dynamicemb_config.py": ["get_sharded_table_capacity", "get_table_value_bytes", "string_to_evict_strategy",
@@ -169,7 +171,7 @@ CALLEES = ["DynamicEmbTableOptions", "DynamicEmbInitializerArgs", "DynamicEmbPar
            "DynamicEmbeddingEnumerator", "DynamicEmbeddingCollectionSharder", "DynamicEmbeddingBagCollectionSharder", "FrequencyAdmissionStrategy",
            "KVCounter", "BatchedDynamicEmbeddingTablesV2", "DynamicEmbDump", "DynamicEmbLoad", "dynamic_emb_save", "dynamic_emb_load",
            "get_sharded_table_capacity", "get_table_value_bytes", "hstu_attn_varlen_func", "incremental_dump", "get_score", "set_score",
-           "fused_hstu_op", "hstu_varlen_fwd_100", "hstu_varlen_bwd_100"]
+           "fused_hstu_op", "hstu_varlen_fwd_100", "hstu_varlen_bwd_100", "get_planner", "gpu_zipf"]
 
 
 def main_calls():
@@ -183,12 +185,13 @@ def main_calls():
                     tree = ast.parse(open(os.path.join(dp, f)).read())
                 except SyntaxError:
                     continue
+                local_defs = {n.name for n in ast.walk(tree) if isinstance(n, (ast.FunctionDef, ast.ClassDef))}      # homonyms defined in the file itself
                 for node in ast.walk(tree):
                     if not isinstance(node, ast.Call):
                         continue
                     fn = node.func
                     name = fn.id if isinstance(fn, ast.Name) else fn.attr if isinstance(fn, ast.Attribute) else None
-                    if name not in CALLEES or any(isinstance(a, ast.Starred) for a in node.args):
+                    if name not in CALLEES or name in local_defs or any(isinstance(a, ast.Starred) for a in node.args):
                         continue
                     kws = sorted(k.arg for k in node.keywords if k.arg is not None)
                     rec = {"file": os.path.relpath(os.path.join(dp, f), REF), "line": node.lineno, "positional": len(node.args), "keywords": kws,

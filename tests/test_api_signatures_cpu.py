@@ -38,6 +38,8 @@ def _ours():
         "LinearBucketTable.__init__": LT.__init__, "LinearBucketTable.lookup": LT.lookup, "LinearBucketTable.insert": LT.insert,
         "LinearBucketTable.insert_and_evict": LT.insert_and_evict, "LinearBucketTable.erase": LT.erase, "LinearBucketTable.load": LT.load,
         "LinearBucketTable.dump": LT.dump, "get_scored_table": get_scored_table,
+        "get_planner": __import__("dynamicemb.get_planner", fromlist=["get_planner"]).get_planner,
+        **{n: getattr(__import__("dynamicemb.benchmark.dataset_generator", fromlist=[n]), n) for n in ("translateToPowerLaw", "PowerLaw", "gen_key", "zipf")},
         "find_sharded_modules": dl.find_sharded_modules, "get_dynamic_emb_module": dl.get_dynamic_emb_module, "DynamicEmbDump": dl.DynamicEmbDump,
         "DynamicEmbLoad": dl.DynamicEmbLoad, "set_score": dl.set_score, "get_score": dl.get_score, "incremental_dump": dl.incremental_dump,
         "is_valid_score_threshold": dl.is_valid_score_threshold, "get_sharded_table_capacity": ty.get_sharded_table_capacity,
@@ -165,8 +167,6 @@ def test_package_exports_every_name_of_the_reference():
 # import sites of the reference's user code (examples/, corelib/dynamicemb/example, benchmark): tests/golden/api_imports.json
 _NOT_ON_THE_PATH = {
     "dynamicemb.exportable_tables": "inference export (torch.export of embedding collections) — SURVEY §2 out of scope",
-    "dynamicemb.get_planner": "convenience wrapper around TorchRec's Topology / planner objects (needs torchrec)",
-    "dynamicemb.utils": "TORCHREC_TYPES (a tuple of TorchRec classes; needs torchrec)",
 }
 
 
@@ -202,7 +202,9 @@ def _callee(name):
     from dynamicemb import dump_load as dl, planner, shard
     from hstu import hstu_attn_varlen_func, hstu_ops_gpu
     from hstu.fused_hstu_op import fused_hstu_op
-    table = {"fused_hstu_op": fused_hstu_op, "hstu_varlen_fwd_100": hstu_ops_gpu.hstu_varlen_fwd_100, "hstu_varlen_bwd_100": hstu_ops_gpu.hstu_varlen_bwd_100,
+    from dynamicemb.benchmark.dataset_generator import zipf
+    from dynamicemb.get_planner import get_planner
+    table = {"get_planner": get_planner, "gpu_zipf": zipf, "fused_hstu_op": fused_hstu_op, "hstu_varlen_fwd_100": hstu_ops_gpu.hstu_varlen_fwd_100, "hstu_varlen_bwd_100": hstu_ops_gpu.hstu_varlen_bwd_100,
              "dynamic_emb_save": dl.DynamicEmbDump, "dynamic_emb_load": dl.DynamicEmbLoad, "hstu_attn_varlen_func": hstu_attn_varlen_func,
              "incremental_dump": None, "get_score": None, "set_score": None}         # module-level AND method forms exist: checked separately
     if name in table:
@@ -258,3 +260,21 @@ def test_benchmark_id_generators():
     assert z.dtype == torch.int64 and int(z.min()) >= 5 and int(z.max()) < 105
     counts = torch.bincount(z - 5, minlength=100).sort(descending=True).values.float()
     assert counts[0] / counts[9] > 8.0                                                                      # rank-1 vs rank-10: 10^1.2 = 15.8
+
+
+def test_get_planner_builds_constraints_and_plans():
+    """get_planner (reference get_planner.py:60-131): data-parallel / DynamicEmb / other tables get their constraints, the planner plans
+    the DynamicEmb ones row-wise."""
+    import torch
+    from dynamicemb import DynamicEmbScoreStrategy, DynamicEmbTableOptions
+    from dynamicemb.get_planner import get_planner
+    from dynamicemb.utils import TORCHREC_TYPES
+
+    class Cfg:
+        def __init__(self, name, dim, num):
+            self.name, self.embedding_dim, self.num_embeddings, self.feature_names = name, dim, num, [name]
+    cfgs = [Cfg("item", 128, 1_000_000), Cfg("ctx", 64, 1000), Cfg("user", 128, 500_000)]
+    planner = get_planner(cfgs, {"ctx"}, {"item": DynamicEmbTableOptions(score_strategy=DynamicEmbScoreStrategy.STEP)}, torch.device("cpu"))
+    plan = planner.plan()
+    assert set(plan) == {"item"} and plan["item"]["sharding_type"] == "row_wise" and plan["item"]["local_capacity"] == 1_000_064
+    assert isinstance(TORCHREC_TYPES, set)
