@@ -337,15 +337,43 @@ class RowWiseShardedDynamicEmbedding(_ShardCheckpointMixin, nn.Module):
         return _GraphedStep(m, graph, keepalive=(ids_static, lengths, offsets, grad_static, self)), out, loss
 
 
+class _PoolRows(torch.autograd.Function):
+    """[n, D] rows of the ids of this rank's batch (feature-major) -> [B, F*D] pooled bags, by the pooled gather kernel over the rows as a
+    value table; backward hands every id its bag's gradient (divided by the bag length for MEAN) through the reduce kernel."""
+
+    @staticmethod
+    def forward(ctx, rows, offsets, batch_size, num_features, combiner):
+        n, D = rows.shape
+        ctx.save_for_backward(offsets)
+        ctx.shape, ctx.batch_size, ctx.num_features, ctx.combiner = (n, D), batch_size, num_features, combiner
+        ident = torch.arange(n, dtype=torch.int64, device=rows.device)
+        return ext.gather_forward(rows.contiguous(), D, ident, None, n, offsets=offsets, batch_size=batch_size, num_features=num_features,
+                                  combiner=combiner, out_dtype=rows.dtype,
+                                  out=torch.empty(batch_size, num_features * D, dtype=rows.dtype, device=rows.device))
+
+    @staticmethod
+    def backward(ctx, grad):
+        (offsets,) = ctx.saved_tensors
+        n, D = ctx.shape
+        ident = torch.arange(n, dtype=torch.int64, device=grad.device)
+        g = ext.reduce_grads(ident, grad.contiguous().to(torch.float32), n, ctx.batch_size, D, offsets=offsets, combiner=ctx.combiner,
+                             total_D=ctx.num_features * D)
+        return g.to(grad.dtype), None, None, None, None
+
+
 class RowWiseShardedDynamicEmbeddingA2A(_ShardCheckpointMixin, nn.Module):
     """The TorchRec-shaped variant of the same data flow over torch.distributed collectives (block bucketize -> all_to_all(lengths, ids) ->
     lookup -> all_to_all(rows), dynamicemb/input_dist.py): for process groups whose ranks do not share an NVLink/NVSwitch domain (multi
-    node) and for the CPU (gloo) tests of the host logic.  Sequence mode only; two host synchronisations per step, as in TorchRec."""
+    node), for shards that decide on the host (admission, cache / hybrid tiers) and for the CPU (gloo) tests of the host logic.  Two host
+    synchronisations per step, as in TorchRec.  `local` is a sequence-mode module; `pooling_mode` SUM / MEAN makes the wrapper an
+    EmbeddingBagCollection: the rows come back per id and are pooled at the requester (like the peer-memory wrapper)."""
 
     def __init__(self, local: BatchedDynamicEmbeddingTablesV2, process_group=None, dist_type: str = "hash_roundrobin",
-                 num_embeddings_per_feature: Optional[List[int]] = None, use_index_dedup: bool = True):
+                 num_embeddings_per_feature: Optional[List[int]] = None, use_index_dedup: bool = True,
+                 pooling_mode: DynamicEmbPoolingMode = DynamicEmbPoolingMode.NONE):
         super().__init__()
-        assert local.pooling_mode == DynamicEmbPoolingMode.NONE, "sequence mode wrapper"
+        assert local.pooling_mode == DynamicEmbPoolingMode.NONE, "the shard looks rows up per id; the wrapper pools (pooling_mode=)"
+        self.pooling_mode = DynamicEmbPoolingMode(pooling_mode)
         self.local, self.group, self.use_index_dedup = local, process_group, use_index_dedup
         self.world_size = dist.get_world_size(process_group)
         self._sync_dist_type(dist_type)
@@ -366,9 +394,15 @@ class RowWiseShardedDynamicEmbeddingA2A(_ShardCheckpointMixin, nn.Module):
 
     def forward(self, ids: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
         from .input_dist import rw_sharded_lookup
-        return rw_sharded_lookup(ids, lengths, self.local.feature_num, self.group, local_fn=self.local, bucketize_fn=self._bucketize,
+        rows = rw_sharded_lookup(ids, lengths, self.local.feature_num, self.group, local_fn=self.local, bucketize_fn=self._bucketize,
                                  unique_fn=self._unique if self.use_index_dedup else None,
                                  reduce_fn=lambda idx, grad, num_rows: ext.reduce_grads(idx, grad, num_rows, 0, grad.shape[1]))
+        if self.pooling_mode == DynamicEmbPoolingMode.NONE:
+            return rows
+        F = self.local.feature_num
+        offsets = torch.zeros(lengths.numel() + 1, dtype=torch.int64, device=ids.device)
+        torch.cumsum(lengths.to(torch.int64), 0, out=offsets[1:])
+        return _PoolRows.apply(rows, offsets, lengths.numel() // F, F, int(self.pooling_mode))
 
 
 def _need_torchrec():
@@ -441,12 +475,22 @@ class _SharderBase:
             assert len(kinds) == 1, "one pooling type per EmbeddingBagCollection shard"
             pooling = DynamicEmbPoolingMode.MEAN if kinds.pop() == "MEAN" else DynamicEmbPoolingMode.SUM
         fp = {k: v for k, v in self.fused_params.items() if k not in ("dynamicemb_options",)}
-        local = BatchedDynamicEmbeddingTablesV2(opts, table_names=names, feature_table_map=fmap, pooling_mode=pooling, device=device,
-                                                optimizer=fp.pop("optimizer", EmbOptimType.SGD), **fp)
-        if not self.pooled and (local._admit_strategy is not None or local._caching or local._hybrid):
-            # admission / cache tier decide on the host side of the op sequence: the all_to_all wrapper carries them (sequence mode)
+        optimizer = fp.pop("optimizer", EmbOptimType.SGD)
+        # the module's own tier rule (batched_dynamicemb_tables.py: value bytes against local_hbm_for_values), evaluated up front
+        from .optimizer import get_optimizer_state_dim
+        max_d = max(o.dim for o in opts)
+        vdim = (max_d + get_optimizer_state_dim(optimizer if opts[0].training else EmbOptimType.NONE, max_d) + 3) // 4 * 4
+        total, local_hbm = sum(o.max_capacity * 4 * vdim for o in opts), sum(o.local_hbm_for_values for o in opts)
+        tiered = (total > local_hbm) if opts[0].caching else (0 < local_hbm < total)
+        if opts[0].admit_strategy is not None or tiered:
+            # admission / cache / hybrid tiers decide on the host side of the op sequence: the all_to_all wrapper carries them; the shard
+            # looks rows up per id and the wrapper pools for an EmbeddingBagCollection
+            local = BatchedDynamicEmbeddingTablesV2(opts, table_names=names, feature_table_map=fmap, pooling_mode=DynamicEmbPoolingMode.NONE,
+                                                    device=device, optimizer=optimizer, **fp)
             return RowWiseShardedDynamicEmbeddingA2A(local, pg, dist_type=opts[0].dist_type, num_embeddings_per_feature=hash_sizes,
-                                                     use_index_dedup=self.use_index_dedup)
+                                                     use_index_dedup=self.use_index_dedup, pooling_mode=pooling)
+        local = BatchedDynamicEmbeddingTablesV2(opts, table_names=names, feature_table_map=fmap, pooling_mode=pooling, device=device,
+                                                optimizer=optimizer, **fp)
         return RowWiseShardedDynamicEmbedding(local, pg, dist_type=opts[0].dist_type, num_embeddings_per_feature=hash_sizes,
                                               use_index_dedup=self.use_index_dedup)
 

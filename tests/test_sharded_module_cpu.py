@@ -22,7 +22,8 @@ from tests.test_dist_cpu import ROOT, _free_port
 LR = 0.5
 
 
-CONFIGS = [(True, None, False), (False, None, False), (True, 2, False), (True, None, True), (True, 2, True)]      # (dedup, threshold, cached)
+CONFIGS = [(True, None, False, "none"), (False, None, False, "none"), (True, 2, False, "none"), (True, None, True, "none"), (True, 2, True, "none"),
+           (True, None, False, "sum"), (True, 2, True, "mean")]      # (dedup, admission threshold, cached shard, pooling at the wrapper)
 
 
 def _worker(rank, world, port, q):
@@ -32,8 +33,8 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        for dedup, threshold, cached in CONFIGS:
-            _run_config(rank, world, dedup, threshold, cached)
+        for cfg in CONFIGS:
+            _run_config(rank, world, *cfg)
         q.put((rank, "ok"))
     except Exception as e:      # noqa: BLE001
         import traceback
@@ -42,57 +43,62 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def _run_config(rank, world, dedup, threshold, cached):
-    tag = f"dedup={dedup} threshold={threshold} cached={cached}: "
-    if True:
-        from tests.cpu_ext_shim import patched_module
-        from tests.test_admission_cpu import _module
-        from dynamicemb.shard import RowWiseShardedDynamicEmbeddingA2A
-        T, B, D = 2, 4, 8
-        with patched_module():
-            local = _module({"fused_prefetch": False}, threshold, T=T, dim=D, caching=cached, local_hbm=1024 * D * 4 if cached else 0)
-            assert (local.cache is not None) == cached
-            local.train()
-            sharded = RowWiseShardedDynamicEmbeddingA2A(local, dist.group.WORLD, dist_type="roundrobin", use_index_dedup=dedup)
-            # every rank can compute every rank's batch (same generator), so the global occurrence counts are known everywhere
-            batches = []
-            for r in range(world):
-                g = np.random.default_rng(7 + r)
-                lengths = g.integers(0, 5, size=T * B).astype(np.int64)
-                ids = g.integers(1, 40, size=int(lengths.sum())).astype(np.int64)
-                batches.append((lengths, ids))
-            lengths, ids = batches[rank]
-            feat = np.repeat(np.arange(T * B) // B, lengths)
-            count = {}
-            for ln, idv in batches:
-                f_ = np.repeat(np.arange(T * B) // B, ln)
-                for f, k in zip(f_.tolist(), idv.tolist()):
-                    count[(f, k)] = count.get((f, k), 0) + 1
-            x, ln = torch.from_numpy(ids), torch.from_numpy(lengths)
-            init = torch.from_numpy((ids % 100000).astype(np.float32))[:, None].expand(-1, D)
-            moved = torch.tensor([count[(f, k)] for f, k in zip(feat.tolist(), ids.tolist())], dtype=torch.float32)[:, None]
-            # step 1: every row is at its initial value (stored or not)
+def _run_config(rank, world, dedup, threshold, cached, pooling):
+    from tests.cpu_ext_shim import patched_module
+    from tests.test_admission_cpu import _module
+    from dynamicemb import DynamicEmbPoolingMode as P
+    from dynamicemb.shard import RowWiseShardedDynamicEmbeddingA2A
+    tag = f"dedup={dedup} threshold={threshold} cached={cached} pooling={pooling}: "
+    T, B, D = 2, 4, 8
+    with patched_module():
+        local = _module({"fused_prefetch": False}, threshold, T=T, dim=D, caching=cached, local_hbm=1024 * D * 4 if cached else 0)
+        assert (local.cache is not None) == cached
+        local.train()
+        sharded = RowWiseShardedDynamicEmbeddingA2A(local, dist.group.WORLD, dist_type="roundrobin", use_index_dedup=dedup,
+                                                    pooling_mode={"none": P.NONE, "sum": P.SUM, "mean": P.MEAN}[pooling])
+        # every rank can compute every rank's batch (same generator), so the global per-key gradient weights are known everywhere
+        batches = []
+        for r in range(world):
+            g = np.random.default_rng(7 + r)
+            lengths = g.integers(0, 5, size=T * B).astype(np.int64)
+            ids = g.integers(1, 40, size=int(lengths.sum())).astype(np.int64)
+            batches.append((lengths, ids))
+
+        def per_id(lengths):        # (feature, bag, pooling weight) of every id: the weight is also its gradient under d(out) = ones
+            bag = np.repeat(np.arange(T * B), lengths)
+            w = np.ones(bag.size) if pooling != "mean" else 1.0 / np.repeat(lengths, lengths)
+            return bag // B, bag, w
+
+        moved = {}
+        for ln_, idv in batches:
+            f_, _, w_ = per_id(ln_)
+            for f, k, w in zip(f_.tolist(), idv.tolist(), w_.tolist()):
+                moved[(f, k)] = moved.get((f, k), 0.0) + w
+        lengths, ids = batches[rank]
+        feat, bag, w = per_id(lengths)
+        x, ln = torch.from_numpy(ids), torch.from_numpy(lengths)
+
+        def expected(trained_steps):
+            val = np.array([(k % 100000) - LR * trained_steps * moved[(f, k)] for f, k in zip(feat.tolist(), ids.tolist())])
+            if pooling == "none":
+                return torch.from_numpy(np.repeat(val[:, None], D, axis=1)).float()
+            out = np.zeros((B, T * D))
+            for v, g_, wi in zip(val.tolist(), bag.tolist(), w.tolist()):
+                f, b = g_ // B, g_ % B
+                out[b, f * D:(f + 1) * D] += v * wi
+            return torch.from_numpy(out).float()
+
+        # with a threshold of 2 the first step only counts the keys: nothing is stored or trained before step 2
+        trained_before = [0, 1, 2] if threshold is None else [0, 0, 1]
+        for step, t_ in enumerate(trained_before, 1):
             out = sharded(x, ln)
-            assert torch.equal(out, init), tag + "step 1 output"
-            out.backward(torch.ones_like(out))
-            # step 2, same batch
-            out = sharded(x, ln)
-            if threshold is None:
-                want = init - LR * moved                          # step 1 trained every key with the gradients of all ranks
-            else:
-                want = init                                       # threshold 2: step 1 only counted; nothing was stored or trained
-            assert torch.allclose(out, want), tag + "step 2 output"
-            out.backward(torch.ones_like(out))
-            # step 3: with admission the keys were stored at step 2 (untrained copy of the initializer) and trained once
-            out = sharded(x, ln)
-            want = init - LR * moved * (2 if threshold is None else 1)
-            assert torch.allclose(out, want), tag + "step 3 output"
-            out.backward(torch.zeros_like(out))
-            # ownership: roundrobin => this rank's table holds exactly the keys with key % world == rank
-            for t in range(T):
-                keys, _ = local.export_keys_values(t)
-                allk = {k for (f, k) in count if f == t}
-                assert set(keys.tolist()) == {k for k in allk if k % world == rank}, tag + f"table {t} ownership"
+            assert torch.allclose(out, expected(t_), rtol=1e-5, atol=1e-4), tag + f"step {step} output"
+            out.backward(torch.ones_like(out) if step < 3 else torch.zeros_like(out))
+        # ownership: roundrobin => this rank's table holds exactly the keys with key % world == rank
+        for t in range(T):
+            keys, _ = local.export_keys_values(t)
+            allk = {k for (f, k) in moved if f == t}
+            assert set(keys.tolist()) == {k for k in allk if k % world == rank}, tag + f"table {t} ownership"
 
 
 def test_sharded_module_matches_closed_form_gloo():
@@ -122,6 +128,9 @@ class _Collection:
         self._cfgs = cfgs
 
     def embedding_configs(self):
+        return self._cfgs
+
+    def embedding_bag_configs(self):
         return self._cfgs
 
 
@@ -168,6 +177,20 @@ def _worker_planner(rank, world, port, q):
             occ = torch.tensor([1.0, 4.0, 2.0, 4.0])[:, None]
             assert torch.allclose(out, init - LR * occ), "step 3"
             out.backward(torch.zeros_like(out))
+            # the bag-collection sharder on a cached table: a pooling all_to_all wrapper around a sequence-mode cached shard
+            from dynamicemb import DynamicEmbPoolingMode
+            from dynamicemb.shard import DynamicEmbeddingBagCollectionSharder
+            opt2 = DynamicEmbTableOptions(score_strategy=DynamicEmbScoreStrategy.STEP, dist_type="roundrobin", caching=True, local_hbm_for_values=1024 * D * 4,
+                                          initializer_args=DynamicEmbInitializerArgs(mode=DynamicEmbInitializerMode.DEBUG))
+            cons2 = {"item": DynamicEmbParameterConstraints(use_dynamicemb=True, dynamicemb_options=opt2)}
+            plan2 = DynamicEmbeddingShardingPlanner(eb_configs=cfgs, constraints=cons2, world_size=world).plan()
+            bag = DynamicEmbeddingBagCollectionSharder(fused_params={"optimizer": EmbOptimType.SGD, "learning_rate": LR, "fused_prefetch": False}) \
+                .shard(_Collection(cfgs), plan2, env=_Env(dist.group.WORLD), device=torch.device("cpu"))
+            assert isinstance(bag, RowWiseShardedDynamicEmbeddingA2A) and bag.pooling_mode == DynamicEmbPoolingMode.SUM and bag.local.cache is not None
+            bag.local.train()
+            out = bag(ids, torch.tensor([3, 1], dtype=torch.int64))                      # two bags: [3+rank, 10, 11] and [10]
+            assert out.shape == (2, D) and out[:, 0].tolist() == [float(3 + rank + 10 + 11), 10.0]
+            out.backward(torch.ones_like(out))
         q.put((rank, "ok"))
     except Exception as e:      # noqa: BLE001
         import traceback
