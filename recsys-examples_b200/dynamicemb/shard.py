@@ -347,9 +347,10 @@ class _PoolRows(torch.autograd.Function):
         ctx.save_for_backward(offsets)
         ctx.shape, ctx.batch_size, ctx.num_features, ctx.combiner = (n, D), batch_size, num_features, combiner
         ident = torch.arange(n, dtype=torch.int64, device=rows.device)
-        return ext.gather_forward(rows.contiguous(), D, ident, None, n, offsets=offsets, batch_size=batch_size, num_features=num_features,
-                                  combiner=combiner, out_dtype=rows.dtype,
-                                  out=torch.empty(batch_size, num_features * D, dtype=rows.dtype, device=rows.device))
+        vals = rows.to(torch.float32).contiguous()                 # the gather kernel reads fp32 value rows (the shard may emit bf16 / fp16)
+        ctx.row_dtype = rows.dtype
+        return ext.gather_forward(vals, D, ident, None, n, offsets=offsets, batch_size=batch_size, num_features=num_features, combiner=combiner,
+                                  out_dtype=rows.dtype, out=torch.empty(batch_size, num_features * D, dtype=rows.dtype, device=rows.device))
 
     @staticmethod
     def backward(ctx, grad):
@@ -358,7 +359,7 @@ class _PoolRows(torch.autograd.Function):
         ident = torch.arange(n, dtype=torch.int64, device=grad.device)
         g = ext.reduce_grads(ident, grad.contiguous().to(torch.float32), n, ctx.batch_size, D, offsets=offsets, combiner=ctx.combiner,
                              total_D=ctx.num_features * D)
-        return g.to(grad.dtype), None, None, None, None
+        return g.to(ctx.row_dtype), None, None, None, None
 
 
 class RowWiseShardedDynamicEmbeddingA2A(_ShardCheckpointMixin, nn.Module):
